@@ -1,0 +1,174 @@
+"""Pin the oracle (oracle/derfinder_oracle.py, oracle/rrng.py) to the reference's own goldens.
+
+Mirrors the reference's testthat files: tests/testthat/test_Fstats.R, test_findRegions.R,
+test_data.R (filterData known answers).  CPU only.
+"""
+import numpy as np
+import pytest
+
+from oracle import derfinder_oracle as O
+from oracle.rrng import RRandom, permutation_indices
+
+
+def test_models_rebuilt_from_coverage(golden):
+    # tests/testthat/test_Fstats.R:4-40 -- sampleDepth(probs=0.5) + makeModels
+    sd = O.sample_depth(O.collapse_full_coverage(golden.cov_rle), 0.5)
+    mod = np.column_stack([np.ones(31), (golden.pop == "YRI") * 1.0, sd, (golden.gender == "male") * 1.0])
+    assert np.array_equal(mod, golden.mod)
+    assert np.array_equal(mod[:, [0, 2, 3]], golden.mod0)
+
+
+def test_preprocess_matches_reference(golden):
+    # tests/testthat/test_findRegions.R:21-45
+    prep = O.preprocess_coverage(golden.cov, golden.position, groupInfo=golden.pop, scalefac=32, chunksize=1e3)
+    assert prep["mclapplyIndex"] == [1000, 434]
+    assert np.array_equal(prep["coverageProcessed"], np.log2(golden.cov + 32.0))
+    assert np.array_equal(prep["meanCoverage"], golden["chr21_prep_meanCoverage"])
+    assert abs(prep["meanCoverage"].sum() - 357.838709677) < 1e-8  # tests/testthat/test_data.R:38
+    for k in ("CEU", "YRI"):
+        assert np.array_equal(prep["groupMeans"][k], golden[f"chr21_prep_groupMeans_{k}"])
+
+
+def test_chunk_lengths():
+    # R/preprocessCoverage.R:182-188 incl. the exact-multiple fix
+    assert O.chunk_lengths(1434, 1e3) == [1000, 434]
+    assert O.chunk_lengths(2000, 1000) == [1000, 1000]
+    assert O.chunk_lengths(999, 1000) == [999]
+    assert O.chunk_lengths(1000, 1000) == [1000]
+    assert O.chunk_lengths(10, None, mc_cores=3) == [4, 4, 2]
+
+
+def test_fstats_golden(golden):
+    # tests/testthat/test_Fstats.R:52-68 (expect_equivalent tolerance 1.5e-8); north_star: 1e-6 rel
+    prep = O.preprocess_coverage(golden.cov, golden.position, scalefac=32, chunksize=1e3)
+    F = O.calculate_stats(prep, golden.mod, golden.mod0)
+    assert np.max(np.abs(F - golden.fstats) / np.abs(golden.fstats)) < 1e-7
+    assert np.max(np.abs(F - golden.fstats_matrix) / np.abs(golden.fstats)) < 1e-7
+
+
+def _tie_band_check(p, pg, areas, nullareas, band=1e-9):
+    """H4 / SURVEY A.7: counts may differ from the R run only by nulls within `band` (relative) of
+    the observed area."""
+    M = len(nullareas)
+    for a, x, y in zip(areas, p, pg):
+        if x == y:
+            continue
+        near = np.sum(np.abs(nullareas - a) <= band * a)
+        assert near > 0, "p-value differs without a near-tie"
+        assert abs(round(x * (M + 1)) - round(y * (M + 1))) <= near
+
+
+def test_calculate_pvalues_golden(golden):
+    # tests/testthat/test_Fstats.R:80-87: nPermute=10, seeds=1:10, cutoff=1, RNGversion("3.5.0")
+    prep = O.preprocess_coverage(golden.cov, golden.position, groupInfo=golden.pop, scalefac=32, chunksize=1e3)
+    perm = permutation_indices(range(1, 11), 31, "Rounding")
+    res = O.calculate_pvalues(prep, golden.mod, golden.mod0, golden.fstats, perm, cutoff=1)
+    r = res["regions"]
+    G = lambda k: golden["genomeRegions_" + k]
+    assert len(r["start"]) == 33
+    for k in ("start", "indexStart", "indexEnd", "cluster", "clusterL", "area", "value", "meanCoverage",
+              "meanCEU", "meanYRI"):
+        assert np.array_equal(r[k], G(k)), k
+    assert np.array_equal(r["end"] - r["start"] + 1, G("width"))
+    assert np.array_equal(r["log2FoldChangeYRIvsCEU"], G("log2FoldChangeYRIvsCEU"), equal_nan=True)
+    assert list(r["name"]) == list(G("names"))
+    assert len(res["nullStats"]) == 540
+    assert np.array_equal(res["nullWidths"], G("nullWidths"))
+    assert np.array_equal(res["nullPermutation"], G("nullPermutation"))
+    assert np.max(np.abs(res["nullStats"] - G("nullStats")) / G("nullStats")) < 1e-10
+    assert np.sum(r["pvalues"] == G("pvalues")) >= 31
+    _tie_band_check(r["pvalues"], G("pvalues"), r["area"], res["nullAreas"])
+    assert np.array_equal(r["significant"], G("significant"))
+
+
+def test_bundled_chr21_run(golden):
+    # inst/extdata/chr21: analyzeChr(..., seeds=20140330, nPermute=1, cutoffFstat=1 manual, method Matrix)
+    prep = O.preprocess_coverage(golden.cov, golden.position, groupInfo=golden.pop)
+    perm = permutation_indices([20140330], 31, "Rounding")
+    res = O.calculate_pvalues(prep, golden.mod, golden.mod0, golden.fstats_matrix, perm, cutoff=1)
+    r = res["regions"]
+    for k in ("start", "indexStart", "indexEnd", "cluster", "clusterL", "area", "value", "pvalues",
+              "meanCoverage"):
+        assert np.array_equal(r[k], golden["chr21_regions_" + k]), k
+    assert np.array_equal(res["nullWidths"], golden["chr21_regions_nullWidths"])
+    assert np.max(np.abs(res["nullStats"] - golden["chr21_regions_nullStats"])) < 1e-9
+
+
+def test_literal_known_answers(golden):
+    # tests/testthat/test_Fstats.R:72-74, 89-90
+    assert np.allclose(O.calc_pval([1, 2], [1, 2, 3, 4]), [0.8, 0.6], rtol=0, atol=0)
+    assert np.array_equal(O.calculate_fwer(10, [1, 2, 3, 4], [1, 1, 3, 3], 3, [1, 2]), [1.0, 0.75])
+    assert O.quantile_type7(np.repeat([1.0, 2.0], 10), 0.5) == 1.5
+    assert abs(O.calc_fstat_cutoff("theoretical", 0.05, mod=golden.mod, mod0=golden.mod0) - 4.210008468) < 1e-8
+    assert O.calc_fstat_cutoff("manual", 1) == 1
+    # tests/testthat/test_findRegions.R:5-18
+    pos = (np.array([1, 0, 1, 0, 1], bool), np.array([1000, 1000, 1000, 200, 1000]))
+    ids, lens = O.cluster_maker_rle(pos)
+    assert list(ids) == [1, 2] and list(lens) == [1000, 2000]
+    st, en = O.cluster_maker_rle(pos, ranges=True)
+    assert list(st) == [1, 1001] and list(en) == [1000, 3000]
+    ids, lens = O.cluster_maker_rle(pos, maxGap=999)
+    assert list(ids) == [1, 2] and list(lens) == [1000, 2000]
+    ids, lens = O.cluster_maker_rle(pos, maxGap=1000)
+    assert list(ids) == [1] and list(lens) == [3000]
+    x = np.repeat([-1.0, 0, 1, 2], 1000)
+    s = O.get_segments(x, 0.5)
+    assert (list(s["upIndex"][0]), list(s["upIndex"][1])) == ([2001], [4000])
+    assert (list(s["dnIndex"][0]), list(s["dnIndex"][1])) == ([1], [1000])
+    s = O.get_segments(x + 3, [1, 1])
+    assert (list(s["upIndex"][0]), list(s["upIndex"][1])) == ([1], [4000]) and len(s["dnIndex"][0]) == 0
+
+
+def test_find_regions_known_answers(golden):
+    # tests/testthat/test_findRegions.R:49-68
+    F = golden.fstats
+    small_pos = (np.array([False, True, False, True]), np.array([47407536, 32, 1256, 36]))
+    rb = O.find_regions(small_pos, F[:68], 1, basic=True)
+    assert list(rb["width"]) == [6, 15, 36]
+    m = F[:68] > 1
+    sums = [F[:68][m][:6].sum(), F[:68][m][6:21].sum(), F[:68][m][21:].sum()]
+    assert np.allclose(rb["area"], sums, rtol=1e-14)
+    assert np.allclose(rb["stat"], rb["area"] / rb["width"], rtol=1e-15)
+    full = O.find_regions(small_pos, F[:68], 1)
+    assert list(full["end"] - full["start"] + 1) == [6, 15, 36]
+    one = O.find_regions(golden.position, F, 0, maxRegionGap=1e5, maxClusterGap=1e6)
+    assert list(one["start"]) == [47407537] and list(one["end"]) == [47418068] and list(one["name"]) == ["up"]
+    assert O.find_regions((np.array([False]), np.array([1])), F, 1) is None
+    # default cutoff quantile(0.99): 15 candidate bases -> regions are subsets of the cutoff-1 ones
+    regs = O.find_regions(golden.position, F, O.quantile_type7(F, 0.99))
+    assert regs is not None and np.all(regs["value"] >= O.quantile_type7(F, 0.99))
+
+
+def test_filter_data_known_answers(golden):
+    # tests/testthat/test_data.R:174-191
+    f = O.filter_data(golden.raw_rle, cutoff=0.5, filter="mean")
+    assert f.coverage.shape == (273, 31)
+    f = O.filter_data(golden.raw_rle, cutoff=10)
+    assert list(f.position[0]) == [False] and list(f.position[1]) == [48129895]
+    f = O.filter_data(golden.raw_rle, cutoff=0, returnMean=True)
+    assert np.array_equal(f.coverage, golden.cov)
+    assert np.array_equal(f.position[0], golden.position[0]) and np.array_equal(f.position[1], golden.position[1])
+    assert f.coverage.shape[0] == int(np.sum(f.position[1][f.position[0]]))
+    f = O.filter_data(golden.raw_rle, cutoff=-1, returnCoverage=False)
+    assert list(f.position[0]) == [True] and list(f.position[1]) == [48129895]
+    with pytest.raises(ValueError):
+        O.filter_data(golden.raw_rle, filter="two")
+    # re-filter with a previous index (R/filterData.R:159-164, example :85-88)
+    f1 = O.filter_data(golden.raw_rle, cutoff=0)
+    cols2 = [O.rle_encode(f1.coverage[:, s]) for s in range(2)]
+    f2 = O.filter_data(cols2, cutoff=1, index=f1.position)
+    dense = O.rle_decode(*f2.position)
+    assert dense.sum() == f2.coverage.shape[0] and len(dense) == 48129895
+    keep = (f1.coverage[:, 0] > 1) | (f1.coverage[:, 1] > 1)
+    assert np.array_equal(f2.coverage, f1.coverage[keep][:, :2])
+
+
+def test_r_rng_streams():
+    # set.seed(1); runif(3) and sample(10) under both sample kinds (values of a stock R session)
+    r = RRandom(1)
+    u = [r.unif_rand() for _ in range(3)]
+    assert np.allclose(u, [0.2655086631421, 0.3721238996368, 0.5728533633519], atol=1e-12)
+    assert list(RRandom(1, "Rounding").sample(10) + 1) == [3, 4, 5, 7, 2, 8, 9, 6, 10, 1]
+    assert list(RRandom(1, "Rejection").sample(10) + 1) == [9, 4, 7, 1, 2, 5, 3, 10, 6, 8]
+    p = permutation_indices([1, 2, 3], 31, "Rejection")
+    assert p.shape == (3, 31) and all(sorted(row) == list(range(31)) for row in p)
