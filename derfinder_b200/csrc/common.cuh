@@ -1,0 +1,160 @@
+// derfinder_b200 -- shared internals of the CUDA library (context, error plumbing, device buffers,
+// kernel timing).  sm_100a only; there is no CPU path in this library.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/derfinder_b200.h"
+
+namespace dfb {
+
+void set_error(const char* fmt, ...);
+
+#define DFB_CUDA(expr)                                                                         \
+    do {                                                                                       \
+        cudaError_t _e = (expr);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            dfb::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+            return DFB_ECUDA;                                                                  \
+        }                                                                                      \
+    } while (0)
+
+#define DFB_TRY(expr)             \
+    do {                          \
+        int _rc = (expr);         \
+        if (_rc < 0) return _rc;  \
+    } while (0)
+
+#define DFB_REQUIRE(cond, ...)          \
+    do {                                \
+        if (!(cond)) {                  \
+            dfb::set_error(__VA_ARGS__); \
+            return DFB_EINVAL;          \
+        }                               \
+    } while (0)
+
+static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b; }
+
+}  // namespace dfb
+
+struct dfb_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    int64_t launches = 0;
+    bool timing = false;
+    struct Ev {
+        cudaEvent_t a, b;
+        int k;
+    };
+    std::vector<Ev> evs;
+    double kms[DFB_K_COUNT] = {0};
+    int64_t klaunch[DFB_K_COUNT] = {0};
+    // options
+    int opt_screen = 1;
+    double opt_null_cap_mb = 0;  // 0 = auto
+    int opt_perm_batch = 0;      // 0 = auto
+    double opt_scratch_gb = 24;  // upper bound for per-call scratch (mask + exceedance values)
+    // pinned staging for small D2H reads
+    void* pinned = nullptr;
+    size_t pinned_bytes = 0;
+};
+
+namespace dfb {
+
+// Brackets the launches of one kernel family with CUDA events (when timing is on) and counts
+// launches.  Usage: { KTimer t(ctx, DFB_K_FSTAT, nlaunches); kernel<<<...>>>(); }
+struct KTimer {
+    dfb_ctx* c;
+    int k;
+    cudaEvent_t a = nullptr, b = nullptr;
+    KTimer(dfb_ctx* ctx, int kernel, int nlaunch = 1) : c(ctx), k(kernel) {
+        c->launches += nlaunch;
+        c->klaunch[k] += nlaunch;
+        if (c->timing) {
+            cudaEventCreate(&a);
+            cudaEventCreate(&b);
+            cudaEventRecord(a, c->stream);
+        }
+    }
+    ~KTimer() {
+        if (c->timing) {
+            cudaEventRecord(b, c->stream);
+            c->evs.push_back({a, b, k});
+        }
+    }
+};
+
+// Stream-ordered device buffer (cudaMallocAsync pool: repeated calls reuse memory without
+// device-wide synchronisation).
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    cudaStream_t s = nullptr;
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) {
+            release();
+            p = o.p; n = o.n; s = o.s;
+            o.p = nullptr; o.n = 0;
+        }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void release() {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+        n = 0;
+    }
+    int alloc(dfb_ctx* ctx, size_t count) {
+        release();
+        s = ctx->stream;
+        n = count;
+        if (count == 0) return DFB_OK;
+        cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), s);
+        if (e != cudaSuccess) {
+            p = nullptr;
+            n = 0;
+            set_error("device allocation of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+            cudaGetLastError();
+            return DFB_ENOMEM;
+        }
+        return DFB_OK;
+    }
+    int zero() {
+        if (p && n) {
+            DFB_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s));
+        }
+        return DFB_OK;
+    }
+};
+
+int h2d(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);
+int d2h(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);  // synchronises the stream
+
+// device-wide exclusive scan of `n` uint32 counts into int64 offsets; total_dev[0] = sum.
+int exclusive_scan_u32(dfb_ctx* ctx, const uint32_t* in, int64_t* out, int64_t n, int64_t* total_dev,
+                       int kernel_family);
+
+static inline int grid_for(int64_t work_items, int threads, int sm_count, int max_waves = 32) {
+    int64_t blocks = ceil_div(work_items, threads);
+    int64_t cap = (int64_t)sm_count * max_waves;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return (int)blocks;
+}
+
+}  // namespace dfb

@@ -1,0 +1,813 @@
+// K1 -- coverage preprocessing: Rle expansion, library-size normalisation, per-base filter,
+// compaction to the dense sample-major matrix, means and the log2(x + scalefac) transform.
+//
+// Reference: filterData (R/filterData.R:89-241) and preprocessCoverage (R/preprocessCoverage.R:
+// 97-260).  In R every step materialises Rle objects per sample; here the chromosome is cut into
+// tiles of 2048 positions, a tile whose samples are all constant (one run each -- ~90% of a
+// genome) is decided with one predicate, and only tiles with kept bases are expanded.
+#include <math.h>
+
+#include <algorithm>
+
+#include "data.cuh"
+
+namespace dfb {
+
+constexpr int K1_THREADS = 256;
+constexpr int K1_PER = 8;                        // consecutive positions per thread
+constexpr int K1_TILE = K1_THREADS * K1_PER;     // 2048 positions per tile
+
+struct RleDev {
+    const void* values;      // concatenated run values of all samples (int32 or double)
+    const int64_t* cum;      // [total_runs + 1] global exclusive prefix of the run lengths
+    const int64_t* run_off;  // [n + 1] first run of each sample in the concatenation
+    int n;
+    int64_t len;  // positions per sample
+};
+
+struct FilterParams {
+    RleDev rle;
+    const double* mapped;  // per-sample divisor or nullptr
+    int filter;            // DFB_FILTER_*
+    double cutoff;
+    uint32_t* mask;        // [ceil(len/32)]
+    uint32_t* tile_count;  // [tiles]
+    const int64_t* tile_off;  // pass 1
+    int64_t ld;
+    void* out;             // [n][ld] int32 or double
+    int out_is_double;
+    double* mean;          // [N]
+    int64_t tiles;
+};
+
+// first run g in [lo, hi] (global run indices of one sample) whose end (cum[g+1]-cb) exceeds pos
+__device__ __forceinline__ int64_t find_run(const int64_t* __restrict__ cum, int64_t cb, int64_t lo, int64_t hi,
+                                            int64_t pos) {
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (cum[mid + 1] - cb > pos) hi = mid;
+        else lo = mid + 1;
+    }
+    return lo;
+}
+
+template <typename V, int PASS>
+__global__ void __launch_bounds__(K1_THREADS) filter_tile_kernel(const FilterParams P) {
+    extern __shared__ int64_t smem_k1[];
+    int64_t* r0 = smem_k1;          // [n] run containing the tile start
+    int64_t* r1 = smem_k1 + P.rle.n;  // [n] run containing the tile end
+    __shared__ int wsum[K1_THREADS / 32];
+    __shared__ int uniform_keep;
+    const int n = P.rle.n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const V* __restrict__ values = reinterpret_cast<const V*>(P.rle.values);
+    const int64_t* __restrict__ cum = P.rle.cum;
+
+    for (int64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+        const int64_t t0 = tile * K1_TILE;
+        const int64_t t1 = min(t0 + (int64_t)K1_TILE, P.rle.len);  // exclusive
+        uint32_t my_count = PASS == 1 ? P.tile_count[tile] : 0u;
+        if (PASS == 1 && my_count == 0) continue;  // block-uniform
+        __syncthreads();                           // r0/r1/wsum reuse across tiles
+        int nonuni = 0, anypass = 0;
+        for (int s = tid; s < n; s += K1_THREADS) {
+            const int64_t lo = P.rle.run_off[s], hi = P.rle.run_off[s + 1] - 1, cb = cum[lo];
+            const int64_t a = find_run(cum, cb, lo, hi, t0);
+            const int64_t b = find_run(cum, cb, a, hi, t1 - 1);
+            r0[s] = a;
+            r1[s] = b;
+            if (a != b) nonuni = 1;
+            else if (PASS == 0 && P.filter == DFB_FILTER_ONE) {
+                double v = (double)values[a];
+                if (P.mapped) v = v / P.mapped[s];
+                if (v > P.cutoff) anypass = 1;
+            }
+        }
+        const int tile_nonuni = __syncthreads_or(nonuni);
+        if (PASS == 0) {
+            // constant tile: one decision for all 2048 positions
+            if (!tile_nonuni) {
+                int keep;
+                if (P.filter == DFB_FILTER_NONE) keep = 1;
+                else if (P.filter == DFB_FILTER_ONE) keep = __syncthreads_or(anypass);
+                else {
+                    if (tid == 0) {
+                        double sum = 0.0;
+                        for (int s = 0; s < n; ++s) {
+                            double v = (double)values[r0[s]];
+                            if (P.mapped) v = v / P.mapped[s];
+                            sum = s == 0 ? v : __dadd_rn(sum, v);
+                        }
+                        uniform_keep = (__ddiv_rn(sum, (double)n) > P.cutoff) ? 1 : 0;
+                    }
+                    __syncthreads();
+                    keep = uniform_keep;
+                }
+                const int64_t w0 = t0 >> 5, w1 = (t1 + 31) >> 5;
+                for (int64_t w = w0 + tid; w < w1; w += K1_THREADS) {
+                    uint32_t bits = keep ? 0xffffffffu : 0u;
+                    const int64_t rem = P.rle.len - w * 32;
+                    if (rem < 32) bits &= (1u << rem) - 1u;
+                    P.mask[w] = bits;
+                }
+                if (tid == 0) P.tile_count[tile] = keep ? (uint32_t)(t1 - t0) : 0u;
+                continue;
+            }
+        }
+        // ---- general tile: every thread walks its 8 positions through all samples, in order
+        const int64_t p0 = t0 + (int64_t)tid * K1_PER;
+        uint32_t bits = 0;  // kept flags of my 8 positions
+        if (PASS == 1) {
+            if (p0 < t1) bits = (P.mask[p0 >> 5] >> (p0 & 31)) & 0xffu;
+        }
+        double sum[K1_PER];
+#pragma unroll
+        for (int q = 0; q < K1_PER; ++q) sum[q] = 0.0;
+        int64_t dst0 = 0;
+        if (PASS == 1) {
+            // exclusive prefix of kept counts over the threads of the block
+            const int c = __popc(bits);
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            if (lane == 31) wsum[warp] = inc;
+            __syncthreads();
+            int wp = 0;
+            for (int w = 0; w < warp; ++w) wp += wsum[w];
+            dst0 = P.tile_off[tile] + wp + inc - c;
+        }
+        if (p0 < t1) {
+            for (int s = 0; s < n; ++s) {
+                const int64_t lo = P.rle.run_off[s], cb = cum[lo];
+                int64_t g = r0[s];
+                if (r1[s] != g) g = find_run(cum, cb, g, r1[s], p0);
+                const double d = P.mapped ? P.mapped[s] : 1.0;
+                int64_t gend = cum[g + 1] - cb;
+                V raw = values[g];
+                int k = 0;
+#pragma unroll
+                for (int q = 0; q < K1_PER; ++q) {
+                    const int64_t pos = p0 + q;
+                    if (pos < t1) {
+                        while (gend <= pos) {
+                            ++g;
+                            gend = cum[g + 1] - cb;
+                            raw = values[g];
+                        }
+                        double v = (double)raw;
+                        if (P.mapped) v = __ddiv_rn(v, d);
+                        if (PASS == 0) {
+                            if (P.filter == DFB_FILTER_ONE) {
+                                if (v > P.cutoff) bits |= 1u << q;
+                            } else {
+                                sum[q] = s == 0 ? v : __dadd_rn(sum[q], v);
+                            }
+                        } else {
+                            sum[q] = s == 0 ? v : __dadd_rn(sum[q], v);
+                            if ((bits >> q) & 1u) {
+                                const int64_t dst = dst0 + k;
+                                if (P.out_is_double) reinterpret_cast<double*>(P.out)[(size_t)s * P.ld + dst] = v;
+                                else reinterpret_cast<int32_t*>(P.out)[(size_t)s * P.ld + dst] = (int32_t)raw;
+                                ++k;
+                            }
+                        }
+                    }
+                }
+            }
+        }
+        if (PASS == 0) {
+            if (p0 < t1) {
+                if (P.filter == DFB_FILTER_NONE) {
+                    const int64_t cnt = min((int64_t)K1_PER, t1 - p0);
+                    bits = (1u << cnt) - 1u;
+                } else if (P.filter == DFB_FILTER_MEAN) {
+#pragma unroll
+                    for (int q = 0; q < K1_PER; ++q)
+                        if (p0 + q < t1 && __ddiv_rn(sum[q], (double)n) > P.cutoff) bits |= 1u << q;
+                }
+            }
+            // four threads share one 32-bit mask word
+            uint32_t word = bits << ((tid & 3) * 8);
+            word |= __shfl_xor_sync(0xffffffffu, word, 1);
+            word |= __shfl_xor_sync(0xffffffffu, word, 2);
+            const int64_t w = (t0 >> 5) + (tid >> 2);
+            if ((tid & 3) == 0 && w * 32 < t1) P.mask[w] = word;
+            int c = __popc(bits);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0) wsum[warp] = c;
+            __syncthreads();
+            if (tid == 0) {
+                int t = 0;
+                for (int w2 = 0; w2 < K1_THREADS / 32; ++w2) t += wsum[w2];
+                P.tile_count[tile] = (uint32_t)t;
+            }
+        } else if (P.mean && p0 < t1) {
+            int k = 0;
+#pragma unroll
+            for (int q = 0; q < K1_PER; ++q)
+                if ((bits >> q) & 1u) {
+                    P.mean[dst0 + k] = __ddiv_rn(sum[q], (double)n);
+                    ++k;
+                }
+        }
+    }
+}
+
+// mask words -> run boundaries: a position starts a run when its bit differs from the previous one
+__global__ void __launch_bounds__(256) mask_run_count_kernel(const uint32_t* __restrict__ mask, int64_t W, int64_t len,
+                                                             uint32_t* __restrict__ counts) {
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < W; w += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t m = mask[w];
+        const uint32_t prev = w > 0 ? (mask[w - 1] >> 31) : (~m & 1u);  // position 0 always starts a run
+        uint32_t d = m ^ ((m << 1) | prev);
+        const int64_t rem = len - w * 32;
+        if (rem < 32) d &= (1u << rem) - 1u;
+        counts[w] = __popc(d);
+    }
+}
+
+__global__ void __launch_bounds__(256) mask_run_emit_kernel(const uint32_t* __restrict__ mask, int64_t W, int64_t len,
+                                                            const int64_t* __restrict__ offsets,
+                                                            int32_t* __restrict__ run_start) {
+    for (int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; w < W; w += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t m = mask[w];
+        const uint32_t prev = w > 0 ? (mask[w - 1] >> 31) : (~m & 1u);
+        uint32_t d = m ^ ((m << 1) | prev);
+        const int64_t rem = len - w * 32;
+        if (rem < 32) d &= (1u << rem) - 1u;
+        int64_t o = offsets[w];
+        while (d) {
+            const int b = __ffs(d) - 1;
+            d &= d - 1;
+            run_start[o++] = (int32_t)(w * 32 + b);
+        }
+    }
+}
+
+// upload n Rle columns: concatenated values + global prefix of the lengths (device scan)
+struct RleUpload {
+    DevBuf<unsigned char> values;
+    DevBuf<uint32_t> lengths;
+    DevBuf<int64_t> cum, run_off;
+    int64_t total_runs = 0;
+};
+
+static int upload_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, const int32_t* const* lengths,
+                      const int64_t* nruns, int64_t len, RleUpload* up) {
+    DFB_REQUIRE(n > 0 && values && lengths && nruns, "Rle input: NULL argument");
+    DFB_REQUIRE(dtype == DFB_I32 || dtype == DFB_F64, "Rle input: unknown dtype %d", dtype);
+    const size_t es = dtype == DFB_I32 ? 4 : 8;
+    std::vector<int64_t> off((size_t)n + 1, 0);
+    for (int s = 0; s < n; ++s) {
+        DFB_REQUIRE(nruns[s] > 0 || len == 0, "Rle column %d is empty", s + 1);
+        off[(size_t)s + 1] = off[(size_t)s] + nruns[s];
+    }
+    up->total_runs = off[(size_t)n];
+    // check lengths sum (cheap, catches ragged DataFrames early like R would)
+    for (int s = 0; s < n; ++s) {
+        int64_t t = 0;
+        for (int64_t r = 0; r < nruns[s]; ++r) {
+            DFB_REQUIRE(lengths[s][r] > 0, "Rle column %d has a non-positive run length", s + 1);
+            t += lengths[s][r];
+        }
+        DFB_REQUIRE(t == len, "Rle column %d has length %lld, expected %lld", s + 1, (long long)t, (long long)len);
+    }
+    DFB_TRY(up->values.alloc(ctx, (size_t)std::max<int64_t>(up->total_runs, 1) * es));
+    DFB_TRY(up->lengths.alloc(ctx, (size_t)std::max<int64_t>(up->total_runs, 1)));
+    DFB_TRY(up->cum.alloc(ctx, (size_t)up->total_runs + 1));
+    DFB_TRY(up->run_off.alloc(ctx, (size_t)n + 1));
+    for (int s = 0; s < n; ++s) {
+        DFB_TRY(h2d(ctx, up->values.p + (size_t)off[(size_t)s] * es, values[s], (size_t)nruns[s] * es));
+        DFB_TRY(h2d(ctx, up->lengths.p + off[(size_t)s], lengths[s], (size_t)nruns[s] * sizeof(int32_t)));
+    }
+    DFB_TRY(h2d(ctx, up->run_off.p, off.data(), off.size() * sizeof(int64_t)));
+    DFB_CUDA(cudaStreamSynchronize(ctx->stream));  // `off` is a local
+    DFB_TRY(exclusive_scan_u32(ctx, up->lengths.p, up->cum.p, up->total_runs, up->cum.p + up->total_runs, DFB_K_PREP));
+    return DFB_OK;
+}
+
+static int alloc_matrix(dfb_cov* c) {
+    c->ld = round_up(std::max<int64_t>(c->N, 1), 64);
+    if (c->dtype == DFB_I32) DFB_TRY(c->xi.alloc(c->ctx, (size_t)c->n * c->ld));
+    else DFB_TRY(c->xd.alloc(c->ctx, (size_t)c->n * c->ld));
+    return DFB_OK;
+}
+
+// filter (or plain expansion when filter == NONE) of Rle columns into a new dfb_cov
+static int filter_rle_impl(dfb_ctx* ctx, int n, int dtype, const void* const* values, const int32_t* const* lengths,
+                           const int64_t* nruns, int64_t len, const double* mapped, int filter, double cutoff,
+                           bool want_mean, std::vector<int32_t>* new_pos_len, int* new_pos_first, dfb_cov** out) {
+    RleUpload up;
+    DFB_TRY(upload_rle(ctx, n, dtype, values, lengths, nruns, len, &up));
+    DevBuf<double> mapped_d;
+    if (mapped) {
+        for (int s = 0; s < n; ++s) DFB_REQUIRE(mapped[s] != 0, "totalMapped/targetSize is zero for sample %d", s + 1);
+        DFB_TRY(mapped_d.alloc(ctx, n));
+        DFB_TRY(h2d(ctx, mapped_d.p, mapped, (size_t)n * sizeof(double)));
+    }
+    const int64_t tiles = ceil_div(len, K1_TILE);
+    const int64_t W = ceil_div(len, 32);
+    DevBuf<uint32_t> mask, tile_count;
+    DevBuf<int64_t> tile_off, total_dev;
+    DFB_TRY(mask.alloc(ctx, (size_t)std::max<int64_t>(W, 1)));
+    DFB_TRY(tile_count.alloc(ctx, (size_t)std::max<int64_t>(tiles, 1)));
+    DFB_TRY(tile_off.alloc(ctx, (size_t)std::max<int64_t>(tiles, 1)));
+    DFB_TRY(total_dev.alloc(ctx, 1));
+    FilterParams P;
+    memset(&P, 0, sizeof P);
+    P.rle.values = up.values.p;
+    P.rle.cum = up.cum.p;
+    P.rle.run_off = up.run_off.p;
+    P.rle.n = n;
+    P.rle.len = len;
+    P.mapped = mapped ? mapped_d.p : nullptr;
+    P.filter = filter;
+    P.cutoff = cutoff;
+    P.mask = mask.p;
+    P.tile_count = tile_count.p;
+    P.tiles = tiles;
+    const size_t smem = (size_t)2 * n * sizeof(int64_t);
+    const int grid = (int)std::min<int64_t>(std::max<int64_t>(tiles, 1), (int64_t)ctx->sm_count * 16);
+    if (tiles > 0) {
+        KTimer t(ctx, DFB_K_PREP);
+        if (dtype == DFB_I32) filter_tile_kernel<int32_t, 0><<<grid, K1_THREADS, smem, ctx->stream>>>(P);
+        else filter_tile_kernel<double, 0><<<grid, K1_THREADS, smem, ctx->stream>>>(P);
+    }
+    DFB_CUDA(cudaGetLastError());
+    DFB_TRY(exclusive_scan_u32(ctx, tile_count.p, tile_off.p, tiles, total_dev.p, DFB_K_PREP));
+    int64_t N = 0;
+    DFB_TRY(d2h(ctx, &N, total_dev.p, sizeof N));
+
+    // position runs of the new mask
+    {
+        DevBuf<uint32_t> rc;
+        DevBuf<int64_t> ro, rt;
+        DFB_TRY(rc.alloc(ctx, (size_t)std::max<int64_t>(W, 1)));
+        DFB_TRY(ro.alloc(ctx, (size_t)std::max<int64_t>(W, 1)));
+        DFB_TRY(rt.alloc(ctx, 1));
+        if (W > 0) {
+            KTimer t(ctx, DFB_K_PREP);
+            mask_run_count_kernel<<<grid_for(W, 256, ctx->sm_count), 256, 0, ctx->stream>>>(mask.p, W, len, rc.p);
+        }
+        DFB_TRY(exclusive_scan_u32(ctx, rc.p, ro.p, W, rt.p, DFB_K_PREP));
+        int64_t nr = 0;
+        DFB_TRY(d2h(ctx, &nr, rt.p, sizeof nr));
+        std::vector<int32_t> starts((size_t)nr);
+        if (nr > 0) {
+            DevBuf<int32_t> rs;
+            DFB_TRY(rs.alloc(ctx, (size_t)nr));
+            {
+                KTimer t(ctx, DFB_K_PREP);
+                mask_run_emit_kernel<<<grid_for(W, 256, ctx->sm_count), 256, 0, ctx->stream>>>(mask.p, W, len, ro.p,
+                                                                                               rs.p);
+            }
+            DFB_TRY(d2h(ctx, starts.data(), rs.p, (size_t)nr * sizeof(int32_t)));
+        }
+        new_pos_len->clear();
+        for (int64_t r = 0; r < nr; ++r) {
+            const int64_t e = r + 1 < nr ? starts[(size_t)r + 1] : len;
+            new_pos_len->push_back((int32_t)(e - starts[(size_t)r]));
+        }
+        uint32_t w0 = 0;
+        if (W > 0) DFB_TRY(d2h(ctx, &w0, mask.p, sizeof w0));
+        *new_pos_first = (int)(w0 & 1u);
+    }
+
+    dfb_cov* c = new dfb_cov();
+    c->ctx = ctx;
+    c->n = n;
+    c->N = N;
+    c->dtype = (mapped || dtype == DFB_F64) ? DFB_F64 : DFB_I32;
+    int rc = alloc_matrix(c);
+    if (rc >= 0 && want_mean) rc = c->mean.alloc(ctx, (size_t)std::max<int64_t>(N, 1));
+    if (rc < 0) {
+        delete c;
+        return rc;
+    }
+    c->has_mean = want_mean;
+    if (N > 0) {
+        P.tile_off = tile_off.p;
+        P.ld = c->ld;
+        P.out = c->dtype == DFB_I32 ? (void*)c->xi.p : (void*)c->xd.p;
+        P.out_is_double = c->dtype == DFB_F64;
+        P.mean = want_mean ? c->mean.p : nullptr;
+        KTimer t(ctx, DFB_K_PREP);
+        if (dtype == DFB_I32) filter_tile_kernel<int32_t, 1><<<grid, K1_THREADS, smem, ctx->stream>>>(P);
+        else filter_tile_kernel<double, 1><<<grid, K1_THREADS, smem, ctx->stream>>>(P);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // `up` buffers die with this frame
+    if (e != cudaSuccess) {
+        set_error("filter kernels: %s", cudaGetErrorString(e));
+        delete c;
+        return DFB_ECUDA;
+    }
+    *out = c;
+    return DFB_OK;
+}
+
+// finalidx[index] <- newindex (R/filterData.R:159-161): scatter the new mask runs (over the kept
+// positions of the previous index) into the previous index' TRUE runs.  Run-level bookkeeping.
+static void compose_position(const int32_t* prev_len, int64_t prev_nruns, int prev_first,
+                             const std::vector<int32_t>& new_len, int new_first, std::vector<int32_t>* out_len,
+                             int* out_first) {
+    std::vector<std::pair<int, int64_t>> runs;  // (value, length)
+    auto push = [&](int v, int64_t l) {
+        if (l <= 0) return;
+        if (!runs.empty() && runs.back().first == v) runs.back().second += l;
+        else runs.push_back({v, l});
+    };
+    size_t ni = 0;
+    int64_t nrem = new_len.empty() ? 0 : new_len[0];
+    int nv = new_first;
+    int pv = prev_first ? 1 : 0;
+    for (int64_t r = 0; r < prev_nruns; ++r, pv ^= 1) {
+        int64_t l = prev_len[r];
+        if (!pv) {
+            push(0, l);
+            continue;
+        }
+        while (l > 0 && ni < new_len.size()) {
+            const int64_t take = std::min(l, nrem);
+            push(nv, take);
+            l -= take;
+            nrem -= take;
+            if (nrem == 0) {
+                ++ni;
+                nv ^= 1;
+                nrem = ni < new_len.size() ? new_len[ni] : 0;
+            }
+        }
+    }
+    out_len->clear();
+    *out_first = runs.empty() ? 0 : runs[0].first;
+    for (auto& r : runs) {
+        // split runs longer than INT32_MAX never occur (chromosome length is int32 in R)
+        out_len->push_back((int32_t)r.second);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// preprocess: means, group means, log2(x + scalefac)
+
+template <typename V>
+__global__ void __launch_bounds__(256) minmax_kernel(const V* __restrict__ x, int64_t ld, int64_t N, int n,
+                                                     long long* __restrict__ mn, long long* __restrict__ mx) {
+    long long lo = LLONG_MAX, hi = LLONG_MIN;
+    const int64_t total = (int64_t)n * N;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t s = g / N, i = g - s * N;
+        const long long v = (long long)x[(size_t)s * ld + i];
+        lo = v < lo ? v : lo;
+        hi = v > hi ? v : hi;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        lo = min(lo, __shfl_xor_sync(0xffffffffu, lo, o));
+        hi = max(hi, __shfl_xor_sync(0xffffffffu, hi, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(mn, lo);
+        atomicMax(mx, hi);
+    }
+}
+
+struct PrepParams {
+    const void* x;
+    int64_t ld, N;
+    int n;
+    double scalefac;
+    const double* lut;  // log2(k + scalefac) for k in [0, lut_n), host-built with libm
+    int64_t lut_n;
+    const int32_t* group;  // [n] or nullptr
+    const double* group_size;  // [G]
+    int G;
+    double* y;      // [n][ld]
+    double* mean;   // [N] or nullptr (already present)
+    double* gmean;  // [G][ld]
+};
+
+template <typename V>
+__global__ void __launch_bounds__(256) preprocess_kernel(const PrepParams P) {
+    extern __shared__ double gs_s[];  // [G][blockDim]
+    const V* __restrict__ x = reinterpret_cast<const V*>(P.x);
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.N; i += (int64_t)gridDim.x * blockDim.x) {
+        double sum = 0.0;
+        for (int g = 0; g < P.G; ++g) gs_s[g * blockDim.x + threadIdx.x] = 0.0;
+        for (int s = 0; s < P.n; ++s) {
+            const V raw = x[(size_t)s * P.ld + i];
+            const double v = (double)raw;
+            sum = s == 0 ? v : __dadd_rn(sum, v);
+            if (P.G > 0) {
+                double* a = &gs_s[P.group[s] * blockDim.x + threadIdx.x];
+                *a = __dadd_rn(*a, v);
+            }
+            double yv;
+            if (sizeof(V) == 4 && P.lut) yv = P.lut[(int64_t)raw];
+            else yv = log2(__dadd_rn(v, P.scalefac));
+            P.y[(size_t)s * P.ld + i] = yv;
+        }
+        if (P.mean) P.mean[i] = __ddiv_rn(sum, (double)P.n);
+        for (int g = 0; g < P.G; ++g)
+            P.gmean[(size_t)g * P.ld + i] = __ddiv_rn(gs_s[g * blockDim.x + threadIdx.x], P.group_size[g]);
+    }
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" {
+
+int dfb_filter_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, const int32_t* const* lengths,
+                   const int64_t* nruns, int64_t len, const double* mapped_per_xm, int filter, double cutoff,
+                   const int32_t* prev_len, int64_t prev_nruns, int prev_first, dfb_cov** out) {
+    DFB_REQUIRE(ctx && out, "dfb_filter_rle: NULL argument");
+    *out = nullptr;
+    DFB_REQUIRE(filter == DFB_FILTER_NONE || filter == DFB_FILTER_ONE || filter == DFB_FILTER_MEAN,
+                "filter %%in%% c('one', 'mean') is not TRUE");
+    DFB_REQUIRE(len >= 0 && len <= INT32_MAX, "coverage length %lld out of range", (long long)len);
+    if (prev_len) {
+        int64_t kept = 0;
+        int v = prev_first ? 1 : 0;
+        for (int64_t r = 0; r < prev_nruns; ++r, v ^= 1)
+            if (v) kept += prev_len[r];
+        DFB_REQUIRE(kept == len, "sum(index) = %lld does not match the coverage length %lld", (long long)kept,
+                    (long long)len);
+    }
+    std::vector<int32_t> npl;
+    int npf = 0;
+    dfb_cov* c = nullptr;
+    DFB_TRY(filter_rle_impl(ctx, n, dtype, values, lengths, nruns, len, mapped_per_xm, filter, cutoff, true, &npl, &npf,
+                            &c));
+    int rc;
+    if (prev_len) {
+        std::vector<int32_t> fl;
+        int ff = 0;
+        compose_position(prev_len, prev_nruns, prev_first, npl, npf, &fl, &ff);
+        rc = c->pos.build(ctx, fl.data(), (int64_t)fl.size(), ff);
+    } else {
+        rc = c->pos.build(ctx, npl.data(), (int64_t)npl.size(), npf);
+    }
+    if (rc < 0) {
+        delete c;
+        return rc;
+    }
+    if (c->pos.N != c->N) {
+        set_error("internal error: position index has %lld TRUE positions but %lld rows were kept",
+                  (long long)c->pos.N, (long long)c->N);
+        delete c;
+        return DFB_ECUDA;
+    }
+    *out = c;
+    return DFB_OK;
+}
+
+static int cov_from_dense_impl(dfb_ctx* ctx, int n, int64_t N, int dtype, const void* cov, int64_t ld, bool on_device,
+                               const int32_t* pos_len, int64_t pos_nruns, int pos_first, dfb_cov** out) {
+    DFB_REQUIRE(ctx && out && (cov || N == 0), "dfb_cov_from_dense: NULL argument");
+    *out = nullptr;
+    DFB_REQUIRE(n > 0 && N >= 0 && ld >= N, "dfb_cov_from_dense: bad shape (n=%d, N=%lld, ld=%lld)", n, (long long)N,
+                (long long)ld);
+    DFB_REQUIRE(dtype == DFB_I32 || dtype == DFB_F64, "unknown dtype %d", dtype);
+    DFB_REQUIRE(pos_len != nullptr, "'coverageInfo$position' is NULL when it shouldn't be.");
+    dfb_cov* c = new dfb_cov();
+    c->ctx = ctx;
+    c->n = n;
+    c->N = N;
+    c->dtype = dtype;
+    int rc = c->pos.build(ctx, pos_len, pos_nruns, pos_first);
+    if (rc >= 0 && c->pos.N != N) {
+        set_error("nrow(coverage) = %lld does not match sum(position) = %lld", (long long)N, (long long)c->pos.N);
+        rc = DFB_EINVAL;
+    }
+    if (rc >= 0) rc = alloc_matrix(c);
+    if (rc < 0) {
+        delete c;
+        return rc;
+    }
+    const size_t es = dtype == DFB_I32 ? 4 : 8;
+    void* dst = dtype == DFB_I32 ? (void*)c->xi.p : (void*)c->xd.p;
+    if (N > 0) {
+        cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)c->ld * es, cov, (size_t)ld * es, (size_t)N * es, (size_t)n,
+                                          on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
+        if (e != cudaSuccess) {
+            set_error("coverage upload: %s", cudaGetErrorString(e));
+            delete c;
+            return DFB_ECUDA;
+        }
+    }
+    *out = c;
+    return DFB_OK;
+}
+
+int dfb_cov_from_dense(dfb_ctx* ctx, int n, int64_t N, int dtype, const void* cov, int64_t ld, const int32_t* pos_len,
+                       int64_t pos_nruns, int pos_first, dfb_cov** out) {
+    int rc = cov_from_dense_impl(ctx, n, N, dtype, cov, ld, false, pos_len, pos_nruns, pos_first, out);
+    if (rc >= 0) cudaStreamSynchronize(ctx->stream);  // the caller may free `cov` right away
+    return rc;
+}
+
+int dfb_cov_from_dense_dev(dfb_ctx* ctx, int n, int64_t N, int dtype, const void* cov_dev, int64_t ld,
+                           const int32_t* pos_len, int64_t pos_nruns, int pos_first, dfb_cov** out) {
+    return cov_from_dense_impl(ctx, n, N, dtype, cov_dev, ld, true, pos_len, pos_nruns, pos_first, out);
+}
+
+int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, const int32_t* const* lengths,
+                     const int64_t* nruns, int64_t N, const int32_t* pos_len, int64_t pos_nruns, int pos_first,
+                     dfb_cov** out) {
+    DFB_REQUIRE(ctx && out, "dfb_cov_from_rle: NULL argument");
+    *out = nullptr;
+    DFB_REQUIRE(pos_len != nullptr, "'coverageInfo$position' is NULL when it shouldn't be.");
+    std::vector<int32_t> npl;
+    int npf = 0;
+    dfb_cov* c = nullptr;
+    DFB_TRY(filter_rle_impl(ctx, n, dtype, values, lengths, nruns, N, nullptr, DFB_FILTER_NONE, 0.0, false, &npl, &npf,
+                            &c));
+    int rc = c->pos.build(ctx, pos_len, pos_nruns, pos_first);
+    if (rc >= 0 && c->pos.N != N) {
+        set_error("nrow(coverage) = %lld does not match sum(position) = %lld", (long long)N, (long long)c->pos.N);
+        rc = DFB_EINVAL;
+    }
+    if (rc < 0) {
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return DFB_OK;
+}
+
+void dfb_cov_free(dfb_cov* cov) {
+    if (!cov) return;
+    cudaStreamSynchronize(cov->ctx->stream);
+    delete cov;
+}
+
+int dfb_cov_info(const dfb_cov* c, int64_t* N, int* n, int64_t* chr_len, int* dtype, int64_t* pos_nruns,
+                 int* n_groups, int* has_processed) {
+    DFB_REQUIRE(c, "dfb_cov_info: NULL handle");
+    if (N) *N = c->N;
+    if (n) *n = c->n;
+    if (chr_len) *chr_len = c->pos.chr_len;
+    if (dtype) *dtype = c->dtype;
+    if (pos_nruns) *pos_nruns = (int64_t)c->pos.len.size();
+    if (n_groups) *n_groups = c->G;
+    if (has_processed) *has_processed = c->y.p != nullptr;
+    return DFB_OK;
+}
+
+int dfb_cov_get_position(const dfb_cov* c, int32_t* lengths, int* first) {
+    DFB_REQUIRE(c, "dfb_cov_get_position: NULL handle");
+    if (lengths) memcpy(lengths, c->pos.len.data(), c->pos.len.size() * sizeof(int32_t));
+    if (first) *first = c->pos.first;
+    return DFB_OK;
+}
+
+int dfb_cov_get_column(const dfb_cov* c, int sample, void* out) {
+    DFB_REQUIRE(c && out, "dfb_cov_get_column: NULL argument");
+    DFB_REQUIRE(sample >= 0 && sample < c->n, "sample %d out of range", sample);
+    if (c->dtype == DFB_I32) return d2h(c->ctx, out, c->xi.p + (size_t)sample * c->ld, (size_t)c->N * 4);
+    return d2h(c->ctx, out, c->xd.p + (size_t)sample * c->ld, (size_t)c->N * 8);
+}
+
+int dfb_cov_get_mean(const dfb_cov* c, double* out) {
+    DFB_REQUIRE(c && out, "dfb_cov_get_mean: NULL argument");
+    if (!c->has_mean) {
+        set_error("meanCoverage is not available (filter with returnMean or run dfb_preprocess)");
+        return DFB_ESTATE;
+    }
+    return d2h(c->ctx, out, c->mean.p, (size_t)c->N * sizeof(double));
+}
+
+int dfb_preprocess(dfb_ctx* ctx, dfb_cov* c, double scalefac, const int32_t* group_of_sample, int n_groups) {
+    DFB_REQUIRE(ctx && c, "dfb_preprocess: NULL argument");
+    DFB_REQUIRE(n_groups >= 0 && n_groups <= 64, "at most 64 groups are supported (got %d)", n_groups);
+    DFB_REQUIRE(n_groups == 0 || group_of_sample, "groupInfo is NULL but n_groups > 0");
+    std::vector<double> gsize((size_t)n_groups, 0.0);
+    for (int s = 0; s < c->n && n_groups > 0; ++s) {
+        DFB_REQUIRE(group_of_sample[s] >= 0 && group_of_sample[s] < n_groups, "groupInfo[%d] out of range", s + 1);
+        gsize[(size_t)group_of_sample[s]] += 1.0;
+    }
+    c->scalefac = scalefac;
+    c->G = n_groups;
+    DFB_TRY(c->y.alloc(ctx, (size_t)c->n * c->ld));
+    if (n_groups > 0) DFB_TRY(c->gmean.alloc(ctx, (size_t)n_groups * c->ld));
+    const bool need_mean = !c->has_mean;
+    if (need_mean) DFB_TRY(c->mean.alloc(ctx, (size_t)std::max<int64_t>(c->N, 1)));
+    if (c->N == 0) {
+        c->has_mean = true;
+        return DFB_OK;
+    }
+    // integer coverage: log2 through a host-built table (glibc log2, the function R calls), so
+    // coverageProcessed is bit-identical to log2(x + scalefac) evaluated by R on this host
+    DevBuf<double> lut;
+    int64_t lut_n = 0;
+    if (c->dtype == DFB_I32) {
+        DevBuf<long long> mm;
+        DFB_TRY(mm.alloc(ctx, 2));
+        long long init[2] = {LLONG_MAX, LLONG_MIN};
+        DFB_TRY(h2d(ctx, mm.p, init, sizeof init));
+        {
+            KTimer t(ctx, DFB_K_PREP);
+            minmax_kernel<int32_t><<<grid_for((int64_t)c->n * c->N, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(
+                c->xi.p, c->ld, c->N, c->n, mm.p, mm.p + 1);
+        }
+        long long got[2];
+        DFB_TRY(d2h(ctx, got, mm.p, sizeof got));
+        if (got[0] >= 0 && got[1] < (1ll << 22)) {
+            lut_n = got[1] + 1;
+            std::vector<double> h((size_t)lut_n);
+            for (int64_t k = 0; k < lut_n; ++k) h[(size_t)k] = log2((double)k + scalefac);
+            DFB_TRY(lut.alloc(ctx, (size_t)lut_n));
+            DFB_TRY(h2d(ctx, lut.p, h.data(), (size_t)lut_n * sizeof(double)));
+            DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    DevBuf<int32_t> grp;
+    DevBuf<double> gsz;
+    if (n_groups > 0) {
+        DFB_TRY(grp.alloc(ctx, c->n));
+        DFB_TRY(gsz.alloc(ctx, n_groups));
+        DFB_TRY(h2d(ctx, grp.p, group_of_sample, (size_t)c->n * sizeof(int32_t)));
+        DFB_TRY(h2d(ctx, gsz.p, gsize.data(), (size_t)n_groups * sizeof(double)));
+    }
+    PrepParams P;
+    memset(&P, 0, sizeof P);
+    P.x = c->dtype == DFB_I32 ? (const void*)c->xi.p : (const void*)c->xd.p;
+    P.ld = c->ld;
+    P.N = c->N;
+    P.n = c->n;
+    P.scalefac = scalefac;
+    P.lut = lut_n ? lut.p : nullptr;
+    P.lut_n = lut_n;
+    P.group = n_groups ? grp.p : nullptr;
+    P.group_size = n_groups ? gsz.p : nullptr;
+    P.G = n_groups;
+    P.y = c->y.p;
+    P.mean = need_mean ? c->mean.p : nullptr;
+    P.gmean = n_groups ? c->gmean.p : nullptr;
+    const size_t smem = (size_t)n_groups * 256 * sizeof(double);
+    {
+        KTimer t(ctx, DFB_K_PREP);
+        const int grid = grid_for(c->N, 256, ctx->sm_count, 16);
+        if (c->dtype == DFB_I32) {
+            if (smem > 48 * 1024)
+                DFB_CUDA(cudaFuncSetAttribute(preprocess_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem));
+            preprocess_kernel<int32_t><<<grid, 256, smem, ctx->stream>>>(P);
+        } else {
+            if (smem > 48 * 1024)
+                DFB_CUDA(cudaFuncSetAttribute(preprocess_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (int)smem));
+            preprocess_kernel<double><<<grid, 256, smem, ctx->stream>>>(P);
+        }
+    }
+    DFB_CUDA(cudaGetLastError());
+    DFB_CUDA(cudaStreamSynchronize(ctx->stream));  // group arrays / LUT are locals
+    c->has_mean = true;
+    c->has_f = false;
+    return DFB_OK;
+}
+
+int dfb_cov_get_processed_column(const dfb_cov* c, int sample, double* out) {
+    DFB_REQUIRE(c && out, "dfb_cov_get_processed_column: NULL argument");
+    DFB_REQUIRE(sample >= 0 && sample < c->n, "sample %d out of range", sample);
+    if (!c->y.p) {
+        set_error("coverageProcessed is not available: run dfb_preprocess first");
+        return DFB_ESTATE;
+    }
+    return d2h(c->ctx, out, c->y.p + (size_t)sample * c->ld, (size_t)c->N * sizeof(double));
+}
+
+int dfb_cov_get_group_mean(const dfb_cov* c, int group, double* out) {
+    DFB_REQUIRE(c && out, "dfb_cov_get_group_mean: NULL argument");
+    DFB_REQUIRE(group >= 0 && group < c->G, "group %d out of range (%d groups)", group, c->G);
+    return d2h(c->ctx, out, c->gmean.p + (size_t)group * c->ld, (size_t)c->N * sizeof(double));
+}
+
+int64_t dfb_chunk_lengths(int64_t N, double chunksize, int mc_cores, int64_t* lens, int64_t cap) {
+    // R/preprocessCoverage.R:171-188, 218-227
+    if (!(chunksize > 0)) chunksize = ceil((double)N / (double)(mc_cores > 0 ? mc_cores : 1));
+    int64_t lastloop = chunksize > 0 ? (int64_t)trunc((double)N / chunksize) : 0;
+    if (chunksize > 0 && fmod((double)N, chunksize) == 0 && lastloop > 0) lastloop -= 1;
+    if (lastloop == 0) {
+        if (lens && cap > 0) lens[0] = N;
+        return 1;
+    }
+    int64_t used = 0, k = 0;
+    for (; k < lastloop; ++k) {
+        if (lens && k < cap) lens[k] = (int64_t)chunksize;
+        used += (int64_t)chunksize;
+    }
+    if (N - used > 0) {
+        if (lens && k < cap) lens[k] = N - used;
+        ++k;
+    }
+    return k;
+}
+
+}  // extern "C"

@@ -1,0 +1,308 @@
+// Context, error string, copies, device-wide scan.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace dfb {
+
+static thread_local std::string g_err;
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+}
+
+int h2d(dfb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes == 0) return DFB_OK;
+    DFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return DFB_OK;
+}
+
+int d2h(dfb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes) DFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// Exclusive scan, uint32 counts -> int64 offsets.  Three-phase (tile reduce, recursive scan of
+// the tile sums, tile scan + offset).  Tiles of 2048 items (256 threads x 8), loads coalesced.
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <typename TIn>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce_kernel(const TIn* __restrict__ in, int64_t n,
+                                                                   int64_t* __restrict__ tile_sums) {
+    __shared__ int64_t wsum[SCAN_THREADS / 32];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    int64_t acc = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int64_t idx = base + (int64_t)i * SCAN_THREADS + threadIdx.x;
+        if (idx < n) acc += (int64_t)in[idx];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int64_t t = 0;
+#pragma unroll
+        for (int w = 0; w < SCAN_THREADS / 32; ++w) t += wsum[w];
+        tile_sums[blockIdx.x] = t;
+    }
+}
+
+// in-place exclusive scan of up to SCAN_TILE int64 values by one block; writes the total.
+__global__ void __launch_bounds__(SCAN_THREADS) scan_small_kernel(int64_t* __restrict__ data, int64_t n,
+                                                                  int64_t* __restrict__ total) {
+    __shared__ int64_t wsum[SCAN_THREADS / 32];
+    __shared__ int64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    // each thread owns SCAN_ITEMS consecutive values (blocked arrangement)
+    for (int64_t base = 0; base < n; base += SCAN_TILE) {
+        int64_t v[SCAN_ITEMS];
+        int64_t tsum = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            int64_t idx = base + (int64_t)threadIdx.x * SCAN_ITEMS + i;
+            v[i] = idx < n ? data[idx] : 0;
+            tsum += v[i];
+        }
+        int64_t inc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((threadIdx.x & 31) >= o) inc += t;
+        }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        int64_t wprefix = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wprefix += wsum[w];
+        int64_t excl = carry_s + wprefix + inc - tsum;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            int64_t idx = base + (int64_t)threadIdx.x * SCAN_ITEMS + i;
+            if (idx < n) data[idx] = excl;
+            excl += v[i];
+        }
+        __syncthreads();
+        if (threadIdx.x == SCAN_THREADS - 1) carry_s = excl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry_s;
+}
+
+template <typename TIn>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_tile_kernel(const TIn* __restrict__ in, int64_t n,
+                                                                 const int64_t* __restrict__ tile_offsets,
+                                                                 int64_t* __restrict__ out) {
+    __shared__ int64_t wsum[SCAN_THREADS / 32];
+    int64_t base = (int64_t)blockIdx.x * SCAN_TILE;
+    int64_t v[SCAN_ITEMS];
+    int64_t tsum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int64_t idx = base + (int64_t)threadIdx.x * SCAN_ITEMS + i;
+        v[i] = idx < n ? (int64_t)in[idx] : 0;
+        tsum += v[i];
+    }
+    int64_t inc = tsum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((threadIdx.x & 31) >= o) inc += t;
+    }
+    if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+    __syncthreads();
+    int64_t wprefix = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wprefix += wsum[w];
+    int64_t excl = tile_offsets[blockIdx.x] + wprefix + inc - tsum;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        int64_t idx = base + (int64_t)threadIdx.x * SCAN_ITEMS + i;
+        if (idx < n) out[idx] = excl;
+        excl += v[i];
+    }
+}
+
+template <typename TIn>
+static int scan_impl(dfb_ctx* ctx, const TIn* in, int64_t* out, int64_t n, int64_t* total_dev, int fam) {
+    if (n <= 0) {
+        if (total_dev) DFB_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(int64_t), ctx->stream));
+        return DFB_OK;
+    }
+    int64_t tiles = ceil_div(n, SCAN_TILE);
+    DevBuf<int64_t> sums;
+    DFB_TRY(sums.alloc(ctx, (size_t)tiles));
+    {
+        KTimer t(ctx, fam, 1);
+        scan_reduce_kernel<TIn><<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(in, n, sums.p);
+    }
+    if (tiles <= SCAN_TILE * 64) {
+        KTimer t(ctx, fam, 1);
+        scan_small_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(sums.p, tiles, total_dev);
+    } else {
+        DevBuf<int64_t> sums_out;
+        DFB_TRY(sums_out.alloc(ctx, (size_t)tiles));
+        DFB_TRY(scan_impl<int64_t>(ctx, sums.p, sums_out.p, tiles, total_dev, fam));
+        sums = std::move(sums_out);
+    }
+    {
+        KTimer t(ctx, fam, 1);
+        scan_tile_kernel<TIn><<<(unsigned)tiles, SCAN_THREADS, 0, ctx->stream>>>(in, n, sums.p, out);
+    }
+    DFB_CUDA(cudaGetLastError());
+    return DFB_OK;
+}
+
+int exclusive_scan_u32(dfb_ctx* ctx, const uint32_t* in, int64_t* out, int64_t n, int64_t* total_dev, int fam) {
+    return scan_impl<uint32_t>(ctx, in, out, n, total_dev, fam);
+}
+
+int exclusive_scan_i64(dfb_ctx* ctx, const int64_t* in, int64_t* out, int64_t n, int64_t* total_dev, int fam) {
+    return scan_impl<int64_t>(ctx, in, out, n, total_dev, fam);
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" {
+
+const char* dfb_last_error(void) { return g_err.c_str(); }
+int dfb_version(void) { return DFB_VERSION; }
+
+int dfb_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int dfb_create(int device, void* stream, dfb_ctx** out) {
+    DFB_REQUIRE(out != nullptr, "dfb_create: out is NULL");
+    *out = nullptr;
+    int ndev = dfb_device_count();
+    if (ndev <= 0) {
+        set_error("dfb_create: no CUDA device available (this engine has no CPU fallback)");
+        return DFB_ECUDA;
+    }
+    DFB_REQUIRE(device >= 0 && device < ndev, "dfb_create: device %d out of range (%d visible)", device, ndev);
+    DFB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    DFB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_error("dfb_create: device %d is sm_%d%d; this library is built for sm_100a (B200) only", device,
+                  prop.major, prop.minor);
+        return DFB_ECUDA;
+    }
+    dfb_ctx* c = new dfb_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    c->smem_optin = prop.sharedMemPerBlockOptin;
+    if (stream) {
+        c->stream = (cudaStream_t)stream;
+    } else {
+        cudaError_t e = cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking);
+        if (e != cudaSuccess) {
+            set_error("cudaStreamCreate: %s", cudaGetErrorString(e));
+            delete c;
+            return DFB_ECUDA;
+        }
+        c->own_stream = true;
+    }
+    // keep freed blocks in the pool: repeated calls re-use them without a device sync
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    cudaGetLastError();
+    *out = c;
+    return DFB_OK;
+}
+
+void dfb_destroy(dfb_ctx* c) {
+    if (!c) return;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    for (auto& e : c->evs) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->own_stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+int dfb_sync(dfb_ctx* c) {
+    DFB_REQUIRE(c, "dfb_sync: NULL context");
+    DFB_CUDA(cudaStreamSynchronize(c->stream));
+    return DFB_OK;
+}
+
+int64_t dfb_launch_count(dfb_ctx* c) { return c ? c->launches : 0; }
+
+static int drain_events(dfb_ctx* c) {
+    if (c->evs.empty()) return DFB_OK;
+    DFB_CUDA(cudaStreamSynchronize(c->stream));
+    for (auto& e : c->evs) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) c->kms[e.k] += ms;
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    c->evs.clear();
+    cudaGetLastError();
+    return DFB_OK;
+}
+
+void dfb_reset_counters(dfb_ctx* c) {
+    if (!c) return;
+    drain_events(c);
+    c->launches = 0;
+    for (int k = 0; k < DFB_K_COUNT; ++k) {
+        c->kms[k] = 0;
+        c->klaunch[k] = 0;
+    }
+}
+
+int dfb_enable_timing(dfb_ctx* c, int on) {
+    DFB_REQUIRE(c, "NULL context");
+    DFB_TRY(drain_events(c));
+    c->timing = on != 0;
+    return DFB_OK;
+}
+
+int dfb_kernel_time(dfb_ctx* c, int kernel, double* ms, int64_t* launches) {
+    DFB_REQUIRE(c && kernel > 0 && kernel < DFB_K_COUNT, "dfb_kernel_time: bad kernel id %d", kernel);
+    DFB_TRY(drain_events(c));
+    if (ms) *ms = c->kms[kernel];
+    if (launches) *launches = c->klaunch[kernel];
+    return DFB_OK;
+}
+
+int dfb_set_option(dfb_ctx* c, const char* key, double value) {
+    DFB_REQUIRE(c && key, "dfb_set_option: NULL argument");
+    if (!strcmp(key, "screen")) c->opt_screen = value != 0;
+    else if (!strcmp(key, "null_capacity_mb")) c->opt_null_cap_mb = value;
+    else if (!strcmp(key, "perm_batch")) c->opt_perm_batch = (int)value;
+    else if (!strcmp(key, "scratch_gb")) c->opt_scratch_gb = value;
+    else {
+        set_error("dfb_set_option: unknown option '%s'", key);
+        return DFB_EINVAL;
+    }
+    return DFB_OK;
+}
+
+}  // extern "C"

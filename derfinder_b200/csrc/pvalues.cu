@@ -1,0 +1,525 @@
+// K5 and the permutation driver: null regions per permutation, null-area sort, exact p-value and
+// FWER counting, empirical quantile cutoff.
+//
+// Reference: calculatePvalues (R/calculatePvalues.R:157-430; the permutation loop :306-358, the
+// duplicated null storage :346-354, the stable decreasing-area order :368), .calcPval (:432-441),
+// .calculateFWER (R/mergeResults.R:380-386), quantile(fstats, 0.99) default cutoff
+// (R/findRegions.R:118).  Sorting uses cub::DeviceRadixSort (CUDA toolkit library).
+#include <math.h>
+
+#include <algorithm>
+#include <cub/cub.cuh>
+
+#include "data.cuh"
+
+namespace dfb {
+
+// ------------------------------------------------------------------------------------------
+
+__global__ void add_perm_offset_kernel(int32_t* __restrict__ perm, int64_t n, int32_t offset) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) perm[i] += offset;
+}
+
+static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const double* mod0, int p0,
+                           double adjust_f, const int32_t* perm_idx, int64_t B, double lo, double hi,
+                           int32_t max_region_gap, dfb_nulls** out) {
+    *out = nullptr;
+    DFB_REQUIRE(cov->y.p != nullptr, "coverageProcessed is missing: run dfb_preprocess first");
+    DFB_REQUIRE(B >= 0 && (perm_idx || B == 0), "perm_idx is NULL");
+    DFB_REQUIRE(lo <= hi, "cutoff pair must be sorted (L <= U)");
+    ModelBasis mb;
+    DFB_TRY(build_model_basis(mod, cov->n, p, mod0, p0, &mb));
+    const int n = cov->n;
+    for (int64_t b = 0; b < B; ++b)
+        for (int k = 0; k < n; ++k)
+            DFB_REQUIRE(perm_idx[b * n + k] >= 0 && perm_idx[b * n + k] < n,
+                        "perm_idx[%lld, %d] = %d is not a 0-based sample index", (long long)b, k, perm_idx[b * n + k]);
+    dfb_nulls* nl = new dfb_nulls();
+    nl->ctx = ctx;
+    nl->B = B;
+    nl->per_perm.assign((size_t)B, 0);
+    if (B == 0 || cov->N == 0) {
+        *out = nl;
+        return DFB_OK;
+    }
+    struct Guard {
+        dfb_nulls* p;
+        ~Guard() { delete p; }
+    } guard{nl};
+
+    DevBuf<double> qd;
+    DevBuf<int32_t> idx_d;
+    DevBuf<uint32_t> seg;
+    DFB_TRY(qd.alloc(ctx, mb.qpad.size()));
+    DFB_TRY(h2d(ctx, qd.p, mb.qpad.data(), mb.qpad.size() * sizeof(double)));
+    DFB_TRY(idx_d.alloc(ctx, (size_t)B * n));
+    DFB_TRY(h2d(ctx, idx_d.p, perm_idx, (size_t)B * n * sizeof(int32_t)));
+    DFB_TRY(build_segment_starts(ctx, cov->pos, max_region_gap, &seg));
+
+    // F >= 0 (or NaN) by construction, so the "dn" side (F <= L) can only fire when L >= 0
+    const bool two_sided = lo >= 0.0;
+    const int sides = two_sided ? 2 : 1;
+    const int64_t N = cov->N;
+    const int tb = fstat_tile_bases(n);
+    const double per_perm_fixed = (double)sides * ((double)ceil_div(N, 32) * 4.0 + (double)ceil_div(N, tb) * 8.0 +
+                                                   (double)ceil_div(N, 32) * 12.0 /* region counts + offsets */);
+    const double budget = ctx->opt_scratch_gb * 1e9;
+    int64_t pb = (int64_t)std::max(1.0, floor(budget * 0.5 / per_perm_fixed));
+    if (ctx->opt_perm_batch > 0) pb = ctx->opt_perm_batch;
+    pb = std::min<int64_t>(pb, B);
+
+    std::vector<RegionSet> sets;
+    std::vector<std::pair<int64_t, int64_t>> work;  // [b_lo, b_hi)
+    for (int64_t b = B; b > 0;) {
+        int64_t lo_b = std::max<int64_t>(0, b - pb);
+        work.push_back({lo_b, b});
+        b = lo_b;
+    }
+    // work is a stack: batches come off in increasing permutation order
+    double density = ctx->opt_null_cap_mb > 0 ? -1.0 : 0.08;
+    while (!work.empty()) {
+        auto [b_lo, b_hi] = work.back();
+        work.pop_back();
+        const int64_t nb = b_hi - b_lo;
+        const double dense = (double)nb * sides * (double)N;
+        size_t hint = density < 0 ? (size_t)(ctx->opt_null_cap_mb * 1e6 / 8.0)
+                                  : (size_t)std::max(dense * density, 4.0e6);
+        if ((double)hint * 8.0 > budget * 0.5) hint = (size_t)(budget * 0.5 / 8.0);
+        PermBatch pbatch;
+        int rc = fstat_perm_batch(ctx, cov, mb, qd.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, lo, hi, two_sided, hint,
+                                  &pbatch);
+        if (rc == DFB_ENOMEM && nb > 1) {  // exceedances did not fit: halve the batch
+            const int64_t mid = b_lo + nb / 2;
+            work.push_back({mid, b_hi});
+            work.push_back({b_lo, mid});
+            continue;
+        }
+        DFB_TRY(rc);
+        if (density >= 0 && dense > 0) density = std::min(1.0, std::max(0.01, 1.3 * (double)pbatch.nvals / dense));
+        RegionSet rs;
+        DFB_TRY(find_regions_rows(ctx, N, pbatch.rows, sides, pbatch.mask.p, seg.p, nullptr, 0, &pbatch, false, true,
+                                  &rs));
+        for (int64_t b = 0; b < nb; ++b)
+            for (int s = 0; s < sides; ++s) nl->per_perm[(size_t)(b_lo + b)] += rs.row_counts[(size_t)(b * sides + s)];
+        if (rs.total > 0 && b_lo > 0) {
+            KTimer t(ctx, DFB_K_REGIONS);
+            add_perm_offset_kernel<<<(unsigned)ceil_div(rs.total, 256), 256, 0, ctx->stream>>>(rs.perm.p, rs.total,
+                                                                                              (int32_t)b_lo);
+        }
+        sets.push_back(std::move(rs));
+    }
+    int64_t total = 0;
+    for (auto& s : sets) total += s.total;
+    nl->count = total;
+    if (total > 0) {
+        if (sets.size() == 1) {
+            nl->area = std::move(sets[0].area);
+            nl->stat = std::move(sets[0].stat);
+            nl->width = std::move(sets[0].width);
+            nl->perm = std::move(sets[0].perm);
+        } else {
+            DFB_TRY(nl->area.alloc(ctx, (size_t)total));
+            DFB_TRY(nl->stat.alloc(ctx, (size_t)total));
+            DFB_TRY(nl->width.alloc(ctx, (size_t)total));
+            DFB_TRY(nl->perm.alloc(ctx, (size_t)total));
+            int64_t o = 0;
+            for (auto& s : sets) {
+                if (s.total == 0) continue;
+                DFB_CUDA(cudaMemcpyAsync(nl->area.p + o, s.area.p, (size_t)s.total * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+                DFB_CUDA(cudaMemcpyAsync(nl->stat.p + o, s.stat.p, (size_t)s.total * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+                DFB_CUDA(cudaMemcpyAsync(nl->width.p + o, s.width.p, (size_t)s.total * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+                DFB_CUDA(cudaMemcpyAsync(nl->perm.p + o, s.perm.p, (size_t)s.total * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+                o += s.total;
+            }
+        }
+    }
+    DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    guard.p = nullptr;
+    *out = nl;
+    return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// p-values: sorted nulls + upper bound
+
+__global__ void pval_kernel(const double* __restrict__ areas, int64_t R, const double* __restrict__ sorted_nulls,
+                            int64_t M, double weight, double* __restrict__ p) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const double a = areas[r];
+    // k = number of nulls <= a  (findInterval on the unique values, then "strictly greater" count)
+    int64_t lo = 0, hi = M;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (sorted_nulls[mid] <= a) lo = mid + 1;
+        else hi = mid;
+    }
+    p[r] = __ddiv_rn(weight * (double)(M - lo) + 1.0, weight * (double)M + 1.0);
+}
+
+static int sort_doubles(dfb_ctx* ctx, const double* in, double* out, int64_t n) {
+    size_t tmp_bytes = 0;
+    DFB_CUDA(cub::DeviceRadixSort::SortKeys(nullptr, tmp_bytes, in, out, n, 0, 64, ctx->stream));
+    DevBuf<unsigned char> tmp;
+    DFB_TRY(tmp.alloc(ctx, tmp_bytes));
+    {
+        KTimer t(ctx, DFB_K_PVAL, 8);
+        DFB_CUDA(cub::DeviceRadixSort::SortKeys(tmp.p, tmp_bytes, in, out, n, 0, 64, ctx->stream));
+    }
+    return DFB_OK;
+}
+
+int calc_pval_device(dfb_ctx* ctx, const double* areas_dev, int64_t R, const double* nulls_dev, int64_t M, int weight,
+                     double* p_dev) {
+    if (R == 0) return DFB_OK;
+    DevBuf<double> sorted;
+    DFB_TRY(sorted.alloc(ctx, (size_t)std::max<int64_t>(M, 1)));
+    if (M > 0) DFB_TRY(sort_doubles(ctx, nulls_dev, sorted.p, M));
+    {
+        KTimer t(ctx, DFB_K_PVAL);
+        pval_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, ctx->stream>>>(areas_dev, R, sorted.p, M, (double)weight,
+                                                                        p_dev);
+    }
+    DFB_CUDA(cudaGetLastError());
+    return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// FWER: per-permutation maximum (areas are >= 0, so the IEEE bit pattern orders like the value)
+
+__global__ void perm_max_kernel(const double* __restrict__ area, const int32_t* __restrict__ perm, int64_t M,
+                                int64_t B, unsigned long long* __restrict__ bits) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= M) return;
+    const int64_t b = (int64_t)perm[i] - 1;
+    if (b < 0 || b >= B) return;
+    const double a = fabs(area[i]);
+    atomicMax(&bits[b], (unsigned long long)__double_as_longlong(a) + 1ull);  // 0 = no region
+}
+
+__global__ void perm_max_decode_kernel(const unsigned long long* __restrict__ bits, int64_t B, double fill,
+                                       double* __restrict__ mx) {
+    int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const unsigned long long v = bits[b];
+    mx[b] = v == 0ull ? fill : __longlong_as_double((long long)(v - 1ull));
+}
+
+__global__ void fwer_kernel(const double* __restrict__ areas, int64_t R, const double* __restrict__ mx, int64_t B,
+                            double* __restrict__ fwer) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const double a = areas[r];
+    int64_t c = 0;
+    for (int64_t b = 0; b < B; ++b) c += mx[b] > a ? 1 : 0;
+    fwer[r] = __ddiv_rn((double)(c + 1), (double)(B + 1));
+}
+
+int perm_max_device(dfb_ctx* ctx, const double* area_dev, const int32_t* perm_dev, int64_t M, int64_t B, double fill,
+                    double* mx_dev) {
+    DevBuf<unsigned long long> bits;
+    DFB_TRY(bits.alloc(ctx, (size_t)std::max<int64_t>(B, 1)));
+    DFB_TRY(bits.zero());
+    KTimer t(ctx, DFB_K_PVAL, 2);
+    if (M > 0)
+        perm_max_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, ctx->stream>>>(area_dev, perm_dev, M, B, bits.p);
+    if (B > 0) perm_max_decode_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, ctx->stream>>>(bits.p, B, fill, mx_dev);
+    DFB_CUDA(cudaGetLastError());
+    return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// quantile type 7 (na.rm = TRUE)
+
+__global__ void nan_to_top_kernel(const double* __restrict__ x, int64_t N, double* __restrict__ out,
+                                  unsigned long long* __restrict__ nan_count) {
+    unsigned long long c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        double v = x[i];
+        if (v != v) {
+            v = __longlong_as_double(0x7ff8000000000000ll);  // sorts after +Inf
+            ++c;
+        }
+        out[i] = v;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(nan_count, c);
+}
+
+int quantile_device(dfb_ctx* ctx, const double* x_dev, int64_t N, double prob, double* out) {
+    DFB_REQUIRE(prob >= 0 && prob <= 1, "'probs' outside [0,1]");
+    DevBuf<double> a, b;
+    DevBuf<unsigned long long> nanc;
+    DFB_TRY(a.alloc(ctx, (size_t)std::max<int64_t>(N, 1)));
+    DFB_TRY(b.alloc(ctx, (size_t)std::max<int64_t>(N, 1)));
+    DFB_TRY(nanc.alloc(ctx, 1));
+    DFB_TRY(nanc.zero());
+    if (N > 0) {
+        {
+            KTimer t(ctx, DFB_K_PVAL);
+            nan_to_top_kernel<<<grid_for(N, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(x_dev, N, a.p, nanc.p);
+        }
+        DFB_TRY(sort_doubles(ctx, a.p, b.p, N));
+    }
+    unsigned long long nn = 0;
+    DFB_TRY(d2h(ctx, &nn, nanc.p, sizeof nn));
+    const int64_t m = N - (int64_t)nn;
+    if (m <= 0) {
+        *out = nan("");
+        return DFB_OK;
+    }
+    // stats::quantile type 7: index = 1 + (m-1)*p; qs = x[lo]; if index > lo and x[hi] != qs:
+    // qs = (1-h)*qs + h*x[hi]
+    const double index = 1.0 + (double)(m - 1) * prob;
+    const double lo = floor(index), hi = ceil(index);
+    double v[2];
+    DFB_TRY(d2h(ctx, &v[0], b.p + (int64_t)lo - 1, sizeof(double)));
+    DFB_TRY(d2h(ctx, &v[1], b.p + (int64_t)hi - 1, sizeof(double)));
+    double qs = v[0];
+    if (index > lo && v[1] != qs) {
+        const double h = index - lo;
+        qs = (1.0 - h) * qs + h * v[1];
+    }
+    *out = qs;
+    return DFB_OK;
+}
+
+// stable order(area, decreasing = TRUE): descending radix sort of (area, iota) pairs is stable
+static int order_desc(dfb_ctx* ctx, const double* area_dev, int64_t R, int32_t* order_dev, double* sorted_dev) {
+    DevBuf<int32_t> iota;
+    DFB_TRY(iota.alloc(ctx, (size_t)R));
+    std::vector<int32_t> h((size_t)R);
+    for (int64_t k = 0; k < R; ++k) h[(size_t)k] = (int32_t)k;
+    DFB_TRY(h2d(ctx, iota.p, h.data(), (size_t)R * sizeof(int32_t)));
+    size_t tmp_bytes = 0;
+    DFB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, area_dev, sorted_dev, iota.p, order_dev, R, 0,
+                                                       64, ctx->stream));
+    DevBuf<unsigned char> tmp;
+    DFB_TRY(tmp.alloc(ctx, tmp_bytes));
+    {
+        KTimer t(ctx, DFB_K_PVAL, 8);
+        DFB_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp.p, tmp_bytes, area_dev, sorted_dev, iota.p, order_dev, R,
+                                                           0, 64, ctx->stream));
+    }
+    DFB_CUDA(cudaStreamSynchronize(ctx->stream));  // `h` is a local
+    return DFB_OK;
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" {
+
+int dfb_fstats(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const double* mod0, int p0, double adjust_f,
+               double* fstats_out) {
+    DFB_REQUIRE(ctx && cov, "dfb_fstats: NULL argument");
+    if (!cov->y.p) {
+        set_error("preprocessCoverage() has not been run on this coverage (coverageProcessed is missing)");
+        return DFB_ESTATE;
+    }
+    ModelBasis mb;
+    DFB_TRY(build_model_basis(mod, cov->n, p, mod0, p0, &mb));
+    DFB_TRY(cov->fstats.alloc(ctx, (size_t)std::max<int64_t>(cov->N, 1)));
+    cov->has_f = false;
+    if (cov->N > 0) DFB_TRY(fstat_observed(ctx, cov, mb, adjust_f, cov->fstats.p));
+    cov->has_f = true;
+    if (fstats_out) DFB_TRY(d2h(ctx, fstats_out, cov->fstats.p, (size_t)cov->N * sizeof(double)));
+    else DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DFB_OK;
+}
+
+int dfb_perm_nulls(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const double* mod0, int p0, double adjust_f,
+                   const int32_t* perm_idx, int64_t B, double cutoff_lo, double cutoff_hi, int32_t max_region_gap,
+                   dfb_nulls** out) {
+    DFB_REQUIRE(ctx && cov && out, "dfb_perm_nulls: NULL argument");
+    return perm_nulls_impl(ctx, cov, mod, p, mod0, p0, adjust_f, perm_idx, B, cutoff_lo, cutoff_hi, max_region_gap,
+                           out);
+}
+
+void dfb_nulls_free(dfb_nulls* nl) {
+    if (!nl) return;
+    cudaStreamSynchronize(nl->ctx->stream);
+    delete nl;
+}
+
+int64_t dfb_nulls_count(const dfb_nulls* nl) { return nl ? nl->count : 0; }
+
+int dfb_nulls_counts_per_perm(const dfb_nulls* nl, int64_t* counts) {
+    DFB_REQUIRE(nl && counts, "dfb_nulls_counts_per_perm: NULL argument");
+    memcpy(counts, nl->per_perm.data(), nl->per_perm.size() * sizeof(int64_t));
+    return DFB_OK;
+}
+
+int dfb_nulls_get(const dfb_nulls* nl, int dup, double* stat, int32_t* width, double* area, int32_t* permutation) {
+    DFB_REQUIRE(nl, "dfb_nulls_get: NULL handle");
+    const size_t M = (size_t)nl->count;
+    if (M == 0) return DFB_OK;
+    std::vector<double> hs, ha;
+    std::vector<int32_t> hw, hp;
+    dfb_ctx* ctx = nl->ctx;
+    if (stat) { hs.resize(M); DFB_TRY(d2h(ctx, hs.data(), nl->stat.p, M * 8)); }
+    if (area) { ha.resize(M); DFB_TRY(d2h(ctx, ha.data(), nl->area.p, M * 8)); }
+    if (width) { hw.resize(M); DFB_TRY(d2h(ctx, hw.data(), nl->width.p, M * 4)); }
+    if (permutation) { hp.resize(M); DFB_TRY(d2h(ctx, hp.data(), nl->perm.p, M * 4)); }
+    if (!dup) {
+        if (stat) memcpy(stat, hs.data(), M * 8);
+        if (area) memcpy(area, ha.data(), M * 8);
+        if (width) memcpy(width, hw.data(), M * 4);
+        if (permutation) memcpy(permutation, hp.data(), M * 4);
+        return DFB_OK;
+    }
+    // the reference appends every permutation's regions twice: [r1..rk, r1..rk] (:346-354)
+    size_t src = 0, dst = 0;
+    for (size_t b = 0; b < nl->per_perm.size(); ++b) {
+        const size_t k = (size_t)nl->per_perm[b];
+        for (int rep = 0; rep < 2; ++rep) {
+            if (stat) memcpy(stat + dst, hs.data() + src, k * 8);
+            if (area) memcpy(area + dst, ha.data() + src, k * 8);
+            if (width) memcpy(width + dst, hw.data() + src, k * 4);
+            if (permutation) memcpy(permutation + dst, hp.data() + src, k * 4);
+            dst += k;
+        }
+        src += k;
+    }
+    return DFB_OK;
+}
+
+int dfb_nulls_copy_dev(const dfb_nulls* nl, double* area_dev, int32_t* perm_dev) {
+    DFB_REQUIRE(nl, "dfb_nulls_copy_dev: NULL handle");
+    const size_t M = (size_t)nl->count;
+    if (M == 0) return DFB_OK;
+    if (area_dev) DFB_CUDA(cudaMemcpyAsync(area_dev, nl->area.p, M * 8, cudaMemcpyDeviceToDevice, nl->ctx->stream));
+    if (perm_dev) DFB_CUDA(cudaMemcpyAsync(perm_dev, nl->perm.p, M * 4, cudaMemcpyDeviceToDevice, nl->ctx->stream));
+    return DFB_OK;
+}
+
+int dfb_calc_pval_dev(dfb_ctx* ctx, const double* areas_dev, int64_t R, double* nullareas_dev, int64_t M, int weight,
+                      double* pvalues_dev) {
+    DFB_REQUIRE(ctx && (areas_dev || R == 0) && (nullareas_dev || M == 0) && (pvalues_dev || R == 0),
+                "dfb_calc_pval_dev: NULL argument");
+    DFB_REQUIRE(weight >= 1, "weight must be >= 1");
+    return calc_pval_device(ctx, areas_dev, R, nullareas_dev, M, weight, pvalues_dev);
+}
+
+int dfb_calc_pval(dfb_ctx* ctx, const double* areas, int64_t R, const double* nullareas, int64_t M, int weight,
+                  double* pvalues) {
+    DFB_REQUIRE(ctx && (areas || R == 0) && (nullareas || M == 0) && (pvalues || R == 0), "dfb_calc_pval: NULL argument");
+    DFB_REQUIRE(weight >= 1, "weight must be >= 1");
+    if (R == 0) return DFB_OK;
+    DevBuf<double> a, nu, pv;
+    DFB_TRY(a.alloc(ctx, (size_t)R));
+    DFB_TRY(nu.alloc(ctx, (size_t)std::max<int64_t>(M, 1)));
+    DFB_TRY(pv.alloc(ctx, (size_t)R));
+    DFB_TRY(h2d(ctx, a.p, areas, (size_t)R * 8));
+    DFB_TRY(h2d(ctx, nu.p, nullareas, (size_t)M * 8));
+    DFB_TRY(calc_pval_device(ctx, a.p, R, nu.p, M, weight, pv.p));
+    return d2h(ctx, pvalues, pv.p, (size_t)R * 8);
+}
+
+int dfb_perm_max_dev(dfb_ctx* ctx, const double* nullareas_dev, const int32_t* perm_dev, int64_t M, int64_t B,
+                     double fill, double* max_dev) {
+    DFB_REQUIRE(ctx && max_dev, "dfb_perm_max_dev: NULL argument");
+    return perm_max_device(ctx, nullareas_dev, perm_dev, M, B, fill, max_dev);
+}
+
+int dfb_calc_fwer(dfb_ctx* ctx, double cutoff_used, const double* nullareas, const int32_t* permutation, int64_t M,
+                  int64_t B, const double* areas, int64_t R, double* fwer) {
+    DFB_REQUIRE(ctx && (areas || R == 0) && (fwer || R == 0), "dfb_calc_fwer: NULL argument");
+    DFB_REQUIRE(B >= 1, "nPermute must be >= 1");
+    if (R == 0) return DFB_OK;
+    DevBuf<double> a, nu, mx, fw;
+    DevBuf<int32_t> pm;
+    DFB_TRY(a.alloc(ctx, (size_t)R));
+    DFB_TRY(fw.alloc(ctx, (size_t)R));
+    DFB_TRY(nu.alloc(ctx, (size_t)std::max<int64_t>(M, 1)));
+    DFB_TRY(pm.alloc(ctx, (size_t)std::max<int64_t>(M, 1)));
+    DFB_TRY(mx.alloc(ctx, (size_t)B));
+    DFB_TRY(h2d(ctx, a.p, areas, (size_t)R * 8));
+    DFB_TRY(h2d(ctx, nu.p, nullareas, (size_t)M * 8));
+    DFB_TRY(h2d(ctx, pm.p, permutation, (size_t)M * 4));
+    DFB_TRY(perm_max_device(ctx, nu.p, pm.p, M, B, cutoff_used, mx.p));
+    {
+        KTimer t(ctx, DFB_K_PVAL);
+        fwer_kernel<<<(unsigned)ceil_div(R, 128), 128, 0, ctx->stream>>>(a.p, R, mx.p, B, fw.p);
+    }
+    DFB_CUDA(cudaGetLastError());
+    return d2h(ctx, fwer, fw.p, (size_t)R * 8);
+}
+
+int dfb_quantile(dfb_ctx* ctx, const dfb_cov* cov, const double* x, int64_t N, double prob, double* out) {
+    DFB_REQUIRE(ctx && out, "dfb_quantile: NULL argument");
+    if (x) {
+        DevBuf<double> tmp;
+        DFB_TRY(tmp.alloc(ctx, (size_t)std::max<int64_t>(N, 1)));
+        DFB_TRY(h2d(ctx, tmp.p, x, (size_t)N * 8));
+        int rc = quantile_device(ctx, tmp.p, N, prob, out);
+        cudaStreamSynchronize(ctx->stream);
+        return rc;
+    }
+    DFB_REQUIRE(cov, "dfb_quantile: neither x nor a coverage handle given");
+    if (!cov->has_f) {
+        set_error("dfb_quantile: no F-statistics cached (run dfb_fstats first)");
+        return DFB_ESTATE;
+    }
+    return quantile_device(ctx, cov->fstats.p, cov->N, prob, out);
+}
+
+int dfb_calculate_pvalues(dfb_ctx* ctx, dfb_cov* cov, const double* fstats, const double* mod, int p,
+                          const double* mod0, int p0, double adjust_f, const int32_t* perm_idx, int64_t B,
+                          double cutoff_lo, double cutoff_hi, int32_t max_region_gap, int32_t max_cluster_gap,
+                          dfb_regions** regions, dfb_nulls** nulls, double* pvalues) {
+    DFB_REQUIRE(ctx && cov && regions && nulls, "dfb_calculate_pvalues: NULL argument");
+    *regions = nullptr;
+    *nulls = nullptr;
+    DFB_REQUIRE(cutoff_lo <= cutoff_hi, "cutoff pair must be sorted (L <= U)");
+    if (fstats) {
+        DFB_TRY(cov->fstats.alloc(ctx, (size_t)std::max<int64_t>(cov->N, 1)));
+        DFB_TRY(h2d(ctx, cov->fstats.p, fstats, (size_t)cov->N * 8));
+        DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        cov->has_f = true;
+    } else if (!cov->has_f) {
+        set_error("dfb_calculate_pvalues: no F-statistics given and none cached");
+        return DFB_ESTATE;
+    }
+    dfb_regions* r = nullptr;
+    int rc = find_regions_dense(ctx, cov->fstats.p, cov->pos, cutoff_lo, cutoff_hi, max_region_gap, max_cluster_gap,
+                                false, &r);
+    if (rc != DFB_OK) return rc;  // DFB_ENOREGIONS: list(regions = NULL, ...) (:245-251)
+    dfb_nulls* nl = nullptr;
+    rc = perm_nulls_impl(ctx, cov, mod, p, mod0, p0, adjust_f, perm_idx, B, cutoff_lo, cutoff_hi, max_region_gap, &nl);
+    if (rc < 0) {
+        delete r;
+        return rc;
+    }
+    // order by decreasing area (stable), then p-values against the (duplicated) null areas
+    const int64_t R = r->R;
+    DevBuf<double> area_d, sorted_d, p_d;
+    DevBuf<int32_t> order_d;
+    auto fail = [&](int code) {
+        delete r;
+        delete nl;
+        return code;
+    };
+    if ((rc = area_d.alloc(ctx, (size_t)R)) < 0) return fail(rc);
+    if ((rc = sorted_d.alloc(ctx, (size_t)R)) < 0) return fail(rc);
+    if ((rc = p_d.alloc(ctx, (size_t)R)) < 0) return fail(rc);
+    if ((rc = order_d.alloc(ctx, (size_t)R)) < 0) return fail(rc);
+    if ((rc = h2d(ctx, area_d.p, r->area.data(), (size_t)R * 8)) < 0) return fail(rc);
+    if ((rc = order_desc(ctx, area_d.p, R, order_d.p, sorted_d.p)) < 0) return fail(rc);
+    r->order.resize((size_t)R);
+    if ((rc = d2h(ctx, r->order.data(), order_d.p, (size_t)R * 4)) < 0) return fail(rc);
+    r->pvalues.assign((size_t)R, nan(""));
+    if (nl->count > 0) {  // no nulls at all -> NA (:408-419)
+        if ((rc = calc_pval_device(ctx, sorted_d.p, R, nl->area.p, nl->count, 2, p_d.p)) < 0) return fail(rc);
+        if ((rc = d2h(ctx, r->pvalues.data(), p_d.p, (size_t)R * 8)) < 0) return fail(rc);
+    }
+    if (pvalues) memcpy(pvalues, r->pvalues.data(), (size_t)R * 8);
+    *regions = r;
+    *nulls = nl;
+    return DFB_OK;
+}
+
+}  // extern "C"

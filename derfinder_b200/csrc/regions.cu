@@ -1,0 +1,725 @@
+// K3 / K4 -- threshold, run segmentation, per-region area, genomic mapping and maxGap clustering.
+//
+// Reference: findRegions (R/findRegions.R:116-296), .getSegmentsRle (:363-396, IRanges::slice with
+// inclusive bounds), .clusterMakerRle (:445-475), and the Views sum/mean of IRanges over a numeric
+// Rle (run-by-run accumulation; see view_sums in oracle/derfinder_oracle.py).
+//
+// Everything works on bit masks: one bit per kept base and row (row = observed statistic, or one
+// permutation [x side]).  A region is a maximal run of set bits that does not cross a set bit of
+// the segment-start mask SEG (segments = .clusterMakerRle(position, maxRegionGap, ranges=TRUE),
+// R/calculatePvalues.R:234-237).  Region starts are found with word-level bit tricks, counted with
+// popc, placed with a device-wide exclusive scan (= (row, index) order, the reference's order) and
+// then every region is summed left to right by one thread in IRanges' order: a run of k equal
+// adjacent values contributes value*k as ONE product (bit-exact areas).
+#include <math.h>
+
+#include <algorithm>
+
+#include "data.cuh"
+
+namespace dfb {
+
+}  // namespace dfb
+
+// ------------------------------------------------------------------------------------------
+// position index
+
+using dfb::h2d;
+using dfb::set_error;
+
+int PositionIndex::build(dfb_ctx* ctx, const int32_t* pos_len, int64_t nruns, int pos_first) {
+    len.clear();
+    first = pos_first ? 1 : 0;
+    chr_len = 0;
+    // normalise: drop zero-length runs, merge neighbours of equal value
+    int cur_val = first;
+    bool have = false;
+    int last_val = 0;
+    for (int64_t r = 0; r < nruns; ++r, cur_val ^= 1) {
+        DFB_REQUIRE(pos_len[r] >= 0, "position: negative run length");
+        if (pos_len[r] == 0) continue;
+        if (have && last_val == cur_val) {
+            DFB_REQUIRE((int64_t)len.back() + pos_len[r] <= INT32_MAX, "position run longer than 2^31-1");
+            len.back() += pos_len[r];
+        } else {
+            if (!have) first = cur_val;
+            len.push_back(pos_len[r]);
+            last_val = cur_val;
+            have = true;
+        }
+        chr_len += pos_len[r];
+    }
+    DFB_REQUIRE(chr_len <= INT32_MAX, "chromosome length %lld exceeds R's integer range", (long long)chr_len);
+    h_gstart.clear();
+    h_cum.clear();
+    int64_t gpos = 1, kept = 0;
+    int v = first;
+    for (size_t r = 0; r < len.size(); ++r, v ^= 1) {
+        if (v) {
+            h_gstart.push_back((int32_t)gpos);
+            h_cum.push_back(kept);
+            kept += len[r];
+        }
+        gpos += len[r];
+    }
+    h_cum.push_back(kept);
+    N = kept;
+    K = (int64_t)h_gstart.size();
+    DFB_TRY(run_gstart.alloc(ctx, (size_t)std::max<int64_t>(K, 1)));
+    DFB_TRY(run_cum.alloc(ctx, (size_t)K + 1));
+    DFB_TRY(h2d(ctx, run_gstart.p, h_gstart.data(), (size_t)K * sizeof(int32_t)));
+    DFB_TRY(h2d(ctx, run_cum.p, h_cum.data(), (size_t)(K + 1) * sizeof(int64_t)));
+    DFB_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors may be reallocated by the caller
+    return DFB_OK;
+}
+
+namespace dfb {
+
+// ------------------------------------------------------------------------------------------
+// segment starts: TRUE run k opens a new segment iff it is the first run or the genomic gap to
+// the previous TRUE run exceeds maxRegionGap (reduce(ir, min.gapwidth = maxGap + 1), :454).
+
+__global__ void segment_start_kernel(const int32_t* __restrict__ gstart, const int64_t* __restrict__ cum,
+                                     int64_t K, int32_t max_gap, uint32_t* __restrict__ seg) {
+    int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= K) return;
+    bool open = true;
+    if (k > 0) {
+        int64_t prev_end = (int64_t)gstart[k - 1] + (cum[k] - cum[k - 1]) - 1;
+        int64_t gap = (int64_t)gstart[k] - prev_end - 1;
+        open = gap > (int64_t)max_gap;
+    }
+    if (open) {
+        int64_t idx = cum[k];
+        atomicOr(&seg[idx >> 5], 1u << (idx & 31));
+    }
+}
+
+int build_segment_starts(dfb_ctx* ctx, const PositionIndex& pos, int32_t max_region_gap, DevBuf<uint32_t>* seg) {
+    int64_t W = ceil_div(pos.N, 32);
+    DFB_TRY(seg->alloc(ctx, (size_t)std::max<int64_t>(W, 1)));
+    DFB_TRY(seg->zero());
+    if (pos.K > 0) {
+        KTimer t(ctx, DFB_K_REGIONS);
+        segment_start_kernel<<<(unsigned)ceil_div(pos.K, 256), 256, 0, ctx->stream>>>(
+            pos.run_gstart.p, pos.run_cum.p, pos.K, max_region_gap, seg->p);
+    }
+    DFB_CUDA(cudaGetLastError());
+    return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// threshold mask of a dense vector: row 0 = x >= U ("up"), row 1 = x <= L ("dn") -- inclusive,
+// IRanges::slice defaults (R/findRegions.R:384-391).  NaN never passes.
+
+__global__ void __launch_bounds__(256) threshold_mask_kernel(const double* __restrict__ x, int64_t N, double U,
+                                                             double L, uint32_t* __restrict__ up,
+                                                             uint32_t* __restrict__ dn, int64_t W) {
+    const int lane = threadIdx.x & 31;
+    int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t w = warp; w < W; w += nwarps) {
+        const int64_t i = w * 32 + lane;
+        const double v = i < N ? x[i] : nan("");
+        const unsigned mu = __ballot_sync(0xffffffffu, v >= U);
+        const unsigned md = __ballot_sync(0xffffffffu, v <= L);
+        if (lane == 0) {
+            up[w] = mu;
+            if (dn) dn[w] = md;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// region starts per word
+
+__device__ __forceinline__ uint32_t region_starts(uint32_t m, uint32_t prev_msb, uint32_t seg) {
+    return m & (~((m << 1) | prev_msb) | seg);
+}
+
+__global__ void __launch_bounds__(256) count_starts_kernel(const uint32_t* __restrict__ mask,
+                                                           const uint32_t* __restrict__ seg, int64_t rows,
+                                                           int64_t W, uint32_t* __restrict__ counts) {
+    const int64_t total = rows * W;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t w = g % W;
+        const uint32_t m = mask[g];
+        uint32_t c = 0;
+        if (m) {
+            const uint32_t prev = w > 0 ? (mask[g - 1] >> 31) : 0u;
+            c = __popc(region_starts(m, prev, seg[w]));
+        }
+        counts[g] = c;
+    }
+}
+
+struct EmitParams {
+    const uint32_t* mask;
+    const uint32_t* seg;
+    const int64_t* offsets;  // exclusive scan of counts
+    int64_t rows, W, N;
+    int sides;  // rows per permutation (1 or 2)
+    // value source
+    const double* dense;  // [rows_dense][N] (row stride N) when not compact
+    int64_t dense_stride;
+    const int64_t* off;  // compact: [rows][tiles]
+    int64_t tiles;
+    int tile_bases;
+    const double* vals;
+    // outputs (any may be null)
+    double* area;
+    double* stat;
+    int32_t* width;
+    int32_t* istart;
+    int32_t* iend;
+    int32_t* perm;  // 1-based permutation id = row / sides + 1
+};
+
+template <bool COMPACT>
+__global__ void __launch_bounds__(128) emit_regions_kernel(const EmitParams P) {
+    const int64_t total = P.rows * P.W;
+    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
+         g += (int64_t)gridDim.x * blockDim.x) {
+        const uint32_t m = P.mask[g];
+        if (!m) continue;
+        const int64_t row = g / P.W, w = g - row * P.W;
+        const uint32_t prev = w > 0 ? (P.mask[g - 1] >> 31) : 0u;
+        const uint32_t sg = P.seg[w];
+        uint32_t starts = region_starts(m, prev, sg);
+        if (!starts) continue;
+        const uint32_t* mrow = P.mask + row * P.W;
+        int64_t out = P.offsets[g];
+        while (starts) {
+            const int b = __ffs(starts) - 1;
+            starts &= starts - 1;
+            const int64_t i = w * 32 + b;
+            // locate the first value
+            int64_t ptr = 0;
+            const double* drow = nullptr;
+            if (COMPACT) {
+                const int64_t t = i / P.tile_bases;
+                ptr = P.off[row * P.tiles + t];
+                for (int64_t ww = t * (P.tile_bases >> 5); ww < w; ++ww) ptr += __popc(mrow[ww]);
+                ptr += __popc(m & ((1u << b) - 1u));
+            } else {
+                drow = P.dense + row * P.dense_stride;
+            }
+            double cur = COMPACT ? P.vals[ptr] : drow[i];
+            double runlen = 1.0;
+            double acc = 0.0;
+            int64_t j = i + 1;
+            int64_t cw = w;
+            uint32_t cm = m, cs = sg;
+            while (j < P.N) {
+                const int64_t wj = j >> 5;
+                if (wj != cw) {
+                    cw = wj;
+                    cm = mrow[wj];
+                    cs = P.seg[wj];
+                }
+                const int bj = (int)(j & 31);
+                if (!((cm >> bj) & 1u) || ((cs >> bj) & 1u)) break;
+                double v;
+                if (COMPACT) {
+                    if (j % P.tile_bases == 0) ptr = P.off[row * P.tiles + j / P.tile_bases];
+                    else ++ptr;
+                    v = P.vals[ptr];
+                } else {
+                    v = drow[j];
+                }
+                if (v == cur) {
+                    runlen += 1.0;
+                } else {
+                    acc = __dadd_rn(acc, __dmul_rn(cur, runlen));
+                    cur = v;
+                    runlen = 1.0;
+                }
+                ++j;
+            }
+            acc = __dadd_rn(acc, __dmul_rn(cur, runlen));
+            const int32_t wd = (int32_t)(j - i);
+            if (P.area) P.area[out] = fabs(acc);
+            if (P.stat) P.stat[out] = __ddiv_rn(acc, (double)wd);
+            if (P.width) P.width[out] = wd;
+            if (P.istart) P.istart[out] = (int32_t)(i + 1);
+            if (P.iend) P.iend[out] = (int32_t)j;
+            if (P.perm) P.perm[out] = (int32_t)(row / P.sides) + 1;
+            ++out;
+        }
+    }
+}
+
+int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const uint32_t* mask, const uint32_t* seg,
+                      const double* dense, int64_t dense_stride, const PermBatch* compact, bool want_index,
+                      bool want_perm, RegionSet* out) {
+    const int64_t W = ceil_div(N, 32);
+    const int64_t total_words = rows * W;
+    out->total = 0;
+    out->row_counts.assign((size_t)rows, 0);
+    if (total_words == 0) return DFB_OK;
+    DevBuf<uint32_t> counts;
+    DevBuf<int64_t> offsets, total_dev;
+    DFB_TRY(counts.alloc(ctx, (size_t)total_words));
+    DFB_TRY(offsets.alloc(ctx, (size_t)total_words + 1));
+    DFB_TRY(total_dev.alloc(ctx, 1));
+    {
+        KTimer t(ctx, DFB_K_REGIONS);
+        count_starts_kernel<<<grid_for(total_words, 256, ctx->sm_count), 256, 0, ctx->stream>>>(mask, seg, rows, W,
+                                                                                               counts.p);
+    }
+    DFB_TRY(exclusive_scan_u32(ctx, counts.p, offsets.p, total_words, total_dev.p, DFB_K_REGIONS));
+    // per-row counts: offsets at the row starts (strided gather) + total
+    std::vector<int64_t> row_off((size_t)rows + 1);
+    DFB_CUDA(cudaMemcpy2DAsync(row_off.data(), sizeof(int64_t), offsets.p, (size_t)W * sizeof(int64_t),
+                               sizeof(int64_t), (size_t)rows, cudaMemcpyDeviceToHost, ctx->stream));
+    DFB_TRY(d2h(ctx, &row_off[(size_t)rows], total_dev.p, sizeof(int64_t)));
+    for (int64_t r = 0; r < rows; ++r) out->row_counts[(size_t)r] = row_off[(size_t)r + 1] - row_off[(size_t)r];
+    out->total = row_off[(size_t)rows];
+    if (out->total == 0) return DFB_OK;
+    DFB_REQUIRE(out->total <= INT32_MAX, "more than 2^31-1 regions");
+    DFB_TRY(out->area.alloc(ctx, (size_t)out->total));
+    DFB_TRY(out->stat.alloc(ctx, (size_t)out->total));
+    DFB_TRY(out->width.alloc(ctx, (size_t)out->total));
+    if (want_index) {
+        DFB_TRY(out->istart.alloc(ctx, (size_t)out->total));
+        DFB_TRY(out->iend.alloc(ctx, (size_t)out->total));
+    }
+    if (want_perm) DFB_TRY(out->perm.alloc(ctx, (size_t)out->total));
+    EmitParams P;
+    memset(&P, 0, sizeof P);
+    P.mask = mask;
+    P.seg = seg;
+    P.offsets = offsets.p;
+    P.rows = rows;
+    P.W = W;
+    P.N = N;
+    P.sides = sides;
+    P.dense = dense;
+    P.dense_stride = dense_stride;
+    if (compact) {
+        P.off = compact->off.p;
+        P.tiles = compact->tiles;
+        P.tile_bases = compact->tile_bases;
+        P.vals = compact->vals.p;
+    }
+    P.area = out->area.p;
+    P.stat = out->stat.p;
+    P.width = out->width.p;
+    P.istart = out->istart.p;
+    P.iend = out->iend.p;
+    P.perm = out->perm.p;
+    {
+        KTimer t(ctx, DFB_K_REGIONS);
+        const int grid = grid_for(total_words, 128, ctx->sm_count, 64);
+        if (compact) emit_regions_kernel<true><<<grid, 128, 0, ctx->stream>>>(P);
+        else emit_regions_kernel<false><<<grid, 128, 0, ctx->stream>>>(P);
+    }
+    DFB_CUDA(cudaGetLastError());
+    return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// genomic coordinates and clusters (full mode)
+
+__device__ __forceinline__ int32_t genomic_pos(const int32_t* gstart, const int64_t* cum, int64_t K, int64_t idx0) {
+    // largest k with cum[k] <= idx0
+    int64_t lo = 0, hi = K;  // cum has K+1 entries, cum[K] = N > idx0
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (cum[mid] <= idx0) lo = mid;
+        else hi = mid;
+    }
+    return (int32_t)((int64_t)gstart[lo] + (idx0 - cum[lo]));
+}
+
+__global__ void genomic_map_kernel(const int32_t* __restrict__ istart, const int32_t* __restrict__ iend, int64_t R,
+                                   const int32_t* __restrict__ gstart, const int64_t* __restrict__ cum, int64_t K,
+                                   int32_t* __restrict__ gs, int32_t* __restrict__ ge) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    gs[r] = genomic_pos(gstart, cum, K, (int64_t)istart[r] - 1);
+    ge[r] = genomic_pos(gstart, cum, K, (int64_t)iend[r] - 1);
+}
+
+// flags / widths feeding the scans
+__global__ void cluster_prep_kernel(const int32_t* __restrict__ gs, const int32_t* __restrict__ ge,
+                                    const int32_t* __restrict__ istart, const int32_t* __restrict__ iend, int64_t R,
+                                    int32_t max_cluster_gap, uint32_t* __restrict__ flag, uint32_t* __restrict__ gw,
+                                    uint32_t* __restrict__ iw) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    bool open = true;
+    if (r > 0) open = ((int64_t)gs[r] - (int64_t)ge[r - 1] - 1) > (int64_t)max_cluster_gap;
+    flag[r] = open ? 1u : 0u;
+    gw[r] = (uint32_t)(ge[r] - gs[r] + 1);
+    iw[r] = (uint32_t)(iend[r] - istart[r] + 1);
+}
+
+__global__ void cluster_prod_kernel(const int64_t* __restrict__ flag_excl, const uint32_t* __restrict__ flag,
+                                    const uint32_t* __restrict__ gw, int64_t R, int64_t* __restrict__ rc,
+                                    int64_t* __restrict__ prod) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int64_t c = flag_excl[r] + flag[r];  // id of the merged covered range holding region r
+    rc[r] = c;
+    prod[r] = c * (int64_t)gw[r];
+}
+
+// sum of the first t entries of the per-covered-base cluster-id vector
+__device__ __forceinline__ int64_t cluster_prefix(const int64_t* G, const int64_t* Phi, const int64_t* rc, int64_t R,
+                                                  int64_t gtot, int64_t t) {
+    if (t > gtot) t = gtot;
+    int64_t lo = 0, hi = R;  // largest j < R with G[j] <= t
+    while (hi - lo > 1) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (G[mid] <= t) lo = mid;
+        else hi = mid;
+    }
+    return Phi[lo] + (t - G[lo]) * rc[lo];
+}
+
+// clusterFinal = as.integer(mean(Views(cluster, IRanges(cumulative INDEX widths)))) (:259-265)
+__global__ void cluster_final_kernel(const int64_t* __restrict__ G, const int64_t* __restrict__ Phi,
+                                     const int64_t* __restrict__ rc, const int64_t* __restrict__ CW,
+                                     const uint32_t* __restrict__ iw, const int64_t* __restrict__ gtot, int64_t R,
+                                     int32_t* __restrict__ cf, uint32_t* __restrict__ gflag) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int64_t t0 = CW[r], t1 = CW[r] + (int64_t)iw[r];
+    const int64_t s = cluster_prefix(G, Phi, rc, R, *gtot, t1) - cluster_prefix(G, Phi, rc, R, *gtot, t0);
+    cf[r] = (int32_t)trunc((double)s / (double)iw[r]);
+}
+
+__global__ void cluster_gflag_kernel(const int32_t* __restrict__ cf, int64_t R, uint32_t* __restrict__ gflag) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    gflag[r] = (r == 0 || cf[r] != cf[r - 1]) ? 1u : 0u;
+}
+
+__global__ void cluster_bounds_kernel(const int32_t* __restrict__ cf, const int64_t* __restrict__ gexcl,
+                                      const uint32_t* __restrict__ gflag, int64_t R, int64_t* __restrict__ gfirst,
+                                      int64_t* __restrict__ glast) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int64_t grp = gexcl[r] + gflag[r] - 1;  // 0-based group (groups = runs of equal cf)
+    if (gflag[r]) gfirst[grp] = r;
+    if (r == R - 1 || cf[r + 1] != cf[r]) glast[grp] = r;
+}
+
+// clusterWidth[clusterFinal]: tapply result indexed by POSITION (:266-271); NaN encodes NA
+__global__ void cluster_len_kernel(const int32_t* __restrict__ cf, const int32_t* __restrict__ gs,
+                                   const int32_t* __restrict__ ge, const int64_t* __restrict__ gfirst,
+                                   const int64_t* __restrict__ glast, const int64_t* __restrict__ ngroups, int64_t R,
+                                   double* __restrict__ cl) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const int64_t c = cf[r];
+    if (c >= 1 && c <= *ngroups) cl[r] = (double)((int64_t)ge[glast[c - 1]] - (int64_t)gs[gfirst[c - 1]] + 1);
+    else cl[r] = nan("");
+}
+
+static int cluster_side(dfb_ctx* ctx, const int32_t* gs, const int32_t* ge, const int32_t* is, const int32_t* ie,
+                        int64_t R, int32_t max_cluster_gap, int32_t* cf, double* cl) {
+    if (R == 0) return DFB_OK;
+    const unsigned grid = (unsigned)ceil_div(R, 256);
+    DevBuf<uint32_t> flag, gw, iw, gflag;
+    DevBuf<int64_t> fexcl, G, rc, prod, Phi, CW, gexcl, gfirst, glast, tot;
+    DFB_TRY(flag.alloc(ctx, R));
+    DFB_TRY(gw.alloc(ctx, R));
+    DFB_TRY(iw.alloc(ctx, R));
+    DFB_TRY(gflag.alloc(ctx, R));
+    DFB_TRY(fexcl.alloc(ctx, R));
+    DFB_TRY(G.alloc(ctx, R));
+    DFB_TRY(rc.alloc(ctx, R));
+    DFB_TRY(prod.alloc(ctx, R));
+    DFB_TRY(Phi.alloc(ctx, R));
+    DFB_TRY(CW.alloc(ctx, R));
+    DFB_TRY(gexcl.alloc(ctx, R));
+    DFB_TRY(gfirst.alloc(ctx, R));
+    DFB_TRY(glast.alloc(ctx, R));
+    DFB_TRY(tot.alloc(ctx, 4));
+    ctx->launches += 6;  // the six element-wise kernels below (scans count themselves)
+    ctx->klaunch[DFB_K_REGIONS] += 6;
+    cluster_prep_kernel<<<grid, 256, 0, ctx->stream>>>(gs, ge, is, ie, R, max_cluster_gap, flag.p, gw.p, iw.p);
+    DFB_TRY(exclusive_scan_u32(ctx, flag.p, fexcl.p, R, tot.p + 0, DFB_K_REGIONS));
+    DFB_TRY(exclusive_scan_u32(ctx, gw.p, G.p, R, tot.p + 1, DFB_K_REGIONS));  // tot[1] = covered bases
+    cluster_prod_kernel<<<grid, 256, 0, ctx->stream>>>(fexcl.p, flag.p, gw.p, R, rc.p, prod.p);
+    DFB_TRY(exclusive_scan_i64(ctx, prod.p, Phi.p, R, tot.p + 2, DFB_K_REGIONS));
+    DFB_TRY(exclusive_scan_u32(ctx, iw.p, CW.p, R, tot.p + 2, DFB_K_REGIONS));
+    cluster_final_kernel<<<grid, 256, 0, ctx->stream>>>(G.p, Phi.p, rc.p, CW.p, iw.p, tot.p + 1, R, cf, gflag.p);
+    cluster_gflag_kernel<<<grid, 256, 0, ctx->stream>>>(cf, R, gflag.p);
+    DFB_TRY(exclusive_scan_u32(ctx, gflag.p, gexcl.p, R, tot.p + 3, DFB_K_REGIONS));  // tot[3] = #groups
+    cluster_bounds_kernel<<<grid, 256, 0, ctx->stream>>>(cf, gexcl.p, gflag.p, R, gfirst.p, glast.p);
+    cluster_len_kernel<<<grid, 256, 0, ctx->stream>>>(cf, gs, ge, gfirst.p, glast.p, tot.p + 3, R, cl);
+    DFB_CUDA(cudaGetLastError());
+    return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// mean(Views(v, IRanges(indexStart, indexEnd))) -- run-by-run like the areas
+
+__global__ void view_means_kernel(const double* __restrict__ v, const int32_t* __restrict__ is,
+                                  const int32_t* __restrict__ ie, int64_t R, double* __restrict__ out) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    int64_t i = (int64_t)is[r] - 1;
+    const int64_t e = ie[r];
+    double acc = 0.0;
+    double cur = v[i];
+    double runlen = 1.0;
+    for (int64_t j = i + 1; j < e; ++j) {
+        const double x = v[j];
+        if (x == cur) {
+            runlen += 1.0;
+        } else {
+            acc = __dadd_rn(acc, __dmul_rn(cur, runlen));
+            cur = x;
+            runlen = 1.0;
+        }
+    }
+    acc = __dadd_rn(acc, __dmul_rn(cur, runlen));
+    out[r] = __ddiv_rn(acc, (double)(e - i));
+}
+
+// ------------------------------------------------------------------------------------------
+// observed regions from a dense device vector
+
+int find_regions_dense(dfb_ctx* ctx, const double* x_dev, const PositionIndex& pos, double lo, double hi,
+                       int32_t max_region_gap, int32_t max_cluster_gap, bool basic, dfb_regions** out) {
+    *out = nullptr;
+    const int64_t N = pos.N;
+    if (N == 0 || pos.K == 0) return DFB_ENOREGIONS;  // warning("Found no regions") :162-165
+    const int64_t W = ceil_div(N, 32);
+    DevBuf<uint32_t> seg, mask;
+    DFB_TRY(build_segment_starts(ctx, pos, max_region_gap, &seg));
+    DFB_TRY(mask.alloc(ctx, (size_t)2 * W));
+    {
+        KTimer t(ctx, DFB_K_REGIONS);
+        threshold_mask_kernel<<<grid_for(W * 32, 256, ctx->sm_count), 256, 0, ctx->stream>>>(x_dev, N, hi, lo, mask.p,
+                                                                                           mask.p + W, W);
+    }
+    RegionSet rs;
+    // both rows read the same dense vector (stride 0)
+    DFB_TRY(find_regions_rows(ctx, N, 2, 1, mask.p, seg.p, x_dev, 0, nullptr, true, false, &rs));
+    if (rs.total == 0) return DFB_ENOREGIONS;
+    dfb_regions* r = new dfb_regions();
+    r->ctx = ctx;
+    r->R = rs.total;
+    r->R_up = rs.row_counts[0];
+    r->basic = basic;
+    const size_t R = (size_t)rs.total;
+    r->value.resize(R);
+    r->area.resize(R);
+    r->index_start.resize(R);
+    r->index_end.resize(R);
+    DevBuf<int32_t> gs, ge, cf;
+    DevBuf<double> cl;
+    if (!basic) {
+        DFB_TRY(gs.alloc(ctx, R));
+        DFB_TRY(ge.alloc(ctx, R));
+        DFB_TRY(cf.alloc(ctx, R));
+        DFB_TRY(cl.alloc(ctx, R));
+        {
+            KTimer t(ctx, DFB_K_REGIONS);
+            genomic_map_kernel<<<(unsigned)ceil_div((int64_t)R, 256), 256, 0, ctx->stream>>>(
+                rs.istart.p, rs.iend.p, (int64_t)R, pos.run_gstart.p, pos.run_cum.p, pos.K, gs.p, ge.p);
+        }
+        // clusters are computed separately for the up and the dn set (loop at :231)
+        int rc1 = cluster_side(ctx, gs.p, ge.p, rs.istart.p, rs.iend.p, r->R_up, max_cluster_gap, cf.p, cl.p);
+        int rc2 = rc1 < 0 ? rc1
+                          : cluster_side(ctx, gs.p + r->R_up, ge.p + r->R_up, rs.istart.p + r->R_up,
+                                         rs.iend.p + r->R_up, r->R - r->R_up, max_cluster_gap, cf.p + r->R_up,
+                                         cl.p + r->R_up);
+        if (rc2 < 0) {
+            delete r;
+            return rc2;
+        }
+        r->start.resize(R);
+        r->end.resize(R);
+        r->cluster.resize(R);
+        r->cluster_l.resize(R);
+        cudaMemcpyAsync(r->start.data(), gs.p, R * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(r->end.data(), ge.p, R * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(r->cluster.data(), cf.p, R * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+        cudaMemcpyAsync(r->cluster_l.data(), cl.p, R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    }
+    std::vector<int32_t> width(R);
+    cudaMemcpyAsync(r->value.data(), rs.stat.p, R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(r->area.data(), rs.area.p, R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(r->index_start.data(), rs.istart.p, R * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(r->index_end.data(), rs.iend.p, R * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        set_error("find_regions: %s", cudaGetErrorString(e));
+        delete r;
+        return DFB_ECUDA;
+    }
+    r->d_is = std::move(rs.istart);
+    r->d_ie = std::move(rs.iend);
+    *out = r;
+    return DFB_OK;
+}
+
+}  // namespace dfb
+
+using namespace dfb;
+
+extern "C" {
+
+int dfb_find_regions(dfb_ctx* ctx, const dfb_cov* cov, const double* x, double cutoff_lo, double cutoff_hi,
+                     int32_t max_region_gap, int32_t max_cluster_gap, int basic, dfb_regions** out) {
+    DFB_REQUIRE(ctx && cov && out, "dfb_find_regions: NULL argument");
+    DFB_REQUIRE(cutoff_lo <= cutoff_hi, "cutoff pair must be sorted (L <= U)");
+    *out = nullptr;
+    const double* xd = nullptr;
+    DevBuf<double> tmp;
+    if (x) {
+        DFB_TRY(tmp.alloc(ctx, (size_t)std::max<int64_t>(cov->N, 1)));
+        DFB_TRY(h2d(ctx, tmp.p, x, (size_t)cov->N * sizeof(double)));
+        xd = tmp.p;
+    } else {
+        if (!cov->has_f) {
+            set_error("dfb_find_regions: no statistics given and none cached (run dfb_fstats first)");
+            return DFB_ESTATE;
+        }
+        xd = cov->fstats.p;
+    }
+    int rc = find_regions_dense(ctx, xd, cov->pos, cutoff_lo, cutoff_hi, max_region_gap, max_cluster_gap, basic != 0,
+                                out);
+    cudaStreamSynchronize(ctx->stream);  // tmp must outlive the kernels reading it
+    return rc;
+}
+
+int dfb_find_regions_pos(dfb_ctx* ctx, const double* x, int64_t N, const int32_t* pos_len, int64_t pos_nruns,
+                         int pos_first, double cutoff_lo, double cutoff_hi, int32_t max_region_gap,
+                         int32_t max_cluster_gap, int basic, dfb_regions** out) {
+    DFB_REQUIRE(ctx && x && pos_len && out, "dfb_find_regions_pos: NULL argument");
+    DFB_REQUIRE(cutoff_lo <= cutoff_hi, "cutoff pair must be sorted (L <= U)");
+    *out = nullptr;
+    PositionIndex pos;
+    DFB_TRY(pos.build(ctx, pos_len, pos_nruns, pos_first));
+    DFB_REQUIRE(pos.N == N, "length(fstats) = %lld does not match sum(position) = %lld", (long long)N,
+                (long long)pos.N);
+    DevBuf<double> tmp;
+    DFB_TRY(tmp.alloc(ctx, (size_t)std::max<int64_t>(N, 1)));
+    DFB_TRY(h2d(ctx, tmp.p, x, (size_t)N * sizeof(double)));
+    int rc = find_regions_dense(ctx, tmp.p, pos, cutoff_lo, cutoff_hi, max_region_gap, max_cluster_gap, basic != 0,
+                                out);
+    cudaStreamSynchronize(ctx->stream);
+    return rc;
+}
+
+void dfb_regions_free(dfb_regions* r) { delete r; }
+int64_t dfb_regions_count(const dfb_regions* r) { return r ? r->R : 0; }
+int64_t dfb_regions_count_up(const dfb_regions* r) { return r ? r->R_up : 0; }
+
+int dfb_regions_get(const dfb_regions* r, int32_t* start, int32_t* end, double* value, double* area,
+                    int32_t* index_start, int32_t* index_end, int32_t* cluster, double* cluster_l) {
+    DFB_REQUIRE(r, "dfb_regions_get: NULL handle");
+    const size_t R = (size_t)r->R;
+    const bool ordered = !r->order.empty();
+    auto put = [&](auto* dst, const auto& src) {
+        if (!dst || src.size() != R) return;
+        for (size_t k = 0; k < R; ++k) dst[k] = src[ordered ? (size_t)r->order[k] : k];
+    };
+    if ((start || end || cluster || cluster_l) && r->basic) {
+        set_error("dfb_regions_get: genomic coordinates / clusters are not available in basic mode");
+        return DFB_ESTATE;
+    }
+    put(start, r->start);
+    put(end, r->end);
+    put(value, r->value);
+    put(area, r->area);
+    put(index_start, r->index_start);
+    put(index_end, r->index_end);
+    put(cluster, r->cluster);
+    put(cluster_l, r->cluster_l);
+    return DFB_OK;
+}
+
+int dfb_regions_get_order(const dfb_regions* r, int32_t* order) {
+    DFB_REQUIRE(r && order, "dfb_regions_get_order: NULL argument");
+    for (int64_t k = 0; k < r->R; ++k) order[k] = r->order.empty() ? (int32_t)k : r->order[(size_t)k];
+    return DFB_OK;
+}
+
+int dfb_regions_get_pvalues(const dfb_regions* r, double* pvalues) {
+    DFB_REQUIRE(r && pvalues, "dfb_regions_get_pvalues: NULL argument");
+    if (r->pvalues.size() != (size_t)r->R) {
+        set_error("dfb_regions_get_pvalues: p-values have not been computed for this result");
+        return DFB_ESTATE;
+    }
+    memcpy(pvalues, r->pvalues.data(), (size_t)r->R * sizeof(double));
+    return DFB_OK;
+}
+
+int dfb_regions_view_means(dfb_ctx* ctx, const dfb_regions* r, const dfb_cov* cov, int which, double* out) {
+    DFB_REQUIRE(ctx && r && cov && out, "dfb_regions_view_means: NULL argument");
+    const double* v = nullptr;
+    if (which < 0) {
+        if (!cov->has_mean) {
+            set_error("meanCoverage has not been computed (run dfb_preprocess or filter with returnMean)");
+            return DFB_ESTATE;
+        }
+        v = cov->mean.p;
+    } else {
+        DFB_REQUIRE(which < cov->G, "group %d out of range (%d groups)", which, cov->G);
+        v = cov->gmean.p + (size_t)which * cov->ld;
+    }
+    const int64_t R = r->R;
+    if (R == 0) return DFB_OK;
+    DevBuf<double> o;
+    DFB_TRY(o.alloc(ctx, (size_t)R));
+    {
+        KTimer t(ctx, DFB_K_REGIONS);
+        view_means_kernel<<<(unsigned)ceil_div(R, 128), 128, 0, ctx->stream>>>(v, r->d_is.p, r->d_ie.p, R, o.p);
+    }
+    DFB_CUDA(cudaGetLastError());
+    std::vector<double> tmp((size_t)R);
+    DFB_TRY(d2h(ctx, tmp.data(), o.p, (size_t)R * sizeof(double)));
+    const bool ordered = !r->order.empty();
+    for (int64_t k = 0; k < R; ++k) out[k] = tmp[ordered ? (size_t)r->order[(size_t)k] : (size_t)k];
+    return DFB_OK;
+}
+
+// .clusterMakerRle on run lengths (position metadata, O(#runs)); the device path uses
+// segment_start_kernel / cluster_side for the same merge rule.
+int64_t dfb_cluster_maker(const int32_t* pos_len, int64_t pos_nruns, int pos_first, int32_t max_gap, int64_t* counts,
+                          int64_t* starts, int64_t* ends, int64_t cap) {
+    if (!pos_len && pos_nruns > 0) {
+        set_error("dfb_cluster_maker: NULL run lengths");
+        return DFB_EINVAL;
+    }
+    int64_t nclus = 0, gpos = 1, prev_end = 0, csum = 0, cur = 0;
+    bool have = false;
+    int v = pos_first ? 1 : 0;
+    auto flush = [&]() {
+        if (!have) return;
+        if (nclus < cap) {
+            if (counts) counts[nclus] = cur;
+            if (starts) starts[nclus] = csum - cur + 1;
+            if (ends) ends[nclus] = csum;
+        }
+        ++nclus;
+    };
+    for (int64_t r = 0; r < pos_nruns; ++r, v ^= 1) {
+        const int64_t l = pos_len[r];
+        if (l <= 0) continue;
+        if (v) {
+            if (have && gpos - prev_end - 1 > (int64_t)max_gap) {
+                flush();
+                cur = 0;
+            }
+            have = true;
+            cur += l;
+            csum += l;
+            prev_end = gpos + l - 1;
+        }
+        gpos += l;
+    }
+    flush();
+    return nclus;
+}
+
+}  // extern "C"

@@ -1,6 +1,6 @@
 """R-compatible Mersenne-Twister `set.seed()` + `sample(n)`.
 
-TEST INFRASTRUCTURE ONLY (see oracle/README.md).  The engine never draws random numbers: the R
+Host-side helper of the Python mirror of the R glue.  The engine never draws random numbers: the R
 glue runs `set.seed(seeds[i]); sample(nSamples)` itself (reference `R/calculatePvalues.R:315-318`)
 and hands the `[B x n]` index matrix to the native library.  This module exists so the Python
 tests / benchmarks can draw *the same* permutations R would, which is what lets the golden

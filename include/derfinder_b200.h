@@ -1,0 +1,269 @@
+/*
+ * derfinder_b200 -- C ABI of the B200-native engine for derfinder's single-base F-statistic
+ * pipeline and expressed-region (ER) path.
+ *
+ * This header is the drop-in boundary.  The reference (lcolladotor/derfinder v1.35.0) is pure R
+ * and has no FFI of its own; its seam is (i) the exported R functions and (ii) the call
+ * `fstats.apply(index, data, mod, mod0, lowMemDir, scalefac, method, adjustF)` dispatched by
+ * `bplapply` (R/calculateStats.R:123-127, R/calculatePvalues.R:325-329).  Each entry point below
+ * names the reference interface it replaces; `INTEGRATION.md` shows the `.Call` stubs and the R
+ * glue that bind them under the unchanged R signatures.
+ *
+ * Conventions
+ *   - plain C: pointers + sizes, no R / torch / C++ types.  Every function returns 0 on success
+ *     or a negative DFB_E* code; `dfb_last_error()` returns the message (thread-local).
+ *   - all inputs are caller-owned and read-only; outputs go to caller-allocated buffers
+ *     ("two-call sizing": query the count, allocate, fetch).
+ *   - indices and coordinates are 1-based where the reference's are (indexStart, indexEnd,
+ *     start, end, cluster ids, permutation ids); permutation row indices `perm_idx` are 0-based
+ *     (`sample(n) - 1`).
+ *   - coverage matrices are sample-major: column s (one sample, all bases) is contiguous, like
+ *     the columns of the reference's DataFrame.
+ *   - "host" pointers are ordinary memory; functions ending in `_dev` take CUDA device pointers
+ *     on the context's device and enqueue on the context's stream without synchronising.
+ *   - there is no CPU fallback: without a CUDA device `dfb_create` fails.
+ */
+#ifndef DERFINDER_B200_H
+#define DERFINDER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DFB_VERSION 100
+
+/* error codes */
+#define DFB_OK 0
+#define DFB_EINVAL (-1)   /* bad argument (the R glue's stopifnot()/stop() cases) */
+#define DFB_ECUDA (-2)    /* CUDA runtime error */
+#define DFB_ENOMEM (-3)   /* host or device allocation failed */
+#define DFB_ESTATE (-4)   /* handle is missing a prerequisite (e.g. preprocess not run) */
+#define DFB_ENOREGIONS 1  /* not an error: nothing passed the cutoff (reference returns NULL) */
+
+/* element types of coverage values (R integer / R numeric) */
+#define DFB_I32 0
+#define DFB_F64 1
+
+/* filter kinds, R/filterData.R:89 `filter = "one" | "mean"` */
+#define DFB_FILTER_NONE 0 /* cutoff = NULL */
+#define DFB_FILTER_ONE 1
+#define DFB_FILTER_MEAN 2
+
+/* kernels whose device time the context can report (dfb_kernel_time) */
+#define DFB_K_PREP 1       /* K1 filter / expand / log2 */
+#define DFB_K_FSTAT 2      /* K2 F-stat scan (FP64 exact kernel) */
+#define DFB_K_FSTAT_TC 3   /* K2 tcgen05 screening contraction */
+#define DFB_K_REGIONS 4    /* K3/K4 segmentation, areas, clusters */
+#define DFB_K_PVAL 5       /* K5 sort + rank */
+#define DFB_K_REGMAT 6     /* K6 region x sample sums */
+#define DFB_K_COUNT 8
+
+typedef struct dfb_ctx dfb_ctx;         /* one per GPU: stream, scratch, timers            */
+typedef struct dfb_cov dfb_cov;         /* device-resident filtered coverage of ONE chromosome
+                                           (+ position, means, and after dfb_preprocess the
+                                           log2 matrix)                                      */
+typedef struct dfb_regions dfb_regions; /* device-resident result of a region search        */
+typedef struct dfb_nulls dfb_nulls;     /* device-resident null regions of a permutation run */
+
+/* ---------------------------------------------------------------- context ------------------- */
+
+const char* dfb_last_error(void);
+int dfb_version(void);
+/* number of visible CUDA devices (0 when there is no driver / GPU). */
+int dfb_device_count(void);
+/* `stream` is a cudaStream_t (or NULL: the library creates its own non-blocking stream). */
+int dfb_create(int device, void* stream, dfb_ctx** out);
+void dfb_destroy(dfb_ctx* ctx);
+int dfb_sync(dfb_ctx* ctx);
+/* Kernel launches issued by this context since creation / the last reset. */
+int64_t dfb_launch_count(dfb_ctx* ctx);
+void dfb_reset_counters(dfb_ctx* ctx);
+/* When enabled every launch of a DFB_K_* kernel family is bracketed by CUDA events on the
+ * context's stream; dfb_kernel_time synchronises and returns the summed device ms and the number
+ * of launches since the last reset. */
+int dfb_enable_timing(dfb_ctx* ctx, int on);
+int dfb_kernel_time(dfb_ctx* ctx, int kernel, double* ms, int64_t* launches);
+/* Engine knobs (all default to the fastest exact configuration):
+ *   "screen"     0/1  use the tcgen05 split-bf16 screening contraction in front of the FP64
+ *                     refinement for permutation nulls (default 1 when n fits; results are
+ *                     identical either way)
+ *   "null_capacity_mb"  initial capacity of the exceedance value buffer
+ *   "perm_batch"        permutations per launch (0 = auto) */
+int dfb_set_option(dfb_ctx* ctx, const char* key, double value);
+
+/* ---------------------------------------------------------------- coverage in --------------- */
+
+/* filterData() -- R/filterData.R:89-241.
+ * Input: n Rle columns (values[s] of `dtype`, lengths[s] int32, nruns[s]) each of total length
+ * `len` (= chromosome length, or = sum(prev_index) when a previous logical index is given as
+ * the run lengths `prev_len[0..prev_nruns)` whose first run has value `prev_first`).
+ * `mapped_per_xm` (NULL or n doubles = totalMapped/targetSize) divides each column first
+ * (:119-130); the stored coverage is then double.  filter: DFB_FILTER_*; strict `>` (:139-155).
+ * The result holds the kept rows (N x n), the final position index, and meanCoverage. */
+int dfb_filter_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values,
+                   const int32_t* const* lengths, const int64_t* nruns, int64_t len,
+                   const double* mapped_per_xm, int filter, double cutoff,
+                   const int32_t* prev_len, int64_t prev_nruns, int prev_first,
+                   dfb_cov** out);
+
+/* Already filtered coverage (what loadCoverage(cutoff=) hands to preprocessCoverage,
+ * R/preprocessCoverage.R:131-165): dense sample-major host matrix cov[s*ld + i], i < N, and the
+ * position index as run lengths over the chromosome. */
+int dfb_cov_from_dense(dfb_ctx* ctx, int n, int64_t N, int dtype, const void* cov, int64_t ld,
+                       const int32_t* pos_len, int64_t pos_nruns, int pos_first, dfb_cov** out);
+/* Same, from n Rle columns of length N (the DataFrame the R glue holds). */
+int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values,
+                     const int32_t* const* lengths, const int64_t* nruns, int64_t N,
+                     const int32_t* pos_len, int64_t pos_nruns, int pos_first, dfb_cov** out);
+/* Device-resident variant used by benchmarks: cov_dev is a device pointer, copied D2D. */
+int dfb_cov_from_dense_dev(dfb_ctx* ctx, int n, int64_t N, int dtype, const void* cov_dev,
+                           int64_t ld, const int32_t* pos_len, int64_t pos_nruns, int pos_first,
+                           dfb_cov** out);
+void dfb_cov_free(dfb_cov* cov);
+
+/* Shapes: N kept bases, n samples, chromosome length, dtype of the stored coverage, number of
+ * runs of the position index, G group-mean vectors (0 before dfb_preprocess). */
+int dfb_cov_info(const dfb_cov* cov, int64_t* N, int* n, int64_t* chr_len, int* dtype,
+                 int64_t* pos_nruns, int* n_groups, int* has_processed);
+/* position logical Rle: run lengths; *first = value of the first run (runs alternate). */
+int dfb_cov_get_position(const dfb_cov* cov, int32_t* lengths, int* first);
+/* one filtered coverage column (N values of the stored dtype) */
+int dfb_cov_get_column(const dfb_cov* cov, int sample, void* out);
+int dfb_cov_get_mean(const dfb_cov* cov, double* out);                 /* meanCoverage [N] */
+
+/* preprocessCoverage() -- R/preprocessCoverage.R:97-260 (the colsubset re-filter is a
+ * dfb_filter_rle call made by the glue first).  Computes on the device, in one pass over the
+ * filtered coverage: meanCoverage (if absent, :191-193), the G group means (:197-206;
+ * group_of_sample[s] in 0..G-1, or NULL/G=0) and Y = log2(x + scalefac) (:209-212). */
+int dfb_preprocess(dfb_ctx* ctx, dfb_cov* cov, double scalefac, const int32_t* group_of_sample,
+                   int n_groups);
+int dfb_cov_get_processed_column(const dfb_cov* cov, int sample, double* out); /* log2 column */
+int dfb_cov_get_group_mean(const dfb_cov* cov, int group, double* out);        /* [N] */
+/* chunk lengths of `mclapplyIndex` (R/preprocessCoverage.R:171-188, 218-227); chunksize <= 0
+ * means NULL -> ceiling(N / mc_cores).  Returns the number of chunks; fills lens if non-NULL. */
+int64_t dfb_chunk_lengths(int64_t N, double chunksize, int mc_cores, int64_t* lens, int64_t cap);
+
+/* ---------------------------------------------------------------- F statistics -------------- */
+
+/* calculateStats() -- R/calculateStats.R:70-132, replacing derfinderHelper::fstats.apply.
+ * mod [n x p], mod0 [n x p0] column-major doubles (R matrices).  F (N doubles) is written to
+ * `fstats_out` (host) if non-NULL and kept on the device inside `cov` for later calls.
+ * F = ((rss0-rss1)/(p-p0)) / (adjustF + rss1/(n-p))  (tests/testthat/test_Fstats.R:52-63). */
+int dfb_fstats(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const double* mod0, int p0,
+               double adjust_f, double* fstats_out);
+/* Orthonormal nested basis the engine uses for (mod0, mod): q is [n x p] column-major, first p0
+ * columns span mod0.  *centered = 1 when the constant vector lies in span(mod0) and rows are
+ * mean-centred before the contraction.  Exposed for the parity tests. */
+int dfb_model_basis(const double* mod, int n, int p, const double* mod0, int p0, double* q,
+                    int* centered);
+
+/* ---------------------------------------------------------------- regions ------------------- */
+
+/* findRegions() -- R/findRegions.R:116-296 (smooth=FALSE) incl. .getSegmentsRle (:363-396) and
+ * .clusterMakerRle (:445-475).  `x` are N host doubles (F-stats or meanCoverage) or NULL to use
+ * the F-stats cached in `cov` by dfb_fstats; position comes from `cov`.  cutoff_lo/cutoff_hi are
+ * the sorted pair (L, U); a scalar cutoff c is passed as (-c, c) (:377-381).
+ * basic != 0 returns only area/width/stat rows (:273-278).
+ * Returns DFB_ENOREGIONS (and *out = NULL) when nothing passes. */
+int dfb_find_regions(dfb_ctx* ctx, const dfb_cov* cov, const double* x, double cutoff_lo,
+                     double cutoff_hi, int32_t max_region_gap, int32_t max_cluster_gap, int basic,
+                     dfb_regions** out);
+/* Position-only variant (no coverage handle): x has N = number of TRUE positions. */
+int dfb_find_regions_pos(dfb_ctx* ctx, const double* x, int64_t N, const int32_t* pos_len,
+                         int64_t pos_nruns, int pos_first, double cutoff_lo, double cutoff_hi,
+                         int32_t max_region_gap, int32_t max_cluster_gap, int basic,
+                         dfb_regions** out);
+void dfb_regions_free(dfb_regions* r);
+int64_t dfb_regions_count(const dfb_regions* r);
+int64_t dfb_regions_count_up(const dfb_regions* r); /* rows named "up"; the rest are "dn" */
+/* Any output pointer may be NULL.  start/end genomic (full mode only), value = mean, area =
+ * |sum|, cluster ids, clusterL (NaN encodes R's NA).  Rows: all "up" then all "dn" (:292). */
+int dfb_regions_get(const dfb_regions* r, int32_t* start, int32_t* end, double* value,
+                    double* area, int32_t* index_start, int32_t* index_end, int32_t* cluster,
+                    double* cluster_l);
+/* mean(Views(v, IRanges(indexStart, indexEnd))) for a host vector v[N] -- R/calculatePvalues.R:
+ * 253-262 (meanCoverage / group means per region). which: -1 = cov meanCoverage, g>=0 = group g */
+int dfb_regions_view_means(dfb_ctx* ctx, const dfb_regions* r, const dfb_cov* cov, int which,
+                           double* out);
+
+/* .clusterMakerRle() -- R/findRegions.R:445-475 on a logical Rle given as run lengths.
+ * ranges = 0: fills ids[k] = k+1 and counts[k] (the integer Rle); ranges = 1: fills
+ * starts/ends (index space).  Returns the number of clusters; pass NULL outputs to size. */
+int64_t dfb_cluster_maker(const int32_t* pos_len, int64_t pos_nruns, int pos_first, int32_t max_gap,
+                          int64_t* counts, int64_t* starts, int64_t* ends, int64_t cap);
+
+/* ---------------------------------------------------------------- permutation nulls --------- */
+
+/* The permutation loop of calculatePvalues() -- R/calculatePvalues.R:306-358.
+ * perm_idx [B x n] row-major, 0-based: row b is `sample(nSamples) - 1` drawn by the R glue under
+ * `set.seed(seeds[b])` (:315-318).  For every permutation the engine computes the F-stats of
+ * the row-permuted models, thresholds them, finds the candidate regions (basic=TRUE) inside the
+ * position segments and keeps {stat, width, area, permutation}.  Null F-stats never touch HBM
+ * beyond a bit mask and the exceedance values. */
+int dfb_perm_nulls(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const double* mod0,
+                   int p0, double adjust_f, const int32_t* perm_idx, int64_t B, double cutoff_lo,
+                   double cutoff_hi, int32_t max_region_gap, dfb_nulls** out);
+void dfb_nulls_free(dfb_nulls* nl);
+/* number of DISTINCT null regions (the reference stores each twice, :346-354; see dup below) */
+int64_t dfb_nulls_count(const dfb_nulls* nl);
+/* per-permutation region counts [B] */
+int dfb_nulls_counts_per_perm(const dfb_nulls* nl, int64_t* counts);
+/* dup = 0: each region once, ordered by (permutation, up/dn, index).
+ * dup = 1: the reference's layout, 2*count rows: per permutation [r1..rk, r1..rk]. */
+int dfb_nulls_get(const dfb_nulls* nl, int dup, double* stat, int32_t* width, double* area,
+                  int32_t* permutation);
+/* device access for multi-GPU pooling (areas as doubles, permutation ids as int32) */
+int dfb_nulls_copy_dev(const dfb_nulls* nl, double* area_dev, int32_t* perm_dev);
+
+/* ---------------------------------------------------------------- p-values ------------------ */
+
+/* .calcPval() -- R/calculatePvalues.R:432-441.  weight = multiplicity of every null entry
+ * (2 reproduces the duplicated null list): p = (weight*#{null > a*} + 1) / (weight*M + 1) with
+ * a* the largest null <= area (all nulls when none is). */
+int dfb_calc_pval(dfb_ctx* ctx, const double* areas, int64_t R, const double* nullareas,
+                  int64_t M, int weight, double* pvalues);
+int dfb_calc_pval_dev(dfb_ctx* ctx, const double* areas_dev, int64_t R, double* nullareas_dev,
+                      int64_t M, int weight, double* pvalues_dev);
+/* .calculateFWER() -- R/mergeResults.R:380-386. permutation ids 1..B. */
+int dfb_calc_fwer(dfb_ctx* ctx, double cutoff_used, const double* nullareas,
+                  const int32_t* permutation, int64_t M, int64_t B, const double* areas, int64_t R,
+                  double* fwer);
+/* per-permutation maxima [B] on the device (input to an all-reduce(max) across GPUs) */
+int dfb_perm_max_dev(dfb_ctx* ctx, const double* nullareas_dev, const int32_t* perm_dev, int64_t M,
+                     int64_t B, double fill, double* max_dev);
+/* quantile(x, prob, na.rm=TRUE), R type 7 -- default cutoff of findRegions/calculatePvalues
+ * (R/findRegions.R:118, R/analyzeChr.R:318).  x = NULL uses the cached F-stats of cov. */
+int dfb_quantile(dfb_ctx* ctx, const dfb_cov* cov, const double* x, int64_t N, double prob,
+                 double* out);
+
+/* calculatePvalues() end to end -- R/calculatePvalues.R:157-430 minus qvalue():
+ * observed regions (full mode) sorted by decreasing area (stable, :368), their meanCoverage /
+ * group means, null regions, p-values.  Returns DFB_ENOREGIONS when no observed region. */
+int dfb_calculate_pvalues(dfb_ctx* ctx, dfb_cov* cov, const double* fstats, const double* mod,
+                          int p, const double* mod0, int p0, double adjust_f,
+                          const int32_t* perm_idx, int64_t B, double cutoff_lo, double cutoff_hi,
+                          int32_t max_region_gap, int32_t max_cluster_gap, dfb_regions** regions,
+                          dfb_nulls** nulls, double* pvalues /* [R], may be NULL: fetch later */);
+int dfb_regions_get_pvalues(const dfb_regions* r, double* pvalues);
+/* row order applied by dfb_calculate_pvalues (0-based indices into the up-then-dn order) */
+int dfb_regions_get_order(const dfb_regions* r, int32_t* order);
+
+/* ---------------------------------------------------------------- ER path ------------------- */
+
+/* coverageMatrix of regionMatrix() -- R/regionMatrix.R:252-270 with getRegionCoverage
+ * (R/getRegionCoverage.R:135-160): out[r + R*s] = sum of rows indexStart..indexEnd of column s.
+ * The division by L (scalar, or the reference's last-column-only vector quirk :267) is applied
+ * when L != NULL (n_l = 1 or n). Column-major [R x n] like an R matrix. */
+int dfb_region_matrix(dfb_ctx* ctx, const dfb_cov* cov, const int32_t* index_start,
+                      const int32_t* index_end, int64_t R, const double* L, int n_l, double* out);
+/* same, regions taken from a dfb_regions result (stays on the device until the final copy) */
+int dfb_region_matrix_r(dfb_ctx* ctx, const dfb_cov* cov, const dfb_regions* r, const double* L,
+                        int n_l, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DERFINDER_B200_H */

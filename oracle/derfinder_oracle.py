@@ -175,6 +175,15 @@ def chunk_lengths(numrow: int, chunksize, mc_cores: int = 1):
     return out
 
 
+def log2_libm(x):
+    """log2 through the C library (what R's log2() calls), not numpy's SIMD kernel, which can differ
+    from glibc in the last bit."""
+    x = np.asarray(x, dtype=np.float64)
+    u, inv = np.unique(x, return_inverse=True)
+    lut = np.array([math.log2(v) if v > 0 else (-np.inf if v == 0 else np.nan) for v in u.tolist()])
+    return lut[inv].reshape(x.shape)
+
+
 def preprocess_coverage(coverage, position, groupInfo=None, scalefac=32, chunksize=5e6,
                         meanCoverage=None, mc_cores=1):
     """coverage [N x n] (already filtered), position Rle.  Returns dict with the 5 reference names.
@@ -193,7 +202,7 @@ def preprocess_coverage(coverage, position, groupInfo=None, scalefac=32, chunksi
         for lev in sorted(set(g.tolist())):
             sel = np.flatnonzero(g == lev)
             groupMeans[lev] = _ordered_row_sum(cov[:, sel].T) / len(sel)
-    Y = np.log2(cov.astype(np.float64) + scalefac)  # :209-212
+    Y = log2_libm(cov.astype(np.float64) + scalefac)  # :209-212
     return dict(coverageProcessed=Y, mclapplyIndex=chunk_lengths(N, chunksize, mc_cores),
                 position=position, meanCoverage=means, groupMeans=groupMeans)
 
@@ -240,8 +249,12 @@ def quantile_type7(x, prob):
     x = np.sort(np.asarray(x, dtype=np.float64)[~np.isnan(x)])
     h = (len(x) - 1) * prob
     lo = int(math.floor(h))
-    hi = min(lo + 1, len(x) - 1)
-    return x[lo] + (h - lo) * (x[hi] - x[lo])
+    hi = int(math.ceil(h))
+    qs = x[lo]
+    if h > lo and x[hi] != qs:  # stats:::quantile.default, type 7
+        g = h - lo
+        qs = (1 - g) * qs + g * x[hi]
+    return qs
 
 
 def calc_fstat_cutoff(cutoffType, cutoffFstat, fstats=None, mod=None, mod0=None):
@@ -328,6 +341,9 @@ def view_sums(x, starts, ends):
     reading of the IRanges C loop and reproduces the golden areas to 7e-12 (the residual being
     F-stat rounding).  The engine implements exactly this order."""
     x = np.asarray(x, dtype=np.float64)
+    if len(starts) > 2000:  # same loop in C (oracle/fstat_oracle.c::oc_view_sums) for the larger cases
+        from . import c_oracle
+        return c_oracle.view_sums(x, starts, ends)
     out = np.zeros(len(starts), dtype=np.float64)
     vals, lens = rle_encode(x)
     run_end = np.cumsum(lens)  # 1-based inclusive end of each run
@@ -476,7 +492,7 @@ def calculate_fwer(cutoffFstatUsed, areaNull, permutation, nPermute, areaReg):
 
 
 def calculate_pvalues(prep, mod, mod0, fstats, perm_idx, cutoff, maxRegionGap=0, maxClusterGap=300,
-                      adjustF=0.0, significantCut=(0.05, 0.1), fstat_fn=None):
+                      adjustF=0.0, significantCut=(0.05, 0.1), fstat_fn=None, fstat_idx_fn=None):
     """perm_idx: [B x n] 0-based permutation rows (== `sample(n) - 1` per seed).  qvalue() is a
     third-party spline fit that stays in R and is not restated.  `fstat_fn(Y, mod, mod0, adjustF)`
     lets tests swap the F-stat formulation (default: the projector definition)."""
@@ -500,7 +516,10 @@ def calculate_pvalues(prep, mod, mod0, fstats, perm_idx, cutoff, maxRegionGap=0,
             regs[f"log2FoldChange{g}vs{names[0]}"] = np.log2(gm[g] / gm[names[0]])
     nstat, nwidth, narea, nperm = [], [], [], []
     for i, idx in enumerate(np.asarray(perm_idx)):  # :306-358
-        f_b = fstat_fn(Y, mod[idx, :], mod0[idx, :], adjustF)
+        if fstat_idx_fn is not None:  # formulation that takes the row permutation itself
+            f_b = fstat_idx_fn(Y, idx)
+        else:
+            f_b = fstat_fn(Y, mod[idx, :], mod0[idx, :], adjustF)
         rp = find_regions(None, f_b, cutoff, segmentIR=segmentIR, basic=True)
         if rp is not None:
             for _ in range(2):  # stored twice (:346-354)

@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 
 from oracle import derfinder_oracle as O
-from oracle.rrng import RRandom, permutation_indices
+from derfinder_b200.rrng import RRandom, permutation_indices
 
 
 def test_models_rebuilt_from_coverage(golden):
