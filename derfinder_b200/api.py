@@ -21,6 +21,7 @@ from __future__ import annotations
 import ctypes as C
 import time
 import warnings
+import weakref
 
 import numpy as np
 
@@ -44,8 +45,11 @@ class Engine:
         h = C.c_void_p()
         L.check(lib.dfb_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
         self.lib, self.h, self.device = lib, h, device
+        self._covs = weakref.WeakSet()  # live Coverage handles: released before the context goes
 
     def close(self):
+        for cov in list(getattr(self, "_covs", ())):
+            cov.free()
         if getattr(self, "h", None):
             self.lib.dfb_destroy(self.h)
             self.h = None
@@ -147,11 +151,14 @@ class Coverage:
         self.N, self.n, self.chr_len, self.dtype = N.value, n.value, clen.value, dt.value
         self._npr = npr.value
         self.names = list(names) if names is not None else [f"V{i + 1}" for i in range(self.n)]
+        engine._covs.add(self)
 
     def free(self):
-        if self.h:
+        # a handle must not outlive its context: once the engine is closed the device memory has
+        # gone with the stream's pool and the handle is simply dropped
+        if self.h and getattr(self.engine, "h", None):
             self.engine.lib.dfb_cov_free(self.h)
-            self.h = None
+        self.h = None
 
     def __del__(self):
         try:

@@ -70,17 +70,38 @@ int build_model_basis(const double* mod, int n, int p, const double* mod0, int p
         for (auto& x : v) x /= nrm;
         basis.push_back(std::move(v));
     }
-    DFB_REQUIRE((int)basis.size() == p,
-                "models$mod is rank deficient or does not contain span(models$mod0) (rank %d, expected %d)",
-                (int)basis.size(), p);
-    // every column of mod must lie in the span (mod0 nested in mod)
-    for (int j = 0; j < p; ++j) {
-        std::vector<double> v(mod + (size_t)j * n, mod + (size_t)(j + 1) * n);
-        double nrm0 = sqrt(dot(v.data(), v.data(), n));
-        orth(v);
-        double nrm = sqrt(dot(v.data(), v.data(), n));
-        DFB_REQUIRE(nrm <= 1e-7 * (nrm0 > 0 ? nrm0 : 1), "models$mod0 is not nested in models$mod");
+    // rank of mod on its own (R's solve(t(mod) %*% mod) fails when deficient) and nestedness:
+    // every column of mod0 must lie in span(mod)
+    {
+        std::vector<std::vector<double>> qm;
+        auto orth_m = [&](std::vector<double>& v) {
+            for (int pass = 0; pass < 2; ++pass)
+                for (auto& q : qm) {
+                    double c = dot(q.data(), v.data(), n);
+                    for (int i = 0; i < n; ++i) v[i] -= c * q[i];
+                }
+        };
+        for (int j = 0; j < p; ++j) {
+            std::vector<double> v(mod + (size_t)j * n, mod + (size_t)(j + 1) * n);
+            double nrm0 = sqrt(dot(v.data(), v.data(), n));
+            orth_m(v);
+            double nrm = sqrt(dot(v.data(), v.data(), n));
+            DFB_REQUIRE(nrm0 > 0 && nrm > tol * nrm0,
+                        "models$mod is rank deficient (column %d); R's solve(t(mod) %%*%% mod) would fail", j + 1);
+            for (auto& x : v) x /= nrm;
+            qm.push_back(std::move(v));
+        }
+        for (int j = 0; j < p0; ++j) {
+            std::vector<double> v(mod0 + (size_t)j * n, mod0 + (size_t)(j + 1) * n);
+            double nrm0 = sqrt(dot(v.data(), v.data(), n));
+            orth_m(v);
+            double nrm = sqrt(dot(v.data(), v.data(), n));
+            DFB_REQUIRE(nrm <= 1e-7 * nrm0, "models$mod0 is not nested in models$mod (column %d of mod0 is outside "
+                        "span(mod)); the engine's F-statistic needs nested models", j + 1);
+        }
     }
+    DFB_REQUIRE((int)basis.size() == p, "internal error: nested basis has %d columns, expected %d", (int)basis.size(),
+                p);
     out->n = n;
     out->p = p;
     out->p0 = p0;
