@@ -1,0 +1,522 @@
+#!/usr/bin/env python
+"""bench.py -- the derfinder F-stat / region p-value hot path on N B200s (one process per GPU).
+
+    python bench.py --gpus 1 --steps K --warmup W            # our CUDA engine
+    python bench.py --impl reference --steps K --warmup W    # the reference's algorithm on host cores
+
+Metric (BASELINE.json): base x permutation F-stats per second = N * (B + 1) / t, where one "step"
+is one full pass of the hot path over one synthetic chromosome:
+    preprocessCoverage (means + log2(x+32))  ->  calculateStats (observed F)
+    ->  calculatePvalues (B permuted-model F scans, thresholding, null regions/areas,
+        observed regions + clusters, null-area sort, exact p-values)
+`value` times it with the filtered coverage already resident in HBM; `e2e` times the same pass
+through the reference-facing calls with HOST buffers (H2D of the coverage, D2H of F-stats, regions,
+nulls and p-values inside the timed region).
+
+Workload: BASELINE.json configs[1] -- synthetic chr21 (Lc = 48,129,895; ~10% of bases pass the
+filter), 12 samples, 2-group model + sampleDepth (p = 3, p0 = 2), 100 permutations, F cutoff
+qf(0.05, 1, 9).  Multi-GPU (torchrun): every rank owns a different synthetic chromosome of the same
+size (weak scaling, chromosome sharding); the only exchange is the pooling of null areas
+(all-gather) and per-permutation maxima (all-reduce max) before the genome-wide p-value / FWER
+ranking (R/mergeResults.R:216-235, 304-307, 380-386).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (chr_len, N kept bases, n samples, adjustment covariates, B permutations, cutoff p)
+    "c2": dict(chr_len=48_129_895, N=4_800_000, n=12, extra=0, B=100, alpha=0.05,
+               label="synthetic chr21 (48.1 Mbp, N=4.8M kept bases) 12 samples, 2-group model, 100 permutations"),
+    "c3": dict(chr_len=249_250_621, N=25_000_000, n=60, extra=3, B=1000, alpha=1e-6,
+               label="synthetic chr1 (249 Mbp, N=25M kept bases) 60 samples, 3 adjustment covariates, 1000 permutations"),
+    "tiny": dict(chr_len=2_000_000, N=200_000, n=12, extra=0, B=20, alpha=0.05,
+                 label="tiny debug workload"),
+}
+
+
+# ---------------------------------------------------------------------------------------------
+# synthetic coverage (post-filter, like BASELINE.md's C4): expressed islands, piecewise-constant
+# per-sample runs (read-length-like), Poisson counts, 5% of islands carry a 2x group effect
+
+
+def island_layout(rng, chr_len, N):
+    """island lengths (geometric, mean 200 bp) summing to N and the gaps between them."""
+    lens = rng.geometric(1.0 / 200.0, size=int(N / 200 * 1.2) + 16)
+    cs = np.cumsum(lens)
+    k = int(np.searchsorted(cs, N))
+    lens = lens[: k + 1].copy()
+    lens[-1] -= cs[k] - N
+    lens = lens[lens > 0]
+    gaps = rng.geometric(len(lens) / max(chr_len - N, len(lens)), size=len(lens)) + 1
+    scale = (chr_len - N) / gaps.sum()
+    gaps = np.maximum(1, np.floor(gaps * scale)).astype(np.int64)
+    gaps[-1] += chr_len - N - gaps.sum() if gaps.sum() < chr_len - N else 0
+    return lens.astype(np.int64), gaps
+
+
+def position_runs(lens, gaps, chr_len):
+    """logical Rle: FALSE gap, TRUE island, ...; trailing FALSE to reach chr_len."""
+    runs = np.empty(2 * len(lens), dtype=np.int64)
+    runs[0::2] = gaps
+    runs[1::2] = lens
+    tail = chr_len - runs.sum()
+    if tail > 0:
+        runs = np.concatenate((runs, [tail]))
+    else:
+        runs[0] += tail  # shrink the first gap if rounding overshot
+    return runs.astype(np.int32), 0
+
+
+def make_workload(cfg, seed, torch=None, device=None):
+    """Returns dict(cov [n x N] int32 (torch cuda tensor or numpy), pos_len, pos_first, models, group)."""
+    rng = np.random.default_rng(seed)
+    N, n = cfg["N"], cfg["n"]
+    lens, gaps = island_layout(rng, cfg["chr_len"], N)
+    pos_len, pos_first = position_runs(lens, gaps, cfg["chr_len"])
+    nisl = len(lens)
+    log_expr = rng.normal(3.0, 1.5, size=nisl).clip(-1, 8)
+    effect = np.where(rng.random(nisl) < 0.05, 2.0, 1.0)
+    depth = rng.uniform(0.6, 1.6, size=n)
+    group = np.array([0] * (n // 2) + [1] * (n - n // 2))
+    runlen = rng.integers(36, 77, size=n)
+    offs = rng.integers(0, 76, size=n)
+    if torch is not None:
+        dev = device
+        isl = torch.repeat_interleave(torch.arange(nisl, device=dev), torch.as_tensor(lens, device=dev))
+        lam = torch.as_tensor(np.exp(log_expr), device=dev, dtype=torch.float32)[isl]
+        eff = torch.as_tensor(effect, device=dev, dtype=torch.float32)[isl]
+        base = torch.arange(N, device=dev)
+        g = torch.Generator(device=dev)
+        g.manual_seed(seed)
+        cov = torch.empty((n, N), dtype=torch.int32, device=dev)
+        for s in range(n):
+            first = ((base + int(offs[s])) // int(runlen[s])) * int(runlen[s]) - int(offs[s])
+            first = first.clamp_(min=0)
+            # a run never crosses an island boundary: restart at the island's first base
+            rate = lam[first] * float(depth[s]) * (eff[first] if group[s] == 1 else 1.0)
+            same = isl[first] == isl
+            rate = torch.where(same, rate, lam * float(depth[s]))
+            draw = torch.poisson(rate, generator=g)
+            val = draw[first]
+            val = torch.where(same, val, draw)
+            cov[s] = val.to(torch.int32)
+        depth_cov = torch.log2(cov.sum(dim=1).double() + 32.0).cpu().numpy()
+    else:
+        isl = np.repeat(np.arange(nisl), lens)
+        lam, eff = np.exp(log_expr)[isl], effect[isl]
+        base = np.arange(N)
+        cov = np.empty((n, N), dtype=np.int32)
+        for s in range(n):
+            first = np.maximum(((base + offs[s]) // runlen[s]) * runlen[s] - offs[s], 0)
+            same = isl[first] == isl
+            rate = np.where(same, lam[first] * depth[s] * np.where(group[s] == 1, eff[first], 1.0), lam * depth[s])
+            draw = rng.poisson(rate)
+            cov[s] = np.where(same, draw[first], draw)
+        depth_cov = np.log2(cov.sum(axis=1).astype(np.float64) + 32.0)
+    cols = [np.ones(n), group.astype(np.float64), depth_cov]
+    cols += [rng.normal(size=n) for _ in range(cfg["extra"])]
+    mod = np.column_stack(cols)
+    mod0 = mod[:, [0] + list(range(2, mod.shape[1]))]
+    return dict(cov=cov, pos_len=pos_len, pos_first=pos_first, mod=np.asfortranarray(mod),
+                mod0=np.asfortranarray(mod0), group=group)
+
+
+def theoretical_cutoff(alpha, mod, mod0):
+    from scipy.stats import f as fdist
+    n, p, p0 = mod.shape[0], mod.shape[1], mod0.shape[1]
+    return float(fdist.isf(alpha, p - p0, n - p))
+
+
+# ---------------------------------------------------------------------------------------------
+# clocks sampler (NVML) -- runs DURING the timed region
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag = index, [], set(), False
+        self.max_mhz = None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            names = {
+                getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+                getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            }
+            while not self.stop_flag:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for bit, nm in names.items():
+                    if r & bit:
+                        self.reasons.add(nm)
+                time.sleep(0.02)
+        except Exception as e:  # NVML missing: report that instead of inventing clocks
+            self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
+
+    def result(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(s)}
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline: the reference's algorithm shape on host cores (numpy/OpenBLAS port, "kind: port")
+
+
+def cpu_reference_pass(cov_nN, pos_len, pos_first, mod, mod0, perm, cutoff):
+    """One pass of the same hot path the way the reference does it: log2 transform, per 1e5-row
+    chunk dense residual-projector products Y %*% P1, Y %*% P0 (BLAS), rowSums, F; serial
+    permutation loop; run segmentation + Rle view sums; .calcPval.  Returns #regions (sanity)."""
+    from oracle import derfinder_oracle as O
+    vals = (np.arange(len(pos_len)) % 2 == 0) == bool(pos_first)
+    position = (vals, pos_len.astype(np.int64))
+    prep = O.preprocess_coverage(np.ascontiguousarray(cov_nN.T), position, chunksize=1e5)
+    F = O.calculate_stats(prep, mod, mod0)
+    res = O.calculate_pvalues(prep, mod, mod0, F, perm, cutoff)
+    return 0 if res["regions"] is None else len(res["regions"]["start"])
+
+
+def cpu_sample(work, cfg, perm, cutoff, n_bases, n_perm):
+    cov = work["cov"]
+    cov = cov[:, :n_bases].cpu().numpy() if hasattr(cov, "cpu") else cov[:, :n_bases]
+    # position restricted to the first n_bases kept bases
+    pl = work["pos_len"].astype(np.int64)
+    vals = (np.arange(len(pl)) % 2 == 0) == bool(work["pos_first"])
+    kept = np.cumsum(np.where(vals, pl, 0))
+    k = int(np.searchsorted(kept, n_bases))
+    pl2 = pl[: k + 1].copy()
+    pl2[k] -= kept[k] - n_bases
+    return cov, pl2.astype(np.int32), work["pos_first"], perm[:n_perm]
+
+
+def run_reference_arm(args, cfg):
+    """`--impl reference`: the reference's CPU implementation of the path (numpy port; R is not in
+    this image) with all host threads OpenBLAS can use, on a bounded sample of the same workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from derfinder_b200.rrng import permutation_indices
+    work = make_workload(cfg, 20140923 + 2)
+    perm_all = permutation_indices(range(1, cfg["B"] + 1), cfg["n"], "Rejection")
+    cutoff = theoretical_cutoff(cfg["alpha"], work["mod"], work["mod0"])
+    nb, npm = min(cfg["N"], args.cpu_bases), min(cfg["B"], args.cpu_perms)
+    cov, pl, pf, perm = cpu_sample(work, cfg, perm_all, cutoff, nb, npm)
+    for _ in range(args.warmup):
+        cpu_reference_pass(cov[:, : nb // 10], *cpu_sample(work, cfg, perm_all, cutoff, nb // 10, 2)[1:3], work["mod"],
+                           work["mod0"], perm[:2], cutoff)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_pass(cov, pl, pf, work["mod"], work["mod0"], perm, cutoff)
+    dt = (time.perf_counter() - t0) / args.steps
+    value = nb * (npm + 1) / dt
+    cores = os.cpu_count()
+    sample = f"first {nb} kept bases x {npm} permutations of the workload per step (numpy/OpenBLAS, chunksize 1e5)"
+    line = {"impl": "reference", "metric": "base_x_permutation_fstats_per_sec", "value": value,
+            "unit": "base*perm F-stats/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": cfg["label"], "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "base*perm F-stats/s", "cores": cores, "kind": "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": "base*perm F-stats/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------
+# our arm
+
+
+class Step:
+    """The hot path through the C ABI (ctypes).  Device-resident and host-buffer variants."""
+
+    def __init__(self, eng, work, perm, cutoff, torch):
+        from derfinder_b200 import _lib as L
+        self.L, self.eng, self.lib, self.torch = L, eng, eng.lib, torch
+        self.work, self.perm, self.cut = work, np.ascontiguousarray(perm, dtype=np.int32), cutoff
+        self.n, self.N = work["cov"].shape
+        self.mod, self.mod0 = work["mod"], work["mod0"]
+        self.pl = np.ascontiguousarray(work["pos_len"], dtype=np.int32)
+
+    def _fp(self, a):
+        return a.ctypes.data_as(self.L.c_f64p)
+
+    def device_pass(self, keep=False):
+        L, lib, eng = self.L, self.lib, self.eng
+        cov = C.c_void_p()
+        L.check(lib.dfb_cov_from_dense_dev(eng.h, self.n, self.N, L.DFB_I32, C.c_void_p(self.work["cov"].data_ptr()),
+                                           self.N, L.ptr(self.pl, C.c_int32), len(self.pl), self.work["pos_first"],
+                                           C.byref(cov)))
+        try:
+            L.check(lib.dfb_preprocess(eng.h, cov, 32.0, None, 0))
+            L.check(lib.dfb_fstats(eng.h, cov, self._fp(self.mod), self.mod.shape[1], self._fp(self.mod0),
+                                   self.mod0.shape[1], 0.0, None))
+            rh, nh = C.c_void_p(), C.c_void_p()
+            rc = L.check(lib.dfb_calculate_pvalues(eng.h, cov, None, self._fp(self.mod), self.mod.shape[1],
+                                                   self._fp(self.mod0), self.mod0.shape[1], 0.0,
+                                                   L.ptr(self.perm, C.c_int32), self.perm.shape[0], -self.cut, self.cut,
+                                                   0, 3000, C.byref(rh), C.byref(nh), None))
+            out = (int(lib.dfb_regions_count(rh)) if rc == 0 else 0, int(lib.dfb_nulls_count(nh)) if rc == 0 else 0)
+            if keep and rc == 0:
+                return out, rh, nh, cov
+            if rc == 0:
+                lib.dfb_regions_free(rh)
+                lib.dfb_nulls_free(nh)
+            return out
+        finally:
+            if not keep:
+                lib.dfb_cov_free(cov)
+
+    def host_pass(self, host_cov):
+        """Reference-facing calls with host buffers: upload coverage, download everything a
+        calculatePvalues() caller receives."""
+        L, lib, eng = self.L, self.lib, self.eng
+        cov = C.c_void_p()
+        L.check(lib.dfb_cov_from_dense(eng.h, self.n, self.N, L.DFB_I32, host_cov.ctypes.data_as(C.c_void_p), self.N,
+                                       L.ptr(self.pl, C.c_int32), len(self.pl), self.work["pos_first"], C.byref(cov)))
+        d2h = 0
+        try:
+            L.check(lib.dfb_preprocess(eng.h, cov, 32.0, None, 0))
+            F = np.empty(self.N)
+            L.check(lib.dfb_fstats(eng.h, cov, self._fp(self.mod), self.mod.shape[1], self._fp(self.mod0),
+                                   self.mod0.shape[1], 0.0, self._fp(F)))
+            d2h += F.nbytes
+            rh, nh = C.c_void_p(), C.c_void_p()
+            rc = L.check(lib.dfb_calculate_pvalues(eng.h, cov, self._fp(F), self._fp(self.mod), self.mod.shape[1],
+                                                   self._fp(self.mod0), self.mod0.shape[1], 0.0,
+                                                   L.ptr(self.perm, C.c_int32), self.perm.shape[0], -self.cut, self.cut,
+                                                   0, 3000, C.byref(rh), C.byref(nh), None))
+            if rc == 0:
+                R, M = int(lib.dfb_regions_count(rh)), int(lib.dfb_nulls_count(nh))
+                st, en, ist, ien, cl = (np.empty(R, dtype=np.int32) for _ in range(5))
+                val, area, cll, pv, mc = (np.empty(R) for _ in range(5))
+                L.check(lib.dfb_regions_get(rh, L.ptr(st, C.c_int32), L.ptr(en, C.c_int32), self._fp(val),
+                                            self._fp(area), L.ptr(ist, C.c_int32), L.ptr(ien, C.c_int32),
+                                            L.ptr(cl, C.c_int32), self._fp(cll)))
+                L.check(lib.dfb_regions_get_pvalues(rh, self._fp(pv)))
+                L.check(lib.dfb_regions_view_means(eng.h, rh, cov, -1, self._fp(mc)))
+                ns, na = np.empty(2 * M), np.empty(2 * M)
+                nw, npid = np.empty(2 * M, dtype=np.int32), np.empty(2 * M, dtype=np.int32)
+                L.check(lib.dfb_nulls_get(nh, 1, self._fp(ns), L.ptr(nw, C.c_int32), self._fp(na),
+                                          L.ptr(npid, C.c_int32)))
+                d2h += R * (5 * 4 + 5 * 8) + M * (8 + 8 + 4 + 4)
+                lib.dfb_regions_free(rh)
+                lib.dfb_nulls_free(nh)
+            h2d = host_cov.nbytes + F.nbytes + self.perm.nbytes
+            return h2d, d2h
+        finally:
+            lib.dfb_cov_free(cov)
+
+
+def pooled_pvalues(step, rh, nh, B, cut, dist, torch, device):
+    """Genome-wide pooling across ranks (the one exchange step): all-gather of null areas, all-reduce
+    (max) of per-permutation maxima, then p-values / FWER of this rank's regions against the pool."""
+    L, lib, eng = step.L, step.lib, step.eng
+    M = int(lib.dfb_nulls_count(nh))
+    R = int(lib.dfb_regions_count(rh))
+    world = dist.get_world_size()
+    counts = torch.tensor([M], device=device, dtype=torch.int64)
+    allc = torch.empty(world, device=device, dtype=torch.int64)
+    dist.all_gather_into_tensor(allc, counts)
+    cap = int(allc.max().item())
+    mine = torch.full((max(cap, 1),), float("nan"), device=device, dtype=torch.float64)
+    perm = torch.zeros(max(cap, 1), device=device, dtype=torch.int32)
+    L.check(lib.dfb_nulls_copy_dev(nh, C.c_void_p(mine.data_ptr()), C.c_void_p(perm.data_ptr())))
+    pool = torch.empty(world * max(cap, 1), device=device, dtype=torch.float64)
+    dist.all_gather_into_tensor(pool, mine)
+    pool = pool[~torch.isnan(pool)].contiguous()
+    mx = torch.empty(B, device=device, dtype=torch.float64)
+    L.check(lib.dfb_perm_max_dev(eng.h, C.c_void_p(mine.data_ptr()), C.c_void_p(perm.data_ptr()), M, B, -1.0,
+                                 C.c_void_p(mx.data_ptr())))
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    mx = torch.where(mx < 0, torch.full_like(mx, cut), mx)
+    area = np.empty(R)
+    L.check(lib.dfb_regions_get(rh, None, None, None, step._fp(area), None, None, None, None))
+    a_dev = torch.as_tensor(area, device=device)
+    p_dev = torch.empty(R, device=device, dtype=torch.float64)
+    L.check(lib.dfb_calc_pval_dev(eng.h, C.c_void_p(a_dev.data_ptr()), R, C.c_void_p(pool.data_ptr()), pool.numel(), 2,
+                                  C.c_void_p(p_dev.data_ptr())))
+    fwer = ((mx[None, :] > a_dev[:, None]).sum(dim=1) + 1).double() / (B + 1)
+    return p_dev, fwer, int(pool.numel())
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--cpu-bases", type=int, default=1_000_000, help="bounded CPU sample: kept bases per step")
+    ap.add_argument("--cpu-perms", type=int, default=30, help="bounded CPU sample: permutations per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--screen", type=int, default=None, help="override the engine's tcgen05 screening option")
+    args = ap.parse_args()
+    cfg = WORKLOADS[args.workload]
+    if args.impl == "reference":
+        run_reference_arm(args, cfg)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    import derfinder_b200 as dfb
+    from derfinder_b200 import _lib as L
+    from derfinder_b200.rrng import permutation_indices
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU fallback")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    W = max(args.warmup, 3)
+
+    # every rank owns its own synthetic chromosome (same shape): weak scaling
+    work = make_workload(cfg, 20140923 + 2 + 1000 * rank, torch=torch, device=device)
+    n, N, B = cfg["n"], cfg["N"], cfg["B"]
+    perm = permutation_indices(range(1, B + 1), n, "Rejection")  # same relabellings on every rank
+    cut = theoretical_cutoff(cfg["alpha"], work["mod"], work["mod0"])
+    eng = dfb.Engine(local, stream=torch.cuda.current_stream().cuda_stream)
+    if args.screen is not None:
+        eng.set_option("screen", args.screen)
+    step = Step(eng, work, perm, cut, torch)
+
+    def one_step():
+        if world > 1:
+            (R, M), rh, nh, cov = step.device_pass(keep=True)
+            p_dev, fwer, pool = pooled_pvalues(step, rh, nh, B, cut, dist, torch, device)
+            eng.lib.dfb_regions_free(rh)
+            eng.lib.dfb_nulls_free(nh)
+            eng.lib.dfb_cov_free(cov)
+            return R, M
+        return step.device_pass()
+
+    for _ in range(W):
+        R, M = one_step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    eng.reset_counters()
+    eng.enable_timing(True)
+    sampler = ClockSampler(local)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    ev0.record()
+    for _ in range(args.steps):
+        R, M = one_step()
+    ev1.record()
+    torch.cuda.synchronize()
+    sampler.stop_flag = True
+    sampler.join()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    launches = eng.launch_count()
+    kt = {k: eng.kernel_time(k) for k in (L.K_PREP, L.K_FSTAT, L.K_FSTAT_TC, L.K_REGIONS, L.K_PVAL)}
+    eng.enable_timing(False)
+    if world > 1:
+        t = torch.tensor([ms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        dist.barrier()
+
+    # end to end through host buffers (pinned), same pass
+    host_cov = torch.empty((n, N), dtype=torch.int32, pin_memory=True)
+    host_cov.copy_(work["cov"])
+    host_np = host_cov.numpy()
+    step.host_pass(host_np)
+    torch.cuda.synchronize()
+    ke = max(2, min(args.steps, 5))
+    t0 = time.perf_counter()
+    for _ in range(ke):
+        h2d, d2h = step.host_pass(host_np)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / ke
+    if world > 1:
+        t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+
+    units = float(N) * (B + 1) * world
+    value = units / (ms * 1e-3)
+    line = {"metric": "base_x_permutation_fstats_per_sec", "value": value, "unit": "base*perm F-stats/s",
+            "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": cfg["label"], "N": N, "n": n, "p": int(work["mod"].shape[1]),
+                       "p0": int(work["mod0"].shape[1]), "B": B, "f_cutoff": cut, "sharding": "chromosome per GPU",
+                       "l2": "inputs larger than L2 (coverage %.0f MB + log2 matrix %.0f MB per step; no flush)"
+                             % (4e-6 * n * N, 8e-6 * n * N),
+                       "regions": R, "null_regions": M},
+            "gpu_launches": int(launches),
+            "e2e": {"value": units / e2e_s, "unit": "base*perm F-stats/s", "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
+            "clocks": sampler.result()}
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        # dominant kernel: the F-stat scan.  Algorithmic work 2*N*n*p FP64-equivalent flops per
+        # (base, labelling) over all launches of the step (observed + permutations).
+        p = int(work["mod"].shape[1])
+        fst_ms, fst_l = kt[L.K_FSTAT]
+        tc_ms, tc_l = kt[L.K_FSTAT_TC]
+        k2_ms = (fst_ms + tc_ms) / args.steps
+        flops = 2.0 * N * n * p * (B + 1)
+        achieved = flops / (k2_ms * 1e-3) / 1e12 if k2_ms > 0 else None
+        peak = peaks.get("bf16_tflops", 1590.0)
+        line["roofline"] = {"bound": "tensor", "kernel": "fstat scan (K2)", "achieved": achieved, "peak": peak,
+                            "unit": "TFLOP/s", "frac": (achieved / peak if achieved else None), "traffic": None,
+                            "peak_source": "MEASURED_PEAKS.json bf16 burst" if "bf16_tflops" in peaks else "fallback",
+                            "algorithmic_flops_per_step": flops, "kernel_ms_per_step": k2_ms,
+                            "launches_per_step": (fst_l + tc_l) / args.steps,
+                            "kernel_share_of_step": k2_ms / ms,
+                            "other_kernels_ms_per_step": {"prep": kt[L.K_PREP][0] / args.steps,
+                                                          "regions": kt[L.K_REGIONS][0] / args.steps,
+                                                          "pval": kt[L.K_PVAL][0] / args.steps}}
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import c_oracle
+            c_oracle.build()
+            nb, npm = min(N, args.cpu_bases), min(B, args.cpu_perms)
+            cov_s, pl_s, pf_s, perm_s = cpu_sample(work, cfg, perm, cut, nb, npm)
+            cpu_reference_pass(cov_s[:, : nb // 10], *cpu_sample(work, cfg, perm, cut, nb // 10, 2)[1:3], work["mod"],
+                               work["mod0"], perm_s[:2], cut)
+            t0 = time.perf_counter()
+            cpu_reference_pass(cov_s, pl_s, pf_s, work["mod"], work["mod0"], perm_s, cut)
+            dt = time.perf_counter() - t0
+            line["cpu_baseline"] = {"value": nb * (npm + 1) / dt, "unit": "base*perm F-stats/s",
+                                    "cores": os.cpu_count(), "kind": "port", "seconds": dt,
+                                    "sample": f"first {nb} kept bases x {npm} permutations of the same workload, "
+                                              "numpy/OpenBLAS port of the reference's algorithm (chunksize 1e5)"}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    eng.close()
+
+
+if __name__ == "__main__":
+    main()
