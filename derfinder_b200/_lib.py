@@ -79,6 +79,8 @@ SIGNATURES = {
     "dfb_cluster_maker": (C.c_int64, [c_i32p, C.c_int64, C.c_int, C.c_int32, c_i64p, c_i64p, c_i64p, C.c_int64]),
     "dfb_perm_nulls": (C.c_int, [C.c_void_p, C.c_void_p, c_f64p, C.c_int, c_f64p, C.c_int, C.c_double, c_i32p,
                                  C.c_int64, C.c_double, C.c_double, C.c_int32, c_vpp]),
+    "dfb_debug_screen": (C.c_int, [C.c_void_p, C.c_void_p, c_f64p, C.c_int, c_f64p, C.c_int, C.c_double, c_i32p,
+                                   C.c_int64, C.c_double, c_i64p, c_i64p, c_i64p, c_i64p]),
     "dfb_nulls_free": (None, [C.c_void_p]),
     "dfb_nulls_count": (C.c_int64, [C.c_void_p]),
     "dfb_nulls_counts_per_perm": (C.c_int, [C.c_void_p, c_i64p]),

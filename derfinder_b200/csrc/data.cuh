@@ -95,6 +95,15 @@ int fstat_perm_batch(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, con
                      double adjust_f, const int32_t* idx_dev, int64_t B, double lo, double hi, bool two_sided,
                      size_t capacity_hint, PermBatch* out);
 
+// ---- fstat_tc.cu: tcgen05 screening contraction + exact FP64 refinement of the candidates
+bool screen_supported(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, double lo, double hi,
+                      double adjust_f);
+int fstat_perm_batch_screen(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, const double* q_dev /*[n][p]*/,
+                            double adjust_f, const int32_t* idx_dev, int64_t B, double hi, size_t capacity_hint,
+                            PermBatch* out, int64_t* ncand_out);
+
+int mask_diff(dfb_ctx* ctx, const uint32_t* a, const uint32_t* b, int64_t words, int64_t* diff);
+
 // ---- regions.cu
 int exclusive_scan_i64(dfb_ctx* ctx, const int64_t* in, int64_t* out, int64_t n, int64_t* total_dev, int fam);
 // Regions of `rows` mask rows: device outputs sized by `total`; row_counts (host) = regions per row.

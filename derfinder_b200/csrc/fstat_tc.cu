@@ -1,0 +1,744 @@
+// K2 (fast path) -- permutation F-stat screening contraction on the 5th-gen tensor cores, followed
+// by an exact FP64 refinement of the candidates.
+//
+// Reference work replaced: the B calls of derfinderHelper::fstats.apply inside the permutation loop
+// of calculatePvalues (R/calculatePvalues.R:306-343), i.e. B full F-stat scans whose only use is
+// "which bases reach the cutoff, and what is F there".
+//
+// Screening.  With S = yc' [Q0|Qd] (see fstat.cu) the test F >= U is algebraically
+//     a*|S_d|^2 + c*|S_0|^2 >= U*(adjustF + |yc|^2/dfden),   a = 1/dfnum + U/dfden,  c = U/dfden,
+// whose right-hand side does not depend on the permutation.  S for 128 bases x PS permutations is
+// one [128 x K] x [K x N] product on tcgen05 (kind::f16, bf16 operands, FP32 accumulation in TMEM).
+// Operands are split hi/lo (y = yh + yl, q = qh + ql, bf16 each) and three of the four cross terms
+// are stacked along K ([yh|yh|yl] x [qh|ql|qh]), so |S~ - S| <= delta*|yc| with delta ~ 1e-5 (bound
+// derived in DESIGN.md; the launch uses a 2x safety factor and tests measure it).  The epilogue
+// reads TMEM, forms L~ = sum_j w_j S~_j^2 and compares it with a per-base threshold lowered by the
+// error bound; the result is a CANDIDATE bit mask that contains every true exceedance.  Null
+// F-stats are never materialised.
+//
+// Refinement.  Every candidate (base, permutation) is recomputed with the exact FP64 arithmetic
+// contract of fstat.cu (same fma chains, bit-identical to the dense kernel and the C oracle),
+// thresholded exactly, and emitted in the same "mask + compacted values" form the region finder
+// consumes.  Results are therefore identical with the screen on or off.
+//
+// Layout: A tile = 128 bases x Kp bf16, B tile = Nmma columns x Kp bf16, both K-major in the
+// 128-byte swizzled UMMA layout (rows of 64 bf16, 8-row / 1024-byte atoms, 16-byte chunk index
+// XOR (row % 8)); the B tiles of all permutation chunks are laid out by a small prep kernel so a
+// plain bulk copy (cp.async.bulk + mbarrier) brings a ready tile into shared memory.  The A tile
+// is built once per CTA and reused for every permutation chunk.
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include <algorithm>
+
+#include "data.cuh"
+
+namespace dfb {
+
+constexpr int TC_M = 128;        // bases per tile (= TMEM lanes)
+constexpr int TC_THREADS = 160;  // warps 0-3: A-tile build + epilogue, warp 4: bulk copies + MMA issue
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers (sm_100a)
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_slot, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_slot), "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 32 lanes x 16 consecutive fp32 columns -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// shared-memory matrix descriptor, K-major, SWIZZLE_128B: start address, LBO (unused for swizzled
+// K-major, encoded 1), SBO = 1024 B (one 8-row atom), descriptor version 1, layout type 2.
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;
+    return d;
+}
+
+// instruction descriptor, kind::f16: D = f32, A = B = bf16, both K-major, M x N
+__host__ __device__ inline uint32_t umma_idesc_bf16(int M, int N) {
+    uint32_t d = 0;
+    d |= 1u << 4;                    // D format f32
+    d |= 1u << 7;                    // A format bf16
+    d |= 1u << 10;                   // B format bf16
+    d |= (uint32_t)(N >> 3) << 17;   // N / 8
+    d |= (uint32_t)(M >> 4) << 24;   // M / 16
+    return d;
+}
+
+// byte offset of element (row, col) inside a [rows x 64-bf16] K-block stored with the 128 B swizzle
+__host__ __device__ inline uint32_t sw128_offset(int row, int col) {
+    const int chunk = (col >> 3) ^ (row & 7);
+    return (uint32_t)row * 128u + (uint32_t)chunk * 16u + (uint32_t)(col & 7) * 2u;
+}
+
+// ------------------------------------------------------------------------------------------
+// geometry shared by the prep kernel, the screen and the refinement
+
+struct ScreenGeom {
+    int n, npad, Kp, KB;  // samples, samples padded to 16, K = 3*npad padded to 64, K blocks of 64
+    int p, p0, pst;       // model columns, column stride per permutation (power of two >= p)
+    int nmma, ps;         // MMA N (TMEM columns per stage) and permutations per stage
+    int64_t B, chunks, Bpad;
+    int64_t tiles;        // 128-base tiles
+    size_t smem;
+};
+
+// ------------------------------------------------------------------------------------------
+// B operand: for every chunk of `ps` permutations a [nmma x Kp] bf16 tile, pre-swizzled.
+// Row r = q*pst + j holds column j of permutation q; K layout [qh | ql | qh] matching [yh | yh | yl].
+
+__global__ void __launch_bounds__(128) build_qb_kernel(const double* __restrict__ q /*[n][p] row-major*/,
+                                                       const int32_t* __restrict__ idx /*[B][n]*/, ScreenGeom G,
+                                                       unsigned char* __restrict__ out) {
+    // one thread per 16-byte chunk of 8 consecutive K values of one row
+    const int64_t chunks_per_row = G.Kp / 8;
+    const int64_t total = G.chunks * G.nmma * chunks_per_row;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = t / (G.nmma * chunks_per_row);
+        const int64_t rem = t - c * G.nmma * chunks_per_row;
+        const int row = (int)(rem / chunks_per_row);
+        const int kc = (int)(rem - (int64_t)row * chunks_per_row);  // 8-column chunk along K
+        const int qi = row / G.pst, j = row - qi * G.pst;
+        const int64_t b = c * G.ps + qi;
+        __nv_bfloat16 vals[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int col = kc * 8 + e;
+            const int term = col / G.npad, k = col - term * G.npad;
+            float f = 0.f;
+            if (b < G.B && j < G.p && term < 3 && k < G.n) {
+                const double v = q[(size_t)idx[b * G.n + k] * G.p + j];
+                const __nv_bfloat16 h = __double2bfloat16(v);
+                if (term == 1) f = __bfloat162float(__double2bfloat16(v - (double)__bfloat162float(h)));
+                else f = __bfloat162float(h);
+            }
+            vals[e] = __float2bfloat16(f);  // exact: f is already a bf16 value
+        }
+        const int kb = (kc * 8) / 64, colb = (kc * 8) % 64;
+        unsigned char* dst = out + ((size_t)(c * G.KB + kb) * G.nmma) * 128 + sw128_offset(row, colb);
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(vals);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// screening kernel
+
+struct ScreenParams {
+    const double* Y;
+    int64_t ld, N;
+    ScreenGeom G;
+    const unsigned char* qb;  // [chunks][KB][nmma][128 B]
+    int center;
+    double U, adjust_f, dfnum, dfden, delta;
+    float w0, wd;        // weights of S_0 / S_d columns (rounded up)
+    uint32_t* cand;      // [tiles][4 warps][Bpad] candidate words
+    uint32_t idesc;
+};
+
+template <int PST>
+__global__ void __launch_bounds__(TC_THREADS) fstat_screen_kernel(const ScreenParams P) {
+    extern __shared__ __align__(1024) unsigned char smem_tc_raw[];
+    // SWIZZLE_128B atoms need 1024-byte alignment: align by hand (the launch reserves the slack)
+    unsigned char* smem_tc = smem_tc_raw + ((1024u - (smem_u32(smem_tc_raw) & 1023u)) & 1023u);
+    const ScreenGeom& G = P.G;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t a_bytes = (uint32_t)G.KB * TC_M * 128u;
+    const uint32_t b_bytes = (uint32_t)G.KB * G.nmma * 128u;
+    unsigned char* As = smem_tc;
+    unsigned char* Bs = smem_tc + a_bytes;  // two stages
+    uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + 2 * b_bytes);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const uint32_t full_b = smem_u32(bars + 0), empty_b = smem_u32(bars + 2);
+    const uint32_t tmem_full = smem_u32(bars + 4), tmem_empty = smem_u32(bars + 6);
+
+    const int64_t tile = blockIdx.x;
+    const int64_t base0 = tile * TC_M;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(full_b + 8 * s, 1);
+                mbar_init(empty_b + 8 * s, 1);
+                mbar_init(tmem_full + 8 * s, 1);
+                mbar_init(tmem_empty + 8 * s, 4);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(smem_u32(tmem_slot), (uint32_t)(2 * G.nmma));
+    }
+
+    // ---- A tile: thread t (< 128) converts base row t
+    float thr = __int_as_float(0x7f800000);  // +inf: rows beyond N never pass
+    if (tid < TC_M) {
+        const int64_t base = base0 + tid;
+        const bool valid = base < P.N;
+        double m = 0.0, yy = 0.0;
+        if (valid && P.center) {
+            double acc = P.Y[base];
+            for (int k = 1; k < G.n; ++k) acc = __dadd_rn(acc, P.Y[(size_t)k * P.ld + base]);
+            m = __ddiv_rn(acc, (double)G.n);
+        }
+        const int nchunk = G.Kp / 8;
+        for (int c = 0; c < nchunk; ++c) {
+            __nv_bfloat16 vals[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int col = c * 8 + e;
+                const int term = col / G.npad, k = col - term * G.npad;
+                float f = 0.f;
+                if (valid && term < 3 && k < G.n) {
+                    const double v = __dsub_rn(P.Y[(size_t)k * P.ld + base], m);
+                    if (term == 0) yy = fma(v, v, yy);
+                    const __nv_bfloat16 h = __double2bfloat16(v);
+                    if (term == 2) f = __bfloat162float(__double2bfloat16(v - (double)__bfloat162float(h)));
+                    else f = __bfloat162float(h);
+                }
+                vals[e] = __float2bfloat16(f);
+            }
+            const int kb = (c * 8) / 64, colb = (c * 8) % 64;
+            *reinterpret_cast<uint4*>(As + (size_t)kb * TC_M * 128 + sw128_offset(tid, colb)) =
+                *reinterpret_cast<const uint4*>(vals);
+        }
+        if (valid) {
+            // candidate iff  a*sd~ + c*s0~ >= (sqrt(T) - kappa*delta*|yc|)^2,  T = U*(adjustF + yy/dfden)
+            const double a = 1.0 / P.dfnum + P.U / P.dfden, cc = P.U / P.dfden;
+            const double kappa = sqrt(a * (double)(G.p - G.p0) + cc * (double)G.p0);
+            const double T = P.U * (P.adjust_f + yy / P.dfden);
+            const double r = sqrt(T) - kappa * P.delta * sqrt(yy);
+            const double t2 = r > 0.0 ? r * r * (1.0 - 1e-5) : 0.0;  // 1e-5: fp32 epilogue rounding
+            thr = (t2 == t2) ? (float)t2 : __int_as_float(0x7fc00000);  // NaN data -> never a candidate
+            if (thr > (float)t2 && thr > 0.f) thr = __int_as_float(__float_as_int(thr) - 1);  // round down
+        }
+    }
+    fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ===== producer + MMA issuer (one lane) =====
+        if (lane == 0) {
+            const uint32_t a_addr = smem_u32(As), b_addr = smem_u32(Bs);
+            const unsigned char* src = P.qb;
+            mbar_expect_tx(full_b, b_bytes);
+            bulk_g2s(b_addr, src, b_bytes, full_b);
+            for (int64_t c = 0; c < G.chunks; ++c) {
+                const int s = (int)(c & 1);
+                const uint32_t ph = (uint32_t)((c >> 1) & 1);
+                if (c + 1 < G.chunks) {  // prefetch the next B tile into the other stage
+                    const int s1 = (int)((c + 1) & 1);
+                    const uint32_t ph1 = (uint32_t)(((c + 1) >> 1) & 1);
+                    mbar_wait(empty_b + 8 * s1, ph1 ^ 1);
+                    mbar_expect_tx(full_b + 8 * s1, b_bytes);
+                    bulk_g2s(b_addr + s1 * b_bytes, src + (size_t)(c + 1) * b_bytes, b_bytes, full_b + 8 * s1);
+                }
+                mbar_wait(full_b + 8 * s, ph);
+                mbar_wait(tmem_empty + 8 * s, ph ^ 1);
+                tc_fence_after();
+                const uint32_t d_addr = tmem_base + (uint32_t)(s * G.nmma);
+                for (int kb = 0; kb < G.KB; ++kb) {
+#pragma unroll
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const uint64_t ad = umma_desc_sw128(a_addr + (uint32_t)kb * TC_M * 128u + kk * 32u);
+                        const uint64_t bd =
+                            umma_desc_sw128(b_addr + s * b_bytes + (uint32_t)kb * G.nmma * 128u + kk * 32u);
+                        umma_bf16(d_addr, ad, bd, P.idesc, (kb | kk) ? 1u : 0u);
+                    }
+                }
+                umma_commit(empty_b + 8 * s);    // B stage reusable once these MMAs have read it
+                umma_commit(tmem_full + 8 * s);  // accumulator ready for the epilogue
+            }
+        }
+    } else {
+        // ===== epilogue: thread = base row; TMEM lanes 32*warp .. 32*warp+31 =====
+        uint32_t* out = P.cand + ((size_t)tile * 4 + warp) * G.Bpad;
+        constexpr int per16 = 16 / PST;  // permutations per 16-column load
+        for (int64_t c = 0; c < G.chunks; ++c) {
+            const int s = (int)(c & 1);
+            const uint32_t ph = (uint32_t)((c >> 1) & 1);
+            mbar_wait(tmem_full + 8 * s, ph);
+            tc_fence_after();
+            uint32_t myword = 0;  // lane l keeps the word of permutation l of this chunk
+            const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * G.nmma);
+            for (int g = 0; g < G.nmma / 16; ++g) {
+                float v[16];
+                tmem_ld16(taddr + (uint32_t)(g * 16), v);
+#pragma unroll
+                for (int qq = 0; qq < per16; ++qq) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int j = 0; j < PST; ++j) {
+                        const float x = v[qq * PST + j];
+                        acc = fmaf(x * x, j < G.p0 ? P.w0 : (j < G.p ? P.wd : 0.f), acc);
+                    }
+                    const unsigned word = __ballot_sync(0xffffffffu, acc >= thr);
+                    const int qi = g * per16 + qq;
+                    if (lane == qi) myword = word;
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(tmem_empty + 8 * s);
+            const int64_t b = c * G.ps + lane;
+            if (lane < G.ps && b < G.Bpad) out[b] = b < G.B ? myword : 0u;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)(2 * G.nmma));
+}
+
+// ------------------------------------------------------------------------------------------
+// refinement: exact FP64 F for every candidate, exact threshold, compaction (same output format as
+// the dense kernel with 128-base tiles)
+
+struct RefineParams {
+    const double* Y;
+    int64_t ld, N;
+    int n, p, p0;
+    const double* q;      // [n][p] row-major
+    const int32_t* idx;   // [B][n]
+    int64_t B, Bpad;
+    int center;
+    double adjust_f, dfnum, dfden, U;
+    const uint32_t* cand;  // [tiles][4][Bpad]
+    uint32_t* mask;        // [B][W]
+    int64_t W;
+    int64_t* off;          // [B][tiles]
+    int64_t tiles;
+    double* vals;
+    unsigned long long capacity;
+    unsigned long long* cursor;
+};
+
+constexpr int RF_THREADS = 128;
+constexpr int RF_PB = 16;  // permutations per block of work
+
+__global__ void __launch_bounds__(RF_THREADS) fstat_refine_kernel(const RefineParams P) {
+    extern __shared__ __align__(16) unsigned char smem_rf[];
+    const int n = P.n, p = P.p;
+    double* ys = reinterpret_cast<double*>(smem_rf);            // [n][128] centred
+    double* Qs = ys + (size_t)n * TC_M;                          // [n][p]
+    double* yy_s = Qs + (size_t)n * p;                           // [128]
+    double* fv_s = yy_s + TC_M;                                  // [RF_PB][128] exact F of candidates
+    int32_t* idx_s = reinterpret_cast<int32_t*>(fv_s + RF_PB * TC_M);  // [RF_PB][n]
+    uint32_t* cw_s = reinterpret_cast<uint32_t*>(idx_s + RF_PB * n);   // [RF_PB][4] candidate words
+    uint32_t* ew_s = cw_s + RF_PB * 4;                                   // [RF_PB][4] exact words
+    int32_t* pre_s = reinterpret_cast<int32_t*>(ew_s + RF_PB * 4);      // [RF_PB*4 + 1] list offsets
+    uint16_t* list_s = reinterpret_cast<uint16_t*>(pre_s + RF_PB * 4 + 1);  // [RF_PB*128] entries
+    __shared__ unsigned long long gbase_s;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t tile = blockIdx.x;
+    const int64_t base0 = tile * TC_M;
+
+    for (int e = tid; e < n * p; e += RF_THREADS) Qs[e] = P.q[e];
+    {
+        const int64_t base = base0 + tid;
+        double acc = 0.0;
+        if (base < P.N) {
+            acc = P.Y[base];
+            ys[tid] = acc;
+            for (int k = 1; k < n; ++k) {
+                const double v = P.Y[(size_t)k * P.ld + base];
+                ys[(size_t)k * TC_M + tid] = v;
+                acc = __dadd_rn(acc, v);
+            }
+        } else {
+            for (int k = 0; k < n; ++k) ys[(size_t)k * TC_M + tid] = 0.0;
+        }
+        const double m = P.center ? __ddiv_rn(acc, (double)n) : 0.0;
+        double s = 0.0;
+        for (int k = 0; k < n; ++k) {
+            const double v = __dsub_rn(ys[(size_t)k * TC_M + tid], m);
+            ys[(size_t)k * TC_M + tid] = v;
+            s = fma(v, v, s);
+        }
+        yy_s[tid] = s;
+    }
+
+    for (int64_t b0 = 0; b0 < P.B; b0 += RF_PB) {
+        const int nb = (int)min((int64_t)RF_PB, P.B - b0);
+        __syncthreads();  // previous block fully consumed (and, first time, the tile is staged)
+        // candidate words + permutation rows of this block
+        if (tid < RF_PB * 4) {
+            const int q = tid >> 2, w = tid & 3;
+            uint32_t cw = 0;
+            if (q < nb) cw = P.cand[((size_t)tile * 4 + w) * P.Bpad + b0 + q];
+            const int64_t rem = P.N - (base0 + w * 32);
+            if (rem < 32) cw = rem > 0 ? (cw & ((1u << rem) - 1u)) : 0u;
+            cw_s[tid] = cw;
+            ew_s[tid] = 0u;
+        }
+        for (int e = tid; e < nb * n; e += RF_THREADS) idx_s[e] = P.idx[b0 * n + e];
+        __syncthreads();
+        // work list: exclusive scan of the 64 popcounts (two warps' worth -> warp 0 does it)
+        if (warp == 0) {
+            const int c0 = __popc(cw_s[lane]), c1 = __popc(cw_s[lane + 32]);
+            int inc = c0 + c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            // entries ordered: lanes own words (lane) and (lane + 32); order is irrelevant here
+            pre_s[lane] = inc - c0 - c1;
+            pre_s[lane + 32] = inc - c1;
+            if (lane == 31) pre_s[64] = inc;
+        }
+        __syncthreads();
+        if (tid < RF_PB * 4) {
+            uint32_t cw = cw_s[tid];
+            int o = pre_s[tid];
+            const int q = tid >> 2, w = tid & 3;
+            while (cw) {
+                const int bit = __ffs(cw) - 1;
+                cw &= cw - 1;
+                list_s[o++] = (uint16_t)((q << 7) | (w * 32 + bit));
+            }
+        }
+        __syncthreads();
+        const int nwork = pre_s[64];
+        for (int e = tid; e < nwork; e += RF_THREADS) {
+            const int ent = list_s[e];
+            const int q = ent >> 7, bl = ent & 127;
+            const int32_t* ix = idx_s + q * n;
+            double s0 = 0.0, sd = 0.0;
+            // S_j in k order, s0 / sd in j order: identical chains to the dense kernel
+            for (int j = 0; j < p; ++j) {
+                double S = 0.0;
+                for (int k = 0; k < n; ++k) S = fma(ys[(size_t)k * TC_M + bl], Qs[(size_t)ix[k] * p + j], S);
+                if (j < P.p0) s0 = fma(S, S, s0);
+                else sd = fma(S, S, sd);
+            }
+            double rss1 = __dsub_rn(__dsub_rn(yy_s[bl], s0), sd);
+            if (rss1 < 0.0) rss1 = 0.0;
+            const double num = __ddiv_rn(sd, P.dfnum);
+            const double den = __dadd_rn(P.adjust_f, __ddiv_rn(rss1, P.dfden));
+            const double f = __ddiv_rn(num, den);
+            if (f >= P.U) {
+                fv_s[q * TC_M + bl] = f;
+                atomicOr(&ew_s[q * 4 + (bl >> 5)], 1u << (bl & 31));
+            }
+        }
+        __syncthreads();
+        // exact mask words out; value offsets: scan of the 64 popcounts in (perm, word) order
+        if (warp == 0) {
+            const int e0 = 2 * lane, e1 = 2 * lane + 1;  // consecutive entries keep (perm, word) order
+            const int c0 = __popc(ew_s[e0]), c1 = __popc(ew_s[e1]);
+            int inc = c0 + c1;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const int total = __shfl_sync(0xffffffffu, inc, 31);
+            unsigned long long gb = 0;
+            if (lane == 0 && total > 0) gb = atomicAdd(P.cursor, (unsigned long long)total);
+            gb = __shfl_sync(0xffffffffu, gb, 0);
+            if (lane == 0) gbase_s = gb;
+            pre_s[e0] = inc - c0 - c1;
+            pre_s[e1] = inc - c1;
+        }
+        __syncthreads();
+        if (tid < RF_PB * 4) {
+            const int q = tid >> 2, w = tid & 3;
+            if (q < nb) {
+                const int64_t b = b0 + q;
+                const int64_t gw = tile * 4 + w;
+                if (gw < P.W) P.mask[b * P.W + gw] = ew_s[tid];
+                if (w == 0) P.off[b * P.tiles + tile] = (int64_t)gbase_s + pre_s[tid];
+            }
+        }
+        // values: thread = base; for every permutation of the block with my bit set
+        {
+            const int w = tid >> 5;
+            for (int q = 0; q < nb; ++q) {
+                const uint32_t ew = ew_s[q * 4 + w];
+                if ((ew >> lane) & 1u) {
+                    const unsigned long long dst =
+                        gbase_s + (unsigned long long)pre_s[q * 4 + w] + __popc(ew & ((1u << lane) - 1u));
+                    if (dst < P.capacity) P.vals[dst] = fv_s[q * TC_M + tid];
+                }
+            }
+        }
+    }
+}
+
+__global__ void popcount_words_kernel(const uint32_t* __restrict__ w, int64_t n, unsigned long long* __restrict__ out) {
+    unsigned long long c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        c += __popc(w[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+// words that differ between two masks of the same shape (debug / validation)
+__global__ void mask_diff_kernel(const uint32_t* __restrict__ a, const uint32_t* __restrict__ b, int64_t n,
+                                 unsigned long long* __restrict__ out) {
+    unsigned long long c = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+        c += __popc(a[i] ^ b[i]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(out, c);
+}
+
+int mask_diff(dfb_ctx* ctx, const uint32_t* a, const uint32_t* b, int64_t words, int64_t* diff) {
+    DevBuf<unsigned long long> cnt;
+    DFB_TRY(cnt.alloc(ctx, 1));
+    DFB_TRY(cnt.zero());
+    mask_diff_kernel<<<grid_for(words, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(a, b, words, cnt.p);
+    unsigned long long h = 0;
+    DFB_TRY(d2h(ctx, &h, cnt.p, sizeof h));
+    *diff = (int64_t)h;
+    return DFB_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+
+static bool screen_geometry(const dfb_cov* cov, const ModelBasis& mb, int64_t B, size_t smem_limit, ScreenGeom* g) {
+    ScreenGeom G;
+    memset(&G, 0, sizeof G);
+    G.n = cov->n;
+    G.npad = (int)round_up(G.n, 16);
+    G.Kp = (int)round_up(3 * G.npad, 64);
+    G.KB = G.Kp / 64;
+    G.p = mb.p;
+    G.p0 = mb.p0;
+    G.pst = 2;
+    while (G.pst < G.p) G.pst *= 2;
+    if (G.pst > 16) return false;
+    G.B = B;
+    G.tiles = ceil_div(cov->N, TC_M);
+    for (int nmma = std::min(128, 32 * G.pst); nmma >= 16; nmma /= 2) {
+        G.nmma = nmma;
+        G.ps = nmma / G.pst;
+        G.smem = (size_t)G.KB * TC_M * 128 + 2 * (size_t)G.KB * nmma * 128 + 8 * 8 + 16 + 1024;
+        if (G.smem <= smem_limit && G.ps >= 1) {
+            G.chunks = ceil_div(B, G.ps);
+            G.Bpad = G.chunks * G.ps;
+            *g = G;
+            return true;
+        }
+    }
+    return false;
+}
+
+// conservative bound on |S~ - S| / |yc| for the 3-term bf16 split with fp32 accumulation over
+// 3*n products (derivation in DESIGN.md), times a 2x safety factor
+static double screen_delta(int n) { return 2.0 * (3.1 * 3.8147e-6 /*2^-18*/ + 3.0 * n * 2.3842e-7 /*2^-22*/); }
+
+bool screen_supported(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, double lo, double hi,
+                      double adjust_f) {
+    if (!ctx->opt_screen) return false;
+    if (!(hi > 0.0) || !(lo < 0.0)) return false;      // one-sided positive cutoff only
+    if (cov->n - mb.p <= 0 || !(adjust_f >= 0.0)) return false;
+    ScreenGeom g;
+    const size_t limit = std::min<size_t>(ctx->smem_optin, 200 * 1024);
+    if (!screen_geometry(cov, mb, 1, limit, &g)) return false;
+    // refinement tile must fit too
+    const size_t rf = ((size_t)cov->n * TC_M + (size_t)cov->n * mb.p + TC_M + RF_PB * TC_M) * 8 +
+                      (size_t)RF_PB * cov->n * 4 + RF_PB * 4 * 8 + (RF_PB * 4 + 1) * 4 + RF_PB * TC_M * 2 + 64;
+    return rf <= limit;
+}
+
+// Screen + refine for one batch of permutations; fills the same PermBatch the dense kernel does.
+int fstat_perm_batch_screen(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, const double* q_dev /*[n][p]*/,
+                            double adjust_f, const int32_t* idx_dev, int64_t B, double hi, size_t capacity_hint,
+                            PermBatch* out, int64_t* ncand_out) {
+    ScreenGeom G;
+    const size_t limit = std::min<size_t>(ctx->smem_optin, 200 * 1024);
+    if (!screen_geometry(cov, mb, B, limit, &G)) {
+        set_error("screen geometry does not fit (internal error)");
+        return DFB_EINVAL;
+    }
+    DevBuf<unsigned char> qb;
+    DevBuf<uint32_t> cand;
+    const size_t qb_bytes = (size_t)G.chunks * G.KB * G.nmma * 128;
+    DFB_TRY(qb.alloc(ctx, qb_bytes));
+    DFB_TRY(cand.alloc(ctx, (size_t)G.tiles * 4 * G.Bpad));
+    {
+        KTimer t(ctx, DFB_K_FSTAT_TC, 1);
+        const int64_t work = G.chunks * G.nmma * (G.Kp / 8);
+        build_qb_kernel<<<grid_for(work, 128, ctx->sm_count, 16), 128, 0, ctx->stream>>>(q_dev, idx_dev, G, qb.p);
+    }
+    ScreenParams S;
+    memset(&S, 0, sizeof S);
+    S.Y = cov->y.p;
+    S.ld = cov->ld;
+    S.N = cov->N;
+    S.G = G;
+    S.qb = qb.p;
+    S.center = mb.centered ? 1 : 0;
+    S.U = hi;
+    S.adjust_f = adjust_f;
+    S.dfnum = (double)(mb.p - mb.p0);
+    S.dfden = (double)(cov->n - mb.p);
+    S.delta = screen_delta(cov->n);
+    const double a = 1.0 / S.dfnum + hi / S.dfden, c = hi / S.dfden;
+    S.w0 = (float)(c * (1.0 + 1e-6));
+    S.wd = (float)(a * (1.0 + 1e-6));
+    if ((double)S.w0 < c) S.w0 = nextafterf(S.w0, INFINITY);
+    if ((double)S.wd < a) S.wd = nextafterf(S.wd, INFINITY);
+    S.cand = cand.p;
+    S.idesc = umma_idesc_bf16(TC_M, G.nmma);
+    auto launch = [&](auto kern) -> int {
+        DFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.smem));
+        KTimer t(ctx, DFB_K_FSTAT_TC, 1);
+        kern<<<(unsigned)G.tiles, TC_THREADS, G.smem, ctx->stream>>>(S);
+        return DFB_OK;
+    };
+    switch (G.pst) {
+        case 2: DFB_TRY(launch(fstat_screen_kernel<2>)); break;
+        case 4: DFB_TRY(launch(fstat_screen_kernel<4>)); break;
+        case 8: DFB_TRY(launch(fstat_screen_kernel<8>)); break;
+        default: DFB_TRY(launch(fstat_screen_kernel<16>)); break;
+    }
+    DFB_CUDA(cudaGetLastError());
+
+    out->rows = B;
+    out->W = ceil_div(cov->N, 32);
+    out->tile_bases = TC_M;
+    out->tiles = G.tiles;
+    DFB_TRY(out->mask.alloc(ctx, (size_t)out->rows * out->W));
+    DFB_TRY(out->off.alloc(ctx, (size_t)out->rows * out->tiles));
+    DevBuf<unsigned long long> cursor;
+    DFB_TRY(cursor.alloc(ctx, 1));
+    const size_t dense = (size_t)B * (size_t)cov->N;
+    size_t cap = std::min(dense, std::max<size_t>(capacity_hint, 1024));
+    const size_t rf_smem = ((size_t)cov->n * TC_M + (size_t)cov->n * mb.p + TC_M + RF_PB * TC_M) * 8 +
+                           (size_t)RF_PB * cov->n * 4 + RF_PB * 4 * 8 + (RF_PB * 4 + 1) * 4 + RF_PB * TC_M * 2 + 64;
+    DFB_CUDA(cudaFuncSetAttribute(fstat_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rf_smem));
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        DFB_TRY(out->vals.alloc(ctx, cap));
+        DFB_TRY(cursor.zero());
+        RefineParams R;
+        memset(&R, 0, sizeof R);
+        R.Y = cov->y.p;
+        R.ld = cov->ld;
+        R.N = cov->N;
+        R.n = cov->n;
+        R.p = mb.p;
+        R.p0 = mb.p0;
+        R.q = q_dev;
+        R.idx = idx_dev;
+        R.B = B;
+        R.Bpad = G.Bpad;
+        R.center = mb.centered ? 1 : 0;
+        R.adjust_f = adjust_f;
+        R.dfnum = S.dfnum;
+        R.dfden = S.dfden;
+        R.U = hi;
+        R.cand = cand.p;
+        R.mask = out->mask.p;
+        R.W = out->W;
+        R.off = out->off.p;
+        R.tiles = out->tiles;
+        R.vals = out->vals.p;
+        R.capacity = cap;
+        R.cursor = cursor.p;
+        {
+            KTimer t(ctx, DFB_K_FSTAT, 1);
+            fstat_refine_kernel<<<(unsigned)G.tiles, RF_THREADS, rf_smem, ctx->stream>>>(R);
+        }
+        DFB_CUDA(cudaGetLastError());
+        unsigned long long used = 0;
+        DFB_TRY(d2h(ctx, &used, cursor.p, sizeof used));
+        out->nvals = (int64_t)used;
+        if (used <= cap) {
+            if (ncand_out) {
+                DevBuf<unsigned long long> cnt;
+                DFB_TRY(cnt.alloc(ctx, 1));
+                DFB_TRY(cnt.zero());
+                const int64_t words = G.tiles * 4 * G.Bpad;
+                popcount_words_kernel<<<grid_for(words, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(cand.p, words,
+                                                                                                     cnt.p);
+                unsigned long long h = 0;
+                DFB_TRY(d2h(ctx, &h, cnt.p, sizeof h));
+                *ncand_out = (int64_t)h;
+            }
+            return DFB_OK;
+        }
+        cap = (size_t)used;
+    }
+    set_error("exceedance buffer overflow after resize (internal error)");
+    return DFB_ECUDA;
+}
+
+}  // namespace dfb

@@ -57,6 +57,14 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
     DFB_TRY(h2d(ctx, idx_d.p, perm_idx, (size_t)B * n * sizeof(int32_t)));
     DFB_TRY(build_segment_starts(ctx, cov->pos, max_region_gap, &seg));
 
+    // tensor-core screen + exact refinement when the cutoff is one-sided positive (the normal case);
+    // otherwise the dense FP64 kernel.  Results are identical either way.
+    const bool use_screen = screen_supported(ctx, cov, mb, lo, hi, adjust_f);
+    DevBuf<double> q_d;
+    if (use_screen) {
+        DFB_TRY(q_d.alloc(ctx, mb.q.size()));
+        DFB_TRY(h2d(ctx, q_d.p, mb.q.data(), mb.q.size() * sizeof(double)));
+    }
     // F >= 0 (or NaN) by construction, so the "dn" side (F <= L) can only fire when L >= 0
     const bool two_sided = lo >= 0.0;
     const int sides = two_sided ? 2 : 1;
@@ -87,8 +95,10 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
                                   : (size_t)std::max(dense * density, 4.0e6);
         if ((double)hint * 8.0 > budget * 0.5) hint = (size_t)(budget * 0.5 / 8.0);
         PermBatch pbatch;
-        int rc = fstat_perm_batch(ctx, cov, mb, qd.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, lo, hi, two_sided, hint,
-                                  &pbatch);
+        int rc = use_screen ? fstat_perm_batch_screen(ctx, cov, mb, q_d.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, hi,
+                                                      hint, &pbatch, nullptr)
+                            : fstat_perm_batch(ctx, cov, mb, qd.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, lo, hi,
+                                               two_sided, hint, &pbatch);
         if (rc == DFB_ENOMEM && nb > 1) {  // exceedances did not fit: halve the batch
             const int64_t mid = b_lo + nb / 2;
             work.push_back({mid, b_hi});
@@ -465,6 +475,43 @@ int dfb_quantile(dfb_ctx* ctx, const dfb_cov* cov, const double* x, int64_t N, d
         return DFB_ESTATE;
     }
     return quantile_device(ctx, cov->fstats.p, cov->N, prob, out);
+}
+
+// Validation hook for the tensor-core screen: runs the dense FP64 kernel and the screen + refine
+// path on the same permutations and reports exceedance counts, the candidate count and the number
+// of mask bits that differ (must be 0).
+int dfb_debug_screen(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const double* mod0, int p0, double adjust_f,
+                     const int32_t* perm_idx, int64_t B, double cutoff, int64_t* n_exact_dense,
+                     int64_t* n_exact_screen, int64_t* n_candidates, int64_t* n_mask_diff) {
+    DFB_REQUIRE(ctx && cov && perm_idx && B > 0, "dfb_debug_screen: bad argument");
+    DFB_REQUIRE(cov->y.p != nullptr, "coverageProcessed is missing: run dfb_preprocess first");
+    ModelBasis mb;
+    DFB_TRY(build_model_basis(mod, cov->n, p, mod0, p0, &mb));
+    if (!screen_supported(ctx, cov, mb, -cutoff, cutoff, adjust_f)) {
+        set_error("the tensor-core screen does not support this configuration");
+        return DFB_ESTATE;
+    }
+    const int n = cov->n;
+    DevBuf<double> qd, q_d;
+    DevBuf<int32_t> idx_d;
+    DFB_TRY(qd.alloc(ctx, mb.qpad.size()));
+    DFB_TRY(h2d(ctx, qd.p, mb.qpad.data(), mb.qpad.size() * sizeof(double)));
+    DFB_TRY(q_d.alloc(ctx, mb.q.size()));
+    DFB_TRY(h2d(ctx, q_d.p, mb.q.data(), mb.q.size() * sizeof(double)));
+    DFB_TRY(idx_d.alloc(ctx, (size_t)B * n));
+    DFB_TRY(h2d(ctx, idx_d.p, perm_idx, (size_t)B * n * sizeof(int32_t)));
+    PermBatch dense, scr;
+    const size_t hint = (size_t)B * (size_t)cov->N;
+    DFB_TRY(fstat_perm_batch(ctx, cov, mb, qd.p, adjust_f, idx_d.p, B, -cutoff, cutoff, false, hint, &dense));
+    int64_t ncand = 0;
+    DFB_TRY(fstat_perm_batch_screen(ctx, cov, mb, q_d.p, adjust_f, idx_d.p, B, cutoff, hint, &scr, &ncand));
+    int64_t diff = 0;
+    DFB_TRY(mask_diff(ctx, dense.mask.p, scr.mask.p, dense.rows * dense.W, &diff));
+    if (n_exact_dense) *n_exact_dense = dense.nvals;
+    if (n_exact_screen) *n_exact_screen = scr.nvals;
+    if (n_candidates) *n_candidates = ncand;
+    if (n_mask_diff) *n_mask_diff = diff;
+    return DFB_OK;
 }
 
 int dfb_calculate_pvalues(dfb_ctx* ctx, dfb_cov* cov, const double* fstats, const double* mod, int p,

@@ -218,6 +218,15 @@ int dfb_nulls_get(const dfb_nulls* nl, int dup, double* stat, int32_t* width, do
 /* device access for multi-GPU pooling (areas as doubles, permutation ids as int32) */
 int dfb_nulls_copy_dev(const dfb_nulls* nl, double* area_dev, int32_t* perm_dev);
 
+/* Validation hook for the tcgen05 screening path (used by the parity tests and profiling): runs
+ * the dense FP64 scan and the screen + refinement on the same permutations with a scalar cutoff
+ * and reports the exceedance counts of both, the number of screened candidates and the number of
+ * mask bits that differ between the two paths (must be 0). */
+int dfb_debug_screen(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const double* mod0, int p0,
+                     double adjust_f, const int32_t* perm_idx, int64_t B, double cutoff,
+                     int64_t* n_exact_dense, int64_t* n_exact_screen, int64_t* n_candidates,
+                     int64_t* n_mask_diff);
+
 /* ---------------------------------------------------------------- p-values ------------------ */
 
 /* .calcPval() -- R/calculatePvalues.R:432-441.  weight = multiplicity of every null entry

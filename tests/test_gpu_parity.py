@@ -486,3 +486,56 @@ def test_region_matrix(dfb, eng):
     assert np.array_equal(rmi["coverageMatrix"], oi["coverageMatrix"])
     none = dfb.regionMatrix({"chr21": icols}, cutoff=50, L=36, engine=eng)["chr21"]
     assert none["regions"] is None and none["coverageMatrix"] is None
+
+
+# ---------------------------------------------------------------------------------------------
+# tcgen05 screening contraction: candidate mask must contain every exceedance; screen + exact
+# refinement must reproduce the dense FP64 kernel bit for bit
+
+
+def debug_screen(eng, cov_handle, models, perm, cutoff, adjustF=0.0):
+    from derfinder_b200 import _lib as L
+    mod, mod0 = np.asfortranarray(models["mod"]), np.asfortranarray(models["mod0"])
+    perm = np.ascontiguousarray(perm, dtype=np.int32)
+    out = [C.c_int64() for _ in range(4)]
+    L.check(eng.lib.dfb_debug_screen(eng.h, cov_handle.h, mod.ctypes.data_as(L.c_f64p), mod.shape[1],
+                                     mod0.ctypes.data_as(L.c_f64p), mod0.shape[1], float(adjustF),
+                                     L.ptr(perm, C.c_int32), perm.shape[0], float(cutoff), *[C.byref(o) for o in out]))
+    return tuple(o.value for o in out)  # exact_dense, exact_screen, candidates, mask bits differing
+
+
+@pytest.mark.parametrize("n,extra,N,B,alpha", [(12, 0, 50000, 37, 0.05), (12, 0, 4099, 100, 0.2),
+                                                 (31, 1, 20000, 33, 0.01), (60, 3, 9000, 50, 1e-3),
+                                                 (20, 5, 7000, 19, 0.05), (9, 0, 5000, 70, 0.5),
+                                                 (80, 3, 3000, 24, 0.01)])
+def test_screen_contains_all_exceedances(dfb, eng, n, extra, N, B, alpha):
+    rng = np.random.default_rng(1000 + n + B)
+    cov, position, group, models = synth(rng, N, n, p_extra=extra)
+    prep = dfb.preprocessCoverage(dict(coverage=cov, position=position), engine=eng)
+    perm = random_perms(rng, B, n)
+    cut = dfb.calcFstatCutoff("theoretical", alpha, models=models)
+    dense, screen, cand, diff = debug_screen(eng, prep["coverageProcessed"], models, perm, cut)
+    assert diff == 0, f"{diff} mask bits differ between the dense kernel and screen+refine"
+    assert dense == screen
+    assert cand >= dense
+    # the candidate set is tight: error-bound slack only
+    assert cand <= dense * 1.05 + 0.001 * N * B + 64, (cand, dense)
+
+
+def test_screen_off_equals_on(dfb, eng):
+    rng = np.random.default_rng(31)
+    cov, position, group, models = synth(rng, 25000, 12, seg=[9000, 16000])
+    perm = random_perms(rng, 40, 12)
+    cut = dfb.calcFstatCutoff("theoretical", 0.05, models=models)
+    res_on, ores = run_both(dfb, eng, cov, position, group, models, perm, cut)
+    assert_pipeline_equal(res_on, ores)
+    e2 = dfb.Engine(0)
+    try:
+        e2.set_option("screen", 0)
+        prep = dfb.preprocessCoverage(dict(coverage=cov, position=position), groupInfo=group, engine=e2)
+        F = dfb.calculateStats(prep, models, engine=e2)
+        res_off = dfb.calculatePvalues(prep, models, F, permIndex=perm, cutoff=cut, engine=e2)
+        assert_pipeline_equal(res_off, ores)
+        assert e2.kernel_time(3)[1] == 0 and eng.kernel_time(3)[1] > 0  # tcgen05 path really ran / really off
+    finally:
+        e2.close()
