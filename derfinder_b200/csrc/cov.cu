@@ -458,10 +458,9 @@ template <typename V>
 __global__ void __launch_bounds__(256) minmax_kernel(const V* __restrict__ x, int64_t ld, int64_t N, int n,
                                                      long long* __restrict__ mn, long long* __restrict__ mx) {
     long long lo = LLONG_MAX, hi = LLONG_MIN;
-    const int64_t total = (int64_t)n * N;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total; g += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t s = g / N, i = g - s * N;
-        const long long v = (long long)x[(size_t)s * ld + i];
+    const V* __restrict__ col = x + (size_t)blockIdx.y * ld;  // one sample per blockIdx.y: no index division
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
+        const long long v = (long long)col[i];
         lo = v < lo ? v : lo;
         hi = v > hi ? v : hi;
     }
@@ -713,7 +712,7 @@ int dfb_preprocess(dfb_ctx* ctx, dfb_cov* c, double scalefac, const int32_t* gro
         DFB_TRY(h2d(ctx, mm.p, init, sizeof init));
         {
             KTimer t(ctx, DFB_K_PREP);
-            minmax_kernel<int32_t><<<grid_for((int64_t)c->n * c->N, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(
+            minmax_kernel<int32_t><<<dim3(grid_for(c->N, 256 * 8, ctx->sm_count, 4), c->n), 256, 0, ctx->stream>>>(
                 c->xi.p, c->ld, c->N, c->n, mm.p, mm.p + 1);
         }
         long long got[2];

@@ -160,7 +160,9 @@ struct ScreenGeom {
 
 __global__ void __launch_bounds__(128) build_qb_kernel(const double* __restrict__ q /*[n][p] row-major*/,
                                                        const int32_t* __restrict__ idx /*[B][n]*/, ScreenGeom G,
-                                                       unsigned char* __restrict__ out) {
+                                                       double sw0, double swd, unsigned char* __restrict__ out) {
+    // columns are pre-scaled by sqrt(w_j) (w = c for the p0 null columns, a for the others) so the
+    // epilogue's test is a plain sum of squares
     // one thread per 16-byte chunk of 8 consecutive K values of one row
     const int64_t chunks_per_row = G.Kp / 8;
     const int64_t total = G.chunks * G.nmma * chunks_per_row;
@@ -178,7 +180,7 @@ __global__ void __launch_bounds__(128) build_qb_kernel(const double* __restrict_
             const int term = col / G.npad, k = col - term * G.npad;
             float f = 0.f;
             if (b < G.B && j < G.p && term < 3 && k < G.n) {
-                const double v = q[(size_t)idx[b * G.n + k] * G.p + j];
+                const double v = q[(size_t)idx[b * G.n + k] * G.p + j] * (j < G.p0 ? sw0 : swd);
                 const __nv_bfloat16 h = __double2bfloat16(v);
                 if (term == 1) f = __bfloat162float(__double2bfloat16(v - (double)__bfloat162float(h)));
                 else f = __bfloat162float(h);
@@ -201,12 +203,12 @@ struct ScreenParams {
     const unsigned char* qb;  // [chunks][KB][nmma][128 B]
     int center;
     double U, adjust_f, dfnum, dfden, delta;
-    float w0, wd;        // weights of S_0 / S_d columns (rounded up)
     uint32_t* cand;      // [tiles][4 warps][Bpad] candidate words
     uint32_t idesc;
 };
 
-template <int PST>
+// PST: TMEM column stride per permutation (power of two), PCOLS: columns actually summed (= p)
+template <int PST, int PCOLS>
 __global__ void __launch_bounds__(TC_THREADS) fstat_screen_kernel(const ScreenParams P) {
     extern __shared__ __align__(1024) unsigned char smem_tc_raw[];
     // SWIZZLE_128B atoms need 1024-byte alignment: align by hand (the launch reserves the slack)
@@ -219,6 +221,7 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_screen_kernel(const ScreenPa
     unsigned char* Bs = smem_tc + a_bytes;  // two stages
     uint64_t* bars = reinterpret_cast<uint64_t*>(Bs + 2 * b_bytes);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    uint32_t* words_s = tmem_slot + 4;  // [4 warps][32] candidate words of the current chunk
     const uint32_t full_b = smem_u32(bars + 0), empty_b = smem_u32(bars + 2);
     const uint32_t tmem_full = smem_u32(bars + 4), tmem_empty = smem_u32(bars + 6);
 
@@ -250,27 +253,31 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_screen_kernel(const ScreenPa
             for (int k = 1; k < G.n; ++k) acc = __dadd_rn(acc, P.Y[(size_t)k * P.ld + base]);
             m = __ddiv_rn(acc, (double)G.n);
         }
-        const int nchunk = G.Kp / 8;
-        for (int c = 0; c < nchunk; ++c) {
-            __nv_bfloat16 vals[8];
+        // every sample is loaded and split once: 8 samples -> one 16-byte chunk of yh (written to
+        // the K ranges of terms 0 and 1) and one of yl (term 2); K columns [3*npad, Kp) are zero
+        const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+        auto put = [&](int col, const uint4& val) {  // col: multiple of 8
+            *reinterpret_cast<uint4*>(As + (size_t)(col >> 6) * TC_M * 128 + sw128_offset(tid, col & 63)) = val;
+        };
+        for (int k0 = 0; k0 < G.npad; k0 += 8) {
+            __nv_bfloat16 hi[8], lo[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int col = c * 8 + e;
-                const int term = col / G.npad, k = col - term * G.npad;
-                float f = 0.f;
-                if (valid && term < 3 && k < G.n) {
-                    const double v = __dsub_rn(P.Y[(size_t)k * P.ld + base], m);
-                    if (term == 0) yy = fma(v, v, yy);
-                    const __nv_bfloat16 h = __double2bfloat16(v);
-                    if (term == 2) f = __bfloat162float(__double2bfloat16(v - (double)__bfloat162float(h)));
-                    else f = __bfloat162float(h);
+                const int k = k0 + e;
+                double v = 0.0;
+                if (valid && k < G.n) {
+                    v = __dsub_rn(P.Y[(size_t)k * P.ld + base], m);
+                    yy = fma(v, v, yy);
                 }
-                vals[e] = __float2bfloat16(f);
+                hi[e] = __double2bfloat16(v);
+                lo[e] = __double2bfloat16(v - (double)__bfloat162float(hi[e]));
             }
-            const int kb = (c * 8) / 64, colb = (c * 8) % 64;
-            *reinterpret_cast<uint4*>(As + (size_t)kb * TC_M * 128 + sw128_offset(tid, colb)) =
-                *reinterpret_cast<const uint4*>(vals);
+            const uint4 h4 = *reinterpret_cast<const uint4*>(hi), l4 = *reinterpret_cast<const uint4*>(lo);
+            put(k0, h4);
+            put(G.npad + k0, h4);
+            put(2 * G.npad + k0, l4);
         }
+        for (int col = 3 * G.npad; col < G.Kp; col += 8) put(col, zero4);
         if (valid) {
             // candidate iff  a*sd~ + c*s0~ >= (sqrt(T) - kappa*delta*|yc|)^2,  T = U*(adjustF + yy/dfden)
             const double a = 1.0 / P.dfnum + P.U / P.dfden, cc = P.U / P.dfden;
@@ -331,29 +338,26 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_screen_kernel(const ScreenPa
             const uint32_t ph = (uint32_t)((c >> 1) & 1);
             mbar_wait(tmem_full + 8 * s, ph);
             tc_fence_after();
-            uint32_t myword = 0;  // lane l keeps the word of permutation l of this chunk
+            uint32_t* wrow = words_s + warp * 32;
             const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * G.nmma);
             for (int g = 0; g < G.nmma / 16; ++g) {
                 float v[16];
                 tmem_ld16(taddr + (uint32_t)(g * 16), v);
 #pragma unroll
                 for (int qq = 0; qq < per16; ++qq) {
-                    float acc = 0.f;
+                    float acc = v[qq * PST] * v[qq * PST];
 #pragma unroll
-                    for (int j = 0; j < PST; ++j) {
-                        const float x = v[qq * PST + j];
-                        acc = fmaf(x * x, j < G.p0 ? P.w0 : (j < G.p ? P.wd : 0.f), acc);
-                    }
+                    for (int j = 1; j < PCOLS; ++j) acc = fmaf(v[qq * PST + j], v[qq * PST + j], acc);
                     const unsigned word = __ballot_sync(0xffffffffu, acc >= thr);
-                    const int qi = g * per16 + qq;
-                    if (lane == qi) myword = word;
+                    if (lane == 0) wrow[g * per16 + qq] = word;
                 }
             }
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(tmem_empty + 8 * s);
-            const int64_t b = c * G.ps + lane;
-            if (lane < G.ps && b < G.Bpad) out[b] = b < G.B ? myword : 0u;
+            const int64_t b = c * G.ps + lane;  // one coalesced store of the chunk's words per warp
+            if (lane < G.ps && b < G.Bpad) out[b] = b < G.B ? wrow[lane] : 0u;
+            __syncwarp();
         }
     }
     tc_fence_before();
@@ -387,6 +391,8 @@ struct RefineParams {
 constexpr int RF_THREADS = 128;
 constexpr int RF_PB = 16;  // permutations per block of work
 
+// PT: number of model columns when <= 8 (accumulators in registers), 0 = generic
+template <int PT>
 __global__ void __launch_bounds__(RF_THREADS) fstat_refine_kernel(const RefineParams P) {
     extern __shared__ __align__(16) unsigned char smem_rf[];
     const int n = P.n, p = P.p;
@@ -478,11 +484,28 @@ __global__ void __launch_bounds__(RF_THREADS) fstat_refine_kernel(const RefinePa
             const int32_t* ix = idx_s + q * n;
             double s0 = 0.0, sd = 0.0;
             // S_j in k order, s0 / sd in j order: identical chains to the dense kernel
-            for (int j = 0; j < p; ++j) {
-                double S = 0.0;
-                for (int k = 0; k < n; ++k) S = fma(ys[(size_t)k * TC_M + bl], Qs[(size_t)ix[k] * p + j], S);
-                if (j < P.p0) s0 = fma(S, S, s0);
-                else sd = fma(S, S, sd);
+            if (PT > 0) {
+                double S[PT > 0 ? PT : 1];
+#pragma unroll
+                for (int j = 0; j < PT; ++j) S[j] = 0.0;
+                for (int k = 0; k < n; ++k) {
+                    const double yv = ys[(size_t)k * TC_M + bl];
+                    const double* qrow = Qs + (size_t)ix[k] * PT;
+#pragma unroll
+                    for (int j = 0; j < PT; ++j) S[j] = fma(yv, qrow[j], S[j]);
+                }
+#pragma unroll
+                for (int j = 0; j < PT; ++j) {
+                    if (j < P.p0) s0 = fma(S[j], S[j], s0);
+                    else sd = fma(S[j], S[j], sd);
+                }
+            } else {
+                for (int j = 0; j < p; ++j) {
+                    double S = 0.0;
+                    for (int k = 0; k < n; ++k) S = fma(ys[(size_t)k * TC_M + bl], Qs[(size_t)ix[k] * p + j], S);
+                    if (j < P.p0) s0 = fma(S, S, s0);
+                    else sd = fma(S, S, sd);
+                }
             }
             double rss1 = __dsub_rn(__dsub_rn(yy_s[bl], s0), sd);
             if (rss1 < 0.0) rss1 = 0.0;
@@ -589,7 +612,7 @@ static bool screen_geometry(const dfb_cov* cov, const ModelBasis& mb, int64_t B,
     for (int nmma = std::min(128, 32 * G.pst); nmma >= 16; nmma /= 2) {
         G.nmma = nmma;
         G.ps = nmma / G.pst;
-        G.smem = (size_t)G.KB * TC_M * 128 + 2 * (size_t)G.KB * nmma * 128 + 8 * 8 + 16 + 1024;
+        G.smem = (size_t)G.KB * TC_M * 128 + 2 * (size_t)G.KB * nmma * 128 + 8 * 8 + 16 + 4 * 32 * 4 + 1024;
         if (G.smem <= smem_limit && G.ps >= 1) {
             G.chunks = ceil_div(B, G.ps);
             G.Bpad = G.chunks * G.ps;
@@ -633,10 +656,13 @@ int fstat_perm_batch_screen(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& 
     const size_t qb_bytes = (size_t)G.chunks * G.KB * G.nmma * 128;
     DFB_TRY(qb.alloc(ctx, qb_bytes));
     DFB_TRY(cand.alloc(ctx, (size_t)G.tiles * 4 * G.Bpad));
+    const double df1 = (double)(mb.p - mb.p0), df2 = (double)(cov->n - mb.p);
+    const double w_a = 1.0 / df1 + hi / df2, w_c = hi / df2;  // weights of the S_d / S_0 columns
     {
         KTimer t(ctx, DFB_K_FSTAT_TC, 1);
         const int64_t work = G.chunks * G.nmma * (G.Kp / 8);
-        build_qb_kernel<<<grid_for(work, 128, ctx->sm_count, 16), 128, 0, ctx->stream>>>(q_dev, idx_dev, G, qb.p);
+        build_qb_kernel<<<grid_for(work, 128, ctx->sm_count, 16), 128, 0, ctx->stream>>>(q_dev, idx_dev, G, sqrt(w_c),
+                                                                                       sqrt(w_a), qb.p);
     }
     ScreenParams S;
     memset(&S, 0, sizeof S);
@@ -651,11 +677,6 @@ int fstat_perm_batch_screen(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& 
     S.dfnum = (double)(mb.p - mb.p0);
     S.dfden = (double)(cov->n - mb.p);
     S.delta = screen_delta(cov->n);
-    const double a = 1.0 / S.dfnum + hi / S.dfden, c = hi / S.dfden;
-    S.w0 = (float)(c * (1.0 + 1e-6));
-    S.wd = (float)(a * (1.0 + 1e-6));
-    if ((double)S.w0 < c) S.w0 = nextafterf(S.w0, INFINITY);
-    if ((double)S.wd < a) S.wd = nextafterf(S.wd, INFINITY);
     S.cand = cand.p;
     S.idesc = umma_idesc_bf16(TC_M, G.nmma);
     auto launch = [&](auto kern) -> int {
@@ -664,11 +685,15 @@ int fstat_perm_batch_screen(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& 
         kern<<<(unsigned)G.tiles, TC_THREADS, G.smem, ctx->stream>>>(S);
         return DFB_OK;
     };
-    switch (G.pst) {
-        case 2: DFB_TRY(launch(fstat_screen_kernel<2>)); break;
-        case 4: DFB_TRY(launch(fstat_screen_kernel<4>)); break;
-        case 8: DFB_TRY(launch(fstat_screen_kernel<8>)); break;
-        default: DFB_TRY(launch(fstat_screen_kernel<16>)); break;
+    switch (G.p) {
+        case 2: DFB_TRY(launch(fstat_screen_kernel<2, 2>)); break;
+        case 3: DFB_TRY(launch(fstat_screen_kernel<4, 3>)); break;
+        case 4: DFB_TRY(launch(fstat_screen_kernel<4, 4>)); break;
+        case 5: DFB_TRY(launch(fstat_screen_kernel<8, 5>)); break;
+        case 6: DFB_TRY(launch(fstat_screen_kernel<8, 6>)); break;
+        case 7: DFB_TRY(launch(fstat_screen_kernel<8, 7>)); break;
+        case 8: DFB_TRY(launch(fstat_screen_kernel<8, 8>)); break;
+        default: DFB_TRY(launch(fstat_screen_kernel<16, 16>)); break;  // zero-padded columns add 0
     }
     DFB_CUDA(cudaGetLastError());
 
@@ -684,7 +709,24 @@ int fstat_perm_batch_screen(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& 
     size_t cap = std::min(dense, std::max<size_t>(capacity_hint, 1024));
     const size_t rf_smem = ((size_t)cov->n * TC_M + (size_t)cov->n * mb.p + TC_M + RF_PB * TC_M) * 8 +
                            (size_t)RF_PB * cov->n * 4 + RF_PB * 4 * 8 + (RF_PB * 4 + 1) * 4 + RF_PB * TC_M * 2 + 64;
-    DFB_CUDA(cudaFuncSetAttribute(fstat_refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rf_smem));
+    auto launch_refine = [&](const RefineParams& R) -> int {
+        auto go = [&](auto kern) -> int {
+            DFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rf_smem));
+            KTimer t(ctx, DFB_K_FSTAT, 1);
+            kern<<<(unsigned)G.tiles, RF_THREADS, rf_smem, ctx->stream>>>(R);
+            return DFB_OK;
+        };
+        switch (mb.p) {
+            case 2: return go(fstat_refine_kernel<2>);
+            case 3: return go(fstat_refine_kernel<3>);
+            case 4: return go(fstat_refine_kernel<4>);
+            case 5: return go(fstat_refine_kernel<5>);
+            case 6: return go(fstat_refine_kernel<6>);
+            case 7: return go(fstat_refine_kernel<7>);
+            case 8: return go(fstat_refine_kernel<8>);
+            default: return go(fstat_refine_kernel<0>);
+        }
+    };
     for (int attempt = 0; attempt < 2; ++attempt) {
         DFB_TRY(out->vals.alloc(ctx, cap));
         DFB_TRY(cursor.zero());
@@ -713,10 +755,7 @@ int fstat_perm_batch_screen(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& 
         R.vals = out->vals.p;
         R.capacity = cap;
         R.cursor = cursor.p;
-        {
-            KTimer t(ctx, DFB_K_FSTAT, 1);
-            fstat_refine_kernel<<<(unsigned)G.tiles, RF_THREADS, rf_smem, ctx->stream>>>(R);
-        }
+        DFB_TRY(launch_refine(R));
         DFB_CUDA(cudaGetLastError());
         unsigned long long used = 0;
         DFB_TRY(d2h(ctx, &used, cursor.p, sizeof used));

@@ -190,52 +190,56 @@ __global__ void __launch_bounds__(128) emit_regions_kernel(const EmitParams P) {
         if (!starts) continue;
         const uint32_t* mrow = P.mask + row * P.W;
         int64_t out = P.offsets[g];
+        const int wpt_shift = COMPACT ? (31 - __clz(P.tile_bases >> 5)) : 0;  // log2(words per value tile)
         while (starts) {
             const int b = __ffs(starts) - 1;
             starts &= starts - 1;
             const int64_t i = w * 32 + b;
-            // locate the first value
+            // first value of the region
             int64_t ptr = 0;
-            const double* drow = nullptr;
+            const double* src;
             if (COMPACT) {
-                const int64_t t = i / P.tile_bases;
+                const int64_t t = w >> wpt_shift;
                 ptr = P.off[row * P.tiles + t];
-                for (int64_t ww = t * (P.tile_bases >> 5); ww < w; ++ww) ptr += __popc(mrow[ww]);
+                for (int64_t ww = t << wpt_shift; ww < w; ++ww) ptr += __popc(mrow[ww]);
                 ptr += __popc(m & ((1u << b) - 1u));
+                src = P.vals + ptr;
             } else {
-                drow = P.dense + row * P.dense_stride;
+                src = P.dense + row * P.dense_stride + i;
             }
-            double cur = COMPACT ? P.vals[ptr] : drow[i];
+            // The region is walked word by word: inside a word its extent is the run of bits that
+            // pass and do not open a new segment (bit tricks, no per-base tests); values of
+            // consecutive passing bases are consecutive in memory until a value-tile boundary.
+            double cur = src[0];
             double runlen = 1.0;
             double acc = 0.0;
-            int64_t j = i + 1;
             int64_t cw = w;
-            uint32_t cm = m, cs = sg;
-            while (j < P.N) {
-                const int64_t wj = j >> 5;
-                if (wj != cw) {
-                    cw = wj;
-                    cm = mrow[wj];
-                    cs = P.seg[wj];
+            int64_t j = i + 1;  // one past the last base taken so far
+            // bases of word cw that may continue the region: bits above b, passing, not a segment start
+            uint32_t cont = (b < 31) ? ((m & ~sg) >> (b + 1)) : 0u;
+            int avail = 31 - b;  // bits of `cont` that are real
+            const double* vp = src + 1;
+            for (;;) {
+                int take = __ffs(~cont) - 1;  // trailing ones (cont has zeros above `avail`)
+                if (take < 0 || take > avail) take = avail;
+                for (int t2 = 0; t2 < take; ++t2) {
+                    const double v = vp[t2];
+                    if (v == cur) {
+                        runlen += 1.0;
+                    } else {
+                        acc = __dadd_rn(acc, __dmul_rn(cur, runlen));
+                        cur = v;
+                        runlen = 1.0;
+                    }
                 }
-                const int bj = (int)(j & 31);
-                if (!((cm >> bj) & 1u) || ((cs >> bj) & 1u)) break;
-                double v;
-                if (COMPACT) {
-                    if (j % P.tile_bases == 0) ptr = P.off[row * P.tiles + j / P.tile_bases];
-                    else ++ptr;
-                    v = P.vals[ptr];
-                } else {
-                    v = drow[j];
-                }
-                if (v == cur) {
-                    runlen += 1.0;
-                } else {
-                    acc = __dadd_rn(acc, __dmul_rn(cur, runlen));
-                    cur = v;
-                    runlen = 1.0;
-                }
-                ++j;
+                j += take;
+                vp += take;
+                if (take < avail || j >= P.N) break;  // the run ended inside this word
+                ++cw;
+                const uint32_t nm = mrow[cw], ns = P.seg[cw];
+                cont = nm & ~ns;
+                avail = 32;
+                if (COMPACT && (cw & ((1 << wpt_shift) - 1)) == 0) vp = P.vals + P.off[row * P.tiles + (cw >> wpt_shift)];
             }
             acc = __dadd_rn(acc, __dmul_rn(cur, runlen));
             const int32_t wd = (int32_t)(j - i);
