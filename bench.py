@@ -257,6 +257,8 @@ class Step:
         self.n, self.N = work["cov"].shape
         self.mod, self.mod0 = work["mod"], work["mod0"]
         self.pl = np.ascontiguousarray(work["pos_len"], dtype=np.int32)
+        self._F_host = np.empty(self.N)  # the caller's fstats vector (R: a numeric vector it already owns)
+        self.last_breakdown = {}
 
     def _fp(self, a):
         return a.ctypes.data_as(self.L.c_f64p)
@@ -292,20 +294,33 @@ class Step:
         calculatePvalues() caller receives."""
         L, lib, eng = self.L, self.lib, self.eng
         cov = C.c_void_p()
+        tm = {}
+        t0 = time.perf_counter()
+
+        def lap(name):
+            nonlocal t0
+            t1 = time.perf_counter()
+            tm[name] = tm.get(name, 0.0) + (t1 - t0) * 1e3
+            t0 = t1
+
         L.check(lib.dfb_cov_from_dense(eng.h, self.n, self.N, L.DFB_I32, host_cov.ctypes.data_as(C.c_void_p), self.N,
                                        L.ptr(self.pl, C.c_int32), len(self.pl), self.work["pos_first"], C.byref(cov)))
+        lap("upload_coverage")
         d2h = 0
         try:
             L.check(lib.dfb_preprocess(eng.h, cov, 32.0, None, 0))
-            F = np.empty(self.N)
+            lap("preprocess")
+            F = self._F_host
             L.check(lib.dfb_fstats(eng.h, cov, self._fp(self.mod), self.mod.shape[1], self._fp(self.mod0),
                                    self.mod0.shape[1], 0.0, self._fp(F)))
             d2h += F.nbytes
+            lap("calculateStats+download_F")
             rh, nh = C.c_void_p(), C.c_void_p()
             rc = L.check(lib.dfb_calculate_pvalues(eng.h, cov, self._fp(F), self._fp(self.mod), self.mod.shape[1],
                                                    self._fp(self.mod0), self.mod0.shape[1], 0.0,
                                                    L.ptr(self.perm, C.c_int32), self.perm.shape[0], -self.cut, self.cut,
                                                    0, 3000, C.byref(rh), C.byref(nh), None))
+            lap("calculatePvalues")
             if rc == 0:
                 R, M = int(lib.dfb_regions_count(rh)), int(lib.dfb_nulls_count(nh))
                 st, en, ist, ien, cl = (np.empty(R, dtype=np.int32) for _ in range(5))
@@ -315,14 +330,20 @@ class Step:
                                             L.ptr(cl, C.c_int32), self._fp(cll)))
                 L.check(lib.dfb_regions_get_pvalues(rh, self._fp(pv)))
                 L.check(lib.dfb_regions_view_means(eng.h, rh, cov, -1, self._fp(mc)))
-                ns, na = np.empty(2 * M), np.empty(2 * M)
-                nw, npid = np.empty(2 * M, dtype=np.int32), np.empty(2 * M, dtype=np.int32)
+                # caller-owned result vectors, reused across steps (grown when needed)
+                if getattr(self, "_null_cap", 0) < 2 * M:
+                    self._null_cap = int(2 * M * 1.1) + 16
+                    self._nbuf = (np.empty(self._null_cap), np.empty(self._null_cap),
+                                  np.empty(self._null_cap, dtype=np.int32), np.empty(self._null_cap, dtype=np.int32))
+                ns, na, nw, npid = (a[:2 * M] for a in self._nbuf)
                 L.check(lib.dfb_nulls_get(nh, 1, self._fp(ns), L.ptr(nw, C.c_int32), self._fp(na),
                                           L.ptr(npid, C.c_int32)))
                 d2h += R * (5 * 4 + 5 * 8) + M * (8 + 8 + 4 + 4)
                 lib.dfb_regions_free(rh)
                 lib.dfb_nulls_free(nh)
+                lap("download_regions_nulls")
             h2d = host_cov.nbytes + F.nbytes + self.perm.nbytes
+            self.last_breakdown = tm
             return h2d, d2h
         finally:
             lib.dfb_cov_free(cov)
@@ -472,7 +493,8 @@ def main():
                        "regions": R, "null_regions": M},
             "gpu_launches": int(launches),
             "e2e": {"value": units / e2e_s, "unit": "base*perm F-stats/s", "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
+                    "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
+                    "last_step_breakdown_ms": {k: round(v, 3) for k, v in step.last_breakdown.items()}},
             "clocks": sampler.result()}
     if rank == 0:
         peaks = {}

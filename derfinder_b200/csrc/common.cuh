@@ -67,6 +67,7 @@ struct dfb_ctx {
     // pinned staging for small D2H reads
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
+    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
 };
 
 namespace dfb {
@@ -144,6 +145,9 @@ struct DevBuf {
 
 int h2d(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);
 int d2h(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);  // synchronises the stream
+// pageable <-> device through pinned, double-buffered staging; both return with the copy complete
+int d2h_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);
+int h2d_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);
 
 // device-wide exclusive scan of `n` uint32 counts into int64 offsets; total_dev[0] = sum.
 int exclusive_scan_u32(dfb_ctx* ctx, const uint32_t* in, int64_t* out, int64_t n, int64_t* total_dev,

@@ -669,8 +669,8 @@ int dfb_cov_get_position(const dfb_cov* c, int32_t* lengths, int* first) {
 int dfb_cov_get_column(const dfb_cov* c, int sample, void* out) {
     DFB_REQUIRE(c && out, "dfb_cov_get_column: NULL argument");
     DFB_REQUIRE(sample >= 0 && sample < c->n, "sample %d out of range", sample);
-    if (c->dtype == DFB_I32) return d2h(c->ctx, out, c->xi.p + (size_t)sample * c->ld, (size_t)c->N * 4);
-    return d2h(c->ctx, out, c->xd.p + (size_t)sample * c->ld, (size_t)c->N * 8);
+    if (c->dtype == DFB_I32) return d2h_big(c->ctx, out, c->xi.p + (size_t)sample * c->ld, (size_t)c->N * 4);
+    return d2h_big(c->ctx, out, c->xd.p + (size_t)sample * c->ld, (size_t)c->N * 8);
 }
 
 int dfb_cov_get_mean(const dfb_cov* c, double* out) {
@@ -679,7 +679,7 @@ int dfb_cov_get_mean(const dfb_cov* c, double* out) {
         set_error("meanCoverage is not available (filter with returnMean or run dfb_preprocess)");
         return DFB_ESTATE;
     }
-    return d2h(c->ctx, out, c->mean.p, (size_t)c->N * sizeof(double));
+    return d2h_big(c->ctx, out, c->mean.p, (size_t)c->N * sizeof(double));
 }
 
 int dfb_preprocess(dfb_ctx* ctx, dfb_cov* c, double scalefac, const int32_t* group_of_sample, int n_groups) {
@@ -779,13 +779,13 @@ int dfb_cov_get_processed_column(const dfb_cov* c, int sample, double* out) {
         set_error("coverageProcessed is not available: run dfb_preprocess first");
         return DFB_ESTATE;
     }
-    return d2h(c->ctx, out, c->y.p + (size_t)sample * c->ld, (size_t)c->N * sizeof(double));
+    return d2h_big(c->ctx, out, c->y.p + (size_t)sample * c->ld, (size_t)c->N * sizeof(double));
 }
 
 int dfb_cov_get_group_mean(const dfb_cov* c, int group, double* out) {
     DFB_REQUIRE(c && out, "dfb_cov_get_group_mean: NULL argument");
     DFB_REQUIRE(group >= 0 && group < c->G, "group %d out of range (%d groups)", group, c->G);
-    return d2h(c->ctx, out, c->gmean.p + (size_t)group * c->ld, (size_t)c->N * sizeof(double));
+    return d2h_big(c->ctx, out, c->gmean.p + (size_t)group * c->ld, (size_t)c->N * sizeof(double));
 }
 
 int64_t dfb_chunk_lengths(int64_t N, double chunksize, int mc_cores, int64_t* lens, int64_t cap) {

@@ -1,6 +1,8 @@
 // Context, error string, copies, device-wide scan.
 #include <stdarg.h>
 
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace dfb {
@@ -24,6 +26,59 @@ int h2d(dfb_ctx* ctx, void* dst, const void* src, size_t bytes) {
 
 int d2h(dfb_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (bytes) DFB_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DFB_OK;
+}
+
+// Large pageable host buffers (R vectors, numpy arrays) are moved through two pinned staging
+// buffers so the DMA runs at PCIe speed and overlaps the host-side memcpy of the previous chunk.
+constexpr size_t STAGE_BYTES = 16u << 20;
+
+static int ensure_staging(dfb_ctx* ctx) {
+    if (ctx->pinned) return DFB_OK;
+    DFB_CUDA(cudaMallocHost(&ctx->pinned, 2 * STAGE_BYTES));
+    ctx->pinned_bytes = 2 * STAGE_BYTES;
+    for (int i = 0; i < 2; ++i) DFB_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+    return DFB_OK;
+}
+
+int d2h_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes < (1u << 20)) return d2h(ctx, dst, src, bytes);
+    DFB_TRY(ensure_staging(ctx));
+    char* pin = (char*)ctx->pinned;
+    const size_t nchunk = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
+    for (size_t i = 0; i <= nchunk; ++i) {
+        if (i < nchunk) {
+            const size_t off = i * STAGE_BYTES, sz = std::min(STAGE_BYTES, bytes - off);
+            DFB_CUDA(cudaMemcpyAsync(pin + (i & 1) * STAGE_BYTES, (const char*)src + off, sz, cudaMemcpyDeviceToHost,
+                                     ctx->stream));
+            DFB_CUDA(cudaEventRecord(ctx->stage_ev[i & 1], ctx->stream));
+        }
+        if (i > 0) {
+            const size_t j = i - 1, off = j * STAGE_BYTES, sz = std::min(STAGE_BYTES, bytes - off);
+            DFB_CUDA(cudaEventSynchronize(ctx->stage_ev[j & 1]));
+            memcpy((char*)dst + off, pin + (j & 1) * STAGE_BYTES, sz);
+        }
+    }
+    return DFB_OK;
+}
+
+int h2d_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes < (1u << 20)) {
+        DFB_TRY(h2d(ctx, dst, src, bytes));
+        DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return DFB_OK;
+    }
+    DFB_TRY(ensure_staging(ctx));
+    char* pin = (char*)ctx->pinned;
+    const size_t nchunk = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
+    for (size_t i = 0; i < nchunk; ++i) {
+        const size_t off = i * STAGE_BYTES, sz = std::min(STAGE_BYTES, bytes - off);
+        if (i >= 2) DFB_CUDA(cudaEventSynchronize(ctx->stage_ev[i & 1]));  // staging buffer free again
+        memcpy(pin + (i & 1) * STAGE_BYTES, (const char*)src + off, sz);
+        DFB_CUDA(cudaMemcpyAsync((char*)dst + off, pin + (i & 1) * STAGE_BYTES, sz, cudaMemcpyHostToDevice, ctx->stream));
+        DFB_CUDA(cudaEventRecord(ctx->stage_ev[i & 1], ctx->stream));
+    }
     DFB_CUDA(cudaStreamSynchronize(ctx->stream));
     return DFB_OK;
 }
@@ -240,7 +295,10 @@ void dfb_destroy(dfb_ctx* c) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
     }
-    if (c->pinned) cudaFreeHost(c->pinned);
+    if (c->pinned) {
+        cudaFreeHost(c->pinned);
+        for (int i = 0; i < 2; ++i) cudaEventDestroy(c->stage_ev[i]);
+    }
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }

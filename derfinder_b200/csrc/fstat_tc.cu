@@ -249,8 +249,15 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_screen_kernel(const ScreenPa
         const bool valid = base < P.N;
         double m = 0.0, yy = 0.0;
         if (valid && P.center) {
-            double acc = P.Y[base];
-            for (int k = 1; k < G.n; ++k) acc = __dadd_rn(acc, P.Y[(size_t)k * P.ld + base]);
+            double acc = 0.0;
+            for (int k0 = 0; k0 < G.n; k0 += 8) {  // 8 independent loads in flight, then the ordered sum
+                double v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = (k0 + e < G.n) ? P.Y[(size_t)(k0 + e) * P.ld + base] : 0.0;
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    if (k0 + e < G.n) acc = (k0 + e == 0) ? v[e] : __dadd_rn(acc, v[e]);
+            }
             m = __ddiv_rn(acc, (double)G.n);
         }
         // every sample is loaded and split once: 8 samples -> one 16-byte chunk of yh (written to
@@ -381,182 +388,217 @@ struct RefineParams {
     const uint32_t* cand;  // [tiles][4][Bpad]
     uint32_t* mask;        // [B][W]
     int64_t W;
-    int64_t* off;          // [B][tiles]
-    int64_t tiles;
+    int64_t* off;          // [B][W] offset of the first value of every 32-base word
+    int64_t tiles128;      // 128-base staging tiles
     double* vals;
     unsigned long long capacity;
     unsigned long long* cursor;
 };
 
 constexpr int RF_THREADS = 128;
-constexpr int RF_PB = 16;  // permutations per block of work
+constexpr int RF_CHUNK = 2048;  // values a warp reserves from the global cursor at a time
 
+static int refine_qstride(int p) { return (p + 1) & ~1; }  // rows of Q padded to 16 bytes
+
+static size_t refine_smem_bytes(int n, int p) {
+    // ys [n][128] + Qs [n][qstride] + yy [128] + per warp: list [1024] u16, ew [32] u32, perm rows [32][n] u8
+    return ((size_t)n * TC_M + (size_t)n * refine_qstride(p) + TC_M) * 8 +
+           4 * (1024 * 2 + 32 * 4 + (size_t)round_up(32 * n, 16)) + 64;
+}
+
+// Persistent, warp-autonomous refinement.  A CTA stages one 128-base tile (centred FP64 log2
+// coverage, read from HBM once); each of its 4 warps then owns 32 bases (= one mask word per
+// permutation) and walks the permutations 32 at a time without any block-level barrier:
+//   lane = permutation: candidate word -> per-warp work list, sorted by (permutation, base);
+//   lane = work item  : exact F with the FP64 contract of fstat.cu; exceedances are compacted
+//                       straight into the value buffer (ballot prefix keeps the list order, which
+//                       is the (permutation, base) order the region finder needs) and set a bit
+//                       of the exact word;
+//   lane = permutation: exact word + value offset out.
+// Value storage comes from per-warp chunks of the global cursor (one atomic per RF_CHUNK values).
+// Value tiles are 32 bases wide: off[b][w].
 // PT: number of model columns when <= 8 (accumulators in registers), 0 = generic
 template <int PT>
 __global__ void __launch_bounds__(RF_THREADS) fstat_refine_kernel(const RefineParams P) {
     extern __shared__ __align__(16) unsigned char smem_rf[];
     const int n = P.n, p = P.p;
-    double* ys = reinterpret_cast<double*>(smem_rf);            // [n][128] centred
-    double* Qs = ys + (size_t)n * TC_M;                          // [n][p]
-    double* yy_s = Qs + (size_t)n * p;                           // [128]
-    double* fv_s = yy_s + TC_M;                                  // [RF_PB][128] exact F of candidates
-    int32_t* idx_s = reinterpret_cast<int32_t*>(fv_s + RF_PB * TC_M);  // [RF_PB][n]
-    uint32_t* cw_s = reinterpret_cast<uint32_t*>(idx_s + RF_PB * n);   // [RF_PB][4] candidate words
-    uint32_t* ew_s = cw_s + RF_PB * 4;                                   // [RF_PB][4] exact words
-    int32_t* pre_s = reinterpret_cast<int32_t*>(ew_s + RF_PB * 4);      // [RF_PB*4 + 1] list offsets
-    uint16_t* list_s = reinterpret_cast<uint16_t*>(pre_s + RF_PB * 4 + 1);  // [RF_PB*128] entries
-    __shared__ unsigned long long gbase_s;
-
+    const int qs = (p + 1) & ~1;
+    double* ys = reinterpret_cast<double*>(smem_rf);  // [n][128] centred
+    double* Qs = ys + (size_t)n * TC_M;               // [n][qs]
+    double* yy_s = Qs + (size_t)n * qs;               // [128]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t tile = blockIdx.x;
-    const int64_t base0 = tile * TC_M;
+    const size_t per_warp = 1024 * 2 + 32 * 4 + (size_t)((32 * n + 15) & ~15);
+    unsigned char* wbase = reinterpret_cast<unsigned char*>(yy_s + TC_M) + (size_t)warp * per_warp;
+    uint16_t* list_w = reinterpret_cast<uint16_t*>(wbase);        // [1024] (perm << 5) | base
+    uint32_t* ew_w = reinterpret_cast<uint32_t*>(list_w + 1024);  // [32] exact words
+    unsigned char* ix_w = reinterpret_cast<unsigned char*>(ew_w + 32);  // [32][n] permutation rows
 
-    for (int e = tid; e < n * p; e += RF_THREADS) Qs[e] = P.q[e];
-    {
-        const int64_t base = base0 + tid;
-        double acc = 0.0;
-        if (base < P.N) {
-            acc = P.Y[base];
-            ys[tid] = acc;
-            for (int k = 1; k < n; ++k) {
-                const double v = P.Y[(size_t)k * P.ld + base];
-                ys[(size_t)k * TC_M + tid] = v;
-                acc = __dadd_rn(acc, v);
-            }
-        } else {
-            for (int k = 0; k < n; ++k) ys[(size_t)k * TC_M + tid] = 0.0;
-        }
-        const double m = P.center ? __ddiv_rn(acc, (double)n) : 0.0;
-        double s = 0.0;
-        for (int k = 0; k < n; ++k) {
-            const double v = __dsub_rn(ys[(size_t)k * TC_M + tid], m);
-            ys[(size_t)k * TC_M + tid] = v;
-            s = fma(v, v, s);
-        }
-        yy_s[tid] = s;
+    for (int e = tid; e < n * qs; e += RF_THREADS) {
+        const int k = e / qs, j = e - k * qs;
+        Qs[e] = j < p ? P.q[(size_t)k * p + j] : 0.0;
     }
+    unsigned long long chunk_ptr = 0;  // warp-uniform: next free value slot of the warp's chunk
+    int chunk_left = 0;
+    const bool num_is_sd = P.dfnum == 1.0;  // x / 1.0 == x: skip one IEEE division
 
-    for (int64_t b0 = 0; b0 < P.B; b0 += RF_PB) {
-        const int nb = (int)min((int64_t)RF_PB, P.B - b0);
-        __syncthreads();  // previous block fully consumed (and, first time, the tile is staged)
-        // candidate words + permutation rows of this block
-        if (tid < RF_PB * 4) {
-            const int q = tid >> 2, w = tid & 3;
-            uint32_t cw = 0;
-            if (q < nb) cw = P.cand[((size_t)tile * 4 + w) * P.Bpad + b0 + q];
-            const int64_t rem = P.N - (base0 + w * 32);
-            if (rem < 32) cw = rem > 0 ? (cw & ((1u << rem) - 1u)) : 0u;
-            cw_s[tid] = cw;
-            ew_s[tid] = 0u;
-        }
-        for (int e = tid; e < nb * n; e += RF_THREADS) idx_s[e] = P.idx[b0 * n + e];
-        __syncthreads();
-        // work list: exclusive scan of the 64 popcounts (two warps' worth -> warp 0 does it)
-        if (warp == 0) {
-            const int c0 = __popc(cw_s[lane]), c1 = __popc(cw_s[lane + 32]);
-            int inc = c0 + c1;
+    for (int64_t tile = blockIdx.x; tile < P.tiles128; tile += gridDim.x) {
+        const int64_t base0 = tile * TC_M;
+        __syncthreads();  // every warp is done with the previous tile (and Qs is staged)
+        {
+            const int64_t base = base0 + tid;
+            double acc = 0.0;
+            if (base < P.N) {
+                // batches of 8 independent loads, then the ordered sum
+                for (int k0 = 0; k0 < n; k0 += 8) {
+                    double v[8];
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            // entries ordered: lanes own words (lane) and (lane + 32); order is irrelevant here
-            pre_s[lane] = inc - c0 - c1;
-            pre_s[lane + 32] = inc - c1;
-            if (lane == 31) pre_s[64] = inc;
-        }
-        __syncthreads();
-        if (tid < RF_PB * 4) {
-            uint32_t cw = cw_s[tid];
-            int o = pre_s[tid];
-            const int q = tid >> 2, w = tid & 3;
-            while (cw) {
-                const int bit = __ffs(cw) - 1;
-                cw &= cw - 1;
-                list_s[o++] = (uint16_t)((q << 7) | (w * 32 + bit));
-            }
-        }
-        __syncthreads();
-        const int nwork = pre_s[64];
-        for (int e = tid; e < nwork; e += RF_THREADS) {
-            const int ent = list_s[e];
-            const int q = ent >> 7, bl = ent & 127;
-            const int32_t* ix = idx_s + q * n;
-            double s0 = 0.0, sd = 0.0;
-            // S_j in k order, s0 / sd in j order: identical chains to the dense kernel
-            if (PT > 0) {
-                double S[PT > 0 ? PT : 1];
+                    for (int e = 0; e < 8; ++e) v[e] = (k0 + e < n) ? P.Y[(size_t)(k0 + e) * P.ld + base] : 0.0;
 #pragma unroll
-                for (int j = 0; j < PT; ++j) S[j] = 0.0;
-                for (int k = 0; k < n; ++k) {
-                    const double yv = ys[(size_t)k * TC_M + bl];
-                    const double* qrow = Qs + (size_t)ix[k] * PT;
-#pragma unroll
-                    for (int j = 0; j < PT; ++j) S[j] = fma(yv, qrow[j], S[j]);
-                }
-#pragma unroll
-                for (int j = 0; j < PT; ++j) {
-                    if (j < P.p0) s0 = fma(S[j], S[j], s0);
-                    else sd = fma(S[j], S[j], sd);
+                    for (int e = 0; e < 8; ++e)
+                        if (k0 + e < n) {
+                            ys[(size_t)(k0 + e) * TC_M + tid] = v[e];
+                            acc = (k0 + e == 0) ? v[e] : __dadd_rn(acc, v[e]);
+                        }
                 }
             } else {
-                for (int j = 0; j < p; ++j) {
-                    double S = 0.0;
-                    for (int k = 0; k < n; ++k) S = fma(ys[(size_t)k * TC_M + bl], Qs[(size_t)ix[k] * p + j], S);
-                    if (j < P.p0) s0 = fma(S, S, s0);
-                    else sd = fma(S, S, sd);
-                }
+                for (int k = 0; k < n; ++k) ys[(size_t)k * TC_M + tid] = 0.0;
             }
-            double rss1 = __dsub_rn(__dsub_rn(yy_s[bl], s0), sd);
-            if (rss1 < 0.0) rss1 = 0.0;
-            const double num = __ddiv_rn(sd, P.dfnum);
-            const double den = __dadd_rn(P.adjust_f, __ddiv_rn(rss1, P.dfden));
-            const double f = __ddiv_rn(num, den);
-            if (f >= P.U) {
-                fv_s[q * TC_M + bl] = f;
-                atomicOr(&ew_s[q * 4 + (bl >> 5)], 1u << (bl & 31));
+            const double m = P.center ? __ddiv_rn(acc, (double)n) : 0.0;
+            double s = 0.0;
+            for (int k = 0; k < n; ++k) {
+                const double v = __dsub_rn(ys[(size_t)k * TC_M + tid], m);
+                ys[(size_t)k * TC_M + tid] = v;
+                s = fma(v, v, s);
             }
+            yy_s[tid] = s;
         }
         __syncthreads();
-        // exact mask words out; value offsets: scan of the 64 popcounts in (perm, word) order
-        if (warp == 0) {
-            const int e0 = 2 * lane, e1 = 2 * lane + 1;  // consecutive entries keep (perm, word) order
-            const int c0 = __popc(ew_s[e0]), c1 = __popc(ew_s[e1]);
-            int inc = c0 + c1;
+
+        const int64_t gw = tile * 4 + warp;  // global mask word of this warp's 32 bases
+        if (gw >= P.W) continue;             // warp-uniform (tail tile)
+        const int64_t rem = P.N - gw * 32;
+        const uint32_t valid_bits = rem >= 32 ? 0xffffffffu : ((1u << rem) - 1u);
+        const uint32_t* crow = P.cand + (size_t)gw * P.Bpad;
+        const double* ycol = ys + warp * 32;
+        const double* yyw = yy_s + warp * 32;
+
+        for (int64_t b0 = 0; b0 < P.B; b0 += 32) {
+            const int64_t b = b0 + lane;
+            const uint32_t cw = (b < P.B) ? (crow[b] & valid_bits) : 0u;
+            // work list, sorted by (permutation, base)
+            const int c = __popc(cw);
+            int inc = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
                 const int t = __shfl_up_sync(0xffffffffu, inc, o);
                 if (lane >= o) inc += t;
             }
-            const int total = __shfl_sync(0xffffffffu, inc, 31);
-            unsigned long long gb = 0;
-            if (lane == 0 && total > 0) gb = atomicAdd(P.cursor, (unsigned long long)total);
-            gb = __shfl_sync(0xffffffffu, gb, 0);
-            if (lane == 0) gbase_s = gb;
-            pre_s[e0] = inc - c0 - c1;
-            pre_s[e1] = inc - c1;
-        }
-        __syncthreads();
-        if (tid < RF_PB * 4) {
-            const int q = tid >> 2, w = tid & 3;
-            if (q < nb) {
-                const int64_t b = b0 + q;
-                const int64_t gw = tile * 4 + w;
-                if (gw < P.W) P.mask[b * P.W + gw] = ew_s[tid];
-                if (w == 0) P.off[b * P.tiles + tile] = (int64_t)gbase_s + pre_s[tid];
+            const int nwork = __shfl_sync(0xffffffffu, inc, 31);
+            if (nwork == 0) {  // nothing to refine for these 32 permutations
+                if (b < P.B) {
+                    P.mask[b * P.W + gw] = 0u;
+                    P.off[b * P.W + gw] = 0;
+                }
+                continue;
             }
-        }
-        // values: thread = base; for every permutation of the block with my bit set
-        {
-            const int w = tid >> 5;
-            for (int q = 0; q < nb; ++q) {
-                const uint32_t ew = ew_s[q * 4 + w];
-                if ((ew >> lane) & 1u) {
-                    const unsigned long long dst =
-                        gbase_s + (unsigned long long)pre_s[q * 4 + w] + __popc(ew & ((1u << lane) - 1u));
-                    if (dst < P.capacity) P.vals[dst] = fv_s[q * TC_M + tid];
+            ew_w[lane] = 0u;
+            {
+                uint32_t t = cw;
+                int o = inc - c;
+                while (t) {
+                    const int bit = __ffs(t) - 1;
+                    t &= t - 1;
+                    list_w[o++] = (uint16_t)((lane << 5) | bit);
                 }
             }
+            // permutation rows of this block as bytes (n <= 255), coalesced over the [32][n] ints
+            {
+                const int64_t nb = min((int64_t)32, P.B - b0);
+                const int32_t* src = P.idx + b0 * n;
+                for (int e = lane; e < (int)nb * n; e += 32) ix_w[e] = (unsigned char)src[e];
+            }
+            if (nwork > chunk_left) {  // warp-uniform: grab a fresh chunk (the remainder is left unused)
+                unsigned long long g = 0;
+                if (lane == 0) g = atomicAdd(P.cursor, (unsigned long long)RF_CHUNK);
+                chunk_ptr = __shfl_sync(0xffffffffu, g, 0);
+                chunk_left = RF_CHUNK;
+            }
+            __syncwarp();
+            unsigned long long run = chunk_ptr;
+            for (int e0 = 0; e0 < nwork; e0 += 32) {
+                const int e = e0 + lane;
+                bool pass = false;
+                double f = 0.0;
+                int q = 0, bl = 0;
+                if (e < nwork) {
+                    const int ent = list_w[e];
+                    q = ent >> 5;
+                    bl = ent & 31;
+                    const unsigned char* ix = ix_w + q * n;
+                    double s0 = 0.0, sd = 0.0;
+                    // S_j in k order, s0 / sd in j order: identical chains to the dense kernel
+                    if (PT > 0) {
+                        constexpr int QS = (PT + 1) & ~1;
+                        double S[PT > 0 ? PT : 1];
+#pragma unroll
+                        for (int j = 0; j < PT; ++j) S[j] = 0.0;
+#pragma unroll 4
+                        for (int k = 0; k < n; ++k) {
+                            const double yv = ycol[(size_t)k * TC_M + bl];
+                            const double2* qrow = reinterpret_cast<const double2*>(Qs + (size_t)ix[k] * QS);
+#pragma unroll
+                            for (int j2 = 0; j2 < QS / 2; ++j2) {
+                                const double2 qq = qrow[j2];
+                                S[2 * j2] = fma(yv, qq.x, S[2 * j2]);
+                                if (2 * j2 + 1 < PT) S[2 * j2 + 1] = fma(yv, qq.y, S[2 * j2 + 1]);
+                            }
+                        }
+#pragma unroll
+                        for (int j = 0; j < PT; ++j) {
+                            if (j < P.p0) s0 = fma(S[j], S[j], s0);
+                            else sd = fma(S[j], S[j], sd);
+                        }
+                    } else {
+                        for (int j = 0; j < p; ++j) {
+                            double S = 0.0;
+                            for (int k = 0; k < n; ++k)
+                                S = fma(ycol[(size_t)k * TC_M + bl], Qs[(size_t)ix[k] * qs + j], S);
+                            if (j < P.p0) s0 = fma(S, S, s0);
+                            else sd = fma(S, S, sd);
+                        }
+                    }
+                    double rss1 = __dsub_rn(__dsub_rn(yyw[bl], s0), sd);
+                    if (rss1 < 0.0) rss1 = 0.0;
+                    const double num = num_is_sd ? sd : __ddiv_rn(sd, P.dfnum);
+                    const double den = __dadd_rn(P.adjust_f, __ddiv_rn(rss1, P.dfden));
+                    f = __ddiv_rn(num, den);
+                    pass = f >= P.U;
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                if (pass) {
+                    const unsigned long long dst = run + __popc(bal & ((1u << lane) - 1u));
+                    if (dst < P.capacity) P.vals[dst] = f;
+                    atomicOr(&ew_w[q], 1u << bl);
+                }
+                run += __popc(bal);
+            }
+            __syncwarp();
+            // lane = permutation again: exact word and the offset of its first value
+            const uint32_t ew = ew_w[lane];
+            const int c2 = __popc(ew);
+            int inc2 = c2;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc2, o);
+                if (lane >= o) inc2 += t;
+            }
+            if (b < P.B) {
+                P.mask[b * P.W + gw] = ew;
+                P.off[b * P.W + gw] = (int64_t)(chunk_ptr + (unsigned long long)(inc2 - c2));
+            }
+            chunk_left -= (int)(run - chunk_ptr);
+            chunk_ptr = run;
+            __syncwarp();
         }
     }
 }
@@ -632,13 +674,12 @@ bool screen_supported(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& 
     if (!ctx->opt_screen) return false;
     if (!(hi > 0.0) || !(lo < 0.0)) return false;      // one-sided positive cutoff only
     if (cov->n - mb.p <= 0 || !(adjust_f >= 0.0)) return false;
+    if (cov->n > 255) return false;  // the refinement keeps permutation rows as bytes
     ScreenGeom g;
     const size_t limit = std::min<size_t>(ctx->smem_optin, 200 * 1024);
     if (!screen_geometry(cov, mb, 1, limit, &g)) return false;
     // refinement tile must fit too
-    const size_t rf = ((size_t)cov->n * TC_M + (size_t)cov->n * mb.p + TC_M + RF_PB * TC_M) * 8 +
-                      (size_t)RF_PB * cov->n * 4 + RF_PB * 4 * 8 + (RF_PB * 4 + 1) * 4 + RF_PB * TC_M * 2 + 64;
-    return rf <= limit;
+    return refine_smem_bytes(cov->n, mb.p) <= limit;
 }
 
 // Screen + refine for one batch of permutations; fills the same PermBatch the dense kernel does.
@@ -699,21 +740,24 @@ int fstat_perm_batch_screen(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& 
 
     out->rows = B;
     out->W = ceil_div(cov->N, 32);
-    out->tile_bases = TC_M;
-    out->tiles = G.tiles;
+    out->tile_bases = 32;  // the refinement emits one value offset per 32-base word
+    out->tiles = out->W;
     DFB_TRY(out->mask.alloc(ctx, (size_t)out->rows * out->W));
     DFB_TRY(out->off.alloc(ctx, (size_t)out->rows * out->tiles));
     DevBuf<unsigned long long> cursor;
     DFB_TRY(cursor.alloc(ctx, 1));
     const size_t dense = (size_t)B * (size_t)cov->N;
-    size_t cap = std::min(dense, std::max<size_t>(capacity_hint, 1024));
-    const size_t rf_smem = ((size_t)cov->n * TC_M + (size_t)cov->n * mb.p + TC_M + RF_PB * TC_M) * 8 +
-                           (size_t)RF_PB * cov->n * 4 + RF_PB * 4 * 8 + (RF_PB * 4 + 1) * 4 + RF_PB * TC_M * 2 + 64;
+    const size_t rf_smem = refine_smem_bytes(cov->n, mb.p);
+    // persistent grid: as many CTAs as fit (4 per SM is enough to hide the per-tile staging)
+    const int rf_grid = (int)std::min<int64_t>(G.tiles, (int64_t)ctx->sm_count * 4);
+    // every warp may leave one partly used chunk behind
+    const size_t slack = (size_t)rf_grid * 4 * RF_CHUNK;
+    size_t cap = std::min(dense, std::max<size_t>(capacity_hint, 1024)) + slack;
     auto launch_refine = [&](const RefineParams& R) -> int {
         auto go = [&](auto kern) -> int {
             DFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rf_smem));
             KTimer t(ctx, DFB_K_FSTAT, 1);
-            kern<<<(unsigned)G.tiles, RF_THREADS, rf_smem, ctx->stream>>>(R);
+            kern<<<rf_grid, RF_THREADS, rf_smem, ctx->stream>>>(R);
             return DFB_OK;
         };
         switch (mb.p) {
@@ -751,7 +795,7 @@ int fstat_perm_batch_screen(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& 
         R.mask = out->mask.p;
         R.W = out->W;
         R.off = out->off.p;
-        R.tiles = out->tiles;
+        R.tiles128 = G.tiles;
         R.vals = out->vals.p;
         R.capacity = cap;
         R.cursor = cursor.p;
@@ -759,9 +803,17 @@ int fstat_perm_batch_screen(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& 
         DFB_CUDA(cudaGetLastError());
         unsigned long long used = 0;
         DFB_TRY(d2h(ctx, &used, cursor.p, sizeof used));
-        out->nvals = (int64_t)used;
+        out->nvals = (int64_t)used;  // allocated value slots (exceedances + unused chunk tails)
         if (used <= cap) {
             if (ncand_out) {
+                DevBuf<unsigned long long> cntm;
+                DFB_TRY(cntm.alloc(ctx, 1));
+                DFB_TRY(cntm.zero());
+                popcount_words_kernel<<<grid_for(out->rows * out->W, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(
+                    out->mask.p, out->rows * out->W, cntm.p);
+                unsigned long long hm = 0;
+                DFB_TRY(d2h(ctx, &hm, cntm.p, sizeof hm));
+                out->nvals = (int64_t)hm;  // debug hook: report the exact exceedance count
                 DevBuf<unsigned long long> cnt;
                 DFB_TRY(cnt.alloc(ctx, 1));
                 DFB_TRY(cnt.zero());

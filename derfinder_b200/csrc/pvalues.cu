@@ -21,6 +21,27 @@ __global__ void add_perm_offset_kernel(int32_t* __restrict__ perm, int64_t n, in
     if (i < n) perm[i] += offset;
 }
 
+// source index of every row of the duplicated null table ([r1..rk, r1..rk] per permutation)
+__global__ void dup_index_kernel(const int64_t* __restrict__ pre, int64_t B, int64_t M, int64_t* __restrict__ src) {
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < 2 * M; o += (int64_t)gridDim.x * blockDim.x) {
+        int64_t lo = 0, hi = B;  // largest b with 2*pre[b] <= o
+        while (hi - lo > 1) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (2 * pre[mid] <= o) lo = mid;
+            else hi = mid;
+        }
+        const int64_t k = pre[lo + 1] - pre[lo];
+        const int64_t r = o - 2 * pre[lo];
+        src[o] = pre[lo] + (r >= k ? r - k : r);
+    }
+}
+
+template <typename T>
+__global__ void gather_kernel(const T* __restrict__ in, const int64_t* __restrict__ src, int64_t n, T* __restrict__ out) {
+    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x)
+        out[o] = in[src[o]];
+}
+
 static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const double* mod0, int p0,
                            double adjust_f, const int32_t* perm_idx, int64_t B, double lo, double hi,
                            int32_t max_region_gap, dfb_nulls** out) {
@@ -336,7 +357,7 @@ int dfb_fstats(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const doubl
     cov->has_f = false;
     if (cov->N > 0) DFB_TRY(fstat_observed(ctx, cov, mb, adjust_f, cov->fstats.p));
     cov->has_f = true;
-    if (fstats_out) DFB_TRY(d2h(ctx, fstats_out, cov->fstats.p, (size_t)cov->N * sizeof(double)));
+    if (fstats_out) DFB_TRY(d2h_big(ctx, fstats_out, cov->fstats.p, (size_t)cov->N * sizeof(double)));
     else DFB_CUDA(cudaStreamSynchronize(ctx->stream));
     return DFB_OK;
 }
@@ -367,33 +388,51 @@ int dfb_nulls_get(const dfb_nulls* nl, int dup, double* stat, int32_t* width, do
     DFB_REQUIRE(nl, "dfb_nulls_get: NULL handle");
     const size_t M = (size_t)nl->count;
     if (M == 0) return DFB_OK;
-    std::vector<double> hs, ha;
-    std::vector<int32_t> hw, hp;
     dfb_ctx* ctx = nl->ctx;
-    if (stat) { hs.resize(M); DFB_TRY(d2h(ctx, hs.data(), nl->stat.p, M * 8)); }
-    if (area) { ha.resize(M); DFB_TRY(d2h(ctx, ha.data(), nl->area.p, M * 8)); }
-    if (width) { hw.resize(M); DFB_TRY(d2h(ctx, hw.data(), nl->width.p, M * 4)); }
-    if (permutation) { hp.resize(M); DFB_TRY(d2h(ctx, hp.data(), nl->perm.p, M * 4)); }
     if (!dup) {
-        if (stat) memcpy(stat, hs.data(), M * 8);
-        if (area) memcpy(area, ha.data(), M * 8);
-        if (width) memcpy(width, hw.data(), M * 4);
-        if (permutation) memcpy(permutation, hp.data(), M * 4);
+        if (stat) DFB_TRY(d2h_big(ctx, stat, nl->stat.p, M * 8));
+        if (area) DFB_TRY(d2h_big(ctx, area, nl->area.p, M * 8));
+        if (width) DFB_TRY(d2h_big(ctx, width, nl->width.p, M * 4));
+        if (permutation) DFB_TRY(d2h_big(ctx, permutation, nl->perm.p, M * 4));
         return DFB_OK;
     }
-    // the reference appends every permutation's regions twice: [r1..rk, r1..rk] (:346-354)
-    size_t src = 0, dst = 0;
-    for (size_t b = 0; b < nl->per_perm.size(); ++b) {
-        const size_t k = (size_t)nl->per_perm[b];
-        for (int rep = 0; rep < 2; ++rep) {
-            if (stat) memcpy(stat + dst, hs.data() + src, k * 8);
-            if (area) memcpy(area + dst, ha.data() + src, k * 8);
-            if (width) memcpy(width + dst, hw.data() + src, k * 4);
-            if (permutation) memcpy(permutation + dst, hp.data() + src, k * 4);
-            dst += k;
-        }
-        src += k;
+    // the reference appends every permutation's regions twice: [r1..rk, r1..rk] (:346-354).  The
+    // duplicated layout is produced on the device (gather) and downloaded straight into the
+    // caller's buffers.
+    const int64_t B = (int64_t)nl->per_perm.size();
+    std::vector<int64_t> pre((size_t)B + 1, 0);
+    for (int64_t b = 0; b < B; ++b) pre[(size_t)b + 1] = pre[(size_t)b] + nl->per_perm[(size_t)b];
+    DevBuf<int64_t> pre_d;
+    DevBuf<int64_t> src_d;
+    DFB_TRY(pre_d.alloc(ctx, (size_t)B + 1));
+    DFB_TRY(src_d.alloc(ctx, 2 * M));
+    DFB_TRY(h2d(ctx, pre_d.p, pre.data(), pre.size() * sizeof(int64_t)));
+    {
+        KTimer t(ctx, DFB_K_PVAL);
+        dup_index_kernel<<<grid_for((int64_t)(2 * M), 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(pre_d.p, B,
+                                                                                                      (int64_t)M, src_d.p);
     }
+    DFB_CUDA(cudaGetLastError());
+    DFB_CUDA(cudaStreamSynchronize(ctx->stream));  // `pre` is a local
+    DevBuf<double> t8;
+    DevBuf<int32_t> t4;
+    DFB_TRY(t8.alloc(ctx, 2 * M));
+    DFB_TRY(t4.alloc(ctx, 2 * M));
+    const int grid = grid_for((int64_t)(2 * M), 256, ctx->sm_count, 16);
+    auto get8 = [&](const double* src, double* dst) -> int {
+        if (!dst) return DFB_OK;
+        gather_kernel<double><<<grid, 256, 0, ctx->stream>>>(src, src_d.p, (int64_t)(2 * M), t8.p);
+        return d2h_big(ctx, dst, t8.p, 2 * M * 8);
+    };
+    auto get4 = [&](const int32_t* src, int32_t* dst) -> int {
+        if (!dst) return DFB_OK;
+        gather_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(src, src_d.p, (int64_t)(2 * M), t4.p);
+        return d2h_big(ctx, dst, t4.p, 2 * M * 4);
+    };
+    DFB_TRY(get8(nl->stat.p, stat));
+    DFB_TRY(get8(nl->area.p, area));
+    DFB_TRY(get4(nl->width.p, width));
+    DFB_TRY(get4(nl->perm.p, permutation));
     return DFB_OK;
 }
 
@@ -524,8 +563,7 @@ int dfb_calculate_pvalues(dfb_ctx* ctx, dfb_cov* cov, const double* fstats, cons
     DFB_REQUIRE(cutoff_lo <= cutoff_hi, "cutoff pair must be sorted (L <= U)");
     if (fstats) {
         DFB_TRY(cov->fstats.alloc(ctx, (size_t)std::max<int64_t>(cov->N, 1)));
-        DFB_TRY(h2d(ctx, cov->fstats.p, fstats, (size_t)cov->N * 8));
-        DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        DFB_TRY(h2d_big(ctx, cov->fstats.p, fstats, (size_t)cov->N * 8));
         cov->has_f = true;
     } else if (!cov->has_f) {
         set_error("dfb_calculate_pvalues: no F-statistics given and none cached");
