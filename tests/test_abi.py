@@ -153,3 +153,22 @@ def test_python_mirror_argument_checks(golden):
             dfb.findRegions(golden.position, golden.fstats, maxClusterGap=1, maxRegionGap=5, cutoff=1)
         except RuntimeError:
             pass  # no GPU here: the call fails loudly after the reference's warning
+
+
+def test_r_shim_typechecks():
+    """r/src/rglue.c (the .Call layer of INTEGRATION.md) must agree with include/derfinder_b200.h.
+    There is no R here, so it is compiled -fsyntax-only against stub R headers."""
+    import shutil
+    import subprocess
+    if shutil.which("gcc") is None:
+        pytest.skip("gcc not available")
+    r = subprocess.run(["gcc", "-fsyntax-only", "-Wall", "-Werror=incompatible-pointer-types", "-Werror=implicit-function-declaration",
+                        "-I", os.path.join(ROOT, "include"), "-I", os.path.join(ROOT, "tests", "r_stub"),
+                        os.path.join(ROOT, "r", "src", "rglue.c")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # every .Call the R glue makes is registered by the shim
+    import re
+    glue = open(os.path.join(ROOT, "r", "R", "engine.R")).read()
+    shim = open(os.path.join(ROOT, "r", "src", "rglue.c")).read()
+    for name in set(re.findall(r"\.Call\((dfbR_\w+)", glue)):
+        assert '{"%s"' % name in shim, name
