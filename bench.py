@@ -349,38 +349,6 @@ class Step:
             lib.dfb_cov_free(cov)
 
 
-def pooled_pvalues(step, rh, nh, B, cut, dist, torch, device):
-    """Genome-wide pooling across ranks (the one exchange step): all-gather of null areas, all-reduce
-    (max) of per-permutation maxima, then p-values / FWER of this rank's regions against the pool."""
-    L, lib, eng = step.L, step.lib, step.eng
-    M = int(lib.dfb_nulls_count(nh))
-    R = int(lib.dfb_regions_count(rh))
-    world = dist.get_world_size()
-    counts = torch.tensor([M], device=device, dtype=torch.int64)
-    allc = torch.empty(world, device=device, dtype=torch.int64)
-    dist.all_gather_into_tensor(allc, counts)
-    cap = int(allc.max().item())
-    mine = torch.full((max(cap, 1),), float("nan"), device=device, dtype=torch.float64)
-    perm = torch.zeros(max(cap, 1), device=device, dtype=torch.int32)
-    L.check(lib.dfb_nulls_copy_dev(nh, C.c_void_p(mine.data_ptr()), C.c_void_p(perm.data_ptr())))
-    pool = torch.empty(world * max(cap, 1), device=device, dtype=torch.float64)
-    dist.all_gather_into_tensor(pool, mine)
-    pool = pool[~torch.isnan(pool)].contiguous()
-    mx = torch.empty(B, device=device, dtype=torch.float64)
-    L.check(lib.dfb_perm_max_dev(eng.h, C.c_void_p(mine.data_ptr()), C.c_void_p(perm.data_ptr()), M, B, -1.0,
-                                 C.c_void_p(mx.data_ptr())))
-    dist.all_reduce(mx, op=dist.ReduceOp.MAX)
-    mx = torch.where(mx < 0, torch.full_like(mx, cut), mx)
-    area = np.empty(R)
-    L.check(lib.dfb_regions_get(rh, None, None, None, step._fp(area), None, None, None, None))
-    a_dev = torch.as_tensor(area, device=device)
-    p_dev = torch.empty(R, device=device, dtype=torch.float64)
-    L.check(lib.dfb_calc_pval_dev(eng.h, C.c_void_p(a_dev.data_ptr()), R, C.c_void_p(pool.data_ptr()), pool.numel(), 2,
-                                  C.c_void_p(p_dev.data_ptr())))
-    fwer = ((mx[None, :] > a_dev[:, None]).sum(dim=1) + 1).double() / (B + 1)
-    return p_dev, fwer, int(pool.numel())
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -403,6 +371,7 @@ def main():
 
     import derfinder_b200 as dfb
     from derfinder_b200 import _lib as L
+    from derfinder_b200 import pool
     from derfinder_b200.rrng import permutation_indices
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -429,7 +398,7 @@ def main():
     def one_step():
         if world > 1:
             (R, M), rh, nh, cov = step.device_pass(keep=True)
-            p_dev, fwer, pool = pooled_pvalues(step, rh, nh, B, cut, dist, torch, device)
+            p_dev, fwer, npool = pool.genomewide_pvalues(eng, rh, nh, B, cut, torch, device, dist=dist)
             eng.lib.dfb_regions_free(rh)
             eng.lib.dfb_nulls_free(nh)
             eng.lib.dfb_cov_free(cov)
