@@ -61,6 +61,7 @@ struct dfb_ctx {
     int64_t klaunch[DFB_K_COUNT] = {0};
     // options
     int opt_screen = 1;
+    int opt_fused = 1;           // fused screen+refine kernel (0: two-kernel screen path)
     double opt_null_cap_mb = 0;  // 0 = auto
     int opt_perm_batch = 0;      // 0 = auto
     double opt_scratch_gb = 24;  // upper bound for per-call scratch (mask + exceedance values)

@@ -102,6 +102,12 @@ int fstat_perm_batch_screen(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& 
                             double adjust_f, const int32_t* idx_dev, int64_t B, double hi, size_t capacity_hint,
                             PermBatch* out, int64_t* ncand_out);
 
+bool fused_supported(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, double lo, double hi,
+                     double adjust_f);
+int fstat_perm_batch_fused(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, const double* q_dev /*[n][p]*/,
+                           double adjust_f, const int32_t* idx_dev, int64_t B, double hi, size_t capacity_hint,
+                           PermBatch* out);
+
 int mask_diff(dfb_ctx* ctx, const uint32_t* a, const uint32_t* b, int64_t words, int64_t* diff);
 
 // ---- regions.cu

@@ -57,12 +57,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(bar),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)  // suspend-time hint: the warp sleeps in hardware instead of spinning
         : "memory");
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
@@ -603,6 +603,425 @@ __global__ void __launch_bounds__(RF_THREADS) fstat_refine_kernel(const RefinePa
     }
 }
 
+// ==========================================================================================
+// Fused null scan: screen + refinement in ONE persistent kernel (the default K2 null path).
+//
+// A CTA walks 128-base tiles.  Per tile the 4 epilogue warps build (i) the centred FP64 tile in
+// shared memory (exact contract, read from HBM once) and (ii) its bf16 [hi | lo] split as the UMMA
+// A operand; warp 4 streams the pre-built B tiles (bulk copy + mbarrier, 2 stages) and issues the
+// MMAs  hi*qh + hi*ql + lo*qh  into a double-buffered TMEM accumulator.  Each epilogue warp then
+// owns 32 bases: it reads its TMEM lanes, ballots the candidate test into one word per
+// permutation, releases the accumulator, and immediately refines the candidates of that
+// permutation chunk with the FP64 contract (same code path as fstat_refine_kernel), writing the
+// exact mask word, the value offset and the compacted values.  Nothing but the final results
+// touches HBM.
+
+struct FusedGeom {
+    int n, npad, nk16;  // samples, padded to 16, K steps of 16 per operand term
+    int KB;             // 64-element K blocks of the stored [hi | lo] rows (2*npad elements)
+    int p, p0, j0, pe, pst;  // model columns, first column used by the screen, columns screened, TMEM stride
+    int ps, nmma;       // permutations per chunk, MMA N = ps * pst
+    int qs, ixs;        // Qs row stride (doubles), bytes per row of the byte permutation table
+    int64_t B, chunks;
+    int64_t tiles;
+    uint32_t a_bytes, b_bytes;
+    uint32_t off_b, off_ys, off_qs, off_yy, off_bar, off_warp, warp_bytes;
+    size_t smem;
+};
+
+// B operand of the fused kernel: per chunk a [nmma x KB*64] bf16 tile, rows r = q*pst + jj (column
+// j0 + jj of permutation q, pre-scaled by sqrt(w_j)), K layout [qh (npad) | ql (npad) | 0].
+__global__ void __launch_bounds__(128) build_qb2_kernel(const double* __restrict__ q /*[n][p]*/,
+                                                        const int32_t* __restrict__ idx /*[B][n]*/, FusedGeom G,
+                                                        double sw0, double swd, unsigned char* __restrict__ out,
+                                                        unsigned char* __restrict__ idx8) {
+    const int64_t chunks_per_row = (int64_t)G.KB * 8;
+    const int64_t total = G.chunks * G.nmma * chunks_per_row;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = t / (G.nmma * chunks_per_row);
+        const int64_t rem = t - c * G.nmma * chunks_per_row;
+        const int row = (int)(rem / chunks_per_row);
+        const int kc = (int)(rem - (int64_t)row * chunks_per_row);
+        const int qi = row / G.pst, jj = row - qi * G.pst;
+        const int j = G.j0 + jj;
+        const int64_t b = c * G.ps + qi;
+        __nv_bfloat16 vals[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int col = kc * 8 + e;
+            const int term = col / G.npad, k = col - term * G.npad;
+            float f = 0.f;
+            if (b < G.B && jj < G.pe && term < 2 && k < G.n) {
+                const double v = q[(size_t)idx[b * G.n + k] * G.p + j] * (j < G.p0 ? sw0 : swd);
+                const __nv_bfloat16 h = __double2bfloat16(v);
+                f = term == 0 ? __bfloat162float(h) : __bfloat162float(__double2bfloat16(v - (double)__bfloat162float(h)));
+            }
+            vals[e] = __float2bfloat16(f);
+        }
+        const int kb = (kc * 8) / 64, colb = (kc * 8) % 64;
+        unsigned char* dst = out + ((size_t)(c * G.KB + kb) * G.nmma) * 128 + sw128_offset(row, colb);
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(vals);
+    }
+    // permutation rows as bytes, padded to ixs per row (rows beyond B are zero)
+    const int64_t rows = G.chunks * G.ps + 32;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < rows * G.ixs; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t b = t / G.ixs;
+        const int k = (int)(t - b * G.ixs);
+        idx8[t] = (b < G.B && k < G.n) ? (unsigned char)idx[b * G.n + k] : 0;
+    }
+}
+
+struct FusedParams {
+    const double* Y;
+    int64_t ld, N;
+    FusedGeom G;
+    const unsigned char* qb;    // [chunks][KB][nmma][128 B]
+    const unsigned char* idx8;  // [chunks*ps + 32][ixs]
+    const double* q;            // [n][p] row-major FP64
+    int center;
+    double U, adjust_f, dfnum, dfden;
+    float kd;    // kappa * delta
+    float e0;    // sqrt(c) * 2 * n^1.5 * 2^-52 when the constant column is dropped from the screen, else 0
+    uint32_t idesc;
+    uint32_t* mask;  // [B][W]
+    int64_t W;
+    int64_t* off;    // [B][W]
+    double* vals;
+    unsigned long long capacity;
+    unsigned long long* cursor;
+};
+
+// 32 lanes x 32 consecutive fp32 columns
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// PT: number of model columns (2..8) or 0 = generic; J0: 1 when the constant column is not screened
+template <int PT, int J0>
+__global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParams P) {
+    constexpr int PCOLS = PT > 0 ? PT - J0 : 16;
+    constexpr int PST = PCOLS <= 2 ? 2 : (PCOLS <= 4 ? 4 : (PCOLS <= 8 ? 8 : 16));
+    constexpr int per16 = 16 / PST;
+    extern __shared__ __align__(1024) unsigned char smem_fz_raw[];
+    unsigned char* sm = smem_fz_raw + ((1024u - (smem_u32(smem_fz_raw) & 1023u)) & 1023u);
+    const FusedGeom& G = P.G;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n = G.n, p = G.p, qs = G.qs;
+    unsigned char* As = sm;
+    unsigned char* Bs = sm + G.off_b;
+    double* ys = reinterpret_cast<double*>(sm + G.off_ys);  // [n][128] centred
+    double* Qs = reinterpret_cast<double*>(sm + G.off_qs);  // [n][qs]
+    double* yy_s = reinterpret_cast<double*>(sm + G.off_yy);  // [128]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sm + G.off_bar);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+    const uint32_t full_b = smem_u32(bars + 0), empty_b = smem_u32(bars + 1), a_ready = smem_u32(bars + 2);
+    const uint32_t tmem_full = smem_u32(bars + 4), tmem_empty = smem_u32(bars + 6);
+    // per-warp scratch (epilogue warps only)
+    unsigned char* wbase = sm + G.off_warp + (size_t)(warp & 3) * G.warp_bytes;
+    uint16_t* list_w = reinterpret_cast<uint16_t*>(wbase);        // [1024] (perm << 5) | base
+    uint32_t* ew_w = reinterpret_cast<uint32_t*>(list_w + 1024);  // [32] exact words
+    unsigned char* ix_w = reinterpret_cast<unsigned char*>(ew_w + 32);  // [32][ixs] permutation rows
+
+    if (warp == 4) {
+        if (lane == 0) {
+            mbar_init(full_b, 1);
+            mbar_init(empty_b, 1);
+            mbar_init(a_ready, 4);
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(tmem_full + 8 * s, 1);
+                mbar_init(tmem_empty + 8 * s, 4);
+            }
+            fence_barrier_init();
+        }
+        __syncwarp();
+        tmem_alloc(smem_u32(tmem_slot), (uint32_t)(2 * G.nmma));
+    } else {
+        for (int e = tid; e < n * qs; e += TC_M) {
+            const int k = e / qs, j = e - k * qs;
+            Qs[e] = j < p ? P.q[(size_t)k * p + j] : 0.0;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    unsigned long long chunk_ptr = 0;  // warp-uniform: next free value slot of the warp's chunk
+    int chunk_left = 0;
+    const bool num_is_sd = P.dfnum == 1.0;
+    int64_t it = 0;  // chunks issued / consumed so far (TMEM stage = it & 1, phase = (it >> 1) & 1)
+    uint32_t tphase = 0;  // parity of the A-tile barrier (one phase per tile)
+    const uint32_t lt_mask = (1u << lane) - 1u;
+
+    for (int64_t tile = blockIdx.x; tile < G.tiles; tile += gridDim.x) {
+        const int64_t base0 = tile * TC_M;
+        float thr = __int_as_float(0x7f800000);  // +inf: rows beyond N never pass
+        if (warp < 4) {
+            // ---- stage the tile: FP64 centred copy (exact contract) + bf16 hi/lo A operand
+            const int64_t base = base0 + tid;
+            const bool valid = base < P.N;
+            double acc = 0.0;
+            if (valid) {
+                for (int k0 = 0; k0 < n; k0 += 8) {  // 8 independent loads in flight, then the ordered sum
+                    double v[8];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = (k0 + e < n) ? P.Y[(size_t)(k0 + e) * P.ld + base] : 0.0;
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        if (k0 + e < n) {
+                            ys[(size_t)(k0 + e) * TC_M + tid] = v[e];
+                            acc = (k0 + e == 0) ? v[e] : __dadd_rn(acc, v[e]);
+                        }
+                }
+            } else {
+                for (int k = 0; k < n; ++k) ys[(size_t)k * TC_M + tid] = 0.0;
+            }
+            const double m = P.center ? __ddiv_rn(acc, (double)n) : 0.0;
+            double yy = 0.0;
+            auto put = [&](int col, const uint4& val) {  // col: multiple of 8
+                *reinterpret_cast<uint4*>(As + (size_t)(col >> 6) * TC_M * 128 + sw128_offset(tid, col & 63)) = val;
+            };
+            for (int k0 = 0; k0 < G.npad; k0 += 8) {
+                __nv_bfloat162 hi[4], lo[4];
+#pragma unroll
+                for (int e = 0; e < 8; e += 2) {
+                    float f[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int k = k0 + e + u;
+                        double v = 0.0;
+                        if (k < n) {
+                            v = __dsub_rn(ys[(size_t)k * TC_M + tid], m);
+                            ys[(size_t)k * TC_M + tid] = v;
+                            yy = fma(v, v, yy);
+                        }
+                        f[u] = (float)v;
+                    }
+                    const __nv_bfloat162 h = __floats2bfloat162_rn(f[0], f[1]);
+                    const float2 hf = __bfloat1622float2(h);
+                    hi[e >> 1] = h;
+                    lo[e >> 1] = __floats2bfloat162_rn(f[0] - hf.x, f[1] - hf.y);  // exact differences
+                }
+                put(k0, *reinterpret_cast<const uint4*>(hi));
+                put(G.npad + k0, *reinterpret_cast<const uint4*>(lo));
+            }
+            const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
+            for (int col = 2 * G.npad; col < G.KB * 64; col += 8) put(col, zero4);
+            yy_s[tid] = yy;
+            if (valid) {
+                // candidate iff  L~ >= (sqrt(T) - kappa*delta*|yc| - e0*(|m| + |yc|))^2, T = U*(adjustF + yy/dfden);
+                // evaluated in FP32 with the rounding pushed to the safe side
+                const float yn = __fsqrt_ru((float)yy * 1.0000002f);
+                const float Tf = (float)(P.U * (P.adjust_f + yy / P.dfden));
+                const float r = __fsqrt_rd(Tf) * 0.999999f - P.kd * yn - P.e0 * (fabsf((float)m) * 1.0000002f + yn);
+                float t2 = r > 0.f ? r * r * 0.99999f : 0.f;  // 1e-5: fp32 epilogue rounding
+                thr = (t2 == t2) ? t2 : __int_as_float(0x7fc00000);  // NaN data -> never a candidate
+            }
+        }
+        if (warp < 4) {
+            // A rows of this warp are written: publish them to the async proxy and tell the MMA warp.
+            // Epilogue warps never wait for each other -- they only meet through tmem_full.
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(a_ready);
+        }
+
+        if (warp == 4) {
+            // ===== producer + MMA issuer (one lane).  B tiles are small and L2-resident: one stage,
+            // reloaded as soon as the MMAs of the previous chunk have consumed it. =====
+            if (lane == 0) {
+                const uint32_t a_addr = smem_u32(As), b_addr = smem_u32(Bs);
+                const unsigned char* src = P.qb;
+                mbar_wait(a_ready, tphase);
+                tc_fence_after();
+                for (int64_t c = 0; c < G.chunks; ++c) {
+                    const int64_t i0 = it + c;
+                    const int s = (int)(i0 & 1);
+                    const uint32_t ph = (uint32_t)((i0 >> 1) & 1);
+                    const uint32_t bph = (uint32_t)(i0 & 1);
+                    mbar_wait(empty_b, bph ^ 1);  // MMAs of the previous chunk have read the B stage
+                    mbar_expect_tx(full_b, G.b_bytes);
+                    bulk_g2s(b_addr, src + (size_t)c * G.b_bytes, G.b_bytes, full_b);
+                    mbar_wait(full_b, bph);
+                    mbar_wait(tmem_empty + 8 * s, ph ^ 1);
+                    tc_fence_after();
+                    const uint32_t d_addr = tmem_base + (uint32_t)(s * G.nmma);
+                    const uint32_t bs_addr = b_addr;
+                    uint32_t accum = 0u;
+                    for (int t = 0; t < G.nk16; ++t) {
+#pragma unroll
+                        for (int term = 0; term < 3; ++term) {
+                            const int acol = (term == 2 ? G.npad : 0) + 16 * t;
+                            const int bcol = (term == 1 ? G.npad : 0) + 16 * t;
+                            const uint64_t ad = umma_desc_sw128(a_addr + (uint32_t)(acol >> 6) * TC_M * 128u + (uint32_t)(acol & 63) * 2u);
+                            const uint64_t bd = umma_desc_sw128(bs_addr + (uint32_t)(bcol >> 6) * G.nmma * 128u + (uint32_t)(bcol & 63) * 2u);
+                            umma_bf16(d_addr, ad, bd, P.idesc, accum);
+                            accum = 1u;
+                        }
+                    }
+                    umma_commit(empty_b);            // B stage reusable once these MMAs have read it
+                    umma_commit(tmem_full + 8 * s);  // accumulator ready for the epilogue
+                }
+            }
+            __syncwarp();
+        } else {
+            // ===== epilogue + refinement: warp owns 32 bases (TMEM lanes 32*warp .. +31) =====
+            const int64_t gw = tile * 4 + warp;  // global mask word of this warp's 32 bases
+            const bool active = gw < P.W;
+            const double* ycol = ys + warp * 32;  // rows beyond N carry thr = +inf: never candidates
+            const double* yyw = yy_s + warp * 32;
+            for (int64_t c = 0; c < G.chunks; ++c) {
+                const int64_t i0 = it + c;
+                const int s = (int)(i0 & 1);
+                const uint32_t ph = (uint32_t)((i0 >> 1) & 1);
+                const int64_t b0 = c * G.ps;
+                const int nq = (int)min((int64_t)G.ps, P.G.B - b0);  // valid permutations of this chunk
+                mbar_wait(tmem_full + 8 * s, ph);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * G.nmma);
+                // candidate test + work list in one pass: the ballot word of a permutation is warp-uniform,
+                // so its candidates are appended (in base order) right away -> list sorted by (perm, base)
+                int nwork = 0;
+                for (int g = 0; g * per16 < nq; g += 2) {
+                    float v[32];
+                    tmem_ld32(taddr + (uint32_t)(g * 16), v);
+                    const bool full = (g + 2) * per16 <= nq;  // warp-uniform: no padded permutation in this load
+#pragma unroll
+                    for (int qq = 0; qq < 2 * per16; ++qq) {
+                        float a = v[qq * PST] * v[qq * PST];
+#pragma unroll
+                        for (int j = 1; j < PCOLS; ++j) a = fmaf(v[qq * PST + j], v[qq * PST + j], a);
+                        const int qi = g * per16 + qq;
+                        const bool cand = (a >= thr) && (full || qi < nq);
+                        const unsigned word = __ballot_sync(0xffffffffu, cand);
+                        if (word) {
+                            if (cand) list_w[nwork + __popc(word & lt_mask)] = (uint16_t)((qi << 5) | lane);
+                            nwork += __popc(word);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(tmem_empty + 8 * s);  // accumulator free: the next MMAs overlap the refinement
+                const int64_t b = b0 + lane;
+                if (nwork == 0) {
+                    if (lane < nq && active) {
+                        P.mask[b * P.W + gw] = 0u;
+                        P.off[b * P.W + gw] = 0;
+                    }
+                    __syncwarp();
+                    continue;
+                }
+                ew_w[lane] = 0u;
+                {  // permutation rows of this chunk as bytes: nq rows of ixs bytes, 16-byte copies
+                    const uint4* src = reinterpret_cast<const uint4*>(P.idx8 + (size_t)b0 * G.ixs);
+                    const int nv = nq * (G.ixs >> 4);
+                    for (int e = lane; e < nv; e += 32) reinterpret_cast<uint4*>(ix_w)[e] = src[e];
+                }
+                if (nwork > chunk_left) {  // warp-uniform: grab a fresh chunk (the remainder is left unused)
+                    unsigned long long g = 0;
+                    if (lane == 0) g = atomicAdd(P.cursor, (unsigned long long)RF_CHUNK);
+                    chunk_ptr = __shfl_sync(0xffffffffu, g, 0);
+                    chunk_left = RF_CHUNK;
+                }
+                __syncwarp();
+                unsigned long long run = chunk_ptr;
+                for (int e0 = 0; e0 < nwork; e0 += 32) {
+                    const int e = e0 + lane;
+                    bool pass = false;
+                    double f = 0.0;
+                    int q = 0, bl = 0;
+                    if (e < nwork) {
+                        const int ent = list_w[e];
+                        q = ent >> 5;
+                        bl = ent & 31;
+                        const unsigned char* ix = ix_w + q * G.ixs;
+                        double s0 = 0.0, sd = 0.0;
+                        // S_j in k order, s0 / sd in j order: identical chains to the dense kernel
+                        if (PT > 0) {
+                            constexpr int QS = (PT + 1) & ~1;
+                            double S[PT > 0 ? PT : 1];
+#pragma unroll
+                            for (int j = 0; j < PT; ++j) S[j] = 0.0;
+#pragma unroll 4
+                            for (int k = 0; k < n; ++k) {
+                                const double yv = ycol[(size_t)k * TC_M + bl];
+                                const double2* qrow = reinterpret_cast<const double2*>(Qs + (size_t)ix[k] * QS);
+#pragma unroll
+                                for (int j2 = 0; j2 < QS / 2; ++j2) {
+                                    const double2 qq = qrow[j2];
+                                    S[2 * j2] = fma(yv, qq.x, S[2 * j2]);
+                                    if (2 * j2 + 1 < PT) S[2 * j2 + 1] = fma(yv, qq.y, S[2 * j2 + 1]);
+                                }
+                            }
+#pragma unroll
+                            for (int j = 0; j < PT; ++j) {
+                                if (j < G.p0) s0 = fma(S[j], S[j], s0);
+                                else sd = fma(S[j], S[j], sd);
+                            }
+                        } else {
+                            for (int j = 0; j < p; ++j) {
+                                double S = 0.0;
+                                for (int k = 0; k < n; ++k)
+                                    S = fma(ycol[(size_t)k * TC_M + bl], Qs[(size_t)ix[k] * qs + j], S);
+                                if (j < G.p0) s0 = fma(S, S, s0);
+                                else sd = fma(S, S, sd);
+                            }
+                        }
+                        double rss1 = __dsub_rn(__dsub_rn(yyw[bl], s0), sd);
+                        if (rss1 < 0.0) rss1 = 0.0;
+                        const double num = num_is_sd ? sd : __ddiv_rn(sd, P.dfnum);
+                        const double den = __dadd_rn(P.adjust_f, __ddiv_rn(rss1, P.dfden));
+                        f = __ddiv_rn(num, den);
+                        pass = f >= P.U;
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, pass);
+                    if (pass) {
+                        const unsigned long long dst = run + __popc(bal & ((1u << lane) - 1u));
+                        if (dst < P.capacity) P.vals[dst] = f;
+                        atomicOr(&ew_w[q], 1u << bl);
+                    }
+                    run += __popc(bal);
+                }
+                __syncwarp();
+                // lane = permutation again: exact word and the offset of its first value
+                const uint32_t ew = ew_w[lane];
+                const int c2 = __popc(ew);
+                int inc2 = c2;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, inc2, o);
+                    if (lane >= o) inc2 += t;
+                }
+                if (lane < nq) {
+                    P.mask[b * P.W + gw] = ew;
+                    P.off[b * P.W + gw] = (int64_t)(chunk_ptr + (unsigned long long)(inc2 - c2));
+                }
+                chunk_left -= (int)(run - chunk_ptr);
+                chunk_ptr = run;
+                __syncwarp();
+            }
+        }
+        it += G.chunks;
+        tphase ^= 1u;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)(2 * G.nmma));
+}
+
 __global__ void popcount_words_kernel(const uint32_t* __restrict__ w, int64_t n, unsigned long long* __restrict__ out) {
     unsigned long long c = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
@@ -826,6 +1245,169 @@ int fstat_perm_batch_screen(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& 
             }
             return DFB_OK;
         }
+        cap = (size_t)used;
+    }
+    set_error("exceedance buffer overflow after resize (internal error)");
+    return DFB_ECUDA;
+}
+
+// ------------------------------------------------------------------------------------------
+// fused path, host side
+
+static bool constant_first_column(const ModelBasis& mb) {
+    if (!mb.centered || mb.p0 < 1) return false;
+    const double c0 = mb.q[0];
+    for (int i = 1; i < mb.n; ++i)
+        if (fabs(mb.q[(size_t)i * mb.p] - c0) > 1e-14) return false;
+    return c0 != 0.0;
+}
+
+static bool fused_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, int64_t B, FusedGeom* g) {
+    FusedGeom G;
+    memset(&G, 0, sizeof G);
+    G.n = cov->n;
+    if (G.n > 255) return false;
+    G.npad = (int)round_up(G.n, 16);
+    G.nk16 = G.npad / 16;
+    G.KB = (int)ceil_div(2 * G.npad, 64);
+    G.p = mb.p;
+    G.p0 = mb.p0;
+    G.j0 = (mb.p <= 8 && constant_first_column(mb)) ? 1 : 0;
+    G.pe = mb.p - G.j0;
+    if (mb.p > 16) return false;
+    G.pst = mb.p > 8 ? 16 : (G.pe <= 2 ? 2 : (G.pe <= 4 ? 4 : 8));
+    G.ps = G.pst <= 4 ? 32 : (G.pst == 8 ? 16 : 8);
+    G.nmma = G.ps * G.pst;
+    G.qs = mb.p <= 8 ? ((mb.p + 1) & ~1) : mb.p;
+    G.ixs = (int)round_up(G.n, 16);
+    G.B = B;
+    G.chunks = ceil_div(B, G.ps);
+    G.tiles = ceil_div(cov->N, TC_M);
+    G.a_bytes = (uint32_t)G.KB * TC_M * 128u;
+    G.b_bytes = (uint32_t)G.KB * (uint32_t)G.nmma * 128u;
+    uint32_t o = G.a_bytes;
+    G.off_b = o;
+    o += G.b_bytes;
+    G.off_ys = o;
+    o += (uint32_t)G.n * TC_M * 8u;
+    G.off_qs = o;
+    o += (uint32_t)round_up((int64_t)G.n * G.qs * 8, 16);
+    G.off_yy = o;
+    o += TC_M * 8u;
+    G.off_bar = o;
+    o += 8 * 8 + 16;
+    o = (uint32_t)round_up(o, 16);
+    G.off_warp = o;
+    G.warp_bytes = (uint32_t)(1024 * 2 + 32 * 4 + 32 * G.ixs);
+    o += 4 * G.warp_bytes;
+    G.smem = (size_t)o + 1024;  // slack for the manual 1024-byte alignment
+    const size_t limit = std::min<size_t>(ctx->smem_optin, 227 * 1024);
+    if (G.smem > limit) return false;
+    *g = G;
+    return true;
+}
+
+bool fused_supported(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, double lo, double hi,
+                     double adjust_f) {
+    if (!ctx->opt_screen || !ctx->opt_fused) return false;
+    if (!(hi > 0.0) || !(lo < 0.0)) return false;  // one-sided positive cutoff only
+    if (cov->n - mb.p <= 0 || !(adjust_f >= 0.0)) return false;
+    FusedGeom g;
+    return fused_geometry(ctx, cov, mb, 1, &g);
+}
+
+template <int PT>
+static int launch_fused(dfb_ctx* ctx, const FusedParams& F, int grid) {
+    auto go = [&](auto kern) -> int {
+        DFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F.G.smem));
+        KTimer t(ctx, DFB_K_FSTAT_TC, 1);
+        kern<<<grid, TC_THREADS, F.G.smem, ctx->stream>>>(F);
+        return DFB_OK;
+    };
+    if (PT > 0 && F.G.j0) return go(fstat_null_kernel<PT, PT == 0 ? 0 : 1>);
+    return go(fstat_null_kernel<PT, 0>);
+}
+
+// Fused screen + refine for one batch of permutations; fills the same PermBatch as the other paths.
+int fstat_perm_batch_fused(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, const double* q_dev /*[n][p]*/,
+                           double adjust_f, const int32_t* idx_dev, int64_t B, double hi, size_t capacity_hint,
+                           PermBatch* out) {
+    FusedGeom G;
+    if (!fused_geometry(ctx, cov, mb, B, &G)) {
+        set_error("fused geometry does not fit (internal error)");
+        return DFB_EINVAL;
+    }
+    DevBuf<unsigned char> qb, idx8;
+    DFB_TRY(qb.alloc(ctx, (size_t)G.chunks * G.b_bytes));
+    DFB_TRY(idx8.alloc(ctx, (size_t)(G.chunks * G.ps + 32) * G.ixs));
+    const double df1 = (double)(mb.p - mb.p0), df2 = (double)(cov->n - mb.p);
+    const double w_a = 1.0 / df1 + hi / df2, w_c = hi / df2;  // weights of the S_d / S_0 columns
+    {
+        KTimer t(ctx, DFB_K_FSTAT_TC, 1);
+        const int64_t work = G.chunks * G.nmma * (G.KB * 8);
+        build_qb2_kernel<<<grid_for(work, 128, ctx->sm_count, 16), 128, 0, ctx->stream>>>(q_dev, idx_dev, G, sqrt(w_c),
+                                                                                        sqrt(w_a), qb.p, idx8.p);
+    }
+    FusedParams F;
+    memset(&F, 0, sizeof F);
+    F.Y = cov->y.p;
+    F.ld = cov->ld;
+    F.N = cov->N;
+    F.G = G;
+    F.qb = qb.p;
+    F.idx8 = idx8.p;
+    F.q = q_dev;
+    F.center = mb.centered ? 1 : 0;
+    F.U = hi;
+    F.adjust_f = adjust_f;
+    F.dfnum = df1;
+    F.dfden = df2;
+    const double kappa = sqrt(w_a * (double)(mb.p - mb.p0) + w_c * (double)mb.p0);
+    F.kd = (float)(kappa * screen_delta(cov->n) * 1.000001);
+    // dropped constant column: |S_const| = |sum_k yc[k]| / sqrt(n) <= n^1.5 * 2^-52 * max|y| (rounding of the
+    // mean and of the n subtractions); 2x safety.  Its weight in the statistic is c.
+    F.e0 = G.j0 ? (float)(sqrt(w_c) * 2.0 * pow((double)cov->n, 1.5) * 2.220446049250313e-16 * 1.000001) : 0.f;
+    F.idesc = umma_idesc_bf16(TC_M, G.nmma);
+
+    out->rows = B;
+    out->W = ceil_div(cov->N, 32);
+    out->tile_bases = 32;
+    out->tiles = out->W;
+    DFB_TRY(out->mask.alloc(ctx, (size_t)out->rows * out->W));
+    DFB_TRY(out->off.alloc(ctx, (size_t)out->rows * out->tiles));
+    DevBuf<unsigned long long> cursor;
+    DFB_TRY(cursor.alloc(ctx, 1));
+    // persistent grid: CTAs per SM limited by shared memory and by TMEM columns (512 per SM)
+    int per_sm = (int)std::min<size_t>((size_t)(227 * 1024) / G.smem, (size_t)(512 / (2 * G.nmma)));
+    per_sm = std::max(1, std::min(per_sm, 6));
+    const int grid = (int)std::min<int64_t>(G.tiles, (int64_t)ctx->sm_count * per_sm);
+    const size_t slack = (size_t)grid * 4 * RF_CHUNK;  // every warp may leave one partly used chunk behind
+    const size_t dense = (size_t)B * (size_t)cov->N;
+    size_t cap = std::min(dense, std::max<size_t>(capacity_hint, 1024)) + slack;
+    F.mask = out->mask.p;
+    F.W = out->W;
+    F.off = out->off.p;
+    F.cursor = cursor.p;
+    for (int attempt = 0; attempt < 2; ++attempt) {
+        DFB_TRY(out->vals.alloc(ctx, cap));
+        DFB_TRY(cursor.zero());
+        F.vals = out->vals.p;
+        F.capacity = cap;
+        switch (mb.p) {
+            case 2: DFB_TRY(launch_fused<2>(ctx, F, grid)); break;
+            case 3: DFB_TRY(launch_fused<3>(ctx, F, grid)); break;
+            case 4: DFB_TRY(launch_fused<4>(ctx, F, grid)); break;
+            case 5: DFB_TRY(launch_fused<5>(ctx, F, grid)); break;
+            case 6: DFB_TRY(launch_fused<6>(ctx, F, grid)); break;
+            case 7: DFB_TRY(launch_fused<7>(ctx, F, grid)); break;
+            case 8: DFB_TRY(launch_fused<8>(ctx, F, grid)); break;
+            default: DFB_TRY(launch_fused<0>(ctx, F, grid)); break;
+        }
+        DFB_CUDA(cudaGetLastError());
+        unsigned long long used = 0;
+        DFB_TRY(d2h(ctx, &used, cursor.p, sizeof used));
+        out->nvals = (int64_t)used;  // allocated value slots (exceedances + unused chunk tails)
+        if (used <= cap) return DFB_OK;
         cap = (size_t)used;
     }
     set_error("exceedance buffer overflow after resize (internal error)");

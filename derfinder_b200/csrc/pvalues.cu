@@ -80,7 +80,8 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
 
     // tensor-core screen + exact refinement when the cutoff is one-sided positive (the normal case);
     // otherwise the dense FP64 kernel.  Results are identical either way.
-    const bool use_screen = screen_supported(ctx, cov, mb, lo, hi, adjust_f);
+    const bool use_fused = fused_supported(ctx, cov, mb, lo, hi, adjust_f);
+    const bool use_screen = use_fused || screen_supported(ctx, cov, mb, lo, hi, adjust_f);
     DevBuf<double> q_d;
     if (use_screen) {
         DFB_TRY(q_d.alloc(ctx, mb.q.size()));
@@ -116,7 +117,9 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
                                   : (size_t)std::max(dense * density, 4.0e6);
         if ((double)hint * 8.0 > budget * 0.5) hint = (size_t)(budget * 0.5 / 8.0);
         PermBatch pbatch;
-        int rc = use_screen ? fstat_perm_batch_screen(ctx, cov, mb, q_d.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, hi,
+        int rc = use_fused  ? fstat_perm_batch_fused(ctx, cov, mb, q_d.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, hi,
+                                                     hint, &pbatch)
+                 : use_screen ? fstat_perm_batch_screen(ctx, cov, mb, q_d.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, hi,
                                                       hint, &pbatch, nullptr)
                             : fstat_perm_batch(ctx, cov, mb, qd.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, lo, hi,
                                                two_sided, hint, &pbatch);
@@ -546,6 +549,13 @@ int dfb_debug_screen(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const
     DFB_TRY(fstat_perm_batch_screen(ctx, cov, mb, q_d.p, adjust_f, idx_d.p, B, cutoff, hint, &scr, &ncand));
     int64_t diff = 0;
     DFB_TRY(mask_diff(ctx, dense.mask.p, scr.mask.p, dense.rows * dense.W, &diff));
+    if (fused_supported(ctx, cov, mb, -cutoff, cutoff, adjust_f)) {  // the fused kernel must agree as well
+        PermBatch fz;
+        DFB_TRY(fstat_perm_batch_fused(ctx, cov, mb, q_d.p, adjust_f, idx_d.p, B, cutoff, hint, &fz));
+        int64_t diff2 = 0;
+        DFB_TRY(mask_diff(ctx, dense.mask.p, fz.mask.p, dense.rows * dense.W, &diff2));
+        diff += diff2;
+    }
     if (n_exact_dense) *n_exact_dense = dense.nvals;
     if (n_exact_screen) *n_exact_screen = scr.nvals;
     if (n_candidates) *n_candidates = ncand;

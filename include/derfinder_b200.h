@@ -90,6 +90,8 @@ int dfb_kernel_time(dfb_ctx* ctx, int kernel, double* ms, int64_t* launches);
  *   "screen"     0/1  use the tcgen05 split-bf16 screening contraction in front of the FP64
  *                     refinement for permutation nulls (default 1 when n fits; results are
  *                     identical either way)
+ *   "fused"      0/1  screen and refinement in one persistent kernel (default 1 when the tile
+ *                     fits in shared memory; 0 = separate screen and refinement kernels)
  *   "null_capacity_mb"  initial capacity of the exceedance value buffer
  *   "perm_batch"        permutations per launch (0 = auto) */
 int dfb_set_option(dfb_ctx* ctx, const char* key, double value);
@@ -221,7 +223,8 @@ int dfb_nulls_copy_dev(const dfb_nulls* nl, double* area_dev, int32_t* perm_dev)
 /* Validation hook for the tcgen05 screening path (used by the parity tests and profiling): runs
  * the dense FP64 scan and the screen + refinement on the same permutations with a scalar cutoff
  * and reports the exceedance counts of both, the number of screened candidates and the number of
- * mask bits that differ between the two paths (must be 0). */
+ * mask bits that differ between the dense path and the screened paths (two-kernel and, when
+ * supported, fused; must be 0). */
 int dfb_debug_screen(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const double* mod0, int p0,
                      double adjust_f, const int32_t* perm_idx, int64_t B, double cutoff,
                      int64_t* n_exact_dense, int64_t* n_exact_screen, int64_t* n_candidates,

@@ -539,3 +539,38 @@ def test_screen_off_equals_on(dfb, eng):
         assert e2.kernel_time(3)[1] == 0 and eng.kernel_time(3)[1] > 0  # tcgen05 path really ran / really off
     finally:
         e2.close()
+
+
+def test_fused_degenerate_rows(dfb, eng):
+    """Bases whose samples all carry the same coverage have yc = 0 (or a constant rounding residue):
+    F is 0/0, Inf or garbage in the exact contract; the fused screen (which drops the constant
+    column) must still flag exactly what the dense FP64 kernel flags."""
+    rng = np.random.default_rng(77)
+    N, n = 12000, 12
+    cov, position, group, models = synth(rng, N, n)
+    flat = rng.random(N) < 0.3
+    cov[flat, :] = rng.integers(0, 40, size=flat.sum())[:, None]  # all samples equal at 30% of the bases
+    prep = dfb.preprocessCoverage(dict(coverage=cov, position=position), engine=eng)
+    perm = random_perms(rng, 45, n)
+    for alpha, adj in ((0.05, 0.0), (0.3, 0.0), (0.05, 1e-3)):
+        cut = dfb.calcFstatCutoff("theoretical", alpha, models=models)
+        dense, screen, cand, diff = debug_screen(eng, prep["coverageProcessed"], models, perm, cut, adjustF=adj)
+        assert diff == 0 and dense == screen, (alpha, adj, diff, dense, screen)
+
+
+def test_fused_off_equals_on(dfb, eng):
+    rng = np.random.default_rng(32)
+    cov, position, group, models = synth(rng, 25000, 14, p_extra=2, seg=[9000, 16000])
+    perm = random_perms(rng, 70, 14)
+    cut = dfb.calcFstatCutoff("theoretical", 0.02, models=models)
+    res_on, ores = run_both(dfb, eng, cov, position, group, models, perm, cut)
+    assert_pipeline_equal(res_on, ores)
+    e2 = dfb.Engine(0)
+    try:
+        e2.set_option("fused", 0)
+        prep = dfb.preprocessCoverage(dict(coverage=cov, position=position), groupInfo=group, engine=e2)
+        F = dfb.calculateStats(prep, models, engine=e2)
+        res_off = dfb.calculatePvalues(prep, models, F, permIndex=perm, cutoff=cut, engine=e2)
+        assert_pipeline_equal(res_off, ores)
+    finally:
+        e2.close()
