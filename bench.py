@@ -10,8 +10,9 @@ is one full pass of the hot path over one synthetic chromosome:
     ->  calculatePvalues (B permuted-model F scans, thresholding, null regions/areas,
         observed regions + clusters, null-area sort, exact p-values)
 `value` times it with the filtered coverage already resident in HBM; `e2e` times the same pass
-through the reference-facing calls with HOST buffers (H2D of the coverage, D2H of F-stats, regions,
-nulls and p-values inside the timed region).
+through the reference-facing calls with HOST buffers (H2D of the coverage -- as integer Rle columns,
+the type the reference holds it in -- and D2H of F-stats, regions, nulls and p-values inside the
+timed region).
 
 Workload: BASELINE.json configs[1] -- synthetic chr21 (Lc = 48,129,895; ~10% of bases pass the
 filter), 12 samples, 2-group model + sampleDepth (p = 3, p0 = 2), 100 permutations, F cutoff
@@ -93,38 +94,37 @@ def make_workload(cfg, seed, torch=None, device=None):
     group = np.array([0] * (n // 2) + [1] * (n - n // 2))
     runlen = rng.integers(36, 77, size=n)
     offs = rng.integers(0, 76, size=n)
+    starts = np.concatenate(([0], np.cumsum(lens)[:-1]))
     if torch is not None:
         dev = device
         isl = torch.repeat_interleave(torch.arange(nisl, device=dev), torch.as_tensor(lens, device=dev))
         lam = torch.as_tensor(np.exp(log_expr), device=dev, dtype=torch.float32)[isl]
         eff = torch.as_tensor(effect, device=dev, dtype=torch.float32)[isl]
+        isl_start = torch.as_tensor(starts, device=dev)[isl]
         base = torch.arange(N, device=dev)
         g = torch.Generator(device=dev)
         g.manual_seed(seed)
         cov = torch.empty((n, N), dtype=torch.int32, device=dev)
         for s in range(n):
+            # piecewise-constant runs (read-length-like); a run never crosses an island boundary: it
+            # restarts at the island's first base
             first = ((base + int(offs[s])) // int(runlen[s])) * int(runlen[s]) - int(offs[s])
-            first = first.clamp_(min=0)
-            # a run never crosses an island boundary: restart at the island's first base
-            rate = lam[first] * float(depth[s]) * (eff[first] if group[s] == 1 else 1.0)
-            same = isl[first] == isl
-            rate = torch.where(same, rate, lam * float(depth[s]))
+            first = torch.maximum(first, isl_start)
+            rate = lam * float(depth[s]) * (eff if group[s] == 1 else 1.0)
             draw = torch.poisson(rate, generator=g)
-            val = draw[first]
-            val = torch.where(same, val, draw)
-            cov[s] = val.to(torch.int32)
+            cov[s] = draw[first].to(torch.int32)
         depth_cov = torch.log2(cov.sum(dim=1).double() + 32.0).cpu().numpy()
     else:
         isl = np.repeat(np.arange(nisl), lens)
         lam, eff = np.exp(log_expr)[isl], effect[isl]
+        isl_start = starts[isl]
         base = np.arange(N)
         cov = np.empty((n, N), dtype=np.int32)
         for s in range(n):
-            first = np.maximum(((base + offs[s]) // runlen[s]) * runlen[s] - offs[s], 0)
-            same = isl[first] == isl
-            rate = np.where(same, lam[first] * depth[s] * np.where(group[s] == 1, eff[first], 1.0), lam * depth[s])
+            first = np.maximum(((base + offs[s]) // runlen[s]) * runlen[s] - offs[s], isl_start)
+            rate = lam * depth[s] * np.where(group[s] == 1, eff, 1.0)
             draw = rng.poisson(rate)
-            cov[s] = np.where(same, draw[first], draw)
+            cov[s] = draw[first]
         depth_cov = np.log2(cov.sum(axis=1).astype(np.float64) + 32.0)
     cols = [np.ones(n), group.astype(np.float64), depth_cov]
     cols += [rng.normal(size=n) for _ in range(cfg["extra"])]
@@ -258,10 +258,26 @@ class Step:
         self.mod, self.mod0 = work["mod"], work["mod0"]
         self.pl = np.ascontiguousarray(work["pos_len"], dtype=np.int32)
         self._F_host = np.empty(self.N)  # the caller's fstats vector (R: a numeric vector it already owns)
+        self.rle = None
         self.last_breakdown = {}
 
     def _fp(self, a):
         return a.ctypes.data_as(self.L.c_f64p)
+
+    def set_rle_input(self, host_cov):
+        """Run-length encode the [n x N] host coverage once (outside any timed region): this is the
+        form in which the reference holds coverage (DataFrame of Rle, R/loadCoverage.R:323-326)."""
+        vals, lens = [], []
+        for s in range(self.n):
+            x = host_cov[s]
+            brk = np.flatnonzero(x[1:] != x[:-1]) + 1
+            starts = np.concatenate(([0], brk))
+            vals.append(np.ascontiguousarray(x[starts], dtype=np.int32))
+            lens.append(np.diff(np.concatenate((starts, [x.size]))).astype(np.int32))
+        vp = (C.c_void_p * self.n)(*[v.ctypes.data for v in vals])
+        lp = (C.c_void_p * self.n)(*[l.ctypes.data for l in lens])
+        nr = np.asarray([len(v) for v in vals], dtype=np.int64)
+        self.rle = (vals, lens, vp, lp, nr)
 
     def device_pass(self, keep=False):
         L, lib, eng = self.L, self.lib, self.eng
@@ -303,8 +319,18 @@ class Step:
             tm[name] = tm.get(name, 0.0) + (t1 - t0) * 1e3
             t0 = t1
 
-        L.check(lib.dfb_cov_from_dense(eng.h, self.n, self.N, L.DFB_I32, host_cov.ctypes.data_as(C.c_void_p), self.N,
-                                       L.ptr(self.pl, C.c_int32), len(self.pl), self.work["pos_first"], C.byref(cov)))
+        if self.rle is not None:
+            # the reference's own input type: a DataFrame of integer Rle columns (values + run lengths)
+            vals, lens, vp, lp, nr = self.rle
+            L.check(lib.dfb_cov_from_rle(eng.h, self.n, L.DFB_I32, vp, lp, L.ptr(nr, C.c_int64), self.N,
+                                         L.ptr(self.pl, C.c_int32), len(self.pl), self.work["pos_first"],
+                                         C.byref(cov)))
+            cov_bytes = sum(v.nbytes + l.nbytes for v, l in zip(vals, lens))
+        else:
+            L.check(lib.dfb_cov_from_dense(eng.h, self.n, self.N, L.DFB_I32, host_cov.ctypes.data_as(C.c_void_p),
+                                           self.N, L.ptr(self.pl, C.c_int32), len(self.pl), self.work["pos_first"],
+                                           C.byref(cov)))
+            cov_bytes = host_cov.nbytes
         lap("upload_coverage")
         d2h = 0
         try:
@@ -316,7 +342,9 @@ class Step:
             d2h += F.nbytes
             lap("calculateStats+download_F")
             rh, nh = C.c_void_p(), C.c_void_p()
-            rc = L.check(lib.dfb_calculate_pvalues(eng.h, cov, self._fp(F), self._fp(self.mod), self.mod.shape[1],
+            # `fstats` is the object calculateStats() just returned: its device copy is still cached in
+            # the coverage handle, so the glue passes NULL instead of uploading it again
+            rc = L.check(lib.dfb_calculate_pvalues(eng.h, cov, None, self._fp(self.mod), self.mod.shape[1],
                                                    self._fp(self.mod0), self.mod0.shape[1], 0.0,
                                                    L.ptr(self.perm, C.c_int32), self.perm.shape[0], -self.cut, self.cut,
                                                    0, 3000, C.byref(rh), C.byref(nh), None))
@@ -342,7 +370,7 @@ class Step:
                 lib.dfb_regions_free(rh)
                 lib.dfb_nulls_free(nh)
                 lap("download_regions_nulls")
-            h2d = host_cov.nbytes + F.nbytes + self.perm.nbytes
+            h2d = cov_bytes + self.pl.nbytes + self.perm.nbytes
             self.last_breakdown = tm
             return h2d, d2h
         finally:
@@ -359,6 +387,8 @@ def main():
     ap.add_argument("--cpu-bases", type=int, default=1_000_000, help="bounded CPU sample: kept bases per step")
     ap.add_argument("--cpu-perms", type=int, default=30, help="bounded CPU sample: permutations per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-input", default="rle", choices=["rle", "dense"],
+                    help="host coverage format of the end-to-end pass: Rle columns (the reference's type) or dense")
     ap.add_argument("--screen", type=int, default=None, help="override the engine's tcgen05 screening option")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
@@ -437,6 +467,8 @@ def main():
     host_cov = torch.empty((n, N), dtype=torch.int32, pin_memory=True)
     host_cov.copy_(work["cov"])
     host_np = host_cov.numpy()
+    if args.e2e_input == "rle":
+        step.set_rle_input(host_np)
     step.host_pass(host_np)
     torch.cuda.synchronize()
     ke = max(2, min(args.steps, 5))

@@ -7,7 +7,12 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/derfinder_b200.h"
@@ -44,6 +49,32 @@ static inline int64_t round_up(int64_t a, int64_t b) { return ceil_div(a, b) * b
 
 }  // namespace dfb
 
+namespace dfb {
+
+// Small persistent host thread pool used only to move bytes between pinned staging buffers and the
+// caller's pageable memory at more than one core's memcpy bandwidth (PCIe 5 x16 outruns a single
+// core).  parallel_for(n, fn) runs fn(0..n-1) on the workers plus the calling thread.
+class CopyPool {
+  public:
+    explicit CopyPool(int nthreads);
+    ~CopyPool();
+    int size() const { return (int)workers_.size() + 1; }
+    void parallel_for(int nparts, const std::function<void(int)>& fn);
+
+  private:
+    void worker();
+    std::vector<std::thread> workers_;
+    std::mutex m_;
+    std::condition_variable work_cv_, done_cv_;
+    const std::function<void(int)>* fn_ = nullptr;
+    std::atomic<int> next_{0};
+    int nparts_ = 0, active_ = 0;
+    uint64_t generation_ = 0;
+    bool stop_ = false;
+};
+
+}  // namespace dfb
+
 struct dfb_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -65,10 +96,13 @@ struct dfb_ctx {
     double opt_null_cap_mb = 0;  // 0 = auto
     int opt_perm_batch = 0;      // 0 = auto
     double opt_scratch_gb = 24;  // upper bound for per-call scratch (mask + exceedance values)
-    // pinned staging for small D2H reads
+    // pinned staging ring for pageable <-> device copies, and the host copy pool that drains it
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
-    cudaEvent_t stage_ev[2] = {nullptr, nullptr};
+    cudaEvent_t stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    dfb::CopyPool* pool = nullptr;
+    // small pinned scratch for scalar / O(B) read-backs (truly asynchronous D2H)
+    void* pinned_small = nullptr;
 };
 
 namespace dfb {
@@ -146,9 +180,17 @@ struct DevBuf {
 
 int h2d(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);
 int d2h(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);  // synchronises the stream
-// pageable <-> device through pinned, double-buffered staging; both return with the copy complete
+// pageable <-> device through a ring of pinned staging buffers drained / filled by the host copy
+// pool; both return with the copy complete.  A source/destination that is already pinned (or
+// registered) host memory is copied directly.
 int d2h_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);
 int h2d_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);
+// H2D of `count` host segments packed back to back at dst (through the pinned ring); synchronises.
+int h2d_gather(dfb_ctx* ctx, void* dst, const void* const* srcs, const size_t* bytes, int count);
+// D2H of `count` elements of `elem` bytes laid out in B consecutive blocks (block b = elements
+// [pre[b], pre[b+1])) into the reference's duplicated layout: block b is written twice, back to
+// back, at dst element 2*pre[b] (R/calculatePvalues.R:346-354).
+int d2h_dup(dfb_ctx* ctx, void* dst, const void* src, size_t elem, const int64_t* pre, int64_t B);
 
 // device-wide exclusive scan of `n` uint32 counts into int64 offsets; total_dev[0] = sum.
 int exclusive_scan_u32(dfb_ctx* ctx, const uint32_t* in, int64_t* out, int64_t n, int64_t* total_dev,

@@ -249,6 +249,70 @@ __global__ void __launch_bounds__(256) mask_run_emit_kernel(const uint32_t* __re
 }
 
 // upload n Rle columns: concatenated values + global prefix of the lengths (device scan)
+// bad[0] = a column holding a run length <= 0, bad[1] = a column whose lengths do not sum to len
+// (-1 when fine; the smallest offending column wins)
+__global__ void __launch_bounds__(256) validate_rle_kernel(const int32_t* __restrict__ lengths,
+                                                           const int64_t* __restrict__ cum,
+                                                           const int64_t* __restrict__ run_off, int n,
+                                                           int64_t total_runs, int64_t len, int64_t* __restrict__ bad) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total_runs + n;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        if (i < total_runs) {
+            if (lengths[i] <= 0) {
+                int lo = 0, hi = n;  // column of run i: largest s with run_off[s] <= i
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if (run_off[mid] <= i) lo = mid;
+                    else hi = mid;
+                }
+                atomicMin((unsigned long long*)&bad[0], (unsigned long long)lo);
+            }
+        } else {
+            const int s = (int)(i - total_runs);
+            if (cum[run_off[s + 1]] - cum[run_off[s]] != len) atomicMin((unsigned long long*)&bad[1], (unsigned long long)s);
+        }
+    }
+}
+
+// Plain expansion of Rle columns into the dense sample-major matrix (no filter): one block per
+// (2048-position tile, sample); a thread finds the run of its first position by binary search in
+// the sample's prefix sums and walks 8 consecutive positions, written as two 16-byte stores.
+template <typename V>
+__global__ void __launch_bounds__(K1_THREADS) expand_rle_kernel(RleDev R, int64_t ld, V* __restrict__ out) {
+    const int s = blockIdx.y;
+    const V* __restrict__ values = reinterpret_cast<const V*>(R.values);
+    const int64_t* __restrict__ cum = R.cum;
+    const int64_t lo = R.run_off[s], hi = R.run_off[s + 1] - 1, cb = cum[lo];
+    for (int64_t tile = blockIdx.x; tile * K1_TILE < R.len; tile += gridDim.x) {
+        const int64_t p0 = tile * K1_TILE + (int64_t)threadIdx.x * K1_PER;
+        if (p0 >= R.len) continue;
+        int64_t r = find_run(cum, cb, lo, hi, p0);
+        int64_t rend = cum[r + 1] - cb;
+        V v = values[r];
+        V vals[K1_PER];
+#pragma unroll
+        for (int e = 0; e < K1_PER; ++e) {
+            const int64_t p = p0 + e;
+            if (p < R.len) {
+                while (rend <= p) {
+                    ++r;
+                    rend = cum[r + 1] - cb;
+                    v = values[r];
+                }
+            }
+            vals[e] = v;
+        }
+        V* dst = out + (size_t)s * ld + p0;
+        if (p0 + K1_PER <= R.len) {
+            constexpr int NV = (int)(sizeof(V) * K1_PER / 16);
+#pragma unroll
+            for (int q = 0; q < NV; ++q) reinterpret_cast<uint4*>(dst)[q] = reinterpret_cast<const uint4*>(vals)[q];
+        } else {
+            for (int e = 0; p0 + e < R.len; ++e) dst[e] = vals[e];
+        }
+    }
+}
+
 struct RleUpload {
     DevBuf<unsigned char> values;
     DevBuf<uint32_t> lengths;
@@ -267,26 +331,43 @@ static int upload_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values,
         off[(size_t)s + 1] = off[(size_t)s] + nruns[s];
     }
     up->total_runs = off[(size_t)n];
-    // check lengths sum (cheap, catches ragged DataFrames early like R would)
-    for (int s = 0; s < n; ++s) {
-        int64_t t = 0;
-        for (int64_t r = 0; r < nruns[s]; ++r) {
-            DFB_REQUIRE(lengths[s][r] > 0, "Rle column %d has a non-positive run length", s + 1);
-            t += lengths[s][r];
-        }
-        DFB_REQUIRE(t == len, "Rle column %d has length %lld, expected %lld", s + 1, (long long)t, (long long)len);
-    }
     DFB_TRY(up->values.alloc(ctx, (size_t)std::max<int64_t>(up->total_runs, 1) * es));
     DFB_TRY(up->lengths.alloc(ctx, (size_t)std::max<int64_t>(up->total_runs, 1)));
     DFB_TRY(up->cum.alloc(ctx, (size_t)up->total_runs + 1));
     DFB_TRY(up->run_off.alloc(ctx, (size_t)n + 1));
-    for (int s = 0; s < n; ++s) {
-        DFB_TRY(h2d(ctx, up->values.p + (size_t)off[(size_t)s] * es, values[s], (size_t)nruns[s] * es));
-        DFB_TRY(h2d(ctx, up->lengths.p + off[(size_t)s], lengths[s], (size_t)nruns[s] * sizeof(int32_t)));
+    {
+        // all columns travel packed through the pinned ring: two streams of DMAs instead of 2n
+        // driver-staged pageable copies
+        std::vector<const void*> srcs((size_t)n);
+        std::vector<size_t> nb((size_t)n);
+        for (int s = 0; s < n; ++s) {
+            srcs[(size_t)s] = values[s];
+            nb[(size_t)s] = (size_t)nruns[s] * es;
+        }
+        DFB_TRY(h2d_gather(ctx, up->values.p, srcs.data(), nb.data(), n));
+        for (int s = 0; s < n; ++s) {
+            srcs[(size_t)s] = lengths[s];
+            nb[(size_t)s] = (size_t)nruns[s] * sizeof(int32_t);
+        }
+        DFB_TRY(h2d_gather(ctx, up->lengths.p, srcs.data(), nb.data(), n));
     }
     DFB_TRY(h2d(ctx, up->run_off.p, off.data(), off.size() * sizeof(int64_t)));
     DFB_CUDA(cudaStreamSynchronize(ctx->stream));  // `off` is a local
     DFB_TRY(exclusive_scan_u32(ctx, up->lengths.p, up->cum.p, up->total_runs, up->cum.p + up->total_runs, DFB_K_PREP));
+    // validation on the device (catches ragged DataFrames like R would, without an O(#runs) host pass):
+    // every run length positive, every column sums to `len`
+    DevBuf<int64_t> bad;
+    DFB_TRY(bad.alloc(ctx, 2));
+    DFB_CUDA(cudaMemsetAsync(bad.p, 0xff, 2 * sizeof(int64_t), ctx->stream));  // -1 = nothing wrong
+    {
+        KTimer t(ctx, DFB_K_PREP);
+        validate_rle_kernel<<<grid_for(up->total_runs + n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(
+            reinterpret_cast<const int32_t*>(up->lengths.p), up->cum.p, up->run_off.p, n, up->total_runs, len, bad.p);
+    }
+    int64_t hbad[2] = {-1, -1};
+    DFB_TRY(d2h(ctx, hbad, bad.p, sizeof hbad));
+    DFB_REQUIRE(hbad[0] < 0, "Rle column %d has a non-positive run length", (int)hbad[0] + 1);
+    DFB_REQUIRE(hbad[1] < 0, "Rle column %d does not have the expected length %lld", (int)hbad[1] + 1, (long long)len);
     return DFB_OK;
 }
 
@@ -622,19 +703,42 @@ int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, 
     DFB_REQUIRE(ctx && out, "dfb_cov_from_rle: NULL argument");
     *out = nullptr;
     DFB_REQUIRE(pos_len != nullptr, "'coverageInfo$position' is NULL when it shouldn't be.");
-    std::vector<int32_t> npl;
-    int npf = 0;
-    dfb_cov* c = nullptr;
-    DFB_TRY(filter_rle_impl(ctx, n, dtype, values, lengths, nruns, N, nullptr, DFB_FILTER_NONE, 0.0, false, &npl, &npf,
-                            &c));
+    RleUpload up;
+    DFB_TRY(upload_rle(ctx, n, dtype, values, lengths, nruns, N, &up));
+    dfb_cov* c = new dfb_cov();
+    c->ctx = ctx;
+    c->n = n;
+    c->N = N;
+    c->dtype = dtype;
     int rc = c->pos.build(ctx, pos_len, pos_nruns, pos_first);
     if (rc >= 0 && c->pos.N != N) {
         set_error("nrow(coverage) = %lld does not match sum(position) = %lld", (long long)N, (long long)c->pos.N);
         rc = DFB_EINVAL;
     }
+    if (rc >= 0) rc = alloc_matrix(c);
     if (rc < 0) {
         delete c;
         return rc;
+    }
+    if (N > 0) {
+        RleDev R;
+        R.values = up.values.p;
+        R.cum = up.cum.p;
+        R.run_off = up.run_off.p;
+        R.n = n;
+        R.len = N;
+        const int64_t tiles = ceil_div(N, K1_TILE);
+        const dim3 grid((unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 8), (unsigned)n);
+        KTimer t(ctx, DFB_K_PREP);
+        if (dtype == DFB_I32) expand_rle_kernel<int32_t><<<grid, K1_THREADS, 0, ctx->stream>>>(R, c->ld, c->xi.p);
+        else expand_rle_kernel<double><<<grid, K1_THREADS, 0, ctx->stream>>>(R, c->ld, c->xd.p);
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // `up` buffers die with this frame
+    if (e != cudaSuccess) {
+        set_error("Rle expansion: %s", cudaGetErrorString(e));
+        delete c;
+        return DFB_ECUDA;
     }
     *out = c;
     return DFB_OK;

@@ -1,4 +1,5 @@
 // Context, error string, copies, device-wide scan.
+#include <emmintrin.h>
 #include <stdarg.h>
 
 #include <algorithm>
@@ -30,41 +31,226 @@ int d2h(dfb_ctx* ctx, void* dst, const void* src, size_t bytes) {
     return DFB_OK;
 }
 
-// Large pageable host buffers (R vectors, numpy arrays) are moved through two pinned staging
-// buffers so the DMA runs at PCIe speed and overlaps the host-side memcpy of the previous chunk.
-constexpr size_t STAGE_BYTES = 16u << 20;
+// ------------------------------------------------------------------------------------------
+// host copy pool
+
+CopyPool::CopyPool(int nthreads) {
+    for (int i = 0; i < nthreads - 1; ++i) workers_.emplace_back([this] { worker(); });
+}
+
+CopyPool::~CopyPool() {
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        stop_ = true;
+    }
+    work_cv_.notify_all();
+    for (auto& t : workers_) t.join();
+}
+
+void CopyPool::worker() {
+    uint64_t seen = 0;
+    for (;;) {
+        const std::function<void(int)>* fn;
+        int nparts;
+        {
+            std::unique_lock<std::mutex> lk(m_);
+            work_cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
+            if (stop_) return;
+            seen = generation_;
+            fn = fn_;
+            nparts = nparts_;
+        }
+        for (int i; (i = next_.fetch_add(1)) < nparts;) (*fn)(i);
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            if (--active_ == 0) done_cv_.notify_all();
+        }
+    }
+}
+
+void CopyPool::parallel_for(int nparts, const std::function<void(int)>& fn) {
+    if (nparts <= 1 || workers_.empty()) {
+        for (int i = 0; i < nparts; ++i) fn(i);
+        return;
+    }
+    {
+        std::lock_guard<std::mutex> lk(m_);
+        fn_ = &fn;
+        nparts_ = nparts;
+        next_.store(0);
+        active_ = (int)workers_.size();
+        ++generation_;
+    }
+    work_cv_.notify_all();
+    for (int i; (i = next_.fetch_add(1)) < nparts;) fn(i);
+    std::unique_lock<std::mutex> lk(m_);
+    done_cv_.wait(lk, [&] { return active_ == 0; });
+}
+
+// Large pageable host buffers (R vectors, numpy arrays) are moved through a ring of pinned staging
+// buffers so the DMA runs at PCIe speed; the host side of every chunk (pinned <-> pageable memcpy)
+// is spread over the copy pool and overlaps the DMA of the following chunks.
+constexpr size_t STAGE_BYTES = 8u << 20;
+constexpr int NSTAGE = 4;
 
 static int ensure_staging(dfb_ctx* ctx) {
     if (ctx->pinned) return DFB_OK;
-    DFB_CUDA(cudaMallocHost(&ctx->pinned, 2 * STAGE_BYTES));
-    ctx->pinned_bytes = 2 * STAGE_BYTES;
-    for (int i = 0; i < 2; ++i) DFB_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
-    return DFB_OK;
-}
-
-int d2h_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes) {
-    if (bytes < (1u << 20)) return d2h(ctx, dst, src, bytes);
-    DFB_TRY(ensure_staging(ctx));
-    char* pin = (char*)ctx->pinned;
-    const size_t nchunk = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
-    for (size_t i = 0; i <= nchunk; ++i) {
-        if (i < nchunk) {
-            const size_t off = i * STAGE_BYTES, sz = std::min(STAGE_BYTES, bytes - off);
-            DFB_CUDA(cudaMemcpyAsync(pin + (i & 1) * STAGE_BYTES, (const char*)src + off, sz, cudaMemcpyDeviceToHost,
-                                     ctx->stream));
-            DFB_CUDA(cudaEventRecord(ctx->stage_ev[i & 1], ctx->stream));
-        }
-        if (i > 0) {
-            const size_t j = i - 1, off = j * STAGE_BYTES, sz = std::min(STAGE_BYTES, bytes - off);
-            DFB_CUDA(cudaEventSynchronize(ctx->stage_ev[j & 1]));
-            memcpy((char*)dst + off, pin + (j & 1) * STAGE_BYTES, sz);
-        }
+    DFB_CUDA(cudaMallocHost(&ctx->pinned, NSTAGE * STAGE_BYTES));
+    ctx->pinned_bytes = NSTAGE * STAGE_BYTES;
+    for (int i = 0; i < NSTAGE; ++i) DFB_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
+    if (!ctx->pool) {
+        unsigned hc = std::thread::hardware_concurrency();
+        int nt = (int)std::min<unsigned>(8, std::max<unsigned>(1, hc / 2));
+        ctx->pool = new CopyPool(nt);
     }
     return DFB_OK;
 }
 
+static bool is_pinned_host(const void* p) {
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// memcpy with non-temporal stores: the destination (the caller's result vector) is written once and
+// not read back here, so bypassing the cache avoids the read-for-ownership traffic of every line.
+static void copy_stream(char* dst, const char* src, size_t n) {
+    if (n < 4096) {
+        memcpy(dst, src, n);
+        return;
+    }
+    const size_t head = (16 - ((uintptr_t)dst & 15)) & 15;
+    memcpy(dst, src, head);
+    dst += head;
+    src += head;
+    n -= head;
+    const size_t body = n & ~(size_t)63;
+    for (size_t i = 0; i < body; i += 64) {
+        const __m128i a = _mm_loadu_si128((const __m128i*)(src + i));
+        const __m128i b = _mm_loadu_si128((const __m128i*)(src + i + 16));
+        const __m128i c = _mm_loadu_si128((const __m128i*)(src + i + 32));
+        const __m128i d = _mm_loadu_si128((const __m128i*)(src + i + 48));
+        _mm_stream_si128((__m128i*)(dst + i), a);
+        _mm_stream_si128((__m128i*)(dst + i + 16), b);
+        _mm_stream_si128((__m128i*)(dst + i + 32), c);
+        _mm_stream_si128((__m128i*)(dst + i + 48), d);
+    }
+    memcpy(dst + body, src + body, n - body);
+    _mm_sfence();
+}
+
+static void pool_memcpy(dfb_ctx* ctx, char* dst, const char* src, size_t bytes) {
+    const int parts = (int)std::min<size_t>((size_t)ctx->pool->size(), std::max<size_t>(1, bytes >> 18));
+    const size_t per = ((bytes + parts - 1) / parts + 63) & ~(size_t)63;
+    ctx->pool->parallel_for(parts, [&](int i) {
+        const size_t o = (size_t)i * per;
+        if (o < bytes) copy_stream(dst + o, src + o, std::min(per, bytes - o));
+    });
+}
+
+// Generic chunked D2H: `sink(chunk_offset, pinned_ptr, chunk_bytes)` consumes each chunk on the host.
+template <typename Sink>
+static int d2h_chunks(dfb_ctx* ctx, const void* src, size_t bytes, Sink sink) {
+    DFB_TRY(ensure_staging(ctx));
+    char* pin = (char*)ctx->pinned;
+    const size_t nchunk = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
+    size_t issued = 0;
+    for (size_t done = 0; done < nchunk; ++done) {
+        for (; issued < nchunk && issued < done + NSTAGE; ++issued) {
+            const size_t off = issued * STAGE_BYTES, sz = std::min(STAGE_BYTES, bytes - off);
+            DFB_CUDA(cudaMemcpyAsync(pin + (issued % NSTAGE) * STAGE_BYTES, (const char*)src + off, sz,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+            DFB_CUDA(cudaEventRecord(ctx->stage_ev[issued % NSTAGE], ctx->stream));
+        }
+        const size_t off = done * STAGE_BYTES, sz = std::min(STAGE_BYTES, bytes - off);
+        DFB_CUDA(cudaEventSynchronize(ctx->stage_ev[done % NSTAGE]));
+        sink(off, pin + (done % NSTAGE) * STAGE_BYTES, sz);
+    }
+    return DFB_OK;
+}
+
+int d2h_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    if (bytes < (1u << 20) || is_pinned_host(dst)) return d2h(ctx, dst, src, bytes);
+    return d2h_chunks(ctx, src, bytes,
+                      [&](size_t off, const char* p, size_t sz) { pool_memcpy(ctx, (char*)dst + off, p, sz); });
+}
+
+int d2h_dup(dfb_ctx* ctx, void* dst, const void* src, size_t elem, const int64_t* pre, int64_t B) {
+    const size_t count = (size_t)pre[B];
+    if (count == 0) return DFB_OK;
+    int64_t blk = 0;  // first block that may overlap the current chunk (chunks arrive in order)
+    return d2h_chunks(ctx, src, count * elem, [&](size_t off, const char* p, size_t sz) {
+        // element range of this chunk (STAGE_BYTES is a multiple of every element size used)
+        const int64_t e0 = (int64_t)(off / elem), e1 = e0 + (int64_t)(sz / elem);
+        struct Seg { char* d1; char* d2; const char* s; size_t n; };
+        std::vector<Seg> segs;
+        while (blk < B && pre[blk + 1] <= e0) ++blk;
+        for (int64_t b = blk; b < B && pre[b] < e1; ++b) {
+            const int64_t lo = std::max(pre[b], e0), hi = std::min(pre[b + 1], e1);
+            if (hi <= lo) continue;
+            const int64_t k = pre[b + 1] - pre[b];
+            char* d1 = (char*)dst + (size_t)(2 * pre[b] + (lo - pre[b])) * elem;
+            segs.push_back({d1, d1 + (size_t)k * elem, p + (size_t)(lo - e0) * elem, (size_t)(hi - lo) * elem});
+        }
+        // split the segments into ~256 KiB pieces for the pool
+        std::vector<Seg> parts;
+        for (auto& sg : segs)
+            for (size_t o = 0; o < sg.n; o += (256u << 10))
+                parts.push_back({sg.d1 + o, sg.d2 + o, sg.s + o, std::min<size_t>(256u << 10, sg.n - o)});
+        ctx->pool->parallel_for((int)parts.size(), [&](int i) {
+            copy_stream(parts[i].d1, parts[i].s, parts[i].n);
+            copy_stream(parts[i].d2, parts[i].s, parts[i].n);
+        });
+    });
+}
+
+// H2D of `count` host segments laid back to back in device memory: the segments are packed into the
+// pinned ring by the copy pool (one DMA per 8 MiB instead of one driver-staged copy per segment).
+int h2d_gather(dfb_ctx* ctx, void* dst, const void* const* srcs, const size_t* bytes, int count) {
+    DFB_TRY(ensure_staging(ctx));
+    char* pin = (char*)ctx->pinned;
+    struct Piece { char* d; const char* s; size_t n; };
+    size_t chunk = 0, fill = 0, dev_off = 0;
+    std::vector<Piece> pieces;
+    bool waited = false;
+    auto flush = [&]() -> int {
+        if (fill == 0) return DFB_OK;
+        ctx->pool->parallel_for((int)pieces.size(), [&](int i) { copy_stream(pieces[i].d, pieces[i].s, pieces[i].n); });
+        DFB_CUDA(cudaMemcpyAsync((char*)dst + dev_off, pin + (chunk % NSTAGE) * STAGE_BYTES, fill, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+        DFB_CUDA(cudaEventRecord(ctx->stage_ev[chunk % NSTAGE], ctx->stream));
+        dev_off += fill;
+        fill = 0;
+        pieces.clear();
+        ++chunk;
+        waited = false;
+        return DFB_OK;
+    };
+    for (int i = 0; i < count; ++i) {
+        size_t done = 0;
+        while (done < bytes[i]) {
+            if (!waited && chunk >= (size_t)NSTAGE) DFB_CUDA(cudaEventSynchronize(ctx->stage_ev[chunk % NSTAGE]));
+            waited = true;
+            const size_t room = STAGE_BYTES - fill;
+            const size_t take = std::min(room, bytes[i] - done);
+            char* base = pin + (chunk % NSTAGE) * STAGE_BYTES + fill;
+            for (size_t o = 0; o < take; o += (256u << 10))
+                pieces.push_back({base + o, (const char*)srcs[i] + done + o, std::min<size_t>(256u << 10, take - o)});
+            fill += take;
+            done += take;
+            if (fill == STAGE_BYTES) DFB_TRY(flush());
+        }
+    }
+    DFB_TRY(flush());
+    DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DFB_OK;
+}
+
 int h2d_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes) {
-    if (bytes < (1u << 20)) {
+    if (bytes < (1u << 20) || is_pinned_host(src)) {
         DFB_TRY(h2d(ctx, dst, src, bytes));
         DFB_CUDA(cudaStreamSynchronize(ctx->stream));
         return DFB_OK;
@@ -74,10 +260,11 @@ int h2d_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes) {
     const size_t nchunk = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
     for (size_t i = 0; i < nchunk; ++i) {
         const size_t off = i * STAGE_BYTES, sz = std::min(STAGE_BYTES, bytes - off);
-        if (i >= 2) DFB_CUDA(cudaEventSynchronize(ctx->stage_ev[i & 1]));  // staging buffer free again
-        memcpy(pin + (i & 1) * STAGE_BYTES, (const char*)src + off, sz);
-        DFB_CUDA(cudaMemcpyAsync((char*)dst + off, pin + (i & 1) * STAGE_BYTES, sz, cudaMemcpyHostToDevice, ctx->stream));
-        DFB_CUDA(cudaEventRecord(ctx->stage_ev[i & 1], ctx->stream));
+        if (i >= NSTAGE) DFB_CUDA(cudaEventSynchronize(ctx->stage_ev[i % NSTAGE]));  // staging buffer free again
+        pool_memcpy(ctx, pin + (i % NSTAGE) * STAGE_BYTES, (const char*)src + off, sz);
+        DFB_CUDA(cudaMemcpyAsync((char*)dst + off, pin + (i % NSTAGE) * STAGE_BYTES, sz, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+        DFB_CUDA(cudaEventRecord(ctx->stage_ev[i % NSTAGE], ctx->stream));
     }
     DFB_CUDA(cudaStreamSynchronize(ctx->stream));
     return DFB_OK;
@@ -297,8 +484,10 @@ void dfb_destroy(dfb_ctx* c) {
     }
     if (c->pinned) {
         cudaFreeHost(c->pinned);
-        for (int i = 0; i < 2; ++i) cudaEventDestroy(c->stage_ev[i]);
+        for (int i = 0; i < 4; ++i) cudaEventDestroy(c->stage_ev[i]);
     }
+    if (c->pinned_small) cudaFreeHost(c->pinned_small);
+    delete c->pool;
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
 }

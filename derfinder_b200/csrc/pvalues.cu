@@ -21,27 +21,6 @@ __global__ void add_perm_offset_kernel(int32_t* __restrict__ perm, int64_t n, in
     if (i < n) perm[i] += offset;
 }
 
-// source index of every row of the duplicated null table ([r1..rk, r1..rk] per permutation)
-__global__ void dup_index_kernel(const int64_t* __restrict__ pre, int64_t B, int64_t M, int64_t* __restrict__ src) {
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < 2 * M; o += (int64_t)gridDim.x * blockDim.x) {
-        int64_t lo = 0, hi = B;  // largest b with 2*pre[b] <= o
-        while (hi - lo > 1) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (2 * pre[mid] <= o) lo = mid;
-            else hi = mid;
-        }
-        const int64_t k = pre[lo + 1] - pre[lo];
-        const int64_t r = o - 2 * pre[lo];
-        src[o] = pre[lo] + (r >= k ? r - k : r);
-    }
-}
-
-template <typename T>
-__global__ void gather_kernel(const T* __restrict__ in, const int64_t* __restrict__ src, int64_t n, T* __restrict__ out) {
-    for (int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; o < n; o += (int64_t)gridDim.x * blockDim.x)
-        out[o] = in[src[o]];
-}
-
 static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const double* mod0, int p0,
                            double adjust_f, const int32_t* perm_idx, int64_t B, double lo, double hi,
                            int32_t max_region_gap, dfb_nulls** out) {
@@ -399,43 +378,17 @@ int dfb_nulls_get(const dfb_nulls* nl, int dup, double* stat, int32_t* width, do
         if (permutation) DFB_TRY(d2h_big(ctx, permutation, nl->perm.p, M * 4));
         return DFB_OK;
     }
-    // the reference appends every permutation's regions twice: [r1..rk, r1..rk] (:346-354).  The
-    // duplicated layout is produced on the device (gather) and downloaded straight into the
-    // caller's buffers.
+    // the reference appends every permutation's regions twice: [r1..rk, r1..rk] (:346-354).  Every
+    // array crosses PCIe once; the duplicated layout is written by the host copy pool while the
+    // next chunk is in flight.
     const int64_t B = (int64_t)nl->per_perm.size();
     std::vector<int64_t> pre((size_t)B + 1, 0);
     for (int64_t b = 0; b < B; ++b) pre[(size_t)b + 1] = pre[(size_t)b] + nl->per_perm[(size_t)b];
-    DevBuf<int64_t> pre_d;
-    DevBuf<int64_t> src_d;
-    DFB_TRY(pre_d.alloc(ctx, (size_t)B + 1));
-    DFB_TRY(src_d.alloc(ctx, 2 * M));
-    DFB_TRY(h2d(ctx, pre_d.p, pre.data(), pre.size() * sizeof(int64_t)));
-    {
-        KTimer t(ctx, DFB_K_PVAL);
-        dup_index_kernel<<<grid_for((int64_t)(2 * M), 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(pre_d.p, B,
-                                                                                                      (int64_t)M, src_d.p);
-    }
-    DFB_CUDA(cudaGetLastError());
-    DFB_CUDA(cudaStreamSynchronize(ctx->stream));  // `pre` is a local
-    DevBuf<double> t8;
-    DevBuf<int32_t> t4;
-    DFB_TRY(t8.alloc(ctx, 2 * M));
-    DFB_TRY(t4.alloc(ctx, 2 * M));
-    const int grid = grid_for((int64_t)(2 * M), 256, ctx->sm_count, 16);
-    auto get8 = [&](const double* src, double* dst) -> int {
-        if (!dst) return DFB_OK;
-        gather_kernel<double><<<grid, 256, 0, ctx->stream>>>(src, src_d.p, (int64_t)(2 * M), t8.p);
-        return d2h_big(ctx, dst, t8.p, 2 * M * 8);
-    };
-    auto get4 = [&](const int32_t* src, int32_t* dst) -> int {
-        if (!dst) return DFB_OK;
-        gather_kernel<int32_t><<<grid, 256, 0, ctx->stream>>>(src, src_d.p, (int64_t)(2 * M), t4.p);
-        return d2h_big(ctx, dst, t4.p, 2 * M * 4);
-    };
-    DFB_TRY(get8(nl->stat.p, stat));
-    DFB_TRY(get8(nl->area.p, area));
-    DFB_TRY(get4(nl->width.p, width));
-    DFB_TRY(get4(nl->perm.p, permutation));
+    DFB_REQUIRE(pre[(size_t)B] == (int64_t)M, "internal error: per-permutation counts do not add up");
+    if (stat) DFB_TRY(d2h_dup(ctx, stat, nl->stat.p, 8, pre.data(), B));
+    if (area) DFB_TRY(d2h_dup(ctx, area, nl->area.p, 8, pre.data(), B));
+    if (width) DFB_TRY(d2h_dup(ctx, width, nl->width.p, 4, pre.data(), B));
+    if (permutation) DFB_TRY(d2h_dup(ctx, permutation, nl->perm.p, 4, pre.data(), B));
     return DFB_OK;
 }
 
