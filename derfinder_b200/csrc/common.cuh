@@ -7,6 +7,7 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <algorithm>
 #include <atomic>
 #include <condition_variable>
 #include <functional>
@@ -86,6 +87,8 @@ struct dfb_ctx {
     struct Ev {
         cudaEvent_t a, b;
         int k;
+        const char* file;
+        int line;
     };
     std::vector<Ev> evs;
     double kms[DFB_K_COUNT] = {0};
@@ -101,8 +104,17 @@ struct dfb_ctx {
     size_t pinned_bytes = 0;
     cudaEvent_t stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
     dfb::CopyPool* pool = nullptr;
-    // small pinned scratch for scalar / O(B) read-backs (truly asynchronous D2H)
-    void* pinned_small = nullptr;
+    // pinned arena for scalar / O(regions) read-backs: D2H into pinned memory is truly asynchronous,
+    // so several results can be fetched with ONE stream synchronisation.  Blocks are kept for reuse.
+    struct PinBlock {
+        char* p;
+        size_t cap, used;
+    };
+    std::vector<PinBlock> pin_blocks;
+    // log2(k + scalefac) table for integer coverage (glibc log2, built once per scalefac)
+    double* lut_dev = nullptr;
+    int64_t lut_n = 0;
+    double lut_scalefac = 0;
 };
 
 namespace dfb {
@@ -113,7 +125,10 @@ struct KTimer {
     dfb_ctx* c;
     int k;
     cudaEvent_t a = nullptr, b = nullptr;
-    KTimer(dfb_ctx* ctx, int kernel, int nlaunch = 1) : c(ctx), k(kernel) {
+    const char* file;
+    int line;
+    KTimer(dfb_ctx* ctx, int kernel, int nlaunch = 1, const char* f = __builtin_FILE(), int l = __builtin_LINE())
+        : c(ctx), k(kernel), file(f), line(l) {
         c->launches += nlaunch;
         c->klaunch[k] += nlaunch;
         if (c->timing) {
@@ -125,7 +140,7 @@ struct KTimer {
     ~KTimer() {
         if (c->timing) {
             cudaEventRecord(b, c->stream);
-            c->evs.push_back({a, b, k});
+            c->evs.push_back({a, b, k, file, line});
         }
     }
 };
@@ -178,6 +193,18 @@ struct DevBuf {
     }
 };
 
+// bump allocation from the context's pinned arena (valid until the next arena_reset)
+void* arena_alloc(dfb_ctx* ctx, size_t bytes);
+void arena_reset(dfb_ctx* ctx);
+// asynchronous D2H into arena memory: returns the pinned pointer, valid after the next stream sync
+template <typename T>
+static inline T* d2h_async_pinned(dfb_ctx* ctx, const T* src_dev, size_t count) {
+    T* h = (T*)arena_alloc(ctx, std::max<size_t>(count, 1) * sizeof(T));
+    if (h && count) {
+        if (cudaMemcpyAsync(h, src_dev, count * sizeof(T), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) return nullptr;
+    }
+    return h;
+}
 int h2d(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);
 int d2h(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);  // synchronises the stream
 // pageable <-> device through a ring of pinned staging buffers drained / filled by the host copy

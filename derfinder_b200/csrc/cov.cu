@@ -569,6 +569,7 @@ struct PrepParams {
     double* y;      // [n][ld]
     double* mean;   // [N] or nullptr (already present)
     double* gmean;  // [G][ld]
+    int* out_of_range;  // set when an integer value falls outside the table (the caller re-runs)
 };
 
 template <typename V>
@@ -587,8 +588,17 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PrepParams P) {
                 *a = __dadd_rn(*a, v);
             }
             double yv;
-            if (sizeof(V) == 4 && P.lut) yv = P.lut[(int64_t)raw];
-            else yv = log2(__dadd_rn(v, P.scalefac));
+            if (sizeof(V) == 4 && P.lut) {
+                const int64_t k = (int64_t)raw;
+                if (k >= 0 && k < P.lut_n) {
+                    yv = P.lut[k];
+                } else {
+                    yv = 0.0;
+                    *P.out_of_range = 1;
+                }
+            } else {
+                yv = log2(__dadd_rn(v, P.scalefac));
+            }
             P.y[(size_t)s * P.ld + i] = yv;
         }
         if (P.mean) P.mean[i] = __ddiv_rn(sum, (double)P.n);
@@ -806,29 +816,33 @@ int dfb_preprocess(dfb_ctx* ctx, dfb_cov* c, double scalefac, const int32_t* gro
         return DFB_OK;
     }
     // integer coverage: log2 through a host-built table (glibc log2, the function R calls), so
-    // coverageProcessed is bit-identical to log2(x + scalefac) evaluated by R on this host
+    // coverageProcessed is bit-identical to log2(x + scalefac) evaluated by R on this host.  The
+    // context keeps a 64 Ki-entry table per scalefac; a value outside it (flagged by the kernel) falls
+    // back to a table sized from the data's min/max, or to device log2 beyond 2^22.
     DevBuf<double> lut;
+    const double* lut_p = nullptr;
     int64_t lut_n = 0;
+    DevBuf<int> oor;
+    DFB_TRY(oor.alloc(ctx, 1));
+    DFB_TRY(oor.zero());
+    auto build_lut = [&](int64_t entries, double* dst_dev) -> int {
+        std::vector<double> h((size_t)entries);
+        for (int64_t k = 0; k < entries; ++k) h[(size_t)k] = log2((double)k + scalefac);
+        DFB_TRY(h2d(ctx, dst_dev, h.data(), (size_t)entries * sizeof(double)));
+        DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        return DFB_OK;
+    };
     if (c->dtype == DFB_I32) {
-        DevBuf<long long> mm;
-        DFB_TRY(mm.alloc(ctx, 2));
-        long long init[2] = {LLONG_MAX, LLONG_MIN};
-        DFB_TRY(h2d(ctx, mm.p, init, sizeof init));
-        {
-            KTimer t(ctx, DFB_K_PREP);
-            minmax_kernel<int32_t><<<dim3(grid_for(c->N, 256 * 8, ctx->sm_count, 4), c->n), 256, 0, ctx->stream>>>(
-                c->xi.p, c->ld, c->N, c->n, mm.p, mm.p + 1);
+        constexpr int64_t CTX_LUT = 65536;
+        if (!ctx->lut_dev || ctx->lut_scalefac != scalefac) {
+            if (!ctx->lut_dev) DFB_CUDA(cudaMalloc((void**)&ctx->lut_dev, CTX_LUT * sizeof(double)));
+            ctx->lut_n = 0;
+            DFB_TRY(build_lut(CTX_LUT, ctx->lut_dev));
+            ctx->lut_n = CTX_LUT;
+            ctx->lut_scalefac = scalefac;
         }
-        long long got[2];
-        DFB_TRY(d2h(ctx, got, mm.p, sizeof got));
-        if (got[0] >= 0 && got[1] < (1ll << 22)) {
-            lut_n = got[1] + 1;
-            std::vector<double> h((size_t)lut_n);
-            for (int64_t k = 0; k < lut_n; ++k) h[(size_t)k] = log2((double)k + scalefac);
-            DFB_TRY(lut.alloc(ctx, (size_t)lut_n));
-            DFB_TRY(h2d(ctx, lut.p, h.data(), (size_t)lut_n * sizeof(double)));
-            DFB_CUDA(cudaStreamSynchronize(ctx->stream));
-        }
+        lut_p = ctx->lut_dev;
+        lut_n = ctx->lut_n;
     }
     DevBuf<int32_t> grp;
     DevBuf<double> gsz;
@@ -845,7 +859,7 @@ int dfb_preprocess(dfb_ctx* ctx, dfb_cov* c, double scalefac, const int32_t* gro
     P.N = c->N;
     P.n = c->n;
     P.scalefac = scalefac;
-    P.lut = lut_n ? lut.p : nullptr;
+    P.lut = lut_n ? lut_p : nullptr;
     P.lut_n = lut_n;
     P.group = n_groups ? grp.p : nullptr;
     P.group_size = n_groups ? gsz.p : nullptr;
@@ -853,8 +867,9 @@ int dfb_preprocess(dfb_ctx* ctx, dfb_cov* c, double scalefac, const int32_t* gro
     P.y = c->y.p;
     P.mean = need_mean ? c->mean.p : nullptr;
     P.gmean = n_groups ? c->gmean.p : nullptr;
+    P.out_of_range = oor.p;
     const size_t smem = (size_t)n_groups * 256 * sizeof(double);
-    {
+    auto launch = [&]() -> int {
         KTimer t(ctx, DFB_K_PREP);
         const int grid = grid_for(c->N, 256, ctx->sm_count, 16);
         if (c->dtype == DFB_I32) {
@@ -868,9 +883,38 @@ int dfb_preprocess(dfb_ctx* ctx, dfb_cov* c, double scalefac, const int32_t* gro
                                               (int)smem));
             preprocess_kernel<double><<<grid, 256, smem, ctx->stream>>>(P);
         }
-    }
+        return DFB_OK;
+    };
+    DFB_TRY(launch());
     DFB_CUDA(cudaGetLastError());
-    DFB_CUDA(cudaStreamSynchronize(ctx->stream));  // group arrays / LUT are locals
+    int flagged = 0;
+    DFB_TRY(d2h(ctx, &flagged, oor.p, sizeof flagged));  // synchronises: group arrays are locals
+    if (flagged) {
+        // rare: coverage beyond the context table.  Size a table from the data, or use device log2.
+        DevBuf<long long> mm;
+        DFB_TRY(mm.alloc(ctx, 2));
+        long long init[2] = {LLONG_MAX, LLONG_MIN};
+        DFB_TRY(h2d(ctx, mm.p, init, sizeof init));
+        {
+            KTimer t(ctx, DFB_K_PREP);
+            minmax_kernel<int32_t><<<dim3(grid_for(c->N, 256 * 8, ctx->sm_count, 4), c->n), 256, 0, ctx->stream>>>(
+                c->xi.p, c->ld, c->N, c->n, mm.p, mm.p + 1);
+        }
+        long long got[2];
+        DFB_TRY(d2h(ctx, got, mm.p, sizeof got));
+        P.lut = nullptr;
+        P.lut_n = 0;
+        if (got[0] >= 0 && got[1] < (1ll << 22)) {
+            DFB_TRY(lut.alloc(ctx, (size_t)got[1] + 1));
+            DFB_TRY(build_lut(got[1] + 1, lut.p));
+            P.lut = lut.p;
+            P.lut_n = got[1] + 1;
+        }
+        DFB_TRY(oor.zero());
+        DFB_TRY(launch());
+        DFB_CUDA(cudaGetLastError());
+        DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     c->has_mean = true;
     c->has_f = false;
     return DFB_OK;

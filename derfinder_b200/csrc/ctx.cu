@@ -1,6 +1,7 @@
 // Context, error string, copies, device-wide scan.
 #include <emmintrin.h>
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -17,6 +18,29 @@ void set_error(const char* fmt, ...) {
     vsnprintf(buf, sizeof buf, fmt, ap);
     va_end(ap);
     g_err = buf;
+}
+
+void* arena_alloc(dfb_ctx* ctx, size_t bytes) {
+    bytes = (bytes + 63) & ~(size_t)63;
+    for (auto& b : ctx->pin_blocks)
+        if (b.cap - b.used >= bytes) {
+            void* p = b.p + b.used;
+            b.used += bytes;
+            return p;
+        }
+    const size_t cap = std::max<size_t>(bytes, (size_t)4 << 20);
+    char* p = nullptr;
+    if (cudaMallocHost((void**)&p, cap) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("pinned host allocation of %zu bytes failed", cap);
+        return nullptr;
+    }
+    ctx->pin_blocks.push_back({p, cap, bytes});
+    return p;
+}
+
+void arena_reset(dfb_ctx* ctx) {
+    for (auto& b : ctx->pin_blocks) b.used = 0;
 }
 
 int h2d(dfb_ctx* ctx, void* dst, const void* src, size_t bytes) {
@@ -486,7 +510,8 @@ void dfb_destroy(dfb_ctx* c) {
         cudaFreeHost(c->pinned);
         for (int i = 0; i < 4; ++i) cudaEventDestroy(c->stage_ev[i]);
     }
-    if (c->pinned_small) cudaFreeHost(c->pinned_small);
+    for (auto& b : c->pin_blocks) cudaFreeHost(b.p);
+    if (c->lut_dev) cudaFree(c->lut_dev);
     delete c->pool;
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -503,6 +528,21 @@ int64_t dfb_launch_count(dfb_ctx* c) { return c ? c->launches : 0; }
 static int drain_events(dfb_ctx* c) {
     if (c->evs.empty()) return DFB_OK;
     DFB_CUDA(cudaStreamSynchronize(c->stream));
+    if (getenv("DFB_GAPS")) {
+        // developer aid: device idle time between consecutive timed launches (host-induced bubbles)
+        double busy = 0, idle = 0;
+        for (size_t i = 0; i < c->evs.size(); ++i) {
+            float ms = 0.f, gap = 0.f;
+            cudaEventElapsedTime(&ms, c->evs[i].a, c->evs[i].b);
+            busy += ms;
+            if (i + 1 < c->evs.size()) cudaEventElapsedTime(&gap, c->evs[i].b, c->evs[i + 1].a);
+            idle += gap;
+            const char* f = strrchr(c->evs[i].file, '/');
+            fprintf(stderr, "[dfb] %-14s:%-5d fam %d  run %8.3f ms   then idle %8.3f ms\n", f ? f + 1 : c->evs[i].file,
+                    c->evs[i].line, c->evs[i].k, ms, gap);
+        }
+        fprintf(stderr, "[dfb] busy %.3f ms, idle between timed launches %.3f ms\n", busy, idle);
+    }
     for (auto& e : c->evs) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) c->kms[e.k] += ms;

@@ -50,8 +50,9 @@ struct dfb_regions {
     std::vector<int32_t> start, end, index_start, index_end, cluster;
     std::vector<double> value, area, cluster_l, pvalues;
     std::vector<int32_t> order;
-    // device copies of the index ranges (kept for view means / region matrix)
+    // device copies of the index ranges (kept for view means / region matrix) and of the areas
     dfb::DevBuf<int32_t> d_is, d_ie;
+    dfb::DevBuf<double> d_area;
 };
 
 struct dfb_nulls {
@@ -87,6 +88,10 @@ struct PermBatch {
     DevBuf<int64_t> off;   // [rows][tiles] offset of the tile's first exceedance value
     DevBuf<double> vals;   // compacted F values
     int64_t nvals = 0;
+    // deferred overflow check (fused path): pinned copy of the value cursor, valid after the next
+    // stream synchronisation; the batch is good iff *used_host <= capacity
+    const unsigned long long* used_host = nullptr;
+    size_t capacity = 0;
 };
 
 int fstat_tile_bases(int n);
@@ -106,7 +111,7 @@ bool fused_supported(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& m
                      double adjust_f);
 int fstat_perm_batch_fused(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, const double* q_dev /*[n][p]*/,
                            double adjust_f, const int32_t* idx_dev, int64_t B, double hi, size_t capacity_hint,
-                           PermBatch* out);
+                           PermBatch* out, bool defer_check = false);
 
 int mask_diff(dfb_ctx* ctx, const uint32_t* a, const uint32_t* b, int64_t words, int64_t* diff);
 

@@ -1331,7 +1331,7 @@ static int launch_fused(dfb_ctx* ctx, const FusedParams& F, int grid) {
 // Fused screen + refine for one batch of permutations; fills the same PermBatch as the other paths.
 int fstat_perm_batch_fused(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, const double* q_dev /*[n][p]*/,
                            double adjust_f, const int32_t* idx_dev, int64_t B, double hi, size_t capacity_hint,
-                           PermBatch* out) {
+                           PermBatch* out, bool defer_check) {
     FusedGeom G;
     if (!fused_geometry(ctx, cov, mb, B, &G)) {
         set_error("fused geometry does not fit (internal error)");
@@ -1404,6 +1404,13 @@ int fstat_perm_batch_fused(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& m
             default: DFB_TRY(launch_fused<0>(ctx, F, grid)); break;
         }
         DFB_CUDA(cudaGetLastError());
+        out->capacity = cap;
+        if (defer_check) {
+            // the caller synchronises anyway (region counts): it checks *used_host <= capacity then
+            out->used_host = d2h_async_pinned(ctx, cursor.p, 1);
+            DFB_REQUIRE(out->used_host != nullptr, "pinned read-back of the value cursor failed");
+            return DFB_OK;
+        }
         unsigned long long used = 0;
         DFB_TRY(d2h(ctx, &used, cursor.p, sizeof used));
         out->nvals = (int64_t)used;  // allocated value slots (exceedances + unused chunk tails)

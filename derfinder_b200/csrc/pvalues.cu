@@ -97,7 +97,7 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
         if ((double)hint * 8.0 > budget * 0.5) hint = (size_t)(budget * 0.5 / 8.0);
         PermBatch pbatch;
         int rc = use_fused  ? fstat_perm_batch_fused(ctx, cov, mb, q_d.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, hi,
-                                                     hint, &pbatch)
+                                                     hint, &pbatch, true)
                  : use_screen ? fstat_perm_batch_screen(ctx, cov, mb, q_d.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, hi,
                                                       hint, &pbatch, nullptr)
                             : fstat_perm_batch(ctx, cov, mb, qd.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, lo, hi,
@@ -109,10 +109,27 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
             continue;
         }
         DFB_TRY(rc);
-        if (density >= 0 && dense > 0) density = std::min(1.0, std::max(0.01, 1.3 * (double)pbatch.nvals / dense));
         RegionSet rs;
         DFB_TRY(find_regions_rows(ctx, N, pbatch.rows, sides, pbatch.mask.p, seg.p, nullptr, 0, &pbatch, false, true,
                                   &rs));
+        if (rs.total < 0) {
+            // deferred overflow check of the fused path fired: re-run K2 with the exact capacity
+            const size_t need = (size_t)*pbatch.used_host;
+            pbatch = PermBatch();
+            rc = fstat_perm_batch_fused(ctx, cov, mb, q_d.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, hi, need, &pbatch,
+                                        false);
+            if (rc == DFB_ENOMEM && nb > 1) {
+                const int64_t mid = b_lo + nb / 2;
+                work.push_back({mid, b_hi});
+                work.push_back({b_lo, mid});
+                continue;
+            }
+            DFB_TRY(rc);
+            DFB_TRY(find_regions_rows(ctx, N, pbatch.rows, sides, pbatch.mask.p, seg.p, nullptr, 0, &pbatch, false,
+                                      true, &rs));
+        }
+        if (pbatch.used_host) pbatch.nvals = (int64_t)*pbatch.used_host;
+        if (density >= 0 && dense > 0) density = std::min(1.0, std::max(0.01, 1.3 * (double)pbatch.nvals / dense));
         for (int64_t b = 0; b < nb; ++b)
             for (int s = 0; s < sides; ++s) nl->per_perm[(size_t)(b_lo + b)] += rs.row_counts[(size_t)(b * sides + s)];
         if (rs.total > 0 && b_lo > 0) {
@@ -299,13 +316,19 @@ int quantile_device(dfb_ctx* ctx, const double* x_dev, int64_t N, double prob, d
     return DFB_OK;
 }
 
+__global__ void iota_kernel(int32_t* __restrict__ x, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) x[i] = (int32_t)i;
+}
+
 // stable order(area, decreasing = TRUE): descending radix sort of (area, iota) pairs is stable
 static int order_desc(dfb_ctx* ctx, const double* area_dev, int64_t R, int32_t* order_dev, double* sorted_dev) {
     DevBuf<int32_t> iota;
     DFB_TRY(iota.alloc(ctx, (size_t)R));
-    std::vector<int32_t> h((size_t)R);
-    for (int64_t k = 0; k < R; ++k) h[(size_t)k] = (int32_t)k;
-    DFB_TRY(h2d(ctx, iota.p, h.data(), (size_t)R * sizeof(int32_t)));
+    {
+        KTimer t(ctx, DFB_K_PVAL);
+        iota_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, ctx->stream>>>(iota.p, R);
+    }
     size_t tmp_bytes = 0;
     DFB_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, area_dev, sorted_dev, iota.p, order_dev, R, 0,
                                                        64, ctx->stream));
@@ -316,8 +339,7 @@ static int order_desc(dfb_ctx* ctx, const double* area_dev, int64_t R, int32_t* 
         DFB_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp.p, tmp_bytes, area_dev, sorted_dev, iota.p, order_dev, R,
                                                            0, 64, ctx->stream));
     }
-    DFB_CUDA(cudaStreamSynchronize(ctx->stream));  // `h` is a local
-    return DFB_OK;
+    return DFB_OK;  // stream-ordered: temporaries are released after the sort
 }
 
 }  // namespace dfb
@@ -348,6 +370,7 @@ int dfb_perm_nulls(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const d
                    const int32_t* perm_idx, int64_t B, double cutoff_lo, double cutoff_hi, int32_t max_region_gap,
                    dfb_nulls** out) {
     DFB_REQUIRE(ctx && cov && out, "dfb_perm_nulls: NULL argument");
+    arena_reset(ctx);
     return perm_nulls_impl(ctx, cov, mod, p, mod0, p0, adjust_f, perm_idx, B, cutoff_lo, cutoff_hi, max_region_gap,
                            out);
 }
@@ -521,6 +544,7 @@ int dfb_calculate_pvalues(dfb_ctx* ctx, dfb_cov* cov, const double* fstats, cons
                           double cutoff_lo, double cutoff_hi, int32_t max_region_gap, int32_t max_cluster_gap,
                           dfb_regions** regions, dfb_nulls** nulls, double* pvalues) {
     DFB_REQUIRE(ctx && cov && regions && nulls, "dfb_calculate_pvalues: NULL argument");
+    arena_reset(ctx);
     *regions = nullptr;
     *nulls = nullptr;
     DFB_REQUIRE(cutoff_lo <= cutoff_hi, "cutoff pair must be sorted (L <= U)");
@@ -542,28 +566,33 @@ int dfb_calculate_pvalues(dfb_ctx* ctx, dfb_cov* cov, const double* fstats, cons
         delete r;
         return rc;
     }
-    // order by decreasing area (stable), then p-values against the (duplicated) null areas
+    // order by decreasing area (stable), then p-values against the (duplicated) null areas; the
+    // region areas are still on the device, order and p-values come back with one synchronisation
     const int64_t R = r->R;
-    DevBuf<double> area_d, sorted_d, p_d;
+    DevBuf<double> sorted_d, p_d;
     DevBuf<int32_t> order_d;
     auto fail = [&](int code) {
         delete r;
         delete nl;
         return code;
     };
-    if ((rc = area_d.alloc(ctx, (size_t)R)) < 0) return fail(rc);
     if ((rc = sorted_d.alloc(ctx, (size_t)R)) < 0) return fail(rc);
     if ((rc = p_d.alloc(ctx, (size_t)R)) < 0) return fail(rc);
     if ((rc = order_d.alloc(ctx, (size_t)R)) < 0) return fail(rc);
-    if ((rc = h2d(ctx, area_d.p, r->area.data(), (size_t)R * 8)) < 0) return fail(rc);
-    if ((rc = order_desc(ctx, area_d.p, R, order_d.p, sorted_d.p)) < 0) return fail(rc);
-    r->order.resize((size_t)R);
-    if ((rc = d2h(ctx, r->order.data(), order_d.p, (size_t)R * 4)) < 0) return fail(rc);
-    r->pvalues.assign((size_t)R, nan(""));
+    if ((rc = order_desc(ctx, r->d_area.p, R, order_d.p, sorted_d.p)) < 0) return fail(rc);
+    const int32_t* h_order = d2h_async_pinned(ctx, order_d.p, (size_t)R);
+    const double* h_p = nullptr;
     if (nl->count > 0) {  // no nulls at all -> NA (:408-419)
         if ((rc = calc_pval_device(ctx, sorted_d.p, R, nl->area.p, nl->count, 2, p_d.p)) < 0) return fail(rc);
-        if ((rc = d2h(ctx, r->pvalues.data(), p_d.p, (size_t)R * 8)) < 0) return fail(rc);
+        h_p = d2h_async_pinned(ctx, p_d.p, (size_t)R);
     }
+    if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || !h_order || (nl->count > 0 && !h_p)) {
+        set_error("dfb_calculate_pvalues: read-back failed");
+        return fail(DFB_ECUDA);
+    }
+    r->order.assign(h_order, h_order + R);
+    if (h_p) r->pvalues.assign(h_p, h_p + R);
+    else r->pvalues.assign((size_t)R, nan(""));
     if (pvalues) memcpy(pvalues, r->pvalues.data(), (size_t)R * 8);
     *regions = r;
     *nulls = nl;

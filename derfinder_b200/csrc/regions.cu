@@ -176,82 +176,97 @@ struct EmitParams {
     int32_t* perm;  // 1-based permutation id = row / sides + 1
 };
 
-template <bool COMPACT>
-__global__ void __launch_bounds__(128) emit_regions_kernel(const EmitParams P) {
-    const int64_t total = P.rows * P.W;
+// position (global word index << 5 | bit) of every region start, in (row, index) order
+__global__ void __launch_bounds__(256) fill_starts_kernel(const uint32_t* __restrict__ mask,
+                                                          const uint32_t* __restrict__ seg,
+                                                          const int64_t* __restrict__ offsets, int64_t rows, int64_t W,
+                                                          int64_t* __restrict__ start_pos) {
+    const int64_t total = rows * W;
     for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
          g += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t m = P.mask[g];
+        const uint32_t m = mask[g];
         if (!m) continue;
-        const int64_t row = g / P.W, w = g - row * P.W;
-        const uint32_t prev = w > 0 ? (P.mask[g - 1] >> 31) : 0u;
-        const uint32_t sg = P.seg[w];
-        uint32_t starts = region_starts(m, prev, sg);
-        if (!starts) continue;
-        const uint32_t* mrow = P.mask + row * P.W;
-        int64_t out = P.offsets[g];
-        const int wpt_shift = COMPACT ? (31 - __clz(P.tile_bases >> 5)) : 0;  // log2(words per value tile)
+        const int64_t w = g % W;
+        const uint32_t prev = w > 0 ? (mask[g - 1] >> 31) : 0u;
+        uint32_t starts = region_starts(m, prev, seg[w]);
+        int64_t out = offsets[g];
         while (starts) {
             const int b = __ffs(starts) - 1;
             starts &= starts - 1;
-            const int64_t i = w * 32 + b;
-            // first value of the region
-            int64_t ptr = 0;
-            const double* src;
-            if (COMPACT) {
-                const int64_t t = w >> wpt_shift;
-                ptr = P.off[row * P.tiles + t];
-                for (int64_t ww = t << wpt_shift; ww < w; ++ww) ptr += __popc(mrow[ww]);
-                ptr += __popc(m & ((1u << b) - 1u));
-                src = P.vals + ptr;
-            } else {
-                src = P.dense + row * P.dense_stride + i;
-            }
-            // The region is walked word by word: inside a word its extent is the run of bits that
-            // pass and do not open a new segment (bit tricks, no per-base tests); values of
-            // consecutive passing bases are consecutive in memory until a value-tile boundary.
-            double cur = src[0];
-            double runlen = 1.0;
-            double acc = 0.0;
-            int64_t cw = w;
-            int64_t j = i + 1;  // one past the last base taken so far
-            // bases of word cw that may continue the region: bits above b, passing, not a segment start
-            uint32_t cont = (b < 31) ? ((m & ~sg) >> (b + 1)) : 0u;
-            int avail = 31 - b;  // bits of `cont` that are real
-            const double* vp = src + 1;
-            for (;;) {
-                int take = __ffs(~cont) - 1;  // trailing ones (cont has zeros above `avail`)
-                if (take < 0 || take > avail) take = avail;
-                for (int t2 = 0; t2 < take; ++t2) {
-                    const double v = vp[t2];
-                    if (v == cur) {
-                        runlen += 1.0;
-                    } else {
-                        acc = __dadd_rn(acc, __dmul_rn(cur, runlen));
-                        cur = v;
-                        runlen = 1.0;
-                    }
-                }
-                j += take;
-                vp += take;
-                if (take < avail || j >= P.N) break;  // the run ended inside this word
-                ++cw;
-                const uint32_t nm = mrow[cw], ns = P.seg[cw];
-                cont = nm & ~ns;
-                avail = 32;
-                if (COMPACT && (cw & ((1 << wpt_shift) - 1)) == 0) vp = P.vals + P.off[row * P.tiles + (cw >> wpt_shift)];
-            }
-            acc = __dadd_rn(acc, __dmul_rn(cur, runlen));
-            const int32_t wd = (int32_t)(j - i);
-            if (P.area) P.area[out] = fabs(acc);
-            if (P.stat) P.stat[out] = __ddiv_rn(acc, (double)wd);
-            if (P.width) P.width[out] = wd;
-            if (P.istart) P.istart[out] = (int32_t)(i + 1);
-            if (P.iend) P.iend[out] = (int32_t)j;
-            if (P.perm) P.perm[out] = (int32_t)(row / P.sides) + 1;
-            ++out;
+            start_pos[out++] = (g << 5) | (int64_t)b;
         }
     }
+}
+
+// One thread per region: all lanes of a warp walk regions of similar length that are adjacent in
+// memory (the word-parallel predecessor left most lanes idle while one walked).
+template <bool COMPACT>
+__global__ void __launch_bounds__(128) walk_regions_kernel(const EmitParams P, const int64_t* __restrict__ start_pos,
+                                                           int64_t total) {
+    const int64_t out = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (out >= total) return;
+    const int64_t sp = start_pos[out];
+    const int64_t g = sp >> 5;
+    const int b = (int)(sp & 31);
+    const int64_t row = g / P.W, w = g - row * P.W;
+    const uint32_t m = P.mask[g];
+    const uint32_t sg = P.seg[w];
+    const uint32_t* mrow = P.mask + row * P.W;
+    const int wpt_shift = COMPACT ? (31 - __clz(P.tile_bases >> 5)) : 0;  // log2(words per value tile)
+    const int64_t i = w * 32 + b;
+    // first value of the region
+    const double* src;
+    if (COMPACT) {
+        const int64_t t = w >> wpt_shift;
+        int64_t ptr = P.off[row * P.tiles + t];
+        for (int64_t ww = t << wpt_shift; ww < w; ++ww) ptr += __popc(mrow[ww]);
+        ptr += __popc(m & ((1u << b) - 1u));
+        src = P.vals + ptr;
+    } else {
+        src = P.dense + row * P.dense_stride + i;
+    }
+    // The region is walked word by word: inside a word its extent is the run of bits that pass and do
+    // not open a new segment (bit tricks, no per-base tests); values of consecutive passing bases are
+    // consecutive in memory until a value-tile boundary.  Sum in IRanges' order: a run of k equal
+    // adjacent values contributes value*k as ONE product.
+    double cur = src[0];
+    double runlen = 1.0;
+    double acc = 0.0;
+    int64_t cw = w;
+    int64_t j = i + 1;  // one past the last base taken so far
+    uint32_t cont = (b < 31) ? ((m & ~sg) >> (b + 1)) : 0u;  // bits above b: passing, not a segment start
+    int avail = 31 - b;                                      // bits of `cont` that are real
+    const double* vp = src + 1;
+    for (;;) {
+        int take = __ffs(~cont) - 1;  // trailing ones (cont has zeros above `avail`)
+        if (take < 0 || take > avail) take = avail;
+        for (int t2 = 0; t2 < take; ++t2) {
+            const double v = vp[t2];
+            if (v == cur) {
+                runlen += 1.0;
+            } else {
+                acc = __dadd_rn(acc, __dmul_rn(cur, runlen));
+                cur = v;
+                runlen = 1.0;
+            }
+        }
+        j += take;
+        vp += take;
+        if (take < avail || j >= P.N) break;  // the run ended inside this word
+        ++cw;
+        const uint32_t nm = mrow[cw], ns = P.seg[cw];
+        cont = nm & ~ns;
+        avail = 32;
+        if (COMPACT && (cw & ((1 << wpt_shift) - 1)) == 0) vp = P.vals + P.off[row * P.tiles + (cw >> wpt_shift)];
+    }
+    acc = __dadd_rn(acc, __dmul_rn(cur, runlen));
+    const int32_t wd = (int32_t)(j - i);
+    if (P.area) P.area[out] = fabs(acc);
+    if (P.stat) P.stat[out] = __ddiv_rn(acc, (double)wd);
+    if (P.width) P.width[out] = wd;
+    if (P.istart) P.istart[out] = (int32_t)(i + 1);
+    if (P.iend) P.iend[out] = (int32_t)j;
+    if (P.perm) P.perm[out] = (int32_t)(row / P.sides) + 1;
 }
 
 int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const uint32_t* mask, const uint32_t* seg,
@@ -273,11 +288,18 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
                                                                                                counts.p);
     }
     DFB_TRY(exclusive_scan_u32(ctx, counts.p, offsets.p, total_words, total_dev.p, DFB_K_REGIONS));
-    // per-row counts: offsets at the row starts (strided gather) + total
-    std::vector<int64_t> row_off((size_t)rows + 1);
-    DFB_CUDA(cudaMemcpy2DAsync(row_off.data(), sizeof(int64_t), offsets.p, (size_t)W * sizeof(int64_t),
-                               sizeof(int64_t), (size_t)rows, cudaMemcpyDeviceToHost, ctx->stream));
-    DFB_TRY(d2h(ctx, &row_off[(size_t)rows], total_dev.p, sizeof(int64_t)));
+    // per-row counts: offsets at the row starts (strided gather) + total, read back through pinned
+    // memory with one synchronisation (which also publishes a deferred K2 cursor, if any)
+    int64_t* row_off = (int64_t*)arena_alloc(ctx, ((size_t)rows + 1) * sizeof(int64_t));
+    DFB_REQUIRE(row_off != nullptr, "pinned arena allocation failed");
+    DFB_CUDA(cudaMemcpy2DAsync(row_off, sizeof(int64_t), offsets.p, (size_t)W * sizeof(int64_t), sizeof(int64_t),
+                               (size_t)rows, cudaMemcpyDeviceToHost, ctx->stream));
+    DFB_CUDA(cudaMemcpyAsync(row_off + rows, total_dev.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (compact && compact->used_host && *compact->used_host > compact->capacity) {
+        out->total = -1;  // exceedance values overflowed: the caller re-runs K2 with the exact capacity
+        return DFB_OK;
+    }
     for (int64_t r = 0; r < rows; ++r) out->row_counts[(size_t)r] = row_off[(size_t)r + 1] - row_off[(size_t)r];
     out->total = row_off[(size_t)rows];
     if (out->total == 0) return DFB_OK;
@@ -313,11 +335,18 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
     P.istart = out->istart.p;
     P.iend = out->iend.p;
     P.perm = out->perm.p;
+    DevBuf<int64_t> start_pos;
+    DFB_TRY(start_pos.alloc(ctx, (size_t)out->total));
     {
         KTimer t(ctx, DFB_K_REGIONS);
-        const int grid = grid_for(total_words, 128, ctx->sm_count, 64);
-        if (compact) emit_regions_kernel<true><<<grid, 128, 0, ctx->stream>>>(P);
-        else emit_regions_kernel<false><<<grid, 128, 0, ctx->stream>>>(P);
+        fill_starts_kernel<<<grid_for(total_words, 256, ctx->sm_count), 256, 0, ctx->stream>>>(mask, seg, offsets.p, rows,
+                                                                                              W, start_pos.p);
+    }
+    {
+        KTimer t(ctx, DFB_K_REGIONS);
+        const unsigned grid = (unsigned)ceil_div(out->total, 128);
+        if (compact) walk_regions_kernel<true><<<grid, 128, 0, ctx->stream>>>(P, start_pos.p, out->total);
+        else walk_regions_kernel<false><<<grid, 128, 0, ctx->stream>>>(P, start_pos.p, out->total);
     }
     DFB_CUDA(cudaGetLastError());
     return DFB_OK;
@@ -513,17 +542,17 @@ int find_regions_dense(dfb_ctx* ctx, const double* x_dev, const PositionIndex& p
     r->R_up = rs.row_counts[0];
     r->basic = basic;
     const size_t R = (size_t)rs.total;
-    r->value.resize(R);
-    r->area.resize(R);
-    r->index_start.resize(R);
-    r->index_end.resize(R);
     DevBuf<int32_t> gs, ge, cf;
     DevBuf<double> cl;
     if (!basic) {
-        DFB_TRY(gs.alloc(ctx, R));
-        DFB_TRY(ge.alloc(ctx, R));
-        DFB_TRY(cf.alloc(ctx, R));
-        DFB_TRY(cl.alloc(ctx, R));
+        int rc0 = gs.alloc(ctx, R);
+        if (rc0 >= 0) rc0 = ge.alloc(ctx, R);
+        if (rc0 >= 0) rc0 = cf.alloc(ctx, R);
+        if (rc0 >= 0) rc0 = cl.alloc(ctx, R);
+        if (rc0 < 0) {
+            delete r;
+            return rc0;
+        }
         {
             KTimer t(ctx, DFB_K_REGIONS);
             genomic_map_kernel<<<(unsigned)ceil_div((int64_t)R, 256), 256, 0, ctx->stream>>>(
@@ -539,26 +568,37 @@ int find_regions_dense(dfb_ctx* ctx, const double* x_dev, const PositionIndex& p
             delete r;
             return rc2;
         }
-        r->start.resize(R);
-        r->end.resize(R);
-        r->cluster.resize(R);
-        r->cluster_l.resize(R);
-        cudaMemcpyAsync(r->start.data(), gs.p, R * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
-        cudaMemcpyAsync(r->end.data(), ge.p, R * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
-        cudaMemcpyAsync(r->cluster.data(), cf.p, R * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
-        cudaMemcpyAsync(r->cluster_l.data(), cl.p, R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
     }
-    std::vector<int32_t> width(R);
-    cudaMemcpyAsync(r->value.data(), rs.stat.p, R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-    cudaMemcpyAsync(r->area.data(), rs.area.p, R * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream);
-    cudaMemcpyAsync(r->index_start.data(), rs.istart.p, R * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
-    cudaMemcpyAsync(r->index_end.data(), rs.iend.p, R * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream);
+    // results travel through pinned memory: all copies are asynchronous, one synchronisation
+    const int32_t *h_gs = nullptr, *h_ge = nullptr, *h_cf = nullptr;
+    const double* h_cl = nullptr;
+    if (!basic) {
+        h_gs = d2h_async_pinned(ctx, gs.p, R);
+        h_ge = d2h_async_pinned(ctx, ge.p, R);
+        h_cf = d2h_async_pinned(ctx, cf.p, R);
+        h_cl = d2h_async_pinned(ctx, cl.p, R);
+    }
+    const double* h_val = d2h_async_pinned(ctx, rs.stat.p, R);
+    const double* h_area = d2h_async_pinned(ctx, rs.area.p, R);
+    const int32_t* h_is = d2h_async_pinned(ctx, rs.istart.p, R);
+    const int32_t* h_ie = d2h_async_pinned(ctx, rs.iend.p, R);
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) {
-        set_error("find_regions: %s", cudaGetErrorString(e));
+    if (e != cudaSuccess || !h_val || !h_area || !h_is || !h_ie || (!basic && (!h_gs || !h_ge || !h_cf || !h_cl))) {
+        set_error("find_regions: %s", e != cudaSuccess ? cudaGetErrorString(e) : "pinned read-back failed");
         delete r;
         return DFB_ECUDA;
     }
+    r->value.assign(h_val, h_val + R);
+    r->area.assign(h_area, h_area + R);
+    r->index_start.assign(h_is, h_is + R);
+    r->index_end.assign(h_ie, h_ie + R);
+    if (!basic) {
+        r->start.assign(h_gs, h_gs + R);
+        r->end.assign(h_ge, h_ge + R);
+        r->cluster.assign(h_cf, h_cf + R);
+        r->cluster_l.assign(h_cl, h_cl + R);
+    }
+    r->d_area = std::move(rs.area);
     r->d_is = std::move(rs.istart);
     r->d_ie = std::move(rs.iend);
     *out = r;
@@ -575,6 +615,7 @@ int dfb_find_regions(dfb_ctx* ctx, const dfb_cov* cov, const double* x, double c
                      int32_t max_region_gap, int32_t max_cluster_gap, int basic, dfb_regions** out) {
     DFB_REQUIRE(ctx && cov && out, "dfb_find_regions: NULL argument");
     DFB_REQUIRE(cutoff_lo <= cutoff_hi, "cutoff pair must be sorted (L <= U)");
+    arena_reset(ctx);
     *out = nullptr;
     const double* xd = nullptr;
     DevBuf<double> tmp;
@@ -600,6 +641,7 @@ int dfb_find_regions_pos(dfb_ctx* ctx, const double* x, int64_t N, const int32_t
                          int32_t max_cluster_gap, int basic, dfb_regions** out) {
     DFB_REQUIRE(ctx && x && pos_len && out, "dfb_find_regions_pos: NULL argument");
     DFB_REQUIRE(cutoff_lo <= cutoff_hi, "cutoff pair must be sorted (L <= U)");
+    arena_reset(ctx);
     *out = nullptr;
     PositionIndex pos;
     DFB_TRY(pos.build(ctx, pos_len, pos_nruns, pos_first));

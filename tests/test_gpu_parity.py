@@ -574,3 +574,21 @@ def test_fused_off_equals_on(dfb, eng):
         assert_pipeline_equal(res_off, ores)
     finally:
         e2.close()
+
+
+def test_preprocess_beyond_context_table(dfb, eng):
+    """Integer coverage beyond the context's 64 Ki-entry log2 table takes the data-sized table path;
+    values must still be bit-identical to libm log2(x + scalefac)."""
+    rng = np.random.default_rng(5)
+    N, n = 3000, 6
+    cov = rng.integers(0, 50, size=(N, n)).astype(np.int32)
+    cov[17, 2] = 70000
+    cov[2999, 5] = 3_000_000
+    position = (np.array([True]), np.array([N]))
+    prep = dfb.preprocessCoverage(dict(coverage=cov, position=position), engine=eng)
+    oprep = O.preprocess_coverage(cov, position)
+    assert np.array_equal(prep["coverageProcessed"].processed(), oprep["coverageProcessed"])
+    # and a following ordinary call still uses the context table
+    cov2 = rng.integers(0, 50, size=(N, n)).astype(np.int32)
+    prep2 = dfb.preprocessCoverage(dict(coverage=cov2, position=position), engine=eng)
+    assert np.array_equal(prep2["coverageProcessed"].processed(), O.preprocess_coverage(cov2, position)["coverageProcessed"])
