@@ -65,6 +65,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity), "r"(0x989680u)  // suspend-time hint: the warp sleeps in hardware instead of spinning
         : "memory");
 }
+// wait used by the single MMA-issuing lane: it is idle most of the time (the epilogue is the long
+// pole), so it backs off with nanosleep instead of competing for issue slots
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+    for (;;) {
+        uint32_t done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (done) return;
+        __nanosleep(128);
+    }
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -844,18 +862,20 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
             if (lane == 0) {
                 const uint32_t a_addr = smem_u32(As), b_addr = smem_u32(Bs);
                 const unsigned char* src = P.qb;
-                mbar_wait(a_ready, tphase);
-                tc_fence_after();
                 for (int64_t c = 0; c < G.chunks; ++c) {
                     const int64_t i0 = it + c;
                     const int s = (int)(i0 & 1);
                     const uint32_t ph = (uint32_t)((i0 >> 1) & 1);
                     const uint32_t bph = (uint32_t)(i0 & 1);
-                    mbar_wait(empty_b, bph ^ 1);  // MMAs of the previous chunk have read the B stage
+                    mbar_wait_relaxed(empty_b, bph ^ 1);  // MMAs of the previous chunk have read the B stage
                     mbar_expect_tx(full_b, G.b_bytes);
                     bulk_g2s(b_addr, src + (size_t)c * G.b_bytes, G.b_bytes, full_b);
-                    mbar_wait(full_b, bph);
-                    mbar_wait(tmem_empty + 8 * s, ph ^ 1);
+                    if (c == 0) {  // the B tile of chunk 0 is in flight while the A tile is still being built
+                        mbar_wait_relaxed(a_ready, tphase);
+                        tc_fence_after();
+                    }
+                    mbar_wait_relaxed(full_b, bph);
+                    mbar_wait_relaxed(tmem_empty + 8 * s, ph ^ 1);
                     tc_fence_after();
                     const uint32_t d_addr = tmem_base + (uint32_t)(s * G.nmma);
                     const uint32_t bs_addr = b_addr;
@@ -897,18 +917,32 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
                 for (int g = 0; g * per16 < nq; g += 2) {
                     float v[32];
                     tmem_ld32(taddr + (uint32_t)(g * 16), v);
-                    const bool full = (g + 2) * per16 <= nq;  // warp-uniform: no padded permutation in this load
+                    const uint16_t ent0 = (uint16_t)(((g * per16) << 5) | lane);
+                    if ((g + 2) * per16 <= nq) {  // warp-uniform: no padded permutation in this load
 #pragma unroll
-                    for (int qq = 0; qq < 2 * per16; ++qq) {
-                        float a = v[qq * PST] * v[qq * PST];
+                        for (int qq = 0; qq < 2 * per16; ++qq) {
+                            float a = v[qq * PST] * v[qq * PST];
 #pragma unroll
-                        for (int j = 1; j < PCOLS; ++j) a = fmaf(v[qq * PST + j], v[qq * PST + j], a);
-                        const int qi = g * per16 + qq;
-                        const bool cand = (a >= thr) && (full || qi < nq);
-                        const unsigned word = __ballot_sync(0xffffffffu, cand);
-                        if (word) {
-                            if (cand) list_w[nwork + __popc(word & lt_mask)] = (uint16_t)((qi << 5) | lane);
-                            nwork += __popc(word);
+                            for (int j = 1; j < PCOLS; ++j) a = fmaf(v[qq * PST + j], v[qq * PST + j], a);
+                            const bool cand = a >= thr;
+                            const unsigned word = __ballot_sync(0xffffffffu, cand);
+                            if (word) {
+                                if (cand) list_w[nwork + __popc(word & lt_mask)] = (uint16_t)(ent0 + (qq << 5));
+                                nwork += __popc(word);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int qq = 0; qq < 2 * per16; ++qq) {
+                            float a = v[qq * PST] * v[qq * PST];
+#pragma unroll
+                            for (int j = 1; j < PCOLS; ++j) a = fmaf(v[qq * PST + j], v[qq * PST + j], a);
+                            const bool cand = (a >= thr) && (g * per16 + qq < nq);
+                            const unsigned word = __ballot_sync(0xffffffffu, cand);
+                            if (word) {
+                                if (cand) list_w[nwork + __popc(word & lt_mask)] = (uint16_t)(ent0 + (qq << 5));
+                                nwork += __popc(word);
+                            }
                         }
                     }
                 }
