@@ -67,7 +67,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
 }
 // wait used by the single MMA-issuing lane: it is idle most of the time (the epilogue is the long
 // pole), so it backs off with nanosleep instead of competing for issue slots
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity) {
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns = 1000) {
     for (;;) {
         uint32_t done;
         asm volatile(
@@ -80,7 +80,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
             : "r"(bar), "r"(parity)
             : "memory");
         if (done) return;
-        __nanosleep(128);
+        __nanosleep(ns);
     }
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
