@@ -43,6 +43,8 @@ WORKLOADS = {
                label="synthetic chr21 (48.1 Mbp, N=4.8M kept bases) 12 samples, 2-group model, 100 permutations"),
     "c3": dict(chr_len=249_250_621, N=25_000_000, n=60, extra=3, B=1000, alpha=1e-6,
                label="synthetic chr1 (249 Mbp, N=25M kept bases) 60 samples, 3 adjustment covariates, 1000 permutations"),
+    "c3s": dict(chr_len=24_925_062, N=2_500_000, n=60, extra=3, B=1000, alpha=1e-6,
+                label="1/10 of synthetic chr1 (N=2.5M kept bases) 60 samples, 3 adjustment covariates, 1000 permutations"),
     "tiny": dict(chr_len=2_000_000, N=200_000, n=12, extra=0, B=20, alpha=0.05,
                  label="tiny debug workload"),
 }
@@ -389,6 +391,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-input", default="rle", choices=["rle", "dense"],
                     help="host coverage format of the end-to-end pass: Rle columns (the reference's type) or dense")
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=value (developer knob)")
     ap.add_argument("--screen", type=int, default=None, help="override the engine's tcgen05 screening option")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
@@ -423,6 +426,9 @@ def main():
     eng = dfb.Engine(local, stream=torch.cuda.current_stream().cuda_stream)
     if args.screen is not None:
         eng.set_option("screen", args.screen)
+    for kv in args.opt:
+        key, val = kv.split("=")
+        eng.set_option(key, float(val))
     step = Step(eng, work, perm, cut, torch)
 
     def one_step():

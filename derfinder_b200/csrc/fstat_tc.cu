@@ -65,24 +65,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity), "r"(0x989680u)  // suspend-time hint: the warp sleeps in hardware instead of spinning
         : "memory");
 }
-// wait used by the single MMA-issuing lane: it is idle most of the time (the epilogue is the long
-// pole), so it backs off with nanosleep instead of competing for issue slots
-__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity, unsigned ns = 1000) {
-    for (;;) {
-        uint32_t done;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (done) return;
-        __nanosleep(ns);
-    }
-}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -640,6 +622,7 @@ struct FusedGeom {
     int p, p0, j0, pe, pst;  // model columns, first column used by the screen, columns screened, TMEM stride
     int ps, nmma;       // permutations per chunk, MMA N = ps * pst
     int qs, ixs;        // Qs row stride (doubles), bytes per row of the byte permutation table
+    int nb;             // B tile stages: 1 when the tile is small (occupancy first), else 2
     int64_t B, chunks;
     int64_t tiles;
     uint32_t a_bytes, b_bytes;
@@ -743,9 +726,10 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
     double* Qs = reinterpret_cast<double*>(sm + G.off_qs);  // [n][qs]
     double* yy_s = reinterpret_cast<double*>(sm + G.off_yy);  // [128]
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + G.off_bar);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-    const uint32_t full_b = smem_u32(bars + 0), empty_b = smem_u32(bars + 1), a_ready = smem_u32(bars + 2);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+    const uint32_t full_b = smem_u32(bars + 0), empty_b = smem_u32(bars + 2), a_ready = smem_u32(bars + 8);
     const uint32_t tmem_full = smem_u32(bars + 4), tmem_empty = smem_u32(bars + 6);
+    const int NB = G.nb;  // B stages (1 or 2)
     // per-warp scratch (epilogue warps only)
     unsigned char* wbase = sm + G.off_warp + (size_t)(warp & 3) * G.warp_bytes;
     uint16_t* list_w = reinterpret_cast<uint16_t*>(wbase);        // [1024] (perm << 5) | base
@@ -754,10 +738,10 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
 
     if (warp == 4) {
         if (lane == 0) {
-            mbar_init(full_b, 1);
-            mbar_init(empty_b, 1);
             mbar_init(a_ready, 4);
             for (int s = 0; s < 2; ++s) {
+                mbar_init(full_b + 8 * s, 1);
+                mbar_init(empty_b + 8 * s, 1);
                 mbar_init(tmem_full + 8 * s, 1);
                 mbar_init(tmem_empty + 8 * s, 4);
             }
@@ -781,6 +765,12 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
     const bool num_is_sd = P.dfnum == 1.0;
     int64_t it = 0;  // chunks issued / consumed so far (TMEM stage = it & 1, phase = (it >> 1) & 1)
     uint32_t tphase = 0;  // parity of the A-tile barrier (one phase per tile)
+    // B tiles: NB stages; with two, the load of the next chunk (running over into this CTA's next tile --
+    // the B operand does not depend on the tile) overlaps the MMAs of the current one.  `loaded` counts
+    // the bulk copies issued by this CTA.
+    const int64_t my_tiles = blockIdx.x < G.tiles ? (G.tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    const int64_t total_chunks = my_tiles * G.chunks;
+    int64_t loaded = 0;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     for (int64_t tile = blockIdx.x; tile < G.tiles; tile += gridDim.x) {
@@ -866,19 +856,25 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
                     const int64_t i0 = it + c;
                     const int s = (int)(i0 & 1);
                     const uint32_t ph = (uint32_t)((i0 >> 1) & 1);
-                    const uint32_t bph = (uint32_t)(i0 & 1);
-                    mbar_wait_relaxed(empty_b, bph ^ 1);  // MMAs of the previous chunk have read the B stage
-                    mbar_expect_tx(full_b, G.b_bytes);
-                    bulk_g2s(b_addr, src + (size_t)c * G.b_bytes, G.b_bytes, full_b);
+                    while (loaded < total_chunks && loaded < i0 + NB) {
+                        const int sb1 = (int)(loaded % NB);
+                        const int64_t use = loaded / NB;
+                        if (use > 0) mbar_wait(empty_b + 8 * sb1, (uint32_t)((use - 1) & 1));  // earlier MMAs on this stage done
+                        mbar_expect_tx(full_b + 8 * sb1, G.b_bytes);
+                        bulk_g2s(b_addr + sb1 * G.b_bytes, src + (size_t)(loaded % G.chunks) * G.b_bytes, G.b_bytes,
+                                 full_b + 8 * sb1);
+                        ++loaded;
+                    }
+                    const int sb = (int)(i0 % NB);
                     if (c == 0) {  // the B tile of chunk 0 is in flight while the A tile is still being built
-                        mbar_wait_relaxed(a_ready, tphase);
+                        mbar_wait(a_ready, tphase);
                         tc_fence_after();
                     }
-                    mbar_wait_relaxed(full_b, bph);
-                    mbar_wait_relaxed(tmem_empty + 8 * s, ph ^ 1);
+                    mbar_wait(full_b + 8 * sb, (uint32_t)((i0 / NB) & 1));
+                    mbar_wait(tmem_empty + 8 * s, ph ^ 1);
                     tc_fence_after();
                     const uint32_t d_addr = tmem_base + (uint32_t)(s * G.nmma);
-                    const uint32_t bs_addr = b_addr;
+                    const uint32_t bs_addr = b_addr + sb * G.b_bytes;
                     uint32_t accum = 0u;
                     for (int t = 0; t < G.nk16; ++t) {
 #pragma unroll
@@ -891,7 +887,7 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
                             accum = 1u;
                         }
                     }
-                    umma_commit(empty_b);            // B stage reusable once these MMAs have read it
+                    umma_commit(empty_b + 8 * sb);   // B stage reusable once these MMAs have read it
                     umma_commit(tmem_full + 8 * s);  // accumulator ready for the epilogue
                 }
             }
@@ -1321,7 +1317,8 @@ static bool fused_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
     G.b_bytes = (uint32_t)G.KB * (uint32_t)G.nmma * 128u;
     uint32_t o = G.a_bytes;
     G.off_b = o;
-    o += G.b_bytes;
+    G.nb = G.b_bytes > 16 * 1024 ? 2 : 1;
+    o += (uint32_t)G.nb * G.b_bytes;
     G.off_ys = o;
     o += (uint32_t)G.n * TC_M * 8u;
     G.off_qs = o;
@@ -1329,7 +1326,7 @@ static bool fused_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
     G.off_yy = o;
     o += TC_M * 8u;
     G.off_bar = o;
-    o += 8 * 8 + 16;
+    o += 10 * 8 + 16;
     o = (uint32_t)round_up(o, 16);
     G.off_warp = o;
     G.warp_bytes = (uint32_t)(1024 * 2 + 32 * 4 + 32 * G.ixs);
