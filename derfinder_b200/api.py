@@ -44,6 +44,7 @@ class Engine:
         lib = L.load()
         h = C.c_void_p()
         L.check(lib.dfb_create(int(device), C.c_void_p(stream) if stream else None, C.byref(h)))
+        self.stream_handle = int(stream) if stream else None  # None: the library owns a private stream
         self.lib, self.h, self.device = lib, h, device
         self._covs = weakref.WeakSet()  # live Coverage handles: released before the context goes
 

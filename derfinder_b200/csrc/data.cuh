@@ -60,6 +60,7 @@ struct dfb_nulls {
     int64_t B = 0;
     int64_t count = 0;
     dfb::DevBuf<double> area, stat;  // [count]
+    dfb::DevBuf<double> area_sorted; // [count] ascending (kept from the p-value ranking; pooled across GPUs)
     dfb::DevBuf<int32_t> width, perm;  // [count], perm ids 1-based
     std::vector<int64_t> per_perm;   // [B]
 };

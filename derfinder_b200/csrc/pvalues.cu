@@ -200,10 +200,27 @@ static int sort_doubles(dfb_ctx* ctx, const double* in, double* out, int64_t n) 
     return DFB_OK;
 }
 
+// number of sorted nulls strictly greater than each area, ADDED to counts (multi-GPU pooling: one
+// call per rank's sorted null list)
+__global__ void count_greater_kernel(const double* __restrict__ areas, int64_t R, const double* __restrict__ sorted_nulls,
+                                     int64_t M, int64_t* __restrict__ counts) {
+    int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const double a = areas[r];
+    int64_t lo = 0, hi = M;
+    while (lo < hi) {
+        const int64_t mid = (lo + hi) >> 1;
+        if (sorted_nulls[mid] <= a) lo = mid + 1;
+        else hi = mid;
+    }
+    counts[r] += M - lo;
+}
+
 int calc_pval_device(dfb_ctx* ctx, const double* areas_dev, int64_t R, const double* nulls_dev, int64_t M, int weight,
-                     double* p_dev) {
+                     double* p_dev, DevBuf<double>* keep_sorted = nullptr) {
     if (R == 0) return DFB_OK;
-    DevBuf<double> sorted;
+    DevBuf<double> sorted_local;
+    DevBuf<double>& sorted = keep_sorted ? *keep_sorted : sorted_local;
     DFB_TRY(sorted.alloc(ctx, (size_t)std::max<int64_t>(M, 1)));
     if (M > 0) DFB_TRY(sort_doubles(ctx, nulls_dev, sorted.p, M));
     {
@@ -220,12 +237,37 @@ int calc_pval_device(dfb_ctx* ctx, const double* areas_dev, int64_t R, const dou
 
 __global__ void perm_max_kernel(const double* __restrict__ area, const int32_t* __restrict__ perm, int64_t M,
                                 int64_t B, unsigned long long* __restrict__ bits) {
-    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M) return;
-    const int64_t b = (int64_t)perm[i] - 1;
-    if (b < 0 || b >= B) return;
-    const double a = fabs(area[i]);
-    atomicMax(&bits[b], (unsigned long long)__double_as_longlong(a) + 1ull);  // 0 = no region
+    // permutation ids arrive sorted, so a warp usually sees ONE id: reduce in the warp, one atomic
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int64_t b = -1;
+    unsigned long long key = 0ull;  // 0 = no region
+    if (i < M) {
+        b = (int64_t)perm[i] - 1;
+        if (b >= 0 && b < B) key = (unsigned long long)__double_as_longlong(fabs(area[i])) + 1ull;
+        else b = -1;
+    }
+    const int64_t b0 = __shfl_sync(0xffffffffu, b, 0);
+    if (__all_sync(0xffffffffu, b == b0 || b < 0)) {
+        unsigned long long m = key;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const unsigned long long t = __shfl_xor_sync(0xffffffffu, m, o);
+            m = t > m ? t : m;
+        }
+        // lane 0 may be out of range (b0 < 0) while others are valid: take any valid id
+        const unsigned valid = __ballot_sync(0xffffffffu, b >= 0);
+        if (valid) {
+            const int64_t bb = __shfl_sync(0xffffffffu, b, __ffs(valid) - 1);
+            const bool uniform = __all_sync(0xffffffffu, b == bb || b < 0);
+            if (uniform) {
+                if ((threadIdx.x & 31) == 0 && m) atomicMax(&bits[bb], m);
+                return;
+            }
+        } else {
+            return;
+        }
+    }
+    if (b >= 0 && key) atomicMax(&bits[b], key);
 }
 
 __global__ void perm_max_decode_kernel(const unsigned long long* __restrict__ bits, int64_t B, double fill,
@@ -424,6 +466,43 @@ int dfb_nulls_copy_dev(const dfb_nulls* nl, double* area_dev, int32_t* perm_dev)
     return DFB_OK;
 }
 
+int dfb_nulls_sorted_areas_dev(dfb_ctx* ctx, dfb_nulls* nl, double* out_dev) {
+    DFB_REQUIRE(ctx && nl && (out_dev || nl->count == 0), "dfb_nulls_sorted_areas_dev: NULL argument");
+    const size_t M = (size_t)nl->count;
+    if (M == 0) return DFB_OK;
+    if (!nl->area_sorted.p) {  // not produced by dfb_calculate_pvalues (e.g. dfb_perm_nulls): sort now
+        DFB_TRY(nl->area_sorted.alloc(ctx, M));
+        DFB_TRY(sort_doubles(ctx, nl->area.p, nl->area_sorted.p, (int64_t)M));
+    }
+    DFB_CUDA(cudaMemcpyAsync(out_dev, nl->area_sorted.p, M * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    return DFB_OK;
+}
+
+int dfb_count_greater_dev(dfb_ctx* ctx, const double* areas_dev, int64_t R, const double* sorted_nulls_dev, int64_t M,
+                          int64_t* counts_dev) {
+    DFB_REQUIRE(ctx && (areas_dev || R == 0) && (sorted_nulls_dev || M == 0) && (counts_dev || R == 0),
+                "dfb_count_greater_dev: NULL argument");
+    if (R == 0) return DFB_OK;
+    {
+        KTimer t(ctx, DFB_K_PVAL);
+        count_greater_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, ctx->stream>>>(areas_dev, R, sorted_nulls_dev, M,
+                                                                                 counts_dev);
+    }
+    DFB_CUDA(cudaGetLastError());
+    return DFB_OK;
+}
+
+int dfb_regions_copy_areas_dev(dfb_ctx* ctx, const dfb_regions* r, double* out_dev) {
+    DFB_REQUIRE(ctx && r && (out_dev || r->R == 0), "dfb_regions_copy_areas_dev: NULL argument");
+    if (r->R == 0) return DFB_OK;
+    if (!r->d_area.p) {
+        set_error("dfb_regions_copy_areas_dev: this result holds no device copy of the areas");
+        return DFB_ESTATE;
+    }
+    DFB_CUDA(cudaMemcpyAsync(out_dev, r->d_area.p, (size_t)r->R * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    return DFB_OK;
+}
+
 int dfb_calc_pval_dev(dfb_ctx* ctx, const double* areas_dev, int64_t R, double* nullareas_dev, int64_t M, int weight,
                       double* pvalues_dev) {
     DFB_REQUIRE(ctx && (areas_dev || R == 0) && (nullareas_dev || M == 0) && (pvalues_dev || R == 0),
@@ -583,7 +662,8 @@ int dfb_calculate_pvalues(dfb_ctx* ctx, dfb_cov* cov, const double* fstats, cons
     const int32_t* h_order = d2h_async_pinned(ctx, order_d.p, (size_t)R);
     const double* h_p = nullptr;
     if (nl->count > 0) {  // no nulls at all -> NA (:408-419)
-        if ((rc = calc_pval_device(ctx, sorted_d.p, R, nl->area.p, nl->count, 2, p_d.p)) < 0) return fail(rc);
+        if ((rc = calc_pval_device(ctx, sorted_d.p, R, nl->area.p, nl->count, 2, p_d.p, &nl->area_sorted)) < 0)
+            return fail(rc);
         h_p = d2h_async_pinned(ctx, p_d.p, (size_t)R);
     }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || !h_order || (nl->count > 0 && !h_p)) {

@@ -220,6 +220,19 @@ int dfb_nulls_get(const dfb_nulls* nl, int dup, double* stat, int32_t* width, do
 /* device access for multi-GPU pooling (areas as doubles, permutation ids as int32) */
 int dfb_nulls_copy_dev(const dfb_nulls* nl, double* area_dev, int32_t* perm_dev);
 
+/* Multi-GPU pooling without a second sort (R/mergeResults.R:216-235, 304-307): every rank keeps its
+ * null areas sorted from its own p-value ranking; ranks all-gather those sorted lists and count,
+ * list by list, how many pooled nulls exceed each of their region areas:
+ *   p = (2 * sum_ranks #{null > area} + 1) / (2 * sum_ranks M + 1).
+ * dfb_nulls_sorted_areas_dev copies the ascending null areas (count doubles) to out_dev;
+ * dfb_count_greater_dev ADDS #{sorted_nulls > areas[r]} to counts_dev[r];
+ * dfb_regions_copy_areas_dev copies the region areas in up-then-dn order (before the
+ * decreasing-area reordering, see dfb_regions_get_order). */
+int dfb_nulls_sorted_areas_dev(dfb_ctx* ctx, dfb_nulls* nl, double* out_dev);
+int dfb_count_greater_dev(dfb_ctx* ctx, const double* areas_dev, int64_t R, const double* sorted_nulls_dev,
+                          int64_t M, int64_t* counts_dev);
+int dfb_regions_copy_areas_dev(dfb_ctx* ctx, const dfb_regions* r, double* out_dev);
+
 /* Validation hook for the tcgen05 screening path (used by the parity tests and profiling): runs
  * the dense FP64 scan and the screen + refinement on the same permutations with a scalar cutoff
  * and reports the exceedance counts of both, the number of screened candidates and the number of

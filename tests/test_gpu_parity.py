@@ -592,3 +592,40 @@ def test_preprocess_beyond_context_table(dfb, eng):
     cov2 = rng.integers(0, 50, size=(N, n)).astype(np.int32)
     prep2 = dfb.preprocessCoverage(dict(coverage=cov2, position=position), engine=eng)
     assert np.array_equal(prep2["coverageProcessed"].processed(), O.preprocess_coverage(cov2, position)["coverageProcessed"])
+
+
+def test_pooled_pvalues_single_rank(dfb, eng):
+    """pool.genomewide_pvalues (sorted-list pooling, no second sort) on one rank must reproduce the
+    p-values dfb_calculate_pvalues computed itself, and .calculateFWER of the oracle."""
+    import torch
+    import bench
+    from derfinder_b200 import pool
+    from derfinder_b200 import _lib as L
+    from derfinder_b200.rrng import permutation_indices
+    cfg = bench.WORKLOADS["tiny"]
+    device = torch.device("cuda", 0)
+    work = bench.make_workload(cfg, 11, torch=torch, device=device)
+    perm = permutation_indices(range(1, cfg["B"] + 1), cfg["n"], "Rejection")
+    cut = bench.theoretical_cutoff(cfg["alpha"], work["mod"], work["mod0"])
+    e2 = dfb.Engine(0, stream=torch.cuda.current_stream().cuda_stream)
+    try:
+        step = bench.Step(e2, work, perm, cut, torch)
+        (R, M), rh, nh, cov = step.device_pass(keep=True)
+        assert R > 0 and M > 0
+        p_dev, fwer, total = pool.genomewide_pvalues(e2, rh, nh, cfg["B"], cut, torch, device)
+        torch.cuda.synchronize()
+        assert total == M
+        pv, order, area = np.empty(R), np.empty(R, dtype=np.int32), np.empty(R)
+        L.check(e2.lib.dfb_regions_get_pvalues(rh, pv.ctypes.data_as(L.c_f64p)))
+        L.check(e2.lib.dfb_regions_get_order(rh, order.ctypes.data_as(L.c_i32p)))
+        L.check(e2.lib.dfb_regions_get(rh, None, None, None, area.ctypes.data_as(L.c_f64p), None, None, None, None))
+        assert np.array_equal(p_dev.cpu().numpy()[order], pv)
+        na, npm = np.empty(M), np.empty(M, dtype=np.int32)
+        L.check(e2.lib.dfb_nulls_get(nh, 0, None, None, na.ctypes.data_as(L.c_f64p), npm.ctypes.data_as(L.c_i32p)))
+        want = O.calculate_fwer(cut, na, npm, cfg["B"], area)
+        assert np.array_equal(fwer.cpu().numpy()[order], want)
+        e2.lib.dfb_regions_free(rh)
+        e2.lib.dfb_nulls_free(nh)
+        e2.lib.dfb_cov_free(cov)
+    finally:
+        e2.close()

@@ -50,8 +50,10 @@ def _worker(rank, world, port, out_dir):
         for a, p in zip(area, perm):
             if not np.isnan(a):
                 mx[p - 1] = max(mx[p - 1], a)
-        pool_t, gmax = pool.exchange_nulls(torch.as_tensor(area), torch.as_tensor(mx))
-        np.savez(os.path.join(out_dir, f"r{rank}.npz"), area=area, perm=perm, pool=pool_t.numpy(), gmax=gmax.numpy())
+        segs, gmax = pool.exchange_nulls(torch.as_tensor(area), torch.as_tensor(mx))
+        assert len(segs) == world and [int(s.numel()) for s in segs][rank] == M
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), area=area, perm=perm, pool=torch.cat(segs).numpy(),
+                 gmax=gmax.numpy())
     finally:
         dist.destroy_process_group()
 
@@ -74,10 +76,17 @@ def test_exchange_nulls_gloo(tmp_path, world):
     region_area = np.array([0.5, 4.0, 50.0])
     fwer = ((gmax[None, :] > region_area[:, None]).sum(axis=1) + 1) / (B + 1)
     np.testing.assert_array_equal(fwer, O.calculate_fwer(3.5, all_area, all_perm, B, region_area))
+    # pooled p-values from per-rank SORTED lists (no second sort) == .calcPval on the duplicated pool
+    cnt = np.zeros(len(region_area), dtype=np.int64)
+    for r in res:
+        srt = np.sort(r["area"][~np.isnan(r["area"])])
+        cnt += len(srt) - np.searchsorted(srt, region_area, side="right")
+    p = (2.0 * cnt + 1.0) / (2.0 * len(all_area) + 1.0)
+    np.testing.assert_array_equal(p, O.calc_pval(region_area, np.concatenate([all_area, all_area])))
 
 
 def test_exchange_is_identity_without_process_group():
     import torch
     a, m = torch.arange(4, dtype=torch.float64), torch.tensor([1.0, -1.0])
     p, g = pool.exchange_nulls(a, m)
-    assert p is a and g is m
+    assert len(p) == 1 and p[0] is a and g is m
