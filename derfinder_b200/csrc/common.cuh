@@ -69,9 +69,10 @@ class CopyPool {
     std::condition_variable work_cv_, done_cv_;
     const std::function<void(int)>* fn_ = nullptr;
     std::atomic<int> next_{0};
-    int nparts_ = 0, active_ = 0;
-    uint64_t generation_ = 0;
-    bool stop_ = false;
+    std::atomic<int> active_{0};
+    std::atomic<uint64_t> generation_{0};
+    int nparts_ = 0;
+    std::atomic<bool> stop_{false};
 };
 
 }  // namespace dfb

@@ -1,5 +1,7 @@
 // Context, error string, copies, device-wide scan.
 #include <emmintrin.h>
+
+#include <chrono>
 #include <stdarg.h>
 #include <stdlib.h>
 
@@ -66,28 +68,42 @@ CopyPool::~CopyPool() {
     {
         std::lock_guard<std::mutex> lk(m_);
         stop_ = true;
+        generation_.fetch_add(1, std::memory_order_release);  // wake spinners too
     }
     work_cv_.notify_all();
     for (auto& t : workers_) t.join();
 }
 
+// Workers spin for a short while after a job before they block: the chunks of one transfer arrive
+// every ~150 us, and a futex wake-up (hundreds of us on a busy VM) would cost more than the copy.
+static inline void cpu_relax() { _mm_pause(); }
+
 void CopyPool::worker() {
     uint64_t seen = 0;
     for (;;) {
-        const std::function<void(int)>* fn;
-        int nparts;
-        {
-            std::unique_lock<std::mutex> lk(m_);
-            work_cv_.wait(lk, [&] { return stop_ || generation_ != seen; });
-            if (stop_) return;
-            seen = generation_;
-            fn = fn_;
-            nparts = nparts_;
+        bool have = false;
+        const auto t0 = std::chrono::steady_clock::now();
+        for (unsigned spin = 0;; ++spin) {  // stay hot for a few ms: one pipeline step issues several transfers
+            if (generation_.load(std::memory_order_acquire) != seen) {
+                have = true;
+                break;
+            }
+            cpu_relax();
+            if ((spin & 255) == 255 &&
+                std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(6)) break;
         }
+        if (!have) {
+            std::unique_lock<std::mutex> lk(m_);
+            work_cv_.wait(lk, [&] { return stop_.load() || generation_.load(std::memory_order_acquire) != seen; });
+        }
+        if (stop_.load()) return;
+        seen = generation_.load(std::memory_order_acquire);
+        const std::function<void(int)>* fn = fn_;
+        const int nparts = nparts_;
         for (int i; (i = next_.fetch_add(1)) < nparts;) (*fn)(i);
-        {
+        if (active_.fetch_sub(1, std::memory_order_acq_rel) == 1) {
             std::lock_guard<std::mutex> lk(m_);
-            if (--active_ == 0) done_cv_.notify_all();
+            done_cv_.notify_all();
         }
     }
 }
@@ -102,13 +118,17 @@ void CopyPool::parallel_for(int nparts, const std::function<void(int)>& fn) {
         fn_ = &fn;
         nparts_ = nparts;
         next_.store(0);
-        active_ = (int)workers_.size();
-        ++generation_;
+        active_.store((int)workers_.size());
+        generation_.fetch_add(1, std::memory_order_release);
     }
     work_cv_.notify_all();
     for (int i; (i = next_.fetch_add(1)) < nparts;) fn(i);
+    for (int spin = 0; spin < 2000000; ++spin) {
+        if (active_.load(std::memory_order_acquire) == 0) return;
+        cpu_relax();
+    }
     std::unique_lock<std::mutex> lk(m_);
-    done_cv_.wait(lk, [&] { return active_ == 0; });
+    done_cv_.wait(lk, [&] { return active_.load(std::memory_order_acquire) == 0; });
 }
 
 // Large pageable host buffers (R vectors, numpy arrays) are moved through a ring of pinned staging
@@ -125,6 +145,7 @@ static int ensure_staging(dfb_ctx* ctx) {
     if (!ctx->pool) {
         unsigned hc = std::thread::hardware_concurrency();
         int nt = (int)std::min<unsigned>(8, std::max<unsigned>(1, hc / 2));
+        if (const char* e = getenv("DFB_COPY_THREADS")) nt = std::max(1, std::min(64, atoi(e)));
         ctx->pool = new CopyPool(nt);
     }
     return DFB_OK;
