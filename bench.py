@@ -45,6 +45,8 @@ WORKLOADS = {
                label="synthetic chr1 (249 Mbp, N=25M kept bases) 60 samples, 3 adjustment covariates, 1000 permutations"),
     "c3s": dict(chr_len=24_925_062, N=2_500_000, n=60, extra=3, B=1000, alpha=1e-6,
                 label="1/10 of synthetic chr1 (N=2.5M kept bases) 60 samples, 3 adjustment covariates, 1000 permutations"),
+    "c4s": dict(chr_len=10_000_000, N=1_000_000, n=100, extra=3, B=1000, alpha=1e-6,
+                label="scaled slice of the whole-genome config (N=1M kept bases) 100 samples, 3 adjustment covariates, 1000 permutations"),
     "tiny": dict(chr_len=2_000_000, N=200_000, n=12, extra=0, B=20, alpha=0.05,
                  label="tiny debug workload"),
 }

@@ -629,3 +629,105 @@ def test_pooled_pvalues_single_rank(dfb, eng):
         e2.lib.dfb_cov_free(cov)
     finally:
         e2.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# full-size properties (BASELINE.json configs[1]: N = 4.8 M kept bases, 12 samples, 100 permutations):
+# the oracle cannot run at this size in seconds, so the checks are size-independent properties
+
+
+@pytest.fixture(scope="module")
+def full_c2(dfb):
+    import torch
+    import bench
+    from derfinder_b200.rrng import permutation_indices
+    cfg = bench.WORKLOADS["c2"]
+    device = torch.device("cuda", 0)
+    work = bench.make_workload(cfg, 20140923 + 2, torch=torch, device=device)
+    perm = permutation_indices(range(1, cfg["B"] + 1), cfg["n"], "Rejection")
+    perm[3] = np.arange(cfg["n"])  # one identity relabelling: its nulls must equal the observed regions
+    cut = bench.theoretical_cutoff(cfg["alpha"], work["mod"], work["mod0"])
+    return cfg, work, perm, cut, torch, bench
+
+
+def _full_pass(dfb, full, **opts):
+    from derfinder_b200 import _lib as L
+    cfg, work, perm, cut, torch, bench = full
+    e2 = dfb.Engine(0, stream=torch.cuda.current_stream().cuda_stream)
+    for k, v in opts.items():
+        e2.set_option(k, v)
+    try:
+        step = bench.Step(e2, work, perm, cut, torch)
+        (R, M), rh, nh, cov = step.device_pass(keep=True)
+        lib = e2.lib
+        out = dict(R=R, M=M)
+        out["area"], out["value"], out["pv"] = np.empty(R), np.empty(R), np.empty(R)
+        out["is"], out["ie"], out["order"] = (np.empty(R, dtype=np.int32) for _ in range(3))
+        L.check(lib.dfb_regions_get(rh, None, None, out["value"].ctypes.data_as(L.c_f64p),
+                                    out["area"].ctypes.data_as(L.c_f64p), L.ptr(out["is"], C.c_int32),
+                                    L.ptr(out["ie"], C.c_int32), None, None))
+        L.check(lib.dfb_regions_get_pvalues(rh, out["pv"].ctypes.data_as(L.c_f64p)))
+        L.check(lib.dfb_regions_get_order(rh, L.ptr(out["order"], C.c_int32)))
+        out["nstat"], out["narea"] = np.empty(M), np.empty(M)
+        out["nw"], out["nperm"] = np.empty(M, dtype=np.int32), np.empty(M, dtype=np.int32)
+        L.check(lib.dfb_nulls_get(nh, 0, out["nstat"].ctypes.data_as(L.c_f64p), L.ptr(out["nw"], C.c_int32),
+                                  out["narea"].ctypes.data_as(L.c_f64p), L.ptr(out["nperm"], C.c_int32)))
+        dup = [np.empty(2 * M), np.empty(2 * M, dtype=np.int32), np.empty(2 * M), np.empty(2 * M, dtype=np.int32)]
+        L.check(lib.dfb_nulls_get(nh, 1, dup[0].ctypes.data_as(L.c_f64p), L.ptr(dup[1], C.c_int32),
+                                  dup[2].ctypes.data_as(L.c_f64p), L.ptr(dup[3], C.c_int32)))
+        out["dup"] = dup
+        cnt = np.empty(cfg["B"], dtype=np.int64)
+        L.check(lib.dfb_nulls_counts_per_perm(nh, cnt.ctypes.data_as(L.c_i64p)))
+        out["per_perm"] = cnt
+        lib.dfb_regions_free(rh)
+        lib.dfb_nulls_free(nh)
+        lib.dfb_cov_free(cov)
+        return out
+    finally:
+        e2.close()
+
+
+def test_full_size_properties(dfb, full_c2):
+    cfg, work, perm, cut, torch, bench = full_c2
+    a = _full_pass(dfb, full_c2)
+    R, M, B = a["R"], a["M"], cfg["B"]
+    assert R > 1000 and M > 100000
+    # regions come back ordered by decreasing area (stable), p-values non-decreasing along that order
+    assert np.all(np.diff(a["area"]) <= 0)
+    assert np.all(np.diff(a["pv"]) >= 0)
+    assert a["pv"].min() >= 1.0 / (2 * M + 1) and a["pv"].max() <= 1.0
+    # widths / index ranges are consistent, regions do not overlap, means pass the cutoff
+    w = a["ie"].astype(np.int64) - a["is"] + 1
+    assert w.min() >= 1 and a["ie"].max() <= cfg["N"]
+    o = np.argsort(a["is"])
+    assert np.all(a["is"][o][1:] > a["ie"][o][:-1])
+    assert np.all(a["value"] >= cut) and np.allclose(a["area"], a["value"] * w, rtol=1e-12)
+    # nulls: ordered by permutation, counts add up, every null region's mean reaches the cutoff
+    assert np.all(np.diff(a["nperm"]) >= 0) and a["nperm"].min() >= 1 and a["nperm"].max() <= B
+    assert np.array_equal(np.bincount(a["nperm"], minlength=B + 1)[1:], a["per_perm"]) and a["per_perm"].sum() == M
+    assert np.all(a["nstat"] >= cut) and np.allclose(a["narea"], a["nstat"] * a["nw"], rtol=1e-12)
+    # the identity relabelling (permutation 4) reproduces the observed regions bit for bit
+    sel = a["nperm"] == 4
+    inv = np.empty(R, dtype=np.int64)
+    inv[a["order"]] = np.arange(R)  # position of up-then-dn region k in the sorted output
+    assert sel.sum() == R
+    assert np.array_equal(a["narea"][sel], a["area"][inv]) and np.array_equal(a["nstat"][sel], a["value"][inv])
+    assert np.array_equal(a["nw"][sel], w[inv])
+    # the duplicated layout is [r1..rk, r1..rk] per permutation (R/calculatePvalues.R:346-354)
+    pre = np.concatenate(([0], np.cumsum(a["per_perm"])))
+    for b in (0, 3, B - 1):
+        k = a["per_perm"][b]
+        blk = a["dup"][2][2 * pre[b]: 2 * pre[b] + 2 * k]
+        assert np.array_equal(blk[:k], a["narea"][pre[b]:pre[b + 1]]) and np.array_equal(blk[k:], blk[:k])
+    assert np.array_equal(np.sort(a["dup"][2]), np.sort(np.concatenate([a["narea"], a["narea"]])))
+    # p-values against the oracle's .calcPval on the (much smaller) region list
+    assert np.array_equal(a["pv"], O.calc_pval(a["area"], a["dup"][2]))
+
+
+def test_full_size_paths_agree(dfb, full_c2):
+    """fused tcgen05 path == two-kernel screen path == dense FP64 path, bit for bit, at full size."""
+    ref = _full_pass(dfb, full_c2)
+    for opts in (dict(fused=0), dict(screen=0)):
+        b = _full_pass(dfb, full_c2, **opts)
+        for k in ("area", "value", "pv", "is", "ie", "nstat", "narea", "nw", "nperm"):
+            assert np.array_equal(ref[k], b[k]), (opts, k)
