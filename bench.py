@@ -363,7 +363,7 @@ class Step:
                 L.check(lib.dfb_regions_get_pvalues(rh, self._fp(pv)))
                 L.check(lib.dfb_regions_view_means(eng.h, rh, cov, -1, self._fp(mc)))
                 # caller-owned result vectors, reused across steps (grown when needed)
-                if getattr(self, "_null_cap", 0) < 2 * M:
+                if getattr(self, "_null_cap", -1) < 2 * M:
                     self._null_cap = int(2 * M * 1.1) + 16
                     self._nbuf = (np.empty(self._null_cap), np.empty(self._null_cap),
                                   np.empty(self._null_cap, dtype=np.int32), np.empty(self._null_cap, dtype=np.int32))

@@ -96,6 +96,7 @@ struct dfb_ctx {
     int64_t klaunch[DFB_K_COUNT] = {0};
     // options
     int opt_screen = 1;
+    int opt_dbg = 0;             // developer timing experiments (results invalid when non-zero)
     int opt_fused = 1;           // fused screen+refine kernel (0: two-kernel screen path)
     double opt_null_cap_mb = 0;  // 0 = auto
     int opt_perm_batch = 0;      // 0 = auto

@@ -690,6 +690,7 @@ struct FusedParams {
     double* vals;
     unsigned long long capacity;
     unsigned long long* cursor;
+    int dbg;  // developer experiments (timing only, results wrong): 1 = reuse the first B tiles, 2 = no MMAs
 };
 
 // 32 lanes x 32 consecutive fp32 columns
@@ -860,9 +861,13 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
                         const int sb1 = (int)(loaded % NB);
                         const int64_t use = loaded / NB;
                         if (use > 0) mbar_wait(empty_b + 8 * sb1, (uint32_t)((use - 1) & 1));  // earlier MMAs on this stage done
-                        mbar_expect_tx(full_b + 8 * sb1, G.b_bytes);
-                        bulk_g2s(b_addr + sb1 * G.b_bytes, src + (size_t)(loaded % G.chunks) * G.b_bytes, G.b_bytes,
-                                 full_b + 8 * sb1);
+                        if ((P.dbg & 1) && loaded >= NB) {
+                            mbar_arrive(full_b + 8 * sb1);  // experiment: keep the tile already in the stage
+                        } else {
+                            mbar_expect_tx(full_b + 8 * sb1, G.b_bytes);
+                            bulk_g2s(b_addr + sb1 * G.b_bytes, src + (size_t)(loaded % G.chunks) * G.b_bytes, G.b_bytes,
+                                     full_b + 8 * sb1);
+                        }
                         ++loaded;
                     }
                     const int sb = (int)(i0 % NB);
@@ -876,7 +881,7 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
                     const uint32_t d_addr = tmem_base + (uint32_t)(s * G.nmma);
                     const uint32_t bs_addr = b_addr + sb * G.b_bytes;
                     uint32_t accum = 0u;
-                    for (int t = 0; t < G.nk16; ++t) {
+                    for (int t = 0; t < ((P.dbg & 2) ? 1 : G.nk16); ++t) {
 #pragma unroll
                         for (int term = 0; term < 3; ++term) {
                             const int acol = (term == 2 ? G.npad : 0) + 16 * t;
@@ -909,34 +914,38 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
                 const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * G.nmma);
                 // candidate test + work list in one pass: the ballot word of a permutation is warp-uniform,
                 // so its candidates are appended (in base order) right away -> list sorted by (perm, base)
+                // All statistics of a 32-column load are formed first (independent FMA chains), then all
+                // ballots, and only then the (rare for stringent cutoffs) non-empty words are appended: no
+                // vote -> branch dependency between consecutive permutations.
                 int nwork = 0;
+                constexpr int NPL = 2 * per16;  // permutations per 32-column load
                 for (int g = 0; g * per16 < nq; g += 2) {
                     float v[32];
                     tmem_ld32(taddr + (uint32_t)(g * 16), v);
-                    const uint16_t ent0 = (uint16_t)(((g * per16) << 5) | lane);
-                    if ((g + 2) * per16 <= nq) {  // warp-uniform: no padded permutation in this load
+                    const bool full = (g + 2) * per16 <= nq;  // warp-uniform: no padded permutation in this load
+                    unsigned words[NPL];
+                    unsigned any = 0u;
 #pragma unroll
-                        for (int qq = 0; qq < 2 * per16; ++qq) {
-                            float a = v[qq * PST] * v[qq * PST];
+                    for (int qq = 0; qq < NPL; ++qq) {
+                        float a = v[qq * PST] * v[qq * PST];
 #pragma unroll
-                            for (int j = 1; j < PCOLS; ++j) a = fmaf(v[qq * PST + j], v[qq * PST + j], a);
-                            const bool cand = a >= thr;
-                            const unsigned word = __ballot_sync(0xffffffffu, cand);
+                        for (int j = 1; j < PCOLS; ++j) a = fmaf(v[qq * PST + j], v[qq * PST + j], a);
+                        words[qq] = __ballot_sync(0xffffffffu, a >= thr);
+                    }
+                    if (!full) {
+#pragma unroll
+                        for (int qq = 0; qq < NPL; ++qq)
+                            if (g * per16 + qq >= nq) words[qq] = 0u;
+                    }
+#pragma unroll
+                    for (int qq = 0; qq < NPL; ++qq) any |= words[qq];
+                    if (any) {
+                        const uint16_t ent0 = (uint16_t)(((g * per16) << 5) | lane);
+#pragma unroll
+                        for (int qq = 0; qq < NPL; ++qq) {
+                            const unsigned word = words[qq];
                             if (word) {
-                                if (cand) list_w[nwork + __popc(word & lt_mask)] = (uint16_t)(ent0 + (qq << 5));
-                                nwork += __popc(word);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int qq = 0; qq < 2 * per16; ++qq) {
-                            float a = v[qq * PST] * v[qq * PST];
-#pragma unroll
-                            for (int j = 1; j < PCOLS; ++j) a = fmaf(v[qq * PST + j], v[qq * PST + j], a);
-                            const bool cand = (a >= thr) && (g * per16 + qq < nq);
-                            const unsigned word = __ballot_sync(0xffffffffu, cand);
-                            if (word) {
-                                if (cand) list_w[nwork + __popc(word & lt_mask)] = (uint16_t)(ent0 + (qq << 5));
+                                if ((word >> lane) & 1u) list_w[nwork + __popc(word & lt_mask)] = (uint16_t)(ent0 + (qq << 5));
                                 nwork += __popc(word);
                             }
                         }
@@ -1399,6 +1408,7 @@ int fstat_perm_batch_fused(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& m
     // mean and of the n subtractions); 2x safety.  Its weight in the statistic is c.
     F.e0 = G.j0 ? (float)(sqrt(w_c) * 2.0 * pow((double)cov->n, 1.5) * 2.220446049250313e-16 * 1.000001) : 0.f;
     F.idesc = umma_idesc_bf16(TC_M, G.nmma);
+    F.dbg = ctx->opt_dbg;
 
     out->rows = B;
     out->W = ceil_div(cov->N, 32);
