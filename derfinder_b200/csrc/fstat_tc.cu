@@ -65,6 +65,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "r"(parity), "r"(0x989680u)  // suspend-time hint: the warp sleeps in hardware instead of spinning
         : "memory");
 }
+// pure spin (no suspend hint)
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "SPIN_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra SPUN_%=;\n"
+        "bra SPIN_%=;\n"
+        "SPUN_%=:\n"
+        "}\n" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_wait_sel(uint32_t bar, uint32_t parity, bool spin) {
+    if (spin) mbar_wait_spin(bar, parity);
+    else mbar_wait(bar, parity);
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
@@ -233,6 +251,8 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_screen_kernel(const ScreenPa
             for (int s = 0; s < 2; ++s) {
                 mbar_init(full_b + 8 * s, 1);
                 mbar_init(empty_b + 8 * s, 1);
+            }
+            for (int s = 0; s < 2; ++s) {
                 mbar_init(tmem_full + 8 * s, 1);
                 mbar_init(tmem_empty + 8 * s, 4);
             }
@@ -623,10 +643,11 @@ struct FusedGeom {
     int ps, nmma;       // permutations per chunk, MMA N = ps * pst
     int qs, ixs;        // Qs row stride (doubles), bytes per row of the byte permutation table
     int nb;             // B tile stages: 1 when the tile is small (occupancy first), else 2
+    int ew;             // epilogue warps per TMEM lane quarter (1, 2 or 4)
     int64_t B, chunks;
     int64_t tiles;
     uint32_t a_bytes, b_bytes;
-    uint32_t off_b, off_ys, off_qs, off_yy, off_bar, off_warp, warp_bytes;
+    uint32_t off_b, off_ys, off_qs, off_yy, off_thr, off_bar, off_warp, warp_bytes;
     size_t smem;
 };
 
@@ -711,8 +732,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
 }
 
 // PT: number of model columns (2..8) or 0 = generic; J0: 1 when the constant column is not screened
+// Thread layout: EW epilogue warps per 32-lane TMEM quarter (warp w: quarter w & 3, share h = w >> 2
+// of the chunk's permutations), then one producer / MMA warp (index 4 * EW).  With one CTA per SM
+// (large sample counts: the FP64 tile fills shared memory) a single epilogue warp per scheduler
+// cannot hide its own latencies and the tensor pipe starves; EW = 4 gives every scheduler four.
+// The siblings of a quarter work on the same 32 bases (same centred tile), different permutations.
+constexpr int FZ_MAX_THREADS = 4 * 128 + 32;
 template <int PT, int J0>
-__global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParams P) {
+__global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedParams P) {
     constexpr int PCOLS = PT > 0 ? PT - J0 : 16;
     constexpr int PST = PCOLS <= 2 ? 2 : (PCOLS <= 4 ? 4 : (PCOLS <= 8 ? 8 : 16));
     constexpr int per16 = 16 / PST;
@@ -721,37 +748,44 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
     const FusedGeom& G = P.G;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n = G.n, p = G.p, qs = G.qs;
+    const int ew = G.ew, mma_warp = 4 * G.ew;
+    const int quarter = warp & 3, hsub = warp >> 2;  // epilogue warps only
+    const int hp = G.ps / ew;                        // permutations of a chunk handled by one warp
+    const int row = quarter * 32 + lane;             // base row (TMEM lane) of this thread
     unsigned char* As = sm;
     unsigned char* Bs = sm + G.off_b;
     double* ys = reinterpret_cast<double*>(sm + G.off_ys);  // [n][128] centred
     double* Qs = reinterpret_cast<double*>(sm + G.off_qs);  // [n][qs]
     double* yy_s = reinterpret_cast<double*>(sm + G.off_yy);  // [128]
+    float* thr_s = reinterpret_cast<float*>(sm + G.off_thr);  // [128] candidate thresholds
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + G.off_bar);
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
-    const uint32_t full_b = smem_u32(bars + 0), empty_b = smem_u32(bars + 2), a_ready = smem_u32(bars + 8);
-    const uint32_t tmem_full = smem_u32(bars + 4), tmem_empty = smem_u32(bars + 6);
-    const int NB = G.nb;  // B stages (1 or 2)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    const uint32_t full_b = smem_u32(bars + 0), empty_b = smem_u32(bars + 4), a_ready = smem_u32(bars + 12);
+    const uint32_t tmem_full = smem_u32(bars + 8), tmem_empty = smem_u32(bars + 10);
+    const int NB = G.nb;  // B stages (1 .. 4)
     // per-warp scratch (epilogue warps only)
-    unsigned char* wbase = sm + G.off_warp + (size_t)(warp & 3) * G.warp_bytes;
-    uint16_t* list_w = reinterpret_cast<uint16_t*>(wbase);        // [1024] (perm << 5) | base
-    uint32_t* ew_w = reinterpret_cast<uint32_t*>(list_w + 1024);  // [32] exact words
-    unsigned char* ix_w = reinterpret_cast<unsigned char*>(ew_w + 32);  // [32][ixs] permutation rows
+    unsigned char* wbase = sm + G.off_warp + (size_t)(warp < mma_warp ? warp : 0) * G.warp_bytes;
+    uint16_t* list_w = reinterpret_cast<uint16_t*>(wbase);              // [hp * 32] (perm << 5) | base
+    uint32_t* ew_w = reinterpret_cast<uint32_t*>(list_w + hp * 32);     // [32] exact words
+    unsigned char* ix_w = reinterpret_cast<unsigned char*>(ew_w + 32);  // [hp][ixs] permutation rows
 
-    if (warp == 4) {
+    if (warp == mma_warp) {
         if (lane == 0) {
             mbar_init(a_ready, 4);
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < NB; ++s) {
                 mbar_init(full_b + 8 * s, 1);
                 mbar_init(empty_b + 8 * s, 1);
+            }
+            for (int s = 0; s < 2; ++s) {
                 mbar_init(tmem_full + 8 * s, 1);
-                mbar_init(tmem_empty + 8 * s, 4);
+                mbar_init(tmem_empty + 8 * s, (uint32_t)(4 * ew));
             }
             fence_barrier_init();
         }
         __syncwarp();
         tmem_alloc(smem_u32(tmem_slot), (uint32_t)(2 * G.nmma));
     } else {
-        for (int e = tid; e < n * qs; e += TC_M) {
+        for (int e = tid; e < n * qs; e += 128 * ew) {
             const int k = e / qs, j = e - k * qs;
             Qs[e] = j < p ? P.q[(size_t)k * p + j] : 0.0;
         }
@@ -777,10 +811,12 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
     for (int64_t tile = blockIdx.x; tile < G.tiles; tile += gridDim.x) {
         const int64_t base0 = tile * TC_M;
         float thr = __int_as_float(0x7f800000);  // +inf: rows beyond N never pass
+        // siblings of a quarter share its centred tile: they meet before it is overwritten ...
+        if (ew > 1 && warp < mma_warp) asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "r"(32 * ew) : "memory");
         if (warp < 4) {
             // ---- stage the tile: FP64 centred copy (exact contract) + bf16 hi/lo A operand
             const int64_t base = base0 + tid;
-            const bool valid = base < P.N;
+            const bool valid = base < P.N && !(P.dbg & 32);
             double acc = 0.0;
             if (valid) {
                 for (int k0 = 0; k0 < n; k0 += 8) {  // 8 independent loads in flight, then the ordered sum
@@ -838,6 +874,7 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
                 float t2 = r > 0.f ? r * r * 0.99999f : 0.f;  // 1e-5: fp32 epilogue rounding
                 thr = (t2 == t2) ? t2 : __int_as_float(0x7fc00000);  // NaN data -> never a candidate
             }
+            if (ew > 1) thr_s[tid] = thr;
         }
         if (warp < 4) {
             // A rows of this warp are written: publish them to the async proxy and tell the MMA warp.
@@ -846,37 +883,40 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
             __syncwarp();
             if (lane == 0) mbar_arrive(a_ready);
         }
+        // ... and after it has been rebuilt
+        if (ew > 1 && warp < mma_warp) {
+            asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "r"(32 * ew) : "memory");
+            thr = thr_s[row];
+        }
 
-        if (warp == 4) {
+        if (warp == mma_warp) {
             // ===== producer + MMA issuer (one lane).  B tiles are small and L2-resident: one stage,
             // reloaded as soon as the MMAs of the previous chunk have consumed it. =====
             if (lane == 0) {
                 const uint32_t a_addr = smem_u32(As), b_addr = smem_u32(Bs);
                 const unsigned char* src = P.qb;
+                // B tile loads never sit between the MMAs of consecutive chunks: the first NB tiles are
+                // requested up front, afterwards the stage of the PREVIOUS chunk is refilled right after the
+                // MMAs of the current one have been issued -- waiting for the previous chunk's MMAs to
+                // retire then overlaps the execution of the current ones instead of stalling their issue.
+                while (loaded < total_chunks && loaded < NB) {
+                    const int sb1 = (int)loaded;
+                    mbar_expect_tx(full_b + 8 * sb1, G.b_bytes);
+                    bulk_g2s(b_addr + sb1 * G.b_bytes, src + (size_t)(loaded % G.chunks) * G.b_bytes, G.b_bytes,
+                             full_b + 8 * sb1);
+                    ++loaded;
+                }
                 for (int64_t c = 0; c < G.chunks; ++c) {
                     const int64_t i0 = it + c;
                     const int s = (int)(i0 & 1);
                     const uint32_t ph = (uint32_t)((i0 >> 1) & 1);
-                    while (loaded < total_chunks && loaded < i0 + NB) {
-                        const int sb1 = (int)(loaded % NB);
-                        const int64_t use = loaded / NB;
-                        if (use > 0) mbar_wait(empty_b + 8 * sb1, (uint32_t)((use - 1) & 1));  // earlier MMAs on this stage done
-                        if ((P.dbg & 1) && loaded >= NB) {
-                            mbar_arrive(full_b + 8 * sb1);  // experiment: keep the tile already in the stage
-                        } else {
-                            mbar_expect_tx(full_b + 8 * sb1, G.b_bytes);
-                            bulk_g2s(b_addr + sb1 * G.b_bytes, src + (size_t)(loaded % G.chunks) * G.b_bytes, G.b_bytes,
-                                     full_b + 8 * sb1);
-                        }
-                        ++loaded;
-                    }
                     const int sb = (int)(i0 % NB);
-                    if (c == 0) {  // the B tile of chunk 0 is in flight while the A tile is still being built
+                    if (c == 0) {  // the B tiles are in flight while the A tile is still being built
                         mbar_wait(a_ready, tphase);
                         tc_fence_after();
                     }
-                    mbar_wait(full_b + 8 * sb, (uint32_t)((i0 / NB) & 1));
-                    mbar_wait(tmem_empty + 8 * s, ph ^ 1);
+                    mbar_wait_sel(full_b + 8 * sb, (uint32_t)((i0 / NB) & 1), P.dbg & 16);
+                    mbar_wait_sel(tmem_empty + 8 * s, ph ^ 1, P.dbg & 16);
                     tc_fence_after();
                     const uint32_t d_addr = tmem_base + (uint32_t)(s * G.nmma);
                     const uint32_t bs_addr = b_addr + sb * G.b_bytes;
@@ -894,24 +934,42 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
                     }
                     umma_commit(empty_b + 8 * sb);   // B stage reusable once these MMAs have read it
                     umma_commit(tmem_full + 8 * s);  // accumulator ready for the epilogue
+                    {
+                        // refill: the stage of chunk r (previous chunk, or this one when there is a single
+                        // stage) receives chunk r + NB
+                        const int64_t r = i0 - (NB > 1 ? 1 : 0);
+                        if (r >= 0 && loaded < total_chunks && loaded == r + NB) {
+                            const int sb1 = (int)(r % NB);
+                            mbar_wait(empty_b + 8 * sb1, (uint32_t)((r / NB) & 1));  // MMAs of chunk r have read it
+                            if ((P.dbg & 1)) {
+                                mbar_arrive(full_b + 8 * sb1);  // experiment: keep the tile already in the stage
+                            } else {
+                                mbar_expect_tx(full_b + 8 * sb1, G.b_bytes);
+                                bulk_g2s(b_addr + sb1 * G.b_bytes, src + (size_t)(loaded % G.chunks) * G.b_bytes,
+                                         G.b_bytes, full_b + 8 * sb1);
+                            }
+                            ++loaded;
+                        }
+                    }
                 }
             }
             __syncwarp();
         } else {
             // ===== epilogue + refinement: warp owns 32 bases (TMEM lanes 32*warp .. +31) =====
-            const int64_t gw = tile * 4 + warp;  // global mask word of this warp's 32 bases
+            const int64_t gw = tile * 4 + quarter;  // global mask word of this warp's 32 bases
             const bool active = gw < P.W;
-            const double* ycol = ys + warp * 32;  // rows beyond N carry thr = +inf: never candidates
-            const double* yyw = yy_s + warp * 32;
+            const double* ycol = ys + quarter * 32;  // rows beyond N carry thr = +inf: never candidates
+            const double* yyw = yy_s + quarter * 32;
             for (int64_t c = 0; c < G.chunks; ++c) {
                 const int64_t i0 = it + c;
                 const int s = (int)(i0 & 1);
                 const uint32_t ph = (uint32_t)((i0 >> 1) & 1);
-                const int64_t b0 = c * G.ps;
-                const int nq = (int)min((int64_t)G.ps, P.G.B - b0);  // valid permutations of this chunk
-                mbar_wait(tmem_full + 8 * s, ph);
+                const int64_t b0 = c * G.ps + hsub * hp;  // first permutation of this warp's share of the chunk
+                const int nq = (int)max((int64_t)0, min((int64_t)hp, P.G.B - b0));  // valid permutations of the share
+                mbar_wait_sel(tmem_full + 8 * s, ph, P.dbg & 16);
                 tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(s * G.nmma);
+                const uint32_t taddr =
+                    tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * G.nmma + hsub * hp * PST);
                 // candidate test + work list in one pass: the ballot word of a permutation is warp-uniform,
                 // so its candidates are appended (in base order) right away -> list sorted by (perm, base)
                 // All statistics of a 32-column load are formed first (independent FMA chains), then all
@@ -919,7 +977,7 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
                 // vote -> branch dependency between consecutive permutations.
                 int nwork = 0;
                 constexpr int NPL = 2 * per16;  // permutations per 32-column load
-                for (int g = 0; g * per16 < nq; g += 2) {
+                for (int g = 0; g * per16 < ((P.dbg & 4) ? 0 : nq); g += 2) {
                     float v[32];
                     tmem_ld32(taddr + (uint32_t)(g * 16), v);
                     const bool full = (g + 2) * per16 <= nq;  // warp-uniform: no padded permutation in this load
@@ -956,7 +1014,7 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
                 if (lane == 0) mbar_arrive(tmem_empty + 8 * s);  // accumulator free: the next MMAs overlap the refinement
                 const int64_t b = b0 + lane;
                 if (nwork == 0) {
-                    if (lane < nq && active) {
+                    if (lane < nq && active && !(P.dbg & 8)) {
                         P.mask[b * P.W + gw] = 0u;
                         P.off[b * P.W + gw] = 0;
                     }
@@ -1058,7 +1116,7 @@ __global__ void __launch_bounds__(TC_THREADS) fstat_null_kernel(const FusedParam
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, (uint32_t)(2 * G.nmma));
+    if (warp == mma_warp) tmem_dealloc(tmem_base, (uint32_t)(2 * G.nmma));
 }
 
 __global__ void popcount_words_kernel(const uint32_t* __restrict__ w, int64_t n, unsigned long long* __restrict__ out) {
@@ -1326,7 +1384,14 @@ static bool fused_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
     G.b_bytes = (uint32_t)G.KB * (uint32_t)G.nmma * 128u;
     uint32_t o = G.a_bytes;
     G.off_b = o;
-    G.nb = G.b_bytes > 16 * 1024 ? 2 : 1;
+    G.nb = 1;
+    if (ctx->opt_b_stages >= 1 && ctx->opt_b_stages <= 4) G.nb = ctx->opt_b_stages;
+    else if (G.b_bytes > 16 * 1024) {
+        // as many stages as fit (<= 3): a 32 KiB bulk copy out of L2 takes longer than its MMAs
+        const size_t fixed = (size_t)G.a_bytes + (size_t)G.n * TC_M * 8 + (size_t)G.n * G.qs * 8 + 20 * 1024;
+        G.nb = 2;
+        while (G.nb < 3 && fixed + (size_t)(G.nb + 1) * G.b_bytes <= (size_t)224 * 1024) ++G.nb;
+    }
     o += (uint32_t)G.nb * G.b_bytes;
     G.off_ys = o;
     o += (uint32_t)G.n * TC_M * 8u;
@@ -1334,12 +1399,29 @@ static bool fused_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
     o += (uint32_t)round_up((int64_t)G.n * G.qs * 8, 16);
     G.off_yy = o;
     o += TC_M * 8u;
+    G.off_thr = o;
+    o += TC_M * 4u;
     G.off_bar = o;
-    o += 10 * 8 + 16;
+    o += 14 * 8 + 16;
     o = (uint32_t)round_up(o, 16);
     G.off_warp = o;
-    G.warp_bytes = (uint32_t)(1024 * 2 + 32 * 4 + 32 * G.ixs);
-    o += 4 * G.warp_bytes;
+    // epilogue warps per quarter: one when several CTAs share an SM anyway (small tiles); otherwise as
+    // many as the 32-column TMEM load granularity allows (a warp's share of a chunk is a multiple of
+    // 32 columns), at most 4
+    {
+        const size_t base_smem = (size_t)o + 4 * (1024 * 2 + 32 * 4 + 32 * G.ixs) + 1024;
+        const bool single_cta = 2 * (base_smem + 1024) > (size_t)227 * 1024;
+        // measured on B200 (c3s workload): the chunk loop is bound by the depth of the MMA -> epilogue
+        // -> MMA hand-off (two TMEM stages), not by epilogue issue, so extra warps do not pay yet; the
+        // knob stays for the deeper pipeline ("next")
+        (void)single_cta;
+        int want = ctx->opt_epi_warps > 0 ? ctx->opt_epi_warps : 1;
+        G.ew = std::max(1, std::min(want, G.nmma / 32));
+        while (G.ps % G.ew) --G.ew;
+    }
+    const int hp = G.ps / G.ew;
+    G.warp_bytes = (uint32_t)round_up(hp * 32 * 2 + 32 * 4 + hp * G.ixs, 16);
+    o += 4 * G.ew * G.warp_bytes;
     G.smem = (size_t)o + 1024;  // slack for the manual 1024-byte alignment
     const size_t limit = std::min<size_t>(ctx->smem_optin, 227 * 1024);
     if (G.smem > limit) return false;
@@ -1361,7 +1443,7 @@ static int launch_fused(dfb_ctx* ctx, const FusedParams& F, int grid) {
     auto go = [&](auto kern) -> int {
         DFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)F.G.smem));
         KTimer t(ctx, DFB_K_FSTAT_TC, 1);
-        kern<<<grid, TC_THREADS, F.G.smem, ctx->stream>>>(F);
+        kern<<<grid, 128 * F.G.ew + 32, F.G.smem, ctx->stream>>>(F);
         return DFB_OK;
     };
     if (PT > 0 && F.G.j0) return go(fstat_null_kernel<PT, PT == 0 ? 0 : 1>);
@@ -1419,10 +1501,12 @@ int fstat_perm_batch_fused(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& m
     DevBuf<unsigned long long> cursor;
     DFB_TRY(cursor.alloc(ctx, 1));
     // persistent grid: CTAs per SM limited by shared memory and by TMEM columns (512 per SM)
-    int per_sm = (int)std::min<size_t>((size_t)(227 * 1024) / G.smem, (size_t)(512 / (2 * G.nmma)));
+    const int threads = 128 * G.ew + 32;
+    int per_sm = (int)std::min<size_t>((size_t)(227 * 1024) / (G.smem + 1024), (size_t)(512 / (2 * G.nmma)));
+    per_sm = std::min(per_sm, 65536 / (threads * 100));  // registers (the kernels compile to <= 100)
     per_sm = std::max(1, std::min(per_sm, 6));
     const int grid = (int)std::min<int64_t>(G.tiles, (int64_t)ctx->sm_count * per_sm);
-    const size_t slack = (size_t)grid * 4 * RF_CHUNK;  // every warp may leave one partly used chunk behind
+    const size_t slack = (size_t)grid * 4 * G.ew * RF_CHUNK;  // every warp may leave one partly used chunk behind
     const size_t dense = (size_t)B * (size_t)cov->N;
     size_t cap = std::min(dense, std::max<size_t>(capacity_hint, 1024)) + slack;
     F.mask = out->mask.p;
