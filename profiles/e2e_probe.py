@@ -1,5 +1,6 @@
+"""Developer probe: per-call wall time of the result downloads of one C2 step (python profiles/e2e_probe.py on a GPU box)."""
 import sys, time, ctypes as C, numpy as np
-sys.path.insert(0, "/root/repo")
+sys.path.insert(0, __import__("os").path.dirname(__import__("os").path.dirname(__import__("os").path.abspath(__file__))))
 import torch, bench
 import derfinder_b200 as dfb
 from derfinder_b200 import _lib as L
