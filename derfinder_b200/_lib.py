@@ -87,6 +87,8 @@ SIGNATURES = {
     "dfb_nulls_get": (C.c_int, [C.c_void_p, C.c_int, c_f64p, c_i32p, c_f64p, c_i32p]),
     "dfb_nulls_copy_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfb_nulls_sorted_areas_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dfb_regions_null_hist_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),
+    "dfb_regions_hist_counts_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfb_count_greater_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p]),
     "dfb_regions_copy_areas_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfb_calc_pval": (C.c_int, [C.c_void_p, c_f64p, C.c_int64, c_f64p, C.c_int64, C.c_int, c_f64p]),

@@ -53,6 +53,8 @@ struct dfb_regions {
     // device copies of the index ranges (kept for view means / region matrix) and of the areas
     dfb::DevBuf<int32_t> d_is, d_ie;
     dfb::DevBuf<double> d_area;
+    dfb::DevBuf<double> d_area_desc;  // areas in decreasing order (after dfb_calculate_pvalues)
+    dfb::DevBuf<int32_t> d_order;     // d_area_desc[i] = d_area[d_order[i]]
 };
 
 struct dfb_nulls {

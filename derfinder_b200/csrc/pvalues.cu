@@ -216,6 +216,65 @@ __global__ void count_greater_kernel(const double* __restrict__ areas, int64_t R
     counts[r] += M - lo;
 }
 
+// Ranking without sorting the nulls: with the R region areas sorted in DEcreasing order (D), a null v
+// exceeds exactly the regions at positions >= i(v) = #{D >= v}; a histogram of i(v) over all nulls
+// and an inclusive prefix sum give #{null > D[i]} for every region.  O(M log R) searches in an array
+// that lives in L1/L2 instead of a radix sort of M keys.
+__global__ void __launch_bounds__(256) null_hist_kernel(const double* __restrict__ nulls, int64_t M,
+                                                        const double* __restrict__ desc, int64_t R,
+                                                        uint32_t* __restrict__ hist) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = nulls[i];
+        int64_t lo = 0, hi = R;  // smallest index with desc[idx] < v (R when none; NaN compares false)
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (desc[mid] < v) hi = mid;
+            else lo = mid + 1;
+        }
+        atomicAdd(&hist[lo], 1u);
+    }
+}
+
+// counts/p-values in sorted (decreasing-area) order from the exclusive prefix of the histogram
+__global__ void hist_pval_kernel(const int64_t* __restrict__ excl, const uint32_t* __restrict__ hist, int64_t R,
+                                 double weight, double total, double* __restrict__ p, int64_t* __restrict__ counts,
+                                 const int32_t* __restrict__ order) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    const int64_t c = excl[i] + (int64_t)hist[i];
+    if (p) p[i] = __ddiv_rn(weight * (double)c + 1.0, weight * total + 1.0);
+    if (counts) counts[order ? order[i] : i] = c;
+}
+
+static int null_hist(dfb_ctx* ctx, const double* nulls_dev, int64_t M, const double* desc_dev, int64_t R,
+                     uint32_t* hist_dev) {
+    if (M <= 0) return DFB_OK;
+    KTimer t(ctx, DFB_K_PVAL);
+    null_hist_kernel<<<grid_for(M, 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(nulls_dev, M, desc_dev, R, hist_dev);
+    DFB_CUDA(cudaGetLastError());
+    return DFB_OK;
+}
+
+// p-values of regions given in decreasing-area order against unsorted nulls
+static int pval_by_hist(dfb_ctx* ctx, const double* desc_dev, int64_t R, const double* nulls_dev, int64_t M, int weight,
+                        double* p_dev) {
+    DevBuf<uint32_t> hist;
+    DevBuf<int64_t> excl, tot;
+    DFB_TRY(hist.alloc(ctx, (size_t)R + 1));
+    DFB_TRY(hist.zero());
+    DFB_TRY(excl.alloc(ctx, (size_t)R + 1));
+    DFB_TRY(tot.alloc(ctx, 1));
+    DFB_TRY(null_hist(ctx, nulls_dev, M, desc_dev, R, hist.p));
+    DFB_TRY(exclusive_scan_u32(ctx, hist.p, excl.p, R + 1, tot.p, DFB_K_PVAL));
+    {
+        KTimer t(ctx, DFB_K_PVAL);
+        hist_pval_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, ctx->stream>>>(excl.p, hist.p, R, (double)weight, (double)M,
+                                                                             p_dev, nullptr, nullptr);
+    }
+    DFB_CUDA(cudaGetLastError());
+    return DFB_OK;
+}
+
 int calc_pval_device(dfb_ctx* ctx, const double* areas_dev, int64_t R, const double* nulls_dev, int64_t M, int weight,
                      double* p_dev, DevBuf<double>* keep_sorted = nullptr) {
     if (R == 0) return DFB_OK;
@@ -492,6 +551,37 @@ int dfb_count_greater_dev(dfb_ctx* ctx, const double* areas_dev, int64_t R, cons
     return DFB_OK;
 }
 
+int dfb_regions_null_hist_dev(dfb_ctx* ctx, const dfb_regions* r, const double* nulls_dev, int64_t M,
+                              uint32_t* hist_dev) {
+    DFB_REQUIRE(ctx && r && (nulls_dev || M == 0) && hist_dev, "dfb_regions_null_hist_dev: NULL argument");
+    if (!r->d_area_desc.p) {
+        set_error("dfb_regions_null_hist_dev: this result was not produced by dfb_calculate_pvalues");
+        return DFB_ESTATE;
+    }
+    return null_hist(ctx, nulls_dev, M, r->d_area_desc.p, r->R, hist_dev);
+}
+
+int dfb_regions_hist_counts_dev(dfb_ctx* ctx, const dfb_regions* r, const uint32_t* hist_dev, int64_t* counts_dev) {
+    DFB_REQUIRE(ctx && r && hist_dev && (counts_dev || r->R == 0), "dfb_regions_hist_counts_dev: NULL argument");
+    if (!r->d_area_desc.p) {
+        set_error("dfb_regions_hist_counts_dev: this result was not produced by dfb_calculate_pvalues");
+        return DFB_ESTATE;
+    }
+    const int64_t R = r->R;
+    if (R == 0) return DFB_OK;
+    DevBuf<int64_t> excl, tot;
+    DFB_TRY(excl.alloc(ctx, (size_t)R + 1));
+    DFB_TRY(tot.alloc(ctx, 1));
+    DFB_TRY(exclusive_scan_u32(ctx, hist_dev, excl.p, R + 1, tot.p, DFB_K_PVAL));
+    {
+        KTimer t(ctx, DFB_K_PVAL);
+        hist_pval_kernel<<<(unsigned)ceil_div(R, 256), 256, 0, ctx->stream>>>(excl.p, hist_dev, R, 0.0, 0.0, nullptr,
+                                                                             counts_dev, r->d_order.p);
+    }
+    DFB_CUDA(cudaGetLastError());
+    return DFB_OK;
+}
+
 int dfb_regions_copy_areas_dev(dfb_ctx* ctx, const dfb_regions* r, double* out_dev) {
     DFB_REQUIRE(ctx && r && (out_dev || r->R == 0), "dfb_regions_copy_areas_dev: NULL argument");
     if (r->R == 0) return DFB_OK;
@@ -662,8 +752,8 @@ int dfb_calculate_pvalues(dfb_ctx* ctx, dfb_cov* cov, const double* fstats, cons
     const int32_t* h_order = d2h_async_pinned(ctx, order_d.p, (size_t)R);
     const double* h_p = nullptr;
     if (nl->count > 0) {  // no nulls at all -> NA (:408-419)
-        if ((rc = calc_pval_device(ctx, sorted_d.p, R, nl->area.p, nl->count, 2, p_d.p, &nl->area_sorted)) < 0)
-            return fail(rc);
+        // the regions are sorted already: rank the nulls against them instead of sorting the nulls
+        if ((rc = pval_by_hist(ctx, sorted_d.p, R, nl->area.p, nl->count, 2, p_d.p)) < 0) return fail(rc);
         h_p = d2h_async_pinned(ctx, p_d.p, (size_t)R);
     }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || !h_order || (nl->count > 0 && !h_p)) {
@@ -673,6 +763,8 @@ int dfb_calculate_pvalues(dfb_ctx* ctx, dfb_cov* cov, const double* fstats, cons
     r->order.assign(h_order, h_order + R);
     if (h_p) r->pvalues.assign(h_p, h_p + R);
     else r->pvalues.assign((size_t)R, nan(""));
+    r->d_area_desc = std::move(sorted_d);  // kept for genome-wide pooling (dfb_regions_null_hist_dev)
+    r->d_order = std::move(order_d);
     if (pvalues) memcpy(pvalues, r->pvalues.data(), (size_t)R * 8);
     *regions = r;
     *nulls = nl;

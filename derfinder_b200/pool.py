@@ -10,9 +10,9 @@ the whole per-chromosome pipeline on its own GPU and only
     per-permutation max [B]   all-reduce(max)
 
 cross NVLink.  Tensors stay where they are (CUDA with NCCL, CPU with gloo in the tests).  Each rank
-contributes its null areas already SORTED (its own p-value ranking sorted them), so the pool is
-never sorted again: a region's pooled count is the sum over ranks of an upper-bound search in that
-rank's list (`dfb_count_greater_dev`).
+ranks its own regions (already sorted by area) against the pooled, UNSORTED null lists with a
+histogram (`dfb_regions_null_hist_dev` / `dfb_regions_hist_counts_dev`): nothing is sorted for the
+pooling.
 """
 from __future__ import annotations
 
@@ -72,30 +72,34 @@ def genomewide_pvalues(engine, regions_handle, nulls_handle, B, cutoff_used, tor
     R = int(lib.dfb_regions_count(regions_handle))
     area = torch.empty(max(M, 1), device=device, dtype=torch.float64)
     perm = torch.zeros(max(M, 1), device=device, dtype=torch.int32)
-    srt = torch.empty(max(M, 1), device=device, dtype=torch.float64)
     mx = torch.empty(B, device=device, dtype=torch.float64)
     a_dev = torch.empty(max(R, 1), device=device, dtype=torch.float64)
     L.check(lib.dfb_nulls_copy_dev(nulls_handle, C.c_void_p(area.data_ptr()), C.c_void_p(perm.data_ptr())))
     L.check(lib.dfb_perm_max_dev(engine.h, C.c_void_p(area.data_ptr()), C.c_void_p(perm.data_ptr()), M, B, -1.0,
                                  C.c_void_p(mx.data_ptr())))
-    L.check(lib.dfb_nulls_sorted_areas_dev(engine.h, nulls_handle, C.c_void_p(srt.data_ptr())))
     L.check(lib.dfb_regions_copy_areas_dev(engine.h, regions_handle, C.c_void_p(a_dev.data_ptr())))
     # the engine and torch share one stream in bench.py; otherwise order them explicitly
-    if engine.stream_handle != torch.cuda.current_stream().cuda_stream:
+    shared = engine.stream_handle == torch.cuda.current_stream().cuda_stream
+    if not shared:
         engine.sync()
-    segments, gmax = exchange_nulls(srt[:M], mx, dist=dist)
+    segments, gmax = exchange_nulls(area[:M], mx, dist=dist)
     # a permutation without any null region anywhere contributes cutoffFstatUsed (R/mergeResults.R:382)
     gmax = torch.where(gmax < 0, torch.full_like(gmax, float(cutoff_used)), gmax)
+    # this rank's regions are sorted by area already: the pooled nulls (unsorted, rank by rank) are
+    # ranked against them with a histogram -- nothing is sorted for the pooling
+    hist = torch.zeros(R + 1, device=device, dtype=torch.int32)
     counts = torch.zeros(max(R, 1), device=device, dtype=torch.int64)
     total = 0
-    if engine.stream_handle != torch.cuda.current_stream().cuda_stream:
+    if not shared:
         torch.cuda.current_stream().synchronize()
     for seg in segments:
         total += seg.numel()
         if seg.numel():
-            L.check(lib.dfb_count_greater_dev(engine.h, C.c_void_p(a_dev.data_ptr()), R, C.c_void_p(seg.data_ptr()),
-                                              seg.numel(), C.c_void_p(counts.data_ptr())))
-    if engine.stream_handle != torch.cuda.current_stream().cuda_stream:
+            L.check(lib.dfb_regions_null_hist_dev(engine.h, regions_handle, C.c_void_p(seg.data_ptr()), seg.numel(),
+                                                  C.c_void_p(hist.data_ptr())))
+    L.check(lib.dfb_regions_hist_counts_dev(engine.h, regions_handle, C.c_void_p(hist.data_ptr()),
+                                            C.c_void_p(counts.data_ptr())))
+    if not shared:
         engine.sync()
     a_dev, counts = a_dev[:R], counts[:R]
     # every null entry is stored twice by the reference (R/calculatePvalues.R:346-354): weight 2

@@ -229,6 +229,16 @@ int dfb_nulls_copy_dev(const dfb_nulls* nl, double* area_dev, int32_t* perm_dev)
  * dfb_regions_copy_areas_dev copies the region areas in up-then-dn order (before the
  * decreasing-area reordering, see dfb_regions_get_order). */
 int dfb_nulls_sorted_areas_dev(dfb_ctx* ctx, dfb_nulls* nl, double* out_dev);
+/* Ranking without sorting any nulls (what dfb_calculate_pvalues does itself): the regions of `r`
+ * are already sorted by decreasing area, so a null v exceeds exactly the regions from position
+ * #{area >= v} on.  dfb_regions_null_hist_dev ADDS the histogram of those positions for M unsorted
+ * nulls to hist_dev [R + 1] (uint32, zeroed by the caller; call once per rank's list);
+ * dfb_regions_hist_counts_dev turns it into counts_dev[k] = #{pooled null > area of region k},
+ * regions in up-then-dn order. */
+int dfb_regions_null_hist_dev(dfb_ctx* ctx, const dfb_regions* r, const double* nulls_dev, int64_t M,
+                              uint32_t* hist_dev);
+int dfb_regions_hist_counts_dev(dfb_ctx* ctx, const dfb_regions* r, const uint32_t* hist_dev,
+                                int64_t* counts_dev);
 int dfb_count_greater_dev(dfb_ctx* ctx, const double* areas_dev, int64_t R, const double* sorted_nulls_dev,
                           int64_t M, int64_t* counts_dev);
 int dfb_regions_copy_areas_dev(dfb_ctx* ctx, const dfb_regions* r, double* out_dev);
