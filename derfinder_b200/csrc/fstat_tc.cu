@@ -28,6 +28,7 @@
 // is built once per CTA and reused for every permutation chunk.
 #include <cuda_bf16.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 
@@ -644,6 +645,7 @@ struct FusedGeom {
     int qs, ixs;        // Qs row stride (doubles), bytes per row of the byte permutation table
     int nb;             // B tile stages: 1 when the tile is small (occupancy first), else 2
     int ew;             // epilogue warps per TMEM lane quarter (1, 2 or 4)
+    int ys_smem;        // 1: centred FP64 tile resident in shared memory; 0: streamed (candidates re-read Y)
     int64_t B, chunks;
     int64_t tiles;
     uint32_t a_bytes, b_bytes;
@@ -757,6 +759,8 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
     double* ys = reinterpret_cast<double*>(sm + G.off_ys);  // [n][128] centred
     double* Qs = reinterpret_cast<double*>(sm + G.off_qs);  // [n][qs]
     double* yy_s = reinterpret_cast<double*>(sm + G.off_yy);  // [128]
+    double* m_s = yy_s + TC_M;                                // [128] row means (streamed-Y variant)
+    const bool ys_smem = G.ys_smem != 0;
     float* thr_s = reinterpret_cast<float*>(sm + G.off_thr);  // [128] candidate thresholds
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + G.off_bar);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
@@ -826,11 +830,11 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
 #pragma unroll
                     for (int e = 0; e < 8; ++e)
                         if (k0 + e < n) {
-                            ys[(size_t)(k0 + e) * TC_M + tid] = v[e];
+                            if (ys_smem) ys[(size_t)(k0 + e) * TC_M + tid] = v[e];
                             acc = (k0 + e == 0) ? v[e] : __dadd_rn(acc, v[e]);
                         }
                 }
-            } else {
+            } else if (ys_smem) {
                 for (int k = 0; k < n; ++k) ys[(size_t)k * TC_M + tid] = 0.0;
             }
             const double m = P.center ? __ddiv_rn(acc, (double)n) : 0.0;
@@ -840,6 +844,12 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
             };
             for (int k0 = 0; k0 < G.npad; k0 += 8) {
                 __nv_bfloat162 hi[4], lo[4];
+                double raw[8];
+                if (!ys_smem) {  // streamed-Y variant: the second pass re-reads the (L2-hot) values
+#pragma unroll
+                    for (int e = 0; e < 8; ++e)
+                        raw[e] = (valid && k0 + e < n) ? P.Y[(size_t)(k0 + e) * P.ld + base] : 0.0;
+                }
 #pragma unroll
                 for (int e = 0; e < 8; e += 2) {
                     float f[2];
@@ -848,8 +858,12 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
                         const int k = k0 + e + u;
                         double v = 0.0;
                         if (k < n) {
-                            v = __dsub_rn(ys[(size_t)k * TC_M + tid], m);
-                            ys[(size_t)k * TC_M + tid] = v;
+                            if (ys_smem) {
+                                v = __dsub_rn(ys[(size_t)k * TC_M + tid], m);
+                                ys[(size_t)k * TC_M + tid] = v;
+                            } else {
+                                v = valid ? __dsub_rn(raw[e + u], m) : 0.0;
+                            }
                             yy = fma(v, v, yy);
                         }
                         f[u] = (float)v;
@@ -865,6 +879,7 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
             const uint4 zero4 = make_uint4(0u, 0u, 0u, 0u);
             for (int col = 2 * G.npad; col < G.KB * 64; col += 8) put(col, zero4);
             yy_s[tid] = yy;
+            if (!ys_smem) m_s[tid] = m;
             if (valid) {
                 // candidate iff  L~ >= (sqrt(T) - kappa*delta*|yc| - e0*(|m| + |yc|))^2, T = U*(adjustF + yy/dfden);
                 // evaluated in FP32 with the rounding pushed to the safe side
@@ -960,6 +975,8 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
             const bool active = gw < P.W;
             const double* ycol = ys + quarter * 32;  // rows beyond N carry thr = +inf: never candidates
             const double* yyw = yy_s + quarter * 32;
+            const double* mw = m_s + quarter * 32;
+            const double* yglob = P.Y + base0 + quarter * 32;  // streamed-Y variant: candidates re-read Y
             for (int64_t c = 0; c < G.chunks; ++c) {
                 const int64_t i0 = it + c;
                 const int s = (int)(i0 & 1);
@@ -1053,8 +1070,10 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
 #pragma unroll
                             for (int j = 0; j < PT; ++j) S[j] = 0.0;
 #pragma unroll 4
+                            const double mrow = ys_smem ? 0.0 : mw[bl];
                             for (int k = 0; k < n; ++k) {
-                                const double yv = ycol[(size_t)k * TC_M + bl];
+                                const double yv = ys_smem ? ycol[(size_t)k * TC_M + bl]
+                                                          : __dsub_rn(yglob[(size_t)k * P.ld + bl], mrow);
                                 const double2* qrow = reinterpret_cast<const double2*>(Qs + (size_t)ix[k] * QS);
 #pragma unroll
                                 for (int j2 = 0; j2 < QS / 2; ++j2) {
@@ -1069,10 +1088,14 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
                                 else sd = fma(S[j], S[j], sd);
                             }
                         } else {
+                            const double mrow = ys_smem ? 0.0 : mw[bl];
                             for (int j = 0; j < p; ++j) {
                                 double S = 0.0;
-                                for (int k = 0; k < n; ++k)
-                                    S = fma(ycol[(size_t)k * TC_M + bl], Qs[(size_t)ix[k] * qs + j], S);
+                                for (int k = 0; k < n; ++k) {
+                                    const double yv = ys_smem ? ycol[(size_t)k * TC_M + bl]
+                                                              : __dsub_rn(yglob[(size_t)k * P.ld + bl], mrow);
+                                    S = fma(yv, Qs[(size_t)ix[k] * qs + j], S);
+                                }
                                 if (j < G.p0) s0 = fma(S, S, s0);
                                 else sd = fma(S, S, sd);
                             }
@@ -1382,23 +1405,33 @@ static bool fused_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
     G.tiles = ceil_div(cov->N, TC_M);
     G.a_bytes = (uint32_t)G.KB * TC_M * 128u;
     G.b_bytes = (uint32_t)G.KB * (uint32_t)G.nmma * 128u;
+    // The centred FP64 tile (n x 128 doubles) stays in shared memory when that still leaves room for
+    // two CTAs per SM; otherwise it is streamed (the rare candidates re-read Y through L2) so that a
+    // second CTA can cover the MMA <-> epilogue hand-off latency and the tile staging of the first.
+    {
+        const size_t ys_bytes = (size_t)G.n * TC_M * 8;
+        const size_t rest = (size_t)G.a_bytes + 2 * (size_t)G.b_bytes + (size_t)G.n * G.qs * 8 + 16 * 1024;
+        G.ys_smem = (ctx->opt_ys_smem >= 0) ? ctx->opt_ys_smem : (2 * (rest + ys_bytes) <= (size_t)225 * 1024 ? 1 : 0);
+        if (!G.ys_smem && rest > (size_t)225 * 1024) return false;
+    }
     uint32_t o = G.a_bytes;
     G.off_b = o;
     G.nb = 1;
     if (ctx->opt_b_stages >= 1 && ctx->opt_b_stages <= 4) G.nb = ctx->opt_b_stages;
     else if (G.b_bytes > 16 * 1024) {
         // as many stages as fit (<= 3): a 32 KiB bulk copy out of L2 takes longer than its MMAs
-        const size_t fixed = (size_t)G.a_bytes + (size_t)G.n * TC_M * 8 + (size_t)G.n * G.qs * 8 + 20 * 1024;
+        const size_t fixed = (size_t)G.a_bytes + (G.ys_smem ? (size_t)G.n * TC_M * 8 : 0) + (size_t)G.n * G.qs * 8 + 20 * 1024;
+        const size_t budget = G.ys_smem ? (size_t)224 * 1024 : (size_t)112 * 1024;  // streamed: leave room for 2 CTAs
         G.nb = 2;
-        while (G.nb < 3 && fixed + (size_t)(G.nb + 1) * G.b_bytes <= (size_t)224 * 1024) ++G.nb;
+        while (G.nb < 3 && fixed + (size_t)(G.nb + 1) * G.b_bytes <= budget) ++G.nb;
     }
     o += (uint32_t)G.nb * G.b_bytes;
     G.off_ys = o;
-    o += (uint32_t)G.n * TC_M * 8u;
+    o += G.ys_smem ? (uint32_t)G.n * TC_M * 8u : 0u;
     G.off_qs = o;
     o += (uint32_t)round_up((int64_t)G.n * G.qs * 8, 16);
     G.off_yy = o;
-    o += TC_M * 8u;
+    o += 2 * TC_M * 8u;  // yy and the row means
     G.off_thr = o;
     o += TC_M * 4u;
     G.off_bar = o;
@@ -1506,6 +1539,9 @@ int fstat_perm_batch_fused(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& m
     per_sm = std::min(per_sm, 65536 / (threads * 100));  // registers (the kernels compile to <= 100)
     per_sm = std::max(1, std::min(per_sm, 6));
     const int grid = (int)std::min<int64_t>(G.tiles, (int64_t)ctx->sm_count * per_sm);
+    if (getenv("DFB_GAPS"))
+        fprintf(stderr, "[dfb] fused geometry: n=%d npad=%d KB=%d pst=%d ps=%d nmma=%d nb=%d ew=%d ys_smem=%d smem=%zu per_sm=%d grid=%d\n",
+                G.n, G.npad, G.KB, G.pst, G.ps, G.nmma, G.nb, G.ew, G.ys_smem, G.smem, per_sm, grid);
     const size_t slack = (size_t)grid * 4 * G.ew * RF_CHUNK;  // every warp may leave one partly used chunk behind
     const size_t dense = (size_t)B * (size_t)cov->N;
     size_t cap = std::min(dense, std::max<size_t>(capacity_hint, 1024)) + slack;

@@ -731,3 +731,24 @@ def test_full_size_paths_agree(dfb, full_c2):
         b = _full_pass(dfb, full_c2, **opts)
         for k in ("area", "value", "pv", "is", "ie", "nstat", "narea", "nw", "nperm"):
             assert np.array_equal(ref[k], b[k]), (opts, k)
+
+
+@pytest.mark.parametrize("opts", [dict(ys_smem=0), dict(ys_smem=0, epi_warps=2), dict(epi_warps=2), dict(b_stages=3),
+                                  dict(ys_smem=1, b_stages=2, epi_warps=4)])
+def test_fused_kernel_variants_agree(dfb, eng, opts):
+    """Every layout variant of the fused null kernel (streamed FP64 tile, several epilogue warps per
+    TMEM quarter, deeper B staging) must reproduce the oracle pipeline bit for bit on a
+    candidate-rich case."""
+    rng = np.random.default_rng(404)
+    cov, position, group, models = synth(rng, 21000, 16, p_extra=1, seg=[8000, 13000])
+    perm = random_perms(rng, 45, 16)
+    cut = dfb.calcFstatCutoff("theoretical", 0.1, models=models)
+    e2 = dfb.Engine(0)
+    try:
+        for k, v in opts.items():
+            e2.set_option(k, v)
+        res, ores = run_both(dfb, e2, cov, position, group, models, perm, cut)
+        assert_pipeline_equal(res, ores)
+        assert e2.kernel_time(3)[1] > 0  # the tcgen05 path really ran
+    finally:
+        e2.close()
