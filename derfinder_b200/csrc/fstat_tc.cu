@@ -713,6 +713,7 @@ struct FusedParams {
     double* vals;
     unsigned long long capacity;
     unsigned long long* cursor;
+    unsigned long long* prof;  // [16] cycle counters (dbg & 64)
     int dbg;  // developer experiments (timing only, results wrong): 1 = reuse the first B tiles, 2 = no MMAs
 };
 
@@ -802,6 +803,17 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
     unsigned long long chunk_ptr = 0;  // warp-uniform: next free value slot of the warp's chunk
     int chunk_left = 0;
     const bool num_is_sd = P.dfnum == 1.0;
+    // developer instrumentation (dbg & 64): cycles per phase, summed over the kernel
+    const bool prof = (P.dbg & 64) != 0;
+    long long pc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = clock64();
+    auto lap = [&](int slot) {
+        if (prof) {
+            const long long t = clock64();
+            pc[slot] += t - tprev;
+            tprev = t;
+        }
+    };
     int64_t it = 0;  // chunks issued / consumed so far (TMEM stage = it & 1, phase = (it >> 1) & 1)
     uint32_t tphase = 0;  // parity of the A-tile barrier (one phase per tile)
     // B tiles: NB stages; with two, the load of the next chunk (running over into this CTA's next tile --
@@ -897,6 +909,7 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
             fence_proxy_async();
             __syncwarp();
             if (lane == 0) mbar_arrive(a_ready);
+            lap(0);  // tile staging
         }
         // ... and after it has been rebuilt
         if (ew > 1 && warp < mma_warp) {
@@ -927,12 +940,16 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
                     const uint32_t ph = (uint32_t)((i0 >> 1) & 1);
                     const int sb = (int)(i0 % NB);
                     if (c == 0) {  // the B tiles are in flight while the A tile is still being built
+                        lap(7);
                         mbar_wait(a_ready, tphase);
                         tc_fence_after();
+                        lap(1);  // MMA lane: wait for the A tile
                     }
                     mbar_wait_sel(full_b + 8 * sb, (uint32_t)((i0 / NB) & 1), P.dbg & 16);
+                    lap(2);  // MMA lane: wait for the B tile
                     mbar_wait_sel(tmem_empty + 8 * s, ph ^ 1, P.dbg & 16);
                     tc_fence_after();
+                    lap(3);  // MMA lane: wait for a free accumulator
                     const uint32_t d_addr = tmem_base + (uint32_t)(s * G.nmma);
                     const uint32_t bs_addr = b_addr + sb * G.b_bytes;
                     uint32_t accum = 0u;
@@ -949,6 +966,7 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
                     }
                     umma_commit(empty_b + 8 * sb);   // B stage reusable once these MMAs have read it
                     umma_commit(tmem_full + 8 * s);  // accumulator ready for the epilogue
+                    lap(4);  // MMA lane: descriptor math + issue
                     {
                         // refill: the stage of chunk r (previous chunk, or this one when there is a single
                         // stage) receives chunk r + NB
@@ -966,6 +984,7 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
                             ++loaded;
                         }
                     }
+                    lap(5);  // MMA lane: refill (waits for the previous chunk's MMAs to retire)
                 }
             }
             __syncwarp();
@@ -983,8 +1002,10 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
                 const uint32_t ph = (uint32_t)((i0 >> 1) & 1);
                 const int64_t b0 = c * G.ps + hsub * hp;  // first permutation of this warp's share of the chunk
                 const int nq = (int)max((int64_t)0, min((int64_t)hp, P.G.B - b0));  // valid permutations of the share
+                lap(3);  // epilogue: refinement + bookkeeping of the previous chunk
                 mbar_wait_sel(tmem_full + 8 * s, ph, P.dbg & 16);
                 tc_fence_after();
+                lap(1);  // epilogue: wait for the accumulator
                 const uint32_t taddr =
                     tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s * G.nmma + hsub * hp * PST);
                 // candidate test + work list in one pass: the ballot word of a permutation is warp-uniform,
@@ -1029,6 +1050,7 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(tmem_empty + 8 * s);  // accumulator free: the next MMAs overlap the refinement
+                lap(2);  // epilogue: TMEM loads + candidate scan
                 const int64_t b = b0 + lane;
                 if (nwork == 0) {
                     if (lane < nq && active && !(P.dbg & 8)) {
@@ -1136,6 +1158,10 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
         }
         it += G.chunks;
         tphase ^= 1u;
+    }
+    if (prof && lane == 0 && (warp == 0 || warp == mma_warp) && P.prof) {
+        unsigned long long* dst = P.prof + (warp == mma_warp ? 8 : 0);
+        for (int i = 0; i < 8; ++i) atomicAdd(&dst[i], (unsigned long long)pc[i]);
     }
     tc_fence_before();
     __syncthreads();
@@ -1524,6 +1550,12 @@ int fstat_perm_batch_fused(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& m
     F.e0 = G.j0 ? (float)(sqrt(w_c) * 2.0 * pow((double)cov->n, 1.5) * 2.220446049250313e-16 * 1.000001) : 0.f;
     F.idesc = umma_idesc_bf16(TC_M, G.nmma);
     F.dbg = ctx->opt_dbg;
+    DevBuf<unsigned long long> profbuf;
+    if (F.dbg & 64) {
+        DFB_TRY(profbuf.alloc(ctx, 16));
+        DFB_TRY(profbuf.zero());
+        F.prof = profbuf.p;
+    }
 
     out->rows = B;
     out->W = ceil_div(cov->N, 32);
@@ -1565,6 +1597,15 @@ int fstat_perm_batch_fused(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& m
             default: DFB_TRY(launch_fused<0>(ctx, F, grid)); break;
         }
         DFB_CUDA(cudaGetLastError());
+        if ((F.dbg & 64) && F.prof) {
+            unsigned long long h[16];
+            DFB_TRY(d2h(ctx, h, F.prof, sizeof h));
+            const double ep = (double)grid, ml = (double)grid;
+            fprintf(stderr, "[dfb] fused phases, mean cycles per CTA (epilogue warp 0): staging %.0f  wait-acc %.0f  scan %.0f  refine+rest %.0f\n",
+                    h[0] / ep, h[1] / ep, h[2] / ep, h[3] / ep);
+            fprintf(stderr, "[dfb] fused phases, mean cycles per CTA (MMA lane): wait-A %.0f  wait-B %.0f  wait-acc %.0f  issue %.0f  refill %.0f  other %.0f\n",
+                    h[8 + 1] / ml, h[8 + 2] / ml, h[8 + 3] / ml, h[8 + 4] / ml, h[8 + 5] / ml, h[8 + 7] / ml);
+        }
         out->capacity = cap;
         if (defer_check) {
             // the caller synchronises anyway (region counts): it checks *used_host <= capacity then
