@@ -642,6 +642,7 @@ struct FusedGeom {
     int KB;             // 64-element K blocks of the stored [hi | lo] rows (2*npad elements)
     int p, p0, j0, pe, pst;  // model columns, first column used by the screen, columns screened, TMEM stride
     int ps, nmma;       // permutations per chunk, MMA N = ps * pst
+    int tmem_cols;      // TMEM allocation: two accumulator stages, rounded up to a power of two
     int qs, ixs;        // Qs row stride (doubles), bytes per row of the byte permutation table
     int nb;             // B tile stages: 1 when the tile is small (occupancy first), else 2
     int ew;             // epilogue warps per TMEM lane quarter (1, 2 or 4)
@@ -734,6 +735,58 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// no-wait TMEM loads (32 lanes x N consecutive 32-bit columns); tmem_ld_wait() completes them
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8_nw(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_nw(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, "
+        "[%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_nw(uint32_t taddr, uint32_t* r) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+// NC consecutive columns (multiple of 8, <= 64) as the fewest loads, all in flight before the wait
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* r) {
+    static_assert(NC % 8 == 0 && NC >= 8 && NC <= 64, "column count");
+    int c = 0;
+    if (NC >= 32) {
+        tmem_ld32_nw(taddr, r);
+        c = 32;
+        if (NC == 64) {
+            tmem_ld32_nw(taddr + 32u, r + 32);
+            c = 64;
+        }
+    }
+    if (NC - c >= 16) {
+        tmem_ld16_nw(taddr + (uint32_t)c, r + c);
+        c += 16;
+    }
+    if (NC - c >= 8) tmem_ld8_nw(taddr + (uint32_t)c, r + c);
+    tmem_ld_wait();
+}
+
+// permutations per epilogue pass for a column stride of `pcols` (host and device agree on this)
+__host__ __device__ constexpr int fz_pass_perms(int pcols) { return pcols <= 4 ? 16 : (pcols <= 8 ? 8 : 2); }
+
 // PT: number of model columns (2..8) or 0 = generic; J0: 1 when the constant column is not screened
 // Thread layout: EW epilogue warps per 32-lane TMEM quarter (warp w: quarter w & 3, share h = w >> 2
 // of the chunk's permutations), then one producer / MMA warp (index 4 * EW).  With one CTA per SM
@@ -744,8 +797,11 @@ constexpr int FZ_MAX_THREADS = 4 * 128 + 32;
 template <int PT, int J0>
 __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedParams P) {
     constexpr int PCOLS = PT > 0 ? PT - J0 : 16;
-    constexpr int PST = PCOLS <= 2 ? 2 : (PCOLS <= 4 ? 4 : (PCOLS <= 8 ? 8 : 16));
-    constexpr int per16 = 16 / PST;
+    // TMEM column stride per permutation = the number of screened columns: no padded columns in the
+    // B tile, the MMA or the accumulator (5 of 8 columns used to be real for p = 6)
+    constexpr int PST = PCOLS;
+    constexpr int PP = fz_pass_perms(PCOLS);  // permutations per epilogue pass
+    constexpr int NC = PP * PCOLS;            // TMEM columns per pass (multiple of 8, <= 64)
     extern __shared__ __align__(1024) unsigned char smem_fz_raw[];
     unsigned char* sm = smem_fz_raw + ((1024u - (smem_u32(smem_fz_raw) & 1023u)) & 1023u);
     const FusedGeom& G = P.G;
@@ -765,6 +821,8 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
     float* thr_s = reinterpret_cast<float*>(sm + G.off_thr);  // [128] candidate thresholds
     uint64_t* bars = reinterpret_cast<uint64_t*>(sm + G.off_bar);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* mma_a = bars + 14;   // [3 * nk16] A descriptors of a chunk's MMA sequence
+    uint64_t* mma_b = mma_a + 48;  // [3 * nk16] B descriptors relative to stage 0
     const uint32_t full_b = smem_u32(bars + 0), empty_b = smem_u32(bars + 4), a_ready = smem_u32(bars + 12);
     const uint32_t tmem_full = smem_u32(bars + 8), tmem_empty = smem_u32(bars + 10);
     const int NB = G.nb;  // B stages (1 .. 4)
@@ -786,9 +844,20 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
                 mbar_init(tmem_empty + 8 * s, (uint32_t)(4 * ew));
             }
             fence_barrier_init();
+            // MMA sequence of a chunk: for every 16-wide K step  hi*qh, hi*ql, lo*qh
+            const uint32_t a_addr0 = smem_u32(As), b_addr0 = smem_u32(Bs);
+            for (int t = 0; t < G.nk16; ++t)
+                for (int term = 0; term < 3; ++term) {
+                    const int acol = (term == 2 ? G.npad : 0) + 16 * t;
+                    const int bcol = (term == 1 ? G.npad : 0) + 16 * t;
+                    mma_a[3 * t + term] =
+                        umma_desc_sw128(a_addr0 + (uint32_t)(acol >> 6) * TC_M * 128u + (uint32_t)(acol & 63) * 2u);
+                    mma_b[3 * t + term] =
+                        umma_desc_sw128(b_addr0 + (uint32_t)(bcol >> 6) * G.nmma * 128u + (uint32_t)(bcol & 63) * 2u);
+                }
         }
         __syncwarp();
-        tmem_alloc(smem_u32(tmem_slot), (uint32_t)(2 * G.nmma));
+        tmem_alloc(smem_u32(tmem_slot), (uint32_t)G.tmem_cols);
     } else {
         for (int e = tid; e < n * qs; e += 128 * ew) {
             const int k = e / qs, j = e - k * qs;
@@ -816,14 +885,23 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
     };
     int64_t it = 0;  // chunks issued / consumed so far (TMEM stage = it & 1, phase = (it >> 1) & 1)
     uint32_t tphase = 0;  // parity of the A-tile barrier (one phase per tile)
-    // B tiles: NB stages; with two, the load of the next chunk (running over into this CTA's next tile --
-    // the B operand does not depend on the tile) overlaps the MMAs of the current one.  `loaded` counts
-    // the bulk copies issued by this CTA.
-    const int64_t my_tiles = blockIdx.x < G.tiles ? (G.tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
-    const int64_t total_chunks = my_tiles * G.chunks;
-    int64_t loaded = 0;
     const uint32_t lt_mask = (1u << lane) - 1u;
-
+    // producer state (MMA lane only): incremental stage indices and barrier parities
+    struct {
+        int sb = 0, s = 0;               // B stage / accumulator stage of the next chunk
+        uint32_t full_par = 0;           // bit sb: parity the next wait on full_b[sb] expects
+        uint32_t empty_par = 0;          // bit sb: parity the next refill wait on empty_b[sb] expects
+        uint32_t acc_par = 0;            // bit s: parity of the accumulator hand-off
+        int load_stage = 0;              // stage the next refill goes to
+        int load_stage_fill = 0;         // prologue counter
+        int load_chunk = 0;              // permutation chunk the next load fetches (B does not depend on the tile)
+        int64_t loads_left = 0;          // bulk copies this CTA still has to issue
+        bool started = false;
+    } pl;
+    {
+        const int64_t my_tiles = blockIdx.x < G.tiles ? (G.tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+        pl.loads_left = my_tiles * G.chunks;
+    }
     for (int64_t tile = blockIdx.x; tile < G.tiles; tile += gridDim.x) {
         const int64_t base0 = tile * TC_M;
         float thr = __int_as_float(0x7f800000);  // +inf: rows beyond N never pass
@@ -918,72 +996,68 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
         }
 
         if (warp == mma_warp) {
-            // ===== producer + MMA issuer (one lane).  B tiles are small and L2-resident: one stage,
-            // reloaded as soon as the MMAs of the previous chunk have consumed it. =====
+            // ===== producer + MMA issuer (one lane).  This single thread is on the critical path of every
+            // chunk, so its loop carries no divisions and no descriptor arithmetic: stage indices and
+            // barrier parities are incremental, the MMA descriptors come from a table built once.
+            // B tiles: the first NB are requested up front; afterwards the stage of the PREVIOUS chunk is
+            // refilled right after the MMAs of the current one have been issued, so waiting for the
+            // previous chunk's MMAs to retire overlaps the execution of the current ones. =====
             if (lane == 0) {
-                const uint32_t a_addr = smem_u32(As), b_addr = smem_u32(Bs);
+                const uint32_t b_addr = smem_u32(Bs);
                 const unsigned char* src = P.qb;
-                // B tile loads never sit between the MMAs of consecutive chunks: the first NB tiles are
-                // requested up front, afterwards the stage of the PREVIOUS chunk is refilled right after the
-                // MMAs of the current one have been issued -- waiting for the previous chunk's MMAs to
-                // retire then overlaps the execution of the current ones instead of stalling their issue.
-                while (loaded < total_chunks && loaded < NB) {
-                    const int sb1 = (int)loaded;
-                    mbar_expect_tx(full_b + 8 * sb1, G.b_bytes);
-                    bulk_g2s(b_addr + sb1 * G.b_bytes, src + (size_t)(loaded % G.chunks) * G.b_bytes, G.b_bytes,
-                             full_b + 8 * sb1);
-                    ++loaded;
+                if (it == 0) {  // first tile of this CTA: prologue loads
+                    while (pl.loads_left > 0 && pl.load_stage_fill < NB) {
+                        const int sb1 = pl.load_stage_fill;
+                        mbar_expect_tx(full_b + 8 * sb1, G.b_bytes);
+                        bulk_g2s(b_addr + sb1 * G.b_bytes, src + (size_t)pl.load_chunk * G.b_bytes, G.b_bytes,
+                                 full_b + 8 * sb1);
+                        pl.load_chunk = pl.load_chunk + 1 == (int)G.chunks ? 0 : pl.load_chunk + 1;
+                        ++pl.load_stage_fill;
+                        --pl.loads_left;
+                    }
                 }
+                const int nmm = (P.dbg & 2) ? 3 : 3 * G.nk16;
                 for (int64_t c = 0; c < G.chunks; ++c) {
-                    const int64_t i0 = it + c;
-                    const int s = (int)(i0 & 1);
-                    const uint32_t ph = (uint32_t)((i0 >> 1) & 1);
-                    const int sb = (int)(i0 % NB);
                     if (c == 0) {  // the B tiles are in flight while the A tile is still being built
                         lap(7);
                         mbar_wait(a_ready, tphase);
                         tc_fence_after();
                         lap(1);  // MMA lane: wait for the A tile
                     }
-                    mbar_wait_sel(full_b + 8 * sb, (uint32_t)((i0 / NB) & 1), P.dbg & 16);
+                    const int sb = pl.sb, s = pl.s;
+                    mbar_wait_sel(full_b + 8 * sb, (pl.full_par >> sb) & 1u, P.dbg & 16);
+                    pl.full_par ^= 1u << sb;
                     lap(2);  // MMA lane: wait for the B tile
-                    mbar_wait_sel(tmem_empty + 8 * s, ph ^ 1, P.dbg & 16);
+                    mbar_wait_sel(tmem_empty + 8 * s, ((pl.acc_par >> s) & 1u) ^ 1u, P.dbg & 16);
+                    pl.acc_par ^= 1u << s;
                     tc_fence_after();
                     lap(3);  // MMA lane: wait for a free accumulator
                     const uint32_t d_addr = tmem_base + (uint32_t)(s * G.nmma);
-                    const uint32_t bs_addr = b_addr + sb * G.b_bytes;
-                    uint32_t accum = 0u;
-                    for (int t = 0; t < ((P.dbg & 2) ? 1 : G.nk16); ++t) {
-#pragma unroll
-                        for (int term = 0; term < 3; ++term) {
-                            const int acol = (term == 2 ? G.npad : 0) + 16 * t;
-                            const int bcol = (term == 1 ? G.npad : 0) + 16 * t;
-                            const uint64_t ad = umma_desc_sw128(a_addr + (uint32_t)(acol >> 6) * TC_M * 128u + (uint32_t)(acol & 63) * 2u);
-                            const uint64_t bd = umma_desc_sw128(bs_addr + (uint32_t)(bcol >> 6) * G.nmma * 128u + (uint32_t)(bcol & 63) * 2u);
-                            umma_bf16(d_addr, ad, bd, P.idesc, accum);
-                            accum = 1u;
-                        }
-                    }
+                    const uint64_t bstage = (uint64_t)(((uint32_t)sb * G.b_bytes) >> 4);  // start-address field offset
+#pragma unroll 3
+                    for (int i = 0; i < nmm; ++i) umma_bf16(d_addr, mma_a[i], mma_b[i] + bstage, P.idesc, i ? 1u : 0u);
                     umma_commit(empty_b + 8 * sb);   // B stage reusable once these MMAs have read it
                     umma_commit(tmem_full + 8 * s);  // accumulator ready for the epilogue
-                    lap(4);  // MMA lane: descriptor math + issue
-                    {
-                        // refill: the stage of chunk r (previous chunk, or this one when there is a single
-                        // stage) receives chunk r + NB
-                        const int64_t r = i0 - (NB > 1 ? 1 : 0);
-                        if (r >= 0 && loaded < total_chunks && loaded == r + NB) {
-                            const int sb1 = (int)(r % NB);
-                            mbar_wait(empty_b + 8 * sb1, (uint32_t)((r / NB) & 1));  // MMAs of chunk r have read it
-                            if ((P.dbg & 1)) {
-                                mbar_arrive(full_b + 8 * sb1);  // experiment: keep the tile already in the stage
-                            } else {
-                                mbar_expect_tx(full_b + 8 * sb1, G.b_bytes);
-                                bulk_g2s(b_addr + sb1 * G.b_bytes, src + (size_t)(loaded % G.chunks) * G.b_bytes,
-                                         G.b_bytes, full_b + 8 * sb1);
-                            }
-                            ++loaded;
+                    lap(4);  // MMA lane: issue
+                    // refill the stage of the previous chunk (of this one when there is a single stage)
+                    if (pl.loads_left > 0 && (NB == 1 || pl.started)) {
+                        const int sb1 = pl.load_stage;
+                        mbar_wait(empty_b + 8 * sb1, (pl.empty_par >> sb1) & 1u);  // its MMAs have retired
+                        pl.empty_par ^= 1u << sb1;
+                        if (P.dbg & 1) {
+                            mbar_arrive(full_b + 8 * sb1);  // experiment: keep the tile already in the stage
+                        } else {
+                            mbar_expect_tx(full_b + 8 * sb1, G.b_bytes);
+                            bulk_g2s(b_addr + sb1 * G.b_bytes, src + (size_t)pl.load_chunk * G.b_bytes, G.b_bytes,
+                                     full_b + 8 * sb1);
                         }
+                        pl.load_chunk = pl.load_chunk + 1 == (int)G.chunks ? 0 : pl.load_chunk + 1;
+                        pl.load_stage = sb1 + 1 == NB ? 0 : sb1 + 1;
+                        --pl.loads_left;
                     }
+                    pl.started = true;
+                    pl.sb = sb + 1 == NB ? 0 : sb + 1;
+                    pl.s = s ^ 1;
                     lap(5);  // MMA lane: refill (waits for the previous chunk's MMAs to retire)
                 }
             }
@@ -1014,31 +1088,34 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
                 // ballots, and only then the (rare for stringent cutoffs) non-empty words are appended: no
                 // vote -> branch dependency between consecutive permutations.
                 int nwork = 0;
-                constexpr int NPL = 2 * per16;  // permutations per 32-column load
-                for (int g = 0; g * per16 < ((P.dbg & 4) ? 0 : nq); g += 2) {
-                    float v[32];
-                    tmem_ld32(taddr + (uint32_t)(g * 16), v);
-                    const bool full = (g + 2) * per16 <= nq;  // warp-uniform: no padded permutation in this load
-                    unsigned words[NPL];
+                for (int q0 = 0; q0 < ((P.dbg & 4) ? 0 : nq); q0 += PP) {
+                    uint32_t vr[NC];
+                    tmem_ld_cols<NC>(taddr + (uint32_t)(q0 * PST), vr);
+                    const bool full = q0 + PP <= nq;  // warp-uniform: no padded permutation in this pass
+                    unsigned words[PP];
                     unsigned any = 0u;
 #pragma unroll
-                    for (int qq = 0; qq < NPL; ++qq) {
-                        float a = v[qq * PST] * v[qq * PST];
+                    for (int qq = 0; qq < PP; ++qq) {
+                        const float v0 = __uint_as_float(vr[qq * PST]);
+                        float a = v0 * v0;
 #pragma unroll
-                        for (int j = 1; j < PCOLS; ++j) a = fmaf(v[qq * PST + j], v[qq * PST + j], a);
+                        for (int j = 1; j < PCOLS; ++j) {
+                            const float vj = __uint_as_float(vr[qq * PST + j]);
+                            a = fmaf(vj, vj, a);
+                        }
                         words[qq] = __ballot_sync(0xffffffffu, a >= thr);
                     }
                     if (!full) {
 #pragma unroll
-                        for (int qq = 0; qq < NPL; ++qq)
-                            if (g * per16 + qq >= nq) words[qq] = 0u;
+                        for (int qq = 0; qq < PP; ++qq)
+                            if (q0 + qq >= nq) words[qq] = 0u;
                     }
 #pragma unroll
-                    for (int qq = 0; qq < NPL; ++qq) any |= words[qq];
+                    for (int qq = 0; qq < PP; ++qq) any |= words[qq];
                     if (any) {
-                        const uint16_t ent0 = (uint16_t)(((g * per16) << 5) | lane);
+                        const uint16_t ent0 = (uint16_t)((q0 << 5) | lane);
 #pragma unroll
-                        for (int qq = 0; qq < NPL; ++qq) {
+                        for (int qq = 0; qq < PP; ++qq) {
                             const unsigned word = words[qq];
                             if (word) {
                                 if ((word >> lane) & 1u) list_w[nwork + __popc(word & lt_mask)] = (uint16_t)(ent0 + (qq << 5));
@@ -1091,8 +1168,8 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
                             double S[PT > 0 ? PT : 1];
 #pragma unroll
                             for (int j = 0; j < PT; ++j) S[j] = 0.0;
-#pragma unroll 4
                             const double mrow = ys_smem ? 0.0 : mw[bl];
+#pragma unroll 4
                             for (int k = 0; k < n; ++k) {
                                 const double yv = ys_smem ? ycol[(size_t)k * TC_M + bl]
                                                           : __dsub_rn(yglob[(size_t)k * P.ld + bl], mrow);
@@ -1165,7 +1242,7 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == mma_warp) tmem_dealloc(tmem_base, (uint32_t)(2 * G.nmma));
+    if (warp == mma_warp) tmem_dealloc(tmem_base, (uint32_t)G.tmem_cols);
 }
 
 __global__ void popcount_words_kernel(const uint32_t* __restrict__ w, int64_t n, unsigned long long* __restrict__ out) {
@@ -1421,9 +1498,14 @@ static bool fused_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
     G.j0 = (mb.p <= 8 && constant_first_column(mb)) ? 1 : 0;
     G.pe = mb.p - G.j0;
     if (mb.p > 16) return false;
-    G.pst = mb.p > 8 ? 16 : (G.pe <= 2 ? 2 : (G.pe <= 4 ? 4 : 8));
-    G.ps = G.pst <= 4 ? 32 : (G.pst == 8 ? 16 : 8);
+    // TMEM / B-tile column stride per permutation: exactly the screened columns for the templated
+    // kernels (p <= 8), 16 (zero padded) for the generic one.  nmma = ps * pst is a multiple of 16.
+    G.pst = mb.p > 8 ? 16 : G.pe;
+    G.ps = mb.p > 8 ? 8 : (G.pst <= 4 ? 32 : 16);
     G.nmma = G.ps * G.pst;
+    if (G.nmma < 16) return false;
+    G.tmem_cols = 32;
+    while (G.tmem_cols < 2 * G.nmma) G.tmem_cols *= 2;
     G.qs = mb.p <= 8 ? ((mb.p + 1) & ~1) : mb.p;
     G.ixs = (int)round_up(G.n, 16);
     G.B = B;
@@ -1461,7 +1543,7 @@ static bool fused_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
     G.off_thr = o;
     o += TC_M * 4u;
     G.off_bar = o;
-    o += 14 * 8 + 16;
+    o += (14 + 96) * 8 + 16;
     o = (uint32_t)round_up(o, 16);
     G.off_warp = o;
     // epilogue warps per quarter: one when several CTAs share an SM anyway (small tiles); otherwise as
@@ -1475,8 +1557,9 @@ static bool fused_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
         // knob stays for the deeper pipeline ("next")
         (void)single_cta;
         int want = ctx->opt_epi_warps > 0 ? ctx->opt_epi_warps : 1;
-        G.ew = std::max(1, std::min(want, G.nmma / 32));
-        while (G.ps % G.ew) --G.ew;
+        const int pp = fz_pass_perms(G.pst);
+        G.ew = std::max(1, std::min(want, G.ps / pp));
+        while (G.ps % G.ew || (G.ps / G.ew) % pp) --G.ew;
     }
     const int hp = G.ps / G.ew;
     G.warp_bytes = (uint32_t)round_up(hp * 32 * 2 + 32 * 4 + hp * G.ixs, 16);
@@ -1567,7 +1650,7 @@ int fstat_perm_batch_fused(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& m
     DFB_TRY(cursor.alloc(ctx, 1));
     // persistent grid: CTAs per SM limited by shared memory and by TMEM columns (512 per SM)
     const int threads = 128 * G.ew + 32;
-    int per_sm = (int)std::min<size_t>((size_t)(227 * 1024) / (G.smem + 1024), (size_t)(512 / (2 * G.nmma)));
+    int per_sm = (int)std::min<size_t>((size_t)(227 * 1024) / (G.smem + 1024), (size_t)(512 / G.tmem_cols));
     per_sm = std::min(per_sm, 65536 / (threads * 100));  // registers (the kernels compile to <= 100)
     per_sm = std::max(1, std::min(per_sm, 6));
     const int grid = (int)std::min<int64_t>(G.tiles, (int64_t)ctx->sm_count * per_sm);
