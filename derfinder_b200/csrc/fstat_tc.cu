@@ -1485,7 +1485,25 @@ static bool constant_first_column(const ModelBasis& mb) {
     return c0 != 0.0;
 }
 
+static bool fused_geometry_ps(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, int64_t B, int force_ps,
+                              FusedGeom* g);
+
+// Chunk width.  Small models (<= 4 screened columns: small tiles, several CTAs per SM) use 32
+// permutations per chunk.  Larger ones are bound by the tcgen05.mma instruction rate -- an M = 128,
+// K = 16 instruction costs ~130 cycles whether N is 80 or 240 (measured) -- so the widest
+// chunk whose two accumulator stages fit TMEM (N <= 240) and whose B stages fit shared memory wins.
 static bool fused_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, int64_t B, FusedGeom* g) {
+    if (ctx->opt_chunk_perms > 0) return fused_geometry_ps(ctx, cov, mb, B, ctx->opt_chunk_perms, g);
+    const int pe = mb.p - ((mb.p <= 8 && constant_first_column(mb)) ? 1 : 0);
+    if (mb.p <= 8 && pe >= 5) {
+        for (int ps = 48; ps >= 24; ps -= 8)
+            if (ps * pe <= 240 && fused_geometry_ps(ctx, cov, mb, B, ps, g)) return true;
+    }
+    return fused_geometry_ps(ctx, cov, mb, B, 0, g);
+}
+
+static bool fused_geometry_ps(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, int64_t B, int force_ps,
+                              FusedGeom* g) {
     FusedGeom G;
     memset(&G, 0, sizeof G);
     G.n = cov->n;
@@ -1502,8 +1520,14 @@ static bool fused_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
     // kernels (p <= 8), 16 (zero padded) for the generic one.  nmma = ps * pst is a multiple of 16.
     G.pst = mb.p > 8 ? 16 : G.pe;
     G.ps = mb.p > 8 ? 8 : (G.pst <= 4 ? 32 : 16);
+    if (force_ps > 0) {  // permutations per chunk (multiple of the pass size)
+        const int pp = fz_pass_perms(G.pst);
+        G.ps = std::max(pp, (force_ps / pp) * pp);
+        while (G.ps * G.pst > 256 || (G.ps * G.pst) % 16) G.ps -= pp;
+        if (G.ps < pp) return false;
+    }
     G.nmma = G.ps * G.pst;
-    if (G.nmma < 16) return false;
+    if (G.nmma < 16 || G.nmma > 256) return false;
     G.tmem_cols = 32;
     while (G.tmem_cols < 2 * G.nmma) G.tmem_cols *= 2;
     G.qs = mb.p <= 8 ? ((mb.p + 1) & ~1) : mb.p;
@@ -1519,7 +1543,9 @@ static bool fused_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
     {
         const size_t ys_bytes = (size_t)G.n * TC_M * 8;
         const size_t rest = (size_t)G.a_bytes + 2 * (size_t)G.b_bytes + (size_t)G.n * G.qs * 8 + 16 * 1024;
-        G.ys_smem = (ctx->opt_ys_smem >= 0) ? ctx->opt_ys_smem : (2 * (rest + ys_bytes) <= (size_t)225 * 1024 ? 1 : 0);
+        const bool single = G.tmem_cols > 256;  // the accumulators alone limit the SM to one CTA
+        const bool fits = single ? (rest + ys_bytes <= (size_t)225 * 1024) : (2 * (rest + ys_bytes) <= (size_t)225 * 1024);
+        G.ys_smem = (ctx->opt_ys_smem >= 0) ? ctx->opt_ys_smem : (fits ? 1 : 0);
         if (!G.ys_smem && rest > (size_t)225 * 1024) return false;
     }
     uint32_t o = G.a_bytes;
@@ -1529,7 +1555,8 @@ static bool fused_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
     else if (G.b_bytes > 16 * 1024) {
         // as many stages as fit (<= 3): a 32 KiB bulk copy out of L2 takes longer than its MMAs
         const size_t fixed = (size_t)G.a_bytes + (G.ys_smem ? (size_t)G.n * TC_M * 8 : 0) + (size_t)G.n * G.qs * 8 + 20 * 1024;
-        const size_t budget = G.ys_smem ? (size_t)224 * 1024 : (size_t)112 * 1024;  // streamed: leave room for 2 CTAs
+        // streamed tile with small accumulators: leave room for a second CTA
+        const size_t budget = (G.ys_smem || G.tmem_cols > 256) ? (size_t)224 * 1024 : (size_t)112 * 1024;
         G.nb = 2;
         while (G.nb < 3 && fixed + (size_t)(G.nb + 1) * G.b_bytes <= budget) ++G.nb;
     }
@@ -1558,8 +1585,11 @@ static bool fused_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
         (void)single_cta;
         int want = ctx->opt_epi_warps > 0 ? ctx->opt_epi_warps : 1;
         const int pp = fz_pass_perms(G.pst);
-        G.ew = std::max(1, std::min(want, G.ps / pp));
-        while (G.ps % G.ew || (G.ps / G.ew) % pp) --G.ew;
+        if (ctx->opt_epi_warps <= 0 && G.ps > 32) want = std::min(4, G.ps / 16);  // wide chunks: ~16 permutations per warp
+        want = std::max(want, (G.ps + 31) / 32);  // a warp's share of a chunk is at most 32 permutations (lane = permutation)
+        G.ew = std::max(1, std::min(std::min(want, 4), G.ps / pp));
+        while (G.ew > 1 && (G.ps % G.ew || (G.ps / G.ew) % pp)) --G.ew;
+        if (G.ps / G.ew > 32) return false;
     }
     const int hp = G.ps / G.ew;
     G.warp_bytes = (uint32_t)round_up(hp * 32 * 2 + 32 * 4 + hp * G.ixs, 16);
