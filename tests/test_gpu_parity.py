@@ -291,7 +291,9 @@ def assert_pipeline_equal(res, ores):
 @pytest.mark.parametrize("n,extra,N,B,seg", [(12, 0, 20000, 12, [7000, 33, 5000, 7967]),
                                              (31, 1, 6000, 7, [6000]),
                                              (60, 3, 3000, 5, [1, 31, 32, 33, 2903]),
-                                             (10, 0, 70001, 9, [20000, 50001])])
+                                             (10, 0, 70001, 9, [20000, 50001]),
+                                             (24, 3, 5000, 100, [5000]),    # wide chunks: 48 + 48 + 4 permutations
+                                             (20, 5, 4000, 70, [4000])])    # p = 8: 32-permutation chunks of 224 columns
 def test_pipeline_vs_oracle(dfb, eng, n, extra, N, B, seg):
     rng = np.random.default_rng(n * 7 + B)
     cov, position, group, models = synth(rng, N, n, p_extra=extra, seg=seg)
