@@ -462,8 +462,9 @@ int dfb_fstats(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const doubl
     cov->has_f = false;
     if (cov->N > 0) DFB_TRY(fstat_observed(ctx, cov, mb, adjust_f, cov->fstats.p));
     cov->has_f = true;
+    // without a host destination the statistics stay on the device and the call returns without
+    // synchronising: everything it enqueued is stream-ordered (the basis was staged by the copy)
     if (fstats_out) DFB_TRY(d2h_big(ctx, fstats_out, cov->fstats.p, (size_t)cov->N * sizeof(double)));
-    else DFB_CUDA(cudaStreamSynchronize(ctx->stream));
     return DFB_OK;
 }
 
