@@ -143,8 +143,13 @@ static int ensure_staging(dfb_ctx* ctx) {
     ctx->pinned_bytes = NSTAGE * STAGE_BYTES;
     for (int i = 0; i < NSTAGE; ++i) DFB_CUDA(cudaEventCreateWithFlags(&ctx->stage_ev[i], cudaEventDisableTiming));
     if (!ctx->pool) {
+        // half the cores, at most 8 -- shared between the processes of one node (one per GPU): the
+        // launcher's LOCAL_WORLD_SIZE tells how many there are.  Spinning workers of 8 ranks on a
+        // 16-core host would otherwise starve each other.
         unsigned hc = std::thread::hardware_concurrency();
-        int nt = (int)std::min<unsigned>(8, std::max<unsigned>(1, hc / 2));
+        unsigned share = 1;
+        if (const char* e = getenv("LOCAL_WORLD_SIZE")) share = (unsigned)std::max(1, atoi(e));
+        int nt = (int)std::min<unsigned>(8, std::max<unsigned>(1, hc / (2 * share)));
         if (const char* e = getenv("DFB_COPY_THREADS")) nt = std::max(1, std::min(64, atoi(e)));
         ctx->pool = new CopyPool(nt);
     }
