@@ -175,7 +175,7 @@ class ClockSampler(threading.Thread):
                 for bit, nm in names.items():
                     if r & bit:
                         self.reasons.add(nm)
-                time.sleep(0.02)
+                time.sleep(0.002)
         except Exception as e:  # NVML missing: report that instead of inventing clocks
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -384,7 +384,7 @@ class Step:
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
