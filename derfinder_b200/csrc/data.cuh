@@ -53,6 +53,14 @@ struct dfb_regions {
     // device copies of the index ranges (kept for view means / region matrix) and of the areas
     dfb::DevBuf<int32_t> d_is, d_ie;
     dfb::DevBuf<double> d_area;
+    // asynchronous read-backs not yet copied into the vectors above (pinned arena memory)
+    struct Pending {
+        const int32_t *gs = nullptr, *ge = nullptr, *cf = nullptr;
+        const double* cl = nullptr;
+        const double *val = nullptr, *area = nullptr;
+        const int32_t *is = nullptr, *ie = nullptr;
+        bool active = false;
+    } pend;
     dfb::DevBuf<double> d_area_desc;  // areas in decreasing order (after dfb_calculate_pvalues)
     dfb::DevBuf<int32_t> d_order;     // d_area_desc[i] = d_area[d_order[i]]
 };
@@ -131,7 +139,9 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
                       const double* dense, int64_t dense_stride, const PermBatch* compact, bool want_index,
                       bool want_perm, RegionSet* out);
 int find_regions_dense(dfb_ctx* ctx, const double* x_dev, const PositionIndex& pos, double lo, double hi,
-                       int32_t max_region_gap, int32_t max_cluster_gap, bool basic, dfb_regions** out);
+                       int32_t max_region_gap, int32_t max_cluster_gap, bool basic, dfb_regions** out,
+                       bool defer = false);
+int finalize_regions(dfb_ctx* ctx, dfb_regions* r);
 int build_segment_starts(dfb_ctx* ctx, const PositionIndex& pos, int32_t max_region_gap, DevBuf<uint32_t>* seg);
 
 }  // namespace dfb

@@ -728,10 +728,14 @@ int dfb_calculate_pvalues(dfb_ctx* ctx, dfb_cov* cov, const double* fstats, cons
     }
     dfb_regions* r = nullptr;
     int rc = find_regions_dense(ctx, cov->fstats.p, cov->pos, cutoff_lo, cutoff_hi, max_region_gap, max_cluster_gap,
-                                false, &r);
+                                false, &r, /*defer=*/true);
     if (rc != DFB_OK) return rc;  // DFB_ENOREGIONS: list(regions = NULL, ...) (:245-251)
     dfb_nulls* nl = nullptr;
     rc = perm_nulls_impl(ctx, cov, mod, p, mod0, p0, adjust_f, perm_idx, B, cutoff_lo, cutoff_hi, max_region_gap, &nl);
+    if (rc >= 0) {
+        rc = finalize_regions(ctx, r);  // the observed-region tables arrived while the null scan ran
+        if (rc < 0) delete nl;
+    }
     if (rc < 0) {
         delete r;
         return rc;

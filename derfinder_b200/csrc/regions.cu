@@ -519,7 +519,7 @@ __global__ void view_means_kernel(const double* __restrict__ v, const int32_t* _
 // observed regions from a dense device vector
 
 int find_regions_dense(dfb_ctx* ctx, const double* x_dev, const PositionIndex& pos, double lo, double hi,
-                       int32_t max_region_gap, int32_t max_cluster_gap, bool basic, dfb_regions** out) {
+                       int32_t max_region_gap, int32_t max_cluster_gap, bool basic, dfb_regions** out, bool defer) {
     *out = nullptr;
     const int64_t N = pos.N;
     if (N == 0 || pos.K == 0) return DFB_ENOREGIONS;  // warning("Found no regions") :162-165
@@ -582,26 +582,49 @@ int find_regions_dense(dfb_ctx* ctx, const double* x_dev, const PositionIndex& p
     const double* h_area = d2h_async_pinned(ctx, rs.area.p, R);
     const int32_t* h_is = d2h_async_pinned(ctx, rs.istart.p, R);
     const int32_t* h_ie = d2h_async_pinned(ctx, rs.iend.p, R);
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess || !h_val || !h_area || !h_is || !h_ie || (!basic && (!h_gs || !h_ge || !h_cf || !h_cl))) {
-        set_error("find_regions: %s", e != cudaSuccess ? cudaGetErrorString(e) : "pinned read-back failed");
+    if (!h_val || !h_area || !h_is || !h_ie || (!basic && (!h_gs || !h_ge || !h_cf || !h_cl))) {
+        set_error("find_regions: pinned read-back failed");
         delete r;
         return DFB_ECUDA;
     }
-    r->value.assign(h_val, h_val + R);
-    r->area.assign(h_area, h_area + R);
-    r->index_start.assign(h_is, h_is + R);
-    r->index_end.assign(h_ie, h_ie + R);
-    if (!basic) {
-        r->start.assign(h_gs, h_gs + R);
-        r->end.assign(h_ge, h_ge + R);
-        r->cluster.assign(h_cf, h_cf + R);
-        r->cluster_l.assign(h_cl, h_cl + R);
-    }
+    r->pend = {h_gs, h_ge, h_cf, h_cl, h_val, h_area, h_is, h_ie, true};
     r->d_area = std::move(rs.area);
     r->d_is = std::move(rs.istart);
     r->d_ie = std::move(rs.iend);
+    if (!defer) {
+        int rc = finalize_regions(ctx, r);
+        if (rc < 0) {
+            delete r;
+            return rc;
+        }
+    }
     *out = r;
+    return DFB_OK;
+}
+
+// Second half of find_regions_dense: wait for the asynchronous read-backs and fill the host
+// vectors.  dfb_calculate_pvalues defers it until the permutation scan has been enqueued, so the
+// device never idles while the host copies region tables around.
+int finalize_regions(dfb_ctx* ctx, dfb_regions* r) {
+    if (!r->pend.active) return DFB_OK;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        set_error("find_regions: %s", cudaGetErrorString(e));
+        return DFB_ECUDA;
+    }
+    const size_t R = (size_t)r->R;
+    const auto& p = r->pend;
+    r->value.assign(p.val, p.val + R);
+    r->area.assign(p.area, p.area + R);
+    r->index_start.assign(p.is, p.is + R);
+    r->index_end.assign(p.ie, p.ie + R);
+    if (!r->basic) {
+        r->start.assign(p.gs, p.gs + R);
+        r->end.assign(p.ge, p.ge + R);
+        r->cluster.assign(p.cf, p.cf + R);
+        r->cluster_l.assign(p.cl, p.cl + R);
+    }
+    r->pend.active = false;
     return DFB_OK;
 }
 
