@@ -8,6 +8,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "data.cuh"
 
@@ -51,11 +52,15 @@ __device__ __forceinline__ int64_t find_run(const int64_t* __restrict__ cum, int
     return lo;
 }
 
-template <typename V, int PASS>
+// NORM: the library-size divisor (mapped) is present.  The division is then done ONCE PER RUN while
+// the tile is expanded (a run's value is the same for all its positions), not once per position.
+template <typename V, int PASS, bool NORM>
 __global__ void __launch_bounds__(K1_THREADS) filter_tile_kernel(const FilterParams P) {
+    using S = typename std::conditional<NORM || sizeof(V) == 8, double, int32_t>::type;  // staged element
     extern __shared__ int64_t smem_k1[];
-    int64_t* r0 = smem_k1;          // [n] run containing the tile start
-    int64_t* r1 = smem_k1 + P.rle.n;  // [n] run containing the tile end
+    int64_t* r0 = smem_k1;                // [n] run containing the tile start
+    int64_t* r1 = smem_k1 + P.rle.n;      // [n] run containing the tile end
+    int64_t* cb_s = smem_k1 + 2 * P.rle.n;  // [n] prefix-sum base of the sample (cum[run_off[s]])
     __shared__ int wsum[K1_THREADS / 32];
     __shared__ int uniform_keep;
     const int n = P.rle.n;
@@ -76,6 +81,7 @@ __global__ void __launch_bounds__(K1_THREADS) filter_tile_kernel(const FilterPar
             const int64_t b = find_run(cum, cb, a, hi, t1 - 1);
             r0[s] = a;
             r1[s] = b;
+            cb_s[s] = cb;
             if (a != b) nonuni = 1;
             else if (PASS == 0 && P.filter == DFB_FILTER_ONE) {
                 double v = (double)values[a];
@@ -139,39 +145,67 @@ __global__ void __launch_bounds__(K1_THREADS) filter_tile_kernel(const FilterPar
             for (int w = 0; w < warp; ++w) wp += wsum[w];
             dst0 = P.tile_off[tile] + wp + inc - c;
         }
-        if (p0 < t1) {
-            for (int s = 0; s < n; ++s) {
-                const int64_t lo = P.rle.run_off[s], cb = cum[lo];
-                int64_t g = r0[s];
-                if (r1[s] != g) g = find_run(cum, cb, g, r1[s], p0);
-                const double d = P.mapped ? P.mapped[s] : 1.0;
-                int64_t gend = cum[g + 1] - cb;
-                V raw = values[g];
-                int k = 0;
+        // The tile is expanded through shared memory, SC samples at a time: warp w turns the runs of
+        // sample s0 + w that overlap the tile into 2048 dense values (run bounds and values are loaded
+        // 32 runs per coalesced request, every run is then filled by the whole warp); afterwards
+        // every thread consumes its 8 positions of those samples, in sample order.  No per-thread
+        // binary searches or dependent global loads: the searches above (r0 / r1) are the only ones.
+        constexpr int SC = sizeof(S) == 4 ? 8 : 4;  // samples per chunk: 64 KiB of staging either way
+        S* vals_s = reinterpret_cast<S*>(smem_k1 + 4 * (size_t)n);
+        for (int s0 = 0; s0 < n; s0 += SC) {
+            __syncthreads();  // the previous chunk has been consumed
+            for (int sl = warp; sl < SC && s0 + sl < n; sl += K1_THREADS / 32) {
+                const int s = s0 + sl;
+                const int64_t cb = cb_s[s];
+                const int64_t ga = r0[s], gb = r1[s];
+                const double d = NORM ? P.mapped[s] : 1.0;
+                S* dstv = vals_s + (size_t)sl * K1_TILE;
+                for (int64_t g0 = ga; g0 <= gb; g0 += 32) {
+                    const int64_t g = g0 + lane;
+                    int st = 0, en = 0;
+                    S val = S(0);
+                    if (g <= gb) {
+                        st = (int)(max(cum[g] - cb, t0) - t0);
+                        en = (int)(min(cum[g + 1] - cb, t1) - t0);
+                        if (NORM) val = (S)__ddiv_rn((double)values[g], d);
+                        else val = (S)values[g];
+                    }
+                    const int nr = (int)min((int64_t)32, gb - g0 + 1);
+                    for (int j = 0; j < nr; ++j) {
+                        const int a = __shfl_sync(0xffffffffu, st, j), e = __shfl_sync(0xffffffffu, en, j);
+                        const S v = __shfl_sync(0xffffffffu, val, j);
+                        for (int pp = a + lane; pp < e; pp += 32) dstv[pp] = v;
+                    }
+                }
+            }
+            __syncthreads();
+            if (p0 < t1) {
+                for (int sl = 0; sl < SC && s0 + sl < n; ++sl) {
+                    const int s = s0 + sl;
+                    const S* src = vals_s + (size_t)sl * K1_TILE + (size_t)tid * K1_PER;
+                    S rawv[K1_PER];
 #pragma unroll
-                for (int q = 0; q < K1_PER; ++q) {
-                    const int64_t pos = p0 + q;
-                    if (pos < t1) {
-                        while (gend <= pos) {
-                            ++g;
-                            gend = cum[g + 1] - cb;
-                            raw = values[g];
-                        }
-                        double v = (double)raw;
-                        if (P.mapped) v = __ddiv_rn(v, d);
-                        if (PASS == 0) {
-                            if (P.filter == DFB_FILTER_ONE) {
-                                if (v > P.cutoff) bits |= 1u << q;
+                    for (int q = 0; q < K1_PER; ++q) rawv[q] = src[q];
+                    int k = 0;
+#pragma unroll
+                    for (int q = 0; q < K1_PER; ++q) {
+                        const int64_t pos = p0 + q;
+                        if (pos < t1) {
+                            const double v = (double)rawv[q];
+                            if (PASS == 0) {
+                                if (P.filter == DFB_FILTER_ONE) {
+                                    if (v > P.cutoff) bits |= 1u << q;
+                                } else {
+                                    sum[q] = s == 0 ? v : __dadd_rn(sum[q], v);
+                                }
                             } else {
                                 sum[q] = s == 0 ? v : __dadd_rn(sum[q], v);
-                            }
-                        } else {
-                            sum[q] = s == 0 ? v : __dadd_rn(sum[q], v);
-                            if ((bits >> q) & 1u) {
-                                const int64_t dst = dst0 + k;
-                                if (P.out_is_double) reinterpret_cast<double*>(P.out)[(size_t)s * P.ld + dst] = v;
-                                else reinterpret_cast<int32_t*>(P.out)[(size_t)s * P.ld + dst] = (int32_t)raw;
-                                ++k;
+                                if ((bits >> q) & 1u) {
+                                    const int64_t dst = dst0 + k;
+                                    if (P.out_is_double) reinterpret_cast<double*>(P.out)[(size_t)s * P.ld + dst] = v;
+                                    else reinterpret_cast<int32_t*>(P.out)[(size_t)s * P.ld + dst] = (int32_t)rawv[q];
+                                    ++k;
+                                }
                             }
                         }
                     }
@@ -411,13 +445,24 @@ static int filter_rle_impl(dfb_ctx* ctx, int n, int dtype, const void* const* va
     P.mask = mask.p;
     P.tile_count = tile_count.p;
     P.tiles = tiles;
-    const size_t smem = (size_t)2 * n * sizeof(int64_t);
+    const size_t smem = (size_t)4 * n * sizeof(int64_t) + (size_t)64 * 1024;  // r0 / r1 / bases + the expansion staging
     const int grid = (int)std::min<int64_t>(std::max<int64_t>(tiles, 1), (int64_t)ctx->sm_count * 16);
-    if (tiles > 0) {
-        KTimer t(ctx, DFB_K_PREP);
-        if (dtype == DFB_I32) filter_tile_kernel<int32_t, 0><<<grid, K1_THREADS, smem, ctx->stream>>>(P);
-        else filter_tile_kernel<double, 0><<<grid, K1_THREADS, smem, ctx->stream>>>(P);
-    }
+    auto launch_filter = [&](int pass) -> int {
+        auto go = [&](auto kern) -> int {
+            DFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            KTimer t(ctx, DFB_K_PREP);
+            kern<<<grid, K1_THREADS, smem, ctx->stream>>>(P);
+            return DFB_OK;
+        };
+        const bool norm = mapped != nullptr;
+        if (dtype == DFB_I32) {
+            if (pass == 0) return norm ? go(filter_tile_kernel<int32_t, 0, true>) : go(filter_tile_kernel<int32_t, 0, false>);
+            return norm ? go(filter_tile_kernel<int32_t, 1, true>) : go(filter_tile_kernel<int32_t, 1, false>);
+        }
+        if (pass == 0) return norm ? go(filter_tile_kernel<double, 0, true>) : go(filter_tile_kernel<double, 0, false>);
+        return norm ? go(filter_tile_kernel<double, 1, true>) : go(filter_tile_kernel<double, 1, false>);
+    };
+    if (tiles > 0) DFB_TRY(launch_filter(0));
     DFB_CUDA(cudaGetLastError());
     DFB_TRY(exclusive_scan_u32(ctx, tile_count.p, tile_off.p, tiles, total_dev.p, DFB_K_PREP));
     int64_t N = 0;
@@ -476,9 +521,11 @@ static int filter_rle_impl(dfb_ctx* ctx, int n, int dtype, const void* const* va
         P.out = c->dtype == DFB_I32 ? (void*)c->xi.p : (void*)c->xd.p;
         P.out_is_double = c->dtype == DFB_F64;
         P.mean = want_mean ? c->mean.p : nullptr;
-        KTimer t(ctx, DFB_K_PREP);
-        if (dtype == DFB_I32) filter_tile_kernel<int32_t, 1><<<grid, K1_THREADS, smem, ctx->stream>>>(P);
-        else filter_tile_kernel<double, 1><<<grid, K1_THREADS, smem, ctx->stream>>>(P);
+        rc = launch_filter(1);
+        if (rc < 0) {
+            delete c;
+            return rc;
+        }
     }
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // `up` buffers die with this frame
