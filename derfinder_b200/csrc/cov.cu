@@ -146,12 +146,31 @@ __global__ void __launch_bounds__(K1_THREADS) filter_tile_kernel(const FilterPar
             dst0 = P.tile_off[tile] + wp + inc - c;
         }
         // The tile is expanded through shared memory, SC samples at a time: warp w turns the runs of
-        // sample s0 + w that overlap the tile into 2048 dense values (run bounds and values are loaded
-        // 32 runs per coalesced request, every run is then filled by the whole warp); afterwards
-        // every thread consumes its 8 positions of those samples, in sample order.  No per-thread
-        // binary searches or dependent global loads: the searches above (r0 / r1) are the only ones.
+        // sample s0 + w that overlap the tile into dense values (run bounds and values are loaded 32 runs
+        // per coalesced request, every run is then filled by the whole warp); afterwards every thread
+        // consumes its 8 positions of those samples, in sample order.  No per-thread binary searches or
+        // dependent global loads: the searches above (r0 / r1) are the only ones.
+        //
+        // Zero runs are never materialised.  A warp owns one 256-position sub-tile; per sample an 8-bit
+        // mask says which sub-tiles hold a non-zero run (PASS 0) or a kept position (PASS 1: every
+        // sample's value is needed there, zeros included).  Only those sub-tiles are zero-filled and
+        // overlaid with the non-zero runs, and only their owners consume them -- adding +0.0 to the
+        // ordered sums of the others would not change them, and 0 > cutoff is false for cutoff >= 0.
         constexpr int SC = sizeof(S) == 4 ? 8 : 4;  // samples per chunk: 64 KiB of staging either way
         S* vals_s = reinterpret_cast<S*>(smem_k1 + 4 * (size_t)n);
+        __shared__ unsigned need_s[8];
+        __shared__ unsigned kept_sub_s;
+        unsigned force_need = 0u;  // sub-tiles every sample must materialise
+        if (PASS == 0) {
+            if (!(P.cutoff >= 0.0) || P.filter == DFB_FILTER_NONE) force_need = 0xffu;  // zeros may pass: no skipping
+        } else {
+            if (tid == 0) kept_sub_s = 0u;
+            __syncthreads();
+            const unsigned wany = __any_sync(0xffffffffu, bits != 0u) ? 1u : 0u;
+            if (lane == 0 && wany) atomicOr(&kept_sub_s, 1u << warp);
+            __syncthreads();
+            force_need = kept_sub_s;
+        }
         for (int s0 = 0; s0 < n; s0 += SC) {
             __syncthreads();  // the previous chunk has been consumed
             for (int sl = warp; sl < SC && s0 + sl < n; sl += K1_THREADS / 32) {
@@ -160,27 +179,58 @@ __global__ void __launch_bounds__(K1_THREADS) filter_tile_kernel(const FilterPar
                 const int64_t ga = r0[s], gb = r1[s];
                 const double d = NORM ? P.mapped[s] : 1.0;
                 S* dstv = vals_s + (size_t)sl * K1_TILE;
-                for (int64_t g0 = ga; g0 <= gb; g0 += 32) {
-                    const int64_t g = g0 + lane;
-                    int st = 0, en = 0;
-                    S val = S(0);
-                    if (g <= gb) {
-                        st = (int)(max(cum[g] - cb, t0) - t0);
-                        en = (int)(min(cum[g + 1] - cb, t1) - t0);
-                        if (NORM) val = (S)__ddiv_rn((double)values[g], d);
-                        else val = (S)values[g];
+                // pass A: which sub-tiles hold a non-zero run of this sample
+                unsigned need = force_need;
+                if (PASS == 0 && need != 0xffu) {
+                    for (int64_t g0 = ga; g0 <= gb; g0 += 32) {
+                        const int64_t g = g0 + lane;
+                        unsigned cov = 0u;
+                        if (g <= gb && values[g] != V(0)) {
+                            const int st = (int)(max(cum[g] - cb, t0) - t0);
+                            const int en = (int)(min(cum[g + 1] - cb, t1) - t0);
+                            if (en > st) cov = ((2u << ((en - 1) >> 8)) - 1u) & ~((1u << (st >> 8)) - 1u);
+                        }
+                        need |= __reduce_or_sync(0xffffffffu, cov);
                     }
-                    const int nr = (int)min((int64_t)32, gb - g0 + 1);
-                    for (int j = 0; j < nr; ++j) {
-                        const int a = __shfl_sync(0xffffffffu, st, j), e = __shfl_sync(0xffffffffu, en, j);
-                        const S v = __shfl_sync(0xffffffffu, val, j);
-                        for (int pp = a + lane; pp < e; pp += 32) dstv[pp] = v;
+                }
+                if (lane == 0) need_s[sl] = need;
+                // zero-fill the needed sub-tiles, then overlay the non-zero runs
+                for (unsigned m = need; m; m &= m - 1) {
+                    const int sub = __ffs(m) - 1;
+#pragma unroll
+                    for (int i = 0; i < 256 / 32; ++i) dstv[sub * 256 + i * 32 + lane] = S(0);
+                }
+                __syncwarp();
+                if (need) {
+                    for (int64_t g0 = ga; g0 <= gb; g0 += 32) {
+                        const int64_t g = g0 + lane;
+                        int st = 0, en = 0;
+                        S val = S(0);
+                        if (g <= gb) {
+                            const V raw = values[g];
+                            if (raw != V(0)) {
+                                st = (int)(max(cum[g] - cb, t0) - t0);
+                                en = (int)(min(cum[g + 1] - cb, t1) - t0);
+                                if (NORM) val = (S)__ddiv_rn((double)raw, d);
+                                else val = (S)raw;
+                            }
+                        }
+                        unsigned live = __ballot_sync(0xffffffffu, en > st);
+                        while (live) {
+                            const int j = __ffs(live) - 1;
+                            live &= live - 1;
+                            const int a = __shfl_sync(0xffffffffu, st, j), e = __shfl_sync(0xffffffffu, en, j);
+                            const S v = __shfl_sync(0xffffffffu, val, j);
+                            for (int pp = a + lane; pp < e; pp += 32)
+                                if ((need >> (pp >> 8)) & 1u) dstv[pp] = v;
+                        }
                     }
                 }
             }
             __syncthreads();
             if (p0 < t1) {
                 for (int sl = 0; sl < SC && s0 + sl < n; ++sl) {
+                    if (!((need_s[sl] >> warp) & 1u)) continue;  // all zero here and nothing to write: no-op
                     const int s = s0 + sl;
                     const S* src = vals_s + (size_t)sl * K1_TILE + (size_t)tid * K1_PER;
                     S rawv[K1_PER];
@@ -196,10 +246,10 @@ __global__ void __launch_bounds__(K1_THREADS) filter_tile_kernel(const FilterPar
                                 if (P.filter == DFB_FILTER_ONE) {
                                     if (v > P.cutoff) bits |= 1u << q;
                                 } else {
-                                    sum[q] = s == 0 ? v : __dadd_rn(sum[q], v);
+                                    sum[q] = __dadd_rn(sum[q], v);  // sums start at +0.0: 0.0 + v == v exactly
                                 }
                             } else {
-                                sum[q] = s == 0 ? v : __dadd_rn(sum[q], v);
+                                sum[q] = __dadd_rn(sum[q], v);
                                 if ((bits >> q) & 1u) {
                                     const int64_t dst = dst0 + k;
                                     if (P.out_is_double) reinterpret_cast<double*>(P.out)[(size_t)s * P.ld + dst] = v;
@@ -454,7 +504,11 @@ static int filter_rle_impl(dfb_ctx* ctx, int n, int dtype, const void* const* va
             kern<<<grid, K1_THREADS, smem, ctx->stream>>>(P);
             return DFB_OK;
         };
-        const bool norm = mapped != nullptr;
+        // x / 1.0 == x: with totalMapped == targetSize (regionMatrix's default) every divisor is 1 and the
+        // integer staging (twice the samples per chunk) serves; the output stays double
+        bool norm = false;
+        if (mapped)
+            for (int s2 = 0; s2 < n; ++s2) norm = norm || mapped[s2] != 1.0;
         if (dtype == DFB_I32) {
             if (pass == 0) return norm ? go(filter_tile_kernel<int32_t, 0, true>) : go(filter_tile_kernel<int32_t, 0, false>);
             return norm ? go(filter_tile_kernel<int32_t, 1, true>) : go(filter_tile_kernel<int32_t, 1, false>);
