@@ -34,6 +34,7 @@ struct FilterParams {
     uint32_t* mask;        // [ceil(len/32)]
     uint32_t* tile_count;  // [tiles]
     const int64_t* tile_off;  // pass 1
+    const int64_t* tile_run;  // [tiles][n] run holding each tile's first position (tile_runs_kernel)
     int64_t ld;
     void* out;             // [n][ld] int32 or double
     int out_is_double;
@@ -50,6 +51,20 @@ __device__ __forceinline__ int64_t find_run(const int64_t* __restrict__ cum, int
         else lo = mid + 1;
     }
     return lo;
+}
+
+// run of every sample that contains the first position of every tile: tab[tile * n + s].  All
+// tiles x samples searches run in parallel here, so the tile loop of the filter kernel starts from a
+// table look-up instead of 2 x log2(#runs) dependent loads per sample.
+__global__ void __launch_bounds__(256) tile_runs_kernel(RleDev R, int64_t tiles, int64_t* __restrict__ tab) {
+    const int n = R.n;
+    const int64_t total = tiles * n;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t tile = i / n;
+        const int s = (int)(i - tile * n);
+        const int64_t lo = R.run_off[s], hi = R.run_off[s + 1] - 1;
+        tab[i] = find_run(R.cum, R.cum[lo], lo, hi, tile * K1_TILE);
+    }
 }
 
 // NORM: the library-size divisor (mapped) is present.  The division is then done ONCE PER RUN while
@@ -77,8 +92,12 @@ __global__ void __launch_bounds__(K1_THREADS) filter_tile_kernel(const FilterPar
         int nonuni = 0, anypass = 0;
         for (int s = tid; s < n; s += K1_THREADS) {
             const int64_t lo = P.rle.run_off[s], hi = P.rle.run_off[s + 1] - 1, cb = cum[lo];
-            const int64_t a = find_run(cum, cb, lo, hi, t0);
-            const int64_t b = find_run(cum, cb, a, hi, t1 - 1);
+            const int64_t a = P.tile_run[tile * n + s];
+            int64_t b = hi;  // run holding the tile's last position
+            if (tile + 1 < P.tiles) {
+                b = P.tile_run[(tile + 1) * n + s];          // holds position t1 ...
+                if (cum[b] - cb >= t1) --b;                  // ... and starts there: t1 - 1 is in the run before
+            }
             r0[s] = a;
             r1[s] = b;
             cb_s[s] = cb;
@@ -495,6 +514,13 @@ static int filter_rle_impl(dfb_ctx* ctx, int n, int dtype, const void* const* va
     P.mask = mask.p;
     P.tile_count = tile_count.p;
     P.tiles = tiles;
+    DevBuf<int64_t> tile_run;
+    DFB_TRY(tile_run.alloc(ctx, (size_t)std::max<int64_t>(tiles, 1) * n));
+    P.tile_run = tile_run.p;
+    if (tiles > 0) {
+        KTimer t(ctx, DFB_K_PREP);
+        tile_runs_kernel<<<grid_for(tiles * n, 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(P.rle, tiles, tile_run.p);
+    }
     const size_t smem = (size_t)4 * n * sizeof(int64_t) + (size_t)64 * 1024;  // r0 / r1 / bases + the expansion staging
     const int grid = (int)std::min<int64_t>(std::max<int64_t>(tiles, 1), (int64_t)ctx->sm_count * 16);
     auto launch_filter = [&](int pass) -> int {
