@@ -908,6 +908,16 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
         // siblings of a quarter share its centred tile: they meet before it is overwritten ...
         if (ew > 1 && warp < mma_warp) asm volatile("bar.sync %0, %1;" ::"r"(1 + quarter), "r"(32 * ew) : "memory");
         if (warp < 4) {
+            // pull this CTA's NEXT tile towards L2 while the current one is processed: its staging then
+            // pays an L2 hit instead of a DRAM round trip per load batch (one 128-byte line per thread)
+            if (n >= 32) {  // measured: pays for wide tiles (C3s -4 %), costs issue slots for n = 12
+                const int64_t nbase = (tile + gridDim.x) * TC_M;
+                for (int i = tid; i < n * 8; i += TC_M) {
+                    const int k = i >> 3, line = i & 7;
+                    const int64_t b = nbase + line * 16;
+                    if (b < P.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(P.Y + (size_t)k * P.ld + b));
+                }
+            }
             // ---- stage the tile: FP64 centred copy (exact contract) + bf16 hi/lo A operand
             const int64_t base = base0 + tid;
             const bool valid = base < P.N && !(P.dbg & 32);
