@@ -101,6 +101,7 @@ struct dfb_ctx {
     int opt_b_stages = 0;        // fused kernel: B tile stages (0 = auto)
     int opt_ys_smem = -1;        // fused kernel: FP64 tile in shared memory (1), streamed (0), auto (-1)
     int opt_chunk_perms = 0;     // fused kernel: permutations per MMA chunk (0 = auto)
+    int opt_tmem_stages = 0;     // fused kernel: accumulator stages (0 = auto)
     int opt_fused = 1;           // fused screen+refine kernel (0: two-kernel screen path)
     double opt_null_cap_mb = 0;  // 0 = auto
     int opt_perm_batch = 0;      // 0 = auto

@@ -642,7 +642,8 @@ struct FusedGeom {
     int KB;             // 64-element K blocks of the stored [hi | lo] rows (2*npad elements)
     int p, p0, j0, pe, pst;  // model columns, first column used by the screen, columns screened, TMEM stride
     int ps, nmma;       // permutations per chunk, MMA N = ps * pst
-    int tmem_cols;      // TMEM allocation: two accumulator stages, rounded up to a power of two
+    int tmem_cols;      // TMEM allocation: nt accumulator stages, rounded up to a power of two
+    int nt;             // accumulator stages (2; 1 trades the intra-CTA overlap for a second CTA per SM)
     int qs, ixs;        // Qs row stride (doubles), bytes per row of the byte permutation table
     int nb;             // B tile stages: 1 when the tile is small (occupancy first), else 2
     int ew;             // epilogue warps per TMEM lane quarter (1, 2 or 4)
@@ -1067,7 +1068,7 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
                     }
                     pl.started = true;
                     pl.sb = sb + 1 == NB ? 0 : sb + 1;
-                    pl.s = s ^ 1;
+                    pl.s = (G.nt > 1) ? (s ^ 1) : 0;
                     lap(5);  // MMA lane: refill (waits for the previous chunk's MMAs to retire)
                 }
             }
@@ -1082,8 +1083,8 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
             const double* yglob = P.Y + base0 + quarter * 32;  // streamed-Y variant: candidates re-read Y
             for (int64_t c = 0; c < G.chunks; ++c) {
                 const int64_t i0 = it + c;
-                const int s = (int)(i0 & 1);
-                const uint32_t ph = (uint32_t)((i0 >> 1) & 1);
+                const int s = G.nt > 1 ? (int)(i0 & 1) : 0;
+                const uint32_t ph = G.nt > 1 ? (uint32_t)((i0 >> 1) & 1) : (uint32_t)(i0 & 1);
                 const int64_t b0 = c * G.ps + hsub * hp;  // first permutation of this warp's share of the chunk
                 const int nq = (int)max((int64_t)0, min((int64_t)hp, P.G.B - b0));  // valid permutations of the share
                 lap(3);  // epilogue: refinement + bookkeeping of the previous chunk
@@ -1496,7 +1497,7 @@ static bool constant_first_column(const ModelBasis& mb) {
 }
 
 static bool fused_geometry_ps(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, int64_t B, int force_ps,
-                              FusedGeom* g);
+                              FusedGeom* g, int force_nt = 0, int force_nb = 0);
 
 // Chunk width.  Small models (<= 4 screened columns: small tiles, several CTAs per SM) use 32
 // permutations per chunk.  Larger ones are bound by the tcgen05.mma instruction rate -- an M = 128,
@@ -1505,7 +1506,12 @@ static bool fused_geometry_ps(const dfb_ctx* ctx, const dfb_cov* cov, const Mode
 static bool fused_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, int64_t B, FusedGeom* g) {
     if (ctx->opt_chunk_perms > 0) return fused_geometry_ps(ctx, cov, mb, B, ctx->opt_chunk_perms, g);
     const int pe = mb.p - ((mb.p <= 8 && constant_first_column(mb)) ? 1 : 0);
-    if (mb.p <= 8 && pe >= 5) {
+    if (mb.p <= 8 && pe >= 5 && ctx->opt_tmem_stages == 0 && ctx->opt_b_stages == 0) {
+        // measured best (C3s 5.2 ms): 32-permutation chunks with ONE accumulator and ONE B stage per CTA
+        // and two CTAs per SM -- the CTAs overlap each other's tile staging, B loads and hand-offs
+        if (32 * pe <= 256 && (32 * pe) % 16 == 0 && fused_geometry_ps(ctx, cov, mb, B, 32, g, 1, 1) &&
+            2 * (g->smem + 1024) <= (size_t)227 * 1024)
+            return true;
         for (int ps = 48; ps >= 24; ps -= 8)
             if (ps * pe <= 240 && fused_geometry_ps(ctx, cov, mb, B, ps, g)) return true;
     }
@@ -1513,7 +1519,7 @@ static bool fused_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
 }
 
 static bool fused_geometry_ps(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, int64_t B, int force_ps,
-                              FusedGeom* g) {
+                              FusedGeom* g, int force_nt, int force_nb) {
     FusedGeom G;
     memset(&G, 0, sizeof G);
     G.n = cov->n;
@@ -1539,7 +1545,8 @@ static bool fused_geometry_ps(const dfb_ctx* ctx, const dfb_cov* cov, const Mode
     G.nmma = G.ps * G.pst;
     if (G.nmma < 16 || G.nmma > 256) return false;
     G.tmem_cols = 32;
-    while (G.tmem_cols < 2 * G.nmma) G.tmem_cols *= 2;
+    G.nt = (force_nt == 1 || ctx->opt_tmem_stages == 1) ? 1 : 2;
+    while (G.tmem_cols < G.nt * G.nmma) G.tmem_cols *= 2;
     G.qs = mb.p <= 8 ? ((mb.p + 1) & ~1) : mb.p;
     G.ixs = (int)round_up(G.n, 16);
     G.B = B;
@@ -1561,7 +1568,8 @@ static bool fused_geometry_ps(const dfb_ctx* ctx, const dfb_cov* cov, const Mode
     uint32_t o = G.a_bytes;
     G.off_b = o;
     G.nb = 1;
-    if (ctx->opt_b_stages >= 1 && ctx->opt_b_stages <= 4) G.nb = ctx->opt_b_stages;
+    if (force_nb >= 1) G.nb = force_nb;
+    else if (ctx->opt_b_stages >= 1 && ctx->opt_b_stages <= 4) G.nb = ctx->opt_b_stages;
     else if (G.b_bytes > 16 * 1024) {
         // as many stages as fit (<= 3): a 32 KiB bulk copy out of L2 takes longer than its MMAs
         const size_t fixed = (size_t)G.a_bytes + (G.ys_smem ? (size_t)G.n * TC_M * 8 : 0) + (size_t)G.n * G.qs * 8 + 20 * 1024;
