@@ -93,7 +93,14 @@ int dfb_kernel_time(dfb_ctx* ctx, int kernel, double* ms, int64_t* launches);
  *   "fused"      0/1  screen and refinement in one persistent kernel (default 1 when the tile
  *                     fits in shared memory; 0 = separate screen and refinement kernels)
  *   "null_capacity_mb"  initial capacity of the exceedance value buffer
- *   "perm_batch"        permutations per launch (0 = auto) */
+ *   "perm_batch"        permutations per launch (0 = auto)
+ *   "scratch_gb"        upper bound for per-call device scratch (default 24)
+ * Developer knobs of the fused null kernel (geometry overrides for measurements; results are
+ * identical for every valid setting, tests/test_gpu_parity.py::test_fused_kernel_variants_agree):
+ *   "chunk_perms" permutations per MMA chunk, "b_stages" B-tile stages (1-4), "tmem_stages"
+ *   accumulator stages (1-2), "epi_warps" epilogue warps per TMEM quarter (1-4), "ys_smem" FP64
+ *   tile resident (1) or streamed (0); "dbg" bit flags switch parts of the kernel OFF for timing
+ *   experiments (results then invalid; 64 = print clock64 phase counters only). */
 int dfb_set_option(dfb_ctx* ctx, const char* key, double value);
 
 /* ---------------------------------------------------------------- coverage in --------------- */
