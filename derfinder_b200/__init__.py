@@ -4,7 +4,7 @@ The product is the CUDA shared library `libderfinder_b200.so` (C ABI: include/de
 `derfinder_b200.api` mirrors the reference's R functions on top of it.
 """
 from .api import (Coverage, Engine, analyzeChr, calcFstatCutoff, calcPval, calculateFWER, calculatePvalues,  # noqa: F401
-                  calculateStats, clusterMakerRle, default_engine, filterData, findRegions, getSegmentsRle,
+                  calculateStats, clusterMakerRle, coverageToExon, default_engine, filterData, findRegions, getSegmentsRle,
                   makeModels, preprocessCoverage, regionMatrix)
 
 __version__ = "0.1.0"

@@ -679,6 +679,64 @@ def regionMatrix(fullCov, cutoff=5, L_=None, totalMapped=80e6, targetSize=80e6, 
 
 
 # ---------------------------------------------------------------------------------------------
+# coverageToExon  (R/coverageToExon.R:112-241): per exon x sample coverage sums / L -- the same
+# segmented column-sum primitive as regionMatrix (K6), driven by annotation ranges
+
+
+def coverageToExon(fullCov, exons, L_=None, returnType="raw", engine=None, verbose=False, **kwargs):
+    """fullCov: {chr: Rle columns | dense [Lc x n]} of UNFILTERED coverage (fullCoverage() output);
+    exons: {chr: (start, end)} 1-based inclusive, disjoint within a chromosome (the reduced exons of a
+    genomic state, which the reference processes strand by strand, R/coverageToExon.R:131-150).
+    Returns {chr: [nExons x n] matrix} in the order given; `L_` is the reference's `L`."""
+    L_read = kwargs.pop("L", L_)
+    if L_read is None:
+        raise ValueError("argument \"L\" is missing, with no default")
+    if returnType not in ("raw", "rpkm"):
+        raise ValueError("length(returnType) == 1 & returnType %in% c('raw', 'rpkm') is not TRUE")
+    engine = engine or default_engine()
+    out, nsamp, msum = {}, None, None
+    for chrom, data in fullCov.items():
+        kind, names, cols = _as_columns(data)
+        if kind == "dense":
+            chr_len, n = cols.shape
+            runsum = cols.astype(np.float64)
+            runsum = np.where(np.vstack([np.ones((1, n), bool), cols[1:] != cols[:-1]]), runsum, 0.0).sum(axis=0)
+        else:
+            n = len(cols)
+            chr_len = int(np.asarray(cols[0][1], dtype=np.int64).sum())
+            runsum = np.array([np.asarray(_rle_norm(v, l)[0], dtype=np.float64).sum() for v, l in cols])
+        nsamp = n if nsamp is None else nsamp
+        msum = runsum if msum is None else msum + runsum  # colSums(Mchr): sum of RUN VALUES (:155-160)
+        if chrom not in exons:
+            continue
+        st = L.i32(exons[chrom][0])
+        en = L.i32(exons[chrom][1])
+        if np.any(st < 1) or np.any(en > chr_len) or np.any(en < st):
+            raise ValueError(f"exon ranges of {chrom} fall outside the chromosome")
+        position = (np.array([True]), np.array([chr_len]))
+        cov = _upload_filtered(engine, data, position, names)
+        Lv = np.atleast_1d(np.asarray(L_read, dtype=np.float64))
+        if Lv.size not in (1, n):
+            warnings.warn("Invalid 'L' value so it won't be used. It has to either be a integer/numeric vector of "
+                          "length 1 or length equal to the number of samples.")
+            Lv = np.zeros(0)
+        R = len(st)
+        mat = np.empty((n, R), dtype=np.float64)  # column-major [R x n]
+        L.check(engine.lib.dfb_region_matrix(engine.h, cov.h, L.ptr(st, C.c_int32), L.ptr(en, C.c_int32), R,
+                                             L.ptr(Lv, C.c_double) if Lv.size else None, int(Lv.size),
+                                             L.ptr(mat, C.c_double)))
+        out[chrom] = mat.T.copy()
+        cov.free()
+    if returnType == "rpkm":  # :154-161
+        Lv = np.asarray(L_read, dtype=np.float64)
+        M = msum / Lv / 1e6
+        for chrom, mat in out.items():
+            width = (np.asarray(exons[chrom][1], dtype=np.float64) - np.asarray(exons[chrom][0], dtype=np.float64) + 1)
+            out[chrom] = mat / (width[:, None] / 1000.0) / M[None, :]
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # analyzeChr  (R/analyzeChr.R:108-310) without annotation / file output
 
 

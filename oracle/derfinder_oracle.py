@@ -572,6 +572,26 @@ def region_matrix(cols, cutoff=5, L=1, totalMapped=80e6, targetSize=80e6, maxReg
     return dict(regions=regs, coverageMatrix=mat, filtered=filt)
 
 
+def coverage_to_exon(dense, starts, ends, L=1):
+    """R/coverageToExon.R:206-222 for one chromosome: colSums of every exon's rows of the dense
+    [Lc x n] coverage, divided by L (scalar; a vector only divides the last column, the same
+    `for (i in length(L))` quirk as regionMatrix)."""
+    dense = np.asarray(dense)
+    n = dense.shape[1]
+    mat = np.zeros((len(starts), n), dtype=np.float64)
+    for r, (a, b) in enumerate(zip(starts, ends)):
+        acc = np.zeros(n, dtype=np.float64)
+        for row in dense[a - 1:b]:
+            acc = acc + row
+        mat[r] = acc
+    Lv = np.atleast_1d(np.asarray(L, dtype=np.float64))
+    if Lv.size == 1:
+        mat = mat / Lv[0]
+    elif Lv.size == n:
+        mat[:, n - 1] = mat[:, n - 1] / Lv[n - 1]
+    return mat
+
+
 # ---------------------------------------------------------------------------------------------
 # Fixture helpers: sampleDepth / collapseFullCoverage / makeModels (host-side, tiny; only needed
 # to rebuild the golden models)

@@ -754,3 +754,23 @@ def test_fused_kernel_variants_agree(dfb, eng, opts):
         assert e2.kernel_time(3)[1] > 0  # the tcgen05 path really ran
     finally:
         e2.close()
+
+
+def test_coverage_to_exon(dfb, eng):
+    """coverageToExon (R/coverageToExon.R:206-222): exon x sample sums of unfiltered coverage."""
+    rng = np.random.default_rng(99)
+    n = 5
+    full, exons, dense_by_chr = {}, {}, {}
+    for chrom, Lc in (("chr21", 30000), ("chrX", 12345)):
+        cols = random_rle_cols(rng, n, Lc, mean_run=40, zero_frac=0.6)
+        full[chrom] = cols
+        dense_by_chr[chrom] = np.column_stack([O.rle_decode(v, l) for v, l in cols])
+        cuts = np.sort(rng.choice(np.arange(1, Lc), size=60, replace=False))
+        st, en = cuts[0::2] + 1, cuts[1::2]
+        keep = en >= st
+        exons[chrom] = (st[keep], en[keep])
+    for Lval in (76, np.arange(1, n + 1) * 10.0):
+        got = dfb.coverageToExon(full, exons, L_=Lval, engine=eng)
+        for chrom in full:
+            want = O.coverage_to_exon(dense_by_chr[chrom], exons[chrom][0], exons[chrom][1], L=Lval)
+            assert np.array_equal(got[chrom], want), chrom
