@@ -118,6 +118,10 @@ struct dfb_ctx {
         size_t cap, used;
     };
     std::vector<PinBlock> pin_blocks;
+    // auxiliary stream: the observed-region chain (dozens of tiny launches) runs here while the
+    // permutation scan occupies the main stream
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_main = nullptr, ev_aux = nullptr;
     // log2(k + scalefac) table for integer coverage (glibc log2, built once per scalefac)
     double* lut_dev = nullptr;
     int64_t lut_n = 0;

@@ -536,6 +536,12 @@ void dfb_destroy(dfb_ctx* c) {
         cudaFreeHost(c->pinned);
         for (int i = 0; i < 4; ++i) cudaEventDestroy(c->stage_ev[i]);
     }
+    if (c->aux) {
+        cudaStreamSynchronize(c->aux);
+        cudaStreamDestroy(c->aux);
+        cudaEventDestroy(c->ev_main);
+        cudaEventDestroy(c->ev_aux);
+    }
     for (auto& b : c->pin_blocks) cudaFreeHost(b.p);
     if (c->lut_dev) cudaFree(c->lut_dev);
     delete c->pool;

@@ -60,6 +60,7 @@ struct dfb_regions {
         const double *val = nullptr, *area = nullptr;
         const int32_t *is = nullptr, *ie = nullptr;
         bool active = false;
+        cudaStream_t stream = nullptr;  // stream the read-backs were enqueued on
     } pend;
     dfb::DevBuf<double> d_area_desc;  // areas in decreasing order (after dfb_calculate_pvalues)
     dfb::DevBuf<int32_t> d_order;     // d_area_desc[i] = d_area[d_order[i]]

@@ -8,6 +8,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <functional>
 #include <cub/cub.cuh>
 
 #include "data.cuh"
@@ -23,7 +24,8 @@ __global__ void add_perm_offset_kernel(int32_t* __restrict__ perm, int64_t n, in
 
 static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const double* mod0, int p0,
                            double adjust_f, const int32_t* perm_idx, int64_t B, double lo, double hi,
-                           int32_t max_region_gap, dfb_nulls** out) {
+                           int32_t max_region_gap, dfb_nulls** out,
+                           const std::function<void()>* after_first_launch = nullptr) {
     *out = nullptr;
     DFB_REQUIRE(cov->y.p != nullptr, "coverageProcessed is missing: run dfb_preprocess first");
     DFB_REQUIRE(B >= 0 && (perm_idx || B == 0), "perm_idx is NULL");
@@ -109,6 +111,10 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
             continue;
         }
         DFB_TRY(rc);
+        if (after_first_launch) {  // the null scan is in flight: independent work can be enqueued behind it now
+            (*after_first_launch)();
+            after_first_launch = nullptr;
+        }
         RegionSet rs;
         DFB_TRY(find_regions_rows(ctx, N, pbatch.rows, sides, pbatch.mask.p, seg.p, nullptr, 0, &pbatch, false, true,
                                   &rs));
@@ -727,13 +733,43 @@ int dfb_calculate_pvalues(dfb_ctx* ctx, dfb_cov* cov, const double* fstats, cons
         return DFB_ESTATE;
     }
     dfb_regions* r = nullptr;
-    int rc = find_regions_dense(ctx, cov->fstats.p, cov->pos, cutoff_lo, cutoff_hi, max_region_gap, max_cluster_gap,
-                                false, &r, /*defer=*/true);
-    if (rc != DFB_OK) return rc;  // DFB_ENOREGIONS: list(regions = NULL, ...) (:245-251)
+    // The observed-region chain (threshold, segmentation, clusters: dozens of tiny launches and one host
+    // synchronisation) runs on the auxiliary stream WHILE the permutation scan occupies the main one:
+    // it is enqueued right after the first null-scan launch.
+    if (!ctx->aux) {
+        DFB_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+        DFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
+        DFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
+    }
+    DFB_CUDA(cudaEventRecord(ctx->ev_main, ctx->stream));  // F-statistics are complete past this point
+    int rc_obs = DFB_OK;
+    bool obs_done = false;
+    const std::function<void()> observed = [&]() {
+        obs_done = true;
+        cudaStream_t main_stream = ctx->stream;
+        if (cudaStreamWaitEvent(ctx->aux, ctx->ev_main, 0) != cudaSuccess) {
+            set_error("cudaStreamWaitEvent failed");
+            rc_obs = DFB_ECUDA;
+            return;
+        }
+        ctx->stream = ctx->aux;
+        rc_obs = find_regions_dense(ctx, cov->fstats.p, cov->pos, cutoff_lo, cutoff_hi, max_region_gap, max_cluster_gap,
+                                    false, &r, /*defer=*/true);
+        if (rc_obs == DFB_OK && cudaEventRecord(ctx->ev_aux, ctx->aux) != cudaSuccess) rc_obs = DFB_ECUDA;
+        ctx->stream = main_stream;
+    };
     dfb_nulls* nl = nullptr;
-    rc = perm_nulls_impl(ctx, cov, mod, p, mod0, p0, adjust_f, perm_idx, B, cutoff_lo, cutoff_hi, max_region_gap, &nl);
+    int rc = perm_nulls_impl(ctx, cov, mod, p, mod0, p0, adjust_f, perm_idx, B, cutoff_lo, cutoff_hi, max_region_gap, &nl,
+                             &observed);
+    if (rc >= 0 && !obs_done) observed();  // no permutation launch happened (B == 0 or nothing kept)
+    if (rc >= 0 && rc_obs != DFB_OK) {     // DFB_ENOREGIONS: list(regions = NULL, ...) (:245-251), or an error
+        delete nl;
+        delete r;
+        return rc_obs;
+    }
     if (rc >= 0) {
         rc = finalize_regions(ctx, r);  // the observed-region tables arrived while the null scan ran
+        if (rc >= 0 && cudaStreamWaitEvent(ctx->stream, ctx->ev_aux, 0) != cudaSuccess) rc = DFB_ECUDA;
         if (rc < 0) delete nl;
     }
     if (rc < 0) {

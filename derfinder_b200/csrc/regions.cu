@@ -587,7 +587,7 @@ int find_regions_dense(dfb_ctx* ctx, const double* x_dev, const PositionIndex& p
         delete r;
         return DFB_ECUDA;
     }
-    r->pend = {h_gs, h_ge, h_cf, h_cl, h_val, h_area, h_is, h_ie, true};
+    r->pend = {h_gs, h_ge, h_cf, h_cl, h_val, h_area, h_is, h_ie, true, ctx->stream};
     r->d_area = std::move(rs.area);
     r->d_is = std::move(rs.istart);
     r->d_ie = std::move(rs.iend);
@@ -607,7 +607,8 @@ int find_regions_dense(dfb_ctx* ctx, const double* x_dev, const PositionIndex& p
 // device never idles while the host copies region tables around.
 int finalize_regions(dfb_ctx* ctx, dfb_regions* r) {
     if (!r->pend.active) return DFB_OK;
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    (void)ctx;
+    cudaError_t e = cudaStreamSynchronize(r->pend.stream);
     if (e != cudaSuccess) {
         set_error("find_regions: %s", cudaGetErrorString(e));
         return DFB_ECUDA;
