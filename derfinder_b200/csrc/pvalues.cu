@@ -744,6 +744,7 @@ int dfb_calculate_pvalues(dfb_ctx* ctx, dfb_cov* cov, const double* fstats, cons
     DFB_CUDA(cudaEventRecord(ctx->ev_main, ctx->stream));  // F-statistics are complete past this point
     int rc_obs = DFB_OK;
     bool obs_done = false;
+    const int32_t* h_order = nullptr;
     const std::function<void()> observed = [&]() {
         obs_done = true;
         cudaStream_t main_stream = ctx->stream;
@@ -755,6 +756,18 @@ int dfb_calculate_pvalues(dfb_ctx* ctx, dfb_cov* cov, const double* fstats, cons
         ctx->stream = ctx->aux;
         rc_obs = find_regions_dense(ctx, cov->fstats.p, cov->pos, cutoff_lo, cutoff_hi, max_region_gap, max_cluster_gap,
                                     false, &r, /*defer=*/true);
+        if (rc_obs == DFB_OK) {
+            // the stable decreasing-area order of the observed regions (:368) does not need the nulls either
+            const int64_t R0 = r->R;
+            int rc2 = r->d_area_desc.alloc(ctx, (size_t)R0);
+            if (rc2 >= 0) rc2 = r->d_order.alloc(ctx, (size_t)R0);
+            if (rc2 >= 0) rc2 = order_desc(ctx, r->d_area.p, R0, r->d_order.p, r->d_area_desc.p);
+            if (rc2 >= 0) {
+                h_order = d2h_async_pinned(ctx, r->d_order.p, (size_t)R0);
+                if (!h_order) rc2 = DFB_ENOMEM;
+            }
+            if (rc2 < 0) rc_obs = rc2;
+        }
         if (rc_obs == DFB_OK && cudaEventRecord(ctx->ev_aux, ctx->aux) != cudaSuccess) rc_obs = DFB_ECUDA;
         ctx->stream = main_stream;
     };
@@ -779,33 +792,26 @@ int dfb_calculate_pvalues(dfb_ctx* ctx, dfb_cov* cov, const double* fstats, cons
     // order by decreasing area (stable), then p-values against the (duplicated) null areas; the
     // region areas are still on the device, order and p-values come back with one synchronisation
     const int64_t R = r->R;
-    DevBuf<double> sorted_d, p_d;
-    DevBuf<int32_t> order_d;
+    DevBuf<double> p_d;
     auto fail = [&](int code) {
         delete r;
         delete nl;
         return code;
     };
-    if ((rc = sorted_d.alloc(ctx, (size_t)R)) < 0) return fail(rc);
     if ((rc = p_d.alloc(ctx, (size_t)R)) < 0) return fail(rc);
-    if ((rc = order_d.alloc(ctx, (size_t)R)) < 0) return fail(rc);
-    if ((rc = order_desc(ctx, r->d_area.p, R, order_d.p, sorted_d.p)) < 0) return fail(rc);
-    const int32_t* h_order = d2h_async_pinned(ctx, order_d.p, (size_t)R);
     const double* h_p = nullptr;
     if (nl->count > 0) {  // no nulls at all -> NA (:408-419)
         // the regions are sorted already: rank the nulls against them instead of sorting the nulls
-        if ((rc = pval_by_hist(ctx, sorted_d.p, R, nl->area.p, nl->count, 2, p_d.p)) < 0) return fail(rc);
+        if ((rc = pval_by_hist(ctx, r->d_area_desc.p, R, nl->area.p, nl->count, 2, p_d.p)) < 0) return fail(rc);
         h_p = d2h_async_pinned(ctx, p_d.p, (size_t)R);
     }
     if (cudaStreamSynchronize(ctx->stream) != cudaSuccess || !h_order || (nl->count > 0 && !h_p)) {
         set_error("dfb_calculate_pvalues: read-back failed");
         return fail(DFB_ECUDA);
     }
-    r->order.assign(h_order, h_order + R);
+    r->order.assign(h_order, h_order + R);  // arrived on the auxiliary stream (finalize_regions synchronised it)
     if (h_p) r->pvalues.assign(h_p, h_p + R);
     else r->pvalues.assign((size_t)R, nan(""));
-    r->d_area_desc = std::move(sorted_d);  // kept for genome-wide pooling (dfb_regions_null_hist_dev)
-    r->d_order = std::move(order_d);
     if (pvalues) memcpy(pvalues, r->pvalues.data(), (size_t)R * 8);
     *regions = r;
     *nulls = nl;
