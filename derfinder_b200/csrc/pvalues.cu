@@ -26,6 +26,7 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
                            double adjust_f, const int32_t* perm_idx, int64_t B, double lo, double hi,
                            int32_t max_region_gap, dfb_nulls** out,
                            const std::function<void()>* after_first_launch = nullptr) {
+    const bool after_first_launch_given = after_first_launch != nullptr;
     *out = nullptr;
     DFB_REQUIRE(cov->y.p != nullptr, "coverageProcessed is missing: run dfb_preprocess first");
     DFB_REQUIRE(B >= 0 && (perm_idx || B == 0), "perm_idx is NULL");
@@ -170,7 +171,8 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
             }
         }
     }
-    DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // stand-alone callers get a finished result; dfb_calculate_pvalues keeps enqueuing behind it
+    if (!after_first_launch_given) DFB_CUDA(cudaStreamSynchronize(ctx->stream));
     guard.p = nullptr;
     *out = nl;
     return DFB_OK;
