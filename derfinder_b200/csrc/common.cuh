@@ -224,11 +224,14 @@ int d2h(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);  // synchronise
 int d2h_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);
 int h2d_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);
 // H2D of `count` host segments packed back to back at dst (through the pinned ring); synchronises.
-int h2d_gather(dfb_ctx* ctx, void* dst, const void* const* srcs, const size_t* bytes, int count);
+int h2d_gather(dfb_ctx* ctx, void* dst, const void* const* srcs, const size_t* bytes, int count, bool sync = true);
 // D2H of `count` elements of `elem` bytes laid out in B consecutive blocks (block b = elements
 // [pre[b], pre[b+1])) into the reference's duplicated layout: block b is written twice, back to
 // back, at dst element 2*pre[b] (R/calculatePvalues.R:346-354).
 int d2h_dup(dfb_ctx* ctx, void* dst, const void* src, size_t elem, const int64_t* pre, int64_t B);
+// several arrays with the same block structure as one DMA / copy pipeline
+int d2h_dup_multi(dfb_ctx* ctx, int na, void* const* dsts, const void* const* srcs, const size_t* elems,
+                  const int64_t* pre, int64_t B);
 
 // device-wide exclusive scan of `n` uint32 counts into int64 offsets; total_dev[0] = sum.
 int exclusive_scan_u32(dfb_ctx* ctx, const uint32_t* in, int64_t* out, int64_t n, int64_t* total_dev,

@@ -228,28 +228,56 @@ int d2h_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes) {
                       [&](size_t off, const char* p, size_t sz) { pool_memcpy(ctx, (char*)dst + off, p, sz); });
 }
 
-int d2h_dup(dfb_ctx* ctx, void* dst, const void* src, size_t elem, const int64_t* pre, int64_t B) {
+// Chunked D2H of several device arrays as ONE pipeline: the DMA of the next array's first chunk is in
+// flight while the host still drains the previous array.  sink(array, chunk_offset, pinned, bytes).
+template <typename Sink>
+static int d2h_chunks_multi(dfb_ctx* ctx, int na, const void* const* srcs, const size_t* bytes, Sink sink) {
+    DFB_TRY(ensure_staging(ctx));
+    char* pin = (char*)ctx->pinned;
+    struct Chunk { int a; size_t off, sz; };
+    std::vector<Chunk> chunks;
+    for (int a = 0; a < na; ++a)
+        for (size_t off = 0; off < bytes[a]; off += STAGE_BYTES) chunks.push_back({a, off, std::min(STAGE_BYTES, bytes[a] - off)});
+    size_t issued = 0;
+    for (size_t done = 0; done < chunks.size(); ++done) {
+        for (; issued < chunks.size() && issued < done + NSTAGE; ++issued) {
+            const Chunk& c = chunks[issued];
+            DFB_CUDA(cudaMemcpyAsync(pin + (issued % NSTAGE) * STAGE_BYTES, (const char*)srcs[c.a] + c.off, c.sz,
+                                     cudaMemcpyDeviceToHost, ctx->stream));
+            DFB_CUDA(cudaEventRecord(ctx->stage_ev[issued % NSTAGE], ctx->stream));
+        }
+        DFB_CUDA(cudaEventSynchronize(ctx->stage_ev[done % NSTAGE]));
+        const Chunk& c = chunks[done];
+        sink(c.a, c.off, pin + (done % NSTAGE) * STAGE_BYTES, c.sz);
+    }
+    return DFB_OK;
+}
+
+int d2h_dup_multi(dfb_ctx* ctx, int na, void* const* dsts, const void* const* srcs, const size_t* elems,
+                  const int64_t* pre, int64_t B) {
     const size_t count = (size_t)pre[B];
-    if (count == 0) return DFB_OK;
-    int64_t blk = 0;  // first block that may overlap the current chunk (chunks arrive in order)
-    return d2h_chunks(ctx, src, count * elem, [&](size_t off, const char* p, size_t sz) {
+    if (count == 0 || na <= 0) return DFB_OK;
+    std::vector<size_t> bytes((size_t)na);
+    std::vector<int64_t> blk((size_t)na, 0);  // first block that may overlap the array's current chunk
+    for (int a = 0; a < na; ++a) bytes[(size_t)a] = count * elems[a];
+    return d2h_chunks_multi(ctx, na, srcs, bytes.data(), [&](int a, size_t off, const char* p, size_t sz) {
         // element range of this chunk (STAGE_BYTES is a multiple of every element size used)
+        const size_t elem = elems[a];
         const int64_t e0 = (int64_t)(off / elem), e1 = e0 + (int64_t)(sz / elem);
         struct Seg { char* d1; char* d2; const char* s; size_t n; };
-        std::vector<Seg> segs;
-        while (blk < B && pre[blk + 1] <= e0) ++blk;
-        for (int64_t b = blk; b < B && pre[b] < e1; ++b) {
+        std::vector<Seg> parts;
+        int64_t& bk = blk[(size_t)a];
+        while (bk < B && pre[bk + 1] <= e0) ++bk;
+        for (int64_t b = bk; b < B && pre[b] < e1; ++b) {
             const int64_t lo = std::max(pre[b], e0), hi = std::min(pre[b + 1], e1);
             if (hi <= lo) continue;
             const int64_t k = pre[b + 1] - pre[b];
-            char* d1 = (char*)dst + (size_t)(2 * pre[b] + (lo - pre[b])) * elem;
-            segs.push_back({d1, d1 + (size_t)k * elem, p + (size_t)(lo - e0) * elem, (size_t)(hi - lo) * elem});
+            char* d1 = (char*)dsts[a] + (size_t)(2 * pre[b] + (lo - pre[b])) * elem;
+            const char* sp = p + (size_t)(lo - e0) * elem;
+            const size_t nb = (size_t)(hi - lo) * elem;
+            for (size_t o = 0; o < nb; o += (256u << 10))  // ~256 KiB pieces for the pool
+                parts.push_back({d1 + o, d1 + (size_t)k * elem + o, sp + o, std::min<size_t>(256u << 10, nb - o)});
         }
-        // split the segments into ~256 KiB pieces for the pool
-        std::vector<Seg> parts;
-        for (auto& sg : segs)
-            for (size_t o = 0; o < sg.n; o += (256u << 10))
-                parts.push_back({sg.d1 + o, sg.d2 + o, sg.s + o, std::min<size_t>(256u << 10, sg.n - o)});
         ctx->pool->parallel_for((int)parts.size(), [&](int i) {
             copy_stream(parts[i].d1, parts[i].s, parts[i].n);
             copy_stream(parts[i].d2, parts[i].s, parts[i].n);
@@ -257,9 +285,15 @@ int d2h_dup(dfb_ctx* ctx, void* dst, const void* src, size_t elem, const int64_t
     });
 }
 
+int d2h_dup(dfb_ctx* ctx, void* dst, const void* src, size_t elem, const int64_t* pre, int64_t B) {
+    void* const dsts[1] = {dst};
+    const void* const srcs[1] = {src};
+    return d2h_dup_multi(ctx, 1, dsts, srcs, &elem, pre, B);
+}
+
 // H2D of `count` host segments laid back to back in device memory: the segments are packed into the
 // pinned ring by the copy pool (one DMA per 8 MiB instead of one driver-staged copy per segment).
-int h2d_gather(dfb_ctx* ctx, void* dst, const void* const* srcs, const size_t* bytes, int count) {
+int h2d_gather(dfb_ctx* ctx, void* dst, const void* const* srcs, const size_t* bytes, int count, bool sync) {
     DFB_TRY(ensure_staging(ctx));
     char* pin = (char*)ctx->pinned;
     struct Piece { char* d; const char* s; size_t n; };
@@ -295,7 +329,9 @@ int h2d_gather(dfb_ctx* ctx, void* dst, const void* const* srcs, const size_t* b
         }
     }
     DFB_TRY(flush());
-    DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    // the sources have been copied into pinned memory: without `sync` the caller may go on (and may
+    // free them); the ring's events guard the reuse of the staging buffers
+    if (sync) DFB_CUDA(cudaStreamSynchronize(ctx->stream));
     return DFB_OK;
 }
 

@@ -518,11 +518,23 @@ int dfb_nulls_get(const dfb_nulls* nl, int dup, double* stat, int32_t* width, do
     std::vector<int64_t> pre((size_t)B + 1, 0);
     for (int64_t b = 0; b < B; ++b) pre[(size_t)b + 1] = pre[(size_t)b] + nl->per_perm[(size_t)b];
     DFB_REQUIRE(pre[(size_t)B] == (int64_t)M, "internal error: per-permutation counts do not add up");
-    if (stat) DFB_TRY(d2h_dup(ctx, stat, nl->stat.p, 8, pre.data(), B));
-    if (area) DFB_TRY(d2h_dup(ctx, area, nl->area.p, 8, pre.data(), B));
-    if (width) DFB_TRY(d2h_dup(ctx, width, nl->width.p, 4, pre.data(), B));
-    if (permutation) DFB_TRY(d2h_dup(ctx, permutation, nl->perm.p, 4, pre.data(), B));
-    return DFB_OK;
+    void* dsts[4];
+    const void* srcs[4];
+    size_t elems[4];
+    int na = 0;
+    auto add = [&](void* d, const void* sp, size_t e) {
+        if (d) {
+            dsts[na] = d;
+            srcs[na] = sp;
+            elems[na] = e;
+            ++na;
+        }
+    };
+    add(stat, nl->stat.p, 8);
+    add(area, nl->area.p, 8);
+    add(width, nl->width.p, 4);
+    add(permutation, nl->perm.p, 4);
+    return d2h_dup_multi(ctx, na, dsts, srcs, elems, pre.data(), B);
 }
 
 int dfb_nulls_copy_dev(const dfb_nulls* nl, double* area_dev, int32_t* perm_dev) {
