@@ -103,6 +103,7 @@ SIGNATURES = {
     "dfb_regions_get_pvalues": (C.c_int, [C.c_void_p, c_f64p]),
     "dfb_regions_get_order": (C.c_int, [C.c_void_p, c_i32p]),
     "dfb_region_matrix": (C.c_int, [C.c_void_p, C.c_void_p, c_i32p, c_i32p, C.c_int64, c_f64p, C.c_int, c_f64p]),
+    "dfb_view_sums": (C.c_int, [C.c_void_p, C.c_void_p, c_i32p, c_i32p, C.c_int64, c_f64p, C.c_int, c_f64p]),
     "dfb_region_matrix_r": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, c_f64p, C.c_int, c_f64p]),
 }
 

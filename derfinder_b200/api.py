@@ -737,6 +737,93 @@ def coverageToExon(fullCov, exons, L_=None, returnType="raw", engine=None, verbo
 
 
 # ---------------------------------------------------------------------------------------------
+# railMatrix  (R/railMatrix.R:115-290) with the BigWig contents handed over in memory
+
+
+def _rle_window(values, lengths, starts, ends):
+    """The Rle restricted to the union of sorted, disjoint, 1-based inclusive ranges -- what
+    `import(sampleFile, selection = reduce(regs))` reads (R/railMatrix.R:273-276); O(runs) host
+    marshalling so that only the bases inside regions ever travel to the device."""
+    values, lengths = _rle_norm(values, lengths)
+    run_end = np.cumsum(lengths)
+    run_start = run_end - lengths + 1
+    first = np.searchsorted(run_end, starts, side="left")
+    last = np.searchsorted(run_start, ends, side="right") - 1
+    cnt = last - first + 1
+    tot = int(cnt.sum())
+    reg = np.repeat(np.arange(len(starts)), cnt)
+    idx = np.arange(tot) - np.repeat(np.cumsum(cnt) - cnt, cnt) + np.repeat(first, cnt)
+    lo = np.maximum(run_start[idx], np.asarray(starts, dtype=np.int64)[reg])
+    hi = np.minimum(run_end[idx], np.asarray(ends, dtype=np.int64)[reg])
+    return values[idx], hi - lo + 1
+
+
+def railMatrix(chrs, summaryCov, sampleCov, L_=None, cutoff=None, maxClusterGap=300, totalMapped=None,
+               targetSize=40e6, maxRegionGap=0, engine=None, verbose=False, deviceBytes=2 ** 31, **kwargs):
+    """railMatrix() on coverage already in memory (reading the BigWig files stays with the caller):
+    summaryCov {chr: (values, lengths)} is the content of the mean BigWig `summaryFiles[chr]`,
+    sampleCov {chr: Rle columns | dense [Lc x n]} the per-sample BigWig contents.  Per chromosome
+    (.railMatrixChr :176-234): ERs of the summary above `cutoff` (mean filter + findRegions), then per
+    sample `sum(Views(cov / mappedPerXM, regions)) / L` (.railMatChrRegionCov :264-290).  Regions are
+    processed in groups bounded by `deviceBytes` of expanded coverage (the reference's `chunksize`
+    groups of 1000 regions; results do not depend on it, tests/testthat/test_ER_level.R:156)."""
+    L_read = kwargs.pop("L", L_)
+    chrs = [chrs] if isinstance(chrs, str) else list(chrs)
+    if len(chrs) != len(summaryCov):
+        raise ValueError("length(chrs) == length(summaryFiles) is not TRUE")
+    if cutoff is None:
+        raise ValueError("!is.null(cutoff) is not TRUE")
+    if L_read is None:
+        raise ValueError("argument \"L\" is missing, with no default")
+    if kwargs.get("smoothMean"):
+        raise NotImplementedError("smoothMean = TRUE is not supported by the B200 engine (bumphunter smoothing)")
+    engine = engine or default_engine()
+    out = {}
+    for chrom in chrs:
+        filt = filterData([summaryCov[chrom]], cutoff=cutoff, filter="mean", returnMean=True, returnCoverage=False,
+                          engine=engine)
+        regs = None
+        if len(filt["meanCoverage"]):
+            regs = findRegions(position=filt["position"], fstats=filt["meanCoverage"], chr=chrom,
+                               maxClusterGap=maxClusterGap, cutoff=cutoff, maxRegionGap=maxRegionGap, engine=engine)
+        if regs is None:  # :190-192
+            out[chrom] = dict(regions=None, coverageMatrix=None)
+            continue
+        kind, names, cols = _as_columns(sampleCov[chrom])
+        if kind == "dense":
+            cols = [_dense_to_rle(cols[:, s]) for s in range(cols.shape[1])]
+        n = len(cols)
+        Lv = np.atleast_1d(np.asarray(L_read, dtype=np.float64))
+        if Lv.size not in (1, n):
+            raise ValueError("'L' has to be of length 1 or one value per sample")
+        st = np.asarray(regs["start"], dtype=np.int64)
+        en = np.asarray(regs["end"], dtype=np.int64)
+        R = len(st)
+        by_pos = np.argsort(st, kind="stable")  # windows are cut in genomic order
+        width = (en - st + 1)[by_pos]
+        mat = np.empty((R, n), dtype=np.float64)
+        per_base = 8 * n
+        r0 = 0
+        while r0 < R:
+            r1 = r0 + max(1, int(np.searchsorted(np.cumsum(width[r0:]) * per_base, deviceBytes, side="right")))
+            sel = by_pos[r0:r1]
+            win = [_rle_window(v, l, st[sel], en[sel]) for v, l in cols]
+            cov = filterData(win, cutoff=None, totalMapped=totalMapped, targetSize=targetSize, engine=engine,
+                             colnames=names)["coverage"]
+            ce = np.cumsum(width[r0:r1])
+            cs = (ce - width[r0:r1] + 1).astype(np.int32)
+            ce = ce.astype(np.int32)
+            part = np.empty((n, r1 - r0), dtype=np.float64)  # column-major [R x n]
+            L.check(engine.lib.dfb_view_sums(engine.h, cov.h, L.ptr(cs, C.c_int32), L.ptr(ce, C.c_int32), r1 - r0,
+                                             L.ptr(Lv, C.c_double), int(Lv.size), L.ptr(part, C.c_double)))
+            mat[sel] = part.T
+            cov.free()
+            r0 = r1
+        out[chrom] = dict(regions=regs, coverageMatrix=mat)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # analyzeChr  (R/analyzeChr.R:108-310) without annotation / file output
 
 

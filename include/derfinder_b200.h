@@ -305,6 +305,15 @@ int dfb_region_matrix(dfb_ctx* ctx, const dfb_cov* cov, const int32_t* index_sta
 int dfb_region_matrix_r(dfb_ctx* ctx, const dfb_cov* cov, const dfb_regions* r, const double* L,
                         int n_l, double* out);
 
+/* railMatrix()'s per-sample column -- .railMatChrRegionCov (R/railMatrix.R:264-290):
+ * out[r + R*s] = sum(Views(cov_s, IRanges(start, end)))[r] / L_s over rows start..end (1-based,
+ * inclusive) of column s.  Library-size normalised (double) coverage is summed in IRanges' Rle
+ * order -- one product value * length per run of identical values, left to right -- so the result
+ * is bit-identical to `regCov / mappedPerXM` followed by viewSums; integer coverage is exact.
+ * L: NULL, one value, or one per sample (every column is divided, unlike regionMatrix's quirk). */
+int dfb_view_sums(dfb_ctx* ctx, const dfb_cov* cov, const int32_t* start, const int32_t* end,
+                  int64_t R, const double* L, int n_l, double* out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -572,6 +572,30 @@ def region_matrix(cols, cutoff=5, L=1, totalMapped=80e6, targetSize=80e6, maxReg
     return dict(regions=regs, coverageMatrix=mat, filtered=filt)
 
 
+def rail_matrix(mean_cov, sample_cols, cutoff, L=1, maxClusterGap=300, totalMapped=None, targetSize=40e6,
+                maxRegionGap=0):
+    """One chromosome of railMatrix() (R/railMatrix.R:176-290) with the file contents in memory:
+    mean_cov = (values, lengths) of the summary BigWig, sample_cols = per-sample Rle columns.  ERs of
+    the mean above `cutoff` (:182-187), then per sample `regCov / mappedPerXM` (:286-288) and
+    `sum(Views(regCov, ranges(regs))) / L` (:289) -- an Rle view sum, i.e. one product per run."""
+    filt = filter_data([mean_cov], cutoff=cutoff, filter="mean", returnMean=True, returnCoverage=False)
+    regs = None
+    if len(filt.meanCoverage):
+        regs = find_regions(filt.position, filt.meanCoverage, cutoff, maxClusterGap=maxClusterGap,
+                            maxRegionGap=maxRegionGap)
+    if regs is None:
+        return dict(regions=None, coverageMatrix=None)
+    n = len(sample_cols)
+    Lv = np.broadcast_to(np.asarray(L, dtype=np.float64), (n,))
+    mat = np.zeros((len(regs["start"]), n), dtype=np.float64)
+    for s, (v, l) in enumerate(sample_cols):
+        x = rle_decode(v, l).astype(np.float64)
+        if totalMapped is not None and targetSize != 0:
+            x = x / (np.broadcast_to(np.asarray(totalMapped, dtype=np.float64), (n,))[s] / targetSize)
+        mat[:, s] = view_sums(x, regs["start"], regs["end"]) / Lv[s]
+    return dict(regions=regs, coverageMatrix=mat)
+
+
 def coverage_to_exon(dense, starts, ends, L=1):
     """R/coverageToExon.R:206-222 for one chromosome: colSums of every exon's rows of the dense
     [Lc x n] coverage, divided by L (scalar; a vector only divides the last column, the same

@@ -183,6 +183,17 @@ calculatePvalues <- function(coveragePrep, models, fstats, nPermute = 1L,
     list(regions = regs, coverageMatrix = m)
 }
 
+## ---- railMatrix's per-chunk coverage matrix (.railMatChrRegion, R/railMatrix.R:238-262): the caller imports the
+## selected ranges of every sample BigWig (`import(sampleFile, selection = reduce(regs), as = "RleList")`) and hands
+## the Rle columns over; one call replaces the bpmapply over .railMatChrRegionCov (:264-290)
+.railMatChrRegion <- function(regCovs, regs, mappedPerXM, L) {
+    filt <- filterData(regCovs, cutoff = NULL, totalMapped = mappedPerXM, targetSize = 1, returnCoverage = FALSE)
+    m <- .Call(dfbR_view_sums, .engine(), attr(filt, "dfb_cov"), GenomicRanges::start(regs), GenomicRanges::end(regs),
+               as.numeric(L))
+    colnames(m) <- names(regCovs)
+    list(coverageMatrix = m)
+}
+
 .calcPval <- function(areas, nullareas) .Call(dfbR_calc_pval, .engine(), as.numeric(areas), as.numeric(nullareas))
 .calculateFWER <- function(cutoffFstatUsed, areaNull, permutation, nPermute, areaReg)
     .Call(dfbR_calc_fwer, .engine(), cutoffFstatUsed, as.numeric(areaNull), as.integer(permutation),

@@ -315,6 +315,20 @@ SEXP dfbR_region_matrix(SEXP ctx, SEXP cov, SEXP index_start, SEXP index_end, SE
     return out;
 }
 
+/* railMatrix: per-sample sum(Views(cov, ranges)) / L  (R/railMatrix.R:264-290) */
+SEXP dfbR_view_sums(SEXP ctx, SEXP cov, SEXP start, SEXP end, SEXP L) {
+    dfb_cov* c = (dfb_cov*)unwrap(cov, "railMatrix");
+    int64_t N, chr_len, k; int n, dtype, G, has;
+    CHECK(dfb_cov_info(c, &N, &n, &chr_len, &dtype, &k, &G, &has));
+    R_xlen_t R = XLENGTH(start);
+    SEXP out = PROTECT(Rf_allocMatrix(REALSXP, (int)R, n));
+    CHECK(dfb_view_sums((dfb_ctx*)unwrap(ctx, "railMatrix"), c, (const int32_t*)INTEGER(start),
+                        (const int32_t*)INTEGER(end), R, Rf_isNull(L) ? NULL : REAL(L),
+                        Rf_isNull(L) ? 0 : Rf_length(L), REAL(out)));
+    UNPROTECT(1);
+    return out;
+}
+
 /* ---------------------------------------------------------------- registration -------------- */
 
 static const R_CallMethodDef call_methods[] = {
@@ -333,6 +347,7 @@ static const R_CallMethodDef call_methods[] = {
     {"dfbR_calc_fwer", (DL_FUNC)&dfbR_calc_fwer, 6},
     {"dfbR_quantile", (DL_FUNC)&dfbR_quantile, 3},
     {"dfbR_region_matrix", (DL_FUNC)&dfbR_region_matrix, 5},
+    {"dfbR_view_sums", (DL_FUNC)&dfbR_view_sums, 5},
     {NULL, NULL, 0}};
 
 void R_init_derfinderB200(DllInfo* dll) {

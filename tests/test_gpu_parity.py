@@ -774,3 +774,42 @@ def test_coverage_to_exon(dfb, eng):
         for chrom in full:
             want = O.coverage_to_exon(dense_by_chr[chrom], exons[chrom][0], exons[chrom][1], L=Lval)
             assert np.array_equal(got[chrom], want), chrom
+
+
+@pytest.mark.gpu
+def test_rail_matrix(dfb, eng):
+    """railMatrix (R/railMatrix.R:176-290): ERs of the mean track, then per-sample Rle view sums of
+    the library-size normalised coverage -- bit for bit against the oracle, for scalar and
+    per-sample L, independent of the region grouping (tests/testthat/test_ER_level.R:156), and the
+    same regions as regionMatrix on the same coverage (:158)."""
+    rng = np.random.default_rng(2718)
+    n, Lc = 6, 40000
+    cols = random_rle_cols(rng, n, Lc, mean_run=45, zero_frac=0.5)
+    dense = np.column_stack([O.rle_decode(v, l) for v, l in cols]).astype(np.float64)
+    acc = np.zeros(Lc)
+    for s in range(n):
+        acc = acc + dense[:, s]
+    mean_rle = O.rle_encode(acc / n)
+    total_mapped = rng.integers(30_000_000, 90_000_000, size=n).astype(np.float64)
+    for Lval, tm, budget in ((76, None, 2 ** 31), (np.arange(1, n + 1) * 25.0, total_mapped, 2 ** 31),
+                             (100, total_mapped, 4096), (76, 55e6, 20000)):
+        got = dfb.railMatrix(["chr21"], {"chr21": mean_rle}, {"chr21": cols}, L_=Lval, cutoff=2.6,
+                             maxClusterGap=3000, totalMapped=tm, engine=eng, deviceBytes=budget)["chr21"]
+        want = O.rail_matrix(mean_rle, cols, 2.6, L=Lval, maxClusterGap=3000, totalMapped=tm)
+        assert len(want["regions"]["start"]) > 50
+        assert_regions_equal(got["regions"], want["regions"])
+        assert np.array_equal(got["coverageMatrix"], want["coverageMatrix"])
+    # dense sample input, and the regionMatrix cross-check of the reference's own test
+    got = dfb.railMatrix("chr21", {"chr21": mean_rle}, {"chr21": dense.astype(np.int32)}, L_=76, cutoff=2.6,
+                         maxClusterGap=3000, engine=eng)["chr21"]
+    rm = dfb.regionMatrix({"chr21": cols}, cutoff=2.6, L_=76, maxClusterGap=3000, returnBP=False, engine=eng)["chr21"]
+    assert_regions_equal(got["regions"], rm["regions"], keys=("start", "end", "cluster", "area", "value"))
+    assert np.array_equal(got["coverageMatrix"], rm["coverageMatrix"])
+    # nothing above the cutoff -> empty result (:190-192)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        none = dfb.railMatrix(["chr21"], {"chr21": mean_rle}, {"chr21": cols}, L_=76, cutoff=1e9, engine=eng)["chr21"]
+    assert none["regions"] is None and none["coverageMatrix"] is None
+    with pytest.raises(ValueError):
+        dfb.railMatrix(["chr21"], {"chr21": mean_rle}, {"chr21": cols}, L_=76, engine=eng)

@@ -172,3 +172,37 @@ def test_r_rng_streams():
     assert list(RRandom(1, "Rejection").sample(10) + 1) == [9, 4, 7, 1, 2, 5, 3, 10, 6, 8]
     p = permutation_indices([1, 2, 3], 31, "Rejection")
     assert p.shape == (3, 31) and all(sorted(row) == list(range(31)) for row in p)
+
+
+def test_rail_matrix_oracle_literal():
+    """railMatrix restatement (R/railMatrix.R:176-290) on a case small enough to do by hand."""
+    mean = (np.array([0.0, 6.0, 0.0, 8.0, 0.0]), np.array([3, 4, 5, 2, 6]))  # ERs 4-7 and 13-14 at cutoff 5
+    s1 = (np.array([0, 3, 9, 0, 4, 0], dtype=np.int32), np.array([3, 2, 2, 5, 2, 6]))
+    s2 = (np.array([1, 12, 0], dtype=np.int32), np.array([4, 9, 7]))
+    res = O.rail_matrix(mean, [s1, s2], cutoff=5, L=2, maxClusterGap=300)
+    assert list(res["regions"]["start"]) == [4, 13] and list(res["regions"]["end"]) == [7, 14]
+    assert np.array_equal(res["coverageMatrix"], np.array([[(3 * 2 + 9 * 2) / 2, (1 + 12 * 3) / 2],
+                                                           [4 * 2 / 2, 12 / 2]]))
+    # normalised: x / (totalMapped / targetSize), one product per run, per-sample L
+    res = O.rail_matrix(mean, [s1, s2], cutoff=5, L=[2, 4], totalMapped=[60e6, 30e6], targetSize=40e6)
+    m1, m2 = 60e6 / 40e6, 30e6 / 40e6
+    want = np.array([[((3 / m1) * 2 + (9 / m1) * 2) / 2, ((1 / m2) * 1 + (12 / m2) * 3) / 4],
+                     [((4 / m1) * 2) / 2, ((12 / m2) * 1) / 4]])
+    assert np.array_equal(res["coverageMatrix"], want)
+    assert O.rail_matrix(mean, [s1, s2], cutoff=50)["regions"] is None
+
+
+def test_rle_window_host_marshalling():
+    """api._rle_window: the Rle cut down to the region union equals the dense gather."""
+    from derfinder_b200 import api
+    rng = np.random.default_rng(5)
+    lens = rng.integers(1, 30, size=400)
+    vals = rng.integers(0, 5, size=400)
+    dense = np.repeat(vals, lens)
+    cuts = np.sort(rng.choice(np.arange(1, len(dense)), size=80, replace=False))
+    st, en = cuts[0::2] + 1, cuts[1::2]
+    v, l = api._rle_window(vals, lens, st, en)
+    want = np.concatenate([dense[a - 1:b] for a, b in zip(st, en)])
+    assert np.array_equal(np.repeat(v, l), want)
+    v, l = api._rle_window(vals, lens, np.array([1]), np.array([len(dense)]))
+    assert np.array_equal(np.repeat(v, l), dense)
