@@ -437,7 +437,8 @@ def main():
     def one_step():
         if world > 1:
             (R, M), rh, nh, cov = step.device_pass(keep=True)
-            p_dev, fwer, npool = pool.genomewide_pvalues(eng, rh, nh, B, cut, torch, device, dist=dist)
+            p_dev, fwer, npool = pool.genomewide_pvalues(eng, rh, nh, B, cut, torch, device, dist=dist,
+                                                             merge_area=True)
             eng.lib.dfb_regions_free(rh)
             eng.lib.dfb_nulls_free(nh)
             eng.lib.dfb_cov_free(cov)

@@ -302,6 +302,14 @@ int calc_pval_device(dfb_ctx* ctx, const double* areas_dev, int64_t R, const dou
 // ------------------------------------------------------------------------------------------
 // FWER: per-permutation maximum (areas are >= 0, so the IEEE bit pattern orders like the value)
 
+// fullNullSummary$area <- abs(stat) * width  (R/mergeResults.R:231): the genome-wide pool ranks this
+// product, which differs from the summed area of calculatePvalues in the last ulps
+__global__ void merge_area_kernel(const double* __restrict__ stat, const int32_t* __restrict__ width, int64_t M,
+                                  double* __restrict__ out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x)
+        out[i] = __dmul_rn(fabs(stat[i]), (double)width[i]);
+}
+
 __global__ void perm_max_kernel(const double* __restrict__ area, const int32_t* __restrict__ perm, int64_t M,
                                 int64_t B, unsigned long long* __restrict__ bits) {
     // permutation ids arrive sorted, so a warp usually sees ONE id: reduce in the warp, one atomic
@@ -543,6 +551,19 @@ int dfb_nulls_copy_dev(const dfb_nulls* nl, double* area_dev, int32_t* perm_dev)
     if (M == 0) return DFB_OK;
     if (area_dev) DFB_CUDA(cudaMemcpyAsync(area_dev, nl->area.p, M * 8, cudaMemcpyDeviceToDevice, nl->ctx->stream));
     if (perm_dev) DFB_CUDA(cudaMemcpyAsync(perm_dev, nl->perm.p, M * 4, cudaMemcpyDeviceToDevice, nl->ctx->stream));
+    return DFB_OK;
+}
+
+int dfb_nulls_merge_areas_dev(const dfb_nulls* nl, double* area_dev) {
+    DFB_REQUIRE(nl && (area_dev || nl->count == 0), "dfb_nulls_merge_areas_dev: NULL argument");
+    if (nl->count == 0) return DFB_OK;
+    dfb_ctx* ctx = nl->ctx;
+    {
+        KTimer t(ctx, DFB_K_PVAL);
+        merge_area_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nl->count, 256), (int64_t)ctx->sm_count * 8), 256, 0,
+                            ctx->stream>>>(nl->stat.p, nl->width.p, nl->count, area_dev);
+    }
+    DFB_CUDA(cudaGetLastError());
     return DFB_OK;
 }
 

@@ -63,9 +63,12 @@ def exchange_nulls(local_area, local_max, dist=None, group=None):
     return [pool[r * cap: r * cap + counts_h[r]] for r in range(world)], gmax
 
 
-def genomewide_pvalues(engine, regions_handle, nulls_handle, B, cutoff_used, torch, device, dist=None):
+def genomewide_pvalues(engine, regions_handle, nulls_handle, B, cutoff_used, torch, device, dist=None,
+                       merge_area=False):
     """This rank's regions ranked against the genome-wide null pool (GPU path; used by bench.py).
-    Returns (pvalues, fwer) device tensors (regions in up-then-dn order) and the pool size."""
+    Returns (pvalues, fwer) device tensors (regions in up-then-dn order) and the pool size.
+    merge_area=True pools `abs(stat) * width` exactly as mergeResults does (R/mergeResults.R:231);
+    False pools the summed areas calculatePvalues ranks (the two differ in the last ulps)."""
     from . import _lib as L
     lib = engine.lib
     M = int(lib.dfb_nulls_count(nulls_handle))
@@ -74,7 +77,10 @@ def genomewide_pvalues(engine, regions_handle, nulls_handle, B, cutoff_used, tor
     perm = torch.zeros(max(M, 1), device=device, dtype=torch.int32)
     mx = torch.empty(B, device=device, dtype=torch.float64)
     a_dev = torch.empty(max(R, 1), device=device, dtype=torch.float64)
-    L.check(lib.dfb_nulls_copy_dev(nulls_handle, C.c_void_p(area.data_ptr()), C.c_void_p(perm.data_ptr())))
+    L.check(lib.dfb_nulls_copy_dev(nulls_handle, None if merge_area else C.c_void_p(area.data_ptr()),
+                                   C.c_void_p(perm.data_ptr())))
+    if merge_area:
+        L.check(lib.dfb_nulls_merge_areas_dev(nulls_handle, C.c_void_p(area.data_ptr())))
     L.check(lib.dfb_perm_max_dev(engine.h, C.c_void_p(area.data_ptr()), C.c_void_p(perm.data_ptr()), M, B, -1.0,
                                  C.c_void_p(mx.data_ptr())))
     L.check(lib.dfb_regions_copy_areas_dev(engine.h, regions_handle, C.c_void_p(a_dev.data_ptr())))

@@ -226,6 +226,9 @@ int dfb_nulls_get(const dfb_nulls* nl, int dup, double* stat, int32_t* width, do
                   int32_t* permutation);
 /* device access for multi-GPU pooling (areas as doubles, permutation ids as int32) */
 int dfb_nulls_copy_dev(const dfb_nulls* nl, double* area_dev, int32_t* perm_dev);
+/* the null areas as mergeResults() pools them: abs(stat) * width (R/mergeResults.R:231), which is
+ * not bit-identical to the summed area calculatePvalues ranks; written to device memory [count] */
+int dfb_nulls_merge_areas_dev(const dfb_nulls* nl, double* area_dev);
 
 /* Multi-GPU pooling without a second sort (R/mergeResults.R:216-235, 304-307): every rank keeps its
  * null areas sorted from its own p-value ranking; ranks all-gather those sorted lists and count,

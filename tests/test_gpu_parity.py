@@ -626,6 +626,14 @@ def test_pooled_pvalues_single_rank(dfb, eng):
         L.check(e2.lib.dfb_nulls_get(nh, 0, None, None, na.ctypes.data_as(L.c_f64p), npm.ctypes.data_as(L.c_i32p)))
         want = O.calculate_fwer(cut, na, npm, cfg["B"], area)
         assert np.array_equal(fwer.cpu().numpy()[order], want)
+        # mergeResults pools abs(stat) * width instead of the summed areas (R/mergeResults.R:231)
+        p_m, fwer_m, _ = pool.genomewide_pvalues(e2, rh, nh, cfg["B"], cut, torch, device, merge_area=True)
+        torch.cuda.synchronize()
+        ns, nw = np.empty(M), np.empty(M, dtype=np.int32)
+        L.check(e2.lib.dfb_nulls_get(nh, 0, ns.ctypes.data_as(L.c_f64p), nw.ctypes.data_as(L.c_i32p), None, None))
+        marea = np.abs(ns) * nw
+        assert np.array_equal(p_m.cpu().numpy()[order], O.calc_pval(area, np.repeat(marea, 2)))
+        assert np.array_equal(fwer_m.cpu().numpy()[order], O.calculate_fwer(cut, marea, npm, cfg["B"], area))
         e2.lib.dfb_regions_free(rh)
         e2.lib.dfb_nulls_free(nh)
         e2.lib.dfb_cov_free(cov)
