@@ -183,6 +183,28 @@ calculatePvalues <- function(coveragePrep, models, fstats, nPermute = 1L,
     list(regions = regs, coverageMatrix = m)
 }
 
+## ---- regionMatrix (R/regionMatrix.R:124-168): chromosomes one after the other on the GPU (the reference's bpmapply
+## over chromosomes :164 would fork the CUDA context); returnBP = TRUE is served by the reference's own
+## getRegionCoverage() on the returned regions
+regionMatrix <- function(fullCov, cutoff = 5, L, totalMapped = 80e6, targetSize = 80e6, runFilter = TRUE,
+    returnBP = TRUE, ...) {
+    stopifnot(!is.null(cutoff), !is.null(names(fullCov)))                                 # :128-131
+    if (!runFilter) stop("runFilter = FALSE: pass the unfiltered coverage; the filter runs on the device")
+    maxRegionGap <- derfinder:::.advanced_argument("maxRegionGap", 0L, ...)
+    maxClusterGap <- derfinder:::.advanced_argument("maxClusterGap", 300L, ...)
+    res <- lapply(names(fullCov), function(chr) {
+        covInfo <- fullCov[[chr]]
+        if (!is.list(covInfo) || is(covInfo, "DataFrame")) covInfo <- list(coverage = covInfo)
+        out <- .regionMatrixByChr(covInfo, chr, cutoff, L, totalMapped, targetSize, maxRegionGap, maxClusterGap)
+        if (returnBP && length(out$regions) > 0)
+            out$bpCoverage <- derfinder::getRegionCoverage(fullCov = fullCov[chr], regions = out$regions,
+                totalMapped = totalMapped, targetSize = targetSize, verbose = FALSE)
+        out
+    })
+    names(res) <- names(fullCov)
+    res
+}
+
 ## ---- railMatrix's per-chunk coverage matrix (.railMatChrRegion, R/railMatrix.R:238-262): the caller imports the
 ## selected ranges of every sample BigWig (`import(sampleFile, selection = reduce(regs), as = "RleList")`) and hands
 ## the Rle columns over; one call replaces the bpmapply over .railMatChrRegionCov (:264-290)
