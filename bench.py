@@ -287,7 +287,8 @@ class Step:
     def device_pass(self, keep=False):
         L, lib, eng = self.L, self.lib, self.eng
         cov = C.c_void_p()
-        L.check(lib.dfb_cov_from_dense_dev(eng.h, self.n, self.N, L.DFB_I32, C.c_void_p(self.work["cov"].data_ptr()),
+        # the coverage is resident in HBM in the engine's layout: the handle reads it in place
+        L.check(lib.dfb_cov_view_dense_dev(eng.h, self.n, self.N, L.DFB_I32, C.c_void_p(self.work["cov"].data_ptr()),
                                            self.N, L.ptr(self.pl, C.c_int32), len(self.pl), self.work["pos_first"],
                                            C.byref(cov)))
         try:
@@ -395,6 +396,10 @@ def main():
     ap.add_argument("--e2e-input", default="rle", choices=["rle", "dense"],
                     help="host coverage format of the end-to-end pass: Rle columns (the reference's type) or dense")
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (developer knob)")
+    ap.add_argument("--as-rank", type=int, default=None,
+                    help="developer: generate the synthetic chromosome rank R would own (single-GPU runs)")
+    ap.add_argument("--force-pool", action="store_true",
+                    help="developer: run the genome-wide pooling step on one GPU too (its local cost without NCCL)")
     ap.add_argument("--screen", type=int, default=None, help="override the engine's tcgen05 screening option")
     args = ap.parse_args()
     cfg = WORKLOADS[args.workload]
@@ -422,7 +427,8 @@ def main():
     W = max(args.warmup, 3)
 
     # every rank owns its own synthetic chromosome (same shape): weak scaling
-    work = make_workload(cfg, 20140923 + 2 + 1000 * rank, torch=torch, device=device)
+    data_rank = rank if args.as_rank is None else args.as_rank
+    work = make_workload(cfg, 20140923 + 2 + 1000 * data_rank, torch=torch, device=device)
     n, N, B = cfg["n"], cfg["N"], cfg["B"]
     perm = permutation_indices(range(1, B + 1), n, "Rejection")  # same relabellings on every rank
     cut = theoretical_cutoff(cfg["alpha"], work["mod"], work["mod0"])
@@ -434,9 +440,17 @@ def main():
         eng.set_option(key, float(val))
     step = Step(eng, work, perm, cut, torch)
 
+    timed_pass = None  # per-step events around this rank's own chromosome pass (timed region only)
+
     def one_step():
-        if world > 1:
+        if world > 1 or args.force_pool:
+            if timed_pass is not None:
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
             (R, M), rh, nh, cov = step.device_pass(keep=True)
+            if timed_pass is not None:
+                e1.record()
+                timed_pass.append((e0, e1))
             p_dev, fwer, npool = pool.genomewide_pvalues(eng, rh, nh, B, cut, torch, device, dist=dist,
                                                              merge_area=True)
             eng.lib.dfb_regions_free(rh)
@@ -452,15 +466,22 @@ def main():
         dist.barrier()
     eng.reset_counters()
     eng.enable_timing(True)
+    pool.reset_profile()
     sampler = ClockSampler(local)
     sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     ev0.record()
+    timed_pass = []
     for _ in range(args.steps):
         R, M = one_step()
     ev1.record()
     torch.cuda.synchronize()
+    own_ms = sum(a.elapsed_time(b) for a, b in timed_pass) / max(len(timed_pass), 1)
+    timed_pass = None
+    pool_prof = pool.profile_summary()
+    pool.reset_profile()
+    os.environ.pop("DFB_POOL_PROFILE", None)
     sampler.stop_flag = True
     sampler.join()
     ms = ev0.elapsed_time(ev1) / args.steps
@@ -471,6 +492,10 @@ def main():
         t = torch.tensor([ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        own = torch.zeros(world, device=device, dtype=torch.float64)
+        own[rank] = own_ms
+        dist.all_reduce(own, op=dist.ReduceOp.SUM)
+        own_all = [round(v, 4) for v in own.tolist()]
         dist.barrier()
 
     # end to end through host buffers (pinned), same pass
@@ -507,6 +532,15 @@ def main():
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                     "last_step_breakdown_ms": {k: round(v, 3) for k, v in step.last_breakdown.items()}},
             "clocks": sampler.result()}
+    if world > 1:
+        # every rank's own chromosome pass (different synthetic chromosomes: the slowest bounds the step)
+        # and what the genome-wide pooling (two all-gathers + ranking) adds on top of it
+        line["multi_gpu"] = {"chromosome_pass_ms_per_rank": own_all,
+                             "pooling_ms": round(ms - max(own_all), 4),
+                             "collectives": "NCCL all-gather of the counts (side stream) + one all-gather of the "
+                                            "records {count, per-permutation max, padded null areas}"}
+        if pool_prof and rank == 0:
+            print("pool sections (ms):", pool_prof, file=sys.stderr)
     if rank == 0:
         peaks = {}
         try:

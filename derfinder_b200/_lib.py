@@ -55,6 +55,8 @@ SIGNATURES = {
                                    C.c_int, c_vpp]),
     "dfb_cov_from_dense_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64, c_i32p,
                                          C.c_int64, C.c_int, c_vpp]),
+    "dfb_cov_view_dense_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64, c_i32p,
+                                         C.c_int64, C.c_int, c_vpp]),
     "dfb_cov_free": (None, [C.c_void_p]),
     "dfb_cov_info": (C.c_int, [C.c_void_p, c_i64p, C.POINTER(C.c_int), c_i64p, C.POINTER(C.c_int), c_i64p,
                                C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -86,6 +88,9 @@ SIGNATURES = {
     "dfb_nulls_counts_per_perm": (C.c_int, [C.c_void_p, c_i64p]),
     "dfb_nulls_get": (C.c_int, [C.c_void_p, C.c_int, c_f64p, c_i32p, c_f64p, c_i32p]),
     "dfb_nulls_copy_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dfb_pool_local_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p]),
+    "dfb_pool_rank_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_double,
+                                    C.c_void_p, C.c_void_p]),
     "dfb_nulls_merge_areas_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dfb_nulls_sorted_areas_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfb_regions_null_hist_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -156,6 +156,7 @@ struct KTimer {
     }
 };
 
+typedef cudaStream_t dfb_ctx_stream_t;
 // Stream-ordered device buffer (cudaMallocAsync pool: repeated calls reuse memory without
 // device-wide synchronisation).
 template <typename T>
@@ -163,23 +164,32 @@ struct DevBuf {
     T* p = nullptr;
     size_t n = 0;
     cudaStream_t s = nullptr;
+    bool borrowed = false;  // p belongs to the caller (dfb_cov_view_dense_dev): never freed here
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
     DevBuf& operator=(const DevBuf&) = delete;
-    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s) { o.p = nullptr; o.n = 0; }
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n), s(o.s), borrowed(o.borrowed) { o.p = nullptr; o.n = 0; }
     DevBuf& operator=(DevBuf&& o) noexcept {
         if (this != &o) {
             release();
-            p = o.p; n = o.n; s = o.s;
+            p = o.p; n = o.n; s = o.s; borrowed = o.borrowed;
             o.p = nullptr; o.n = 0;
         }
         return *this;
     }
     ~DevBuf() { release(); }
     void release() {
-        if (p) cudaFreeAsync(p, s);
+        if (p && !borrowed) cudaFreeAsync(p, s);
         p = nullptr;
         n = 0;
+        borrowed = false;
+    }
+    void borrow(dfb_ctx_stream_t stream, T* ptr, size_t count) {
+        release();
+        p = ptr;
+        n = count;
+        s = stream;
+        borrowed = true;
     }
     int alloc(dfb_ctx* ctx, size_t count) {
         release();
@@ -207,6 +217,8 @@ struct DevBuf {
 // bump allocation from the context's pinned arena (valid until the next arena_reset)
 void* arena_alloc(dfb_ctx* ctx, size_t bytes);
 void arena_reset(dfb_ctx* ctx);
+// give back the most recent arena_alloc of a block (no-op if something was allocated after it)
+void arena_release(dfb_ctx* ctx, void* ptr, size_t bytes);
 // asynchronous D2H into arena memory: returns the pinned pointer, valid after the next stream sync
 template <typename T>
 static inline T* d2h_async_pinned(dfb_ctx* ctx, const T* src_dev, size_t count) {

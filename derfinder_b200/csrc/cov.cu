@@ -785,7 +785,8 @@ int dfb_filter_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, co
 }
 
 static int cov_from_dense_impl(dfb_ctx* ctx, int n, int64_t N, int dtype, const void* cov, int64_t ld, bool on_device,
-                               const int32_t* pos_len, int64_t pos_nruns, int pos_first, dfb_cov** out) {
+                               const int32_t* pos_len, int64_t pos_nruns, int pos_first, dfb_cov** out,
+                               bool view = false) {
     DFB_REQUIRE(ctx && out && (cov || N == 0), "dfb_cov_from_dense: NULL argument");
     *out = nullptr;
     DFB_REQUIRE(n > 0 && N >= 0 && ld >= N, "dfb_cov_from_dense: bad shape (n=%d, N=%lld, ld=%lld)", n, (long long)N,
@@ -797,19 +798,26 @@ static int cov_from_dense_impl(dfb_ctx* ctx, int n, int64_t N, int dtype, const 
     c->n = n;
     c->N = N;
     c->dtype = dtype;
-    int rc = c->pos.build(ctx, pos_len, pos_nruns, pos_first);
-    if (rc >= 0 && c->pos.N != N) {
-        set_error("nrow(coverage) = %lld does not match sum(position) = %lld", (long long)N, (long long)c->pos.N);
-        rc = DFB_EINVAL;
+    // the matrix copy is queued first: the device moves the coverage while the host builds the position
+    // index below (its run loops and small uploads used to leave the GPU idle at the start of a step)
+    // a device matrix in the engine's own layout (row stride a multiple of 64 elements, 256-byte aligned
+    // base) is read in place when the caller asks for a view: no second copy of resident coverage
+    view = view && on_device && N > 0 && ld % 64 == 0 && ((uintptr_t)cov & 255u) == 0;
+    int rc = DFB_OK;
+    if (view) {
+        c->ld = ld;
+        if (dtype == DFB_I32) c->xi.borrow(ctx->stream, (int32_t*)const_cast<void*>(cov), (size_t)n * ld);
+        else c->xd.borrow(ctx->stream, (double*)const_cast<void*>(cov), (size_t)n * ld);
+    } else {
+        rc = alloc_matrix(c);
     }
-    if (rc >= 0) rc = alloc_matrix(c);
     if (rc < 0) {
         delete c;
         return rc;
     }
     const size_t es = dtype == DFB_I32 ? 4 : 8;
     void* dst = dtype == DFB_I32 ? (void*)c->xi.p : (void*)c->xd.p;
-    if (N > 0) {
+    if (N > 0 && !view) {
         cudaError_t e = cudaMemcpy2DAsync(dst, (size_t)c->ld * es, cov, (size_t)ld * es, (size_t)N * es, (size_t)n,
                                           on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, ctx->stream);
         if (e != cudaSuccess) {
@@ -817,6 +825,16 @@ static int cov_from_dense_impl(dfb_ctx* ctx, int n, int64_t N, int dtype, const 
             delete c;
             return DFB_ECUDA;
         }
+    }
+    rc = c->pos.build(ctx, pos_len, pos_nruns, pos_first);
+    if (rc >= 0 && c->pos.N != N) {
+        set_error("nrow(coverage) = %lld does not match sum(position) = %lld", (long long)N, (long long)c->pos.N);
+        rc = DFB_EINVAL;
+    }
+    if (rc < 0) {
+        cudaStreamSynchronize(ctx->stream);
+        delete c;
+        return rc;
     }
     *out = c;
     return DFB_OK;
@@ -834,6 +852,11 @@ int dfb_cov_from_dense_dev(dfb_ctx* ctx, int n, int64_t N, int dtype, const void
     return cov_from_dense_impl(ctx, n, N, dtype, cov_dev, ld, true, pos_len, pos_nruns, pos_first, out);
 }
 
+int dfb_cov_view_dense_dev(dfb_ctx* ctx, int n, int64_t N, int dtype, const void* cov_dev, int64_t ld,
+                           const int32_t* pos_len, int64_t pos_nruns, int pos_first, dfb_cov** out) {
+    return cov_from_dense_impl(ctx, n, N, dtype, cov_dev, ld, true, pos_len, pos_nruns, pos_first, out, true);
+}
+
 int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, const int32_t* const* lengths,
                      const int64_t* nruns, int64_t N, const int32_t* pos_len, int64_t pos_nruns, int pos_first,
                      dfb_cov** out) {
@@ -847,12 +870,7 @@ int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, 
     c->n = n;
     c->N = N;
     c->dtype = dtype;
-    int rc = c->pos.build(ctx, pos_len, pos_nruns, pos_first);
-    if (rc >= 0 && c->pos.N != N) {
-        set_error("nrow(coverage) = %lld does not match sum(position) = %lld", (long long)N, (long long)c->pos.N);
-        rc = DFB_EINVAL;
-    }
-    if (rc >= 0) rc = alloc_matrix(c);
+    int rc = alloc_matrix(c);
     if (rc < 0) {
         delete c;
         return rc;
@@ -871,6 +889,19 @@ int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, 
         else expand_rle_kernel<double><<<grid, K1_THREADS, 0, ctx->stream>>>(R, c->ld, c->xd.p);
     }
     cudaError_t e = cudaGetLastError();
+    // the position index is built while the expansion runs (host run loops + two small uploads)
+    if (e == cudaSuccess) {
+        rc = c->pos.build(ctx, pos_len, pos_nruns, pos_first);
+        if (rc >= 0 && c->pos.N != N) {
+            set_error("nrow(coverage) = %lld does not match sum(position) = %lld", (long long)N, (long long)c->pos.N);
+            rc = DFB_EINVAL;
+        }
+        if (rc < 0) {
+            cudaStreamSynchronize(ctx->stream);
+            delete c;
+            return rc;
+        }
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // `up` buffers die with this frame
     if (e != cudaSuccess) {
         set_error("Rle expansion: %s", cudaGetErrorString(e));

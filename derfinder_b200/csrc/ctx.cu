@@ -41,6 +41,15 @@ void* arena_alloc(dfb_ctx* ctx, size_t bytes) {
     return p;
 }
 
+void arena_release(dfb_ctx* ctx, void* ptr, size_t bytes) {
+    bytes = (bytes + 63) & ~(size_t)63;
+    for (auto& b : ctx->pin_blocks)
+        if (b.p + b.used == (char*)ptr + bytes && b.used >= bytes) {
+            b.used -= bytes;
+            return;
+        }
+}
+
 void arena_reset(dfb_ctx* ctx) {
     for (auto& b : ctx->pin_blocks) b.used = 0;
 }

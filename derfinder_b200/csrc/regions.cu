@@ -28,48 +28,75 @@ using dfb::h2d;
 using dfb::set_error;
 
 int PositionIndex::build(dfb_ctx* ctx, const int32_t* pos_len, int64_t nruns, int pos_first) {
+    // This runs on the host at the start of every chromosome while the device has little queued, so
+    // the common case -- runs already normalised (all lengths > 0, values alternating) -- is a plain
+    // copy plus one pass over the TRUE runs into pre-sized arrays.
     len.clear();
     first = pos_first ? 1 : 0;
     chr_len = 0;
-    // normalise: drop zero-length runs, merge neighbours of equal value
-    int cur_val = first;
-    bool have = false;
-    int last_val = 0;
-    for (int64_t r = 0; r < nruns; ++r, cur_val ^= 1) {
-        DFB_REQUIRE(pos_len[r] >= 0, "position: negative run length");
-        if (pos_len[r] == 0) continue;
-        if (have && last_val == cur_val) {
-            DFB_REQUIRE((int64_t)len.back() + pos_len[r] <= INT32_MAX, "position run longer than 2^31-1");
-            len.back() += pos_len[r];
-        } else {
-            if (!have) first = cur_val;
-            len.push_back(pos_len[r]);
-            last_val = cur_val;
-            have = true;
+    int32_t lo = 1;
+    int64_t total = 0;
+    for (int64_t r = 0; r < nruns; ++r) {
+        lo = std::min(lo, pos_len[r]);
+        total += pos_len[r];
+    }
+    DFB_REQUIRE(lo >= 0, "position: negative run length");
+    if (lo > 0) {
+        len.assign(pos_len, pos_len + nruns);
+        chr_len = total;
+    } else {
+        // normalise: drop zero-length runs, merge neighbours of equal value
+        int cur_val = first;
+        bool have = false;
+        int last_val = 0;
+        for (int64_t r = 0; r < nruns; ++r, cur_val ^= 1) {
+            if (pos_len[r] == 0) continue;
+            if (have && last_val == cur_val) {
+                DFB_REQUIRE((int64_t)len.back() + pos_len[r] <= INT32_MAX, "position run longer than 2^31-1");
+                len.back() += pos_len[r];
+            } else {
+                if (!have) first = cur_val;
+                len.push_back(pos_len[r]);
+                last_val = cur_val;
+                have = true;
+            }
+            chr_len += pos_len[r];
         }
-        chr_len += pos_len[r];
     }
     DFB_REQUIRE(chr_len <= INT32_MAX, "chromosome length %lld exceeds R's integer range", (long long)chr_len);
-    h_gstart.clear();
-    h_cum.clear();
-    int64_t gpos = 1, kept = 0;
-    int v = first;
-    for (size_t r = 0; r < len.size(); ++r, v ^= 1) {
-        if (v) {
-            h_gstart.push_back((int32_t)gpos);
-            h_cum.push_back(kept);
-            kept += len[r];
-        }
-        gpos += len[r];
+    const size_t nl = len.size();
+    const size_t r0 = first ? 0 : 1;  // index of the first TRUE run
+    K = nl > r0 ? (int64_t)((nl - r0 + 1) / 2) : 0;
+    h_gstart.resize((size_t)K);
+    h_cum.resize((size_t)K + 1);
+    int64_t gpos = 1 + ((r0 == 1 && nl > 0) ? (int64_t)len[0] : 0), kept = 0;
+    const int32_t* lp = len.data();
+    for (size_t k = 0, r = r0; r < nl; ++k, r += 2) {
+        h_gstart[k] = (int32_t)gpos;
+        h_cum[k] = kept;
+        kept += lp[r];
+        gpos += (int64_t)lp[r] + (r + 1 < nl ? (int64_t)lp[r + 1] : 0);
     }
-    h_cum.push_back(kept);
+    h_cum[(size_t)K] = kept;
     N = kept;
-    K = (int64_t)h_gstart.size();
     DFB_TRY(run_gstart.alloc(ctx, (size_t)std::max<int64_t>(K, 1)));
     DFB_TRY(run_cum.alloc(ctx, (size_t)K + 1));
-    DFB_TRY(h2d(ctx, run_gstart.p, h_gstart.data(), (size_t)K * sizeof(int32_t)));
-    DFB_TRY(h2d(ctx, run_cum.p, h_cum.data(), (size_t)(K + 1) * sizeof(int64_t)));
-    DFB_CUDA(cudaStreamSynchronize(ctx->stream));  // host vectors may be reallocated by the caller
+    // one pinned staging block for both tables: a pageable cudaMemcpyAsync first drains the stream and
+    // then goes through the driver's bounce buffer, twice
+    const size_t b_g = (size_t)K * sizeof(int32_t), b_c = (size_t)(K + 1) * sizeof(int64_t);
+    unsigned char* pin = (unsigned char*)dfb::arena_alloc(ctx, b_c + b_g);
+    if (pin) {
+        memcpy(pin, h_cum.data(), b_c);
+        memcpy(pin + b_c, h_gstart.data(), b_g);
+        DFB_TRY(h2d(ctx, run_cum.p, pin, b_c));
+        DFB_TRY(h2d(ctx, run_gstart.p, pin + b_c, b_g));
+    } else {
+        DFB_TRY(h2d(ctx, run_gstart.p, h_gstart.data(), b_g));
+        DFB_TRY(h2d(ctx, run_cum.p, h_cum.data(), b_c));
+    }
+    const cudaError_t e = cudaStreamSynchronize(ctx->stream);  // host vectors may be reallocated by the caller
+    if (pin) dfb::arena_release(ctx, pin, b_c + b_g);
+    DFB_CUDA(e);
     return DFB_OK;
 }
 

@@ -5,18 +5,25 @@ Chromosomes are independent up to the genome-wide p-value / FWER ranking of `mer
 on the pool, :380-386 takes the per-permutation maximum area over the genome).  So every rank runs
 the whole per-chromosome pipeline on its own GPU and only
 
-    counts [world]            all-gather   (how many null regions each rank found)
-    null areas [cap] padded   all-gather   (variable length -> fixed capacity)
-    per-permutation max [B]   all-reduce(max)
+    counts [world]                     all-gather on a SIDE stream (how many null regions each rank
+                                       found; the host needs the largest to size the records, and
+                                       waits for its peers only -- not for its own pending GPU work)
+    records [world][1 + B + cap]       ONE all-gather: {count, per-permutation max area, null areas
+                                       padded with -1 to the largest count}
 
 cross NVLink.  Tensors stay where they are (CUDA with NCCL, CPU with gloo in the tests).  Each rank
-ranks its own regions (already sorted by area) against the pooled, UNSORTED null lists with a
-histogram (`dfb_regions_null_hist_dev` / `dfb_regions_hist_counts_dev`): nothing is sorted for the
-pooling.
+ranks its own regions (already sorted by area) against the gathered, UNSORTED null areas with a
+histogram (`dfb_pool_rank_dev`): nothing is sorted for the pooling and the per-permutation maxima
+are reduced from the same records (no separate all-reduce).
 """
 from __future__ import annotations
 
 import ctypes as C
+import os
+
+# developer instrumentation (DFB_POOL_PROFILE=1): CUDA-event time of the sections of
+# genomewide_pvalues, summed over calls -> pool.PROFILE
+PROFILE = {"calls": 0, "events": []}
 
 
 def assign_chromosomes(sizes, world):
@@ -31,36 +38,43 @@ def assign_chromosomes(sizes, world):
     return bins
 
 
-def exchange_nulls(local_area, local_max, dist=None, group=None):
-    """Pool null areas and per-permutation maxima over all ranks.
-
-    local_area: 1-d float64 tensor, this rank's null areas (any length, may be empty).
-    local_max : [B] float64 tensor, max null area per permutation on this rank, NEGATIVE where the
-                rank found no region for that permutation (areas are >= 0).
-    Returns (segments, global_max): `segments[r]` is rank r's area list (a view into the gathered
-    buffer, in the order rank r supplied it -- padding is dropped by COUNT, so a genuine NaN area
-    survives) and global_max the element-wise maximum of local_max.  `torch.cat(segments)` is the
-    pooled list in rank order.  Without an initialised process group this is the identity.
-    """
+def exchange_counts(count, device, dist=None, group=None, side_stream=None):
+    """Every rank's null-region count, as a Python list.  On CUDA the tiny all-gather and the host
+    read run on `side_stream`, so the caller's main stream (still finishing the chromosome pass) is
+    neither waited for nor drained; the host blocks until the peers have reached the same point."""
     import torch
     if dist is None:
         import torch.distributed as dist
     if not (dist.is_available() and dist.is_initialized()):
-        return [local_area], local_max
+        return [int(count)]
     world = dist.get_world_size(group)
-    dev = local_area.device
-    count = torch.tensor([local_area.numel()], device=dev, dtype=torch.int64)
-    counts = torch.empty(world, device=dev, dtype=torch.int64)
-    dist.all_gather_into_tensor(counts, count, group=group)
-    gmax = local_max.clone()
-    dist.all_reduce(gmax, op=dist.ReduceOp.MAX, group=group)
-    counts_h = counts.tolist()  # the one host synchronisation of the exchange
-    cap = max(max(counts_h), 1)
-    mine = torch.empty(cap, device=dev, dtype=torch.float64)
-    mine[: local_area.numel()] = local_area
-    pool = torch.empty(world * cap, device=dev, dtype=torch.float64)
-    dist.all_gather_into_tensor(pool, mine, group=group)
-    return [pool[r * cap: r * cap + counts_h[r]] for r in range(world)], gmax
+    if device.type != "cuda":
+        mine = torch.tensor([int(count)], dtype=torch.int64)
+        out = torch.empty(world, dtype=torch.int64)
+        dist.all_gather_into_tensor(out, mine, group=group)
+        return out.tolist()
+    side = side_stream or torch.cuda.Stream(device=device)
+    with torch.cuda.stream(side):
+        mine = torch.tensor([int(count)], dtype=torch.int64).pin_memory().to(device, non_blocking=True)
+        out = torch.empty(world, device=device, dtype=torch.int64)
+        dist.all_gather_into_tensor(out, mine, group=group)
+        return out.tolist()  # synchronises the side stream only
+
+
+def gather_records(record, dist=None, group=None):
+    """All-gather of equal-length 1-d records -> [world, len] (the identity without a process group)."""
+    import torch
+    if dist is None:
+        import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return record[None, :]
+    world = dist.get_world_size(group)
+    out = torch.empty(world * record.numel(), device=record.device, dtype=record.dtype)
+    dist.all_gather_into_tensor(out, record.contiguous(), group=group)
+    return out.view(world, record.numel())
+
+
+_side_streams = {}
 
 
 def genomewide_pvalues(engine, regions_handle, nulls_handle, B, cutoff_used, torch, device, dist=None,
@@ -68,51 +82,66 @@ def genomewide_pvalues(engine, regions_handle, nulls_handle, B, cutoff_used, tor
     """This rank's regions ranked against the genome-wide null pool (GPU path; used by bench.py).
     Returns (pvalues, fwer) device tensors (regions in up-then-dn order) and the pool size.
     merge_area=True pools `abs(stat) * width` exactly as mergeResults does (R/mergeResults.R:231);
-    False pools the summed areas calculatePvalues ranks (the two differ in the last ulps)."""
+    False pools the summed areas calculatePvalues ranks (the two differ in the last ulps).
+
+    `exchange_counts` (side stream), `dfb_pool_local_dev` (this rank's record), `gather_records`
+    (one all-gather), `dfb_pool_rank_dev` (histogram of the pooled, UNSORTED nulls against this rank's
+    sorted regions, p-values and FWER).  The main stream is never synchronised with the host."""
     from . import _lib as L
     lib = engine.lib
     M = int(lib.dfb_nulls_count(nulls_handle))
     R = int(lib.dfb_regions_count(regions_handle))
-    area = torch.empty(max(M, 1), device=device, dtype=torch.float64)
-    perm = torch.zeros(max(M, 1), device=device, dtype=torch.int32)
-    mx = torch.empty(B, device=device, dtype=torch.float64)
-    a_dev = torch.empty(max(R, 1), device=device, dtype=torch.float64)
-    L.check(lib.dfb_nulls_copy_dev(nulls_handle, None if merge_area else C.c_void_p(area.data_ptr()),
-                                   C.c_void_p(perm.data_ptr())))
-    if merge_area:
-        L.check(lib.dfb_nulls_merge_areas_dev(nulls_handle, C.c_void_p(area.data_ptr())))
-    L.check(lib.dfb_perm_max_dev(engine.h, C.c_void_p(area.data_ptr()), C.c_void_p(perm.data_ptr()), M, B, -1.0,
-                                 C.c_void_p(mx.data_ptr())))
-    L.check(lib.dfb_regions_copy_areas_dev(engine.h, regions_handle, C.c_void_p(a_dev.data_ptr())))
+    marks = []
+
+    def mark(name):
+        if os.environ.get("DFB_POOL_PROFILE"):
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append((name, ev))
+
+    mark("start")
+    key = (device.index, id(dist))
+    if key not in _side_streams:
+        _side_streams[key] = torch.cuda.Stream(device=device)
+    counts = exchange_counts(M, device, dist=dist, side_stream=_side_streams[key])
+    world = len(counts)
+    cap = max(max(counts), 1)
+    record = torch.empty(1 + B + cap, device=device, dtype=torch.float64)
+    p_dev = torch.empty(max(R, 1), device=device, dtype=torch.float64)
+    fwer = torch.empty(max(R, 1), device=device, dtype=torch.float64)
     # the engine and torch share one stream in bench.py; otherwise order them explicitly
     shared = engine.stream_handle == torch.cuda.current_stream().cuda_stream
     if not shared:
+        torch.cuda.current_stream().synchronize()
+    L.check(lib.dfb_pool_local_dev(engine.h, nulls_handle, B, 1 if merge_area else 0, cap,
+                                   C.c_void_p(record.data_ptr())))
+    if not shared:
         engine.sync()
-    segments, gmax = exchange_nulls(area[:M], mx, dist=dist)
-    # a permutation without any null region anywhere contributes cutoffFstatUsed (R/mergeResults.R:382)
-    gmax = torch.where(gmax < 0, torch.full_like(gmax, float(cutoff_used)), gmax)
-    # this rank's regions are sorted by area already: the pooled nulls (unsorted, rank by rank) are
-    # ranked against them with a histogram -- nothing is sorted for the pooling
-    hist = torch.zeros(R + 1, device=device, dtype=torch.int32)
-    counts = torch.zeros(max(R, 1), device=device, dtype=torch.int64)
-    total = 0
+    mark("local")
+    records = gather_records(record, dist=dist)
+    mark("exchange")
     if not shared:
         torch.cuda.current_stream().synchronize()
-    for seg in segments:
-        total += seg.numel()
-        if seg.numel():
-            L.check(lib.dfb_regions_null_hist_dev(engine.h, regions_handle, C.c_void_p(seg.data_ptr()), seg.numel(),
-                                                  C.c_void_p(hist.data_ptr())))
-    L.check(lib.dfb_regions_hist_counts_dev(engine.h, regions_handle, C.c_void_p(hist.data_ptr()),
-                                            C.c_void_p(counts.data_ptr())))
+    L.check(lib.dfb_pool_rank_dev(engine.h, regions_handle, C.c_void_p(records.data_ptr()), world, B, cap,
+                                  float(cutoff_used), C.c_void_p(p_dev.data_ptr()), C.c_void_p(fwer.data_ptr())))
     if not shared:
         engine.sync()
-    a_dev, counts = a_dev[:R], counts[:R]
-    # every null entry is stored twice by the reference (R/calculatePvalues.R:346-354): weight 2
-    # divide by TENSORS: torch turns `tensor / python_scalar` into a multiplication by the reciprocal,
-    # which is not the correctly rounded quotient R computes
-    num = 2.0 * counts.double() + 1.0
-    p_dev = num / torch.full_like(num, 2.0 * total + 1.0)
-    fnum = ((gmax[None, :] > a_dev[:, None]).sum(dim=1) + 1).double()
-    fwer = fnum / torch.full_like(fnum, float(B + 1))
-    return p_dev, fwer, total
+    mark("rank")
+    if marks:
+        PROFILE["calls"] += 1
+        PROFILE["events"].append(marks)
+    return p_dev[:R], fwer[:R], int(sum(counts))
+
+
+def reset_profile():
+    PROFILE["calls"] = 0
+    PROFILE["events"].clear()
+
+
+def profile_summary():
+    """Mean milliseconds per section over the recorded calls (call after a device synchronise)."""
+    out = {}
+    for marks in PROFILE["events"]:
+        for (_, a), (name, b) in zip(marks[:-1], marks[1:]):
+            out[name] = out.get(name, 0.0) + a.elapsed_time(b)
+    return {k: v / max(PROFILE["calls"], 1) for k, v in out.items()}

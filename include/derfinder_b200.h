@@ -131,6 +131,12 @@ int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values,
 int dfb_cov_from_dense_dev(dfb_ctx* ctx, int n, int64_t N, int dtype, const void* cov_dev,
                            int64_t ld, const int32_t* pos_len, int64_t pos_nruns, int pos_first,
                            dfb_cov** out);
+/* Zero-copy variant: when cov_dev is laid out like the engine's own matrix (ld a multiple of 64
+ * elements, base aligned to 256 bytes) the handle READS IT IN PLACE -- the caller keeps it alive and
+ * unmodified until dfb_cov_free; any other layout is copied as above. */
+int dfb_cov_view_dense_dev(dfb_ctx* ctx, int n, int64_t N, int dtype, const void* cov_dev,
+                           int64_t ld, const int32_t* pos_len, int64_t pos_nruns, int pos_first,
+                           dfb_cov** out);
 void dfb_cov_free(dfb_cov* cov);
 
 /* Shapes: N kept bases, n samples, chromosome length, dtype of the stored coverage, number of
@@ -226,6 +232,19 @@ int dfb_nulls_get(const dfb_nulls* nl, int dup, double* stat, int32_t* width, do
                   int32_t* permutation);
 /* device access for multi-GPU pooling (areas as doubles, permutation ids as int32) */
 int dfb_nulls_copy_dev(const dfb_nulls* nl, double* area_dev, int32_t* perm_dev);
+/* Genome-wide ranking in two calls per rank around ONE all-gather (R/mergeResults.R:216-235,
+ * 300-307, 380-386).  A rank's record is [count | max area of permutation 1..B, -1 when it has
+ * none | cap null areas padded with -1] (1 + B + cap doubles; cap >= every rank's count, agreed
+ * beforehand).  dfb_pool_local_dev writes this rank's record (merge_area != 0: the areas are
+ * abs(stat) * width, :231); the caller all-gathers the records (NCCL);  dfb_pool_rank_dev ranks
+ * this rank's regions against all records: pooled p-values (.calcPval on the concatenation, every
+ * entry counted twice) and FWER (.calculateFWER, empty permutation -> cutoff_used), both [R] on the
+ * device in up-then-dn order. */
+int dfb_pool_local_dev(dfb_ctx* ctx, const dfb_nulls* nl, int64_t B, int merge_area, int64_t cap,
+                       double* record_dev);
+int dfb_pool_rank_dev(dfb_ctx* ctx, const dfb_regions* r, const double* records_dev /* [world][1+B+cap] */,
+                      int world, int64_t B, int64_t cap, double cutoff_used, double* p_dev,
+                      double* fwer_dev);
 /* the null areas as mergeResults() pools them: abs(stat) * width (R/mergeResults.R:231), which is
  * not bit-identical to the summed area calculatePvalues ranks; written to device memory [count] */
 int dfb_nulls_merge_areas_dev(const dfb_nulls* nl, double* area_dev);

@@ -821,3 +821,36 @@ def test_rail_matrix(dfb, eng):
     assert none["regions"] is None and none["coverageMatrix"] is None
     with pytest.raises(ValueError):
         dfb.railMatrix(["chr21"], {"chr21": mean_rle}, {"chr21": cols}, L_=76, engine=eng)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("N", [6400, 6401])
+def test_view_dense_dev_equals_copy(dfb, eng, N):
+    """dfb_cov_view_dense_dev reads a device matrix in the engine's layout in place (N = ld = 6400) and
+    copies any other layout (6401): both must give the statistics of the copying entry point."""
+    import torch
+    from derfinder_b200 import _lib as L
+    rng = np.random.default_rng(N)
+    n = 7
+    cov = rng.poisson(4.0, size=(n, N)).astype(np.int32)
+    dev = torch.as_tensor(cov, device="cuda")
+    e2 = dfb.Engine(0, stream=torch.cuda.current_stream().cuda_stream)
+    try:
+        mod = np.column_stack([np.ones(n), np.arange(n) % 2, rng.normal(size=n)])
+        mod0 = mod[:, [0, 2]].copy()
+        pl = np.array([N], dtype=np.int32)
+        outs = []
+        for fn in (e2.lib.dfb_cov_from_dense_dev, e2.lib.dfb_cov_view_dense_dev):
+            h = C.c_void_p()
+            L.check(fn(e2.h, n, N, L.DFB_I32, C.c_void_p(dev.data_ptr()), N, L.ptr(pl, C.c_int32), 1, 1, C.byref(h)))
+            L.check(e2.lib.dfb_preprocess(e2.h, h, 32.0, None, 0))
+            f = np.empty(N)
+            L.check(e2.lib.dfb_fstats(e2.h, h, np.asfortranarray(mod).ctypes.data_as(L.c_f64p), 3,
+                                      np.asfortranarray(mod0).ctypes.data_as(L.c_f64p), 2, 0.0,
+                                      f.ctypes.data_as(L.c_f64p)))
+            outs.append(f)
+            e2.lib.dfb_cov_free(h)
+        assert np.array_equal(outs[0], outs[1], equal_nan=True)  # constant rows give NaN (0 / 0)
+        assert np.array_equal(dev.cpu().numpy(), cov)  # the borrowed matrix is never written or freed
+    finally:
+        e2.close()

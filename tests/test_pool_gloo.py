@@ -43,50 +43,57 @@ def _worker(rank, world, port, out_dir):
         if world == 2:
             M = [13, 4][rank]
         area = rng.gamma(2.0, 3.0, size=M)
-        if rank == 0:
-            area[3] = np.nan  # a NaN area must survive the padding removal
         perm = rng.integers(1, B - 1, size=M)  # permutations B-1, B never produce a region anywhere
         mx = np.full(B, -1.0)
         for a, p in zip(area, perm):
-            if not np.isnan(a):
-                mx[p - 1] = max(mx[p - 1], a)
-        segs, gmax = pool.exchange_nulls(torch.as_tensor(area), torch.as_tensor(mx))
-        assert len(segs) == world and [int(s.numel()) for s in segs][rank] == M
-        np.savez(os.path.join(out_dir, f"r{rank}.npz"), area=area, perm=perm, pool=torch.cat(segs).numpy(),
-                 gmax=gmax.numpy())
+            mx[p - 1] = max(mx[p - 1], a)
+        # the exchange of pool.genomewide_pvalues: counts first, then ONE all-gather of the records
+        # [count | per-permutation max or -1 | areas padded with -1] that dfb_pool_local_dev writes
+        counts = pool.exchange_counts(M, torch.device("cpu"))
+        assert counts[rank] == M and len(counts) == world
+        cap = max(max(counts), 1)
+        record = np.concatenate([[float(M)], mx, area, np.full(cap - M, -1.0)])
+        records = pool.gather_records(torch.as_tensor(record))
+        assert tuple(records.shape) == (world, 1 + B + cap)
+        np.savez(os.path.join(out_dir, f"r{rank}.npz"), area=area, perm=perm, mx=mx, records=records.numpy())
     finally:
         dist.destroy_process_group()
 
 
 @pytest.mark.parametrize("world", [2, 3])
-def test_exchange_nulls_gloo(tmp_path, world):
+def test_record_exchange_gloo(tmp_path, world):
     import torch.multiprocessing as mp
     port = _free_port()
     mp.spawn(_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
     res = [np.load(tmp_path / f"r{r}.npz") for r in range(world)]
-    want_pool = np.concatenate([r["area"] for r in res])
     B = 7
+    cap = max(max(len(r["area"]) for r in res), 1)
+    want = np.stack([np.concatenate([[float(len(r["area"]))], r["mx"], r["area"], np.full(cap - len(r["area"]), -1.0)])
+                     for r in res])
     for r in res:
-        np.testing.assert_array_equal(r["pool"], want_pool)  # rank order, NaN kept, padding gone
-        np.testing.assert_array_equal(r["gmax"], res[0]["gmax"])
-    # genome-wide ranking on the pool == the reference's mergeResults arithmetic on the concatenation
-    all_area = want_pool[~np.isnan(want_pool)]
-    all_perm = np.concatenate([r["perm"] for r in res])[~np.isnan(want_pool)]
-    gmax = np.where(res[0]["gmax"] < 0, 3.5, res[0]["gmax"])  # empty permutation -> cutoffFstatUsed
+        np.testing.assert_array_equal(r["records"], want)  # the same buffer on every rank
+    # what dfb_pool_rank_dev computes from the records == the reference's mergeResults arithmetic on the
+    # concatenation of all ranks' nulls (.calcPval on the duplicated pool, .calculateFWER)
+    rec = res[0]["records"]
+    all_area = np.concatenate([r["area"] for r in res])
+    all_perm = np.concatenate([r["perm"] for r in res])
+    gmax = rec[:, 1:1 + B].max(axis=0)
+    gmax = np.where(gmax < 0, 3.5, gmax)  # empty permutation -> cutoffFstatUsed
     region_area = np.array([0.5, 4.0, 50.0])
     fwer = ((gmax[None, :] > region_area[:, None]).sum(axis=1) + 1) / (B + 1)
     np.testing.assert_array_equal(fwer, O.calculate_fwer(3.5, all_area, all_perm, B, region_area))
-    # pooled p-values from per-rank SORTED lists (no second sort) == .calcPval on the duplicated pool
-    cnt = np.zeros(len(region_area), dtype=np.int64)
-    for r in res:
-        srt = np.sort(r["area"][~np.isnan(r["area"])])
-        cnt += len(srt) - np.searchsorted(srt, region_area, side="right")
-    p = (2.0 * cnt + 1.0) / (2.0 * len(all_area) + 1.0)
+    pooled = rec[:, 1 + B:].ravel()
+    pooled = pooled[pooled >= 0]  # pads never outrank a region
+    total = rec[:, 0].sum()
+    assert total == len(all_area) == len(pooled)
+    cnt = (pooled[None, :] > region_area[:, None]).sum(axis=1)
+    p = (2.0 * cnt + 1.0) / (2.0 * total + 1.0)
     np.testing.assert_array_equal(p, O.calc_pval(region_area, np.concatenate([all_area, all_area])))
 
 
 def test_exchange_is_identity_without_process_group():
     import torch
-    a, m = torch.arange(4, dtype=torch.float64), torch.tensor([1.0, -1.0])
-    p, g = pool.exchange_nulls(a, m)
-    assert len(p) == 1 and p[0] is a and g is m
+    rec = torch.arange(4, dtype=torch.float64)
+    assert pool.exchange_counts(3, torch.device("cpu")) == [3]
+    out = pool.gather_records(rec)
+    assert out.shape == (1, 4) and out.data_ptr() == rec.data_ptr()
