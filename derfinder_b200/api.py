@@ -67,8 +67,12 @@ class Engine:
     def set_option(self, key: str, value: float):
         L.check(self.lib.dfb_set_option(self.h, key.encode(), float(value)))
 
-    def enable_timing(self, on=True):
-        L.check(self.lib.dfb_enable_timing(self.h, 1 if on else 0))
+    def enable_timing(self, on=True, families=None):
+        """Bracket kernel launches with CUDA events: every family, or only those listed (L.K_*)."""
+        mask = 0
+        for k in families or ():
+            mask |= 1 << int(k)
+        L.check(self.lib.dfb_enable_timing(self.h, mask if families else (1 if on else 0)))
 
     def reset_counters(self):
         self.lib.dfb_reset_counters(self.h)

@@ -84,7 +84,8 @@ struct dfb_ctx {
     int sm_count = 148;
     size_t smem_optin = 0;
     int64_t launches = 0;
-    bool timing = false;
+    unsigned timing = 0;  // bit k: launches of kernel family k are bracketed by CUDA events
+    std::vector<cudaEvent_t> ev_free;  // recycled timing events (creating two per launch costs more than the launch)
     struct Ev {
         cudaEvent_t a, b;
         int k;
@@ -142,17 +143,27 @@ struct KTimer {
         : c(ctx), k(kernel), file(f), line(l) {
         c->launches += nlaunch;
         c->klaunch[k] += nlaunch;
-        if (c->timing) {
-            cudaEventCreate(&a);
-            cudaEventCreate(&b);
+        if ((c->timing >> k) & 1u) {
+            a = take(c);
+            b = take(c);
             cudaEventRecord(a, c->stream);
         }
     }
     ~KTimer() {
-        if (c->timing) {
+        if (a) {
             cudaEventRecord(b, c->stream);
             c->evs.push_back({a, b, k, file, line});
         }
+    }
+    static cudaEvent_t take(dfb_ctx* c) {
+        cudaEvent_t e = nullptr;
+        if (!c->ev_free.empty()) {
+            e = c->ev_free.back();
+            c->ev_free.pop_back();
+        } else {
+            cudaEventCreate(&e);
+        }
+        return e;
     }
 };
 

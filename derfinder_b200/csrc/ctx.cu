@@ -577,6 +577,7 @@ void dfb_destroy(dfb_ctx* c) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
     }
+    for (auto e : c->ev_free) cudaEventDestroy(e);
     if (c->pinned) {
         cudaFreeHost(c->pinned);
         for (int i = 0; i < 4; ++i) cudaEventDestroy(c->stage_ev[i]);
@@ -623,8 +624,8 @@ static int drain_events(dfb_ctx* c) {
     for (auto& e : c->evs) {
         float ms = 0.f;
         if (cudaEventElapsedTime(&ms, e.a, e.b) == cudaSuccess) c->kms[e.k] += ms;
-        cudaEventDestroy(e.a);
-        cudaEventDestroy(e.b);
+        c->ev_free.push_back(e.a);
+        c->ev_free.push_back(e.b);
     }
     c->evs.clear();
     cudaGetLastError();
@@ -644,7 +645,7 @@ void dfb_reset_counters(dfb_ctx* c) {
 int dfb_enable_timing(dfb_ctx* c, int on) {
     DFB_REQUIRE(c, "NULL context");
     DFB_TRY(drain_events(c));
-    c->timing = on != 0;
+    c->timing = on == 0 ? 0u : (on == 1 ? ~0u : (unsigned)on);  // 1 = every family, else a mask of (1 << family)
     return DFB_OK;
 }
 

@@ -83,7 +83,8 @@ int64_t dfb_launch_count(dfb_ctx* ctx);
 void dfb_reset_counters(dfb_ctx* ctx);
 /* When enabled every launch of a DFB_K_* kernel family is bracketed by CUDA events on the
  * context's stream; dfb_kernel_time synchronises and returns the summed device ms and the number
- * of launches since the last reset. */
+ * of launches since the last reset.  on = 1: every family; on > 1: a mask of (1 << DFB_K_*), so a
+ * benchmark can time its dominant kernel live without paying two event records on every launch. */
 int dfb_enable_timing(dfb_ctx* ctx, int on);
 int dfb_kernel_time(dfb_ctx* ctx, int kernel, double* ms, int64_t* launches);
 /* Engine knobs (all default to the fastest exact configuration):
