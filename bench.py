@@ -554,8 +554,9 @@ def main():
         # and what the genome-wide pooling (two all-gathers + ranking) adds on top of it
         line["multi_gpu"] = {"chromosome_pass_ms_per_rank": own_all,
                              "pooling_ms": round(ms - max(own_all), 4),
-                             "collectives": "NCCL all-gather of the counts (side stream) + one all-gather of the "
-                                            "records {count, per-permutation max, padded null areas}"}
+                             "collectives": "NCCL all-gather of the records {counts, per-permutation max null area, "
+                                            "this rank's region areas} + all-reduce(sum) of the null histogram "
+                                            "over the merged region list; the null lists stay on their GPU"}
         if pool_prof and rank == 0:
             print("pool sections (ms):", pool_prof, file=sys.stderr)
     if rank == 0:

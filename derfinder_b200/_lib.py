@@ -88,9 +88,11 @@ SIGNATURES = {
     "dfb_nulls_counts_per_perm": (C.c_int, [C.c_void_p, c_i64p]),
     "dfb_nulls_get": (C.c_int, [C.c_void_p, C.c_int, c_f64p, c_i32p, c_f64p, c_i32p]),
     "dfb_nulls_copy_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
-    "dfb_pool_local_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p]),
-    "dfb_pool_rank_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int64, C.c_double,
-                                    C.c_void_p, C.c_void_p]),
+    "dfb_pool_local_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_int64, C.c_void_p]),
+    "dfb_pool_hist_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int64, C.c_int64,
+                                    C.c_void_p, C.c_void_p, C.c_void_p]),
+    "dfb_pool_rank_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int64, C.c_int64,
+                                    C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p]),
     "dfb_nulls_merge_areas_dev": (C.c_int, [C.c_void_p, C.c_void_p]),
     "dfb_nulls_sorted_areas_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p]),
     "dfb_regions_null_hist_dev": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p]),

@@ -72,6 +72,7 @@ struct dfb_nulls {
     int64_t count = 0;
     dfb::DevBuf<double> area, stat;  // [count]
     dfb::DevBuf<double> area_sorted; // [count] ascending (kept from the p-value ranking; pooled across GPUs)
+    dfb::DevBuf<double> area_merge;  // [count] abs(stat) * width (R/mergeResults.R:231), built on first use
     dfb::DevBuf<int32_t> width, perm;  // [count], perm ids 1-based
     std::vector<int64_t> per_perm;   // [B]
 };

@@ -243,26 +243,6 @@ __global__ void __launch_bounds__(256) null_hist_kernel(const double* __restrict
     }
 }
 
-// the same over the gathered per-rank records of the multi-GPU pooling: segment w (blockIdx.y) holds
-// `seg_len` areas at base + w * stride; pads are -1 and land in hist[R], which nobody reads
-__global__ void __launch_bounds__(256) null_hist_seg_kernel(const double* __restrict__ base, int64_t stride,
-                                                            int64_t seg_len, const double* __restrict__ desc,
-                                                            int64_t R, uint32_t* __restrict__ hist) {
-    const double* __restrict__ nulls = base + (size_t)blockIdx.y * stride;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < seg_len;
-         i += (int64_t)gridDim.x * blockDim.x) {
-        const double v = nulls[i];
-        if (v < 0.0) continue;  // padding
-        int64_t lo = 0, hi = R;
-        while (lo < hi) {
-            const int64_t mid = (lo + hi) >> 1;
-            if (desc[mid] < v) hi = mid;
-            else lo = mid + 1;
-        }
-        atomicAdd(&hist[lo], 1u);
-    }
-}
-
 // counts/p-values in sorted (decreasing-area) order from the exclusive prefix of the histogram
 __global__ void hist_pval_kernel(const int64_t* __restrict__ excl, const uint32_t* __restrict__ hist, int64_t R,
                                  double weight, double total, double* __restrict__ p, int64_t* __restrict__ counts,
@@ -383,46 +363,101 @@ __global__ void fwer_kernel(const double* __restrict__ areas, int64_t R, const d
     fwer[r] = __ddiv_rn((double)(c + 1), (double)(B + 1));
 }
 
-// ---- multi-GPU pooling (R/mergeResults.R:216-235, 300-307, 380-386) in two calls per rank
+// ---- multi-GPU pooling (R/mergeResults.R:216-235, 300-307, 380-386).  Per-rank work does not grow
+// with the number of GPUs: ranks exchange their REGION areas (small) and a histogram, never the nulls.
 
-// local half: the rank's null areas (summed, or abs(stat) * width as mergeResults recomputes them,
-// :231) padded with -1 up to `cap` (areas are >= 0, so a pad never outranks a region), and the head
-// record [count, max area of permutation 1..B (-1 when the rank has none)] that is all-gathered
-__global__ void pool_local_kernel(const double* __restrict__ area, const double* __restrict__ stat,
-                                  const int32_t* __restrict__ width, int64_t M, int64_t cap, int merge,
-                                  double* __restrict__ out, double* __restrict__ head) {
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (int64_t)gridDim.x * blockDim.x)
-        out[i] = i < M ? (merge ? __dmul_rn(fabs(stat[i]), (double)width[i]) : area[i]) : -1.0;
-    if (blockIdx.x == 0 && threadIdx.x == 0) head[0] = (double)M;
+// record of a rank: [R | M | max null area of permutation 1..B (-1: none) | region areas, descending, -1 padded
+// to rcap].  A rank with more than rcap regions writes the first rcap: every rank sees R > rcap in the
+// gathered records and the caller repeats the exchange with a larger capacity.
+__global__ void pool_record_kernel(const double* __restrict__ desc, int64_t R, int64_t M, int64_t rcap, int64_t B,
+                                   double* __restrict__ rec) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < rcap; i += (int64_t)gridDim.x * blockDim.x)
+        rec[2 + B + i] = i < R ? desc[i] : -1.0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        rec[0] = (double)R;
+        rec[1] = (double)M;
+    }
 }
 
-// genome-wide maximum area per permutation over all ranks' heads; a permutation without a null region
-// anywhere contributes cutoffFstatUsed (:382).  Also the pooled count (every entry is stored twice).
-__global__ void pool_gmax_kernel(const double* __restrict__ recs, int64_t stride, int world, int64_t B,
-                                 double cutoff_used, double* __restrict__ gmax, double* __restrict__ total) {
-    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (b == 0) {
-        double t = 0.0;
-        for (int w = 0; w < world; ++w) t += recs[(size_t)w * stride];
-        *total = t;
+// Stable merge of the ranks' descending lists without a sort: element i of list w goes to position
+// i + sum_{w' < w} #{list w' >= a} + sum_{w' > w} #{list w' > a}  (one binary search per other list).
+__global__ void __launch_bounds__(256) pool_merge_kernel(const double* __restrict__ recs, int64_t stride, int64_t off,
+                                                         int64_t rcap, int world, double* __restrict__ merged,
+                                                         int32_t* __restrict__ src) {
+    const int64_t n = (int64_t)world * rcap;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t w = t / rcap, i = t - w * rcap;
+        const double a = recs[w * stride + off + i];
+        int64_t pos = i;
+        for (int w2 = 0; w2 < world; ++w2) {
+            if (w2 == w) continue;
+            const double* __restrict__ list = recs + (size_t)w2 * stride + off;
+            int64_t lo = 0, hi = rcap;
+            if (w2 < w) {  // first index with list[idx] < a
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (list[mid] < a) hi = mid;
+                    else lo = mid + 1;
+                }
+            } else {  // first index with list[idx] <= a
+                while (lo < hi) {
+                    const int64_t mid = (lo + hi) >> 1;
+                    if (list[mid] <= a) hi = mid;
+                    else lo = mid + 1;
+                }
+            }
+            pos += lo;
+        }
+        merged[pos] = a;
+        src[pos] = (int32_t)t;
     }
+}
+
+// i(v) = #{D >= v} over the merged, descending region list D of every rank; 64-bit bins (they are
+// summed over ranks and a genome-wide run can exceed 2^32 nulls)
+__global__ void __launch_bounds__(256) null_hist64_kernel(const double* __restrict__ nulls, int64_t M,
+                                                          const double* __restrict__ desc, int64_t R,
+                                                          unsigned long long* __restrict__ hist) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += (int64_t)gridDim.x * blockDim.x) {
+        const double v = nulls[i];
+        int64_t lo = 0, hi = R;
+        while (lo < hi) {
+            const int64_t mid = (lo + hi) >> 1;
+            if (desc[mid] < v) hi = mid;
+            else lo = mid + 1;
+        }
+        atomicAdd(&hist[lo], 1ull);
+    }
+}
+
+// genome-wide maximum area per permutation over all ranks' records; a permutation without a null
+// region anywhere contributes cutoffFstatUsed (:382)
+__global__ void pool_gmax_kernel(const double* __restrict__ recs, int64_t stride, int world, int64_t B,
+                                 double cutoff_used, double* __restrict__ gmax) {
+    const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     double m = -1.0;
-    for (int w = 0; w < world; ++w) m = fmax(m, recs[(size_t)w * stride + 1 + b]);
+    for (int w = 0; w < world; ++w) m = fmax(m, recs[(size_t)w * stride + 2 + b]);
     gmax[b] = m < 0.0 ? cutoff_used : m;
 }
 
-// p-value and FWER of the region at sorted position i, written in the caller's (up-then-dn) order
-__global__ void pool_rank_kernel(const int64_t* __restrict__ excl, const uint32_t* __restrict__ hist,
-                                 const double* __restrict__ desc, const int32_t* __restrict__ order, int64_t R,
-                                 const double* __restrict__ total, const double* __restrict__ gmax, int64_t B,
-                                 double* __restrict__ p, double* __restrict__ fwer) {
+// merged position i belongs to region src[i] = rank * rcap + (position in that rank's sorted list);
+// this rank's entries get their pooled p-value and FWER, written in the caller's (up-then-dn) order
+__global__ void pool_rank_kernel(const unsigned long long* __restrict__ incl, const double* __restrict__ merged,
+                                 const int32_t* __restrict__ src, int64_t n, int64_t rcap, int rank, int64_t R,
+                                 const int32_t* __restrict__ order, const double* __restrict__ recs, int64_t stride,
+                                 int world, const double* __restrict__ gmax, int64_t B, double* __restrict__ p,
+                                 double* __restrict__ fwer) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= R) return;
-    const int64_t c = excl[i] + (int64_t)hist[i];
-    const int64_t dst = order ? order[i] : i;
-    p[dst] = __ddiv_rn(2.0 * (double)c + 1.0, 2.0 * *total + 1.0);
-    const double a = desc[i];
+    if (i >= n) return;
+    const int64_t s = src[i];
+    const int64_t w = s / rcap, il = s - w * rcap;
+    if (w != rank || il >= R) return;
+    double total = 0.0;  // pooled null regions (each is stored twice by the reference: weight 2 below)
+    for (int w2 = 0; w2 < world; ++w2) total += recs[(size_t)w2 * stride + 1];
+    const int64_t dst = order ? order[il] : il;
+    p[dst] = __ddiv_rn(2.0 * (double)incl[i] + 1.0, 2.0 * total + 1.0);
+    const double a = merged[i];
     int64_t k = 0;
     for (int64_t b = 0; b < B; ++b) k += gmax[b] > a ? 1 : 0;
     fwer[dst] = __ddiv_rn((double)(k + 1), (double)(B + 1));
@@ -632,55 +667,89 @@ int dfb_nulls_merge_areas_dev(const dfb_nulls* nl, double* area_dev) {
     return DFB_OK;
 }
 
-int dfb_pool_local_dev(dfb_ctx* ctx, const dfb_nulls* nl, int64_t B, int merge_area, int64_t cap, double* record_dev) {
-    DFB_REQUIRE(ctx && nl && record_dev, "dfb_pool_local_dev: NULL argument");
-    DFB_REQUIRE(B >= 1 && cap >= nl->count && cap >= 1, "dfb_pool_local_dev: capacity below the null count");
-    const int64_t M = nl->count;
-    double* area_dev = record_dev + 1 + B;
-    {
+static int pooled_null_areas(dfb_ctx* ctx, dfb_nulls* nl, int merge_area, const double** out) {
+    *out = nl->area.p;
+    if (!merge_area || nl->count == 0) return DFB_OK;
+    if (!nl->area_merge.p) {
+        DFB_TRY(nl->area_merge.alloc(ctx, (size_t)nl->count));
         KTimer t(ctx, DFB_K_PVAL);
-        pool_local_kernel<<<grid_for(cap, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(
-            nl->area.p, nl->stat.p, nl->width.p, M, cap, merge_area, area_dev, record_dev);
+        merge_area_kernel<<<(unsigned)std::min<int64_t>(ceil_div(nl->count, 256), (int64_t)ctx->sm_count * 8), 256, 0,
+                            ctx->stream>>>(nl->stat.p, nl->width.p, nl->count, nl->area_merge.p);
+        DFB_CUDA(cudaGetLastError());
     }
-    DFB_CUDA(cudaGetLastError());
-    return perm_max_device(ctx, area_dev, nl->perm.p, M, B, -1.0, record_dev + 1);
+    *out = nl->area_merge.p;
+    return DFB_OK;
 }
 
-int dfb_pool_rank_dev(dfb_ctx* ctx, const dfb_regions* r, const double* records_dev, int world, int64_t B,
-                      int64_t cap, double cutoff_used, double* p_dev, double* fwer_dev) {
-    DFB_REQUIRE(ctx && r && records_dev, "dfb_pool_rank_dev: NULL argument");
-    DFB_REQUIRE(world >= 1 && B >= 1 && cap >= 1, "dfb_pool_rank_dev: world, nPermute and capacity must be >= 1");
-    const int64_t R = r->R;
-    if (R == 0) return DFB_OK;
-    DFB_REQUIRE(p_dev && fwer_dev, "dfb_pool_rank_dev: NULL output");
-    if (!r->d_area_desc.p) {
-        set_error("dfb_pool_rank_dev: this result was not produced by dfb_calculate_pvalues");
+int dfb_pool_local_dev(dfb_ctx* ctx, const dfb_regions* r, dfb_nulls* nl, int64_t B, int merge_area, int64_t rcap,
+                       double* record_dev) {
+    DFB_REQUIRE(ctx && r && nl && record_dev, "dfb_pool_local_dev: NULL argument");
+    DFB_REQUIRE(B >= 1 && rcap >= 1, "dfb_pool_local_dev: nPermute and capacity must be >= 1");
+    if (r->R > 0 && !r->d_area_desc.p) {
+        set_error("dfb_pool_local_dev: this result was not produced by dfb_calculate_pvalues");
         return DFB_ESTATE;
     }
-    const int64_t stride = 1 + B + cap;
-    DevBuf<uint32_t> hist;
-    DevBuf<int64_t> excl, tot;
-    DevBuf<double> gmax;  // [B] maxima + the pooled count
-    DFB_TRY(hist.alloc(ctx, (size_t)R + 1));
-    DFB_TRY(hist.zero());
-    DFB_TRY(excl.alloc(ctx, (size_t)R + 1));
-    DFB_TRY(tot.alloc(ctx, 1));
-    DFB_TRY(gmax.alloc(ctx, (size_t)B + 1));
+    const double* areas = nullptr;
+    DFB_TRY(pooled_null_areas(ctx, nl, merge_area, &areas));
     {
         KTimer t(ctx, DFB_K_PVAL);
-        dim3 grid((unsigned)std::min<int64_t>(ceil_div(cap, 256), (int64_t)ctx->sm_count * 16), (unsigned)world);
-        null_hist_seg_kernel<<<grid, 256, 0, ctx->stream>>>(records_dev + 1 + B, stride, cap, r->d_area_desc.p, R,
-                                                          hist.p);
+        pool_record_kernel<<<grid_for(rcap, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(r->d_area_desc.p, r->R,
+                                                                                      nl->count, rcap, B, record_dev);
     }
     DFB_CUDA(cudaGetLastError());
-    DFB_TRY(exclusive_scan_u32(ctx, hist.p, excl.p, R + 1, tot.p, DFB_K_PVAL));
+    return perm_max_device(ctx, areas, nl->perm.p, nl->count, B, -1.0, record_dev + 2);
+}
+
+int dfb_pool_hist_dev(dfb_ctx* ctx, dfb_nulls* nl, int merge_area, const double* records_dev, int world, int64_t B,
+                      int64_t rcap, double* merged_dev, int32_t* src_dev, unsigned long long* hist_dev) {
+    DFB_REQUIRE(ctx && nl && records_dev && merged_dev && src_dev && hist_dev, "dfb_pool_hist_dev: NULL argument");
+    DFB_REQUIRE(world >= 1 && B >= 1 && rcap >= 1, "dfb_pool_hist_dev: world, nPermute and capacity must be >= 1");
+    const int64_t n = (int64_t)world * rcap;
+    DFB_REQUIRE(n < INT32_MAX, "dfb_pool_hist_dev: %lld pooled regions exceed the 32-bit index", (long long)n);
     {
-        KTimer t(ctx, DFB_K_PVAL, 2);
-        pool_gmax_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, ctx->stream>>>(records_dev, stride, world, B, cutoff_used,
-                                                                             gmax.p, gmax.p + B);
-        pool_rank_kernel<<<(unsigned)ceil_div(R, 128), 128, 0, ctx->stream>>>(excl.p, hist.p, r->d_area_desc.p,
-                                                                            r->d_order.p, R, gmax.p + B, gmax.p, B, p_dev,
-                                                                            fwer_dev);
+        KTimer t(ctx, DFB_K_PVAL);
+        pool_merge_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(records_dev, 2 + B + rcap, 2 + B,
+                                                                                    rcap, world, merged_dev, src_dev);
+    }
+    DFB_CUDA(cudaGetLastError());
+    DFB_CUDA(cudaMemsetAsync(hist_dev, 0, (size_t)(n + 1) * sizeof(unsigned long long), ctx->stream));
+    const double* areas = nullptr;
+    DFB_TRY(pooled_null_areas(ctx, nl, merge_area, &areas));
+    if (nl->count > 0) {
+        KTimer t(ctx, DFB_K_PVAL);
+        null_hist64_kernel<<<grid_for(nl->count, 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(areas, nl->count,
+                                                                                             merged_dev, n, hist_dev);
+    }
+    DFB_CUDA(cudaGetLastError());
+    return DFB_OK;
+}
+
+int dfb_pool_rank_dev(dfb_ctx* ctx, const dfb_regions* r, const double* records_dev, int world, int rank, int64_t B,
+                      int64_t rcap, const double* merged_dev, const int32_t* src_dev,
+                      const unsigned long long* hist_dev, double cutoff_used, double* p_dev, double* fwer_dev) {
+    DFB_REQUIRE(ctx && r && records_dev && merged_dev && src_dev && hist_dev, "dfb_pool_rank_dev: NULL argument");
+    DFB_REQUIRE(world >= 1 && rank >= 0 && rank < world && B >= 1 && rcap >= 1,
+                "dfb_pool_rank_dev: bad world / rank / capacity");
+    const int64_t R = std::min<int64_t>(r->R, rcap);  // R > rcap: the caller repeats with a larger capacity
+    if (R == 0) return DFB_OK;
+    DFB_REQUIRE(p_dev && fwer_dev, "dfb_pool_rank_dev: NULL output");
+    const int64_t n = (int64_t)world * rcap;
+    DevBuf<unsigned long long> incl;
+    DevBuf<double> gmax;
+    DevBuf<unsigned char> tmp;
+    DFB_TRY(incl.alloc(ctx, (size_t)n));
+    DFB_TRY(gmax.alloc(ctx, (size_t)B));
+    size_t tmp_bytes = 0;
+    DFB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, hist_dev, incl.p, n, ctx->stream));
+    DFB_TRY(tmp.alloc(ctx, tmp_bytes));
+    {
+        KTimer t(ctx, DFB_K_PVAL, 4);
+        DFB_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, hist_dev, incl.p, n, ctx->stream));
+        pool_gmax_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, ctx->stream>>>(records_dev, 2 + B + rcap, world, B,
+                                                                             cutoff_used, gmax.p);
+        pool_rank_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(incl.p, merged_dev, src_dev, n, rcap, rank, R,
+                                                                            r->d_order.p, records_dev, 2 + B + rcap,
+                                                                            world, gmax.p, B, p_dev, fwer_dev);
     }
     DFB_CUDA(cudaGetLastError());
     return DFB_OK;

@@ -5,16 +5,20 @@ Chromosomes are independent up to the genome-wide p-value / FWER ranking of `mer
 on the pool, :380-386 takes the per-permutation maximum area over the genome).  So every rank runs
 the whole per-chromosome pipeline on its own GPU and only
 
-    counts [world]                     all-gather on a SIDE stream (how many null regions each rank
-                                       found; the host needs the largest to size the records, and
-                                       waits for its peers only -- not for its own pending GPU work)
-    records [world][1 + B + cap]       ONE all-gather: {count, per-permutation max area, null areas
-                                       padded with -1 to the largest count}
+    records [world][2 + B + rcap] all-gather: {regions R, null regions M, per-permutation max null
+                                  area, this rank's REGION areas (sorted, padded with -1 to rcap)}
+    histogram [world * rcap + 1]  all-reduce(sum): this rank's nulls binned against the merged region
+                                  list of all ranks
 
-cross NVLink.  Tensors stay where they are (CUDA with NCCL, CPU with gloo in the tests).  Each rank
-ranks its own regions (already sorted by area) against the gathered, UNSORTED null areas with a
-histogram (`dfb_pool_rank_dev`): nothing is sorted for the pooling and the per-permutation maxima
-are reduced from the same records (no separate all-reduce).
+cross NVLink -- a few MB per rank.  The null lists themselves (the bulk: ~10 MB per chromosome at
+C2, far more at C3/C4) never leave their GPU, and per-rank work is O(own nulls * log(all regions))
+whatever the number of GPUs: every rank merges the gathered region areas into one descending list,
+histograms its own UNSORTED nulls against it, and after the all-reduce reads the pooled count of
+its own regions off the prefix sums.  The record capacity `rcap` is agreed once (a count exchange
+on the first call) and kept with head room; the counts travel inside the records, so a rank that
+outgrows the capacity is seen by everybody and the exchange is repeated once with a larger one.
+Tensors stay where they are (CUDA with NCCL, CPU with gloo in the tests); nothing is read back to
+the host until all the work of the step has been queued.
 """
 from __future__ import annotations
 
@@ -38,27 +42,30 @@ def assign_chromosomes(sizes, world):
     return bins
 
 
-def exchange_counts(count, device, dist=None, group=None, side_stream=None):
-    """Every rank's null-region count, as a Python list.  On CUDA the tiny all-gather and the host
-    read run on `side_stream`, so the caller's main stream (still finishing the chromosome pass) is
-    neither waited for nor drained; the host blocks until the peers have reached the same point."""
+def exchange_counts(values, device, dist=None, group=None, side_stream=None):
+    """All-gather of a few integers per rank (here: region and null-region counts) -> list of
+    per-rank lists.  On CUDA the tiny collective and the host read run on `side_stream`, so the
+    caller's main stream (still finishing the chromosome pass) is neither waited for nor drained;
+    the host blocks until the peers have reached the same point."""
     import torch
     if dist is None:
         import torch.distributed as dist
+    values = [int(v) for v in values]
     if not (dist.is_available() and dist.is_initialized()):
-        return [int(count)]
+        return [values]
     world = dist.get_world_size(group)
+    k = len(values)
     if device.type != "cuda":
-        mine = torch.tensor([int(count)], dtype=torch.int64)
-        out = torch.empty(world, dtype=torch.int64)
+        mine = torch.tensor(values, dtype=torch.int64)
+        out = torch.empty(world * k, dtype=torch.int64)
         dist.all_gather_into_tensor(out, mine, group=group)
-        return out.tolist()
+        return out.view(world, k).tolist()
     side = side_stream or torch.cuda.Stream(device=device)
     with torch.cuda.stream(side):
-        mine = torch.tensor([int(count)], dtype=torch.int64).pin_memory().to(device, non_blocking=True)
-        out = torch.empty(world, device=device, dtype=torch.int64)
+        mine = torch.tensor(values, dtype=torch.int64).pin_memory().to(device, non_blocking=True)
+        out = torch.empty(world * k, device=device, dtype=torch.int64)
         dist.all_gather_into_tensor(out, mine, group=group)
-        return out.tolist()  # synchronises the side stream only
+        return out.view(world, k).tolist()  # synchronises the side stream only
 
 
 def gather_records(record, dist=None, group=None):
@@ -74,7 +81,21 @@ def gather_records(record, dist=None, group=None):
     return out.view(world, record.numel())
 
 
+def reduce_histogram(hist, dist=None, group=None):
+    """In-place all-reduce(sum) of the int64 histogram (no-op without a process group)."""
+    if dist is None:
+        import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(hist, op=dist.ReduceOp.SUM, group=group)
+    return hist
+
+
 _side_streams = {}
+_capacity = {}  # (device, process group) -> agreed record capacity
+
+
+def _headroom(r):
+    return int(r) + (int(r) >> 2) + 1024
 
 
 def genomewide_pvalues(engine, regions_handle, nulls_handle, B, cutoff_used, torch, device, dist=None,
@@ -84,12 +105,10 @@ def genomewide_pvalues(engine, regions_handle, nulls_handle, B, cutoff_used, tor
     merge_area=True pools `abs(stat) * width` exactly as mergeResults does (R/mergeResults.R:231);
     False pools the summed areas calculatePvalues ranks (the two differ in the last ulps).
 
-    `exchange_counts` (side stream), `dfb_pool_local_dev` (this rank's record), `gather_records`
-    (one all-gather), `dfb_pool_rank_dev` (histogram of the pooled, UNSORTED nulls against this rank's
-    sorted regions, p-values and FWER).  The main stream is never synchronised with the host."""
+    dfb_pool_local_dev -> gather_records -> dfb_pool_hist_dev -> reduce_histogram ->
+    dfb_pool_rank_dev, then ONE host read of the gathered counts; see the module docstring."""
     from . import _lib as L
     lib = engine.lib
-    M = int(lib.dfb_nulls_count(nulls_handle))
     R = int(lib.dfb_regions_count(regions_handle))
     marks = []
 
@@ -100,37 +119,67 @@ def genomewide_pvalues(engine, regions_handle, nulls_handle, B, cutoff_used, tor
             marks.append((name, ev))
 
     mark("start")
-    key = (device.index, id(dist))
-    if key not in _side_streams:
-        _side_streams[key] = torch.cuda.Stream(device=device)
-    counts = exchange_counts(M, device, dist=dist, side_stream=_side_streams[key])
-    world = len(counts)
-    cap = max(max(counts), 1)
-    record = torch.empty(1 + B + cap, device=device, dtype=torch.float64)
-    p_dev = torch.empty(max(R, 1), device=device, dtype=torch.float64)
-    fwer = torch.empty(max(R, 1), device=device, dtype=torch.float64)
+    active = dist is not None and dist.is_available() and dist.is_initialized()
+    world = dist.get_world_size() if active else 1
+    rank = dist.get_rank() if active else 0
+    key = (device.index, id(dist) if active else None)
+    if key not in _capacity:  # first call: agree on a capacity (side stream: the main stream keeps running)
+        if key not in _side_streams:
+            _side_streams[key] = torch.cuda.Stream(device=device)
+        counts = exchange_counts([R], device, dist=dist if active else None, side_stream=_side_streams[key])
+        _capacity[key] = _headroom(max(c[0] for c in counts))
     # the engine and torch share one stream in bench.py; otherwise order them explicitly
     shared = engine.stream_handle == torch.cuda.current_stream().cuda_stream
-    if not shared:
-        torch.cuda.current_stream().synchronize()
-    L.check(lib.dfb_pool_local_dev(engine.h, nulls_handle, B, 1 if merge_area else 0, cap,
-                                   C.c_void_p(record.data_ptr())))
-    if not shared:
-        engine.sync()
-    mark("local")
-    records = gather_records(record, dist=dist)
-    mark("exchange")
-    if not shared:
-        torch.cuda.current_stream().synchronize()
-    L.check(lib.dfb_pool_rank_dev(engine.h, regions_handle, C.c_void_p(records.data_ptr()), world, B, cap,
-                                  float(cutoff_used), C.c_void_p(p_dev.data_ptr()), C.c_void_p(fwer.data_ptr())))
-    if not shared:
-        engine.sync()
-    mark("rank")
+
+    def to_engine():
+        if not shared:
+            torch.cuda.current_stream().synchronize()
+
+    def to_torch():
+        if not shared:
+            engine.sync()
+
+    ma = 1 if merge_area else 0
+    p_dev = torch.empty(max(R, 1), device=device, dtype=torch.float64)
+    fwer = torch.empty(max(R, 1), device=device, dtype=torch.float64)
+    while True:
+        rcap = _capacity[key]
+        record = torch.empty(2 + B + rcap, device=device, dtype=torch.float64)
+        merged = torch.empty(world * rcap, device=device, dtype=torch.float64)
+        src = torch.empty(world * rcap, device=device, dtype=torch.int32)
+        hist = torch.empty(world * rcap + 1, device=device, dtype=torch.int64)
+        to_engine()
+        L.check(lib.dfb_pool_local_dev(engine.h, regions_handle, nulls_handle, B, ma, rcap,
+                                       C.c_void_p(record.data_ptr())))
+        to_torch()
+        mark("local")
+        records = gather_records(record, dist=dist if active else None)
+        mark("gather")
+        to_engine()
+        L.check(lib.dfb_pool_hist_dev(engine.h, nulls_handle, ma, C.c_void_p(records.data_ptr()), world, B, rcap,
+                                      C.c_void_p(merged.data_ptr()), C.c_void_p(src.data_ptr()),
+                                      C.c_void_p(hist.data_ptr())))
+        to_torch()
+        mark("hist")
+        if active:
+            reduce_histogram(hist, dist=dist)
+        mark("reduce")
+        to_engine()
+        L.check(lib.dfb_pool_rank_dev(engine.h, regions_handle, C.c_void_p(records.data_ptr()), world, rank, B, rcap,
+                                      C.c_void_p(merged.data_ptr()), C.c_void_p(src.data_ptr()),
+                                      C.c_void_p(hist.data_ptr()), float(cutoff_used), C.c_void_p(p_dev.data_ptr()),
+                                      C.c_void_p(fwer.data_ptr())))
+        to_torch()
+        mark("rank")
+        head = records[:, :2].to("cpu")  # everything is queued: the one host read (identical on every rank)
+        biggest = int(head[:, 0].max().item())
+        if biggest <= rcap:
+            break
+        _capacity[key] = _headroom(biggest)  # somebody outgrew the records: every rank repeats
     if marks:
         PROFILE["calls"] += 1
         PROFILE["events"].append(marks)
-    return p_dev[:R], fwer[:R], int(sum(counts))
+    return p_dev[:R], fwer[:R], int(head[:, 1].sum().item())
 
 
 def reset_profile():

@@ -233,19 +233,32 @@ int dfb_nulls_get(const dfb_nulls* nl, int dup, double* stat, int32_t* width, do
                   int32_t* permutation);
 /* device access for multi-GPU pooling (areas as doubles, permutation ids as int32) */
 int dfb_nulls_copy_dev(const dfb_nulls* nl, double* area_dev, int32_t* perm_dev);
-/* Genome-wide ranking in two calls per rank around ONE all-gather (R/mergeResults.R:216-235,
- * 300-307, 380-386).  A rank's record is [count | max area of permutation 1..B, -1 when it has
- * none | cap null areas padded with -1] (1 + B + cap doubles; cap >= every rank's count, agreed
- * beforehand).  dfb_pool_local_dev writes this rank's record (merge_area != 0: the areas are
- * abs(stat) * width, :231); the caller all-gathers the records (NCCL);  dfb_pool_rank_dev ranks
- * this rank's regions against all records: pooled p-values (.calcPval on the concatenation, every
- * entry counted twice) and FWER (.calculateFWER, empty permutation -> cutoff_used), both [R] on the
- * device in up-then-dn order. */
-int dfb_pool_local_dev(dfb_ctx* ctx, const dfb_nulls* nl, int64_t B, int merge_area, int64_t cap,
-                       double* record_dev);
-int dfb_pool_rank_dev(dfb_ctx* ctx, const dfb_regions* r, const double* records_dev /* [world][1+B+cap] */,
-                      int world, int64_t B, int64_t cap, double cutoff_used, double* p_dev,
-                      double* fwer_dev);
+/* Genome-wide ranking of mergeResults() across GPUs (R/mergeResults.R:216-235, 300-307, 380-386) in
+ * three calls per rank around two small collectives.  Ranks never exchange their null lists: they
+ * all-gather their REGION areas, histogram their own nulls against the merged region list and
+ * all-reduce that histogram, so per-rank work and traffic do not grow with the number of GPUs.
+ *   dfb_pool_local_dev  record [2 + B + rcap] = {R, M, max null area of permutation 1..B (-1 when
+ *                       the rank has none), this rank's region areas, descending, padded with -1};
+ *                       merge_area != 0: null areas are abs(stat) * width (:231).  A rank with
+ *                       R > rcap writes the first rcap areas; every rank then sees R > rcap in
+ *                       the gathered records and the exchange is repeated with a larger capacity.
+ *                                                                 -> all-gather the records
+ *   dfb_pool_hist_dev   merged_dev / src_dev [world * rcap]: every rank's region areas merged into
+ *                       one descending list and where each came from (rank * rcap + position);
+ *                       hist_dev [world * rcap + 1]: this rank's nulls binned by the number of
+ *                       pooled regions they do not exceed.        -> all-reduce(sum) hist_dev
+ *   dfb_pool_rank_dev   pooled p-values ((2 * #{null > area} + 1) / (2 * sum(M) + 1), i.e. .calcPval
+ *                       on the duplicated pool) and FWER (.calculateFWER, empty permutation ->
+ *                       cutoff_used) of THIS rank's regions, [R] on the device in up-then-dn order. */
+int dfb_pool_local_dev(dfb_ctx* ctx, const dfb_regions* r, dfb_nulls* nl, int64_t B, int merge_area,
+                       int64_t rcap, double* record_dev);
+int dfb_pool_hist_dev(dfb_ctx* ctx, dfb_nulls* nl, int merge_area,
+                      const double* records_dev /* [world][2 + B + rcap] */, int world, int64_t B,
+                      int64_t rcap, double* merged_dev, int32_t* src_dev, unsigned long long* hist_dev);
+int dfb_pool_rank_dev(dfb_ctx* ctx, const dfb_regions* r, const double* records_dev, int world,
+                      int rank, int64_t B, int64_t rcap, const double* merged_dev,
+                      const int32_t* src_dev, const unsigned long long* hist_dev, double cutoff_used,
+                      double* p_dev, double* fwer_dev);
 /* the null areas as mergeResults() pools them: abs(stat) * width (R/mergeResults.R:231), which is
  * not bit-identical to the summed area calculatePvalues ranks; written to device memory [count] */
 int dfb_nulls_merge_areas_dev(const dfb_nulls* nl, double* area_dev);

@@ -626,6 +626,13 @@ def test_pooled_pvalues_single_rank(dfb, eng):
         L.check(e2.lib.dfb_nulls_get(nh, 0, None, None, na.ctypes.data_as(L.c_f64p), npm.ctypes.data_as(L.c_i32p)))
         want = O.calculate_fwer(cut, na, npm, cfg["B"], area)
         assert np.array_equal(fwer.cpu().numpy()[order], want)
+        # a record capacity that is too small is noticed by every rank and the exchange repeated
+        for k in list(pool._capacity):
+            pool._capacity[k] = 8
+        p_again, fwer_again, total_again = pool.genomewide_pvalues(e2, rh, nh, cfg["B"], cut, torch, device)
+        torch.cuda.synchronize()
+        assert total_again == M and min(pool._capacity.values()) >= R
+        assert torch.equal(p_again, p_dev) and torch.equal(fwer_again, fwer)
         # mergeResults pools abs(stat) * width instead of the summed areas (R/mergeResults.R:231)
         p_m, fwer_m, _ = pool.genomewide_pvalues(e2, rh, nh, cfg["B"], cut, torch, device, merge_area=True)
         torch.cuda.synchronize()
