@@ -264,6 +264,7 @@ class Step:
         self.pl = np.ascontiguousarray(work["pos_len"], dtype=np.int32)
         self._F_host = np.empty(self.N)  # the caller's fstats vector (R: a numeric vector it already owns)
         self.rle = None
+        self.sync_f = False  # True: dfb_fstats blocks until the F-statistics are in host memory
         self.last_breakdown = {}
 
     def _fp(self, a):
@@ -343,10 +344,13 @@ class Step:
             L.check(lib.dfb_preprocess(eng.h, cov, 32.0, None, 0))
             lap("preprocess")
             F = self._F_host
-            L.check(lib.dfb_fstats(eng.h, cov, self._fp(self.mod), self.mod.shape[1], self._fp(self.mod0),
-                                   self.mod0.shape[1], 0.0, self._fp(F)))
+            # the F-statistics are downloaded into the caller's vector in the background while
+            # calculatePvalues (which uses their device copy) runs; the wait below is inside the timed region
+            fstats_call = lib.dfb_fstats if self.sync_f else lib.dfb_fstats_begin
+            L.check(fstats_call(eng.h, cov, self._fp(self.mod), self.mod.shape[1], self._fp(self.mod0),
+                                self.mod0.shape[1], 0.0, self._fp(F)))
             d2h += F.nbytes
-            lap("calculateStats+download_F")
+            lap("calculateStats+download_F" if self.sync_f else "calculateStats(F download started)")
             rh, nh = C.c_void_p(), C.c_void_p()
             # `fstats` is the object calculateStats() just returned: its device copy is still cached in
             # the coverage handle, so the glue passes NULL instead of uploading it again
@@ -355,6 +359,9 @@ class Step:
                                                    L.ptr(self.perm, C.c_int32), self.perm.shape[0], -self.cut, self.cut,
                                                    0, 3000, C.byref(rh), C.byref(nh), None))
             lap("calculatePvalues")
+            if not self.sync_f:
+                L.check(lib.dfb_fstats_wait(eng.h))
+                lap("wait_for_F_download")
             if rc == 0:
                 R, M = int(lib.dfb_regions_count(rh)), int(lib.dfb_nulls_count(nh))
                 st, en, ist, ien, cl = (np.empty(R, dtype=np.int32) for _ in range(5))
@@ -395,6 +402,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-input", default="rle", choices=["rle", "dense"],
                     help="host coverage format of the end-to-end pass: Rle columns (the reference's type) or dense")
+    ap.add_argument("--e2e-sync-f", action="store_true",
+                    help="end-to-end pass: blocking dfb_fstats download instead of dfb_fstats_begin / dfb_fstats_wait")
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (developer knob)")
     ap.add_argument("--as-rank", type=int, default=None,
                     help="developer: generate the synthetic chromosome rank R would own (single-GPU runs)")
@@ -439,6 +448,7 @@ def main():
         key, val = kv.split("=")
         eng.set_option(key, float(val))
     step = Step(eng, work, perm, cut, torch)
+    step.sync_f = args.e2e_sync_f
 
     timed_pass = None  # per-step events around this rank's own chromosome pass (timed region only)
 

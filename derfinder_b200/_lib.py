@@ -68,6 +68,8 @@ SIGNATURES = {
     "dfb_cov_get_group_mean": (C.c_int, [C.c_void_p, C.c_int, c_f64p]),
     "dfb_chunk_lengths": (C.c_int64, [C.c_int64, C.c_double, C.c_int, c_i64p, C.c_int64]),
     "dfb_fstats": (C.c_int, [C.c_void_p, C.c_void_p, c_f64p, C.c_int, c_f64p, C.c_int, C.c_double, c_f64p]),
+    "dfb_fstats_begin": (C.c_int, [C.c_void_p, C.c_void_p, c_f64p, C.c_int, c_f64p, C.c_int, C.c_double, c_f64p]),
+    "dfb_fstats_wait": (C.c_int, [C.c_void_p]),
     "dfb_model_basis": (C.c_int, [c_f64p, C.c_int, C.c_int, c_f64p, C.c_int, c_f64p, C.POINTER(C.c_int)]),
     "dfb_find_regions": (C.c_int, [C.c_void_p, C.c_void_p, c_f64p, C.c_double, C.c_double, C.c_int32, C.c_int32,
                                    C.c_int, c_vpp]),

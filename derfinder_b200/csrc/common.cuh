@@ -123,6 +123,16 @@ struct dfb_ctx {
     // permutation scan occupies the main stream
     cudaStream_t aux = nullptr;
     cudaEvent_t ev_main = nullptr, ev_aux = nullptr;
+    // background download (dfb_fstats_begin): its own stream, two pinned stages and one host thread, so a
+    // large result crosses PCIe and lands in the caller's pageable vector while the main stream computes
+    struct Background {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t ready = nullptr, ev[2] = {nullptr, nullptr};
+        char* pin = nullptr;
+        std::thread th;
+        bool active = false;
+        int rc = 0;
+    } bg;
     // log2(k + scalefac) table for integer coverage (glibc log2, built once per scalefac)
     double* lut_dev = nullptr;
     int64_t lut_n = 0;
@@ -245,6 +255,10 @@ int d2h(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);  // synchronise
 // pool; both return with the copy complete.  A source/destination that is already pinned (or
 // registered) host memory is copied directly.
 int d2h_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);
+// the same copy in the background, ordered after the work queued on the stream so far; dst must not
+// be touched until bg_download_wait (every other pooled transfer of the context waits for it too)
+int bg_download_begin(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);
+int bg_download_wait(dfb_ctx* ctx);
 int h2d_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);
 // H2D of `count` host segments packed back to back at dst (through the pinned ring); synchronises.
 int h2d_gather(dfb_ctx* ctx, void* dst, const void* const* srcs, const size_t* bytes, int count, bool sync = true);

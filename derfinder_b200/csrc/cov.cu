@@ -914,6 +914,7 @@ int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, 
 
 void dfb_cov_free(dfb_cov* cov) {
     if (!cov) return;
+    bg_download_wait(cov->ctx);  // a pending dfb_fstats_begin download reads this handle's buffer
     cudaStreamSynchronize(cov->ctx->stream);
     delete cov;
 }

@@ -147,6 +147,7 @@ constexpr size_t STAGE_BYTES = 8u << 20;
 constexpr int NSTAGE = 4;
 
 static int ensure_staging(dfb_ctx* ctx) {
+    if (ctx->bg.active) DFB_TRY(bg_download_wait(ctx));  // the copy pool serves one transfer at a time
     if (ctx->pinned) return DFB_OK;
     DFB_CUDA(cudaMallocHost(&ctx->pinned, NSTAGE * STAGE_BYTES));
     ctx->pinned_bytes = NSTAGE * STAGE_BYTES;
@@ -228,6 +229,60 @@ static int d2h_chunks(dfb_ctx* ctx, const void* src, size_t bytes, Sink sink) {
         DFB_CUDA(cudaEventSynchronize(ctx->stage_ev[done % NSTAGE]));
         sink(off, pin + (done % NSTAGE) * STAGE_BYTES, sz);
     }
+    return DFB_OK;
+}
+
+int bg_download_wait(dfb_ctx* ctx) {
+    if (!ctx->bg.active) return DFB_OK;
+    ctx->bg.th.join();
+    ctx->bg.active = false;
+    if (ctx->bg.rc < 0) {
+        set_error("background download failed");
+        return ctx->bg.rc;
+    }
+    return DFB_OK;
+}
+
+int bg_download_begin(dfb_ctx* ctx, void* dst, const void* src, size_t bytes) {
+    DFB_TRY(ensure_staging(ctx));  // waits for a previous background download; creates the copy pool
+    if (bytes == 0) return DFB_OK;
+    auto& g = ctx->bg;
+    if (!g.stream) {
+        DFB_CUDA(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+        DFB_CUDA(cudaEventCreateWithFlags(&g.ready, cudaEventDisableTiming));
+        for (int i = 0; i < 2; ++i) DFB_CUDA(cudaEventCreateWithFlags(&g.ev[i], cudaEventDisableTiming));
+        DFB_CUDA(cudaMallocHost((void**)&g.pin, 2 * STAGE_BYTES));
+    }
+    DFB_CUDA(cudaEventRecord(g.ready, ctx->stream));
+    DFB_CUDA(cudaStreamWaitEvent(g.stream, g.ready, 0));
+    g.rc = DFB_OK;
+    g.active = true;
+    g.th = std::thread([ctx, dst, src, bytes] {
+        auto& b = ctx->bg;
+        if (cudaSetDevice(ctx->device) != cudaSuccess) {
+            b.rc = DFB_ECUDA;
+            return;
+        }
+        const size_t nchunk = (bytes + STAGE_BYTES - 1) / STAGE_BYTES;
+        size_t issued = 0;
+        for (size_t done = 0; done < nchunk; ++done) {
+            for (; issued < nchunk && issued < done + 2; ++issued) {
+                const size_t off = issued * STAGE_BYTES, sz = std::min(STAGE_BYTES, bytes - off);
+                if (cudaMemcpyAsync(b.pin + (issued & 1) * STAGE_BYTES, (const char*)src + off, sz, cudaMemcpyDeviceToHost,
+                                    b.stream) != cudaSuccess ||
+                    cudaEventRecord(b.ev[issued & 1], b.stream) != cudaSuccess) {
+                    b.rc = DFB_ECUDA;
+                    return;
+                }
+            }
+            if (cudaEventSynchronize(b.ev[done & 1]) != cudaSuccess) {
+                b.rc = DFB_ECUDA;
+                return;
+            }
+            const size_t off = done * STAGE_BYTES, sz = std::min(STAGE_BYTES, bytes - off);
+            pool_memcpy(ctx, (char*)dst + off, b.pin + (done & 1) * STAGE_BYTES, sz);
+        }
+    });
     return DFB_OK;
 }
 
@@ -577,6 +632,15 @@ void dfb_destroy(dfb_ctx* c) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
     }
+    bg_download_wait(c);
+    if (c->bg.stream) {
+        cudaStreamSynchronize(c->bg.stream);
+        cudaStreamDestroy(c->bg.stream);
+        cudaEventDestroy(c->bg.ready);
+        cudaEventDestroy(c->bg.ev[0]);
+        cudaEventDestroy(c->bg.ev[1]);
+        cudaFreeHost(c->bg.pin);
+    }
     for (auto e : c->ev_free) cudaEventDestroy(e);
     if (c->pinned) {
         cudaFreeHost(c->pinned);
@@ -597,6 +661,7 @@ void dfb_destroy(dfb_ctx* c) {
 
 int dfb_sync(dfb_ctx* c) {
     DFB_REQUIRE(c, "dfb_sync: NULL context");
+    DFB_TRY(bg_download_wait(c));
     DFB_CUDA(cudaStreamSynchronize(c->stream));
     return DFB_OK;
 }

@@ -584,6 +584,18 @@ int dfb_fstats(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const doubl
     return DFB_OK;
 }
 
+int dfb_fstats_begin(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const double* mod0, int p0, double adjust_f,
+                     double* fstats_out) {
+    DFB_REQUIRE(fstats_out, "dfb_fstats_begin: NULL destination (use dfb_fstats to keep the statistics on the device)");
+    DFB_TRY(dfb_fstats(ctx, cov, mod, p, mod0, p0, adjust_f, nullptr));
+    return bg_download_begin(ctx, fstats_out, cov->fstats.p, (size_t)cov->N * sizeof(double));
+}
+
+int dfb_fstats_wait(dfb_ctx* ctx) {
+    DFB_REQUIRE(ctx, "dfb_fstats_wait: NULL context");
+    return bg_download_wait(ctx);
+}
+
 int dfb_perm_nulls(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const double* mod0, int p0, double adjust_f,
                    const int32_t* perm_idx, int64_t B, double cutoff_lo, double cutoff_hi, int32_t max_region_gap,
                    dfb_nulls** out) {

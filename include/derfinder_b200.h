@@ -170,6 +170,15 @@ int64_t dfb_chunk_lengths(int64_t N, double chunksize, int mc_cores, int64_t* le
  * F = ((rss0-rss1)/(p-p0)) / (adjustF + rss1/(n-p))  (tests/testthat/test_Fstats.R:52-63). */
 int dfb_fstats(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const double* mod0, int p0,
                double adjust_f, double* fstats_out);
+/* Split form for callers that do not read the statistics right away (the R glue can hand back a
+ * lazily materialised vector: calculatePvalues() uses the device copy, R/calculatePvalues.R:234):
+ * dfb_fstats_begin returns once the kernel is queued and downloads into fstats_out in the
+ * background -- its own stream, pinned stages and host threads -- while the caller goes on (normally
+ * to dfb_calculate_pvalues).  fstats_out is complete, and may be touched, after dfb_fstats_wait;
+ * dfb_cov_free and any other bulk transfer of the context wait for it as well. */
+int dfb_fstats_begin(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const double* mod0,
+                     int p0, double adjust_f, double* fstats_out);
+int dfb_fstats_wait(dfb_ctx* ctx);
 /* Orthonormal nested basis the engine uses for (mod0, mod): q is [n x p] column-major, first p0
  * columns span mod0.  *centered = 1 when the constant vector lies in span(mod0) and rows are
  * mean-centred before the contraction.  Exposed for the parity tests. */

@@ -861,3 +861,44 @@ def test_view_dense_dev_equals_copy(dfb, eng, N):
         assert np.array_equal(dev.cpu().numpy(), cov)  # the borrowed matrix is never written or freed
     finally:
         e2.close()
+
+
+@pytest.mark.gpu
+def test_fstats_begin_wait_equals_blocking(dfb, eng):
+    """dfb_fstats_begin / dfb_fstats_wait deliver the same vector as the blocking dfb_fstats, also when
+    dfb_calculate_pvalues runs in between (the download proceeds on its own stream and host threads)
+    and when the handle is freed without an explicit wait."""
+    from derfinder_b200 import _lib as L
+    rng = np.random.default_rng(808)
+    n, N = 9, 3_000_000  # 24 MB of statistics: three 8 MiB stages
+    cov = rng.poisson(3.0, size=(n, N)).astype(np.int32)
+    mod = np.asfortranarray(np.column_stack([np.ones(n), np.arange(n) % 2, rng.normal(size=n)]))
+    mod0 = np.asfortranarray(mod[:, [0, 2]])
+    pl = np.array([N], dtype=np.int32)
+    perm = random_perms(rng, 3, n).astype(np.int32)
+
+    def handle():
+        h = C.c_void_p()
+        L.check(eng.lib.dfb_cov_from_dense(eng.h, n, N, L.DFB_I32, cov.ctypes.data_as(C.c_void_p), N,
+                                           L.ptr(pl, C.c_int32), 1, 1, C.byref(h)))
+        L.check(eng.lib.dfb_preprocess(eng.h, h, 32.0, None, 0))
+        return h
+
+    args = (mod.ctypes.data_as(L.c_f64p), 3, mod0.ctypes.data_as(L.c_f64p), 2, 0.0)
+    h = handle()
+    want = np.empty(N)
+    L.check(eng.lib.dfb_fstats(eng.h, h, *args, want.ctypes.data_as(L.c_f64p)))
+    got = np.full(N, -7.0)
+    L.check(eng.lib.dfb_fstats_begin(eng.h, h, *args, got.ctypes.data_as(L.c_f64p)))
+    rh, nh = C.c_void_p(), C.c_void_p()
+    rc = L.check(eng.lib.dfb_calculate_pvalues(eng.h, h, None, *args[:4], 0.0, L.ptr(perm, C.c_int32), 3, -6.0, 6.0, 0,
+                                               300, C.byref(rh), C.byref(nh), None))
+    L.check(eng.lib.dfb_fstats_wait(eng.h))
+    assert np.array_equal(got, want, equal_nan=True)
+    if rc == 0:
+        eng.lib.dfb_regions_free(rh)
+        eng.lib.dfb_nulls_free(nh)
+    got2 = np.full(N, -7.0)
+    L.check(eng.lib.dfb_fstats_begin(eng.h, h, *args, got2.ctypes.data_as(L.c_f64p)))
+    eng.lib.dfb_cov_free(h)  # waits for the pending download
+    assert np.array_equal(got2, want, equal_nan=True)
