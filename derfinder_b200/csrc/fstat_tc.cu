@@ -924,12 +924,13 @@ __global__ void __launch_bounds__(FZ_MAX_THREADS) fstat_null_kernel(const FusedP
             const bool valid = base < P.N && !(P.dbg & 32);
             double acc = 0.0;
             if (valid) {
-                for (int k0 = 0; k0 < n; k0 += 8) {  // 8 independent loads in flight, then the ordered sum
-                    double v[8];
+                constexpr int LB = 12;  // independent loads in flight, then the ordered sum
+                for (int k0 = 0; k0 < n; k0 += LB) {
+                    double v[LB];
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = (k0 + e < n) ? P.Y[(size_t)(k0 + e) * P.ld + base] : 0.0;
+                    for (int e = 0; e < LB; ++e) v[e] = (k0 + e < n) ? P.Y[(size_t)(k0 + e) * P.ld + base] : 0.0;
 #pragma unroll
-                    for (int e = 0; e < 8; ++e)
+                    for (int e = 0; e < LB; ++e)
                         if (k0 + e < n) {
                             if (ys_smem) ys[(size_t)(k0 + e) * TC_M + tid] = v[e];
                             acc = (k0 + e == 0) ? v[e] : __dadd_rn(acc, v[e]);
