@@ -164,27 +164,9 @@ __device__ __forceinline__ uint32_t region_starts(uint32_t m, uint32_t prev_msb,
     return m & (~((m << 1) | prev_msb) | seg);
 }
 
-__global__ void __launch_bounds__(256) count_starts_kernel(const uint32_t* __restrict__ mask,
-                                                           const uint32_t* __restrict__ seg, int64_t rows,
-                                                           int64_t W, uint32_t* __restrict__ counts) {
-    const int64_t total = rows * W;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
-         g += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t w = g % W;
-        const uint32_t m = mask[g];
-        uint32_t c = 0;
-        if (m) {
-            const uint32_t prev = w > 0 ? (mask[g - 1] >> 31) : 0u;
-            c = __popc(region_starts(m, prev, seg[w]));
-        }
-        counts[g] = c;
-    }
-}
-
 struct EmitParams {
     const uint32_t* mask;
     const uint32_t* seg;
-    const int64_t* offsets;  // exclusive scan of counts
     int64_t rows, W, N;
     int sides;  // rows per permutation (1 or 2)
     // value source
@@ -203,20 +185,62 @@ struct EmitParams {
     int32_t* perm;  // 1-based permutation id = row / sides + 1
 };
 
-// position (global word index << 5 | bit) of every region start, in (row, index) order
-__global__ void __launch_bounds__(256) fill_starts_kernel(const uint32_t* __restrict__ mask,
-                                                          const uint32_t* __restrict__ seg,
-                                                          const int64_t* __restrict__ offsets, int64_t rows, int64_t W,
-                                                          int64_t* __restrict__ start_pos) {
-    const int64_t total = rows * W;
-    for (int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; g < total;
-         g += (int64_t)gridDim.x * blockDim.x) {
-        const uint32_t m = mask[g];
-        if (!m) continue;
-        const int64_t w = g % W;
-        const uint32_t prev = w > 0 ? (mask[g - 1] >> 31) : 0u;
-        uint32_t starts = region_starts(m, prev, seg[w]);
-        int64_t out = offsets[g];
+// position (global word index << 5 | bit) of every region start, in (row, index) order:
+// The null scan has rows * W ~ 10^7 mask words but ~10^6 region starts: counting per GROUP of 32 words
+// (one warp, row-local so that a row starts a group) keeps the scan 32x smaller and drops the per-word
+// count and offset arrays (180 B of traffic per 32 words -> 12); the fill pass recomputes the word's
+// starts and places them with a warp prefix sum.
+__global__ void __launch_bounds__(256) count_starts_group_kernel(const uint32_t* __restrict__ mask,
+                                                                 const uint32_t* __restrict__ seg, int64_t rows,
+                                                                 int64_t W, int64_t Gr, uint32_t* __restrict__ counts) {
+    const int lane = threadIdx.x & 31;
+    const int64_t groups = rows * Gr;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < groups; grp += warps) {
+        const int64_t row = grp / Gr, w = (grp - row * Gr) * 32 + lane;
+        uint32_t c = 0;
+        if (w < W) {
+            const int64_t g = row * W + w;
+            const uint32_t m = mask[g];
+            if (m) {
+                const uint32_t prev = w > 0 ? (mask[g - 1] >> 31) : 0u;
+                c = __popc(region_starts(m, prev, seg[w]));
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) counts[grp] = c;
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_starts_group_kernel(const uint32_t* __restrict__ mask,
+                                                                const uint32_t* __restrict__ seg,
+                                                                const int64_t* __restrict__ goffsets, int64_t rows,
+                                                                int64_t W, int64_t Gr, int64_t* __restrict__ start_pos) {
+    const int lane = threadIdx.x & 31;
+    const int64_t groups = rows * Gr;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < groups; grp += warps) {
+        const int64_t row = grp / Gr, w = (grp - row * Gr) * 32 + lane;
+        uint32_t starts = 0;
+        int64_t g = 0;
+        if (w < W) {
+            g = row * W + w;
+            const uint32_t m = mask[g];
+            if (m) {
+                const uint32_t prev = w > 0 ? (mask[g - 1] >> 31) : 0u;
+                starts = region_starts(m, prev, seg[w]);
+            }
+        }
+        if (!__any_sync(0xffffffffu, starts != 0u)) continue;
+        const int c = __popc(starts);
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        int64_t out = goffsets[grp] + (int64_t)(inc - c);
         while (starts) {
             const int b = __ffs(starts) - 1;
             starts &= starts - 1;
@@ -304,22 +328,23 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
     out->total = 0;
     out->row_counts.assign((size_t)rows, 0);
     if (total_words == 0) return DFB_OK;
+    const int64_t Gr = ceil_div(W, 32), groups = rows * Gr;  // groups of 32 words, row-local
     DevBuf<uint32_t> counts;
     DevBuf<int64_t> offsets, total_dev;
-    DFB_TRY(counts.alloc(ctx, (size_t)total_words));
-    DFB_TRY(offsets.alloc(ctx, (size_t)total_words + 1));
+    DFB_TRY(counts.alloc(ctx, (size_t)groups));
+    DFB_TRY(offsets.alloc(ctx, (size_t)groups + 1));
     DFB_TRY(total_dev.alloc(ctx, 1));
     {
         KTimer t(ctx, DFB_K_REGIONS);
-        count_starts_kernel<<<grid_for(total_words, 256, ctx->sm_count), 256, 0, ctx->stream>>>(mask, seg, rows, W,
-                                                                                               counts.p);
+        count_starts_group_kernel<<<grid_for(groups * 32, 256, ctx->sm_count), 256, 0, ctx->stream>>>(mask, seg, rows, W,
+                                                                                                    Gr, counts.p);
     }
-    DFB_TRY(exclusive_scan_u32(ctx, counts.p, offsets.p, total_words, total_dev.p, DFB_K_REGIONS));
+    DFB_TRY(exclusive_scan_u32(ctx, counts.p, offsets.p, groups, total_dev.p, DFB_K_REGIONS));
     // per-row counts: offsets at the row starts (strided gather) + total, read back through pinned
     // memory with one synchronisation (which also publishes a deferred K2 cursor, if any)
     int64_t* row_off = (int64_t*)arena_alloc(ctx, ((size_t)rows + 1) * sizeof(int64_t));
     DFB_REQUIRE(row_off != nullptr, "pinned arena allocation failed");
-    DFB_CUDA(cudaMemcpy2DAsync(row_off, sizeof(int64_t), offsets.p, (size_t)W * sizeof(int64_t), sizeof(int64_t),
+    DFB_CUDA(cudaMemcpy2DAsync(row_off, sizeof(int64_t), offsets.p, (size_t)Gr * sizeof(int64_t), sizeof(int64_t),
                                (size_t)rows, cudaMemcpyDeviceToHost, ctx->stream));
     DFB_CUDA(cudaMemcpyAsync(row_off + rows, total_dev.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     DFB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -343,7 +368,6 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
     memset(&P, 0, sizeof P);
     P.mask = mask;
     P.seg = seg;
-    P.offsets = offsets.p;
     P.rows = rows;
     P.W = W;
     P.N = N;
@@ -366,8 +390,8 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
     DFB_TRY(start_pos.alloc(ctx, (size_t)out->total));
     {
         KTimer t(ctx, DFB_K_REGIONS);
-        fill_starts_kernel<<<grid_for(total_words, 256, ctx->sm_count), 256, 0, ctx->stream>>>(mask, seg, offsets.p, rows,
-                                                                                              W, start_pos.p);
+        fill_starts_group_kernel<<<grid_for(groups * 32, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
+            mask, seg, offsets.p, rows, W, Gr, start_pos.p);
     }
     {
         KTimer t(ctx, DFB_K_REGIONS);
