@@ -190,26 +190,34 @@ struct EmitParams {
 // (one warp, row-local so that a row starts a group) keeps the scan 32x smaller and drops the per-word
 // count and offset arrays (180 B of traffic per 32 words -> 12); the fill pass recomputes the word's
 // starts and places them with a warp prefix sum.
+constexpr int GROUPS_PER_WARP = 8;  // independent 128-byte loads a warp keeps in flight
+
 __global__ void __launch_bounds__(256) count_starts_group_kernel(const uint32_t* __restrict__ mask,
                                                                  const uint32_t* __restrict__ seg, int64_t rows,
                                                                  int64_t W, int64_t Gr, uint32_t* __restrict__ counts) {
+    // grid: (groups of a row / 64, rows); a warp owns GROUPS_PER_WARP consecutive groups and issues all
+    // of their loads before it looks at any (one load per short-lived warp left the kernel latency-bound)
     const int lane = threadIdx.x & 31;
-    const int64_t groups = rows * Gr;
-    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < groups; grp += warps) {
-        const int64_t row = grp / Gr, w = (grp - row * Gr) * 32 + lane;
-        uint32_t c = 0;
-        if (w < W) {
+    for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+        const int64_t k0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS_PER_WARP;
+        if (k0 >= Gr) continue;
+        uint32_t m[GROUPS_PER_WARP], pv[GROUPS_PER_WARP], sg[GROUPS_PER_WARP];
+#pragma unroll
+        for (int u = 0; u < GROUPS_PER_WARP; ++u) {
+            const int64_t w = (k0 + u) * 32 + lane;
+            const bool valid = w < W;
             const int64_t g = row * W + w;
-            const uint32_t m = mask[g];
-            if (m) {
-                const uint32_t prev = w > 0 ? (mask[g - 1] >> 31) : 0u;
-                c = __popc(region_starts(m, prev, seg[w]));
-            }
+            m[u] = valid ? mask[g] : 0u;
+            pv[u] = (valid && w > 0) ? mask[g - 1] : 0u;
+            sg[u] = valid ? seg[w] : 0u;
         }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (lane == 0) counts[grp] = c;
+        for (int u = 0; u < GROUPS_PER_WARP; ++u) {
+            uint32_t c = __popc(region_starts(m[u], pv[u] >> 31, sg[u]));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+            if (lane == 0 && k0 + u < Gr) counts[row * Gr + k0 + u] = c;
+        }
     }
 }
 
@@ -218,33 +226,37 @@ __global__ void __launch_bounds__(256) fill_starts_group_kernel(const uint32_t* 
                                                                 const int64_t* __restrict__ goffsets, int64_t rows,
                                                                 int64_t W, int64_t Gr, int64_t* __restrict__ start_pos) {
     const int lane = threadIdx.x & 31;
-    const int64_t groups = rows * Gr;
-    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-    for (int64_t grp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; grp < groups; grp += warps) {
-        const int64_t row = grp / Gr, w = (grp - row * Gr) * 32 + lane;
-        uint32_t starts = 0;
-        int64_t g = 0;
-        if (w < W) {
-            g = row * W + w;
-            const uint32_t m = mask[g];
-            if (m) {
-                const uint32_t prev = w > 0 ? (mask[g - 1] >> 31) : 0u;
-                starts = region_starts(m, prev, seg[w]);
-            }
-        }
-        if (!__any_sync(0xffffffffu, starts != 0u)) continue;
-        const int c = __popc(starts);
-        int inc = c;
+    for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+        const int64_t k0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS_PER_WARP;
+        if (k0 >= Gr) continue;
+        uint32_t m[GROUPS_PER_WARP], pv[GROUPS_PER_WARP], sg[GROUPS_PER_WARP];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int t = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += t;
+        for (int u = 0; u < GROUPS_PER_WARP; ++u) {
+            const int64_t w = (k0 + u) * 32 + lane;
+            const bool valid = w < W;
+            const int64_t g = row * W + w;
+            m[u] = valid ? mask[g] : 0u;
+            pv[u] = (valid && w > 0) ? mask[g - 1] : 0u;
+            sg[u] = valid ? seg[w] : 0u;
         }
-        int64_t out = goffsets[grp] + (int64_t)(inc - c);
-        while (starts) {
-            const int b = __ffs(starts) - 1;
-            starts &= starts - 1;
-            start_pos[out++] = (g << 5) | (int64_t)b;
+#pragma unroll
+        for (int u = 0; u < GROUPS_PER_WARP; ++u) {
+            uint32_t starts = region_starts(m[u], pv[u] >> 31, sg[u]);
+            if (!__any_sync(0xffffffffu, starts != 0u)) continue;
+            const int c = __popc(starts);
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const int64_t g = row * W + (k0 + u) * 32 + lane;
+            int64_t out = goffsets[row * Gr + k0 + u] + (int64_t)(inc - c);
+            while (starts) {
+                const int b = __ffs(starts) - 1;
+                starts &= starts - 1;
+                start_pos[out++] = (g << 5) | (int64_t)b;
+            }
         }
     }
 }
@@ -329,6 +341,7 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
     out->row_counts.assign((size_t)rows, 0);
     if (total_words == 0) return DFB_OK;
     const int64_t Gr = ceil_div(W, 32), groups = rows * Gr;  // groups of 32 words, row-local
+    const dim3 group_grid((unsigned)ceil_div(Gr, 8 * GROUPS_PER_WARP), (unsigned)std::min<int64_t>(rows, 65535));
     DevBuf<uint32_t> counts;
     DevBuf<int64_t> offsets, total_dev;
     DFB_TRY(counts.alloc(ctx, (size_t)groups));
@@ -336,8 +349,7 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
     DFB_TRY(total_dev.alloc(ctx, 1));
     {
         KTimer t(ctx, DFB_K_REGIONS);
-        count_starts_group_kernel<<<grid_for(groups * 32, 256, ctx->sm_count), 256, 0, ctx->stream>>>(mask, seg, rows, W,
-                                                                                                    Gr, counts.p);
+        count_starts_group_kernel<<<group_grid, 256, 0, ctx->stream>>>(mask, seg, rows, W, Gr, counts.p);
     }
     DFB_TRY(exclusive_scan_u32(ctx, counts.p, offsets.p, groups, total_dev.p, DFB_K_REGIONS));
     // per-row counts: offsets at the row starts (strided gather) + total, read back through pinned
@@ -390,8 +402,7 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
     DFB_TRY(start_pos.alloc(ctx, (size_t)out->total));
     {
         KTimer t(ctx, DFB_K_REGIONS);
-        fill_starts_group_kernel<<<grid_for(groups * 32, 256, ctx->sm_count), 256, 0, ctx->stream>>>(
-            mask, seg, offsets.p, rows, W, Gr, start_pos.p);
+        fill_starts_group_kernel<<<group_grid, 256, 0, ctx->stream>>>(mask, seg, offsets.p, rows, W, Gr, start_pos.p);
     }
     {
         KTimer t(ctx, DFB_K_REGIONS);
