@@ -263,9 +263,14 @@ __global__ void __launch_bounds__(256) fill_starts_group_kernel(const uint32_t* 
 
 // One thread per region: all lanes of a warp walk regions of similar length that are adjacent in
 // memory (the word-parallel predecessor left most lanes idle while one walked).
+// A region that runs past LONG_WORDS mask words is handed to walk_long_regions_kernel (one WARP per
+// region) through `long_list`: the kernel's duration used to be the serial walk of its longest regions
+// (thousands of bases on one thread) rather than its memory traffic.
+constexpr int LONG_WORDS = 3;
 template <bool COMPACT>
 __global__ void __launch_bounds__(128) walk_regions_kernel(const EmitParams P, const int64_t* __restrict__ start_pos,
-                                                           int64_t total) {
+                                                           int64_t total, int32_t* __restrict__ long_list,
+                                                           unsigned int* __restrict__ long_count) {
     const int64_t out = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (out >= total) return;
     const int64_t sp = start_pos[out];
@@ -316,6 +321,10 @@ __global__ void __launch_bounds__(128) walk_regions_kernel(const EmitParams P, c
         j += take;
         vp += take;
         if (take < avail || j >= P.N) break;  // the run ended inside this word
+        if (long_list && cw - w >= LONG_WORDS) {
+            long_list[atomicAdd(long_count, 1u)] = (int32_t)out;
+            return;
+        }
         ++cw;
         const uint32_t nm = mrow[cw], ns = P.seg[cw];
         cont = nm & ~ns;
@@ -330,6 +339,91 @@ __global__ void __launch_bounds__(128) walk_regions_kernel(const EmitParams P, c
     if (P.istart) P.istart[out] = (int32_t)(i + 1);
     if (P.iend) P.iend[out] = (int32_t)j;
     if (P.perm) P.perm[out] = (int32_t)(row / P.sides) + 1;
+}
+
+// One warp per long region: 32 bases (one mask word) per step, loaded together; run heads by ballot,
+// per-run value * length products in parallel, one ordered addition per run -- the same IRanges order
+// as the thread walk (and as view_sums_kernel), with ~1-2 serial steps per word instead of 32.
+template <bool COMPACT>
+__global__ void __launch_bounds__(128) walk_long_regions_kernel(const EmitParams P,
+                                                                const int64_t* __restrict__ start_pos,
+                                                                const int32_t* __restrict__ long_list,
+                                                                const unsigned int* __restrict__ long_count) {
+    const unsigned full = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const int64_t warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    const int64_t n_long = (int64_t)*long_count;
+    const int wpt_shift = COMPACT ? (31 - __clz(P.tile_bases >> 5)) : 0;
+    for (int64_t li = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5; li < n_long; li += warps) {
+        const int64_t out = long_list[li];
+        const int64_t sp = start_pos[out];
+        const int64_t g0 = sp >> 5;
+        const int b0 = (int)(sp & 31);
+        const int64_t row = g0 / P.W, w0 = g0 - row * P.W;
+        const uint32_t* mrow = P.mask + row * P.W;
+        const int64_t i0 = w0 * 32 + b0;
+        double acc = 0.0, open_v = 0.0;
+        int64_t open_len = 0, width = 0;
+        for (int64_t cw = w0;; ++cw) {
+            const uint32_t m = mrow[cw];
+            const int sbit = cw == w0 ? b0 : 0;
+            // bits of the region inside this word: from sbit, while passing and not opening a new segment
+            // (the region's own first base may sit on a segment start)
+            uint32_t x = m & ~P.seg[cw];
+            if (cw == w0) x |= 1u << b0;
+            x >>= sbit;
+            const int avail = (int)min((int64_t)(32 - sbit), P.N - (cw * 32 + sbit));
+            int cnt = __ffs(~x) - 1;  // trailing ones
+            if (cnt < 0 || cnt > avail) cnt = avail;
+            const int bit = sbit + lane;
+            const bool valid = lane < cnt;
+            double v = 0.0;
+            if (valid) {
+                if (COMPACT) {
+                    const int64_t t = cw >> wpt_shift;
+                    int64_t ptr = P.off[row * P.tiles + t];
+                    for (int64_t ww = t << wpt_shift; ww < cw; ++ww) ptr += __popc(mrow[ww]);
+                    v = P.vals[ptr + __popc(m & ((1u << bit) - 1u))];
+                } else {
+                    v = P.dense[row * P.dense_stride + cw * 32 + bit];
+                }
+            }
+            double pv = __shfl_up_sync(full, v, 1);
+            if (lane == 0) pv = open_v;
+            const bool head = valid && ((cw == w0 && lane == 0) || v != pv);
+            const unsigned hm = __ballot_sync(full, head);
+            if (hm == 0) {
+                open_len += cnt;
+            } else {
+                open_len += __ffs(hm) - 1;
+                if (open_len > 0) acc = __dadd_rn(acc, __dmul_rn(open_v, (double)open_len));
+                const unsigned above = hm & ~((2u << lane) - 1u);
+                const int next_head = above ? __ffs(above) - 1 : cnt;
+                const double prod = __dmul_rn(v, (double)(next_head - lane));
+                const int last = 31 - __clz(hm);
+                unsigned mm = hm & ~(1u << last);
+                while (mm) {
+                    const int b = __ffs(mm) - 1;
+                    mm &= mm - 1;
+                    acc = __dadd_rn(acc, __shfl_sync(full, prod, b));
+                }
+                open_v = __shfl_sync(full, v, last);
+                open_len = cnt - last;
+            }
+            width += cnt;
+            if (cnt < 32 - sbit || (cw + 1) * 32 >= P.N) break;  // ended inside this word / at the last base
+        }
+        if (open_len > 0) acc = __dadd_rn(acc, __dmul_rn(open_v, (double)open_len));
+        if (lane == 0) {
+            const int32_t wd = (int32_t)width;
+            if (P.area) P.area[out] = fabs(acc);
+            if (P.stat) P.stat[out] = __ddiv_rn(acc, (double)wd);
+            if (P.width) P.width[out] = wd;
+            if (P.istart) P.istart[out] = (int32_t)(i0 + 1);
+            if (P.iend) P.iend[out] = (int32_t)(i0 + width);
+            if (P.perm) P.perm[out] = (int32_t)(row / P.sides) + 1;
+        }
+    }
 }
 
 int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const uint32_t* mask, const uint32_t* seg,
@@ -400,6 +494,11 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
     P.perm = out->perm.p;
     DevBuf<int64_t> start_pos;
     DFB_TRY(start_pos.alloc(ctx, (size_t)out->total));
+    DevBuf<int32_t> long_list;  // regions handed from the thread walk to the warp walk
+    DevBuf<unsigned int> long_count;
+    DFB_TRY(long_list.alloc(ctx, (size_t)out->total));
+    DFB_TRY(long_count.alloc(ctx, 1));
+    DFB_TRY(long_count.zero());
     {
         KTimer t(ctx, DFB_K_REGIONS);
         fill_starts_group_kernel<<<group_grid, 256, 0, ctx->stream>>>(mask, seg, offsets.p, rows, W, Gr, start_pos.p);
@@ -407,8 +506,17 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
     {
         KTimer t(ctx, DFB_K_REGIONS);
         const unsigned grid = (unsigned)ceil_div(out->total, 128);
-        if (compact) walk_regions_kernel<true><<<grid, 128, 0, ctx->stream>>>(P, start_pos.p, out->total);
-        else walk_regions_kernel<false><<<grid, 128, 0, ctx->stream>>>(P, start_pos.p, out->total);
+        if (compact)
+            walk_regions_kernel<true><<<grid, 128, 0, ctx->stream>>>(P, start_pos.p, out->total, long_list.p, long_count.p);
+        else
+            walk_regions_kernel<false><<<grid, 128, 0, ctx->stream>>>(P, start_pos.p, out->total, long_list.p,
+                                                                      long_count.p);
+    }
+    {
+        KTimer t(ctx, DFB_K_REGIONS);
+        const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(out->total, 4), (int64_t)ctx->sm_count * 16);
+        if (compact) walk_long_regions_kernel<true><<<grid, 128, 0, ctx->stream>>>(P, start_pos.p, long_list.p, long_count.p);
+        else walk_long_regions_kernel<false><<<grid, 128, 0, ctx->stream>>>(P, start_pos.p, long_list.p, long_count.p);
     }
     DFB_CUDA(cudaGetLastError());
     return DFB_OK;

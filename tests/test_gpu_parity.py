@@ -902,3 +902,41 @@ def test_fstats_begin_wait_equals_blocking(dfb, eng):
     L.check(eng.lib.dfb_fstats_begin(eng.h, h, *args, got2.ctypes.data_as(L.c_f64p)))
     eng.lib.dfb_cov_free(h)  # waits for the pending download
     assert np.array_equal(got2, want, equal_nan=True)
+
+
+@pytest.mark.gpu
+def test_long_regions_warp_walk(dfb, eng):
+    """Regions longer than a few mask words are walked by one warp each (32 bases per step, run heads by
+    ballot) instead of one thread: same IRanges run-product order, so areas, means and widths must
+    stay bit-identical to the oracle -- for long runs of equal values, for runs of length one, across
+    segment boundaries, at odd start bits and at the very end of the vector."""
+    rng = np.random.default_rng(4242)
+    N = 60_000
+    x = np.zeros(N)
+    pos_ptr = 17
+    truth_long = 0
+    while pos_ptr < N - 10:
+        width = int(rng.choice([1, 3, 31, 33, 64, 97, 129, 400, 2500, 7001]))
+        width = min(width, N - pos_ptr)
+        kind = rng.integers(0, 3)
+        if kind == 0:    # piecewise constant (read-length-like runs): long Rle runs
+            runs = np.repeat(rng.uniform(2.0, 9.0, size=width // 40 + 1), 40)[:width]
+        elif kind == 1:  # every value different: every base its own run
+            runs = rng.uniform(2.0, 9.0, size=width)
+        else:            # short runs of 1..5
+            runs = np.repeat(rng.uniform(2.0, 9.0, size=width), rng.integers(1, 6, size=width))[:width]
+        x[pos_ptr:pos_ptr + width] = runs
+        truth_long += width > 128
+        pos_ptr += width + int(rng.integers(1, 70))
+    x[N - 300:] = np.repeat(rng.uniform(2.0, 9.0, size=6), 50)  # a long region ending at the last base
+    assert truth_long > 5
+    position = (np.array([True, False, True, False, True]), np.array([20_011, 500, 19_989, 3000, 20_000]))
+    for gap in (0, 600):
+        got = dfb.findRegions(position, x, "chr1", cutoff=1.5, maxRegionGap=gap, maxClusterGap=3000, engine=eng)
+        want = O.find_regions(position, x, 1.5, maxRegionGap=gap, maxClusterGap=3000)
+        assert_regions_equal(got, want)
+        assert (np.asarray(want["indexEnd"]) - np.asarray(want["indexStart"]) + 1).max() > 2000
+    gb = dfb.findRegions(position, x, "chr1", cutoff=1.5, basic=True, engine=eng)
+    ob = O.find_regions(position, x, 1.5, basic=True)
+    for k in ("area", "width", "stat"):
+        assert np.array_equal(gb[k], ob[k])
