@@ -588,8 +588,8 @@ def main():
         hbm = peaks.get("hbm_gbs", 6650.0)
         alg_bytes = 8.0 * N * n  # read Y once (SURVEY 8d lower bound for the null scan)
         # DRAM traffic of one fstat_null_kernel launch from the committed ncu --set full capture of
-        # this same command (profiles/r1_c_kernels.txt: 469.0 MB read + 341.7 MB written)
-        traffic = 810.7e6 if args.workload == "c2" else None
+        # this same command (profiles/r1_e_kernels.txt: 469.9 MB read + 342.0 MB written)
+        traffic = 811.9e6 if args.workload == "c2" else None
         line["roofline"] = {"bound": "tensor", "kernel": "fstat_null_kernel (K2 permutation scan)", "achieved": achieved,
                             "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak if achieved else None),
                             "traffic": traffic,

@@ -266,7 +266,7 @@ __global__ void __launch_bounds__(256) fill_starts_group_kernel(const uint32_t* 
 // A region that runs past LONG_WORDS mask words is handed to walk_long_regions_kernel (one WARP per
 // region) through `long_list`: the kernel's duration used to be the serial walk of its longest regions
 // (thousands of bases on one thread) rather than its memory traffic.
-constexpr int LONG_WORDS = 3;
+constexpr int LONG_WORDS = 8;
 template <bool COMPACT>
 __global__ void __launch_bounds__(128) walk_regions_kernel(const EmitParams P, const int64_t* __restrict__ start_pos,
                                                            int64_t total, int32_t* __restrict__ long_list,
