@@ -730,6 +730,7 @@ int dfb_set_option(dfb_ctx* c, const char* key, double value) {
     else if (!strcmp(key, "fused")) c->opt_fused = value != 0;
     else if (!strcmp(key, "dbg")) c->opt_dbg = (int)value;
     else if (!strcmp(key, "tmem_stages")) c->opt_tmem_stages = (int)value;
+    else if (!strcmp(key, "k2_waves")) c->opt_k2_waves = (int)value;
     else if (!strcmp(key, "chunk_perms")) c->opt_chunk_perms = (int)value;
     else if (!strcmp(key, "ys_smem")) c->opt_ys_smem = (int)value;
     else if (!strcmp(key, "b_stages")) c->opt_b_stages = (int)value;

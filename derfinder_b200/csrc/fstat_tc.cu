@@ -1702,7 +1702,15 @@ int fstat_perm_batch_fused(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& m
     int per_sm = (int)std::min<size_t>((size_t)(227 * 1024) / (G.smem + 1024), (size_t)(512 / G.tmem_cols));
     per_sm = std::min(per_sm, 65536 / (threads * 100));  // registers (the kernels compile to <= 100)
     per_sm = std::max(1, std::min(per_sm, 6));
-    const int grid = (int)std::min<int64_t>(G.tiles, (int64_t)ctx->sm_count * per_sm);
+    // Not one CTA per resident slot for the whole scan: k2_waves (16) times as many, each walking its
+    // share of the tiles and retiring.  A fully persistent grid keeps every SM slot until the scan ends,
+    // so the observed-region chain on the auxiliary stream (dozens of small dependent kernels) could
+    // not start before that; with CTAs retiring every few tiles and the auxiliary stream at the highest
+    // priority, its blocks take the freed slots first and the chain finishes inside the scan (C2 step
+    // 2.39 -> 2.27 ms; the per-CTA set-up -- TMEM allocation, barriers, Q in shared memory -- is paid 16
+    // times per slot and does not show: K2 1.39 ms either way).  Without the priority the extra waves
+    // only cost (2.5 ms); with the priority but a persistent grid the scan itself slows down (2.0 ms).
+    const int grid = (int)std::min<int64_t>(G.tiles, (int64_t)ctx->sm_count * per_sm * std::max(1, ctx->opt_k2_waves));
     if (getenv("DFB_GAPS"))
         fprintf(stderr, "[dfb] fused geometry: n=%d npad=%d KB=%d pst=%d ps=%d nmma=%d nb=%d ew=%d ys_smem=%d smem=%zu per_sm=%d grid=%d\n",
                 G.n, G.npad, G.KB, G.pst, G.ps, G.nmma, G.nb, G.ew, G.ys_smem, G.smem, per_sm, grid);

@@ -972,7 +972,10 @@ int dfb_calculate_pvalues(dfb_ctx* ctx, dfb_cov* cov, const double* fstats, cons
     // synchronisation) runs on the auxiliary stream WHILE the permutation scan occupies the main one:
     // it is enqueued right after the first null-scan launch.
     if (!ctx->aux) {
-        DFB_CUDA(cudaStreamCreateWithFlags(&ctx->aux, cudaStreamNonBlocking));
+        // highest priority: when the null scan's CTAs retire, the freed SM slots go to this chain first
+        int prio_lo = 0, prio_hi = 0;
+        DFB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        DFB_CUDA(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prio_hi));
         DFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
         DFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
     }

@@ -100,7 +100,8 @@ int dfb_kernel_time(dfb_ctx* ctx, int kernel, double* ms, int64_t* launches);
  * identical for every valid setting, tests/test_gpu_parity.py::test_fused_kernel_variants_agree):
  *   "chunk_perms" permutations per MMA chunk, "b_stages" B-tile stages (1-4), "tmem_stages"
  *   accumulator stages (1-2), "epi_warps" epilogue warps per TMEM quarter (1-4), "ys_smem" FP64
- *   tile resident (1) or streamed (0); "dbg" bit flags switch parts of the kernel OFF for timing
+ *   tile resident (1) or streamed (0), "k2_waves" CTAs launched per resident slot (default 16;
+ *   1 = fully persistent grid); "dbg" bit flags switch parts of the kernel OFF for timing
  *   experiments (results then invalid; 64 = print clock64 phase counters only). */
 int dfb_set_option(dfb_ctx* ctx, const char* key, double value);
 

@@ -751,7 +751,7 @@ def test_full_size_paths_agree(dfb, full_c2):
 
 
 @pytest.mark.parametrize("opts", [dict(ys_smem=0), dict(ys_smem=0, epi_warps=2), dict(epi_warps=2), dict(b_stages=3),
-                                  dict(ys_smem=1, b_stages=2, epi_warps=4)])
+                                  dict(ys_smem=1, b_stages=2, epi_warps=4), dict(k2_waves=1), dict(k2_waves=3)])
 def test_fused_kernel_variants_agree(dfb, eng, opts):
     """Every layout variant of the fused null kernel (streamed FP64 tile, several epilogue warps per
     TMEM quarter, deeper B staging) must reproduce the oracle pipeline bit for bit on a
