@@ -364,12 +364,30 @@ __global__ void __launch_bounds__(128) walk_long_regions_kernel(const EmitParams
         const int64_t i0 = w0 * 32 + b0;
         double acc = 0.0, open_v = 0.0;
         int64_t open_len = 0, width = 0;
+        // first value slot of a word (COMPACT): tile offset + passing bases of the tile's earlier words
+        auto word_ptr = [&](int64_t cw) -> int64_t {
+            const int64_t t = cw >> wpt_shift;
+            int64_t ptr = P.off[row * P.tiles + t];
+            for (int64_t ww = t << wpt_shift; ww < cw; ++ww) ptr += __popc(mrow[ww]);
+            return ptr;
+        };
+        // the mask word, segment word and value offset of the NEXT word are requested before the values of
+        // the current one: one dependent memory round trip per 32 bases instead of three
+        uint32_t m = mrow[w0], sgw = P.seg[w0];
+        int64_t wptr = COMPACT ? word_ptr(w0) : 0;
         for (int64_t cw = w0;; ++cw) {
-            const uint32_t m = mrow[cw];
+            const bool has_next = (cw + 1) * 32 < P.N;
+            uint32_t m_next = 0u, sg_next = 0u;
+            int64_t wptr_next = 0;
+            if (has_next) {
+                m_next = mrow[cw + 1];
+                sg_next = P.seg[cw + 1];
+                if (COMPACT) wptr_next = word_ptr(cw + 1);
+            }
             const int sbit = cw == w0 ? b0 : 0;
             // bits of the region inside this word: from sbit, while passing and not opening a new segment
             // (the region's own first base may sit on a segment start)
-            uint32_t x = m & ~P.seg[cw];
+            uint32_t x = m & ~sgw;
             if (cw == w0) x |= 1u << b0;
             x >>= sbit;
             const int avail = (int)min((int64_t)(32 - sbit), P.N - (cw * 32 + sbit));
@@ -380,10 +398,7 @@ __global__ void __launch_bounds__(128) walk_long_regions_kernel(const EmitParams
             double v = 0.0;
             if (valid) {
                 if (COMPACT) {
-                    const int64_t t = cw >> wpt_shift;
-                    int64_t ptr = P.off[row * P.tiles + t];
-                    for (int64_t ww = t << wpt_shift; ww < cw; ++ww) ptr += __popc(mrow[ww]);
-                    v = P.vals[ptr + __popc(m & ((1u << bit) - 1u))];
+                    v = P.vals[wptr + __popc(m & ((1u << bit) - 1u))];
                 } else {
                     v = P.dense[row * P.dense_stride + cw * 32 + bit];
                 }
@@ -411,7 +426,10 @@ __global__ void __launch_bounds__(128) walk_long_regions_kernel(const EmitParams
                 open_len = cnt - last;
             }
             width += cnt;
-            if (cnt < 32 - sbit || (cw + 1) * 32 >= P.N) break;  // ended inside this word / at the last base
+            if (cnt < 32 - sbit || !has_next) break;  // ended inside this word / at the last base
+            m = m_next;
+            sgw = sg_next;
+            wptr = wptr_next;
         }
         if (open_len > 0) acc = __dadd_rn(acc, __dmul_rn(open_v, (double)open_len));
         if (lane == 0) {
