@@ -112,6 +112,10 @@ struct dfb_ctx {
     void* pinned = nullptr;
     size_t pinned_bytes = 0;
     cudaEvent_t stage_ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    // h2d_gather pipelines the same ring in 2 MiB sub-stages (a 10 MB Rle upload overlaps its packing with
+    // its DMA instead of alternating 8 MiB of each); the counter runs on across calls
+    std::vector<cudaEvent_t> gather_ev;
+    size_t gather_chunk = 0;
     dfb::CopyPool* pool = nullptr;
     // pinned arena for scalar / O(regions) read-backs: D2H into pinned memory is truly asynchronous,
     // so several results can be fetched with ONE stream synchronisation.  Blocks are kept for reuse.

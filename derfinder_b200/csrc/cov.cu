@@ -447,7 +447,7 @@ static int upload_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values,
             srcs[(size_t)s] = values[s];
             nb[(size_t)s] = (size_t)nruns[s] * es;
         }
-        DFB_TRY(h2d_gather(ctx, up->values.p, srcs.data(), nb.data(), n));
+        DFB_TRY(h2d_gather(ctx, up->values.p, srcs.data(), nb.data(), n, /*sync=*/false));  // lengths follow
         for (int s = 0; s < n; ++s) {
             srcs[(size_t)s] = lengths[s];
             nb[(size_t)s] = (size_t)nruns[s] * sizeof(int32_t);

@@ -361,17 +361,23 @@ int d2h_dup(dfb_ctx* ctx, void* dst, const void* src, size_t elem, const int64_t
 // pinned ring by the copy pool (one DMA per 8 MiB instead of one driver-staged copy per segment).
 int h2d_gather(dfb_ctx* ctx, void* dst, const void* const* srcs, const size_t* bytes, int count, bool sync) {
     DFB_TRY(ensure_staging(ctx));
+    constexpr size_t GS = 2u << 20;                      // sub-stage
+    constexpr size_t NG = NSTAGE * STAGE_BYTES / GS;     // sub-stages in the ring
+    if (ctx->gather_ev.empty()) {
+        ctx->gather_ev.resize(NG, nullptr);
+        for (auto& e : ctx->gather_ev) DFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    }
     char* pin = (char*)ctx->pinned;
     struct Piece { char* d; const char* s; size_t n; };
-    size_t chunk = 0, fill = 0, dev_off = 0;
+    size_t& chunk = ctx->gather_chunk;  // persistent: a call that does not synchronise leaves DMAs in flight
+    size_t fill = 0, dev_off = 0;
     std::vector<Piece> pieces;
     bool waited = false;
     auto flush = [&]() -> int {
         if (fill == 0) return DFB_OK;
         ctx->pool->parallel_for((int)pieces.size(), [&](int i) { copy_stream(pieces[i].d, pieces[i].s, pieces[i].n); });
-        DFB_CUDA(cudaMemcpyAsync((char*)dst + dev_off, pin + (chunk % NSTAGE) * STAGE_BYTES, fill, cudaMemcpyHostToDevice,
-                                 ctx->stream));
-        DFB_CUDA(cudaEventRecord(ctx->stage_ev[chunk % NSTAGE], ctx->stream));
+        DFB_CUDA(cudaMemcpyAsync((char*)dst + dev_off, pin + (chunk % NG) * GS, fill, cudaMemcpyHostToDevice, ctx->stream));
+        DFB_CUDA(cudaEventRecord(ctx->gather_ev[chunk % NG], ctx->stream));
         dev_off += fill;
         fill = 0;
         pieces.clear();
@@ -382,21 +388,21 @@ int h2d_gather(dfb_ctx* ctx, void* dst, const void* const* srcs, const size_t* b
     for (int i = 0; i < count; ++i) {
         size_t done = 0;
         while (done < bytes[i]) {
-            if (!waited && chunk >= (size_t)NSTAGE) DFB_CUDA(cudaEventSynchronize(ctx->stage_ev[chunk % NSTAGE]));
+            if (!waited && chunk >= NG) DFB_CUDA(cudaEventSynchronize(ctx->gather_ev[chunk % NG]));
             waited = true;
-            const size_t room = STAGE_BYTES - fill;
+            const size_t room = GS - fill;
             const size_t take = std::min(room, bytes[i] - done);
-            char* base = pin + (chunk % NSTAGE) * STAGE_BYTES + fill;
-            for (size_t o = 0; o < take; o += (256u << 10))
-                pieces.push_back({base + o, (const char*)srcs[i] + done + o, std::min<size_t>(256u << 10, take - o)});
+            char* base = pin + (chunk % NG) * GS + fill;
+            for (size_t o = 0; o < take; o += (128u << 10))
+                pieces.push_back({base + o, (const char*)srcs[i] + done + o, std::min<size_t>(128u << 10, take - o)});
             fill += take;
             done += take;
-            if (fill == STAGE_BYTES) DFB_TRY(flush());
+            if (fill == GS) DFB_TRY(flush());
         }
     }
     DFB_TRY(flush());
-    // the sources have been copied into pinned memory: without `sync` the caller may go on (and may
-    // free them); the ring's events guard the reuse of the staging buffers
+    // the sources have been copied into pinned memory: without `sync` the caller may go on (and may free
+    // them) but must synchronise the stream before any other user of the ring runs
     if (sync) DFB_CUDA(cudaStreamSynchronize(ctx->stream));
     return DFB_OK;
 }
@@ -644,6 +650,8 @@ void dfb_destroy(dfb_ctx* c) {
         cudaFreeHost(c->bg.pin);
     }
     for (auto e : c->ev_free) cudaEventDestroy(e);
+    for (auto e : c->gather_ev)
+        if (e) cudaEventDestroy(e);
     if (c->pinned) {
         cudaFreeHost(c->pinned);
         for (int i = 0; i < 4; ++i) cudaEventDestroy(c->stage_ev[i]);
