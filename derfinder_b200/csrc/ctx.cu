@@ -168,6 +168,15 @@ static int ensure_staging(dfb_ctx* ctx) {
     return DFB_OK;
 }
 
+constexpr size_t SUB_BYTES = 2u << 20;                       // sub-stage of the ring
+constexpr size_t NSUB = NSTAGE * STAGE_BYTES / SUB_BYTES;      // sub-stages in the ring
+static int ensure_substage_events(dfb_ctx* ctx) {
+    if (!ctx->gather_ev.empty()) return DFB_OK;
+    ctx->gather_ev.resize(NSUB, nullptr);
+    for (auto& e : ctx->gather_ev) DFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    return DFB_OK;
+}
+
 static bool is_pinned_host(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
@@ -299,22 +308,26 @@ int d2h_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes) {
 template <typename Sink>
 static int d2h_chunks_multi(dfb_ctx* ctx, int na, const void* const* srcs, const size_t* bytes, Sink sink) {
     DFB_TRY(ensure_staging(ctx));
+    DFB_TRY(ensure_substage_events(ctx));
+    // 2 MiB sub-stages of the ring, 16 in flight: the whole ~30 MB of a C2 result is requested up front
+    // and the host drains each piece as it lands (8 MiB stages left 0.2 ms of DMA and 0.2 ms of host
+    // copy un-overlapped at the two ends)
     char* pin = (char*)ctx->pinned;
     struct Chunk { int a; size_t off, sz; };
     std::vector<Chunk> chunks;
     for (int a = 0; a < na; ++a)
-        for (size_t off = 0; off < bytes[a]; off += STAGE_BYTES) chunks.push_back({a, off, std::min(STAGE_BYTES, bytes[a] - off)});
+        for (size_t off = 0; off < bytes[a]; off += SUB_BYTES) chunks.push_back({a, off, std::min(SUB_BYTES, bytes[a] - off)});
     size_t issued = 0;
     for (size_t done = 0; done < chunks.size(); ++done) {
-        for (; issued < chunks.size() && issued < done + NSTAGE; ++issued) {
+        for (; issued < chunks.size() && issued < done + NSUB; ++issued) {
             const Chunk& c = chunks[issued];
-            DFB_CUDA(cudaMemcpyAsync(pin + (issued % NSTAGE) * STAGE_BYTES, (const char*)srcs[c.a] + c.off, c.sz,
+            DFB_CUDA(cudaMemcpyAsync(pin + (issued % NSUB) * SUB_BYTES, (const char*)srcs[c.a] + c.off, c.sz,
                                      cudaMemcpyDeviceToHost, ctx->stream));
-            DFB_CUDA(cudaEventRecord(ctx->stage_ev[issued % NSTAGE], ctx->stream));
+            DFB_CUDA(cudaEventRecord(ctx->gather_ev[issued % NSUB], ctx->stream));
         }
-        DFB_CUDA(cudaEventSynchronize(ctx->stage_ev[done % NSTAGE]));
+        DFB_CUDA(cudaEventSynchronize(ctx->gather_ev[done % NSUB]));
         const Chunk& c = chunks[done];
-        sink(c.a, c.off, pin + (done % NSTAGE) * STAGE_BYTES, c.sz);
+        sink(c.a, c.off, pin + (done % NSUB) * SUB_BYTES, c.sz);
     }
     return DFB_OK;
 }
@@ -341,8 +354,8 @@ int d2h_dup_multi(dfb_ctx* ctx, int na, void* const* dsts, const void* const* sr
             char* d1 = (char*)dsts[a] + (size_t)(2 * pre[b] + (lo - pre[b])) * elem;
             const char* sp = p + (size_t)(lo - e0) * elem;
             const size_t nb = (size_t)(hi - lo) * elem;
-            for (size_t o = 0; o < nb; o += (256u << 10))  // ~256 KiB pieces for the pool
-                parts.push_back({d1 + o, d1 + (size_t)k * elem + o, sp + o, std::min<size_t>(256u << 10, nb - o)});
+            for (size_t o = 0; o < nb; o += (128u << 10))  // ~128 KiB pieces for the pool
+                parts.push_back({d1 + o, d1 + (size_t)k * elem + o, sp + o, std::min<size_t>(128u << 10, nb - o)});
         }
         ctx->pool->parallel_for((int)parts.size(), [&](int i) {
             copy_stream(parts[i].d1, parts[i].s, parts[i].n);
@@ -361,12 +374,8 @@ int d2h_dup(dfb_ctx* ctx, void* dst, const void* src, size_t elem, const int64_t
 // pinned ring by the copy pool (one DMA per 8 MiB instead of one driver-staged copy per segment).
 int h2d_gather(dfb_ctx* ctx, void* dst, const void* const* srcs, const size_t* bytes, int count, bool sync) {
     DFB_TRY(ensure_staging(ctx));
-    constexpr size_t GS = 2u << 20;                      // sub-stage
-    constexpr size_t NG = NSTAGE * STAGE_BYTES / GS;     // sub-stages in the ring
-    if (ctx->gather_ev.empty()) {
-        ctx->gather_ev.resize(NG, nullptr);
-        for (auto& e : ctx->gather_ev) DFB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
-    }
+    constexpr size_t GS = SUB_BYTES, NG = NSUB;
+    DFB_TRY(ensure_substage_events(ctx));
     char* pin = (char*)ctx->pinned;
     struct Piece { char* d; const char* s; size_t n; };
     size_t& chunk = ctx->gather_chunk;  // persistent: a call that does not synchronise leaves DMAs in flight
