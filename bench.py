@@ -189,16 +189,60 @@ class ClockSampler(threading.Thread):
 # CPU baseline: the reference's algorithm shape on host cores (numpy/OpenBLAS port, "kind: port")
 
 
+CPU_CHUNK = 100_000  # rows per chunk: the reference's documented chunksize for bplapply (users guide :1327)
+_cpu_pool = None
+
+
+def cpu_workers():
+    """Worker count of the CPU arm: every host core the process may use, whatever the launcher set
+    OMP_NUM_THREADS to (torchrun exports OMP_NUM_THREADS=1)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def _cpu_fstats_chunked(Y, mod, mod0, adjustF=0.0):
+    """fstats.apply over 1e5-row chunks on a pool of host threads -- the shape of the reference's
+    bplapply(chunks, fstats.apply, BPPARAM = SnowParam(mc.cores)) (R/calculateStats.R:105-127,
+    R/calculatePvalues.R:325-329).  Each chunk is two dense residual-projector products (BLAS, one
+    thread per worker: numpy releases the GIL inside them) + row sums."""
+    global _cpu_pool
+    from concurrent.futures import ThreadPoolExecutor
+    from oracle import derfinder_oracle as O
+    if _cpu_pool is None:
+        _cpu_pool = ThreadPoolExecutor(max_workers=cpu_workers())
+    P1, P0 = O._residual_projector(mod), O._residual_projector(mod0)
+    n, df1, df0 = Y.shape[1], mod.shape[1], mod0.shape[1]
+
+    def one(lo):
+        y = Y[lo:lo + CPU_CHUNK]
+        r0, r1 = y @ P0, y @ P1
+        rss0 = np.einsum("ij,ij->i", r0, r0)
+        rss1 = np.einsum("ij,ij->i", r1, r1)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            return ((rss0 - rss1) / (df1 - df0)) / (adjustF + rss1 / (n - df1))
+
+    parts = list(_cpu_pool.map(one, range(0, Y.shape[0], CPU_CHUNK)))
+    return np.concatenate(parts) if parts else np.zeros(0)
+
+
 def cpu_reference_pass(cov_nN, pos_len, pos_first, mod, mod0, perm, cutoff):
     """One pass of the same hot path the way the reference does it: log2 transform, per 1e5-row
-    chunk dense residual-projector products Y %*% P1, Y %*% P0 (BLAS), rowSums, F; serial
-    permutation loop; run segmentation + Rle view sums; .calcPval.  Returns #regions (sanity)."""
+    chunk dense residual-projector products Y %*% P1, Y %*% P0 (BLAS) on all host cores, rowSums, F;
+    serial permutation loop; run segmentation + Rle view sums; .calcPval.  Returns #regions (sanity)."""
+    from threadpoolctl import threadpool_limits
     from oracle import derfinder_oracle as O
     vals = (np.arange(len(pos_len)) % 2 == 0) == bool(pos_first)
     position = (vals, pos_len.astype(np.int64))
-    prep = O.preprocess_coverage(np.ascontiguousarray(cov_nN.T), position, chunksize=1e5)
-    F = O.calculate_stats(prep, mod, mod0)
-    res = O.calculate_pvalues(prep, mod, mod0, F, perm, cutoff)
+    with threadpool_limits(limits=1):  # one BLAS thread per chunk worker, the same at every --gpus N
+        # preprocessCoverage: R's vectorised log2 and Reduce("+") (the oracle's exact-libm table look-up is a
+        # test device, not how the reference spends its time)
+        cov = np.ascontiguousarray(cov_nN.T)
+        prep = dict(coverageProcessed=np.log2(cov + 32.0), mclapplyIndex=O.chunk_lengths(cov.shape[0], CPU_CHUNK, 1),
+                    position=position, meanCoverage=O._ordered_row_sum(cov.T) / cov.shape[1], groupMeans={})
+        F = _cpu_fstats_chunked(prep["coverageProcessed"], mod, mod0)
+        res = O.calculate_pvalues(prep, mod, mod0, F, perm, cutoff, fstat_fn=_cpu_fstats_chunked)
     return 0 if res["regions"] is None else len(res["regions"]["start"])
 
 
@@ -236,8 +280,9 @@ def run_reference_arm(args, cfg):
         cpu_reference_pass(cov, pl, pf, work["mod"], work["mod0"], perm, cutoff)
     dt = (time.perf_counter() - t0) / steps
     value = nb * (npm + 1) / dt
-    cores = os.cpu_count()
-    sample = f"first {nb} kept bases x {npm} permutations of the workload per step (numpy/OpenBLAS, chunksize 1e5)"
+    cores = cpu_workers()
+    sample = (f"first {nb} kept bases x {npm} permutations of the workload per step (numpy/OpenBLAS port, 1e5-row "
+              f"chunks on {cores} host threads)")
     line = {"impl": "reference", "metric": "base_x_permutation_fstats_per_sec", "value": value,
             "unit": "base*perm F-stats/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -397,9 +442,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
-    ap.add_argument("--cpu-bases", type=int, default=1_000_000, help="bounded CPU sample: kept bases per step")
-    ap.add_argument("--cpu-perms", type=int, default=30, help="bounded CPU sample: permutations per step")
+    ap.add_argument("--cpu-bases", type=int, default=1_600_000, help="bounded CPU sample: kept bases per step")
+    ap.add_argument("--cpu-perms", type=int, default=20, help="bounded CPU sample: permutations per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true", help="developer: skip the end-to-end pass (the line has no e2e key)")
     ap.add_argument("--e2e-input", default="rle", choices=["rle", "dense"],
                     help="host coverage format of the end-to-end pass: Rle columns (the reference's type) or dense")
     ap.add_argument("--e2e-sync-f", action="store_true",
@@ -526,19 +572,28 @@ def main():
         dist.barrier()
 
     # end to end through host buffers (pinned), same pass
-    host_cov = torch.empty((n, N), dtype=torch.int32, pin_memory=True)
-    host_cov.copy_(work["cov"])
-    host_np = host_cov.numpy()
-    if args.e2e_input == "rle":
-        step.set_rle_input(host_np)
-    step.host_pass(host_np)
-    torch.cuda.synchronize()
-    ke = max(2, min(args.steps, 5))
-    t0 = time.perf_counter()
-    for _ in range(ke):
-        h2d, d2h = step.host_pass(host_np)
-    torch.cuda.synchronize()
-    e2e_s = (time.perf_counter() - t0) / ke
+    h2d = d2h = 0
+    e2e_s = float("nan")
+    if not args.no_e2e:
+        host_cov = torch.empty((n, N), dtype=torch.int32, pin_memory=True)
+        host_cov.copy_(work["cov"])
+        host_np = host_cov.numpy()
+        if args.e2e_input == "rle":
+            step.set_rle_input(host_np)
+        step.host_pass(host_np)
+        torch.cuda.synchronize()
+        ke = max(2, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(ke):
+            h2d, d2h = step.host_pass(host_np)
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / ke
+        if os.environ.get("DFB_GAPS"):  # developer: per-launch trace of one end-to-end pass
+            print("[bench] end-to-end pass trace", file=sys.stderr)
+            eng.enable_timing(True)
+            step.host_pass(host_np)
+            eng.enable_timing(False)
+            print("[bench] end-to-end breakdown (ms):", step.last_breakdown, file=sys.stderr)
     if world > 1:
         t = torch.tensor([e2e_s], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -559,6 +614,8 @@ def main():
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
                     "last_step_breakdown_ms": {k: round(v, 3) for k, v in step.last_breakdown.items()}},
             "clocks": sampler.result()}
+    if args.no_e2e:
+        del line["e2e"]
     if world > 1:
         # every rank's own chromosome pass (different synthetic chromosomes: the slowest bounds the step)
         # and what the genome-wide pooling (two all-gathers + ranking) adds on top of it
@@ -625,9 +682,10 @@ def main():
             cpu_reference_pass(cov_s, pl_s, pf_s, work["mod"], work["mod0"], perm_s, cut)
             dt = time.perf_counter() - t0
             line["cpu_baseline"] = {"value": nb * (npm + 1) / dt, "unit": "base*perm F-stats/s",
-                                    "cores": os.cpu_count(), "kind": "port", "seconds": dt,
+                                    "cores": cpu_workers(), "kind": "port", "seconds": dt,
                                     "sample": f"first {nb} kept bases x {npm} permutations of the same workload, "
-                                              "numpy/OpenBLAS port of the reference's algorithm (chunksize 1e5)"}
+                                              "numpy/OpenBLAS port of the reference's algorithm (1e5-row chunks "
+                                              f"on {cpu_workers()} host threads)"}
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()

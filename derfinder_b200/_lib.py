@@ -80,6 +80,7 @@ SIGNATURES = {
     "dfb_regions_count_up": (C.c_int64, [C.c_void_p]),
     "dfb_regions_get": (C.c_int, [C.c_void_p, c_i32p, c_i32p, c_f64p, c_f64p, c_i32p, c_i32p, c_i32p, c_f64p]),
     "dfb_regions_view_means": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_f64p]),
+    "dfb_regions_view_means_host": (C.c_int, [C.c_void_p, C.c_void_p, c_f64p, C.c_int64, c_f64p]),
     "dfb_cluster_maker": (C.c_int64, [c_i32p, C.c_int64, C.c_int, C.c_int32, c_i64p, c_i64p, c_i64p, C.c_int64]),
     "dfb_perm_nulls": (C.c_int, [C.c_void_p, C.c_void_p, c_f64p, C.c_int, c_f64p, C.c_int, C.c_double, c_i32p,
                                  C.c_int64, C.c_double, C.c_double, C.c_int32, c_vpp]),

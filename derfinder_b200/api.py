@@ -156,6 +156,9 @@ class Coverage:
         self.N, self.n, self.chr_len, self.dtype = N.value, n.value, clen.value, dt.value
         self._npr = npr.value
         self.names = list(names) if names is not None else [f"V{i + 1}" for i in range(self.n)]
+        # mean vectors handed out by preprocessCoverage(): when calculatePvalues() gets these very objects
+        # back it uses the device copies; any other vector is uploaded and used as given
+        self._issued = {}
         engine._covs.add(self)
 
     def free(self):
@@ -320,6 +323,8 @@ def preprocessCoverage(coverageInfo, groupInfo=None, cutoff=5, colsubset=None, l
         filt = filterData(subdata, cutoff=cutoff, index=position, returnMean=True, engine=engine,
                           colnames=[names[c] for c in sub], **kwargs)
         cov, position = filt["coverage"], filt["position"]
+        means = filt["meanCoverage"]  # the re-filtered mean replaces a pre-existing one (:157-159)
+        cov._issued["mean"] = means
     else:
         cov = _upload_filtered(engine, coverage, position, names)
     if position is None:
@@ -336,8 +341,17 @@ def preprocessCoverage(coverageInfo, groupInfo=None, cutoff=5, colsubset=None, l
     engine.lib.dfb_chunk_lengths(cov.N, float(chunksize) if chunksize else 0.0, int(mc_cores), L.ptr(lens, C.c_int64),
                                  nchunk)
     groupMeans = {lev: cov.group_mean(i) for i, lev in enumerate(levels)} if levels else {}
+    for i, lev in enumerate(levels or ()):
+        cov._issued[("group", i)] = groupMeans[lev]
+    if means is None:  # Reduce("+", coverage) / length(coverage) (:191-193): computed on the device
+        means = cov.mean()
+        cov._issued["mean"] = means
+    else:
+        means = np.asarray(means, dtype=np.float64)
+        if len(means) != cov.N:
+            raise ValueError("length(coverageInfo$meanCoverage) does not match the number of filtered bases")
     return dict(coverageProcessed=cov, mclapplyIndex=[int(x) for x in lens], position=position,
-                meanCoverage=cov.mean() if means is None else np.asarray(means), groupMeans=groupMeans)
+                meanCoverage=means, groupMeans=groupMeans)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -577,14 +591,24 @@ def calculatePvalues(coveragePrep, models, fstats, nPermute=1, seeds=None, chr=N
     try:
         regs = _regions_dict(engine, rh, False)
         R = len(regs["start"])
-        mc = np.empty(R)
-        L.check(lib.dfb_regions_view_means(engine.h, rh, cov.h, -1, L.ptr(mc, C.c_double)))
-        regs["meanCoverage"] = mc  # :254-255
+
+        def view_means(vec, key, which):
+            # mean(Views(vec, indexIR)) (:253-262) of the vector the caller passed: the device copy when
+            # it is the object preprocessCoverage() returned for this handle, else the vector as given
+            out = np.empty(R)
+            if vec is cov._issued.get(key):
+                L.check(lib.dfb_regions_view_means(engine.h, rh, cov.h, which, L.ptr(out, C.c_double)))
+            else:
+                v = L.f64(vec)
+                L.check(lib.dfb_regions_view_means_host(engine.h, rh, L.ptr(v, C.c_double), len(v),
+                                                        L.ptr(out, C.c_double)))
+            return out
+
+        regs["meanCoverage"] = view_means(coveragePrep["meanCoverage"], "mean", -1)  # :254-255
         names = list(coveragePrep["groupMeans"].keys())
         gm = {}
         for gi, g in enumerate(names):  # :258-262
-            v = np.empty(R)
-            L.check(lib.dfb_regions_view_means(engine.h, rh, cov.h, gi, L.ptr(v, C.c_double)))
+            v = view_means(coveragePrep["groupMeans"][g], ("group", gi), gi)
             gm[g] = v
             regs["mean" + str(g)] = v
         for g in names[1:]:  # :265-283 (R glue computes this ratio/log2 on the R vectors)

@@ -104,6 +104,8 @@ struct dfb_ctx {
     int opt_chunk_perms = 0;     // fused kernel: permutations per MMA chunk (0 = auto)
     int opt_tmem_stages = 0;     // fused kernel: accumulator stages (0 = auto)
     int opt_fused = 1;           // fused screen+refine kernel (0: two-kernel screen path)
+    int opt_mma_warps = 0;       // null2 kernel: MMA-issuing warps (0 = auto)
+    int opt_null2 = 1;           // second-generation null scan (fstat_tc2.cu); 0: the first fused kernel
     int opt_k2_waves = 16;       // fused kernel: CTAs per resident slot (1 = persistent); see launch_fused
     double opt_null_cap_mb = 0;  // 0 = auto
     int opt_perm_batch = 0;      // 0 = auto

@@ -1076,6 +1076,7 @@ int dfb_preprocess(dfb_ctx* ctx, dfb_cov* c, double scalefac, const int32_t* gro
     }
     c->has_mean = true;
     c->has_f = false;
+    c->a16_center = -1;  // the log2 matrix changed: the null scan's fp16 operand is stale
     return DFB_OK;
 }
 

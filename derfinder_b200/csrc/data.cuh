@@ -40,6 +40,12 @@ struct dfb_cov {
     bool has_f = false;
     double scalefac = 32;
     PositionIndex pos;
+    // operand cache of the K2 null scan (fstat_tc2.cu): centred log2 coverage as fp16 rows [a16_rows][a16_ka],
+    // |yc|^2 and the row mean in FP64; valid while `y` is unchanged (a16_center: -1 = stale)
+    dfb::DevBuf<uint16_t> a16;
+    dfb::DevBuf<double> a16_yy, a16_m;
+    int a16_center = -1, a16_ka = 0;
+    int64_t a16_rows = 0;
 };
 
 struct dfb_regions {
@@ -123,6 +129,13 @@ int fstat_perm_batch_screen(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& 
 bool fused_supported(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, double lo, double hi,
                      double adjust_f);
 int fstat_perm_batch_fused(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, const double* q_dev /*[n][p]*/,
+                           double adjust_f, const int32_t* idx_dev, int64_t B, double hi, size_t capacity_hint,
+                           PermBatch* out, bool defer_check = false);
+
+// ---- fstat_tc2.cu: second-generation null scan (TMA-fed fp16 screen, permutation operand resident in smem)
+bool null2_supported(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, double lo, double hi,
+                     double adjust_f);
+int fstat_perm_batch_null2(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, const double* q_dev /*[n][p]*/,
                            double adjust_f, const int32_t* idx_dev, int64_t B, double hi, size_t capacity_hint,
                            PermBatch* out, bool defer_check = false);
 

@@ -62,7 +62,8 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
 
     // tensor-core screen + exact refinement when the cutoff is one-sided positive (the normal case);
     // otherwise the dense FP64 kernel.  Results are identical either way.
-    const bool use_fused = fused_supported(ctx, cov, mb, lo, hi, adjust_f);
+    const bool use_null2 = null2_supported(ctx, cov, mb, lo, hi, adjust_f);
+    const bool use_fused = use_null2 || fused_supported(ctx, cov, mb, lo, hi, adjust_f);
     const bool use_screen = use_fused || screen_supported(ctx, cov, mb, lo, hi, adjust_f);
     DevBuf<double> q_d;
     if (use_screen) {
@@ -99,7 +100,9 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
                                   : (size_t)std::max(dense * density, 4.0e6);
         if ((double)hint * 8.0 > budget * 0.5) hint = (size_t)(budget * 0.5 / 8.0);
         PermBatch pbatch;
-        int rc = use_fused  ? fstat_perm_batch_fused(ctx, cov, mb, q_d.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, hi,
+        int rc = use_null2  ? fstat_perm_batch_null2(ctx, cov, mb, q_d.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, hi,
+                                                     hint, &pbatch, true)
+                 : use_fused  ? fstat_perm_batch_fused(ctx, cov, mb, q_d.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, hi,
                                                      hint, &pbatch, true)
                  : use_screen ? fstat_perm_batch_screen(ctx, cov, mb, q_d.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, hi,
                                                       hint, &pbatch, nullptr)
@@ -123,8 +126,10 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
             // deferred overflow check of the fused path fired: re-run K2 with the exact capacity
             const size_t need = (size_t)*pbatch.used_host;
             pbatch = PermBatch();
-            rc = fstat_perm_batch_fused(ctx, cov, mb, q_d.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, hi, need, &pbatch,
-                                        false);
+            rc = use_null2 ? fstat_perm_batch_null2(ctx, cov, mb, q_d.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, hi, need,
+                                                    &pbatch, false)
+                           : fstat_perm_batch_fused(ctx, cov, mb, q_d.p, adjust_f, idx_d.p + (size_t)b_lo * n, nb, hi, need,
+                                                    &pbatch, false);
             if (rc == DFB_ENOMEM && nb > 1) {
                 const int64_t mid = b_lo + nb / 2;
                 work.push_back({mid, b_hi});
@@ -695,8 +700,22 @@ static int pooled_null_areas(dfb_ctx* ctx, dfb_nulls* nl, int merge_area, const 
 
 int dfb_pool_local_dev(dfb_ctx* ctx, const dfb_regions* r, dfb_nulls* nl, int64_t B, int merge_area, int64_t rcap,
                        double* record_dev) {
-    DFB_REQUIRE(ctx && r && nl && record_dev, "dfb_pool_local_dev: NULL argument");
+    DFB_REQUIRE(ctx && record_dev, "dfb_pool_local_dev: NULL argument");
     DFB_REQUIRE(B >= 1 && rcap >= 1, "dfb_pool_local_dev: nPermute and capacity must be >= 1");
+    if (!r || !nl) {
+        // a chromosome without observed regions: calculatePvalues() returned list(regions = NULL, nullStats =
+        // NULL, ...) before its permutation loop (:245-251), so it adds nothing to the genome-wide pool
+        DFB_REQUIRE(!r && !nl, "dfb_pool_local_dev: regions and nulls must both be NULL for an empty chromosome");
+        DevBuf<double> none;
+        DFB_TRY(none.alloc(ctx, 1));
+        {
+            KTimer t(ctx, DFB_K_PVAL);
+            pool_record_kernel<<<grid_for(rcap, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(none.p, 0, 0, rcap, B,
+                                                                                          record_dev);
+        }
+        DFB_CUDA(cudaGetLastError());
+        return perm_max_device(ctx, nullptr, nullptr, 0, B, -1.0, record_dev + 2);
+    }
     if (r->R > 0 && !r->d_area_desc.p) {
         set_error("dfb_pool_local_dev: this result was not produced by dfb_calculate_pvalues");
         return DFB_ESTATE;
@@ -714,7 +733,7 @@ int dfb_pool_local_dev(dfb_ctx* ctx, const dfb_regions* r, dfb_nulls* nl, int64_
 
 int dfb_pool_hist_dev(dfb_ctx* ctx, dfb_nulls* nl, int merge_area, const double* records_dev, int world, int64_t B,
                       int64_t rcap, double* merged_dev, int32_t* src_dev, unsigned long long* hist_dev) {
-    DFB_REQUIRE(ctx && nl && records_dev && merged_dev && src_dev && hist_dev, "dfb_pool_hist_dev: NULL argument");
+    DFB_REQUIRE(ctx && records_dev && merged_dev && src_dev && hist_dev, "dfb_pool_hist_dev: NULL argument");
     DFB_REQUIRE(world >= 1 && B >= 1 && rcap >= 1, "dfb_pool_hist_dev: world, nPermute and capacity must be >= 1");
     const int64_t n = (int64_t)world * rcap;
     DFB_REQUIRE(n < INT32_MAX, "dfb_pool_hist_dev: %lld pooled regions exceed the 32-bit index", (long long)n);
@@ -726,8 +745,8 @@ int dfb_pool_hist_dev(dfb_ctx* ctx, dfb_nulls* nl, int merge_area, const double*
     DFB_CUDA(cudaGetLastError());
     DFB_CUDA(cudaMemsetAsync(hist_dev, 0, (size_t)(n + 1) * sizeof(unsigned long long), ctx->stream));
     const double* areas = nullptr;
-    DFB_TRY(pooled_null_areas(ctx, nl, merge_area, &areas));
-    if (nl->count > 0) {
+    if (nl) DFB_TRY(pooled_null_areas(ctx, nl, merge_area, &areas));
+    if (nl && nl->count > 0) {
         KTimer t(ctx, DFB_K_PVAL);
         null_hist64_kernel<<<grid_for(nl->count, 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(areas, nl->count,
                                                                                              merged_dev, n, hist_dev);
@@ -739,9 +758,10 @@ int dfb_pool_hist_dev(dfb_ctx* ctx, dfb_nulls* nl, int merge_area, const double*
 int dfb_pool_rank_dev(dfb_ctx* ctx, const dfb_regions* r, const double* records_dev, int world, int rank, int64_t B,
                       int64_t rcap, const double* merged_dev, const int32_t* src_dev,
                       const unsigned long long* hist_dev, double cutoff_used, double* p_dev, double* fwer_dev) {
-    DFB_REQUIRE(ctx && r && records_dev && merged_dev && src_dev && hist_dev, "dfb_pool_rank_dev: NULL argument");
+    DFB_REQUIRE(ctx && records_dev && merged_dev && src_dev && hist_dev, "dfb_pool_rank_dev: NULL argument");
     DFB_REQUIRE(world >= 1 && rank >= 0 && rank < world && B >= 1 && rcap >= 1,
                 "dfb_pool_rank_dev: bad world / rank / capacity");
+    if (!r) return DFB_OK;  // empty chromosome: nothing to rank
     const int64_t R = std::min<int64_t>(r->R, rcap);  // R > rcap: the caller repeats with a larger capacity
     if (R == 0) return DFB_OK;
     DFB_REQUIRE(p_dev && fwer_dev, "dfb_pool_rank_dev: NULL output");
@@ -930,7 +950,8 @@ int dfb_debug_screen(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const
     DFB_TRY(idx_d.alloc(ctx, (size_t)B * n));
     DFB_TRY(h2d(ctx, idx_d.p, perm_idx, (size_t)B * n * sizeof(int32_t)));
     PermBatch dense, scr;
-    const size_t hint = (size_t)B * (size_t)cov->N;
+    // value capacity: everything for small problems, else 2^27 values (an overflow re-runs with the exact need)
+    const size_t hint = std::min<size_t>((size_t)B * (size_t)cov->N, (size_t)1 << 27);
     DFB_TRY(fstat_perm_batch(ctx, cov, mb, qd.p, adjust_f, idx_d.p, B, -cutoff, cutoff, false, hint, &dense));
     int64_t ncand = 0;
     DFB_TRY(fstat_perm_batch_screen(ctx, cov, mb, q_d.p, adjust_f, idx_d.p, B, cutoff, hint, &scr, &ncand));
@@ -942,6 +963,13 @@ int dfb_debug_screen(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const
         int64_t diff2 = 0;
         DFB_TRY(mask_diff(ctx, dense.mask.p, fz.mask.p, dense.rows * dense.W, &diff2));
         diff += diff2;
+    }
+    if (null2_supported(ctx, cov, mb, -cutoff, cutoff, adjust_f)) {  // and the second-generation scan
+        PermBatch nz;
+        DFB_TRY(fstat_perm_batch_null2(ctx, cov, mb, q_d.p, adjust_f, idx_d.p, B, cutoff, hint, &nz));
+        int64_t diff3 = 0;
+        DFB_TRY(mask_diff(ctx, dense.mask.p, nz.mask.p, dense.rows * dense.W, &diff3));
+        diff += diff3;
     }
     if (n_exact_dense) *n_exact_dense = dense.nvals;
     if (n_exact_screen) *n_exact_screen = scr.nvals;

@@ -941,6 +941,32 @@ int dfb_regions_view_means(dfb_ctx* ctx, const dfb_regions* r, const dfb_cov* co
     return DFB_OK;
 }
 
+// The same per-region means for a caller-supplied host vector (coveragePrep$meanCoverage or one of
+// coveragePrep$groupMeans when the caller did not take them from this handle, R/calculatePvalues.R:222-262).
+int dfb_regions_view_means_host(dfb_ctx* ctx, const dfb_regions* r, const double* v, int64_t N, double* out) {
+    DFB_REQUIRE(ctx && r && v && out, "dfb_regions_view_means_host: NULL argument");
+    const int64_t R = r->R;
+    if (R == 0) return DFB_OK;
+    for (int64_t k = 0; k < R; ++k)
+        DFB_REQUIRE(r->index_end.empty() || (int64_t)r->index_end[(size_t)k] <= N,
+                    "region %lld ends at index %d beyond the %lld values given", (long long)k, r->index_end[(size_t)k],
+                    (long long)N);
+    DevBuf<double> vd, o;
+    DFB_TRY(vd.alloc(ctx, (size_t)std::max<int64_t>(N, 1)));
+    DFB_TRY(h2d_big(ctx, vd.p, v, (size_t)N * sizeof(double)));
+    DFB_TRY(o.alloc(ctx, (size_t)R));
+    {
+        KTimer t(ctx, DFB_K_REGIONS);
+        view_means_kernel<<<(unsigned)ceil_div(R, 128), 128, 0, ctx->stream>>>(vd.p, r->d_is.p, r->d_ie.p, R, o.p);
+    }
+    DFB_CUDA(cudaGetLastError());
+    std::vector<double> tmp((size_t)R);
+    DFB_TRY(d2h(ctx, tmp.data(), o.p, (size_t)R * sizeof(double)));
+    const bool ordered = !r->order.empty();
+    for (int64_t k = 0; k < R; ++k) out[k] = tmp[ordered ? (size_t)r->order[(size_t)k] : (size_t)k];
+    return DFB_OK;
+}
+
 // .clusterMakerRle on run lengths (position metadata, O(#runs)); the device path uses
 // segment_start_kernel / cluster_side for the same merge rule.
 int64_t dfb_cluster_maker(const int32_t* pos_len, int64_t pos_nruns, int pos_first, int32_t max_gap, int64_t* counts,

@@ -109,7 +109,9 @@ def genomewide_pvalues(engine, regions_handle, nulls_handle, B, cutoff_used, tor
     dfb_pool_rank_dev, then ONE host read of the gathered counts; see the module docstring."""
     from . import _lib as L
     lib = engine.lib
-    R = int(lib.dfb_regions_count(regions_handle))
+    # a chromosome without observed regions has no handles (calculatePvalues returned NULLs, R/calculatePvalues.R:
+    # 245-251): it takes part in the collectives with an empty record
+    R = int(lib.dfb_regions_count(regions_handle)) if regions_handle else 0
     marks = []
 
     def mark(name):

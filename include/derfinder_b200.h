@@ -214,6 +214,11 @@ int dfb_regions_get(const dfb_regions* r, int32_t* start, int32_t* end, double* 
  * 253-262 (meanCoverage / group means per region). which: -1 = cov meanCoverage, g>=0 = group g */
 int dfb_regions_view_means(dfb_ctx* ctx, const dfb_regions* r, const dfb_cov* cov, int which,
                            double* out);
+/* The same for a caller-supplied host vector v[N] (a coveragePrep$meanCoverage / groupMeans entry
+ * that did not come from this handle; the reference uses whatever vector it is given,
+ * R/calculatePvalues.R:222-224, 253-262). */
+int dfb_regions_view_means_host(dfb_ctx* ctx, const dfb_regions* r, const double* v, int64_t N,
+                                double* out);
 
 /* .clusterMakerRle() -- R/findRegions.R:445-475 on a logical Rle given as run lengths.
  * ranges = 0: fills ids[k] = k+1 and counts[k] (the integer Rle); ranges = 1: fills
@@ -259,7 +264,9 @@ int dfb_nulls_copy_dev(const dfb_nulls* nl, double* area_dev, int32_t* perm_dev)
  *                       pooled regions they do not exceed.        -> all-reduce(sum) hist_dev
  *   dfb_pool_rank_dev   pooled p-values ((2 * #{null > area} + 1) / (2 * sum(M) + 1), i.e. .calcPval
  *                       on the duplicated pool) and FWER (.calculateFWER, empty permutation ->
- *                       cutoff_used) of THIS rank's regions, [R] on the device in up-then-dn order. */
+ *                       cutoff_used) of THIS rank's regions, [R] on the device in up-then-dn order.
+ * A chromosome without observed regions (calculatePvalues returned NULLs, :245-251) passes r = nl = NULL
+ * to all three calls: it contributes an empty record and no nulls. */
 int dfb_pool_local_dev(dfb_ctx* ctx, const dfb_regions* r, dfb_nulls* nl, int64_t B, int merge_area,
                        int64_t rcap, double* record_dev);
 int dfb_pool_hist_dev(dfb_ctx* ctx, dfb_nulls* nl, int merge_area,

@@ -1,0 +1,311 @@
+"""GPU parity at the parameters of BASELINE.json configs[2] / configs[3] (60 and 100 samples, p = 6,
+p0 = 5, 1000 permutations, stringent theoretical cutoffs), on slices the oracle finishes in seconds,
+plus the multi-rank pooling kernels (several ranks' records on one device) against .calcPval /
+.calculateFWER of the oracle on the concatenated nulls (R/mergeResults.R:216-235, 300-307, 380-386).
+
+Bars as in test_gpu_parity.py: regions, widths, permutation ids and p-value counts bit-exact; F
+statistics bit-exact against the C oracle of the same arithmetic and <= 1e-6 relative against the
+reference's projector definition.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+from oracle import c_oracle  # noqa: E402
+from oracle import derfinder_oracle as O  # noqa: E402
+from test_gpu_parity import (F_RTOL, assert_pipeline_equal, debug_screen, oracle_idx_fn, random_perms,  # noqa: E402
+                             run_both, synth)
+
+
+@pytest.fixture(scope="module")
+def dfb():
+    import derfinder_b200 as m
+    return m
+
+
+@pytest.fixture(scope="module")
+def eng(dfb):
+    e = dfb.Engine(0)
+    yield e
+    e.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# C3 / C4 parameters on slices: n = 60 / 100, p = 6, p0 = 5, B = 1000
+
+
+@pytest.mark.parametrize("n,N", [(60, 12000), (100, 6000)])
+def test_c3_c4_parameters_vs_oracle(dfb, eng, n, N):
+    from derfinder_b200.rrng import permutation_indices
+    rng = np.random.default_rng(3000 + n)
+    cov, position, group, models = synth(rng, N, n, p_extra=3, seg=[N // 3, 77, N - N // 3 - 77])
+    assert models["mod"].shape[1] == 6 and models["mod0"].shape[1] == 5
+    B = 1000
+    perm = permutation_indices(range(1, B + 1), n, "Rejection")  # the relabellings R would draw for seeds 1:B
+    for alpha, need_nulls in ((1e-6, False), (1e-3, True)):
+        cut = dfb.calcFstatCutoff("theoretical", alpha, models=models)  # qf(alpha, 1, n - 6, lower.tail = FALSE)
+        res, ores = run_both(dfb, eng, cov, position, group, models, perm, cut, cgap=3000)
+        assert ores["regions"] is not None
+        if need_nulls:
+            assert len(ores["nullStats"]) > 100
+        assert_pipeline_equal(res, ores)
+        assert eng.kernel_time(3)[1] > 0  # the tcgen05 path ran
+
+
+@pytest.mark.parametrize("n,extra,N,B", [(60, 3, 5000, 60), (100, 3, 3000, 40), (24, 2, 8000, 50)])
+def test_permuted_nulls_vs_projector_definition(dfb, eng, n, extra, N, B):
+    """Independent of the engine's own basis: null statistics of permuted models computed with the
+    reference's residual-projector definition (tests/testthat/test_Fstats.R:52-63 on mod[idx, ],
+    mod0[idx, ], R/calculatePvalues.R:321-329) must give the same null regions, and region means
+    within the F-statistic tolerance."""
+    rng = np.random.default_rng(4100 + n)
+    cov, position, group, models = synth(rng, N, n, p_extra=extra)
+    perm = random_perms(rng, B, n)
+    cut = dfb.calcFstatCutoff("theoretical", 0.01, models=models)
+    prep = dfb.preprocessCoverage(dict(coverage=cov, position=position), groupInfo=group, engine=eng)
+    F = dfb.calculateStats(prep, models, engine=eng)
+    res = dfb.calculatePvalues(prep, models, F, permIndex=perm, cutoff=cut, engine=eng)
+    oprep = O.preprocess_coverage(cov, position, groupInfo=group)
+    Y = oprep["coverageProcessed"]
+    # per-base check first: a base whose projector F is within tolerance of the cutoff may legitimately fall
+    # on either side; the region comparison below is only meaningful when no base is that close
+    fn = oracle_idx_fn(eng, models["mod"], models["mod0"])
+    close = 0
+    for b in range(B):
+        fp = c_oracle.fstats_projector(Y, models["mod"][perm[b]], models["mod0"][perm[b]])
+        fe = fn(Y, perm[b])
+        ok = np.isfinite(fp) & (fp > 1e-3)
+        assert np.max(np.abs(fe[ok] - fp[ok]) / fp[ok]) < F_RTOL
+        close += int(np.sum(np.abs(fp[ok] - cut) <= 2 * F_RTOL * cut))
+    ores = O.calculate_pvalues(oprep, models["mod"], models["mod0"], F, perm, cut, fstat_fn=c_oracle.fstats_projector)
+    assert len(ores["nullStats"]) > 0
+    if close == 0:
+        assert np.array_equal(res["nullWidths"], ores["nullWidths"])
+        assert np.array_equal(res["nullPermutation"], ores["nullPermutation"])
+        assert np.max(np.abs(res["nullStats"] - ores["nullStats"]) / ores["nullStats"]) < F_RTOL
+        assert np.max(np.abs(res["nullAreas"] - ores["nullAreas"]) / ores["nullAreas"]) < F_RTOL
+
+
+def _device_workload(dfb, name, seed):
+    import torch
+    import bench
+    from derfinder_b200.rrng import permutation_indices
+    cfg = bench.WORKLOADS[name]
+    device = torch.device("cuda", 0)
+    work = bench.make_workload(cfg, seed, torch=torch, device=device)
+    perm = permutation_indices(range(1, cfg["B"] + 1), cfg["n"], "Rejection")
+    return cfg, work, perm, torch, bench
+
+
+@pytest.mark.parametrize("name", ["c3s", "c4s"])
+def test_screen_exact_at_c3_c4_size(dfb, name):
+    """dfb_debug_screen on the scaled C3 / C4 workloads (N = 2.5 M x 60 samples, N = 1 M x 100 samples,
+    1000 permutations): the dense FP64 kernel and the tcgen05 screen + exact refinement (both the
+    two-kernel and the fused form) must set identical mask bits -- the error bound of the screen is
+    validated at the sample counts the headline configs use."""
+    from derfinder_b200 import _lib as L
+    cfg, work, perm, torch, bench = _device_workload(dfb, name, 20140923 + 3)
+    e2 = dfb.Engine(0, stream=torch.cuda.current_stream().cuda_stream)
+    try:
+        pl = np.ascontiguousarray(work["pos_len"], dtype=np.int32)
+        h = C.c_void_p()
+        L.check(e2.lib.dfb_cov_view_dense_dev(e2.h, cfg["n"], cfg["N"], L.DFB_I32, C.c_void_p(work["cov"].data_ptr()),
+                                              cfg["N"], L.ptr(pl, C.c_int32), len(pl), work["pos_first"], C.byref(h)))
+        L.check(e2.lib.dfb_preprocess(e2.h, h, 32.0, None, 0))
+        mod, mod0 = work["mod"], work["mod0"]
+        B = 200  # the dense FP64 reference scan is the expensive side
+        for alpha in (1e-6, 1e-3):
+            cut = bench.theoretical_cutoff(alpha, mod, mod0)
+            out = [C.c_int64() for _ in range(4)]
+            L.check(e2.lib.dfb_debug_screen(e2.h, h, mod.ctypes.data_as(L.c_f64p), mod.shape[1],
+                                            mod0.ctypes.data_as(L.c_f64p), mod0.shape[1], 0.0,
+                                            L.ptr(np.ascontiguousarray(perm[:B]), C.c_int32), B, float(cut),
+                                            *[C.byref(o) for o in out]))
+            dense, screen, cand, diff = (o.value for o in out)
+            assert diff == 0, (name, alpha, diff)
+            assert dense == screen and cand >= dense
+            if alpha == 1e-3:
+                assert dense > 1000
+        e2.lib.dfb_cov_free(h)
+    finally:
+        e2.close()
+
+
+def test_c2_slice_vs_oracle(dfb, eng):
+    """A 1e5-base slice of the configs[1] workload (12 samples, 100 permutations, qf(0.05, 1, 9)) end to
+    end against the oracle."""
+    import bench
+    from derfinder_b200.rrng import permutation_indices
+    cfg = dict(bench.WORKLOADS["c2"], chr_len=1_000_000, N=100_000)
+    work = bench.make_workload(cfg, 20140923 + 2)
+    cov = np.ascontiguousarray(work["cov"].T)
+    pl = work["pos_len"].astype(np.int64)
+    position = ((np.arange(len(pl)) % 2 == 0) == bool(work["pos_first"]), pl)
+    models = dict(mod=np.array(work["mod"]), mod0=np.array(work["mod0"]))
+    perm = permutation_indices(range(1, cfg["B"] + 1), cfg["n"], "Rejection")
+    cut = bench.theoretical_cutoff(cfg["alpha"], work["mod"], work["mod0"])
+    group = np.where(work["group"] == 0, "a", "b")
+    res, ores = run_both(dfb, eng, cov, position, group, models, perm, cut, cgap=3000)
+    assert len(ores["regions"]["start"]) > 100 and len(ores["nullStats"]) > 10000
+    assert_pipeline_equal(res, ores)
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-rank pooling kernels with world > 1, all "ranks" on one device
+
+
+def _chromosome_result(dfb, eng, rng, N, n, models, perm, cut):
+    """One rank's chromosome through the C ABI, handles kept: (cov, regions, nulls) or (cov, None, None)."""
+    from derfinder_b200 import _lib as L
+    cov, position, group, _ = synth(rng, N, n, p_extra=models["mod"].shape[1] - 3)
+    mat = np.ascontiguousarray(cov.T, dtype=np.int32)
+    pl = np.ascontiguousarray(position[1], dtype=np.int32)
+    h = C.c_void_p()
+    L.check(eng.lib.dfb_cov_from_dense(eng.h, n, N, L.DFB_I32, mat.ctypes.data_as(C.c_void_p), N, L.ptr(pl, C.c_int32),
+                                       len(pl), int(position[0][0]), C.byref(h)))
+    L.check(eng.lib.dfb_preprocess(eng.h, h, 32.0, None, 0))
+    mod, mod0 = np.asfortranarray(models["mod"]), np.asfortranarray(models["mod0"])
+    L.check(eng.lib.dfb_fstats(eng.h, h, mod.ctypes.data_as(L.c_f64p), mod.shape[1], mod0.ctypes.data_as(L.c_f64p),
+                               mod0.shape[1], 0.0, None))
+    rh, nh = C.c_void_p(), C.c_void_p()
+    rc = L.check(eng.lib.dfb_calculate_pvalues(eng.h, h, None, mod.ctypes.data_as(L.c_f64p), mod.shape[1],
+                                               mod0.ctypes.data_as(L.c_f64p), mod0.shape[1], 0.0,
+                                               L.ptr(perm, C.c_int32), perm.shape[0], -cut, cut, 0, 300, C.byref(rh),
+                                               C.byref(nh), None))
+    if rc == L.DFB_ENOREGIONS:
+        return h, None, None
+    return h, rh, nh
+
+
+def _fetch(eng, rh, nh):
+    from derfinder_b200 import _lib as L
+    lib = eng.lib
+    R, M = int(lib.dfb_regions_count(rh)), int(lib.dfb_nulls_count(nh))
+    area, order = np.empty(R), np.empty(R, dtype=np.int32)
+    L.check(lib.dfb_regions_get(rh, None, None, None, L.ptr(area, C.c_double), None, None, None, None))
+    L.check(lib.dfb_regions_get_order(rh, L.ptr(order, C.c_int32)))
+    ns, na = np.empty(M), np.empty(M)
+    nw, npm = np.empty(M, dtype=np.int32), np.empty(M, dtype=np.int32)
+    if M:
+        L.check(lib.dfb_nulls_get(nh, 0, L.ptr(ns, C.c_double), L.ptr(nw, C.c_int32), L.ptr(na, C.c_double),
+                                  L.ptr(npm, C.c_int32)))
+    return dict(R=R, M=M, area=area, order=order, nstat=ns, narea=na, nwidth=nw, nperm=npm)
+
+
+@pytest.mark.parametrize("world,sizes,empty_rank", [(2, [9000, 4000], None), (3, [5000, 12000, 3000], 1),
+                                                    (8, [3000, 7000, 2500, 4000, 6000, 2000, 5000, 3500], 5)])
+@pytest.mark.parametrize("merge_area", [False, True])
+def test_pool_kernels_world_gt_1(dfb, eng, world, sizes, empty_rank, merge_area):
+    import torch
+    from derfinder_b200 import _lib as L
+    rng = np.random.default_rng(500 + world)
+    n, B = 14, 24
+    _, _, _, models = synth(rng, 2000, n, p_extra=1)
+    perm = random_perms(rng, B, n)
+    perm[3] = perm[2]  # a repeated relabelling: identical null areas on purpose (ties across the pool)
+    cut = dfb.calcFstatCutoff("theoretical", 0.05, models=models)
+    ranks = []
+    for w in range(world):
+        this_cut = 1e12 if w == empty_rank else cut  # nothing passes on that chromosome: regions = NULL
+        ranks.append(_chromosome_result(dfb, eng, rng, sizes[w], n, models, perm, this_cut))
+    try:
+        info = [None if rh is None else _fetch(eng, rh, nh) for _, rh, nh in ranks]
+        assert sum(i is not None for i in info) >= 2
+        if empty_rank is not None:
+            assert info[empty_rank] is None
+        dev = torch.device("cuda", 0)
+        lib = eng.lib
+        ma = 1 if merge_area else 0
+        key = (lambda i: np.abs(i["nstat"]) * i["nwidth"]) if merge_area else (lambda i: i["narea"])
+        pool_area = np.concatenate([key(i) for i in info if i is not None])
+        pool_perm = np.concatenate([i["nperm"] for i in info if i is not None])
+        maxR = max(i["R"] for i in info if i is not None)
+        for rcap in (maxR + 17, maxR):
+            records = torch.empty((world, 2 + B + rcap), device=dev, dtype=torch.float64)
+            for w, (_, rh, nh) in enumerate(ranks):
+                L.check(lib.dfb_pool_local_dev(eng.h, rh, nh, B, ma, rcap, C.c_void_p(records[w].data_ptr())))
+            eng.sync()
+            head = records[:, :2].cpu().numpy()
+            assert list(head[:, 0]) == [0 if i is None else i["R"] for i in info]
+            assert list(head[:, 1]) == [0 if i is None else i["M"] for i in info]
+            merged = torch.empty(world * rcap, device=dev, dtype=torch.float64)
+            src = torch.empty(world * rcap, device=dev, dtype=torch.int32)
+            total_hist = torch.zeros(world * rcap + 1, device=dev, dtype=torch.int64)
+            for w, (_, rh, nh) in enumerate(ranks):  # every rank's histogram, then their sum (the all-reduce)
+                hist = torch.empty(world * rcap + 1, device=dev, dtype=torch.int64)
+                L.check(lib.dfb_pool_hist_dev(eng.h, nh, ma, C.c_void_p(records.data_ptr()), world, B, rcap,
+                                              C.c_void_p(merged.data_ptr()), C.c_void_p(src.data_ptr()),
+                                              C.c_void_p(hist.data_ptr())))
+                eng.sync()
+                total_hist += hist
+            torch.cuda.synchronize()
+            assert int(total_hist.sum().item()) == len(pool_area)
+            for w, (_, rh, nh) in enumerate(ranks):
+                if info[w] is None:
+                    L.check(lib.dfb_pool_rank_dev(eng.h, None, C.c_void_p(records.data_ptr()), world, w, B, rcap,
+                                                  C.c_void_p(merged.data_ptr()), C.c_void_p(src.data_ptr()),
+                                                  C.c_void_p(total_hist.data_ptr()), cut, None, None))
+                    continue
+                R = info[w]["R"]
+                p_dev = torch.full((R,), -1.0, device=dev, dtype=torch.float64)
+                f_dev = torch.full((R,), -1.0, device=dev, dtype=torch.float64)
+                L.check(lib.dfb_pool_rank_dev(eng.h, rh, C.c_void_p(records.data_ptr()), world, w, B, rcap,
+                                              C.c_void_p(merged.data_ptr()), C.c_void_p(src.data_ptr()),
+                                              C.c_void_p(total_hist.data_ptr()), cut, C.c_void_p(p_dev.data_ptr()),
+                                              C.c_void_p(f_dev.data_ptr())))
+                eng.sync()
+                order = info[w]["order"]
+                want_p = O.calc_pval(info[w]["area"], np.repeat(pool_area, 2))  # every null is stored twice
+                want_f = O.calculate_fwer(cut, pool_area, pool_perm, B, info[w]["area"])
+                assert np.array_equal(p_dev.cpu().numpy()[order], want_p), (world, w, rcap)
+                assert np.array_equal(f_dev.cpu().numpy()[order], want_f), (world, w, rcap)
+        # a capacity below some rank's region count: the record still reports the true R (the host logic
+        # of pool.genomewide_pvalues repeats the exchange when it sees R > rcap)
+        small = max(1, maxR // 2)
+        rec = torch.empty(2 + B + small, device=dev, dtype=torch.float64)
+        big = max(range(world), key=lambda w: -1 if info[w] is None else info[w]["R"])
+        L.check(lib.dfb_pool_local_dev(eng.h, ranks[big][1], ranks[big][2], B, ma, small, C.c_void_p(rec.data_ptr())))
+        eng.sync()
+        assert int(rec[0].item()) == maxR > small
+    finally:
+        for h, rh, nh in ranks:
+            if rh is not None:
+                eng.lib.dfb_regions_free(rh)
+                eng.lib.dfb_nulls_free(nh)
+            eng.lib.dfb_cov_free(h)
+
+
+def test_preprocess_colsubset_refreshes_mean(dfb, eng, golden):
+    """preprocessCoverage(colsubset = ...) replaces a pre-existing meanCoverage with the re-filtered
+    mean (R/preprocessCoverage.R:145-160); calculatePvalues uses the meanCoverage / groupMeans vectors it
+    is handed (R/calculatePvalues.R:222-262)."""
+    info = dict(coverage=golden.cov, position=golden.position,
+                meanCoverage=golden.cov.astype(np.float64).mean(axis=1))  # stale: all 31 samples
+    sub = [1, 2, 3, 4, 5, 6]
+    grp = np.array(["a", "a", "a", "b", "b", "b"])
+    ps = dfb.preprocessCoverage(info, groupInfo=grp, cutoff=1, colsubset=sub, chunksize=1e3, engine=eng)
+    cols = [O.rle_encode(golden.cov[:, s - 1]) for s in sub]
+    ds = O.filter_data(cols, 1, golden.position, returnMean=True)
+    assert len(ps["meanCoverage"]) == ds.coverage.shape[0] < golden.cov.shape[0]
+    assert np.array_equal(ps["meanCoverage"], ds.meanCoverage)
+    # a caller-supplied mean vector is the one summarised per region
+    rng = np.random.default_rng(12)
+    cov, position, group, models = synth(rng, 6000, 10)
+    prep = dfb.preprocessCoverage(dict(coverage=cov, position=position), groupInfo=group, engine=eng)
+    F = dfb.calculateStats(prep, models, engine=eng)
+    perm = random_perms(rng, 4, 10)
+    base = dfb.calculatePvalues(prep, models, F, permIndex=perm, cutoff=2.0, engine=eng)
+    mine = dict(prep)
+    mine["meanCoverage"] = rng.uniform(0, 50, size=len(F))
+    mine["groupMeans"] = {k: v * 2.0 for k, v in prep["groupMeans"].items()}
+    got = dfb.calculatePvalues(mine, models, F, permIndex=perm, cutoff=2.0, engine=eng)
+    r = got["regions"]
+    w = r["indexEnd"] - r["indexStart"] + 1
+    assert np.array_equal(r["meanCoverage"], O.view_sums(mine["meanCoverage"], r["indexStart"], r["indexEnd"]) / w)
+    for g in prep["groupMeans"]:
+        assert np.array_equal(r["mean" + g], O.view_sums(mine["groupMeans"][g], r["indexStart"], r["indexEnd"]) / w)
+    assert np.array_equal(r["area"], base["regions"]["area"])
+    assert not np.array_equal(r["meanCoverage"], base["regions"]["meanCoverage"])
