@@ -104,6 +104,7 @@ struct dfb_ctx {
     int opt_chunk_perms = 0;     // fused kernel: permutations per MMA chunk (0 = auto)
     int opt_tmem_stages = 0;     // fused kernel: accumulator stages (0 = auto)
     int opt_fused = 1;           // fused screen+refine kernel (0: two-kernel screen path)
+    int opt_a16_fused = 1;       // observed-F kernel also writes the null scan's fp16 operand (0: built on first use)
     int opt_mma_warps = 0;       // null2 kernel: MMA-issuing warps (0 = auto)
     int opt_null2 = 1;           // second-generation null scan (fstat_tc2.cu); 0: the first fused kernel
     int opt_k2_waves = 16;       // fused kernel: CTAs per resident slot (1 = persistent); see launch_fused

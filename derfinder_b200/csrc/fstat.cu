@@ -20,6 +20,7 @@
 // processed in groups of BP, each thread accumulating BM x (BP*PC) FP64 dot products.  In mask
 // mode the epilogue thresholds in registers and emits one bit per (base, permutation) plus the
 // exceedance values, compacted per (permutation, tile) -- null F-stats never reach HBM.
+#include <cuda_fp16.h>
 #include <math.h>
 
 #include <algorithm>
@@ -155,6 +156,12 @@ struct FstatParams {
     double* vals;
     unsigned long long capacity;
     unsigned long long* cursor;
+    // observed scan only: operand cache of the tensor-core null scan (fstat_tc2.cu), written on the way --
+    // centred coverage as fp16 rows [N][a16_ka] (zero padded), |yc|^2 and the row mean; null when not wanted
+    __half* a16;
+    int a16_ka;
+    double* a16_yy;
+    double* a16_m;
 };
 
 template <int PC, int BP, int BM, int NT>
@@ -472,7 +479,7 @@ static void fill_common(FstatParams& P, const dfb_cov* cov, const ModelBasis& mb
 // Observed statistics (identity labelling): one thread per base, the log2 matrix is streamed once
 // (coalesced along bases for every sample), Q is broadcast from shared memory.  HBM-bound:
 // 8*n bytes read + 8 bytes written per base.  Same arithmetic contract as the tiled kernel.
-template <int PC>
+template <int PC, bool EMIT>
 __global__ void __launch_bounds__(256) fstat_observed_kernel(const FstatParams P) {
     extern __shared__ __align__(16) double Qs_obs[];  // [n][pp]
     const int n = P.n;
@@ -488,18 +495,56 @@ __global__ void __launch_bounds__(256) fstat_observed_kernel(const FstatParams P
             double S[PC];
 #pragma unroll
             for (int j = 0; j < PC; ++j) S[j] = 0.0;
-            for (int k = 0; k < n; ++k) {
-                const double v = __dsub_rn(P.Y[(size_t)k * P.ld + base], m);  // L1/L2 hit after the first pass
-                if (c == 0) yy = fma(v, v, yy);
-                const double* q = Qs_obs + (size_t)k * P.pp + c * PC;
+            if (!EMIT) {
+                for (int k = 0; k < n; ++k) {
+                    const double v = __dsub_rn(P.Y[(size_t)k * P.ld + base], m);  // L1/L2 hit after the first pass
+                    if (c == 0) yy = fma(v, v, yy);
+                    const double* q = Qs_obs + (size_t)k * P.pp + c * PC;
 #pragma unroll
-                for (int j = 0; j < PC; ++j) S[j] = fma(v, q[j], S[j]);
+                    for (int j = 0; j < PC; ++j) S[j] = fma(v, q[j], S[j]);
+                }
             }
+            const bool emit = EMIT && c == 0;
+            uint4* arow = emit ? reinterpret_cast<uint4*>(P.a16 + (size_t)base * P.a16_ka) : nullptr;
+            // sixteen samples per step: sixteen loads in flight and, when the fp16 operand is emitted, one whole
+            // 32-byte sector of the base's row per step (two 16-byte stores; half sectors would make L2 read
+            // the other half back from DRAM)
+            for (int k0 = 0; EMIT && k0 < n; k0 += 16) {
+                __half2 h2[8];
+#pragma unroll
+                for (int e = 0; e < 16; e += 2) {
+                    double v2[2];
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        const int k = k0 + e + u;
+                        v2[u] = 0.0;
+                        if (k < n) {
+                            const double v = __dsub_rn(P.Y[(size_t)k * P.ld + base], m);  // L1/L2 hit after the first pass
+                            if (c == 0) yy = fma(v, v, yy);
+                            const double* q = Qs_obs + (size_t)k * P.pp + c * PC;
+#pragma unroll
+                            for (int j = 0; j < PC; ++j) S[j] = fma(v, q[j], S[j]);
+                            v2[u] = v;
+                        }
+                    }
+                    h2[e >> 1] = __halves2half2(__double2half(v2[0]), __double2half(v2[1]));
+                }
+                if (emit) {
+                    arow[k0 >> 3] = reinterpret_cast<const uint4*>(h2)[0];
+                    arow[(k0 >> 3) + 1] = reinterpret_cast<const uint4*>(h2)[1];
+                }
+            }
+            if (emit)
+                for (int k0 = (n + 15) & ~15; k0 < P.a16_ka; k0 += 8) arow[k0 >> 3] = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
             for (int j = 0; j < PC; ++j) {
                 if (c * PC + j < P.p0) s0 = fma(S[j], S[j], s0);
                 else sd = fma(S[j], S[j], sd);
             }
+        }
+        if (EMIT) {
+            P.a16_yy[base] = yy;
+            P.a16_m[base] = m;
         }
         double rss1 = __dsub_rn(__dsub_rn(yy, s0), sd);
         if (rss1 < 0.0) rss1 = 0.0;
@@ -520,16 +565,53 @@ int fstat_observed(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, doubl
     P.B = 1;
     P.mode = 0;
     P.fout = f_dev;
+    // The tensor-core null scan of calculatePvalues() needs the centred coverage as fp16 rows plus |yc|^2 and
+    // the row mean: exactly what this kernel has in registers.  Writing them here costs 2 bytes per element
+    // (the stand-alone builder re-reads the whole FP64 matrix: 3.9 ms at the chr1 shape).
+    {
+        dfb_cov* cw = const_cast<dfb_cov*>(cov);
+        cw->a16_center = -1;
+        if (ctx->opt_a16_fused && ctx->opt_screen && ctx->opt_null2 && cov->n <= 255 && mb.p >= 2 && mb.p <= 8 &&
+            cov->n - mb.p > 0) {
+            const int KA = (int)ceil_div(round_up(cov->n, 16), 64) * 64;
+            const int64_t rows_pad = ceil_div(cov->N, 128) * 128;
+            DFB_TRY(cw->a16.alloc(ctx, (size_t)rows_pad * KA));
+            DFB_TRY(cw->a16_yy.alloc(ctx, (size_t)std::max<int64_t>(cov->N, 1)));
+            DFB_TRY(cw->a16_m.alloc(ctx, (size_t)std::max<int64_t>(cov->N, 1)));
+            if (rows_pad > cov->N)  // rows of the last 128-base tile beyond N
+                DFB_CUDA(cudaMemsetAsync(cw->a16.p + (size_t)cov->N * KA, 0, (size_t)(rows_pad - cov->N) * KA * 2, ctx->stream));
+            P.a16 = reinterpret_cast<__half*>(cw->a16.p);
+            P.a16_ka = KA;
+            P.a16_yy = cw->a16_yy.p;
+            P.a16_m = cw->a16_m.p;
+            cw->a16_center = mb.centered ? 1 : 0;
+            cw->a16_ka = KA;
+            cw->a16_rows = rows_pad;
+        }
+    }
     const size_t smem = mb.qpad.size() * sizeof(double);
     const int grid = grid_for(cov->N, 256, ctx->sm_count, 8);
-    {
+    auto launch = [&](auto kern) -> int {
+        if (smem > 48 * 1024) DFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         KTimer t(ctx, DFB_K_FSTAT, 1);
+        kern<<<grid, 256, smem, ctx->stream>>>(P);
+        return DFB_OK;
+    };
+    if (P.a16) {
         switch (mb.pc) {
-            case 2: fstat_observed_kernel<2><<<grid, 256, smem, ctx->stream>>>(P); break;
-            case 3: fstat_observed_kernel<3><<<grid, 256, smem, ctx->stream>>>(P); break;
-            case 4: fstat_observed_kernel<4><<<grid, 256, smem, ctx->stream>>>(P); break;
-            case 5: fstat_observed_kernel<5><<<grid, 256, smem, ctx->stream>>>(P); break;
-            default: fstat_observed_kernel<6><<<grid, 256, smem, ctx->stream>>>(P); break;
+            case 2: DFB_TRY(launch(fstat_observed_kernel<2, true>)); break;
+            case 3: DFB_TRY(launch(fstat_observed_kernel<3, true>)); break;
+            case 4: DFB_TRY(launch(fstat_observed_kernel<4, true>)); break;
+            case 5: DFB_TRY(launch(fstat_observed_kernel<5, true>)); break;
+            default: DFB_TRY(launch(fstat_observed_kernel<6, true>)); break;
+        }
+    } else {
+        switch (mb.pc) {
+            case 2: DFB_TRY(launch(fstat_observed_kernel<2, false>)); break;
+            case 3: DFB_TRY(launch(fstat_observed_kernel<3, false>)); break;
+            case 4: DFB_TRY(launch(fstat_observed_kernel<4, false>)); break;
+            case 5: DFB_TRY(launch(fstat_observed_kernel<5, false>)); break;
+            default: DFB_TRY(launch(fstat_observed_kernel<6, false>)); break;
         }
     }
     DFB_CUDA(cudaGetLastError());

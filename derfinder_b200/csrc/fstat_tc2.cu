@@ -130,7 +130,8 @@ __global__ void __launch_bounds__(128) build_qb16_kernel(const double* __restric
         const int pass = row / pass_cols, within = row - pass * pass_cols;
         const int jj = within / G.pp, qq = within - jj * G.pp;
         const int j = G.j0 + jj;
-        const int64_t b = c * G.ps + pass * G.pp + qq;
+        // rows beyond ps * pe pad the MMA N to a multiple of 16: zero
+        const int64_t b = row < G.ps * G.pe ? c * G.ps + pass * G.pp + qq : G.B;
         __half vals[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
@@ -225,9 +226,63 @@ static uint32_t umma_idesc_f16(int M, int N) {
 // then the producer warp (TMA A tiles, bulk copies of the B group) and mw MMA warps (one lane each; the
 // chunks alternate between them: one thread spends ~600 cycles per chunk on waits, fences, four MMA
 // issues and a commit, which is more than the tensor pipe needs to execute it).
-constexpr int N2_MAX_THREADS = 4 * 128 + 96;
+// accumulator stages = epilogue warp groups for `pe` screened columns at the default 32-permutation chunk
+// epilogue warp groups the kernel is compiled for: four for tiny models (the FP64 refinement of frequent
+// candidates dominates there), two otherwise (168 registers per thread: two TMEM register sets without spills)
+__host__ __device__ constexpr int n2_max_groups(int pe) { return pe <= 8 ? 4 : 2; }
+// Default chunk width: 32 permutations (a lane per permutation in the bookkeeping; at most 256 accumulator
+// columns for the model sizes the kernel is compiled for).  Measured on the chr1 shape (pe = 5, c3s workload,
+// gpurun_out/r2_*_sweep.txt): 32 permutations x 3 stages x 3 warp groups 2.14 ms; 24 permutations (128 columns)
+// x 4 stages x 4 groups 2.35 ms; 24 x 4 stages x 2 groups with the whole accumulator row in one TMEM round trip
+// 2.41 ms (two warps per scheduler cannot hide their own instruction latencies).
+__host__ __device__ constexpr int n2_default_ps(int pe) {
+    int ps = n2_pass_perms(pe);
+    while (ps + n2_pass_perms(pe) <= 32 && ((ps + n2_pass_perms(pe)) * pe + 15) / 16 * 16 <= 256) ps += n2_pass_perms(pe);
+    return ps;
+}
+// columns [0, NCOL) of an accumulator row as 32 / 16 / 8-column loads, none of them waited for
+template <int NCOL>
+__device__ __forceinline__ void tmem_ld_row_nw(uint32_t taddr, uint32_t* r) {
+    static_assert(NCOL % 8 == 0, "column count");
+    constexpr int N32 = NCOL / 32, REM = NCOL % 32;
+#pragma unroll
+    for (int i = 0; i < N32; ++i) tmem_ld32_nw(taddr + (uint32_t)(32 * i), r + 32 * i);
+    if (REM >= 16) tmem_ld16_nw(taddr + (uint32_t)(32 * N32), r + 32 * N32);
+    if (REM % 16 >= 8) tmem_ld8_nw(taddr + (uint32_t)(32 * N32 + (REM >= 16 ? 16 : 0)), r + 32 * N32 + (REM >= 16 ? 16 : 0));
+}
+__host__ __device__ constexpr int n2_max_threads(int pe) { return 128 * n2_max_groups(pe) + 96; }
+
+// registers of a TMEM load are valid after tcgen05.wait::ld; this ties their first use behind the wait for
+// the compiler as well (it sees no dependence between the wait and plain arithmetic on the registers)
+template <int NREG>
+__device__ __forceinline__ void tmem_regs_ready(uint32_t* r) {
+#pragma unroll
+    for (int i = 0; i + 8 <= NREG; i += 8)
+        asm volatile("" : "+r"(r[i]), "+r"(r[i + 1]), "+r"(r[i + 2]), "+r"(r[i + 3]), "+r"(r[i + 4]), "+r"(r[i + 5]),
+                          "+r"(r[i + 6]), "+r"(r[i + 7]));
+}
+// NC consecutive columns as the fewest loads, NOT waited for
+template <int NC>
+__device__ __forceinline__ void tmem_ld_cols_nw(uint32_t taddr, uint32_t* r) {
+    static_assert(NC % 8 == 0 && NC >= 8 && NC <= 64, "column count");
+    int c = 0;
+    if (NC >= 32) {
+        tmem_ld32_nw(taddr, r);
+        c = 32;
+        if (NC == 64) {
+            tmem_ld32_nw(taddr + 32u, r + 32);
+            c = 64;
+        }
+    }
+    if (NC - c >= 16) {
+        tmem_ld16_nw(taddr + (uint32_t)c, r + c);
+        c += 16;
+    }
+    if (NC - c >= 8) tmem_ld8_nw(taddr + (uint32_t)c, r + c);
+}
+
 template <int PT, int J0>
-__global__ void __launch_bounds__(N2_MAX_THREADS, 1) fstat_null2_kernel(const Null2Params P,
+__global__ void __launch_bounds__(n2_max_threads(PT - J0), 1) fstat_null2_kernel(const Null2Params P,
                                                                         const __grid_constant__ CUtensorMap tmA) {
     constexpr int PE = PT - J0;
     constexpr int PP = n2_pass_perms(PE);
@@ -296,98 +351,120 @@ __global__ void __launch_bounds__(N2_MAX_THREADS, 1) fstat_null2_kernel(const Nu
     };
 
     if (warp == prod_warp) {
-        // ===== producer: B group per pass (bulk copies), A tiles (TMA) through the ring =====
-        if (lane == 0) {
-            int stage = 0;
-            uint32_t aphase = 0;  // parity of the NEXT wait on a_empty[stage] is aphase ^ 1 on the first round
-            for (int64_t g = 0; g < G.groups; ++g) {
-                const int cgl = (int)min((int64_t)G.cg, G.chunks - g * G.cg);
-                lap(0);
-                if (g > 0) mbar_wait(b_empty, (uint32_t)((g - 1) & 1));  // the MMAs of the previous pass have retired
-                lap(1);  // producer: wait for the previous pass to retire
+        // ===== producer: B group per pass (bulk copies), A tiles (TMA) through the ring; whole warp, one
+        // elected lane issues (see the MMA warps) =====
+        const bool count_me = prof && lane == 0;
+        auto lap = [&](int slot) {
+            if (count_me) {
+                const long long t = clock64();
+                pc[slot] += (unsigned long long)(t - tprev);
+                tprev = t;
+            }
+        };
+        int stage = 0;
+        uint32_t aphase = 0;  // parity of the NEXT wait on a_empty[stage] is aphase ^ 1 on the first round
+        for (int64_t g = 0; g < G.groups; ++g) {
+            const int cgl = (int)min((int64_t)G.cg, G.chunks - g * G.cg);
+            lap(0);
+            if (g > 0) mbar_wait(b_empty, (uint32_t)((g - 1) & 1));  // the MMAs of the previous pass have retired
+            lap(1);  // producer: wait for the previous pass to retire
+            if (elect_one()) {
                 mbar_expect_tx(b_full, (uint32_t)cgl * G.b_bytes);
                 for (int c = 0; c < cgl; ++c)
                     bulk_g2s(smem_u32(Bs) + (uint32_t)c * G.b_bytes, P.qb + (size_t)(g * G.cg + c) * G.b_bytes, G.b_bytes,
                              b_full);
-                for (int64_t i = 0; i < my_tiles; ++i) {
-                    const int64_t tile = blockIdx.x + i * gridDim.x;
-                    lap(0);
-                    mbar_wait(a_empty + 8 * stage, aphase ^ 1u);
-                    lap(2);  // producer: wait for a free A stage
+            }
+            __syncwarp();
+            for (int64_t i = 0; i < my_tiles; ++i) {
+                const int64_t tile = blockIdx.x + i * gridDim.x;
+                lap(0);
+                mbar_wait(a_empty + 8 * stage, aphase ^ 1u);
+                lap(2);  // producer: wait for a free A stage
+                if (elect_one()) {
                     mbar_expect_tx(a_full + 8 * stage, G.a_bytes);
                     for (int kb = 0; kb < G.KB; ++kb)
                         tma_load_2d(smem_u32(As) + (uint32_t)stage * G.a_bytes + (uint32_t)kb * (TC_M * 128u), &tmA, kb * 64,
                                     (int32_t)(tile * TC_M), a_full + 8 * stage);
-                    if (++stage == NA) {
-                        stage = 0;
-                        aphase ^= 1u;
-                    }
+                }
+                __syncwarp();
+                if (++stage == NA) {
+                    stage = 0;
+                    aphase ^= 1u;
                 }
             }
-            lap(0);
-            if (prof && P.prof)
-                for (int i = 0; i < 8; ++i) atomicAdd(&P.prof[16 + i], pc[i]);
         }
-        __syncwarp();
+        lap(0);
+        if (count_me && P.prof)
+            for (int i = 0; i < 8; ++i) atomicAdd(&P.prof[16 + i], pc[i]);
     } else if (warp >= mma_warp) {
-        // ===== MMA issuers (one lane each): nk16 instructions per (tile, chunk), accumulator ring of NT stages;
-        // issuer m takes the chunk units with (running index) % mw == m =====
-        if (lane == 0) {
-            const int me = warp - mma_warp;
-            const bool count_me = prof && me == 0;
-            auto lap = [&](int slot) {
-                if (count_me) {
-                    const long long t = clock64();
-                    pc[slot] += (unsigned long long)(t - tprev);
-                    tprev = t;
-                }
-            };
-            int turn = 0;  // running chunk-unit index modulo mw
-            // Issue order.  Accumulator stages are shared between the issuers (NT need not be a multiple of mw),
-            // and an mbarrier wait only tells parities apart: an issuer running two uses of a stage ahead of the
-            // other one would take the stage's INITIAL state for "released" and overwrite an accumulator that has
-            // not been scanned yet.  So unit u is issued only after unit u - 1 has been (a sequence number in
-            // shared memory): the use before it on the same stage has then passed its own wait, which puts the
-            // barrier at most one phase behind.  Waits, fences and commits of the two issuers still overlap.
-            volatile uint32_t* issue_seq = reinterpret_cast<volatile uint32_t*>(bars + 19);
-            uint32_t unit = 0;            // Descriptors stay in registers (a table in local memory costs an L2 round trip per MMA: with
-            // 215 KB of shared memory the L1 is a few KB and the stack lines do not survive).  K step t reads
-            // columns 16 t .. 16 t + 15: 64-column block t >> 2 (one [rows x 128 B] swizzled slab each), 32 bytes
-            // per step inside the block; the start-address field counts 16-byte units.
-            const uint64_t da0 = umma_desc_sw128(smem_u32(As)), db0 = umma_desc_sw128(smem_u32(Bs));
-            const uint64_t a_blk = (uint64_t)((TC_M * 128u) >> 4), b_blk = (uint64_t)(((uint32_t)G.nmma * 128u) >> 4);
-            const int nmm = (P.dbg & 2) ? 1 : G.nk16;
-            int stage = 0, s = 0;
-            uint32_t aphase = 0, tphase = 0;
-            for (int64_t g = 0; g < G.groups; ++g) {
-                const int cgl = (int)min((int64_t)G.cg, G.chunks - g * G.cg);
-                lap(0);
-                mbar_wait(b_full, (uint32_t)(g & 1));
-                lap(1);  // MMA lane: wait for the B group
-                for (int64_t i = 0; i < my_tiles; ++i) {
-                    mbar_wait(a_full + 8 * stage, aphase);
-                    tc_fence_after();
-                    lap(2);  // MMA lane: wait for the A tile
-                    const uint64_t astage = (uint64_t)(((uint32_t)stage * G.a_bytes) >> 4);
-                    for (int c = 0; c < cgl; ++c) {
-                        const bool mine = turn == me;
-                        if (++turn == mw) turn = 0;
-                        const uint32_t u = unit++;
-                        if (!mine) {
-                            if (++s == NT) {
-                                s = 0;
-                                tphase ^= 1u;
-                            }
-                            continue;
+        // ===== MMA issuers: nk16 instructions per (tile, chunk), accumulator ring of NT stages; issuer m takes
+        // the chunk units with (running index) % mw == m.  The WHOLE warp runs the loop with warp-uniform
+        // values and one elected lane executes the tcgen05 instructions: inside an `if (lane == 0)` region the
+        // compiler cannot prove the descriptors uniform and wraps every UTCHMMA in a vote / elect / R2UR
+        // broadcast loop (~130 cycles per instruction, measured) =====
+        const int me = __shfl_sync(0xffffffffu, warp - mma_warp, 0);
+        const bool count_me = prof && me == 0 && lane == 0;
+        auto lap = [&](int slot) {
+            if (count_me) {
+                const long long t = clock64();
+                pc[slot] += (unsigned long long)(t - tprev);
+                tprev = t;
+            }
+        };
+        int turn = 0;  // running chunk-unit index modulo mw
+        // Issue order.  Accumulator stages are shared between the issuers (NT need not be a multiple of mw),
+        // and an mbarrier wait only tells parities apart: an issuer running two uses of a stage ahead of the
+        // other one would take the stage's INITIAL state for "released" and overwrite an accumulator that has
+        // not been scanned yet.  So unit u waits for its accumulator only after unit u - 1 has got its own (a
+        // sequence number in shared memory): the use before it on the same stage has then passed its wait,
+        // which puts the barrier at most one phase behind.  The MMA issues of the two warps interleave.
+        // (With NT a multiple of mw every stage has one issuer and none of this is needed.)
+        volatile uint32_t* issue_seq = reinterpret_cast<volatile uint32_t*>(bars + 19);
+        const bool use_seq = mw > 1 && (NT % mw) != 0;
+        uint32_t unit = 0;
+        // K step t reads columns 16 t .. 16 t + 15: 64-column block t >> 2 (one [rows x 128 B] swizzled slab
+        // each), 32 bytes per step inside the block; the start-address field counts 16-byte units.
+        const uint64_t da0 = umma_desc_sw128(smem_u32(As)), db0 = umma_desc_sw128(smem_u32(Bs));
+        const uint64_t a_blk = (uint64_t)((TC_M * 128u) >> 4), b_blk = (uint64_t)(((uint32_t)G.nmma * 128u) >> 4);
+        const int nmm = (P.dbg & 2) ? 1 : G.nk16;
+        int stage = 0, s = 0;
+        uint32_t aphase = 0, tphase = 0;
+        for (int64_t g = 0; g < G.groups; ++g) {
+            const int cgl = (int)min((int64_t)G.cg, G.chunks - g * G.cg);
+            lap(0);
+            mbar_wait(b_full, (uint32_t)(g & 1));
+            lap(1);  // MMA warp: wait for the B group
+            for (int64_t i = 0; i < my_tiles; ++i) {
+                mbar_wait(a_full + 8 * stage, aphase);
+                tc_fence_after();
+                lap(2);  // MMA warp: wait for the A tile
+                const uint64_t astage = (uint64_t)(((uint32_t)stage * G.a_bytes) >> 4);
+                for (int c = 0; c < cgl; ++c) {
+                    const bool mine = turn == me;
+                    if (++turn == mw) turn = 0;
+                    const uint32_t u = unit++;
+                    if (!mine) {
+                        if (++s == NT) {
+                            s = 0;
+                            tphase ^= 1u;
                         }
-                        if (mw > 1)
-                            while (*issue_seq != u) {
-                            }
-                        mbar_wait(tmem_empty + 8 * s, tphase ^ 1u);
-                        tc_fence_after();
-                        lap(3);  // MMA lane: wait for a free accumulator
-                        const uint32_t d_addr = tmem_base + (uint32_t)(s * G.nmma);
-                        const uint64_t bchunk = (uint64_t)(((uint32_t)c * G.b_bytes) >> 4);
+                        continue;
+                    }
+                    lap(0);
+                    if (use_seq)
+                        while (*issue_seq != u) {
+                        }
+                    lap(7);  // MMA warp: wait for the other issuer
+                    mbar_wait_sel(tmem_empty + 8 * s, tphase ^ 1u, P.dbg & 16);
+                    tc_fence_after();
+                    lap(3);  // MMA warp: wait for a free accumulator
+                    const uint32_t d_addr = tmem_base + (uint32_t)(s * G.nmma);
+                    const uint64_t bchunk = (uint64_t)(((uint32_t)c * G.b_bytes) >> 4);
+                    if (elect_one()) {
+                        if (use_seq) {  // hand the sequence over before issuing
+                            __threadfence_block();
+                            *issue_seq = u + 1;
+                        }
                         uint64_t ad = da0 + astage, bd = db0 + bchunk;
                         for (int t = 0; t < nmm; ++t) {
                             umma_f16(d_addr, ad, bd, P.idesc, t ? 1u : 0u);
@@ -399,30 +476,34 @@ __global__ void __launch_bounds__(N2_MAX_THREADS, 1) fstat_null2_kernel(const Nu
                                 bd += 2;
                             }
                         }
-                        if (mw > 1) {
-                            __threadfence_block();
-                            *issue_seq = u + 1;
-                        }
                         umma_commit(tmem_full + 8 * s);  // accumulator ready for the epilogue
-                        lap(4);  // MMA lane: issue
-                        if (++s == NT) {
-                            s = 0;
-                            tphase ^= 1u;
-                        }
+                        if (c + 1 == cgl) umma_commit(a_empty + 8 * stage);  // last unit of the tile in this pass
                     }
-                    umma_commit(a_empty + 8 * stage);  // A stage reusable once these MMAs have read it
-                    if (++stage == NA) {
-                        stage = 0;
-                        aphase ^= 1u;
+                    __syncwarp();
+                    lap(4);  // MMA warp: issue + commit
+                    if (++s == NT) {
+                        s = 0;
+                        tphase ^= 1u;
                     }
                 }
-                umma_commit(b_empty);  // every MMA of this pass has retired: the B group may be replaced
+                // A stage reusable once the MMAs that read it have retired: every issuer reports (count mw); the
+                // one that issued the tile's last unit did so above, right behind its MMAs
+                {
+                    const int last_turn = (int)((unit - 1u) % (uint32_t)mw);
+                    if (last_turn != me && elect_one()) umma_commit(a_empty + 8 * stage);
+                    __syncwarp();
+                }
+                if (++stage == NA) {
+                    stage = 0;
+                    aphase ^= 1u;
+                }
             }
-            lap(0);
-            if (prof && P.prof && me == 0)
-                for (int i = 0; i < 8; ++i) atomicAdd(&P.prof[8 + i], pc[i]);
+            if (elect_one()) umma_commit(b_empty);  // every MMA of this pass has retired: the B group may be replaced
+            __syncwarp();
         }
-        __syncwarp();
+        lap(0);
+        if (count_me && P.prof)
+            for (int i = 0; i < 8; ++i) atomicAdd(&P.prof[8 + i], pc[i]);
     } else {
         // ===== epilogue + exact refinement.  Warp group h = warp >> 2 (four warps = the four TMEM lane
         // quarters) owns every chunk unit with (running index) % ew == h and scans ALL of its permutations:
@@ -477,14 +558,14 @@ __global__ void __launch_bounds__(N2_MAX_THREADS, 1) fstat_null2_kernel(const Nu
                     const int b0 = (g * G.cg + c) * ps;  // first permutation of this unit
                     const int nq = min(ps, Bi - b0);
                     lap(0);
-                    mbar_wait(tmem_full + 8 * s_mine, ph_mine);
+                    mbar_wait_sel(tmem_full + 8 * s_mine, ph_mine, P.dbg & 16);
                     tc_fence_after();
                     lap(2);  // epilogue: wait for the accumulator
                     const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(s_mine * G.nmma);
                     int nwork = 0;
-                    for (int q0 = 0; q0 < ((P.dbg & 4) ? 0 : nq); q0 += PP) {
-                        uint32_t vr[NC];
-                        tmem_ld_cols<NC>(taddr + (uint32_t)(q0 * PE), vr);
+                    // one pass = PP permutations = NC accumulator columns; the load of pass k + 1 is in flight while
+                    // pass k is evaluated (two register sets, selected statically)
+                    auto scan_pass = [&](const uint32_t* vr, int q0) {
                         float a[PP];
 #pragma unroll
                         for (int h = 0; h < PP / 2; ++h) {
@@ -501,7 +582,7 @@ __global__ void __launch_bounds__(N2_MAX_THREADS, 1) fstat_null2_kernel(const Nu
                         float mx = a[0];
 #pragma unroll
                         for (int qq = 1; qq < PP; ++qq) mx = fmaxf(mx, a[qq]);
-                        if (!__any_sync(0xffffffffu, mx >= thr)) continue;  // the common case for stringent cutoffs
+                        if (!__any_sync(0xffffffffu, mx >= thr)) return;  // the common case for stringent cutoffs
                         const uint16_t ent0 = (uint16_t)((q0 << 5) | lane);
 #pragma unroll
                         for (int qq = 0; qq < PP; ++qq) {
@@ -512,6 +593,27 @@ __global__ void __launch_bounds__(N2_MAX_THREADS, 1) fstat_null2_kernel(const Nu
                                 nwork += __popc(word);
                             }
                         }
+                    };
+                    constexpr int PSD = n2_default_ps(PE);
+                    if (n2_max_groups(PE) > 2 || ps != PSD) {  // 96 registers per thread (or a developer chunk width): pass by pass
+                        const int nscan = (P.dbg & 4) ? 0 : nq;
+                        for (int q0 = 0; q0 < nscan; q0 += PP) {
+                            uint32_t va[NC];
+                            tmem_ld_cols_nw<NC>(taddr + (uint32_t)(q0 * PE), va);
+                            tmem_ld_wait();
+                            tmem_regs_ready<NC>(va);
+                            scan_pass(va, q0);
+                        }
+                    } else if (!(P.dbg & 4)) {
+                        // the whole accumulator row of the unit in ONE round trip to TMEM (up to 128 registers; two
+                        // warp groups leave 168 per thread), then the passes back to back
+                        uint32_t va[PSD * PE];
+                        tmem_ld_row_nw<PSD * PE>(taddr, va);
+                        tmem_ld_wait();
+                        tmem_regs_ready<PSD * PE>(va);
+#pragma unroll
+                        for (int pass = 0; pass < PSD / PP; ++pass)
+                            if (pass * PP < nq) scan_pass(va + pass * NC, pass * PP);
                     }
                     tc_fence_before();
                     __syncwarp();
@@ -648,18 +750,20 @@ static bool null2_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
     const size_t limit = std::min<size_t>(ctx->smem_optin, 227 * 1024);
     {
         const int unit = G.pp;  // a chunk is a whole number of epilogue passes
-        // widest chunk of at most 32 permutations (a lane per permutation in the bookkeeping) ...
-        int ps = unit;
-        while (ps + unit <= 32 && (ps + unit) * G.pe <= 256) ps += unit;
+        // Chunk width (see n2_default_ps) and as many accumulator stages as the 512 TMEM columns hold: the
+        // MMA -> scan -> MMA round trip of a stage (~1500 cycles) hides behind the other stages' tensor time.
+        int ps = n2_default_ps(G.pe);
         if (ctx->opt_chunk_perms > 0) ps = std::max(unit, std::min(32, (ctx->opt_chunk_perms / unit) * unit));
         for (; ps >= unit; ps -= unit) {
-            const int nmma = ps * G.pe;
-            if (nmma > 256 || nmma % 16) continue;
-            // ... and as many accumulator stages as the 512 TMEM columns hold (at most 4): one epilogue warp
-            // group per stage
+            const int nmma = (int)round_up(ps * G.pe, 16);
+            if (nmma > 256) continue;
             G.nt = std::min(4, 512 / nmma);
             if (ctx->opt_tmem_stages > 0) G.nt = std::max(1, std::min(G.nt, ctx->opt_tmem_stages));
-            const int ew = G.nt;
+            // epilogue warp groups: group h scans the units with index % ew == h; NT is a multiple of ew so that
+            // every stage has ONE owner group (a parity wait cannot tell a stage two uses behind from a ready one)
+            int ew = ctx->opt_epi_warps > 0 ? ctx->opt_epi_warps : n2_max_groups(G.pe);
+            ew = std::max(1, std::min(std::min(ew, n2_max_groups(G.pe)), G.nt));
+            while (G.nt % ew) --ew;
             G.ew = ew;
             G.ps = ps;
             G.hp = ps;
@@ -885,8 +989,8 @@ int fstat_perm_batch_null2(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& m
             const double g = (double)grid;
             fprintf(stderr, "[dfb] null2 phases, mean cycles per CTA -- epilogue warp 0: thresholds %.0f  wait-acc %.0f  scan %.0f  refine %.0f  other %.0f\n",
                     h[1] / g, h[2] / g, h[3] / g, h[5] / g, h[0] / g);
-            fprintf(stderr, "[dfb] null2 phases, mean cycles per CTA -- MMA lane: wait-B %.0f  wait-A %.0f  wait-acc %.0f  issue %.0f  other %.0f;  producer: wait-pass %.0f  wait-A-stage %.0f  other %.0f\n",
-                    h[8 + 1] / g, h[8 + 2] / g, h[8 + 3] / g, h[8 + 4] / g, h[8 + 0] / g, h[16 + 1] / g, h[16 + 2] / g, h[16 + 0] / g);
+            fprintf(stderr, "[dfb] null2 phases, mean cycles per CTA -- MMA lane: wait-B %.0f  wait-A %.0f  wait-turn %.0f  wait-acc %.0f  issue %.0f  hand-over %.0f  commit %.0f  other %.0f;  producer: wait-pass %.0f  wait-A-stage %.0f  other %.0f\n",
+                    h[8 + 1] / g, h[8 + 2] / g, h[8 + 7] / g, h[8 + 3] / g, h[8 + 4] / g, h[8 + 5] / g, h[8 + 6] / g, h[8 + 0] / g, h[16 + 1] / g, h[16 + 2] / g, h[16 + 0] / g);
         }
         out->capacity = cap;
         if (defer_check) {

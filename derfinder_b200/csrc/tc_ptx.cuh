@@ -55,6 +55,18 @@ __device__ __forceinline__ void mbar_wait_sel(uint32_t bar, uint32_t parity, boo
     if (spin) mbar_wait_spin(bar, parity);
     else mbar_wait(bar, parity);
 }
+// one lane of the (fully active) warp: the form the compiler recognises as a uniform single-thread region
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "elect.sync _|P1, 0xffffffff;\n"
+        "selp.u32 %0, 1, 0, P1;\n"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
                  "l"(src), "r"(bytes), "r"(bar)
