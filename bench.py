@@ -14,12 +14,16 @@ through the reference-facing calls with HOST buffers (H2D of the coverage -- as 
 the type the reference holds it in -- and D2H of F-stats, regions, nulls and p-values inside the
 timed region).
 
-Workload: BASELINE.json configs[1] -- synthetic chr21 (Lc = 48,129,895; ~10% of bases pass the
-filter), 12 samples, 2-group model + sampleDepth (p = 3, p0 = 2), 100 permutations, F cutoff
-qf(0.05, 1, 9).  Multi-GPU (torchrun): every rank owns a different synthetic chromosome of the same
-size (weak scaling, chromosome sharding); the only exchange is the pooling of null areas
-(all-gather) and per-permutation maxima (all-reduce max) before the genome-wide p-value / FWER
-ranking (R/mergeResults.R:216-235, 304-307, 380-386).
+Workload (default `c3`): BASELINE.json configs[2], the largest single-GPU configuration -- synthetic
+chr1 (Lc = 249,250,621; 25 M bases pass the filter), 60 samples, 2-group model + sampleDepth + 3
+adjustment covariates (p = 6, p0 = 5), 1000 permutations, F cutoff qf(1e-6, 1, 54).  `--workload c2`
+is configs[1] (chr21, 12 samples, 100 permutations, qf(0.05, 1, 9)), `--workload c4` the whole-genome
+configuration (24 chromosomes, 300 M kept bases, 100 samples, 1000 permutations) bin-packed over the
+ranks (strong scaling, needs >= 2 GPUs for the coverage to be resident).  Multi-GPU (torchrun): every
+rank owns a different synthetic chromosome of the same size (weak scaling, chromosome sharding); the
+only exchange is the genome-wide pooling of mergeResults (R/mergeResults.R:216-235, 304-307,
+380-386): an all-gather of the ranks' region areas and per-permutation maxima and an all-reduce of
+the null histogram, once per step.
 """
 from __future__ import annotations
 
@@ -175,7 +179,7 @@ class ClockSampler(threading.Thread):
                 for bit, nm in names.items():
                     if r & bit:
                         self.reasons.add(nm)
-                time.sleep(0.002)
+                time.sleep(0.010)  # NVML queries take the driver lock: keep them sparse next to a latency-sensitive host loop
         except Exception as e:  # NVML missing: report that instead of inventing clocks
             self.reasons.add(f"nvml_unavailable:{type(e).__name__}")
 
@@ -441,7 +445,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
     ap.add_argument("--cpu-bases", type=int, default=1_600_000, help="bounded CPU sample: kept bases per step")
     ap.add_argument("--cpu-perms", type=int, default=20, help="bounded CPU sample: permutations per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -534,8 +538,11 @@ def main():
     torch.cuda.synchronize()
     ev0.record()
     timed_pass = []
+    step_wall = []
     for _ in range(args.steps):
+        t_s = time.perf_counter()
         R, M = one_step()
+        step_wall.append((time.perf_counter() - t_s) * 1e3)
     ev1.record()
     torch.cuda.synchronize()
     own_ms = sum(a.elapsed_time(b) for a, b in timed_pass) / max(len(timed_pass), 1)
@@ -547,6 +554,8 @@ def main():
     if sampler.is_alive():
         sampler.join()
     ms = ev0.elapsed_time(ev1) / args.steps
+    if os.environ.get("DFB_GAPS"):
+        print("[bench] host wall per timed step (ms):", [round(x, 2) for x in step_wall], file=sys.stderr)
     launches = eng.launch_count()
     kt = {L.K_FSTAT_TC: eng.kernel_time(L.K_FSTAT_TC)}
     eng.enable_timing(False)
@@ -644,20 +653,38 @@ def main():
         peak = peaks.get("bf16_tflops", 1590.0)
         hbm = peaks.get("hbm_gbs", 6650.0)
         alg_bytes = 8.0 * N * n  # read Y once (SURVEY 8d lower bound for the null scan)
-        # DRAM traffic of one fstat_null_kernel launch from the committed ncu --set full capture of
-        # this same command (profiles/r1_e_kernels.txt: 469.9 MB read + 342.0 MB written)
-        traffic = 811.9e6 if args.workload == "c2" else None
-        line["roofline"] = {"bound": "tensor", "kernel": "fstat_null_kernel (K2 permutation scan)", "achieved": achieved,
+        # DRAM traffic per step of the K2 launches: from the committed summary of an `ncu --set full` capture of
+        # this same command (profiles/k2_traffic.json, written by tools/ncu_summary.py), else null
+        traffic, traffic_src = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "k2_traffic.json")))
+            if args.workload in tj:
+                traffic = float(tj[args.workload]["dram_bytes_per_step"])
+                traffic_src = tj[args.workload].get("source")
+        except Exception:
+            pass
+        if n <= 16:
+            why = ("n=%d, p=%d: %d flop per (base, permutation) and K = 16 of a 64-wide operand row; the kernel is "
+                   "bound by the TMEM epilogue and the FP64 refinement of the exceedances (a few percent of all "
+                   "pairs at this cutoff), not by the tensor pipe or HBM (DESIGN.md section 4)" % (n, p, 2 * n * p))
+        else:
+            why = ("n=%d, p=%d: one fp16 tcgen05 product per (128-base tile, 32-permutation chunk) with the constant "
+                   "basis column dropped -- executed flops are %.2fx the algorithmic 2*N*n*p*B; the chunk loop is "
+                   "bound by the MMA -> TMEM scan -> MMA round trip of an accumulator stage (tensor pipe ~40-50%% "
+                   "active in the ncu capture), see DESIGN.md section 4" %
+                   (n, p, (((n + 15) // 16) * 16) * (p - 1) / float(n * p)))
+        line["roofline"] = {"bound": "tensor", "kernel": "fstat_null2_kernel (K2 permutation scan)", "achieved": achieved,
                             "peak": peak, "unit": "TFLOP/s", "frac": (achieved / peak if achieved else None),
                             "traffic": traffic,
                             "peak_source": "MEASURED_PEAKS.json bf16 burst" if "bf16_tflops" in peaks else "fallback",
                             "algorithmic_flops_per_step": flops, "kernel_ms_per_step": k2_ms,
                             "launches_per_step": tc_l / args.steps,
                             "kernel_share_of_step": k2_ms / ms,
-                            "notes": {"why_low": "n=12, p=3: 72 flop per (base, permutation) and K = 32 of a 64-wide "
-                                                 "MMA; the kernel is bound by SM instruction issue in the TMEM "
-                                                 "epilogue and the FP64 refinement of the ~5% exceedances, not by the "
-                                                 "tensor pipe or HBM (DESIGN.md section 4)",
+                            "traffic_source": traffic_src,
+                            "notes": {"what_bounds_it": why,
+                                      "k2_family": "K2 time = the null-scan launches plus their operand builders "
+                                                   "(permuted basis tiles, per-base thresholds) measured by CUDA "
+                                                   "events on the engine's stream inside the timed region",
                                       "hbm_equivalent_GBps": alg_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else None,
                                       "hbm_equivalent_frac": (alg_bytes / (k2_ms * 1e-3) / 1e9 / hbm) if k2_ms > 0 else None,
                                       "base_x_perm_per_s_kernel_only": N * float(B) / (k2_ms * 1e-3) if k2_ms > 0 else None,

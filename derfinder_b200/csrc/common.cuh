@@ -110,6 +110,7 @@ struct dfb_ctx {
     int opt_k2_waves = 16;       // fused kernel: CTAs per resident slot (1 = persistent); see launch_fused
     double opt_null_cap_mb = 0;  // 0 = auto
     int opt_perm_batch = 0;      // 0 = auto
+    double null_density = 0;     // exceedance values per (base, permutation) seen by the last null scan (0 = unknown)
     double opt_scratch_gb = 24;  // upper bound for per-call scratch (mask + exceedance values)
     // pinned staging ring for pageable <-> device copies, and the host copy pool that drains it
     void* pinned = nullptr;

@@ -106,6 +106,7 @@ struct PermBatch {
     DevBuf<uint32_t> mask; // [rows][W]
     DevBuf<int64_t> off;   // [rows][tiles] offset of the tile's first exceedance value
     DevBuf<double> vals;   // compacted F values
+    DevBuf<unsigned char> gflag;  // optional [rows][ceil(W / 32)]: 1 when the 32-word group holds a non-empty word
     int64_t nvals = 0;
     // deferred overflow check (fused path): pinned copy of the value cursor, valid after the next
     // stream synchronisation; the batch is good iff *used_host <= capacity

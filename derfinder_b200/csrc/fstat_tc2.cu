@@ -169,6 +169,8 @@ struct Null2Params {
     uint32_t idesc;
     uint32_t* mask;  // [B][W]
     int64_t W;
+    unsigned char* gflag;  // [B][Gr]: set to 1 for every 32-word group with a non-empty word
+    int64_t Gr;
     int64_t* off;    // [B][W], written for non-empty words only
     double* vals;
     unsigned long long capacity;
@@ -700,6 +702,7 @@ __global__ void __launch_bounds__(n2_max_threads(PT - J0), 1) fstat_null2_kernel
                         const int64_t b = (int64_t)b0 + lane;
                         P.mask[b * P.W + gw] = eword;
                         P.off[b * P.W + gw] = (int64_t)(chunk_ptr + (unsigned long long)(inc2 - c2));
+                        P.gflag[b * P.Gr + (gw >> 5)] = 1;
                     }
                     chunk_left -= (int)(run - chunk_ptr);
                     chunk_ptr = run;
@@ -947,6 +950,9 @@ int fstat_perm_batch_null2(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& m
     out->tiles = out->W;
     DFB_TRY(out->mask.alloc(ctx, (size_t)out->rows * out->W));
     DFB_TRY(out->off.alloc(ctx, (size_t)out->rows * out->tiles));
+    F.Gr = ceil_div(out->W, 32);
+    DFB_TRY(out->gflag.alloc(ctx, (size_t)out->rows * (size_t)F.Gr));
+    F.gflag = out->gflag.p;
     DevBuf<unsigned long long> cursor;
     DFB_TRY(cursor.alloc(ctx, 1));
     // One CTA per SM (the accumulator ring takes all 512 TMEM columns), `k2_waves` CTAs per SM slot over the
@@ -970,6 +976,7 @@ int fstat_perm_batch_null2(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& m
         // the kernel writes the non-empty mask words only (at stringent cutoffs nearly all are empty, and 16
         // warps storing 4-byte zeros to 32 different rows per chunk cost more than the scan itself)
         DFB_TRY(out->mask.zero());
+        DFB_TRY(out->gflag.zero());
         F.vals = out->vals.p;
         F.capacity = cap;
         switch (mb.p) {

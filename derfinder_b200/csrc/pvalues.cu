@@ -74,13 +74,15 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
     const bool two_sided = lo >= 0.0;
     const int sides = two_sided ? 2 : 1;
     const int64_t N = cov->N;
-    const int tb = fstat_tile_bases(n);
+    const int tb = use_screen ? 32 : fstat_tile_bases(n);  // bases per value-offset entry
+    // per permutation: mask words, value offsets, and per 32-word group the region counts + offsets (+ flag)
     const double per_perm_fixed = (double)sides * ((double)ceil_div(N, 32) * 4.0 + (double)ceil_div(N, tb) * 8.0 +
-                                                   (double)ceil_div(N, 32) * 12.0 /* region counts + offsets */);
+                                                   (double)ceil_div(N, 1024) * 13.0);
     const double budget = ctx->opt_scratch_gb * 1e9;
     int64_t pb = (int64_t)std::max(1.0, floor(budget * 0.5 / per_perm_fixed));
     if (ctx->opt_perm_batch > 0) pb = ctx->opt_perm_batch;
     pb = std::min<int64_t>(pb, B);
+    if (ctx->opt_perm_batch <= 0) pb = ceil_div(B, ceil_div(B, pb));  // batches of equal size
 
     std::vector<RegionSet> sets;
     std::vector<std::pair<int64_t, int64_t>> work;  // [b_lo, b_hi)
@@ -90,7 +92,10 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
         b = lo_b;
     }
     // work is a stack: batches come off in increasing permutation order
-    double density = ctx->opt_null_cap_mb > 0 ? -1.0 : 0.08;
+    // exceedance density: the context remembers what the last scan saw (a fresh context assumes 8 %), so a
+    // repeated analysis does not reserve gigabytes of value slots it will not use; an underestimate costs one
+    // re-run of the scan with the exact capacity
+    double density = ctx->opt_null_cap_mb > 0 ? -1.0 : (ctx->null_density > 0 ? ctx->null_density : 0.08);
     while (!work.empty()) {
         auto [b_lo, b_hi] = work.back();
         work.pop_back();
@@ -141,7 +146,10 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
                                       true, &rs));
         }
         if (pbatch.used_host) pbatch.nvals = (int64_t)*pbatch.used_host;
-        if (density >= 0 && dense > 0) density = std::min(1.0, std::max(0.01, 1.3 * (double)pbatch.nvals / dense));
+        if (density >= 0 && dense > 0) {
+            density = std::min(1.0, std::max(1e-4, 1.3 * (double)pbatch.nvals / dense));
+            ctx->null_density = density;
+        }
         for (int64_t b = 0; b < nb; ++b)
             for (int s = 0; s < sides; ++s) nl->per_perm[(size_t)(b_lo + b)] += rs.row_counts[(size_t)(b * sides + s)];
         if (rs.total > 0 && b_lo > 0) {

@@ -192,20 +192,32 @@ struct EmitParams {
 // starts and places them with a warp prefix sum.
 constexpr int GROUPS_PER_WARP = 8;  // independent 128-byte loads a warp keeps in flight
 
+// `gflag` (optional, [rows][Gr]): 0 marks a group without a single passing base -- at stringent cutoffs
+// nearly all of them -- whose mask words are then not even loaded.
 __global__ void __launch_bounds__(256) count_starts_group_kernel(const uint32_t* __restrict__ mask,
                                                                  const uint32_t* __restrict__ seg, int64_t rows,
-                                                                 int64_t W, int64_t Gr, uint32_t* __restrict__ counts) {
+                                                                 int64_t W, int64_t Gr, uint32_t* __restrict__ counts,
+                                                                 const unsigned char* __restrict__ gflag) {
     // grid: (groups of a row / 64, rows); a warp owns GROUPS_PER_WARP consecutive groups and issues all
     // of their loads before it looks at any (one load per short-lived warp left the kernel latency-bound)
     const int lane = threadIdx.x & 31;
     for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
         const int64_t k0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS_PER_WARP;
         if (k0 >= Gr) continue;
+        unsigned live = 0xffu;  // bit u: group k0 + u may hold passing bases
+        if (gflag) {
+            const bool f = lane < GROUPS_PER_WARP && k0 + lane < Gr && gflag[row * Gr + k0 + lane] != 0;
+            live = __ballot_sync(0xffffffffu, f);
+            if (live == 0u) {
+                if (lane < GROUPS_PER_WARP && k0 + lane < Gr) counts[row * Gr + k0 + lane] = 0u;
+                continue;
+            }
+        }
         uint32_t m[GROUPS_PER_WARP], pv[GROUPS_PER_WARP], sg[GROUPS_PER_WARP];
 #pragma unroll
         for (int u = 0; u < GROUPS_PER_WARP; ++u) {
             const int64_t w = (k0 + u) * 32 + lane;
-            const bool valid = w < W;
+            const bool valid = w < W && ((live >> u) & 1u);
             const int64_t g = row * W + w;
             m[u] = valid ? mask[g] : 0u;
             pv[u] = (valid && w > 0) ? mask[g - 1] : 0u;
@@ -224,16 +236,23 @@ __global__ void __launch_bounds__(256) count_starts_group_kernel(const uint32_t*
 __global__ void __launch_bounds__(256) fill_starts_group_kernel(const uint32_t* __restrict__ mask,
                                                                 const uint32_t* __restrict__ seg,
                                                                 const int64_t* __restrict__ goffsets, int64_t rows,
-                                                                int64_t W, int64_t Gr, int64_t* __restrict__ start_pos) {
+                                                                int64_t W, int64_t Gr, int64_t* __restrict__ start_pos,
+                                                                const unsigned char* __restrict__ gflag) {
     const int lane = threadIdx.x & 31;
     for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
         const int64_t k0 = ((int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * GROUPS_PER_WARP;
         if (k0 >= Gr) continue;
+        unsigned live = 0xffu;
+        if (gflag) {
+            const bool f = lane < GROUPS_PER_WARP && k0 + lane < Gr && gflag[row * Gr + k0 + lane] != 0;
+            live = __ballot_sync(0xffffffffu, f);
+            if (live == 0u) continue;
+        }
         uint32_t m[GROUPS_PER_WARP], pv[GROUPS_PER_WARP], sg[GROUPS_PER_WARP];
 #pragma unroll
         for (int u = 0; u < GROUPS_PER_WARP; ++u) {
             const int64_t w = (k0 + u) * 32 + lane;
-            const bool valid = w < W;
+            const bool valid = w < W && ((live >> u) & 1u);
             const int64_t g = row * W + w;
             m[u] = valid ? mask[g] : 0u;
             pv[u] = (valid && w > 0) ? mask[g - 1] : 0u;
@@ -453,6 +472,7 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
     out->row_counts.assign((size_t)rows, 0);
     if (total_words == 0) return DFB_OK;
     const int64_t Gr = ceil_div(W, 32), groups = rows * Gr;  // groups of 32 words, row-local
+    const unsigned char* gflag = (compact && compact->gflag.p) ? compact->gflag.p : nullptr;
     const dim3 group_grid((unsigned)ceil_div(Gr, 8 * GROUPS_PER_WARP), (unsigned)std::min<int64_t>(rows, 65535));
     DevBuf<uint32_t> counts;
     DevBuf<int64_t> offsets, total_dev;
@@ -461,7 +481,7 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
     DFB_TRY(total_dev.alloc(ctx, 1));
     {
         KTimer t(ctx, DFB_K_REGIONS);
-        count_starts_group_kernel<<<group_grid, 256, 0, ctx->stream>>>(mask, seg, rows, W, Gr, counts.p);
+        count_starts_group_kernel<<<group_grid, 256, 0, ctx->stream>>>(mask, seg, rows, W, Gr, counts.p, gflag);
     }
     DFB_TRY(exclusive_scan_u32(ctx, counts.p, offsets.p, groups, total_dev.p, DFB_K_REGIONS));
     // per-row counts: offsets at the row starts (strided gather) + total, read back through pinned
@@ -519,7 +539,8 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
     DFB_TRY(long_count.zero());
     {
         KTimer t(ctx, DFB_K_REGIONS);
-        fill_starts_group_kernel<<<group_grid, 256, 0, ctx->stream>>>(mask, seg, offsets.p, rows, W, Gr, start_pos.p);
+        fill_starts_group_kernel<<<group_grid, 256, 0, ctx->stream>>>(mask, seg, offsets.p, rows, W, Gr, start_pos.p,
+                                                                      gflag);
     }
     {
         KTimer t(ctx, DFB_K_REGIONS);
