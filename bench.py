@@ -49,11 +49,36 @@ WORKLOADS = {
                label="synthetic chr1 (249 Mbp, N=25M kept bases) 60 samples, 3 adjustment covariates, 1000 permutations"),
     "c3s": dict(chr_len=24_925_062, N=2_500_000, n=60, extra=3, B=1000, alpha=1e-6,
                 label="1/10 of synthetic chr1 (N=2.5M kept bases) 60 samples, 3 adjustment covariates, 1000 permutations"),
-    "c4s": dict(chr_len=10_000_000, N=1_000_000, n=100, extra=3, B=1000, alpha=1e-6,
-                label="scaled slice of the whole-genome config (N=1M kept bases) 100 samples, 3 adjustment covariates, 1000 permutations"),
     "tiny": dict(chr_len=2_000_000, N=200_000, n=12, extra=0, B=20, alpha=0.05,
                  label="tiny debug workload"),
+    # BASELINE.json configs[3]: the whole genome after filtering, chromosome-sharded (strong scaling)
+    "c4": dict(genome=True, N=300_000_000, n=100, extra=3, B=1000, alpha=1e-6,
+               label="synthetic whole genome (24 chromosomes, 300M kept bases) 100 samples, 3 adjustment covariates, "
+                     "1000 permutations, chromosomes bin-packed over the GPUs"),
+    "c4s": dict(chr_len=10_000_000, N=1_000_000, n=100, extra=3, B=1000, alpha=1e-6,
+                label="scaled slice of the whole-genome config (N=1M kept bases) 100 samples, 3 adjustment covariates, 1000 permutations"),
+    "g_tiny": dict(genome=True, N=3_000_000, n=12, extra=0, B=20, alpha=0.05, label="tiny genome-mode debug workload"),
 }
+
+# hg19 chromosome lengths (tests/testthat/test_data.R:199 uses chr1's)
+HG19 = {"chr1": 249250621, "chr2": 243199373, "chr3": 198022430, "chr4": 191154276, "chr5": 180915260,
+        "chr6": 171115067, "chr7": 159138663, "chr8": 146364022, "chr9": 141213431, "chr10": 135534747,
+        "chr11": 135006516, "chr12": 133851895, "chr13": 115169878, "chr14": 107349540, "chr15": 102531392,
+        "chr16": 90354753, "chr17": 81195210, "chr18": 78077248, "chr19": 59128983, "chr20": 63025520,
+        "chr21": 48129895, "chr22": 51304566, "chrX": 155270560, "chrY": 59373566}
+
+
+def genome_chromosomes(cfg):
+    """Per-chromosome configs of a genome workload: kept bases proportional to the chromosome length."""
+    total = float(sum(HG19.values()))
+    out = {}
+    for name, length in HG19.items():
+        c = dict(cfg)
+        c.pop("genome")
+        c["chr_len"] = length
+        c["N"] = int(round(cfg["N"] * length / total / 64.0)) * 64
+        out[name] = c
+    return out
 
 
 # ---------------------------------------------------------------------------------------------
@@ -351,8 +376,8 @@ class Step:
                                                    L.ptr(self.perm, C.c_int32), self.perm.shape[0], -self.cut, self.cut,
                                                    0, 3000, C.byref(rh), C.byref(nh), None))
             out = (int(lib.dfb_regions_count(rh)) if rc == 0 else 0, int(lib.dfb_nulls_count(nh)) if rc == 0 else 0)
-            if keep and rc == 0:
-                return out, rh, nh, cov
+            if keep:  # no observed regions: the chromosome takes part in the pooling with NULL handles
+                return (out, rh, nh, cov) if rc == 0 else (out, None, None, cov)
             if rc == 0:
                 lib.dfb_regions_free(rh)
                 lib.dfb_nulls_free(nh)
@@ -485,39 +510,76 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     W = max(args.warmup, 3)
 
-    # every rank owns its own synthetic chromosome (same shape): weak scaling
-    data_rank = rank if args.as_rank is None else args.as_rank
-    work = make_workload(cfg, 20140923 + 2 + 1000 * data_rank, torch=torch, device=device)
-    n, N, B = cfg["n"], cfg["N"], cfg["B"]
-    perm = permutation_indices(range(1, B + 1), n, "Rejection")  # same relabellings on every rank
-    cut = theoretical_cutoff(cfg["alpha"], work["mod"], work["mod0"])
     eng = dfb.Engine(local, stream=torch.cuda.current_stream().cuda_stream)
     if args.screen is not None:
         eng.set_option("screen", args.screen)
     for kv in args.opt:
         key, val = kv.split("=")
         eng.set_option(key, float(val))
-    step = Step(eng, work, perm, cut, torch)
+    if world > 1:
+        pool.init_communicator(eng, dist, device)  # the library's own NCCL communicator (id via the process group)
+    genome = bool(cfg.get("genome"))
+    n, B = cfg["n"], cfg["B"]
+    perm = permutation_indices(range(1, B + 1), n, "Rejection")  # same relabellings on every rank
+    if genome:
+        # strong scaling: the 24 chromosomes of one genome, longest first onto the least loaded rank
+        chr_cfg = genome_chromosomes(cfg)
+        mine = pool.assign_chromosomes({k: v["N"] for k, v in chr_cfg.items()}, world)[rank]
+        need_gb = sum(chr_cfg[k]["N"] for k in mine) * n * 4e-9 + max(chr_cfg[k]["N"] for k in chr_cfg) * n * 16e-9
+        if need_gb > 150:
+            raise SystemExit("workload %s needs %.0f GB on this rank: run it on more GPUs" % (args.workload, need_gb))
+        steps_obj = []
+        for k in mine:
+            w = make_workload(chr_cfg[k], 20140923 + 4 + 7919 * list(HG19).index(k), torch=torch, device=device)
+            steps_obj.append((k, w))
+        # one design for the whole genome (the samples are the same on every chromosome)
+        gm = make_workload(dict(chr_cfg["chr21"], N=64000, chr_len=640000), 20140923 + 4)
+        cut = theoretical_cutoff(cfg["alpha"], gm["mod"], gm["mod0"])
+        chroms = []
+        for k, w in steps_obj:
+            w["mod"], w["mod0"] = gm["mod"], gm["mod0"]
+            chroms.append(Step(eng, w, perm, cut, torch))
+        N = sum(chr_cfg[k]["N"] for k in chr_cfg)  # units of the whole job
+        N_mine = sum(chr_cfg[k]["N"] for k in mine)
+        work = gm
+    else:
+        # every rank owns its own synthetic chromosome (same shape): weak scaling
+        data_rank = rank if args.as_rank is None else args.as_rank
+        work = make_workload(cfg, 20140923 + 2 + 1000 * data_rank, torch=torch, device=device)
+        N = cfg["N"]
+        N_mine = N
+        cut = theoretical_cutoff(cfg["alpha"], work["mod"], work["mod0"])
+        chroms = [Step(eng, work, perm, cut, torch)]
+        mine = ["chr"]
+    step = chroms[0]
     step.sync_f = args.e2e_sync_f
+    pooled = world > 1 or args.force_pool or genome
 
-    timed_pass = None  # per-step events around this rank's own chromosome pass (timed region only)
+    timed_pass = None  # per-step events around this rank's own chromosome passes (timed region only)
 
     def one_step():
-        if world > 1 or args.force_pool:
-            if timed_pass is not None:
-                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                e0.record()
-            (R, M), rh, nh, cov = step.device_pass(keep=True)
-            if timed_pass is not None:
-                e1.record()
-                timed_pass.append((e0, e1))
-            p_dev, fwer, npool = pool.genomewide_pvalues(eng, rh, nh, B, cut, torch, device, dist=dist,
-                                                             merge_area=True)
-            eng.lib.dfb_regions_free(rh)
-            eng.lib.dfb_nulls_free(nh)
+        if not pooled:
+            return step.device_pass()
+        if timed_pass is not None:
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+        kept, Rs, Ms = [], 0, 0
+        for st in chroms:
+            (R_c, M_c), rh, nh, cov = st.device_pass(keep=True)
+            kept.append((rh, nh, cov))
+            Rs += R_c
+            Ms += M_c
+        if timed_pass is not None:
+            e1.record()
+            timed_pass.append((e0, e1))
+        # mergeResults over all GPUs: ONE library call, once per rank after its last chromosome
+        pool.merge_results(eng, [(rh, nh) for rh, nh, _ in kept], B, cut, merge_area=True)
+        for rh, nh, cov in kept:
+            if rh is not None:
+                eng.lib.dfb_regions_free(rh)
+                eng.lib.dfb_nulls_free(nh)
             eng.lib.dfb_cov_free(cov)
-            return R, M
-        return step.device_pass()
+        return Rs, Ms
 
     for _ in range(W):
         R, M = one_step()
@@ -530,7 +592,6 @@ def main():
     # do not sit inside the measurement
     if not os.environ.get("BENCH_NO_KTIMER"):
         eng.enable_timing(families=[L.K_FSTAT_TC])
-    pool.reset_profile()
     sampler = ClockSampler(local)
     if not os.environ.get("BENCH_NO_SAMPLER"):
         sampler.start()
@@ -547,9 +608,6 @@ def main():
     torch.cuda.synchronize()
     own_ms = sum(a.elapsed_time(b) for a, b in timed_pass) / max(len(timed_pass), 1)
     timed_pass = None
-    pool_prof = pool.profile_summary()
-    pool.reset_profile()
-    os.environ.pop("DFB_POOL_PROFILE", None)
     sampler.stop_flag = True
     if sampler.is_alive():
         sampler.join()
@@ -560,7 +618,7 @@ def main():
     kt = {L.K_FSTAT_TC: eng.kernel_time(L.K_FSTAT_TC)}
     eng.enable_timing(False)
     # breakdown pass (not part of `value`): every family bracketed, a few steps
-    prof_steps = max(3, min(10, args.steps))
+    prof_steps = max(2, min(10, args.steps)) if not genome else 1
     eng.reset_counters()
     eng.enable_timing(True)
     for _ in range(prof_steps):
@@ -570,6 +628,7 @@ def main():
         t_ms, t_l = eng.kernel_time(k)
         kt[k] = (t_ms * args.steps / prof_steps, t_l * args.steps / prof_steps)
     eng.enable_timing(False)
+    own_all = [own_ms]
     if world > 1:
         t = torch.tensor([ms], device=device, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -583,6 +642,8 @@ def main():
     # end to end through host buffers (pinned), same pass
     h2d = d2h = 0
     e2e_s = float("nan")
+    if genome:
+        args.no_e2e = True  # the genome workload is the strong-scaling arm; the host-buffer pass is measured on c3
     if not args.no_e2e:
         host_cov = torch.empty((n, N), dtype=torch.int32, pin_memory=True)
         host_cov.copy_(work["cov"])
@@ -608,16 +669,19 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
 
-    units = float(N) * (B + 1) * world
+    units = float(N) * (B + 1) * (1 if genome else world)  # a genome is one fixed job; else one chromosome per rank
     value = units / (ms * 1e-3)
     line = {"metric": "base_x_permutation_fstats_per_sec", "value": value, "unit": "base*perm F-stats/s",
             "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "scaling": "strong" if genome else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": cfg["label"], "N": N, "n": n, "p": int(work["mod"].shape[1]),
-                       "p0": int(work["mod0"].shape[1]), "B": B, "f_cutoff": cut, "sharding": "chromosome per GPU",
-                       "l2": "inputs larger than L2 (coverage %.0f MB + log2 matrix %.0f MB per step; no flush)"
-                             % (4e-6 * n * N, 8e-6 * n * N),
-                       "regions": R, "null_regions": M},
+                       "p0": int(work["mod0"].shape[1]), "B": B, "f_cutoff": cut,
+                       "sharding": ("24 chromosomes bin-packed over the GPUs (longest first), mergeResults pooling once "
+                                    "per step" if genome else "one chromosome per GPU, mergeResults pooling once per step"
+                                    if world > 1 else "single GPU"),
+                       "l2": "inputs larger than L2 (coverage %.0f MB + log2 matrix %.0f MB per rank and step; no flush)"
+                             % (4e-6 * n * N_mine, 8e-6 * n * N_mine),
+                       "regions_rank0": R, "null_regions_rank0": M},
             "gpu_launches": int(launches),
             "e2e": {"value": units / e2e_s, "unit": "base*perm F-stats/s", "h2d_bytes_per_step": int(h2d),
                     "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3,
@@ -630,11 +694,10 @@ def main():
         # and what the genome-wide pooling (two all-gathers + ranking) adds on top of it
         line["multi_gpu"] = {"chromosome_pass_ms_per_rank": own_all,
                              "pooling_ms": round(ms - max(own_all), 4),
-                             "collectives": "NCCL all-gather of the records {counts, per-permutation max null area, "
-                                            "this rank's region areas} + all-reduce(sum) of the null histogram "
-                                            "over the merged region list; the null lists stay on their GPU"}
-        if pool_prof and rank == 0:
-            print("pool sections (ms):", pool_prof, file=sys.stderr)
+                             "collectives": "dfb_merge_results on the library's NCCL communicator: all-gather of "
+                                            "{region and null counts}, all-gather of the records {per-permutation max "
+                                            "null area, this rank's region areas}, all-reduce(sum) of the null "
+                                            "histogram over the merged region list; the null lists stay on their GPU"}
     if rank == 0:
         peaks = {}
         try:
@@ -648,11 +711,11 @@ def main():
         fst_ms, fst_l = kt[L.K_FSTAT]
         tc_ms, tc_l = kt[L.K_FSTAT_TC]
         k2_ms = tc_ms / args.steps
-        flops = 2.0 * N * n * p * B
+        flops = 2.0 * N_mine * n * p * B  # what rank 0's own K2 launches (the timed ones) computed
         achieved = flops / (k2_ms * 1e-3) / 1e12 if k2_ms > 0 else None
         peak = peaks.get("bf16_tflops", 1590.0)
         hbm = peaks.get("hbm_gbs", 6650.0)
-        alg_bytes = 8.0 * N * n  # read Y once (SURVEY 8d lower bound for the null scan)
+        alg_bytes = 8.0 * N_mine * n  # read Y once (SURVEY 8d lower bound for the null scan)
         # DRAM traffic per step of the K2 launches: from the committed summary of an `ncu --set full` capture of
         # this same command (profiles/k2_traffic.json, written by tools/ncu_summary.py), else null
         traffic, traffic_src = None, None
@@ -687,7 +750,7 @@ def main():
                                                    "events on the engine's stream inside the timed region",
                                       "hbm_equivalent_GBps": alg_bytes / (k2_ms * 1e-3) / 1e9 if k2_ms > 0 else None,
                                       "hbm_equivalent_frac": (alg_bytes / (k2_ms * 1e-3) / 1e9 / hbm) if k2_ms > 0 else None,
-                                      "base_x_perm_per_s_kernel_only": N * float(B) / (k2_ms * 1e-3) if k2_ms > 0 else None,
+                                      "base_x_perm_per_s_kernel_only": N_mine * float(B) / (k2_ms * 1e-3) if k2_ms > 0 else None,
                                       "other_kernels": "timed in a separate pass of %d steps with every launch "
                                                        "bracketed (not inside the timed region); " % prof_steps +
                                                        "regions / pval include the observed-region chain, which runs on "
@@ -698,7 +761,7 @@ def main():
                                                           "prep": kt[L.K_PREP][0] / args.steps,
                                                           "regions": kt[L.K_REGIONS][0] / args.steps,
                                                           "pval": kt[L.K_PVAL][0] / args.steps}}
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and not genome:
             from oracle import c_oracle
             c_oracle.build()
             nb, npm = min(N, args.cpu_bases), min(B, args.cpu_perms)

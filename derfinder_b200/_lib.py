@@ -81,6 +81,14 @@ SIGNATURES = {
     "dfb_regions_get": (C.c_int, [C.c_void_p, c_i32p, c_i32p, c_f64p, c_f64p, c_i32p, c_i32p, c_i32p, c_f64p]),
     "dfb_regions_view_means": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_f64p]),
     "dfb_regions_view_means_host": (C.c_int, [C.c_void_p, C.c_void_p, c_f64p, C.c_int64, c_f64p]),
+    "dfb_comm_unique_id": (C.c_int, [C.c_void_p]),
+    "dfb_comm_init_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "dfb_comm_init_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),
+    "dfb_comm_destroy": (None, [C.c_void_p]),
+    "dfb_comm_info": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "dfb_merge_results": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int64,
+                                    C.c_double, C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
+                                    C.POINTER(C.c_int64)]),
     "dfb_cluster_maker": (C.c_int64, [c_i32p, C.c_int64, C.c_int, C.c_int32, c_i64p, c_i64p, c_i64p, C.c_int64]),
     "dfb_perm_nulls": (C.c_int, [C.c_void_p, C.c_void_p, c_f64p, C.c_int, c_f64p, C.c_int, C.c_double, c_i32p,
                                  C.c_int64, C.c_double, C.c_double, C.c_int32, c_vpp]),

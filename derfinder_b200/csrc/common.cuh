@@ -142,6 +142,9 @@ struct dfb_ctx {
         bool active = false;
         int rc = 0;
     } bg;
+    // multi-GPU exchange (comm.cu): NCCL communicator of this context's rank, null for a single GPU
+    void* nccl_comm = nullptr;
+    int world = 1, rank = 0;
     // log2(k + scalefac) table for integer coverage (glibc log2, built once per scalefac)
     double* lut_dev = nullptr;
     int64_t lut_n = 0;
@@ -282,6 +285,10 @@ int d2h_dup_multi(dfb_ctx* ctx, int na, void* const* dsts, const void* const* sr
 // device-wide exclusive scan of `n` uint32 counts into int64 offsets; total_dev[0] = sum.
 int exclusive_scan_u32(dfb_ctx* ctx, const uint32_t* in, int64_t* out, int64_t n, int64_t* total_dev,
                        int kernel_family);
+
+// comm.cu: collectives on the context's stream (copies / no-ops for a single GPU)
+int comm_all_gather(dfb_ctx* ctx, const void* send, void* recv, size_t count, int dtype_bytes);
+int comm_all_reduce_sum_u64(dfb_ctx* ctx, void* buf, size_t count);
 
 static inline int grid_for(int64_t work_items, int threads, int sm_count, int max_waves = 32) {
     int64_t blocks = ceil_div(work_items, threads);

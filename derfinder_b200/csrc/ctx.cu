@@ -645,6 +645,7 @@ void dfb_destroy(dfb_ctx* c) {
     if (!c) return;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    dfb_comm_destroy(c);
     for (auto& e : c->evs) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);

@@ -795,6 +795,164 @@ int dfb_pool_rank_dev(dfb_ctx* ctx, const dfb_regions* r, const double* records_
     return DFB_OK;
 }
 
+// scatter of the pooled results from the rank's merged (decreasing-area) order back to chromosome order
+__global__ void merge_scatter_kernel(const double* __restrict__ p_sorted, const double* __restrict__ f_sorted,
+                                     const int32_t* __restrict__ payload, int64_t R, double* __restrict__ p_cat,
+                                     double* __restrict__ f_cat) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= R) return;
+    p_cat[payload[i]] = p_sorted[i];
+    f_cat[payload[i]] = f_sorted[i];
+}
+
+__global__ void merge_header_kernel(double* __restrict__ rec, double R, double M) {
+    rec[0] = R;
+    rec[1] = M;
+}
+
+int dfb_merge_results(dfb_ctx* ctx, int nchr, dfb_regions* const* r, dfb_nulls* const* nl, int64_t B,
+                      double cutoff_used, int merge_area, double* const* pvalues, double* const* fwer,
+                      int64_t* total_nulls) {
+    DFB_REQUIRE(ctx && nchr >= 0 && (nchr == 0 || (r && nl)) && B >= 1, "dfb_merge_results: bad argument");
+    arena_reset(ctx);
+    const int world = ctx->world, rank = ctx->rank;
+    // ---- this rank's chromosomes: regions concatenated (each list is already in decreasing-area order)
+    std::vector<int64_t> roff((size_t)nchr + 1, 0);
+    int64_t M_loc = 0;
+    for (int c = 0; c < nchr; ++c) {
+        DFB_REQUIRE((r[c] == nullptr) == (nl[c] == nullptr), "dfb_merge_results: chromosome %d has only one of regions / nulls", c);
+        const int64_t Rc = r[c] ? r[c]->R : 0;
+        if (Rc > 0 && !r[c]->d_area_desc.p) {
+            set_error("dfb_merge_results: chromosome %d was not produced by dfb_calculate_pvalues", c);
+            return DFB_ESTATE;
+        }
+        roff[(size_t)c + 1] = roff[(size_t)c] + Rc;
+        if (nl[c]) {
+            DFB_REQUIRE(nl[c]->B == B, "dfb_merge_results: chromosome %d was analysed with %lld permutations, not %lld", c,
+                        (long long)nl[c]->B, (long long)B);
+            M_loc += nl[c]->count;
+        }
+    }
+    const int64_t R_loc = roff[(size_t)nchr];
+    DFB_REQUIRE(R_loc < INT32_MAX, "dfb_merge_results: too many regions on one rank");
+    // ---- every rank learns every rank's counts (the one host synchronisation of the exchange)
+    DevBuf<int64_t> cnt_d;
+    DFB_TRY(cnt_d.alloc(ctx, (size_t)2 * (world + 1)));
+    const int64_t mine[2] = {R_loc, M_loc};
+    DFB_TRY(h2d(ctx, cnt_d.p + 2 * world, mine, sizeof mine));
+    DFB_TRY(comm_all_gather(ctx, cnt_d.p + 2 * world, cnt_d.p, 2, sizeof(int64_t)));
+    std::vector<int64_t> cnt((size_t)2 * world);
+    DFB_TRY(d2h(ctx, cnt.data(), cnt_d.p, cnt.size() * sizeof(int64_t)));
+    int64_t rcap = 1, M_tot = 0;
+    for (int w = 0; w < world; ++w) {
+        rcap = std::max(rcap, cnt[(size_t)2 * w]);
+        M_tot += cnt[(size_t)2 * w + 1];
+    }
+    if (total_nulls) *total_nulls = M_tot;
+    const int64_t n = (int64_t)world * rcap;
+    DFB_REQUIRE(n < INT32_MAX, "dfb_merge_results: %lld pooled regions exceed the 32-bit index", (long long)n);
+    // ---- local merged list (sort of the concatenation; payload = position in the concatenation)
+    DevBuf<double> cat, desc;
+    DevBuf<int32_t> payload;
+    DFB_TRY(cat.alloc(ctx, (size_t)std::max<int64_t>(R_loc, 1)));
+    DFB_TRY(desc.alloc(ctx, (size_t)std::max<int64_t>(R_loc, 1)));
+    DFB_TRY(payload.alloc(ctx, (size_t)std::max<int64_t>(R_loc, 1)));
+    for (int c = 0; c < nchr; ++c)
+        if (r[c] && r[c]->R > 0)
+            DFB_CUDA(cudaMemcpyAsync(cat.p + roff[(size_t)c], r[c]->d_area_desc.p, (size_t)r[c]->R * 8, cudaMemcpyDeviceToDevice,
+                                     ctx->stream));
+    if (R_loc > 0) DFB_TRY(order_desc(ctx, cat.p, R_loc, payload.p, desc.p));
+    // ---- record {R, M, per-permutation max null area (-1: none), region areas desc padded with -1}
+    const int64_t stride = 2 + B + rcap;
+    DevBuf<double> recs;
+    DFB_TRY(recs.alloc(ctx, (size_t)(world + 1) * stride));
+    double* rec = recs.p + (size_t)world * stride;
+    {
+        KTimer t(ctx, DFB_K_PVAL);
+        pool_record_kernel<<<grid_for(rcap, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(desc.p, R_loc, M_loc, rcap, B, rec);
+    }
+    {
+        DevBuf<unsigned long long> bits;
+        DFB_TRY(bits.alloc(ctx, (size_t)B));
+        DFB_TRY(bits.zero());
+        KTimer t(ctx, DFB_K_PVAL, nchr + 1);
+        for (int c = 0; c < nchr; ++c) {
+            if (!nl[c] || nl[c]->count == 0) continue;
+            const double* areas = nullptr;
+            DFB_TRY(pooled_null_areas(ctx, nl[c], merge_area, &areas));
+            perm_max_kernel<<<(unsigned)ceil_div(nl[c]->count, 256), 256, 0, ctx->stream>>>(areas, nl[c]->perm.p, nl[c]->count,
+                                                                                           B, bits.p);
+        }
+        perm_max_decode_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, ctx->stream>>>(bits.p, B, -1.0, rec + 2);
+        DFB_CUDA(cudaGetLastError());
+    }
+    DFB_TRY(comm_all_gather(ctx, rec, recs.p, (size_t)stride, sizeof(double)));
+    // ---- merged region list of all ranks, histogram of this rank's nulls over it, summed over the ranks
+    DevBuf<double> merged;
+    DevBuf<int32_t> src;
+    DevBuf<unsigned long long> hist, incl;
+    DFB_TRY(merged.alloc(ctx, (size_t)n));
+    DFB_TRY(src.alloc(ctx, (size_t)n));
+    DFB_TRY(hist.alloc(ctx, (size_t)n + 1));
+    DFB_TRY(incl.alloc(ctx, (size_t)n));
+    DFB_TRY(hist.zero());
+    {
+        KTimer t(ctx, DFB_K_PVAL);
+        pool_merge_kernel<<<grid_for(n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(recs.p, stride, 2 + B, rcap, world,
+                                                                                    merged.p, src.p);
+    }
+    for (int c = 0; c < nchr; ++c) {
+        if (!nl[c] || nl[c]->count == 0) continue;
+        const double* areas = nullptr;
+        DFB_TRY(pooled_null_areas(ctx, nl[c], merge_area, &areas));
+        KTimer t(ctx, DFB_K_PVAL);
+        null_hist64_kernel<<<grid_for(nl[c]->count, 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(areas, nl[c]->count,
+                                                                                                merged.p, n, hist.p);
+    }
+    DFB_CUDA(cudaGetLastError());
+    DFB_TRY(comm_all_reduce_sum_u64(ctx, hist.p, (size_t)n + 1));
+    // ---- pooled p-values and FWER of this rank's regions
+    if (R_loc > 0) {
+        DevBuf<double> gmax, p_s, f_s, p_cat, f_cat;
+        DevBuf<unsigned char> tmp;
+        DFB_TRY(gmax.alloc(ctx, (size_t)B));
+        DFB_TRY(p_s.alloc(ctx, (size_t)R_loc));
+        DFB_TRY(f_s.alloc(ctx, (size_t)R_loc));
+        DFB_TRY(p_cat.alloc(ctx, (size_t)R_loc));
+        DFB_TRY(f_cat.alloc(ctx, (size_t)R_loc));
+        size_t tmp_bytes = 0;
+        DFB_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tmp_bytes, hist.p, incl.p, n, ctx->stream));
+        DFB_TRY(tmp.alloc(ctx, tmp_bytes));
+        {
+            KTimer t(ctx, DFB_K_PVAL, 5);
+            DFB_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tmp_bytes, hist.p, incl.p, n, ctx->stream));
+            pool_gmax_kernel<<<(unsigned)ceil_div(B, 256), 256, 0, ctx->stream>>>(recs.p, stride, world, B, cutoff_used, gmax.p);
+            pool_rank_kernel<<<(unsigned)ceil_div(n, 256), 256, 0, ctx->stream>>>(incl.p, merged.p, src.p, n, rcap, rank, R_loc,
+                                                                                nullptr, recs.p, stride, world, gmax.p, B,
+                                                                                p_s.p, f_s.p);
+            merge_scatter_kernel<<<(unsigned)ceil_div(R_loc, 256), 256, 0, ctx->stream>>>(p_s.p, f_s.p, payload.p, R_loc,
+                                                                                         p_cat.p, f_cat.p);
+        }
+        DFB_CUDA(cudaGetLastError());
+        const double* hp = (pvalues) ? d2h_async_pinned(ctx, p_cat.p, (size_t)R_loc) : nullptr;
+        const double* hf = (fwer) ? d2h_async_pinned(ctx, f_cat.p, (size_t)R_loc) : nullptr;
+        DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+        DFB_REQUIRE((!pvalues || hp) && (!fwer || hf), "dfb_merge_results: read-back failed");
+        for (int c = 0; c < nchr; ++c) {
+            const int64_t Rc = roff[(size_t)c + 1] - roff[(size_t)c];
+            if (Rc == 0) continue;
+            if (pvalues && pvalues[c]) {
+                if (M_tot > 0) memcpy(pvalues[c], hp + roff[(size_t)c], (size_t)Rc * 8);
+                else for (int64_t i = 0; i < Rc; ++i) pvalues[c][i] = nan("");  // no nulls anywhere: NA (:408-419)
+            }
+            if (fwer && fwer[c]) memcpy(fwer[c], hf + roff[(size_t)c], (size_t)Rc * 8);
+        }
+    } else {
+        DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return DFB_OK;
+}
+
 int dfb_nulls_sorted_areas_dev(dfb_ctx* ctx, dfb_nulls* nl, double* out_dev) {
     DFB_REQUIRE(ctx && nl && (out_dev || nl->count == 0), "dfb_nulls_sorted_areas_dev: NULL argument");
     const size_t M = (size_t)nl->count;

@@ -184,6 +184,61 @@ def genomewide_pvalues(engine, regions_handle, nulls_handle, B, cutoff_used, tor
     return p_dev[:R], fwer[:R], int(head[:, 1].sum().item())
 
 
+# ---------------------------------------------------------------------------------------------
+# one-call mergeResults on the library's own NCCL communicator (no torch on the data path)
+
+
+def init_communicator(engine, dist=None, device=None):
+    """Give `engine` its rank in the job's NCCL communicator.  The library creates the communicator
+    itself (dfb_comm_unique_id on rank 0, dfb_comm_init_rank everywhere); the process group is only the
+    courier of the 128-byte id -- any host-side channel would do (the R glue uses a file)."""
+    import numpy as np
+    from . import _lib as L
+    if dist is None:
+        import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return 1, 0
+    import torch
+    world, rank = dist.get_world_size(), dist.get_rank()
+    buf = (C.c_ubyte * 128)()
+    if rank == 0:
+        L.check(engine.lib.dfb_comm_unique_id(buf))
+    t = torch.tensor(list(bytes(buf)), dtype=torch.uint8)
+    if dist.get_backend() == "nccl":
+        t = t.to(device if device is not None else torch.device("cuda", engine.device))
+    dist.broadcast(t, 0)
+    raw = bytes(np.asarray(t.cpu().numpy(), dtype=np.uint8).tobytes())
+    idb = (C.c_ubyte * 128).from_buffer_copy(raw)
+    L.check(engine.lib.dfb_comm_init_rank(engine.h, world, rank, idb))
+    return world, rank
+
+
+def merge_results(engine, chromosomes, B, cutoff_used, merge_area=True, want=True):
+    """mergeResults() for the chromosomes this rank holds (R/mergeResults.R:216-235, 300-307, 380-386) as
+    ONE library call; collective over the engine's communicator.  `chromosomes`: list of
+    (regions_handle, nulls_handle), (None, None) for a chromosome without observed regions.  Returns
+    ([(pvalues, fwer) per chromosome, regions in decreasing-area order], genome-wide null count)."""
+    import numpy as np
+    from . import _lib as L
+    lib = engine.lib
+    k = len(chromosomes)
+    rp = (C.c_void_p * max(k, 1))(*[(rh.value if isinstance(rh, C.c_void_p) else rh) for rh, _ in chromosomes])
+    npp = (C.c_void_p * max(k, 1))(*[(nh.value if isinstance(nh, C.c_void_p) else nh) for _, nh in chromosomes])
+    outs = []
+    pp = (C.c_void_p * max(k, 1))()
+    fp = (C.c_void_p * max(k, 1))()
+    for c, (rh, _) in enumerate(chromosomes):
+        R = int(lib.dfb_regions_count(rh)) if rh else 0
+        pv, fw = np.empty(R), np.empty(R)
+        outs.append((pv, fw))
+        pp[c] = pv.ctypes.data if (want and R) else None
+        fp[c] = fw.ctypes.data if (want and R) else None
+    total = C.c_int64()
+    L.check(lib.dfb_merge_results(engine.h, k, rp, npp, int(B), float(cutoff_used), 1 if merge_area else 0, pp, fp,
+                                  C.byref(total)))
+    return outs, int(total.value)
+
+
 def reset_profile():
     PROFILE["calls"] = 0
     PROFILE["events"].clear()

@@ -280,6 +280,30 @@ int dfb_pool_rank_dev(dfb_ctx* ctx, const dfb_regions* r, const double* records_
  * not bit-identical to the summed area calculatePvalues ranks; written to device memory [count] */
 int dfb_nulls_merge_areas_dev(const dfb_nulls* nl, double* area_dev);
 
+/* ---------------------------------------------------------------- mergeResults -------------- */
+
+/* One-call genome-wide pass of mergeResults() -- R/mergeResults.R:216-235 (pool the null regions of every
+ * chromosome, area = abs(stat) * width when merge_area != 0, :231), :300-307 (.calcPval of every region
+ * against the pool) and :380-386 (.calculateFWER: per-permutation maximum over the genome, an empty
+ * permutation counts as cutoff_used) -- across all GPUs of the job.  Every rank passes the results of the
+ * chromosomes IT holds (nchr >= 0; a chromosome without observed regions passes r[c] = nl[c] = NULL, see
+ * R/calculatePvalues.R:245-251); the ranks exchange their region areas and per-permutation maxima
+ * (all-gather) and the histogram of their nulls over the merged region list (all-reduce) on the context's
+ * communicator -- the null lists never leave their GPU.  Outputs, per chromosome c, in the order of
+ * dfb_regions_get (decreasing area): pvalues[c][R_c], fwer[c][R_c] (host; either array of pointers may be
+ * NULL); *total_nulls = number of distinct null regions in the genome-wide pool.  Collective: every rank of
+ * the communicator must call it (with the same B, cutoff_used and merge_area).  A context without a
+ * communicator pools its own chromosomes only. */
+#define DFB_COMM_ID_BYTES 128
+int dfb_comm_unique_id(void* id_out /* DFB_COMM_ID_BYTES */);
+int dfb_comm_init_rank(dfb_ctx* ctx, int world, int rank, const void* id /* DFB_COMM_ID_BYTES */);
+int dfb_comm_init_all(dfb_ctx* const* ctxs, int ngpu); /* one process, one context per GPU */
+void dfb_comm_destroy(dfb_ctx* ctx);
+int dfb_comm_info(const dfb_ctx* ctx, int* world, int* rank);
+int dfb_merge_results(dfb_ctx* ctx, int nchr, dfb_regions* const* r, dfb_nulls* const* nl, int64_t B,
+                      double cutoff_used, int merge_area, double* const* pvalues, double* const* fwer,
+                      int64_t* total_nulls);
+
 /* Multi-GPU pooling without a second sort (R/mergeResults.R:216-235, 304-307): every rank keeps its
  * null areas sorted from its own p-value ranking; ranks all-gather those sorted lists and count,
  * list by list, how many pooled nulls exceed each of their region areas:

@@ -309,3 +309,43 @@ def test_preprocess_colsubset_refreshes_mean(dfb, eng, golden):
         assert np.array_equal(r["mean" + g], O.view_sums(mine["groupMeans"][g], r["indexStart"], r["indexEnd"]) / w)
     assert np.array_equal(r["area"], base["regions"]["area"])
     assert not np.array_equal(r["meanCoverage"], base["regions"]["meanCoverage"])
+
+
+# ---------------------------------------------------------------------------------------------
+# dfb_merge_results: the one-call genome-wide pass (single rank here; tests/test_multi_gpu.py runs it over NCCL)
+
+
+@pytest.mark.parametrize("merge_area", [False, True])
+def test_merge_results_single_rank(dfb, eng, merge_area):
+    from derfinder_b200 import pool
+    rng = np.random.default_rng(909)
+    n, B = 14, 24
+    _, _, _, models = synth(rng, 2000, n, p_extra=1)
+    perm = random_perms(rng, B, n)
+    perm[5] = perm[4]
+    cut = dfb.calcFstatCutoff("theoretical", 0.05, models=models)
+    sizes = [9000, 2500, 6000, 4000]
+    chroms = [_chromosome_result(dfb, eng, rng, sizes[c], n, models, perm, 1e12 if c == 1 else cut) for c in range(4)]
+    try:
+        info = [None if rh is None else _fetch(eng, rh, nh) for _, rh, nh in chroms]
+        assert info[1] is None
+        key = (lambda i: np.abs(i["nstat"]) * i["nwidth"]) if merge_area else (lambda i: i["narea"])
+        pool_area = np.concatenate([key(i) for i in info if i is not None])
+        pool_perm = np.concatenate([i["nperm"] for i in info if i is not None])
+        outs, total = pool.merge_results(eng, [(rh, nh) for _, rh, nh in chroms], B, cut, merge_area=merge_area)
+        assert total == len(pool_area)
+        for c, i in enumerate(info):
+            if i is None:
+                assert len(outs[c][0]) == 0
+                continue
+            assert np.array_equal(outs[c][0], O.calc_pval(i["area"], np.repeat(pool_area, 2))), c
+            assert np.array_equal(outs[c][1], O.calculate_fwer(cut, pool_area, pool_perm, B, i["area"])), c
+        # nothing to pool at all
+        outs, total = pool.merge_results(eng, [], B, cut)
+        assert outs == [] and total == 0
+    finally:
+        for h, rh, nh in chroms:
+            if rh is not None:
+                eng.lib.dfb_regions_free(rh)
+                eng.lib.dfb_nulls_free(nh)
+            eng.lib.dfb_cov_free(h)
