@@ -29,14 +29,18 @@ filterData <- function(data, cutoff = NULL, index = NULL, filter = "one", totalM
     returnMean <- derfinder:::.advanced_argument("returnMean", FALSE, ...)
     returnCoverage <- derfinder:::.advanced_argument("returnCoverage", TRUE, ...)
     if (is.list(data) && !is(data, "DataFrame")) data <- S4Vectors::DataFrame(data, check.names = FALSE)
-    mapped <- if (!is.null(totalMapped)) { stopifnot(length(totalMapped) == ncol(data)); totalMapped / targetSize }
+    ## library-size normalisation only when asked for AND targetSize != 0 (:119); totalMapped is recycled over the
+    ## samples exactly like the reference's mapply(function(x, d) x / d, data, mappedPerXM) (:120-126)
+    mapped <- NULL
+    if (!is.null(totalMapped) && targetSize != 0) mapped <- rep_len(as.numeric(totalMapped) / targetSize, ncol(data))
     r <- .rle_lists(data)
     prev <- if (!is.null(index)) .lgl_runs(index)
     kind <- if (is.null(cutoff)) 0L else if (filter == "one") 1L else 2L
     h <- .Call(dfbR_filter, .engine(), r$values, r$lengths, nrow(data), mapped, kind,
                if (is.null(cutoff)) 0 else as.numeric(cutoff), prev$lengths, prev$first)
     res <- list(coverage = if (returnCoverage) .cov_dataframe(h, names(data)) else NULL,
-                position = .as_lgl_rle(.Call(dfbR_cov_position, h)))
+                ## cutoff = NULL: nothing is filtered and `position` is `index`, NULL included (:133-135)
+                position = if (is.null(cutoff)) index else .as_lgl_rle(.Call(dfbR_cov_position, h)))
     if (returnMean) res$meanCoverage <- S4Vectors::Rle(.Call(dfbR_cov_vector, h, 2L, 0L))
     attr(res, "dfb_cov") <- h      # device-resident copy: later stages skip the re-upload
     res
@@ -51,10 +55,12 @@ preprocessCoverage <- function(coverageInfo, groupInfo = NULL, cutoff = 5, colsu
     stopifnot(scalefac >= 0)
     if (is.null(coverageInfo$position)) stop("'position' must not be NULL")                # :163-165
     h <- attr(coverageInfo, "dfb_cov")
+    means <- coverageInfo$meanCoverage
     if (!is.null(colsubset)) {                                                             # :145-160
         sub <- filterData(coverageInfo$coverage[, colsubset, drop = FALSE], cutoff = cutoff,
-                          index = coverageInfo$position, ...)
+                          index = coverageInfo$position, returnMean = TRUE, ...)
         h <- attr(sub, "dfb_cov"); coverageInfo <- sub
+        means <- sub$meanCoverage            # the re-filtered mean replaces a pre-existing one (:157-159)
     } else if (is.null(h)) {
         r <- .rle_lists(coverageInfo$coverage); p <- .lgl_runs(coverageInfo$position)
         h <- .Call(dfbR_cov_from_rle, .engine(), r$values, r$lengths, nrow(coverageInfo$coverage), p$lengths, p$first)
@@ -69,10 +75,11 @@ preprocessCoverage <- function(coverageInfo, groupInfo = NULL, cutoff = 5, colsu
         coverageProcessed = if (is.null(lowMemDir)) .cov_dataframe(h, names(coverageInfo$coverage), 1L) else NULL,
         mclapplyIndex = if (is.null(lowMemDir)) lapply(seq_len(k), function(x) split.idx == x) else seq_len(k),
         position = coverageInfo$position,
-        meanCoverage = S4Vectors::Rle(.Call(dfbR_cov_vector, h, 2L, 0L)),
+        meanCoverage = if (is.null(means)) S4Vectors::Rle(.Call(dfbR_cov_vector, h, 2L, 0L)) else means,  # :191-193
         groupMeans = if (!is.null(groupInfo)) structure(lapply(seq_len(nlevels(groupInfo)) - 1L, function(g)
             S4Vectors::Rle(.Call(dfbR_cov_vector, h, 3L, g))), names = levels(groupInfo)) else list())
     attr(res, "dfb_cov") <- h
+    attr(res, "dfb_means") <- list(meanCoverage = res$meanCoverage, groupMeans = res$groupMeans)
     res
 }
 
@@ -107,16 +114,32 @@ calculateStats <- function(coveragePrep, models, lowMemDir = NULL, ...) {
 findRegions <- function(position = NULL, fstats, chr, oneTable = TRUE, maxClusterGap = 300L,
     cutoff = quantile(fstats, 0.99, na.rm = TRUE), segmentIR = NULL, smooth = FALSE, weights = NULL,
     smoothFunction = bumphunter::locfitByCluster, ...) {
-    if (smooth) stop("smooth = TRUE is not supported by the B200 engine")
     basic <- derfinder:::.advanced_argument("basic", FALSE, ...)
     maxRegionGap <- derfinder:::.advanced_argument("maxRegionGap", 0L, ...)
-    if (!basic) stopifnot(!is.null(position))                                            # :135-137
     if (maxClusterGap < maxRegionGap)
-        warning("'maxClusterGap' is less than 'maxRegionGap' which nullifies it's intended use.")
-    cp <- .cutoff_pair(as.numeric(cutoff)); p <- .lgl_runs(position)
+        warning("'maxClusterGap' is less than 'maxRegionGap' which nullifies it's intended use.")   # :137-139
+    if (!basic) {
+        if (is.null(segmentIR) | smooth) stopifnot(!is.null(position))                   # :141-144
+        if (smooth) stop("smooth = TRUE is not supported by the B200 engine")
+    } else if (smooth) warning("Ignoring 'smooth' = TRUE since 'basic' = TRUE")          # :152
+    if (is.null(segmentIR)) {
+        if (!any(position)) { warning("Found no regions"); return(NULL) }                # :163-166
+        p <- .lgl_runs(position); gap <- as.integer(maxRegionGap)
+    } else if (!is.null(position)) {
+        ## segmentIR is the cache of .clusterMakerRle(position, maxRegionGap, ranges = TRUE) (R/calculatePvalues.R:
+        ## 234-237): the engine derives the same segments from `position`; check that the two belong together
+        stopifnot(sum(IRanges::width(segmentIR)) == sum(position))
+        p <- .lgl_runs(position); gap <- as.integer(maxRegionGap)
+    } else {
+        ## basic = TRUE with the segments only (index space, :155-170): a position index whose TRUE runs ARE the
+        ## segments, one filtered-out base between neighbours
+        w <- IRanges::width(segmentIR); k <- length(w)
+        p <- list(lengths = as.integer(head(as.vector(rbind(w, 1L)), 2L * k - 1L)), first = TRUE); gap <- 0L
+    }
+    cp <- .cutoff_pair(as.numeric(cutoff))
     x <- .Call(dfbR_find_regions, .engine(), as.numeric(fstats), p$lengths, p$first, cp[1], cp[2],
-               as.integer(maxRegionGap), as.integer(maxClusterGap), basic)
-    if (is.null(x)) { warning("Found no regions. Consider changing the F-statistics cutoff, or increasing 'maxRegionGap' if you are smoothing."); return(NULL) }
+               gap, as.integer(maxClusterGap), basic)
+    if (is.null(x)) return(NULL)                                                         # no segments (:185-193)
     if (basic) return(S4Vectors::DataFrame(area = S4Vectors::Rle(x$area),
         width = S4Vectors::Rle(x$indexEnd - x$indexStart + 1L), stat = S4Vectors::Rle(x$value)))   # :274-278
     gr <- .regions_granges(x, chr)
@@ -147,9 +170,16 @@ calculatePvalues <- function(coveragePrep, models, fstats, nPermute = 1L,
     dim(perm) <- c(n, nPermute)
     cp <- .cutoff_pair(as.numeric(cutoff))
     cached <- identical(attr(fstats, "dfb_cov"), h)       # statistics still on the device: no re-upload
+    ## the reference summarises whatever meanCoverage / groupMeans vectors it is handed (:222-224, 253-262): the
+    ## device copies are used only for the very objects preprocessCoverage() returned for this handle
+    own <- attr(coveragePrep, "dfb_means")
+    meanv <- if (!is.null(own) && identical(own$meanCoverage, coveragePrep$meanCoverage)) NULL
+             else as.numeric(coveragePrep$meanCoverage)
+    groupv <- if (!is.null(own) && identical(own$groupMeans, coveragePrep$groupMeans)) NULL
+              else lapply(coveragePrep$groupMeans, as.numeric)
     x <- .Call(dfbR_calculate_pvalues, .engine(), h, if (cached) NULL else as.numeric(fstats), models$mod,
                models$mod0, adjustF, perm, cp[1], cp[2], as.integer(maxRegionGap), as.integer(maxClusterGap),
-               length(coveragePrep$groupMeans))
+               length(coveragePrep$groupMeans), meanv, groupv)
     if (is.null(x)) return(list(regions = NULL, nullStats = NULL, nullWidths = NULL, nullPermutation = NULL))  # :245-251
     regs <- .regions_granges(x$regions, chr)
     regs$meanCoverage <- x$meanCoverage                                                  # :254-255
@@ -166,19 +196,54 @@ calculatePvalues <- function(coveragePrep, models, fstats, nPermute = 1L,
     } else {
         regs$qvalues <- NA; regs$significantQval <- NA                                   # :408-419
     }
-    list(regions = regs, nullStats = S4Vectors::Rle(x$nullStats), nullWidths = S4Vectors::Rle(x$nullWidths),
-         nullPermutation = S4Vectors::Rle(x$nullPermutation))                            # :421-424
+    res <- list(regions = regs, nullStats = S4Vectors::Rle(x$nullStats), nullWidths = S4Vectors::Rle(x$nullWidths),
+                nullPermutation = S4Vectors::Rle(x$nullPermutation))                     # :421-424
+    ## device handles of this chromosome's regions and nulls: .mergeResultsGPU() pools them genome-wide
+    attr(res, "dfb_regions") <- x$handles$regions
+    attr(res, "dfb_nulls") <- x$handles$nulls
+    res
+}
+
+## ---- the genome-wide pass of mergeResults (R/mergeResults.R:216-235, 300-307, 380-386) for chromosomes analysed in
+## THIS R process (one or more GPUs-worth; with several processes, one per GPU, call .commInit() in each first):
+## pooled p-values and FWER per chromosome, regions in the order calculatePvalues() returned them
+.mergeResultsGPU <- function(chrResults, nPermute, cutoffFstatUsed, mergeArea = TRUE) {
+    rh <- lapply(chrResults, attr, "dfb_regions"); nh <- lapply(chrResults, attr, "dfb_nulls")
+    x <- .Call(dfbR_merge_results, .engine(), rh, nh, as.integer(nPermute), as.numeric(cutoffFstatUsed), isTRUE(mergeArea))
+    names(x$pvalues) <- names(x$fwer) <- names(chrResults)
+    x
+}
+## one process per GPU (e.g. one Rscript per device): rank 0 writes the 128-byte id to `idFile`, the others read it
+.commInit <- function(world, rank, idFile) {
+    if (rank == 0L) { id <- .Call(dfbR_comm_unique_id); writeBin(id, idFile) }
+    else { while (!file.exists(idFile) || file.size(idFile) < 128) Sys.sleep(0.05); id <- readBin(idFile, "raw", 128L) }
+    .Call(dfbR_comm_init_rank, .engine(), as.integer(world), as.integer(rank), id)
+    invisible(TRUE)
 }
 
 ## ---- regionMatrix per chromosome (R/regionMatrix.R:170-283), coverageMatrix only
-.regionMatrixByChr <- function(covInfo, chr, cutoff, L, totalMapped, targetSize, maxRegionGap = 0L, maxClusterGap = 300L) {
-    filt <- filterData(covInfo$coverage, cutoff = cutoff, filter = "mean", totalMapped = totalMapped,
-                       targetSize = targetSize, returnMean = TRUE, returnCoverage = FALSE)
+.regionMatrixByChr <- function(covInfo, chr, cutoff, L, totalMapped, targetSize, runFilter = TRUE, maxRegionGap = 0L,
+                               maxClusterGap = 300L) {
+    if (runFilter) {                                                                     # :193-212
+        filt <- filterData(covInfo$coverage, cutoff = cutoff, index = covInfo$position, filter = "mean",
+                           totalMapped = totalMapped, targetSize = targetSize, returnMean = TRUE, returnCoverage = FALSE)
+    } else {                                                                             # :213-228: already filtered
+        filt <- covInfo
+        if (is.null(attr(filt, "dfb_cov"))) {
+            r <- .rle_lists(filt$coverage); p <- .lgl_runs(filt$position)
+            attr(filt, "dfb_cov") <- .Call(dfbR_cov_from_rle, .engine(), r$values, r$lengths, nrow(filt$coverage),
+                                           p$lengths, p$first)
+        }
+    }
     h <- attr(filt, "dfb_cov")
     regs <- findRegions(position = filt$position, fstats = filt$meanCoverage, chr = chr, cutoff = cutoff,
                         maxRegionGap = maxRegionGap, maxClusterGap = maxClusterGap)
     if (is.null(regs)) return(list(regions = GenomicRanges::GRanges(), coverageMatrix = NULL))             # :230-239
-    m <- .Call(dfbR_region_matrix, .engine(), h, regs$indexStart, regs$indexEnd, as.numeric(L))
+    if (!(length(L) %in% c(1L, length(covInfo$coverage)))) {                                               # :254-258
+        warning("Invalid 'L' value so it won't be used. It has to either be a integer/numeric vector of length 1 or length equal to the number of samples.")
+        L <- NULL
+    }
+    m <- .Call(dfbR_region_matrix, .engine(), h, regs$indexStart, regs$indexEnd, if (is.null(L)) NULL else as.numeric(L))
     colnames(m) <- names(covInfo$coverage)
     list(regions = regs, coverageMatrix = m)
 }
@@ -189,13 +254,17 @@ calculatePvalues <- function(coveragePrep, models, fstats, nPermute = 1L,
 regionMatrix <- function(fullCov, cutoff = 5, L, totalMapped = 80e6, targetSize = 80e6, runFilter = TRUE,
     returnBP = TRUE, ...) {
     stopifnot(!is.null(cutoff), !is.null(names(fullCov)))                                 # :128-131
-    if (!runFilter) stop("runFilter = FALSE: pass the unfiltered coverage; the filter runs on the device")
+    if (!runFilter) {                                                                     # :133-146
+        if (any(totalMapped != targetSize)) stop("When using 'runFilter' = FALSE the arguments 'totalMapped' and 'targetSize' are not used. If you have not normalized the data, please do so before running regionMatrix(runFilter = FALSE).")
+        ok <- vapply(fullCov, function(x) is.list(x) && all(c("coverage", "position", "meanCoverage") %in% names(x)), logical(1))
+        if (!all(ok)) stop("When 'runFilter' = FALSE, all the elements of 'fullCov' are expected to be the output from filterData(..., returnMean=TRUE) with some non-NULL 'cutoff'.")
+    }
     maxRegionGap <- derfinder:::.advanced_argument("maxRegionGap", 0L, ...)
     maxClusterGap <- derfinder:::.advanced_argument("maxClusterGap", 300L, ...)
     res <- lapply(names(fullCov), function(chr) {
         covInfo <- fullCov[[chr]]
-        if (!is.list(covInfo) || is(covInfo, "DataFrame")) covInfo <- list(coverage = covInfo)
-        out <- .regionMatrixByChr(covInfo, chr, cutoff, L, totalMapped, targetSize, maxRegionGap, maxClusterGap)
+        if (!is.list(covInfo) || is(covInfo, "DataFrame")) covInfo <- list(coverage = covInfo, position = NULL)
+        out <- .regionMatrixByChr(covInfo, chr, cutoff, L, totalMapped, targetSize, runFilter, maxRegionGap, maxClusterGap)
         if (returnBP && length(out$regions) > 0)
             out$bpCoverage <- derfinder::getRegionCoverage(fullCov = fullCov[chr], regions = out$regions,
                 totalMapped = totalMapped, targetSize = targetSize, verbose = FALSE)
@@ -220,3 +289,94 @@ regionMatrix <- function(fullCov, cutoff = 5, L, totalMapped = 80e6, targetSize 
 .calculateFWER <- function(cutoffFstatUsed, areaNull, permutation, nPermute, areaReg)
     .Call(dfbR_calc_fwer, .engine(), cutoffFstatUsed, as.numeric(areaNull), as.integer(permutation),
           as.integer(nPermute), as.numeric(areaReg))
+
+
+## ---- railMatrix (R/railMatrix.R:115-175): ERs of the mean BigWig per chromosome, then the region x sample matrix.
+## BigWig I/O stays with rtracklayer (as in the reference); filter, segmentation, clusters and the per-sample
+## sum(Views(cov / mappedPerXM, regions)) / L run on the device.  Chromosomes and sample files are walked serially
+## (BPPARAM arguments are accepted and ignored: the CUDA context must not be forked).
+railMatrix <- function(chrs, summaryFiles, sampleFiles, L, cutoff = NULL, maxClusterGap = 300L, totalMapped = NULL,
+    targetSize = 40e6, file.cores = 1L, chrlens = NULL, ...) {
+    stopifnot(length(chrs) == length(summaryFiles))                                      # :119
+    stopifnot(!is.null(cutoff))                                                          # :125
+    stopifnot(length(L) != 1 | length(L) != length(sampleFiles))                         # :126 (sic)
+    if (!is.null(totalMapped)) stopifnot(length(totalMapped) != 1 | length(totalMapped) != length(sampleFiles))
+    if (is.null(chrlens)) chrlens <- rep(list(NULL), length(chrs))
+    mappedPerXM <- if (!is.null(totalMapped) & targetSize != 0) totalMapped / targetSize else NULL        # :151-155
+    chunksize <- derfinder:::.advanced_argument("chunksize", 1000, ...)
+    res <- mapply(function(chr, summaryFile, chrlen) {
+        meanCov <- derfinder::loadCoverage(files = summaryFile, chr = chr, chrlen = chrlen)                # :181
+        filteredMean <- filterData(meanCov$coverage, cutoff = cutoff, filter = "mean", returnMean = TRUE, ...)
+        regs <- findRegions(position = filteredMean$position, fstats = filteredMean$meanCoverage, chr = chr,
+                            maxClusterGap = maxClusterGap, cutoff = cutoff, ...)
+        if (is.null(regs)) return(list(regions = GenomicRanges::GRanges(), coverageMatrix = NULL))        # :190-192
+        names(regs) <- seq_len(length(regs))
+        GenomeInfoDb::seqlengths(regs) <- length(meanCov$coverage[[1]])
+        ## regions in chunks of `chunksize` (:203-216), every sample's BigWig imported for the chunk's ranges only
+        chunks <- split(seq_len(length(regs)), ceiling(seq_len(length(regs)) / chunksize))
+        mats <- lapply(chunks, function(ii) {
+            rg <- regs[ii]
+            covs <- lapply(sampleFiles, function(f)
+                rtracklayer::import(f, selection = GenomicRanges::reduce(rg), as = "RleList")[[chr]])      # :271-284
+            names(covs) <- if (is.null(names(sampleFiles))) sampleFiles else names(sampleFiles)
+            .railMatChrRegion(S4Vectors::DataFrame(covs, check.names = FALSE), rg,
+                              if (is.null(mappedPerXM)) NULL else rep_len(mappedPerXM, length(sampleFiles)),
+                              rep_len(L, length(sampleFiles)))$coverageMatrix
+        })
+        list(regions = regs, coverageMatrix = do.call(rbind, mats))
+    }, chrs, summaryFiles, chrlens, SIMPLIFY = FALSE)
+    names(res) <- chrs
+    res
+}
+
+## ---- analyzeChr (R/analyzeChr.R:108-310): the per-chromosome driver; every numeric stage is this package's, the
+## annotation and the on-disk layout are the reference's
+analyzeChr <- function(chr, coverageInfo, models, cutoffPre = 5, cutoffFstat = 1e-08, cutoffType = "theoretical",
+    nPermute = 1, seeds = as.integer(gsub("-", "", Sys.Date())) + seq_len(nPermute), groupInfo, txdb = NULL,
+    writeOutput = TRUE, runAnnotation = TRUE, lowMemDir = file.path(chr, "chunksDir"), smooth = FALSE, weights = NULL,
+    smoothFunction = bumphunter::locfitByCluster, ...) {
+    stopifnot(length(intersect(cutoffType, c("empirical", "theoretical", "manual"))) == 1)                 # :117-120
+    stopifnot(is.factor(groupInfo))
+    stopifnot(length(intersect(names(models), c("mod", "mod0"))) == 2)
+    returnOutput <- derfinder:::.advanced_argument("returnOutput", !writeOutput, ...)
+    timeinfo <- c(init = Sys.time())
+    if (writeOutput) {
+        dir.create(chr, showWarnings = FALSE, recursive = TRUE)
+        optionsStats <- list(models = models, cutoffPre = cutoffPre, cutoffFstat = cutoffFstat, cutoffType = cutoffType,
+            nPermute = nPermute, seeds = seeds, groupInfo = groupInfo, lowMemDir = lowMemDir, analyzeCall = match.call(),
+            cutoffFstatUsed = NULL, smooth = smooth, smoothFunction = smoothFunction, weights = weights, ...)
+    }
+    ## the device keeps the chunks: lowMemDir is accepted for signature compatibility and not used (:167)
+    prep <- preprocessCoverage(coverageInfo = coverageInfo, groupInfo = groupInfo, cutoff = cutoffPre, lowMemDir = NULL, ...)
+    timeinfo <- c(timeinfo, setup = Sys.time())
+    fstats <- calculateStats(coveragePrep = prep, models = models, ...)                                   # :187
+    timeinfo <- c(timeinfo, calculateStats = Sys.time())
+    ## F cutoff (.calcFstatCutoff, :312-328)
+    cutoffFstatUsed <- switch(cutoffType,
+        empirical = quantile(as.numeric(fstats), cutoffFstat, na.rm = TRUE),
+        theoretical = { n <- nrow(models$mod); df1 <- ncol(models$mod); df0 <- ncol(models$mod0)
+                        qf(cutoffFstat, df1 - df0, n - df1, lower.tail = FALSE) },
+        manual = cutoffFstat)
+    if (writeOutput) {
+        optionsStats$cutoffFstatUsed <- cutoffFstatUsed
+        save(optionsStats, file = file.path(chr, "optionsStats.Rdata"))
+        save(fstats, file = file.path(chr, "fstats.Rdata"))
+        coveragePrep <- prep; save(coveragePrep, file = file.path(chr, "coveragePrep.Rdata"))
+    }
+    regions <- calculatePvalues(coveragePrep = prep, models = models, fstats = fstats, nPermute = nPermute,
+        seeds = seeds, chr = chr, cutoff = cutoffFstatUsed, smooth = smooth, weights = weights,
+        smoothFunction = smoothFunction, ...)                                                              # :237
+    timeinfo <- c(timeinfo, calculatePvalues = Sys.time())
+    if (writeOutput) save(regions, file = file.path(chr, "regions.Rdata"))
+    annotation <- NULL
+    if (runAnnotation && !is.null(regions$regions)) {                                                      # :262-283
+        annotation <- if (is.null(txdb)) bumphunter::matchGenes(x = regions$regions, subject = bumphunter::annotateTranscripts(
+            TxDb.Hsapiens.UCSC.hg19.knownGene::TxDb.Hsapiens.UCSC.hg19.knownGene))
+            else bumphunter::matchGenes(x = regions$regions, subject = bumphunter::annotateTranscripts(txdb))
+        if (writeOutput) save(annotation, file = file.path(chr, "annotation.Rdata"))
+    }
+    timeinfo <- c(timeinfo, annotation = Sys.time())
+    if (writeOutput) save(timeinfo, file = file.path(chr, "timeinfo.Rdata"))
+    if (returnOutput) list(timeinfo = timeinfo, optionsStats = if (writeOutput) optionsStats else NULL,
+        coveragePrep = prep, fstats = fstats, regions = regions, annotation = annotation) else invisible(NULL)
+}

@@ -45,9 +45,13 @@ static void nulls_finalizer(SEXP p) {
     if (n) dfb_nulls_free(n);
     R_ClearExternalPtr(p);
 }
-static SEXP wrap(void* h, const char* tag, R_CFinalizer_t fin) {
-    SEXP p = PROTECT(R_MakeExternalPtr(h, Rf_install(tag), R_NilValue));
-    R_RegisterCFinalizerEx(p, fin, TRUE);
+/* Child handles (coverage, regions, nulls) keep their context alive: the context's external pointer is the
+ * `prot` value of theirs, so the garbage collector cannot finalise it first, and no finaliser runs at exit
+ * (onexit = FALSE) where R gives no order at all -- the process teardown releases the device.  dfb_cov_free /
+ * dfb_nulls_free / dfb_regions_free dereference ctx->stream, so the context must outlive them. */
+static SEXP wrap(void* h, const char* tag, R_CFinalizer_t fin, SEXP owner) {
+    SEXP p = PROTECT(R_MakeExternalPtr(h, Rf_install(tag), owner));
+    R_RegisterCFinalizerEx(p, fin, FALSE);
     UNPROTECT(1);
     return p;
 }
@@ -60,7 +64,7 @@ static void* unwrap(SEXP p, const char* what) {
 SEXP dfbR_create(SEXP device) {
     dfb_ctx* c = NULL;
     CHECK(dfb_create(Rf_asInteger(device), NULL, &c));
-    return wrap(c, "dfb_ctx", ctx_finalizer);
+    return wrap(c, "dfb_ctx", ctx_finalizer, R_NilValue);
 }
 
 /* ---------------------------------------------------------------- Rle marshalling ----------- */
@@ -94,7 +98,7 @@ SEXP dfbR_filter(SEXP ctx, SEXP values, SEXP lengths, SEXP len, SEXP mapped, SEX
                          (int64_t)Rf_asReal(len), Rf_isNull(mapped) ? NULL : REAL(mapped), Rf_asInteger(filter),
                          Rf_asReal(cutoff), Rf_isNull(prev_len) ? NULL : (const int32_t*)INTEGER(prev_len),
                          Rf_isNull(prev_len) ? 0 : XLENGTH(prev_len), Rf_asLogical(prev_first), &cov));
-    return wrap(cov, "dfb_cov", cov_finalizer);
+    return wrap(cov, "dfb_cov", cov_finalizer, ctx);
 }
 
 /* already filtered DataFrame (what loadCoverage(cutoff=) returns) + its position index */
@@ -105,7 +109,7 @@ SEXP dfbR_cov_from_rle(SEXP ctx, SEXP values, SEXP lengths, SEXP N, SEXP pos_len
     CHECK(dfb_cov_from_rle((dfb_ctx*)unwrap(ctx, "coverage"), Rf_length(values), dtype, v, l, nr,
                            (int64_t)Rf_asReal(N), (const int32_t*)INTEGER(pos_len), XLENGTH(pos_len),
                            Rf_asLogical(pos_first), &cov));
-    return wrap(cov, "dfb_cov", cov_finalizer);
+    return wrap(cov, "dfb_cov", cov_finalizer, ctx);
 }
 
 SEXP dfbR_cov_info(SEXP cov) {
@@ -220,7 +224,7 @@ SEXP dfbR_find_regions(SEXP ctx, SEXP x, SEXP pos_len, SEXP pos_first, SEXP cut_
                                   Rf_asInteger(max_cluster_gap), Rf_asLogical(basic), &r);
     CHECK(rc);
     if (rc == DFB_ENOREGIONS) return R_NilValue; /* glue issues warning("Found no regions") and returns NULL */
-    SEXP h = PROTECT(wrap(r, "dfb_regions", regions_finalizer)); /* freed by the GC, also on error */
+    SEXP h = PROTECT(wrap(r, "dfb_regions", regions_finalizer, ctx)); /* freed by the GC, also on error */
     (void)h;
     SEXP out = regions_to_list(r, Rf_asLogical(basic));
     UNPROTECT(1);
@@ -232,8 +236,11 @@ SEXP dfbR_find_regions(SEXP ctx, SEXP x, SEXP pos_len, SEXP pos_first, SEXP cut_
 /* fstats = NULL uses the statistics cached on the device by dfbR_fstats (the glue passes NULL when
  * the `fstats` argument still carries the handle attribute calculateStats() attached).
  * perm: integer matrix [n x B] = sapply(seeds, function(s) { set.seed(s); sample(n) }) - 1L. */
+/* mean_v / group_v: NULL = summarise the device copies (the vectors preprocessCoverage() returned for this handle);
+ * otherwise the caller's own meanCoverage (numeric) / groupMeans (list of numeric), R/calculatePvalues.R:222-262 */
 SEXP dfbR_calculate_pvalues(SEXP ctx, SEXP cov, SEXP fstats, SEXP mod, SEXP mod0, SEXP adjustF, SEXP perm, SEXP cut_lo,
-                            SEXP cut_hi, SEXP max_region_gap, SEXP max_cluster_gap, SEXP n_groups) {
+                            SEXP cut_hi, SEXP max_region_gap, SEXP max_cluster_gap, SEXP n_groups, SEXP mean_v,
+                            SEXP group_v) {
     dfb_ctx* cx = (dfb_ctx*)unwrap(ctx, "calculatePvalues");
     dfb_cov* c = (dfb_cov*)unwrap(cov, "calculatePvalues");
     dfb_regions* r = NULL;
@@ -245,12 +252,20 @@ SEXP dfbR_calculate_pvalues(SEXP ctx, SEXP cov, SEXP fstats, SEXP mod, SEXP mod0
                                    Rf_asInteger(max_cluster_gap), &r, &nl, NULL);
     CHECK(rc);
     if (rc == DFB_ENOREGIONS) return R_NilValue; /* list(regions = NULL, nullStats = NULL, ...) (:245-251) */
-    SEXP hr = PROTECT(wrap(r, "dfb_regions", regions_finalizer));
-    SEXP hn = PROTECT(wrap(nl, "dfb_nulls", nulls_finalizer));
-    (void)hr; (void)hn; /* owned by the GC from here on: an Rf_error below cannot leak them */
+    SEXP hr = PROTECT(wrap(r, "dfb_regions", regions_finalizer, ctx));
+    SEXP hn = PROTECT(wrap(nl, "dfb_nulls", nulls_finalizer, ctx));
+    /* owned by the GC from here on: an Rf_error below cannot leak them */
     const char* nm[] = {"regions", "pvalues", "meanCoverage", "groupMeans", "nullStats", "nullWidths",
-                        "nullPermutation", "nullAreas", ""};
+                        "nullPermutation", "nullAreas", "handles", ""};
     SEXP out = PROTECT(Rf_mkNamed(VECSXP, nm));
+    {
+        const char* hn_names[] = {"regions", "nulls", ""};
+        SEXP hl = PROTECT(Rf_mkNamed(VECSXP, hn_names));
+        SET_VECTOR_ELT(hl, 0, hr);
+        SET_VECTOR_ELT(hl, 1, hn);
+        SET_VECTOR_ELT(out, 8, hl);
+        UNPROTECT(1);
+    }
     SET_VECTOR_ELT(out, 0, regions_to_list(r, 0));
     R_xlen_t R = (R_xlen_t)dfb_regions_count(r), M = (R_xlen_t)dfb_nulls_count(nl);
     SEXP pv = PROTECT(Rf_allocVector(REALSXP, R));
@@ -258,13 +273,15 @@ SEXP dfbR_calculate_pvalues(SEXP ctx, SEXP cov, SEXP fstats, SEXP mod, SEXP mod0
     if (M == 0) for (R_xlen_t i = 0; i < R; ++i) REAL(pv)[i] = NA_REAL; /* :408-419 */
     SET_VECTOR_ELT(out, 1, pv);
     SEXP mc = PROTECT(Rf_allocVector(REALSXP, R));
-    CHECK(dfb_regions_view_means(cx, r, c, -1, REAL(mc)));
+    if (Rf_isNull(mean_v)) CHECK(dfb_regions_view_means(cx, r, c, -1, REAL(mc)));
+    else CHECK(dfb_regions_view_means_host(cx, r, REAL(mean_v), XLENGTH(mean_v), REAL(mc)));
     SET_VECTOR_ELT(out, 2, mc);
     int G = Rf_asInteger(n_groups);
     SEXP gm = PROTECT(Rf_allocVector(VECSXP, G));
     for (int g = 0; g < G; ++g) {
         SEXP v = PROTECT(Rf_allocVector(REALSXP, R));
-        CHECK(dfb_regions_view_means(cx, r, c, g, REAL(v)));
+        if (Rf_isNull(group_v)) CHECK(dfb_regions_view_means(cx, r, c, g, REAL(v)));
+        else CHECK(dfb_regions_view_means_host(cx, r, REAL(VECTOR_ELT(group_v, g)), XLENGTH(VECTOR_ELT(group_v, g)), REAL(v)));
         SET_VECTOR_ELT(gm, g, v);
         UNPROTECT(1);
     }
@@ -329,6 +346,60 @@ SEXP dfbR_view_sums(SEXP ctx, SEXP cov, SEXP start, SEXP end, SEXP L) {
     return out;
 }
 
+/* ---------------------------------------------------------------- mergeResults -------------- */
+
+/* regions / nulls: lists of external pointers (NULL entries: chromosome without observed regions) */
+SEXP dfbR_merge_results(SEXP ctx, SEXP regions, SEXP nulls, SEXP nperm, SEXP cutoff_used, SEXP merge_area) {
+    dfb_ctx* cx = (dfb_ctx*)unwrap(ctx, "mergeResults");
+    int k = Rf_length(regions);
+    if (Rf_length(nulls) != k) Rf_error("regions and nulls must have one entry per chromosome");
+    dfb_regions** rp = (dfb_regions**)R_alloc((size_t)(k > 0 ? k : 1), sizeof(void*));
+    dfb_nulls** np = (dfb_nulls**)R_alloc((size_t)(k > 0 ? k : 1), sizeof(void*));
+    double** pp = (double**)R_alloc((size_t)(k > 0 ? k : 1), sizeof(double*));
+    double** fp = (double**)R_alloc((size_t)(k > 0 ? k : 1), sizeof(double*));
+    const char* nm[] = {"pvalues", "fwer", "totalNulls", ""};
+    SEXP out = PROTECT(Rf_mkNamed(VECSXP, nm));
+    SEXP pl = PROTECT(Rf_allocVector(VECSXP, k)), fl = PROTECT(Rf_allocVector(VECSXP, k));
+    for (int c = 0; c < k; ++c) {
+        SEXP re = VECTOR_ELT(regions, c), ne = VECTOR_ELT(nulls, c);
+        rp[c] = Rf_isNull(re) ? NULL : (dfb_regions*)unwrap(re, "mergeResults");
+        np[c] = Rf_isNull(ne) ? NULL : (dfb_nulls*)unwrap(ne, "mergeResults");
+        R_xlen_t R = rp[c] ? (R_xlen_t)dfb_regions_count(rp[c]) : 0;
+        SEXP pv = PROTECT(Rf_allocVector(REALSXP, R)), fw = PROTECT(Rf_allocVector(REALSXP, R));
+        SET_VECTOR_ELT(pl, c, pv);
+        SET_VECTOR_ELT(fl, c, fw);
+        UNPROTECT(2);
+        pp[c] = R ? REAL(pv) : NULL;
+        fp[c] = R ? REAL(fw) : NULL;
+    }
+    int64_t total = 0;
+    CHECK(dfb_merge_results(cx, k, rp, np, (int64_t)Rf_asInteger(nperm), Rf_asReal(cutoff_used), Rf_asLogical(merge_area), pp,
+                            fp, &total));
+    for (int c = 0; c < k; ++c) { /* NaN encodes NA (no nulls anywhere, R/calculatePvalues.R:408-419) */
+        SEXP pv = VECTOR_ELT(pl, c);
+        for (R_xlen_t i = 0; i < XLENGTH(pv); ++i)
+            if (ISNAN(REAL(pv)[i])) REAL(pv)[i] = NA_REAL;
+    }
+    SET_VECTOR_ELT(out, 0, pl);
+    SET_VECTOR_ELT(out, 1, fl);
+    SET_VECTOR_ELT(out, 2, Rf_ScalarReal((double)total));
+    UNPROTECT(3);
+    return out;
+}
+
+SEXP dfbR_comm_unique_id(void) {
+    SEXP id = PROTECT(Rf_allocVector(RAWSXP, DFB_COMM_ID_BYTES));
+    CHECK(dfb_comm_unique_id(RAW(id)));
+    UNPROTECT(1);
+    return id;
+}
+
+SEXP dfbR_comm_init_rank(SEXP ctx, SEXP world, SEXP rank, SEXP id) {
+    if (TYPEOF(id) != RAWSXP || XLENGTH(id) != DFB_COMM_ID_BYTES) Rf_error("communicator id must be %d raw bytes", DFB_COMM_ID_BYTES);
+    CHECK(dfb_comm_init_rank((dfb_ctx*)unwrap(ctx, "communicator"), Rf_asInteger(world), Rf_asInteger(rank), RAW(id)));
+    return R_NilValue;
+}
+
 /* ---------------------------------------------------------------- registration -------------- */
 
 static const R_CallMethodDef call_methods[] = {
@@ -342,7 +413,10 @@ static const R_CallMethodDef call_methods[] = {
     {"dfbR_chunk_lengths", (DL_FUNC)&dfbR_chunk_lengths, 3},
     {"dfbR_fstats", (DL_FUNC)&dfbR_fstats, 5},
     {"dfbR_find_regions", (DL_FUNC)&dfbR_find_regions, 9},
-    {"dfbR_calculate_pvalues", (DL_FUNC)&dfbR_calculate_pvalues, 12},
+    {"dfbR_calculate_pvalues", (DL_FUNC)&dfbR_calculate_pvalues, 14},
+    {"dfbR_merge_results", (DL_FUNC)&dfbR_merge_results, 6},
+    {"dfbR_comm_unique_id", (DL_FUNC)&dfbR_comm_unique_id, 0},
+    {"dfbR_comm_init_rank", (DL_FUNC)&dfbR_comm_init_rank, 4},
     {"dfbR_calc_pval", (DL_FUNC)&dfbR_calc_pval, 3},
     {"dfbR_calc_fwer", (DL_FUNC)&dfbR_calc_fwer, 6},
     {"dfbR_quantile", (DL_FUNC)&dfbR_quantile, 3},

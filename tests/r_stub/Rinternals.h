@@ -6,7 +6,7 @@ typedef ptrdiff_t R_xlen_t;
 typedef int Rboolean;
 #define TRUE 1
 #define FALSE 0
-enum { INTSXP = 13, REALSXP = 14, VECSXP = 19 };
+enum { INTSXP = 13, REALSXP = 14, VECSXP = 19, RAWSXP = 24 };
 extern SEXP R_NilValue;
 extern double R_NaReal;
 #define NA_REAL R_NaReal
@@ -33,6 +33,7 @@ SEXP VECTOR_ELT(SEXP, R_xlen_t);
 SEXP SET_VECTOR_ELT(SEXP, R_xlen_t, SEXP);
 int* INTEGER(SEXP);
 double* REAL(SEXP);
+unsigned char* RAW(SEXP);
 SEXP Rf_allocVector(unsigned int, R_xlen_t);
 SEXP Rf_allocMatrix(unsigned int, int, int);
 SEXP Rf_mkNamed(unsigned int, const char**);
