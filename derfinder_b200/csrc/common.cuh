@@ -79,6 +79,7 @@ class CopyPool {
 
 struct dfb_ctx {
     int device = 0;
+    cudaMemPool_t mempool = nullptr;  // private stream-ordered allocation pool of this context
     cudaStream_t stream = nullptr;
     bool own_stream = false;
     int sm_count = 148;
@@ -105,6 +106,7 @@ struct dfb_ctx {
     int opt_tmem_stages = 0;     // fused kernel: accumulator stages (0 = auto)
     int opt_fused = 1;           // fused screen+refine kernel (0: two-kernel screen path)
     int opt_a16_fused = 1;       // observed-F kernel also writes the null scan's fp16 operand (0: built on first use)
+    int opt_a_stages = 0;        // null2 kernel: A tile ring depth (0 = auto)
     int opt_mma_warps = 0;       // null2 kernel: MMA-issuing warps (0 = auto)
     int opt_null2 = 1;           // second-generation null scan (fstat_tc2.cu); 0: the first fused kernel
     int opt_k2_waves = 16;       // fused kernel: CTAs per resident slot (1 = persistent); see launch_fused
@@ -229,7 +231,8 @@ struct DevBuf {
         s = ctx->stream;
         n = count;
         if (count == 0) return DFB_OK;
-        cudaError_t e = cudaMallocAsync((void**)&p, count * sizeof(T), s);
+        cudaError_t e = ctx->mempool ? cudaMallocFromPoolAsync((void**)&p, count * sizeof(T), ctx->mempool, s)
+                                     : cudaMallocAsync((void**)&p, count * sizeof(T), s);
         if (e != cudaSuccess) {
             p = nullptr;
             n = 0;

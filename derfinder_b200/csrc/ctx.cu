@@ -630,11 +630,22 @@ int dfb_create(int device, void* stream, dfb_ctx** out) {
         }
         c->own_stream = true;
     }
-    // keep freed blocks in the pool: repeated calls re-use them without a device sync
-    cudaMemPool_t pool;
-    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-        uint64_t thr = UINT64_MAX;
-        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    // A PRIVATE stream-ordered pool that keeps freed blocks (repeated calls re-use them without a device
+    // synchronisation).  The device's default pool is left alone: other cudaMallocAsync users of the host
+    // process keep their own release policy.
+    {
+        cudaMemPoolProps props;
+        memset(&props, 0, sizeof props);
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = device;
+        if (cudaMemPoolCreate(&c->mempool, &props) == cudaSuccess) {
+            uint64_t thr = UINT64_MAX;
+            cudaMemPoolSetAttribute(c->mempool, cudaMemPoolAttrReleaseThreshold, &thr);
+        } else {
+            c->mempool = nullptr;  // fall back to the default pool with its default policy
+        }
     }
     cudaGetLastError();
     *out = c;
@@ -674,6 +685,7 @@ void dfb_destroy(dfb_ctx* c) {
     }
     for (auto& b : c->pin_blocks) cudaFreeHost(b.p);
     if (c->lut_dev) cudaFree(c->lut_dev);
+    if (c->mempool) cudaMemPoolDestroy(c->mempool);  // released once the last outstanding block is freed
     delete c->pool;
     if (c->own_stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -748,6 +760,7 @@ int dfb_set_option(dfb_ctx* c, const char* key, double value) {
     else if (!strcmp(key, "fused")) c->opt_fused = value != 0;
     else if (!strcmp(key, "null2")) c->opt_null2 = value != 0;
     else if (!strcmp(key, "mma_warps")) c->opt_mma_warps = (int)value;
+    else if (!strcmp(key, "a_stages")) c->opt_a_stages = (int)value;
     else if (!strcmp(key, "a16_fused")) c->opt_a16_fused = value != 0;
     else if (!strcmp(key, "dbg")) c->opt_dbg = (int)value;
     else if (!strcmp(key, "tmem_stages")) c->opt_tmem_stages = (int)value;

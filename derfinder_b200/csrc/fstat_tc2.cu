@@ -777,7 +777,7 @@ static bool null2_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
             G.warp_bytes = (uint32_t)round_up(G.ps * 32 * 2 + 32 * 4, 16);
             // A ring depth: three stages unless two leave room for a larger resident group (fewer passes over
             // the fp16 coverage: at 100 samples a pass reads 256 bytes per base)
-            int na_first = 3;
+            int na_first = ctx->opt_a_stages >= 2 && ctx->opt_a_stages <= 4 ? ctx->opt_a_stages : 3;
             {
                 const size_t rest0 = (size_t)round_up((int64_t)G.n * G.qs * 8, 16) + 64 * 8 + 4 * (size_t)ew * G.warp_bytes + 1024;
                 auto fit = [&](int na) -> int64_t {
@@ -785,7 +785,8 @@ static bool null2_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
                     return o + rest0 + G.b_bytes > limit ? 0 : (int64_t)((limit - o - rest0) / G.b_bytes);
                 };
                 const int64_t c3 = std::min<int64_t>(fit(3), G.chunks), c2 = std::min<int64_t>(fit(2), G.chunks);
-                if (c3 < 1 || (c2 > c3 && ceil_div(G.chunks, c2) < ceil_div(G.chunks, std::max<int64_t>(c3, 1)))) na_first = 2;
+                if (na_first == 3 && (c3 < 1 || (c2 > c3 && ceil_div(G.chunks, c2) < ceil_div(G.chunks, std::max<int64_t>(c3, 1)))))
+                    na_first = 2;
             }
             for (int na = na_first; na >= 2; --na) {
                 uint32_t o = (uint32_t)na * G.a_bytes;

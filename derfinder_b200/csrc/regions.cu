@@ -889,7 +889,17 @@ int dfb_find_regions_pos(dfb_ctx* ctx, const double* x, int64_t N, const int32_t
     return rc;
 }
 
-void dfb_regions_free(dfb_regions* r) { delete r; }
+void dfb_regions_free(dfb_regions* r) {
+    if (!r) return;
+    // some of the buffers were allocated on the auxiliary stream (the observed-region chain of
+    // dfb_calculate_pvalues) and are read by launches on the main one: both must have drained before the
+    // stream-ordered frees are queued
+    if (r->ctx) {
+        cudaStreamSynchronize(r->ctx->stream);
+        if (r->ctx->aux) cudaStreamSynchronize(r->ctx->aux);
+    }
+    delete r;
+}
 int64_t dfb_regions_count(const dfb_regions* r) { return r ? r->R : 0; }
 int64_t dfb_regions_count_up(const dfb_regions* r) { return r ? r->R_up : 0; }
 
