@@ -295,10 +295,16 @@ def run_reference_arm(args, cfg):
     if rank != 0:
         return
     from derfinder_b200.rrng import permutation_indices
+    if cfg.get("genome"):
+        cfg = dict(genome_chromosomes(cfg)["chr1"])
+    nb, npm = min(cfg["N"], args.cpu_bases), min(cfg["B"], args.cpu_perms)
+    # the bounded sample: the first `nb` kept bases of a chromosome of the workload's shape (same generator, same
+    # island statistics; generating all 25 M bases x 60 samples on the host would take longer than the arm itself)
+    scale = nb / float(cfg["N"])
+    cfg = dict(cfg, N=nb, chr_len=max(int(cfg["chr_len"] * scale), nb + 1000))
     work = make_workload(cfg, 20140923 + 2)
     perm_all = permutation_indices(range(1, cfg["B"] + 1), cfg["n"], "Rejection")
     cutoff = theoretical_cutoff(cfg["alpha"], work["mod"], work["mod0"])
-    nb, npm = min(cfg["N"], args.cpu_bases), min(cfg["B"], args.cpu_perms)
     cov, pl, pf, perm = cpu_sample(work, cfg, perm_all, cutoff, nb, npm)
     for _ in range(args.warmup):
         cpu_reference_pass(cov[:, : nb // 10], *cpu_sample(work, cfg, perm_all, cutoff, nb // 10, 2)[1:3], work["mod"],
@@ -315,7 +321,7 @@ def run_reference_arm(args, cfg):
     line = {"impl": "reference", "metric": "base_x_permutation_fstats_per_sec", "value": value,
             "unit": "base*perm F-stats/s", "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
             "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "config": {"workload": cfg["label"], "sample": sample},
+            "dtype": "f64", "data": "synthetic", "config": {"workload": WORKLOADS[args.workload]["label"], "sample": sample},
             "cpu_baseline": {"value": value, "unit": "base*perm F-stats/s", "cores": cores, "kind": "port",
                              "sample": sample},
             "e2e": {"value": value, "unit": "base*perm F-stats/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}

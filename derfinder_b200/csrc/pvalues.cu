@@ -492,51 +492,152 @@ int perm_max_device(dfb_ctx* ctx, const double* area_dev, const int32_t* perm_de
 // ------------------------------------------------------------------------------------------
 // quantile type 7 (na.rm = TRUE)
 
-__global__ void nan_to_top_kernel(const double* __restrict__ x, int64_t N, double* __restrict__ out,
-                                  unsigned long long* __restrict__ nan_count) {
-    unsigned long long c = 0;
+// Order statistics WITHOUT sorting: radix select over the order-preserving 64-bit image of the doubles, 11
+// bits per pass (2048 shared-memory bins), six read-only passes over x, all bookkeeping on the device (one
+// host synchronisation at the end).  The default cutoff quantile(fstats, 0.99) (R/findRegions.R:118,
+// R/calculatePvalues.R:160, R/analyzeChr.R:318) used to be a full radix sort of the N statistics.
+constexpr int QS_BITS = 11, QS_BINS = 1 << QS_BITS, QS_PASSES = 6;  // 6 * 11 = 66 >= 64
+
+__device__ __forceinline__ unsigned long long qs_key(double v) {  // ascending order of doubles == ascending order of keys
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+__device__ __forceinline__ double qs_unkey(unsigned long long k) {
+    const unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffull) : ~k;
+    return __longlong_as_double((long long)b);
+}
+
+// state[0] = key prefix fixed so far, state[1] = rank still to find inside the prefix (0-based), state[2] = NaN count,
+// state[3] = number of non-NaN values m
+__global__ void __launch_bounds__(256) qs_hist_kernel(const double* __restrict__ x, int64_t N, int pass,
+                                                      const unsigned long long* __restrict__ state,
+                                                      unsigned int* __restrict__ hist, unsigned long long* __restrict__ nan_count) {
+    __shared__ unsigned int h[QS_BINS];
+    for (int i = threadIdx.x; i < QS_BINS; i += blockDim.x) h[i] = 0u;
+    __syncthreads();
+    const int shift = 64 - QS_BITS * (pass + 1);  // negative in the last pass: the remaining low bits
+    const unsigned long long prefix = pass ? state[0] : 0ull;
+    unsigned long long nn = 0;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += (int64_t)gridDim.x * blockDim.x) {
-        double v = x[i];
+        const double v = x[i];
         if (v != v) {
-            v = __longlong_as_double(0x7ff8000000000000ll);  // sorts after +Inf
-            ++c;
+            ++nn;
+            continue;
         }
-        out[i] = v;
+        const unsigned long long k = qs_key(v);
+        const int hs = 64 - QS_BITS * pass;  // bits above the current digit
+        if (pass && (hs >= 64 ? 0ull : (k >> hs)) != prefix) continue;
+        const unsigned int d = shift >= 0 ? (unsigned int)((k >> shift) & (QS_BINS - 1)) : (unsigned int)((k << (-shift)) & (QS_BINS - 1));
+        atomicAdd(&h[d], 1u);
     }
+    __syncthreads();
+    for (int i = threadIdx.x; i < QS_BINS; i += blockDim.x)
+        if (h[i]) atomicAdd(&hist[i], h[i]);
+    if (pass == 0 && nan_count) {
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-    if ((threadIdx.x & 31) == 0 && c) atomicAdd(nan_count, c);
+        for (int o = 16; o > 0; o >>= 1) nn += __shfl_xor_sync(0xffffffffu, nn, o);
+        if ((threadIdx.x & 31) == 0 && nn) atomicAdd(nan_count, nn);
+    }
+}
+
+// one block: pick the bin that holds the wanted rank, extend the prefix, clear the histogram for the next pass
+__global__ void __launch_bounds__(QS_BINS / 2) qs_pick_kernel(unsigned int* __restrict__ hist, int pass, int64_t N, double prob,
+                                                              int which, unsigned long long* __restrict__ state) {
+    __shared__ unsigned long long cum[QS_BINS];
+    __shared__ unsigned long long want;
+    if (threadIdx.x == 0) {
+        if (pass == 0) {
+            const unsigned long long m = (unsigned long long)N - state[2];
+            state[3] = m;
+            // stats::quantile type 7: index = 1 + (m - 1) * p; ranks floor(index) and ceil(index) (1-based)
+            const double index = 1.0 + (double)(m ? m - 1 : 0) * prob;
+            const double r = which == 0 ? floor(index) : ceil(index);
+            state[1] = (unsigned long long)(r - 1.0);
+            state[0] = 0ull;
+        }
+        want = state[1];
+    }
+    __shared__ unsigned long long part[64];
+    for (int i = threadIdx.x; i < QS_BINS; i += blockDim.x) cum[i] = hist[i];
+    __syncthreads();
+    if (threadIdx.x < 64) {  // 64 partial sums of 32 bins, then two short serial scans
+        unsigned long long sum = 0;
+        for (int i = 0; i < 32; ++i) sum += cum[threadIdx.x * 32 + i];
+        part[threadIdx.x] = sum;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned long long run = 0;
+        int blk = 63;
+        for (int i = 0; i < 64; ++i) {
+            if (want < run + part[i]) {
+                blk = i;
+                break;
+            }
+            run += part[i];
+        }
+        int pick = blk * 32 + 31;
+        for (int i = blk * 32; i < blk * 32 + 32; ++i) {
+            if (want < run + cum[i]) {
+                pick = i;
+                break;
+            }
+            run += cum[i];
+        }
+        state[1] = want - run;
+        const int bits = (64 - QS_BITS * pass) >= QS_BITS ? QS_BITS : (64 - QS_BITS * pass);  // 9 bits in the last pass
+        state[0] = (state[0] << bits) | (unsigned long long)(bits == QS_BITS ? pick : (pick >> (QS_BITS - bits)));
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < QS_BINS; i += blockDim.x) hist[i] = 0u;
+}
+
+__global__ void qs_result_kernel(const unsigned long long* __restrict__ state, double* __restrict__ out) {
+    out[0] = qs_unkey(state[0]);
+}
+
+// k-th smallest (type-7 rank `which`: 0 = floor(index), 1 = ceil(index)) of the non-NaN values of x; *m_out = their count
+static int select_rank(dfb_ctx* ctx, const double* x_dev, int64_t N, double prob, int which, double* value_dev,
+                       unsigned long long* state_dev, unsigned int* hist_dev) {
+    const int grid = grid_for(N, 256, ctx->sm_count, 8);
+    KTimer t(ctx, DFB_K_PVAL, 2 * QS_PASSES + 1);
+    for (int pass = 0; pass < QS_PASSES; ++pass) {
+        qs_hist_kernel<<<grid, 256, 0, ctx->stream>>>(x_dev, N, pass, state_dev, hist_dev, pass == 0 && which == 0 ? state_dev + 2 : nullptr);
+        qs_pick_kernel<<<1, QS_BINS / 2, 0, ctx->stream>>>(hist_dev, pass, N, prob, which, state_dev);
+    }
+    qs_result_kernel<<<1, 1, 0, ctx->stream>>>(state_dev, value_dev);
+    DFB_CUDA(cudaGetLastError());
+    return DFB_OK;
 }
 
 int quantile_device(dfb_ctx* ctx, const double* x_dev, int64_t N, double prob, double* out) {
     DFB_REQUIRE(prob >= 0 && prob <= 1, "'probs' outside [0,1]");
-    DevBuf<double> a, b;
-    DevBuf<unsigned long long> nanc;
-    DFB_TRY(a.alloc(ctx, (size_t)std::max<int64_t>(N, 1)));
-    DFB_TRY(b.alloc(ctx, (size_t)std::max<int64_t>(N, 1)));
-    DFB_TRY(nanc.alloc(ctx, 1));
-    DFB_TRY(nanc.zero());
-    if (N > 0) {
-        {
-            KTimer t(ctx, DFB_K_PVAL);
-            nan_to_top_kernel<<<grid_for(N, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(x_dev, N, a.p, nanc.p);
-        }
-        DFB_TRY(sort_doubles(ctx, a.p, b.p, N));
+    if (N <= 0) {
+        *out = nan("");
+        return DFB_OK;
     }
-    unsigned long long nn = 0;
-    DFB_TRY(d2h(ctx, &nn, nanc.p, sizeof nn));
-    const int64_t m = N - (int64_t)nn;
+    DevBuf<unsigned long long> state;
+    DevBuf<unsigned int> hist;
+    DevBuf<double> vals;
+    DFB_TRY(state.alloc(ctx, 4));
+    DFB_TRY(hist.alloc(ctx, QS_BINS));
+    DFB_TRY(vals.alloc(ctx, 2));
+    DFB_TRY(state.zero());
+    DFB_TRY(hist.zero());
+    DFB_TRY(select_rank(ctx, x_dev, N, prob, 0, vals.p, state.p, hist.p));      // x[floor(index)]
+    DFB_TRY(select_rank(ctx, x_dev, N, prob, 1, vals.p + 1, state.p, hist.p));  // x[ceil(index)] (NaN count kept in state[2])
+    double v[2];
+    unsigned long long st[4];
+    DFB_TRY(d2h(ctx, v, vals.p, sizeof v));
+    DFB_TRY(d2h(ctx, st, state.p, sizeof st));
+    const int64_t m = (int64_t)st[3];
     if (m <= 0) {
         *out = nan("");
         return DFB_OK;
     }
-    // stats::quantile type 7: index = 1 + (m-1)*p; qs = x[lo]; if index > lo and x[hi] != qs:
-    // qs = (1-h)*qs + h*x[hi]
+    // stats::quantile type 7: qs = x[lo]; if index > lo and x[hi] != qs: qs = (1-h)*qs + h*x[hi]
     const double index = 1.0 + (double)(m - 1) * prob;
-    const double lo = floor(index), hi = ceil(index);
-    double v[2];
-    DFB_TRY(d2h(ctx, &v[0], b.p + (int64_t)lo - 1, sizeof(double)));
-    DFB_TRY(d2h(ctx, &v[1], b.p + (int64_t)hi - 1, sizeof(double)));
+    const double lo = floor(index);
     double qs = v[0];
     if (index > lo && v[1] != qs) {
         const double h = index - lo;

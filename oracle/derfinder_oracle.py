@@ -247,13 +247,17 @@ def calculate_stats(prep, mod, mod0, adjustF=0.0):
 def quantile_type7(x, prob):
     """R's default quantile() (type 7) with na.rm=TRUE."""
     x = np.sort(np.asarray(x, dtype=np.float64)[~np.isnan(x)])
-    h = (len(x) - 1) * prob
-    lo = int(math.floor(h))
-    hi = int(math.ceil(h))
-    qs = x[lo]
-    if h > lo and x[hi] != qs:  # stats:::quantile.default, type 7
-        g = h - lo
-        qs = (1 - g) * qs + g * x[hi]
+    if len(x) == 0:  # quantile(c(NA, NA), na.rm = TRUE) is NA
+        return float("nan")
+    # stats:::quantile.default, type 7, in R's own operation order: index <- 1 + max(n - 1, 0) * probs;
+    # lo <- floor(index); hi <- ceiling(index); h <- index - lo  (1-based ranks)
+    index = 1.0 + (len(x) - 1) * prob
+    lo = int(math.floor(index))
+    hi = int(math.ceil(index))
+    qs = x[lo - 1]
+    if index > lo and x[hi - 1] != qs:
+        g = index - lo
+        qs = (1 - g) * qs + g * x[hi - 1]
     return qs
 
 

@@ -349,3 +349,20 @@ def test_merge_results_single_rank(dfb, eng, merge_area):
                 eng.lib.dfb_regions_free(rh)
                 eng.lib.dfb_nulls_free(nh)
             eng.lib.dfb_cov_free(h)
+
+
+def test_quantile_radix_select(dfb, eng):
+    """quantile(x, p, na.rm = TRUE) type 7 by radix select (no sort): negative values, signed zeros, infinities,
+    ties, NaNs, one / two values, nothing but NaN (R/findRegions.R:118)."""
+    rng = np.random.default_rng(77)
+    cases = [rng.normal(size=100003), np.round(rng.normal(size=50000), 1), np.array([3.5]), np.array([2.0, -7.0]),
+             np.concatenate((rng.normal(size=999), [np.inf, -np.inf, 0.0, -0.0, np.inf])),
+             np.abs(rng.standard_cauchy(size=200001)) * 1e-300, np.full(7, np.nan), -np.abs(rng.gamma(2.0, size=4097))]
+    x = rng.normal(size=30000)
+    x[rng.random(30000) < 0.3] = np.nan
+    cases.append(x)
+    for x in cases:
+        for p in (0.0, 1e-9, 0.25, 0.5, 0.99, 0.999999, 1.0, 0.123456):
+            got = dfb.calcFstatCutoff("empirical", p, fstats=x, engine=eng)
+            want = O.quantile_type7(x, p)
+            assert (got == want) or (np.isnan(got) and np.isnan(want)), (len(x), p, got, want)
