@@ -81,6 +81,8 @@ SIGNATURES = {
     "dfb_regions_get": (C.c_int, [C.c_void_p, c_i32p, c_i32p, c_f64p, c_f64p, c_i32p, c_i32p, c_i32p, c_f64p]),
     "dfb_regions_view_means": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, c_f64p]),
     "dfb_regions_view_means_host": (C.c_int, [C.c_void_p, C.c_void_p, c_f64p, C.c_int64, c_f64p]),
+    "dfb_cov_from_bigwig": (C.c_int, [C.c_void_p, C.c_int, c_vpp, c_vpp, c_i64p, C.POINTER(C.c_uint32), c_i32p, c_i32p,
+                                      C.c_int64, c_f64p, c_vpp]),
     "dfb_comm_unique_id": (C.c_int, [C.c_void_p]),
     "dfb_comm_init_rank": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "dfb_comm_init_all": (C.c_int, [C.POINTER(C.c_void_p), C.c_int]),

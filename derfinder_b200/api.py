@@ -808,7 +808,13 @@ def railMatrix(chrs, summaryCov, sampleCov, L_=None, cutoff=None, maxClusterGap=
     engine = engine or default_engine()
     out = {}
     for chrom in chrs:
-        filt = filterData([summaryCov[chrom]], cutoff=cutoff, filter="mean", returnMean=True, returnCoverage=False,
+        summary = summaryCov[chrom]
+        if isinstance(summary, str):  # the mean BigWig itself (loadCoverage(files = summaryFile), :181)
+            from .bigwig import BigWigFile
+            bw = BigWigFile(summary)
+            summary = bw.read_rle(chrom)
+            bw.close()
+        filt = filterData([summary], cutoff=cutoff, filter="mean", returnMean=True, returnCoverage=False,
                           engine=engine)
         regs = None
         if len(filt["meanCoverage"]):
@@ -817,7 +823,14 @@ def railMatrix(chrs, summaryCov, sampleCov, L_=None, cutoff=None, maxClusterGap=
         if regs is None:  # :190-192
             out[chrom] = dict(regions=None, coverageMatrix=None)
             continue
-        kind, names, cols = _as_columns(sampleCov[chrom])
+        samples = sampleCov[chrom]
+        if isinstance(samples, (list, tuple)) and len(samples) and all(isinstance(f, str) for f in samples):
+            # sample BigWig files: the data sections overlapping the regions are inflated on the host and decoded
+            # on the device (dfb_cov_from_bigwig), :271-289
+            out[chrom] = dict(regions=regs, coverageMatrix=_rail_from_bigwig(engine, chrom, list(samples), regs, L_read,
+                                                                            totalMapped, targetSize))
+            continue
+        kind, names, cols = _as_columns(samples)
         if kind == "dense":
             cols = [_dense_to_rle(cols[:, s]) for s in range(cols.shape[1])]
         n = len(cols)
@@ -849,6 +862,52 @@ def railMatrix(chrs, summaryCov, sampleCov, L_=None, cutoff=None, maxClusterGap=
             r0 = r1
         out[chrom] = dict(regions=regs, coverageMatrix=mat)
     return out
+
+
+def _rail_from_bigwig(engine, chrom, files, regs, L_read, totalMapped, targetSize):
+    """Region x sample matrix straight from the samples' BigWig files (.railMatChrRegionCov, R/railMatrix.R:264-290)."""
+    from .bigwig import BigWigFile
+    n = len(files)
+    Lv = np.atleast_1d(np.asarray(L_read, dtype=np.float64))
+    if Lv.size not in (1, n):
+        raise ValueError("'L' has to be of length 1 or one value per sample")
+    st = np.asarray(regs["start"], dtype=np.int64)
+    en = np.asarray(regs["end"], dtype=np.int64)
+    R = len(st)
+    by_pos = np.argsort(st, kind="stable")
+    rs, re = st[by_pos].astype(np.int32), en[by_pos].astype(np.int32)
+    mapped = None
+    if totalMapped is not None and targetSize != 0:  # :151-155
+        mapped = np.broadcast_to(np.asarray(totalMapped, dtype=np.float64) / float(targetSize), (n,)).copy()
+    blobs, offs, ids = [], [], np.zeros(n, dtype=np.uint32)
+    for s, f in enumerate(files):
+        bw = BigWigFile(f)
+        blob, off, cid = bw.sections(chrom, rs, re)
+        bw.close()
+        blobs.append(np.frombuffer(blob, dtype=np.uint8) if len(blob) else np.zeros(1, dtype=np.uint8))
+        offs.append(off)
+        ids[s] = cid
+    bp = (C.c_void_p * n)(*[b.ctypes.data for b in blobs])
+    op = (C.c_void_p * n)(*[o.ctypes.data for o in offs])
+    nsec = np.asarray([len(o) - 1 for o in offs], dtype=np.int64)
+    h = C.c_void_p()
+    L.check(engine.lib.dfb_cov_from_bigwig(engine.h, n, bp, op, L.ptr(nsec, C.c_int64), L.ptr(ids, C.c_uint32),
+                                           L.ptr(rs, C.c_int32), L.ptr(re, C.c_int32), R, L.ptr(mapped, C.c_double),
+                                           C.byref(h)))
+    cov = Coverage(engine, h, [str(f) for f in files])
+    try:
+        width = (re.astype(np.int64) - rs + 1)
+        ce = np.cumsum(width)
+        cs = (ce - width + 1).astype(np.int32)
+        ce = ce.astype(np.int32)
+        part = np.empty((n, R), dtype=np.float64)  # column-major [R x n]
+        L.check(engine.lib.dfb_view_sums(engine.h, cov.h, L.ptr(cs, C.c_int32), L.ptr(ce, C.c_int32), R,
+                                         L.ptr(Lv, C.c_double), int(Lv.size), L.ptr(part, C.c_double)))
+    finally:
+        cov.free()
+    mat = np.empty((R, n), dtype=np.float64)
+    mat[by_pos] = part.T
+    return mat
 
 
 # ---------------------------------------------------------------------------------------------

@@ -280,6 +280,18 @@ int dfb_pool_rank_dev(dfb_ctx* ctx, const dfb_regions* r, const double* records_
  * not bit-identical to the summed area calculatePvalues ranks; written to device memory [count] */
 int dfb_nulls_merge_areas_dev(const dfb_nulls* nl, double* area_dev);
 
+/* BigWig data sections -> coverage of the regions, on the device (R/railMatrix.R:271-289: per sample
+ * `import(sampleFile, selection = regs, as = "RleList")`, `/ mappedPerXM`; the view sums follow with
+ * dfb_view_sums).  The host finds the file's leaf blocks that overlap the regions (R-tree), inflates them
+ * and passes, per sample s, the concatenated uncompressed data sections `sections[s]` with their byte
+ * offsets `sec_off[s][0 .. nsec[s]]` and the id the file gives the chromosome (`chrom_id[s]`).  Regions:
+ * 1-based inclusive, sorted, disjoint.  Result: an F64 coverage handle of N = sum(width(regions)) bases
+ * (region k occupies rows sum(width[0..k)) + 1 ...), value / mapped_per_xm[s] where the file has data,
+ * 0 elsewhere. */
+int dfb_cov_from_bigwig(dfb_ctx* ctx, int n, const void* const* sections, const int64_t* const* sec_off,
+                        const int64_t* nsec, const uint32_t* chrom_id, const int32_t* rstart,
+                        const int32_t* rend, int64_t R, const double* mapped_per_xm, dfb_cov** out);
+
 /* ---------------------------------------------------------------- mergeResults -------------- */
 
 /* One-call genome-wide pass of mergeResults() -- R/mergeResults.R:216-235 (pool the null regions of every
