@@ -690,48 +690,153 @@ struct PrepParams {
     double scalefac;
     const double* lut;  // log2(k + scalefac) for k in [0, lut_n), host-built with libm
     int64_t lut_n;
+    int lut_s;          // leading table entries staged in shared memory (<= lut_n)
     const int32_t* group;  // [n] or nullptr
     const double* group_size;  // [G]
     int G;
-    double* y;      // [n][ld]
+    double* y;      // [n][ld], or nullptr when the log2 matrix is not materialised (STORE_Y = false)
     double* mean;   // [N] or nullptr (already present)
     double* gmean;  // [G][ld]
+    double* ymean;  // [N] (sum_s y[s]) / n in sample order (the F-stat contract's row mean), or nullptr
     int* out_of_range;  // set when an integer value falls outside the table (the caller re-runs)
 };
 
-template <typename V>
+// One thread per base, eight samples' loads in flight; the head of the log2 table sits in shared memory
+// (coverage values are small almost everywhere: a table gather from L1 per element would bound the kernel).
+// GR: group sums in registers for up to GR groups (0: shared-memory accumulators, any G).
+template <typename V, bool STORE_Y, int GR>
 __global__ void __launch_bounds__(256) preprocess_kernel(const PrepParams P) {
-    extern __shared__ double gs_s[];  // [G][blockDim]
+    extern __shared__ double prep_s[];  // [lut_s] table head, [G][blockDim] group sums (GR == 0), group ids [n]
+    double* lut_s = prep_s;
+    double* gs_s = prep_s + P.lut_s;
+    unsigned char* grp_s = reinterpret_cast<unsigned char*>(gs_s + (GR == 0 ? (size_t)P.G * blockDim.x : 0));
+    for (int e = threadIdx.x; e < P.lut_s; e += blockDim.x) lut_s[e] = P.lut[e];
+    if (P.G > 0)
+        for (int e = threadIdx.x; e < P.n; e += blockDim.x) grp_s[e] = (unsigned char)P.group[e];
+    __syncthreads();
     const V* __restrict__ x = reinterpret_cast<const V*>(P.x);
+    constexpr int LB = 8;
+    const int n = P.n;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.N; i += (int64_t)gridDim.x * blockDim.x) {
-        double sum = 0.0;
-        for (int g = 0; g < P.G; ++g) gs_s[g * blockDim.x + threadIdx.x] = 0.0;
-        for (int s = 0; s < P.n; ++s) {
-            const V raw = x[(size_t)s * P.ld + i];
-            const double v = (double)raw;
-            sum = s == 0 ? v : __dadd_rn(sum, v);
-            if (P.G > 0) {
-                double* a = &gs_s[P.group[s] * blockDim.x + threadIdx.x];
-                *a = __dadd_rn(*a, v);
-            }
-            double yv;
-            if (sizeof(V) == 4 && P.lut) {
-                const int64_t k = (int64_t)raw;
-                if (k >= 0 && k < P.lut_n) {
-                    yv = P.lut[k];
-                } else {
-                    yv = 0.0;
-                    *P.out_of_range = 1;
+        double sum = 0.0, ysum = 0.0;
+        double gr[GR > 0 ? GR : 1];
+#pragma unroll
+        for (int g = 0; g < (GR > 0 ? GR : 1); ++g) gr[g] = 0.0;
+        if (GR == 0)
+            for (int g = 0; g < P.G; ++g) gs_s[g * blockDim.x + threadIdx.x] = 0.0;
+        for (int s0 = 0; s0 < n; s0 += LB) {
+            V rawv[LB];
+            // clamped row index instead of a predicate per load: the loads stay back to back
+#pragma unroll
+            for (int e = 0; e < LB; ++e) rawv[e] = __ldg(x + (size_t)min(s0 + e, n - 1) * P.ld + i);
+            asm volatile("" ::: "memory");
+#pragma unroll
+            for (int e = 0; e < LB; ++e) {
+                const int s = s0 + e;
+                if (s < n) {
+                    const V raw = rawv[e];
+                    const double v = (double)raw;
+                    sum = s == 0 ? v : __dadd_rn(sum, v);
+                    if (GR > 0) {
+                        if (P.G > 0) {
+                            const int g = grp_s[s];
+#pragma unroll
+                            for (int gg = 0; gg < GR; ++gg)
+                                if (g == gg) gr[gg] = __dadd_rn(gr[gg], v);
+                        }
+                    } else if (P.G > 0) {
+                        double* a = &gs_s[grp_s[s] * blockDim.x + threadIdx.x];
+                        *a = __dadd_rn(*a, v);
+                    }
+                    double yv;
+                    if (sizeof(V) == 4 && P.lut) {
+                        const int64_t k = (int64_t)raw;
+                        if (k >= 0 && k < P.lut_n) {
+                            yv = lut_s[min((int)k, P.lut_s - 1)];
+                            if (k >= P.lut_s) yv = __ldg(P.lut + k);
+                        } else {
+                            yv = 0.0;
+                            *P.out_of_range = 1;
+                        }
+                    } else {
+                        yv = log2(__dadd_rn(v, P.scalefac));
+                    }
+                    ysum = s == 0 ? yv : __dadd_rn(ysum, yv);
+                    if (STORE_Y) P.y[(size_t)s * P.ld + i] = yv;
                 }
-            } else {
-                yv = log2(__dadd_rn(v, P.scalefac));
             }
-            P.y[(size_t)s * P.ld + i] = yv;
         }
-        if (P.mean) P.mean[i] = __ddiv_rn(sum, (double)P.n);
-        for (int g = 0; g < P.G; ++g)
-            P.gmean[(size_t)g * P.ld + i] = __ddiv_rn(gs_s[g * blockDim.x + threadIdx.x], P.group_size[g]);
+        if (P.mean) P.mean[i] = __ddiv_rn(sum, (double)n);
+        if (P.ymean) P.ymean[i] = __ddiv_rn(ysum, (double)n);
+        for (int g = 0; g < P.G; ++g) {
+            double gsum = GR > 0 ? 0.0 : gs_s[g * blockDim.x + threadIdx.x];
+#pragma unroll
+            for (int gg = 0; gg < GR; ++gg)
+                if (g == gg) gsum = gr[gg];
+            P.gmean[(size_t)g * P.ld + i] = __ddiv_rn(gsum, P.group_size[g]);
+        }
     }
+}
+
+static int launch_preprocess(dfb_ctx* ctx, const dfb_cov* c, PrepParams P, bool store_y) {
+    P.lut_s = (c->dtype == DFB_I32 && P.lut) ? (int)std::min<int64_t>(LUT_SMEM, P.lut_n) : 0;
+    const bool greg = P.G <= 2;  // group sums in registers
+    const size_t smem = ((size_t)P.lut_s + (greg ? 0 : (size_t)P.G * 256)) * sizeof(double) + (size_t)round_up(c->n, 8);
+    auto go = [&](auto kern) -> int {
+        if (smem > 48 * 1024) DFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        KTimer t(ctx, DFB_K_PREP);
+        const int grid = grid_for(c->N, 256, ctx->sm_count, 8);
+        kern<<<grid, 256, smem, ctx->stream>>>(P);
+        return DFB_OK;
+    };
+    if (c->dtype == DFB_I32) {
+        if (store_y) DFB_TRY(greg ? go(preprocess_kernel<int32_t, true, 2>) : go(preprocess_kernel<int32_t, true, 0>));
+        else DFB_TRY(greg ? go(preprocess_kernel<int32_t, false, 2>) : go(preprocess_kernel<int32_t, false, 0>));
+    } else {
+        DFB_TRY(greg ? go(preprocess_kernel<double, true, 2>) : go(preprocess_kernel<double, true, 0>));
+    }
+    DFB_CUDA(cudaGetLastError());
+    return DFB_OK;
+}
+
+int ensure_lut(dfb_ctx* ctx, double scalefac) {
+    constexpr int64_t CTX_LUT = 65536;
+    if (ctx->lut_dev && ctx->lut_n == CTX_LUT && ctx->lut_scalefac == scalefac) return DFB_OK;
+    if (!ctx->lut_dev) DFB_CUDA(cudaMalloc((void**)&ctx->lut_dev, CTX_LUT * sizeof(double)));
+    ctx->lut_n = 0;
+    // glibc log2, the function R calls: coverageProcessed is bit-identical to log2(x + scalefac) evaluated
+    // by R on this host
+    std::vector<double> h((size_t)CTX_LUT);
+    for (int64_t k = 0; k < CTX_LUT; ++k) h[(size_t)k] = log2((double)k + scalefac);
+    DFB_TRY(h2d(ctx, ctx->lut_dev, h.data(), (size_t)CTX_LUT * sizeof(double)));
+    DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->lut_n = CTX_LUT;
+    ctx->lut_scalefac = scalefac;
+    return DFB_OK;
+}
+
+// Materialise log2(x + scalefac) of a handle whose dfb_preprocess skipped it (integer coverage, every value
+// inside the context table -- checked there).
+int ensure_y(dfb_ctx* ctx, const dfb_cov* cov) {
+    dfb_cov* c = const_cast<dfb_cov*>(cov);
+    if (c->y.p || !c->y_lazy || c->N == 0) return DFB_OK;
+    DFB_TRY(ensure_lut(ctx, c->scalefac));
+    DFB_TRY(c->y.alloc(ctx, (size_t)c->n * c->ld));
+    PrepParams P;
+    memset(&P, 0, sizeof P);
+    P.x = c->xi.p;
+    P.ld = c->ld;
+    P.N = c->N;
+    P.n = c->n;
+    P.scalefac = c->scalefac;
+    P.lut = ctx->lut_dev;
+    P.lut_n = ctx->lut_n;
+    P.y = c->y.p;
+    DevBuf<int> oor;  // cannot fire: dfb_preprocess saw every value inside the table
+    DFB_TRY(oor.alloc(ctx, 1));
+    DFB_TRY(oor.zero());
+    P.out_of_range = oor.p;
+    return launch_preprocess(ctx, c, P, true);
 }
 
 }  // namespace dfb
@@ -928,7 +1033,7 @@ int dfb_cov_info(const dfb_cov* c, int64_t* N, int* n, int64_t* chr_len, int* dt
     if (dtype) *dtype = c->dtype;
     if (pos_nruns) *pos_nruns = (int64_t)c->pos.len.size();
     if (n_groups) *n_groups = c->G;
-    if (has_processed) *has_processed = c->y.p != nullptr;
+    if (has_processed) *has_processed = c->y.p != nullptr || c->y_lazy;
     return DFB_OK;
 }
 
@@ -966,12 +1071,20 @@ int dfb_preprocess(dfb_ctx* ctx, dfb_cov* c, double scalefac, const int32_t* gro
     }
     c->scalefac = scalefac;
     c->G = n_groups;
-    DFB_TRY(c->y.alloc(ctx, (size_t)c->n * c->ld));
+    // integer coverage: the log2 matrix is not written (dfb_cov::y_lazy) unless a value falls outside the table
+    bool lazy = ctx->opt_lazy_y && c->dtype == DFB_I32;
+    c->y.release();
+    c->y_lazy = false;
+    c->has_ym = false;
+    if (!lazy) DFB_TRY(c->y.alloc(ctx, (size_t)c->n * c->ld));
+    DFB_TRY(c->ym.alloc(ctx, (size_t)std::max<int64_t>(c->N, 1)));
     if (n_groups > 0) DFB_TRY(c->gmean.alloc(ctx, (size_t)n_groups * c->ld));
     const bool need_mean = !c->has_mean;
     if (need_mean) DFB_TRY(c->mean.alloc(ctx, (size_t)std::max<int64_t>(c->N, 1)));
     if (c->N == 0) {
         c->has_mean = true;
+        c->has_ym = true;
+        c->y_lazy = lazy;
         return DFB_OK;
     }
     // integer coverage: log2 through a host-built table (glibc log2, the function R calls), so
@@ -979,30 +1092,10 @@ int dfb_preprocess(dfb_ctx* ctx, dfb_cov* c, double scalefac, const int32_t* gro
     // context keeps a 64 Ki-entry table per scalefac; a value outside it (flagged by the kernel) falls
     // back to a table sized from the data's min/max, or to device log2 beyond 2^22.
     DevBuf<double> lut;
-    const double* lut_p = nullptr;
-    int64_t lut_n = 0;
     DevBuf<int> oor;
     DFB_TRY(oor.alloc(ctx, 1));
     DFB_TRY(oor.zero());
-    auto build_lut = [&](int64_t entries, double* dst_dev) -> int {
-        std::vector<double> h((size_t)entries);
-        for (int64_t k = 0; k < entries; ++k) h[(size_t)k] = log2((double)k + scalefac);
-        DFB_TRY(h2d(ctx, dst_dev, h.data(), (size_t)entries * sizeof(double)));
-        DFB_CUDA(cudaStreamSynchronize(ctx->stream));
-        return DFB_OK;
-    };
-    if (c->dtype == DFB_I32) {
-        constexpr int64_t CTX_LUT = 65536;
-        if (!ctx->lut_dev || ctx->lut_scalefac != scalefac) {
-            if (!ctx->lut_dev) DFB_CUDA(cudaMalloc((void**)&ctx->lut_dev, CTX_LUT * sizeof(double)));
-            ctx->lut_n = 0;
-            DFB_TRY(build_lut(CTX_LUT, ctx->lut_dev));
-            ctx->lut_n = CTX_LUT;
-            ctx->lut_scalefac = scalefac;
-        }
-        lut_p = ctx->lut_dev;
-        lut_n = ctx->lut_n;
-    }
+    if (c->dtype == DFB_I32) DFB_TRY(ensure_lut(ctx, scalefac));
     DevBuf<int32_t> grp;
     DevBuf<double> gsz;
     if (n_groups > 0) {
@@ -1018,38 +1111,22 @@ int dfb_preprocess(dfb_ctx* ctx, dfb_cov* c, double scalefac, const int32_t* gro
     P.N = c->N;
     P.n = c->n;
     P.scalefac = scalefac;
-    P.lut = lut_n ? lut_p : nullptr;
-    P.lut_n = lut_n;
+    P.lut = c->dtype == DFB_I32 ? ctx->lut_dev : nullptr;
+    P.lut_n = c->dtype == DFB_I32 ? ctx->lut_n : 0;
     P.group = n_groups ? grp.p : nullptr;
     P.group_size = n_groups ? gsz.p : nullptr;
     P.G = n_groups;
     P.y = c->y.p;
     P.mean = need_mean ? c->mean.p : nullptr;
     P.gmean = n_groups ? c->gmean.p : nullptr;
+    P.ymean = c->ym.p;
     P.out_of_range = oor.p;
-    const size_t smem = (size_t)n_groups * 256 * sizeof(double);
-    auto launch = [&]() -> int {
-        KTimer t(ctx, DFB_K_PREP);
-        const int grid = grid_for(c->N, 256, ctx->sm_count, 16);
-        if (c->dtype == DFB_I32) {
-            if (smem > 48 * 1024)
-                DFB_CUDA(cudaFuncSetAttribute(preprocess_kernel<int32_t>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)smem));
-            preprocess_kernel<int32_t><<<grid, 256, smem, ctx->stream>>>(P);
-        } else {
-            if (smem > 48 * 1024)
-                DFB_CUDA(cudaFuncSetAttribute(preprocess_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                              (int)smem));
-            preprocess_kernel<double><<<grid, 256, smem, ctx->stream>>>(P);
-        }
-        return DFB_OK;
-    };
-    DFB_TRY(launch());
-    DFB_CUDA(cudaGetLastError());
+    DFB_TRY(launch_preprocess(ctx, c, P, !lazy));
     int flagged = 0;
     DFB_TRY(d2h(ctx, &flagged, oor.p, sizeof flagged));  // synchronises: group arrays are locals
     if (flagged) {
-        // rare: coverage beyond the context table.  Size a table from the data, or use device log2.
+        // rare: coverage beyond the context table.  Size a table from the data, or use device log2; the log2
+        // matrix is materialised in this case (the lazy readers only know the context table).
         DevBuf<long long> mm;
         DFB_TRY(mm.alloc(ctx, 2));
         long long init[2] = {LLONG_MAX, LLONG_MIN};
@@ -1064,17 +1141,26 @@ int dfb_preprocess(dfb_ctx* ctx, dfb_cov* c, double scalefac, const int32_t* gro
         P.lut = nullptr;
         P.lut_n = 0;
         if (got[0] >= 0 && got[1] < (1ll << 22)) {
-            DFB_TRY(lut.alloc(ctx, (size_t)got[1] + 1));
-            DFB_TRY(build_lut(got[1] + 1, lut.p));
+            std::vector<double> h((size_t)got[1] + 1);
+            for (int64_t k = 0; k <= got[1]; ++k) h[(size_t)k] = log2((double)k + scalefac);
+            DFB_TRY(lut.alloc(ctx, h.size()));
+            DFB_TRY(h2d(ctx, lut.p, h.data(), h.size() * sizeof(double)));
+            DFB_CUDA(cudaStreamSynchronize(ctx->stream));
             P.lut = lut.p;
             P.lut_n = got[1] + 1;
         }
+        if (lazy) {
+            lazy = false;
+            DFB_TRY(c->y.alloc(ctx, (size_t)c->n * c->ld));
+            P.y = c->y.p;
+        }
         DFB_TRY(oor.zero());
-        DFB_TRY(launch());
-        DFB_CUDA(cudaGetLastError());
+        DFB_TRY(launch_preprocess(ctx, c, P, true));
         DFB_CUDA(cudaStreamSynchronize(ctx->stream));
     }
     c->has_mean = true;
+    c->has_ym = true;
+    c->y_lazy = lazy;
     c->has_f = false;
     c->a16_center = -1;  // the log2 matrix changed: the null scan's fp16 operand is stale
     return DFB_OK;
@@ -1083,10 +1169,11 @@ int dfb_preprocess(dfb_ctx* ctx, dfb_cov* c, double scalefac, const int32_t* gro
 int dfb_cov_get_processed_column(const dfb_cov* c, int sample, double* out) {
     DFB_REQUIRE(c && out, "dfb_cov_get_processed_column: NULL argument");
     DFB_REQUIRE(sample >= 0 && sample < c->n, "sample %d out of range", sample);
-    if (!c->y.p) {
+    if (!c->y.p && !c->y_lazy) {
         set_error("coverageProcessed is not available: run dfb_preprocess first");
         return DFB_ESTATE;
     }
+    DFB_TRY(ensure_y(c->ctx, c));
     return d2h_big(c->ctx, out, c->y.p + (size_t)sample * c->ld, (size_t)c->N * sizeof(double));
 }
 

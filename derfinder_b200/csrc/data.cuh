@@ -31,7 +31,14 @@ struct dfb_cov {
     int dtype = DFB_I32;
     dfb::DevBuf<int32_t> xi;  // [n][ld] raw filtered coverage (dtype I32)
     dfb::DevBuf<double> xd;   // [n][ld] raw filtered coverage (dtype F64, e.g. normalised)
-    dfb::DevBuf<double> y;    // [n][ld] log2(x + scalefac)   (after dfb_preprocess)
+    dfb::DevBuf<double> y;    // [n][ld] log2(x + scalefac)   (after dfb_preprocess; see y_lazy)
+    // Integer coverage: dfb_preprocess does not write the log2 matrix at all (8 bytes per element that the hot
+    // path would write once and read once).  The observed-F kernel and the refinement of the null scan read the
+    // int32 coverage through the host-built log2 table instead; ensure_y() materialises `y` for everything else
+    // (coverageProcessed read-back, the dense FP64 fallback, the first-generation tensor kernels).
+    bool y_lazy = false;
+    dfb::DevBuf<double> ym;   // [N] (sum_k y[k]) / n in sample order: the row mean of the F-stat contract
+    bool has_ym = false;
     dfb::DevBuf<double> mean; // [N] meanCoverage
     bool has_mean = false;
     int G = 0;
@@ -84,6 +91,13 @@ struct dfb_nulls {
 };
 
 namespace dfb {
+
+// ---- cov.cu
+// the log2 matrix of a handle whose dfb_preprocess left it un-materialised (dfb_cov::y_lazy); no-op otherwise
+int ensure_y(dfb_ctx* ctx, const dfb_cov* cov);
+// the context's host-built log2 table for this scalefac (64 Ki entries), rebuilt when the scalefac changed
+int ensure_lut(dfb_ctx* ctx, double scalefac);
+constexpr int LUT_SMEM = 4096;  // table entries the streaming kernels keep in shared memory
 
 // ---- fstat.cu
 struct ModelBasis {

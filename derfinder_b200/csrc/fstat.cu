@@ -22,6 +22,7 @@
 // exceedance values, compacted per (permutation, tile) -- null F-stats never reach HBM.
 #include <cuda_fp16.h>
 #include <math.h>
+#include <type_traits>
 
 #include <algorithm>
 
@@ -162,6 +163,11 @@ struct FstatParams {
     int a16_ka;
     double* a16_yy;
     double* a16_m;
+    // observed scan only: the row mean of the contract as dfb_preprocess computed it (same chain of additions),
+    // and -- when the log2 matrix is not materialised -- the integer coverage plus the log2 table
+    const double* ym;
+    const int32_t* xi;
+    const double* lut;
 };
 
 template <int PC, int BP, int BM, int NT>
@@ -476,40 +482,54 @@ static void fill_common(FstatParams& P, const dfb_cov* cov, const ModelBasis& mb
     P.inv_dfden = 1.0 / P.dfden;
 }
 
-// Observed statistics (identity labelling): one thread per base, the log2 matrix is streamed once
-// (coalesced along bases for every sample), Q is broadcast from shared memory.  HBM-bound:
-// 8*n bytes read + 8 bytes written per base.  Same arithmetic contract as the tiled kernel.
-template <int PC, bool EMIT>
-__global__ void __launch_bounds__(256) fstat_observed_kernel(const FstatParams P) {
-    extern __shared__ __align__(16) double Qs_obs[];  // [n][pp]
+// Observed statistics (identity labelling): one thread per base, the coverage is streamed ONCE (coalesced
+// along bases for every sample) -- the row mean of the contract comes from dfb_preprocess (same chain of
+// additions), so there is no second pass -- and Q is broadcast from shared memory.  HBM-bound: 8*n bytes read
+// per base from the log2 matrix, or 4*n from the integer coverage when the log2 matrix is not materialised
+// (SRCI: values go through the log2 table, whose head sits in shared memory).  Same arithmetic contract as the
+// tiled kernel.
+template <int PC, bool EMIT, bool SRCI>
+__global__ void __launch_bounds__(256, 3) fstat_observed_kernel(const FstatParams P) {
+    extern __shared__ __align__(16) double Qs_obs[];  // [n][pp], then the table head [LUT_SMEM] (SRCI)
     const int n = P.n;
     for (int e = threadIdx.x; e < n * P.pp; e += blockDim.x) Qs_obs[e] = P.qpad[e];
+    const double* lut_s = Qs_obs + (((size_t)n * P.pp + 1) & ~(size_t)1);
+    if (SRCI)
+        for (int e = threadIdx.x; e < LUT_SMEM; e += blockDim.x) const_cast<double*>(lut_s)[e] = P.lut[e];
     __syncthreads();
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < P.N;
          base += (int64_t)gridDim.x * blockDim.x) {
-        double acc = P.Y[base];
-        for (int k = 1; k < n; ++k) acc = __dadd_rn(acc, P.Y[(size_t)k * P.ld + base]);
-        const double m = P.center ? __ddiv_rn(acc, (double)n) : 0.0;
+        const double m = P.center ? P.ym[base] : 0.0;
         double yy = 0.0, s0 = 0.0, sd = 0.0;
         for (int c = 0; c < P.chunks; ++c) {
             double S[PC];
 #pragma unroll
             for (int j = 0; j < PC; ++j) S[j] = 0.0;
-            if (!EMIT) {
-                for (int k = 0; k < n; ++k) {
-                    const double v = __dsub_rn(P.Y[(size_t)k * P.ld + base], m);  // L1/L2 hit after the first pass
-                    if (c == 0) yy = fma(v, v, yy);
-                    const double* q = Qs_obs + (size_t)k * P.pp + c * PC;
-#pragma unroll
-                    for (int j = 0; j < PC; ++j) S[j] = fma(v, q[j], S[j]);
-                }
-            }
             const bool emit = EMIT && c == 0;
             uint4* arow = emit ? reinterpret_cast<uint4*>(P.a16 + (size_t)base * P.a16_ka) : nullptr;
             // sixteen samples per step: sixteen loads in flight and, when the fp16 operand is emitted, one whole
             // 32-byte sector of the base's row per step (two 16-byte stores; half sectors would make L2 read
             // the other half back from DRAM)
-            for (int k0 = 0; EMIT && k0 < n; k0 += 16) {
+            for (int k0 = 0; k0 < n; k0 += 16) {
+                double yv[16];
+                // the sixteen loads are issued back to back (clamped row index instead of a predicate per load:
+                // with predicates the compiler sinks every load next to its table look-up and the warp waits for
+                // each of them in turn), then the table look-ups
+                if (SRCI) {
+                    int32_t raw[16];
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) raw[e] = __ldg(P.xi + (size_t)min(k0 + e, n - 1) * P.ld + base);
+                    asm volatile("" ::: "memory");
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) {
+                        yv[e] = lut_s[min(raw[e], LUT_SMEM - 1)];
+                        if (raw[e] >= LUT_SMEM) yv[e] = __ldg(P.lut + raw[e]);  // rare: beyond the table head
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; ++e) yv[e] = __ldg(P.Y + (size_t)min(k0 + e, n - 1) * P.ld + base);
+                    asm volatile("" ::: "memory");
+                }
                 __half2 h2[8];
 #pragma unroll
                 for (int e = 0; e < 16; e += 2) {
@@ -519,7 +539,7 @@ __global__ void __launch_bounds__(256) fstat_observed_kernel(const FstatParams P
                         const int k = k0 + e + u;
                         v2[u] = 0.0;
                         if (k < n) {
-                            const double v = __dsub_rn(P.Y[(size_t)k * P.ld + base], m);  // L1/L2 hit after the first pass
+                            const double v = __dsub_rn(yv[e + u], m);
                             if (c == 0) yy = fma(v, v, yy);
                             const double* q = Qs_obs + (size_t)k * P.pp + c * PC;
 #pragma unroll
@@ -527,7 +547,7 @@ __global__ void __launch_bounds__(256) fstat_observed_kernel(const FstatParams P
                             v2[u] = v;
                         }
                     }
-                    h2[e >> 1] = __halves2half2(__double2half(v2[0]), __double2half(v2[1]));
+                    if (EMIT) h2[e >> 1] = __halves2half2(__double2half(v2[0]), __double2half(v2[1]));
                 }
                 if (emit) {
                     arow[k0 >> 3] = reinterpret_cast<const uint4*>(h2)[0];
@@ -589,7 +609,15 @@ int fstat_observed(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, doubl
             cw->a16_rows = rows_pad;
         }
     }
-    const size_t smem = mb.qpad.size() * sizeof(double);
+    DFB_REQUIRE(cov->has_ym, "internal error: the row means of the log2 matrix are missing");
+    P.ym = cov->ym.p;
+    const bool srci = cov->y_lazy && !cov->y.p;  // log2 matrix not materialised: integer coverage + table
+    if (srci) {
+        DFB_TRY(ensure_lut(ctx, cov->scalefac));
+        P.xi = cov->xi.p;
+        P.lut = ctx->lut_dev;
+    }
+    const size_t smem = (((mb.qpad.size() + 1) & ~(size_t)1) + (srci ? (size_t)LUT_SMEM : 0)) * sizeof(double);
     const int grid = grid_for(cov->N, 256, ctx->sm_count, 8);
     auto launch = [&](auto kern) -> int {
         if (smem > 48 * 1024) DFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -597,23 +625,23 @@ int fstat_observed(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, doubl
         kern<<<grid, 256, smem, ctx->stream>>>(P);
         return DFB_OK;
     };
-    if (P.a16) {
+    auto by_src = [&](auto emit_tag, auto pc_tag) -> int {
+        constexpr bool E = decltype(emit_tag)::value;
+        constexpr int PCV = decltype(pc_tag)::value;
+        if (srci) return launch(fstat_observed_kernel<PCV, E, true>);
+        return launch(fstat_observed_kernel<PCV, E, false>);
+    };
+    auto by_pc = [&](auto emit_tag) -> int {
         switch (mb.pc) {
-            case 2: DFB_TRY(launch(fstat_observed_kernel<2, true>)); break;
-            case 3: DFB_TRY(launch(fstat_observed_kernel<3, true>)); break;
-            case 4: DFB_TRY(launch(fstat_observed_kernel<4, true>)); break;
-            case 5: DFB_TRY(launch(fstat_observed_kernel<5, true>)); break;
-            default: DFB_TRY(launch(fstat_observed_kernel<6, true>)); break;
+            case 2: return by_src(emit_tag, std::integral_constant<int, 2>());
+            case 3: return by_src(emit_tag, std::integral_constant<int, 3>());
+            case 4: return by_src(emit_tag, std::integral_constant<int, 4>());
+            case 5: return by_src(emit_tag, std::integral_constant<int, 5>());
+            default: return by_src(emit_tag, std::integral_constant<int, 6>());
         }
-    } else {
-        switch (mb.pc) {
-            case 2: DFB_TRY(launch(fstat_observed_kernel<2, false>)); break;
-            case 3: DFB_TRY(launch(fstat_observed_kernel<3, false>)); break;
-            case 4: DFB_TRY(launch(fstat_observed_kernel<4, false>)); break;
-            case 5: DFB_TRY(launch(fstat_observed_kernel<5, false>)); break;
-            default: DFB_TRY(launch(fstat_observed_kernel<6, false>)); break;
-        }
-    }
+    };
+    if (P.a16) DFB_TRY(by_pc(std::true_type()));
+    else DFB_TRY(by_pc(std::false_type()));
     DFB_CUDA(cudaGetLastError());
     // qd is released stream-ordered after the kernel
     return DFB_OK;
@@ -623,6 +651,7 @@ int fstat_observed(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, doubl
 int fstat_perm_batch(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, const double* qpad_dev,
                      double adjust_f, const int32_t* idx_dev, int64_t B, double lo, double hi, bool two_sided,
                      size_t capacity_hint, PermBatch* out) {
+    DFB_TRY(ensure_y(ctx, cov));
     const int sides = two_sided ? 2 : 1;
     const int tb = fstat_tile_bases(cov->n);
     out->rows = B * sides;

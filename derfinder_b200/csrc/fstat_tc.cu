@@ -1152,6 +1152,7 @@ bool screen_supported(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& 
 int fstat_perm_batch_screen(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, const double* q_dev /*[n][p]*/,
                             double adjust_f, const int32_t* idx_dev, int64_t B, double hi, size_t capacity_hint,
                             PermBatch* out, int64_t* ncand_out) {
+    DFB_TRY(ensure_y(ctx, cov));  // the first-generation kernels read the materialised log2 matrix
     ScreenGeom G;
     const size_t limit = std::min<size_t>(ctx->smem_optin, 200 * 1024);
     if (!screen_geometry(cov, mb, B, limit, &G)) {
@@ -1457,6 +1458,7 @@ static int launch_fused(dfb_ctx* ctx, const FusedParams& F, int grid) {
 int fstat_perm_batch_fused(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, const double* q_dev /*[n][p]*/,
                            double adjust_f, const int32_t* idx_dev, int64_t B, double hi, size_t capacity_hint,
                            PermBatch* out, bool defer_check) {
+    DFB_TRY(ensure_y(ctx, cov));  // the first-generation kernels read the materialised log2 matrix
     FusedGeom G;
     if (!fused_geometry(ctx, cov, mb, B, &G)) {
         set_error("fused geometry does not fit (internal error)");

@@ -156,7 +156,9 @@ __global__ void __launch_bounds__(128) build_qb16_kernel(const double* __restric
 // ------------------------------------------------------------------------------------------
 
 struct Null2Params {
-    const double* Y;
+    const double* Y;       // log2 matrix, or nullptr when it is not materialised:
+    const int32_t* xi;     //   then the integer coverage [n][ld] ...
+    const double* lut;     //   ... and the log2 table (every value is inside it, checked by dfb_preprocess)
     int64_t ld, N;
     Null2Geom G;
     const unsigned char* qb;    // [chunks][KB][nmma][128 B]
@@ -546,7 +548,9 @@ __global__ void __launch_bounds__(n2_max_threads(PT - J0), 1) fstat_null2_kernel
                     thr_next = __int_as_float(0x7f800000);
                     if (i + 1 < my_tiles && b_nx < P.N) thr_next = P.thr[b_nx];
                 }
-                const double* yglob = P.Y + base0 + quarter * 32;  // candidates re-read Y (L2)
+                // candidates re-read their row (L2): the log2 matrix, or the integer coverage through the table
+                const double* yglob = P.Y ? P.Y + base0 + quarter * 32 : nullptr;
+                const int32_t* xglob = P.Y ? nullptr : P.xi + base0 + quarter * 32;
                 for (int c = 0; c < cgl; ++c) {
                     const bool mine = turn == hsub;
                     if (++turn == ew) turn = 0;
@@ -657,7 +661,9 @@ __global__ void __launch_bounds__(n2_max_threads(PT - J0), 1) fstat_null2_kernel
                                     const int k = k0 + e16;
                                     if (k < n) {
                                         const uint32_t row = (ixw[e16 >> 2] >> ((e16 & 3) * 8)) & 0xffu;
-                                        const double yv = __dsub_rn(yglob[(size_t)k * P.ld + bl], m_c);
+                                        const double yraw = yglob ? yglob[(size_t)k * P.ld + bl]
+                                                                  : __ldg(P.lut + xglob[(size_t)k * P.ld + bl]);
+                                        const double yv = __dsub_rn(yraw, m_c);
                                         const double2* qrow = reinterpret_cast<const double2*>(Qs + (size_t)row * QS);
 #pragma unroll
                                         for (int j2 = 0; j2 < QS / 2; ++j2) {
@@ -847,6 +853,7 @@ static int ensure_a16(dfb_ctx* ctx, const dfb_cov* cov_c, int KA, int center, in
     dfb_cov* cov = const_cast<dfb_cov*>(cov_c);
     if (cov->a16.p && cov->a16_center == center && cov->a16_ka == KA && cov->a16_rows == rows_pad) return DFB_OK;
     cov->a16_center = -1;
+    DFB_TRY(ensure_y(ctx, cov));  // stand-alone builder (dfb_fstats was not run with this model): reads the log2 matrix
     DFB_TRY(cov->a16.alloc(ctx, (size_t)rows_pad * KA));
     DFB_TRY(cov->a16_yy.alloc(ctx, (size_t)std::max<int64_t>(cov->N, 1)));
     DFB_TRY(cov->a16_m.alloc(ctx, (size_t)std::max<int64_t>(cov->N, 1)));
@@ -914,6 +921,12 @@ int fstat_perm_batch_null2(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& m
     Null2Params F;
     memset(&F, 0, sizeof F);
     F.Y = cov->y.p;
+    if (!F.Y) {
+        DFB_REQUIRE(cov->y_lazy, "coverageProcessed is missing: run dfb_preprocess first");
+        DFB_TRY(ensure_lut(ctx, cov->scalefac));
+        F.xi = cov->xi.p;
+        F.lut = ctx->lut_dev;
+    }
     F.ld = cov->ld;
     F.N = cov->N;
     F.G = G;

@@ -28,7 +28,7 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
                            const std::function<void()>* after_first_launch = nullptr) {
     const bool after_first_launch_given = after_first_launch != nullptr;
     *out = nullptr;
-    DFB_REQUIRE(cov->y.p != nullptr, "coverageProcessed is missing: run dfb_preprocess first");
+    DFB_REQUIRE(cov->y.p != nullptr || cov->y_lazy, "coverageProcessed is missing: run dfb_preprocess first");
     DFB_REQUIRE(B >= 0 && (perm_idx || B == 0), "perm_idx is NULL");
     DFB_REQUIRE(lo <= hi, "cutoff pair must be sorted (L <= U)");
     ModelBasis mb;
@@ -682,7 +682,7 @@ extern "C" {
 int dfb_fstats(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const double* mod0, int p0, double adjust_f,
                double* fstats_out) {
     DFB_REQUIRE(ctx && cov, "dfb_fstats: NULL argument");
-    if (!cov->y.p) {
+    if (!cov->y.p && !cov->y_lazy) {
         set_error("preprocessCoverage() has not been run on this coverage (coverageProcessed is missing)");
         return DFB_ESTATE;
     }
@@ -1200,7 +1200,7 @@ int dfb_debug_screen(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p, const
                      const int32_t* perm_idx, int64_t B, double cutoff, int64_t* n_exact_dense,
                      int64_t* n_exact_screen, int64_t* n_candidates, int64_t* n_mask_diff) {
     DFB_REQUIRE(ctx && cov && perm_idx && B > 0, "dfb_debug_screen: bad argument");
-    DFB_REQUIRE(cov->y.p != nullptr, "coverageProcessed is missing: run dfb_preprocess first");
+    DFB_REQUIRE(cov->y.p != nullptr || cov->y_lazy, "coverageProcessed is missing: run dfb_preprocess first");
     ModelBasis mb;
     DFB_TRY(build_model_basis(mod, cov->n, p, mod0, p0, &mb));
     if (!screen_supported(ctx, cov, mb, -cutoff, cutoff, adjust_f)) {

@@ -438,3 +438,61 @@ def test_rail_matrix_from_bigwig(dfb, eng, tmp_path, kind, compress):
         mem = dfb.railMatrix(["chr21"], {"chr21": mean_rle}, {"chr21": cols}, L_=Lval, cutoff=2.2, maxClusterGap=3000,
                              totalMapped=tm, engine=eng)["chr21"]
         assert np.array_equal(got["coverageMatrix"], mem["coverageMatrix"])
+
+
+# ---------------------------------------------------------------------------------------------
+# log2 matrix not materialised (integer coverage read through the log2 table) == materialised
+
+
+@pytest.mark.parametrize("n,extra,N,B,alpha", [(12, 0, 30000, 40, 0.05), (60, 3, 9000, 200, 1e-3)])
+def test_lazy_log2_matrix_equals_materialised(dfb, n, extra, N, B, alpha):
+    """dfb_preprocess leaves the log2 matrix un-materialised for integer coverage: the observed-F kernel and
+    the refinement of the null scan read the int32 coverage through the host-built log2 table.  Same bits as
+    the materialised path everywhere (F, regions, nulls, p-values), coverageProcessed still readable, and a
+    coverage value beyond the context table falls back to the materialised matrix."""
+    rng = np.random.default_rng(1234 + n)
+    cov, position, group, models = synth(rng, N, n, p_extra=extra, seg=[N // 3, N - N // 3])
+    cov[7, 0] = 5000  # beyond the shared-memory head of the table, inside the context table
+    perm = random_perms(rng, B, n)
+    cut = dfb.calcFstatCutoff("theoretical", alpha, models=models)
+    out = {}
+    for lazy in (1, 0):
+        e = dfb.Engine(0)
+        try:
+            e.set_option("lazy_y", lazy)
+            prep = dfb.preprocessCoverage(dict(coverage=cov, position=position), groupInfo=group, engine=e)
+            has = C.c_int(0)
+            e.lib.dfb_cov_info(prep["coverageProcessed"].h, None, None, None, None, None, None, C.byref(has))
+            assert has.value == 1
+            F = dfb.calculateStats(prep, models, engine=e)
+            res = dfb.calculatePvalues(prep, models, F, permIndex=perm, cutoff=cut, engine=e)
+            Y = prep["coverageProcessed"].processed()
+            out[lazy] = (np.asarray(F), res, Y, np.asarray(prep["meanCoverage"]))
+        finally:
+            e.close()
+    assert np.array_equal(out[1][0], out[0][0])
+    assert np.array_equal(out[1][2], out[0][2])
+    assert np.array_equal(out[1][2], O.log2_libm(cov.astype(np.float64) + 32.0))
+    assert np.array_equal(out[1][3], out[0][3])
+    assert_pipeline_equal(out[1][1], out[0][1])
+    e = dfb.Engine(0)
+    try:
+        oprep = O.preprocess_coverage(cov, position, groupInfo=group)
+        ores = O.calculate_pvalues(oprep, models["mod"], models["mod0"], out[1][0], perm, cut,
+                                   fstat_idx_fn=oracle_idx_fn(e, models["mod"], models["mod0"], 0.0))
+        assert_pipeline_equal(out[1][1], ores)
+    finally:
+        e.close()
+
+
+def test_lazy_log2_matrix_out_of_table(dfb, eng):
+    rng = np.random.default_rng(99)
+    cov, position, group, models = synth(rng, 4000, 10)
+    cov[11, 3] = 70000  # outside the 64 Ki-entry context table: materialised fallback with a data-sized table
+    prep = dfb.preprocessCoverage(dict(coverage=cov, position=position), groupInfo=group, engine=eng)
+    Y = prep["coverageProcessed"].processed()
+    assert np.array_equal(Y, O.log2_libm(cov.astype(np.float64) + 32.0))
+    F = np.asarray(dfb.calculateStats(prep, models, engine=eng))
+    Fo = O.fstats_projector(O.log2_libm(cov.astype(np.float64) + 32.0), models["mod"], models["mod0"])
+    ok = np.isfinite(Fo) & (np.abs(Fo) > 1e-8)
+    assert np.allclose(F[ok], Fo[ok], rtol=F_RTOL)
