@@ -778,6 +778,77 @@ __global__ void __launch_bounds__(256) preprocess_kernel(const PrepParams P) {
     }
 }
 
+// Integer coverage with a log2 table and at most two groups -- the hot configuration.  Sums are integer (exact, so
+// identical to the left-to-right double sums while every partial sum stays below 2^53: n <= 255 values of 31 bits),
+// the second group's sum is selected by a bit mask of the samples and the first one is the difference; one range /
+// table-head test per eight samples instead of one per value.
+template <bool STORE_Y>
+__global__ void __launch_bounds__(256) preprocess_i32_kernel(const PrepParams P) {
+    extern __shared__ double prep_s[];  // [lut_s] table head, then one byte of group-2 membership bits per 8 samples
+    double* lut_s = prep_s;
+    unsigned char* gm_s = reinterpret_cast<unsigned char*>(prep_s + P.lut_s);
+    const int n = P.n;
+    for (int e = threadIdx.x; e < P.lut_s; e += blockDim.x) lut_s[e] = P.lut[e];
+    for (int e = threadIdx.x; e < (n + 7) / 8; e += blockDim.x) {
+        unsigned m = 0;
+        for (int b = 0; b < 8; ++b)
+            if (P.G > 1 && e * 8 + b < n && P.group[e * 8 + b] == 1) m |= 1u << b;
+        gm_s[e] = (unsigned char)m;
+    }
+    __syncthreads();
+    const int32_t* __restrict__ x = reinterpret_cast<const int32_t*>(P.x);
+    const int lut_n = (int)min(P.lut_n, (int64_t)INT32_MAX), lut_h = P.lut_s;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < P.N; i += (int64_t)gridDim.x * blockDim.x) {
+        long long isum = 0, g1 = 0;
+        double ysum = 0.0;  // 0.0 + y == y bit for bit (log2 never returns -0.0)
+        bool bad = false;
+        auto step = [&](const int s0, auto full_tag) {
+            constexpr bool FULL = decltype(full_tag)::value;
+            int32_t raw[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) raw[e] = __ldg(x + (size_t)(FULL ? s0 + e : min(s0 + e, n - 1)) * P.ld + i);
+            asm volatile("" ::: "memory");
+            const unsigned gm = gm_s[s0 >> 3];
+            int mx = raw[0], mn = raw[0];
+#pragma unroll
+            for (int e = 1; e < 8; ++e) {
+                mx = max(mx, raw[e]);
+                mn = min(mn, raw[e]);
+            }
+            double yv[8];
+            if (mn >= 0 && mx < lut_h) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) yv[e] = lut_s[raw[e]];
+            } else {  // rare: beyond the table head, or outside the table (flagged: the caller re-runs)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int k = raw[e];
+                    yv[e] = 0.0;
+                    if (k >= 0 && k < lut_n) yv[e] = k < lut_h ? lut_s[k] : __ldg(P.lut + k);
+                    else bad = true;
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                if (FULL || s0 + e < n) {
+                    isum += raw[e];
+                    g1 += ((gm >> e) & 1u) ? raw[e] : 0;
+                    ysum = __dadd_rn(ysum, yv[e]);
+                    if (STORE_Y) P.y[(size_t)(s0 + e) * P.ld + i] = yv[e];
+                }
+            }
+        };
+        int s0 = 0;
+        for (; s0 + 8 <= n; s0 += 8) step(s0, std::true_type());
+        if (s0 < n) step(s0, std::false_type());
+        if (P.mean) P.mean[i] = __ddiv_rn((double)isum, (double)n);
+        if (P.ymean) P.ymean[i] = __ddiv_rn(ysum, (double)n);
+        if (P.G > 0) P.gmean[i] = __ddiv_rn((double)(isum - g1), P.group_size[0]);
+        if (P.G > 1) P.gmean[(size_t)P.ld + i] = __ddiv_rn((double)g1, P.group_size[1]);
+        if (bad) *P.out_of_range = 1;
+    }
+}
+
 static int launch_preprocess(dfb_ctx* ctx, const dfb_cov* c, PrepParams P, bool store_y) {
     P.lut_s = (c->dtype == DFB_I32 && P.lut) ? (int)std::min<int64_t>(LUT_SMEM, P.lut_n) : 0;
     const bool greg = P.G <= 2;  // group sums in registers
@@ -789,7 +860,10 @@ static int launch_preprocess(dfb_ctx* ctx, const dfb_cov* c, PrepParams P, bool 
         kern<<<grid, 256, smem, ctx->stream>>>(P);
         return DFB_OK;
     };
-    if (c->dtype == DFB_I32) {
+    if (c->dtype == DFB_I32 && P.lut && P.G <= 2) {
+        if (store_y) DFB_TRY(go(preprocess_i32_kernel<true>));
+        else DFB_TRY(go(preprocess_i32_kernel<false>));
+    } else if (c->dtype == DFB_I32) {
         if (store_y) DFB_TRY(greg ? go(preprocess_kernel<int32_t, true, 2>) : go(preprocess_kernel<int32_t, true, 0>));
         else DFB_TRY(greg ? go(preprocess_kernel<int32_t, false, 2>) : go(preprocess_kernel<int32_t, false, 0>));
     } else {

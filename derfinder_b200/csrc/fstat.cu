@@ -490,12 +490,16 @@ static void fill_common(FstatParams& P, const dfb_cov* cov, const ModelBasis& mb
 // tiled kernel.
 template <int PC, bool EMIT, bool SRCI>
 __global__ void __launch_bounds__(256, 3) fstat_observed_kernel(const FstatParams P) {
-    extern __shared__ __align__(16) double Qs_obs[];  // [n][pp], then the table head [LUT_SMEM] (SRCI)
+    constexpr int QS = (PC + 1) & ~1;  // row stride of a column chunk in shared memory: 16-byte aligned rows
+    extern __shared__ __align__(16) double Qs_obs[];  // [chunks][n][QS], then the table head [LUT_SMEM] (SRCI)
     const int n = P.n;
-    for (int e = threadIdx.x; e < n * P.pp; e += blockDim.x) Qs_obs[e] = P.qpad[e];
-    const double* lut_s = Qs_obs + (((size_t)n * P.pp + 1) & ~(size_t)1);
+    for (int e = threadIdx.x; e < P.chunks * n * QS; e += blockDim.x) {
+        const int c = e / (n * QS), r = e - c * n * QS, k = r / QS, j = r - k * QS;
+        Qs_obs[e] = j < PC ? P.qpad[(size_t)k * P.pp + c * PC + j] : 0.0;
+    }
+    double* lut_s = Qs_obs + (size_t)P.chunks * n * QS;
     if (SRCI)
-        for (int e = threadIdx.x; e < LUT_SMEM; e += blockDim.x) const_cast<double*>(lut_s)[e] = P.lut[e];
+        for (int e = threadIdx.x; e < LUT_SMEM; e += blockDim.x) lut_s[e] = P.lut[e];
     __syncthreads();
     for (int64_t base = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; base < P.N;
          base += (int64_t)gridDim.x * blockDim.x) {
@@ -505,57 +509,73 @@ __global__ void __launch_bounds__(256, 3) fstat_observed_kernel(const FstatParam
             double S[PC];
 #pragma unroll
             for (int j = 0; j < PC; ++j) S[j] = 0.0;
-            const bool emit = EMIT && c == 0;
-            uint4* arow = emit ? reinterpret_cast<uint4*>(P.a16 + (size_t)base * P.a16_ka) : nullptr;
-            // sixteen samples per step: sixteen loads in flight and, when the fp16 operand is emitted, one whole
-            // 32-byte sector of the base's row per step (two 16-byte stores; half sectors would make L2 read
-            // the other half back from DRAM)
-            for (int k0 = 0; k0 < n; k0 += 16) {
+            const double* Qc = Qs_obs + (size_t)c * n * QS;
+            uint4* arow = EMIT ? reinterpret_cast<uint4*>(P.a16 + (size_t)base * P.a16_ka) : nullptr;
+            // Sixteen samples per step: the sixteen loads are issued back to back (no predicate per load -- with
+            // predicates the compiler sinks every load next to its table look-up and the warp waits for each of
+            // them in turn), then the table look-ups, then the products.  When the fp16 operand is emitted a step
+            // writes one whole 32-byte sector of the base's row (two 16-byte stores; half sectors would make L2
+            // read the other half back from DRAM).  FULL: all sixteen samples exist; FIRST: first column chunk
+            // (|yc|^2 and the fp16 row are produced there).
+            auto step = [&](const int k0, auto full_tag, auto first_tag) {
+                constexpr bool FULL = decltype(full_tag)::value, FIRST = decltype(first_tag)::value;
                 double yv[16];
-                // the sixteen loads are issued back to back (clamped row index instead of a predicate per load:
-                // with predicates the compiler sinks every load next to its table look-up and the warp waits for
-                // each of them in turn), then the table look-ups
                 if (SRCI) {
                     int32_t raw[16];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) raw[e] = __ldg(P.xi + (size_t)min(k0 + e, n - 1) * P.ld + base);
+                    for (int e = 0; e < 16; ++e)
+                        raw[e] = __ldg(P.xi + (size_t)(FULL ? k0 + e : min(k0 + e, n - 1)) * P.ld + base);
                     asm volatile("" ::: "memory");
+                    int mx = raw[0];
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) {
-                        yv[e] = lut_s[min(raw[e], LUT_SMEM - 1)];
-                        if (raw[e] >= LUT_SMEM) yv[e] = __ldg(P.lut + raw[e]);  // rare: beyond the table head
+                    for (int e = 1; e < 16; ++e) mx = max(mx, raw[e]);
+                    if (mx < LUT_SMEM) {
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) yv[e] = lut_s[raw[e]];
+                    } else {  // rare: a value beyond the table head
+#pragma unroll
+                        for (int e = 0; e < 16; ++e) yv[e] = raw[e] < LUT_SMEM ? lut_s[raw[e]] : __ldg(P.lut + raw[e]);
                     }
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 16; ++e) yv[e] = __ldg(P.Y + (size_t)min(k0 + e, n - 1) * P.ld + base);
+                    for (int e = 0; e < 16; ++e)
+                        yv[e] = __ldg(P.Y + (size_t)(FULL ? k0 + e : min(k0 + e, n - 1)) * P.ld + base);
                     asm volatile("" ::: "memory");
                 }
                 __half2 h2[8];
+                const double* qk = Qc + (size_t)k0 * QS;
 #pragma unroll
                 for (int e = 0; e < 16; e += 2) {
                     double v2[2];
 #pragma unroll
                     for (int u = 0; u < 2; ++u) {
-                        const int k = k0 + e + u;
                         v2[u] = 0.0;
-                        if (k < n) {
+                        if (FULL || k0 + e + u < n) {
                             const double v = __dsub_rn(yv[e + u], m);
-                            if (c == 0) yy = fma(v, v, yy);
-                            const double* q = Qs_obs + (size_t)k * P.pp + c * PC;
+                            if (FIRST) yy = fma(v, v, yy);
+                            const double* q = qk + (e + u) * QS;
 #pragma unroll
                             for (int j = 0; j < PC; ++j) S[j] = fma(v, q[j], S[j]);
                             v2[u] = v;
                         }
                     }
-                    if (EMIT) h2[e >> 1] = __halves2half2(__double2half(v2[0]), __double2half(v2[1]));
+                    if (EMIT && FIRST) h2[e >> 1] = __halves2half2(__double2half(v2[0]), __double2half(v2[1]));
                 }
-                if (emit) {
+                if (EMIT && FIRST) {
                     arow[k0 >> 3] = reinterpret_cast<const uint4*>(h2)[0];
                     arow[(k0 >> 3) + 1] = reinterpret_cast<const uint4*>(h2)[1];
                 }
+            };
+            int k0 = 0;
+            if (c == 0) {
+                for (; k0 + 16 <= n; k0 += 16) step(k0, std::true_type(), std::true_type());
+                if (k0 < n) step(k0, std::false_type(), std::true_type());
+                if (EMIT)
+                    for (int kz = (n + 15) & ~15; kz < P.a16_ka; kz += 8) arow[kz >> 3] = make_uint4(0u, 0u, 0u, 0u);
+            } else {
+                for (; k0 + 16 <= n; k0 += 16) step(k0, std::true_type(), std::false_type());
+                if (k0 < n) step(k0, std::false_type(), std::false_type());
             }
-            if (emit)
-                for (int k0 = (n + 15) & ~15; k0 < P.a16_ka; k0 += 8) arow[k0 >> 3] = make_uint4(0u, 0u, 0u, 0u);
 #pragma unroll
             for (int j = 0; j < PC; ++j) {
                 if (c * PC + j < P.p0) s0 = fma(S[j], S[j], s0);
@@ -617,7 +637,8 @@ int fstat_observed(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, doubl
         P.xi = cov->xi.p;
         P.lut = ctx->lut_dev;
     }
-    const size_t smem = (((mb.qpad.size() + 1) & ~(size_t)1) + (srci ? (size_t)LUT_SMEM : 0)) * sizeof(double);
+    // shared memory: the basis as [chunks][n][pc rounded up to even] + the head of the log2 table
+    const size_t smem = ((size_t)mb.chunks * mb.n * ((mb.pc + 1) & ~1) + (srci ? (size_t)LUT_SMEM : 0)) * sizeof(double);
     const int grid = grid_for(cov->N, 256, ctx->sm_count, 8);
     auto launch = [&](auto kern) -> int {
         if (smem > 48 * 1024) DFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
