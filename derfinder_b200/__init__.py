@@ -5,6 +5,6 @@ The product is the CUDA shared library `libderfinder_b200.so` (C ABI: include/de
 """
 from .api import (Coverage, Engine, analyzeChr, calcFstatCutoff, calcPval, calculateFWER, calculatePvalues,  # noqa: F401
                   calculateStats, clusterMakerRle, coverageToExon, default_engine, filterData, findRegions, getSegmentsRle,
-                  makeModels, preprocessCoverage, railMatrix, regionMatrix)
+                  makeModels, mergeResults, preprocessCoverage, railMatrix, regionMatrix)
 
 __version__ = "0.1.0"

@@ -638,6 +638,85 @@ def calculatePvalues(coveragePrep, models, fstats, nPermute=1, seeds=None, chr=N
 
 
 # ---------------------------------------------------------------------------------------------
+# mergeResults  (R/mergeResults.R:109-357) -- the genome-wide pass, without the file plumbing
+
+
+def mergeResults(chrs=None, results=None, optionsStats=None, significantCut=(0.05, 0.10), cutoffFstatUsed=None,
+                 fullFstats=None, prefix=None, engine=None, verbose=False, **kwargs):
+    """Genome-wide pooling of per-chromosome results.  `results`: dict chr -> output of calculatePvalues() /
+    analyzeChr()["regions"] (what the reference loads from `<prefix>/<chr>/regions.Rdata`, :170-175).  Returns the
+    objects the reference saves -- `fullRegions` (regions of all chromosomes with `fwer`, `significantFWER`, pooled
+    `pvalues`, `significant`, in decreasing-area order, :199, :266-327), `fullNullSummary` (stat, width, chr,
+    permutation, area = abs(stat) * width in decreasing order, :216-238) and `optionsMerge` -- and, with `prefix`,
+    writes them as .npz next to where the reference writes the .Rdata files.  The ranking (.calcPval) and the
+    per-permutation maxima (.calculateFWER) run on the device; for chromosomes whose device handles are still alive
+    `pool.merge_results` does the same over all GPUs in one library call.  Annotation (`genomicState`), timing and
+    qvalue() stay in R."""
+    if len(significantCut) != 2 or not all(0 <= s <= 1 for s in significantCut):
+        raise ValueError("length(significantCut) == 2 & all(significantCut >= 0 & significantCut <= 1) is not TRUE")
+    if results is None:
+        raise ValueError("'results' (chr -> calculatePvalues() output) is required: the engine has no .Rdata reader")
+    chrs = list(results) if chrs is None else [c for c in chrs]
+    engine = engine or default_engine()
+    have = [c for c in chrs if results[c].get("regions") is not None]
+    regs = [results[c]["regions"] for c in have]
+    full = None
+    if regs:
+        keys = [k for k in regs[0] if all(k in r for r in regs)]
+        full = {k: np.concatenate([np.asarray(r[k]) for r in regs]) for k in keys}
+        full["seqnames"] = np.concatenate([np.repeat(c, len(r["area"])) for c, r in zip(have, regs)])
+
+    def cat(key, dt):
+        parts = [np.asarray(results[c][key], dtype=dt) for c in chrs if results[c].get(key) is not None]
+        return np.concatenate(parts) if parts else np.zeros(0, dtype=dt)
+
+    stat, width, perm = cat("nullStats", np.float64), cat("nullWidths", np.int64), cat("nullPermutation", np.int64)
+    how = [0 if results[c].get("nullStats") is None else len(results[c]["nullStats"]) for c in chrs]
+    null = None
+    if len(stat) > 0:
+        area = np.abs(stat) * width  # :231
+        o = np.argsort(-area, kind="stable")
+        null = dict(stat=stat[o], width=width[o], chr=np.repeat(np.asarray(chrs, dtype=object), how)[o],
+                    permutation=perm[o], area=area[o])
+    if cutoffFstatUsed is None and optionsStats is not None:  # :241-263
+        for k in ("cutoffType", "cutoffFstat", "models"):
+            if k not in optionsStats:
+                raise ValueError('all(c("cutoffType", "cutoffFstat", "models") %in% names(optionsStats)) is not TRUE')
+        fs = None if fullFstats is None else np.concatenate([np.asarray(fullFstats[c], dtype=np.float64) for c in chrs])
+        cutoffFstatUsed = calcFstatCutoff(optionsStats["cutoffType"], optionsStats["cutoffFstat"], fstats=fs,
+                                          models=optionsStats["models"], engine=engine)
+    if cutoffFstatUsed is not None and full is not None:
+        if null is not None:  # :266-283
+            if optionsStats is None or "nPermute" not in optionsStats:
+                raise ValueError('"nPermute" %in% names(optionsStats) is not TRUE')
+            full["fwer"] = calculateFWER(cutoffFstatUsed, null["area"], null["permutation"], optionsStats["nPermute"],
+                                         full["area"], engine=engine)
+            full["significantFWER"] = full["fwer"] < significantCut[0]
+        elif verbose:
+            warnings.warn("No null regions were found, so the FWER calculation step will be skipped.")
+    if full is not None:
+        o = np.argsort(-full["area"], kind="stable")  # :300
+        full = {k: v[o] for k, v in full.items()}
+        if null is not None:  # :302-327
+            full["pvalues"] = calcPval(full["area"], null["area"], engine=engine)
+            full["significant"] = full["pvalues"] < significantCut[0]
+            full["qvalues"] = np.full(len(o), np.nan)  # qvalue::qvalue() stays in R
+            full["significantQval"] = np.full(len(o), np.nan)
+    optionsMerge = dict(chrs=chrs, significantCut=tuple(significantCut), cutoffFstatUsed=cutoffFstatUsed,
+                        optionsStats=optionsStats)
+    out = dict(fullRegions=full, fullNullSummary=null, optionsMerge=optionsMerge)
+    if prefix is not None:
+        import os
+        os.makedirs(prefix, exist_ok=True)
+        if full is not None:
+            np.savez(os.path.join(prefix, "fullRegions.npz"), **{k: np.asarray(v) for k, v in full.items()})
+        if null is not None:
+            np.savez(os.path.join(prefix, "fullNullSummary.npz"), **{k: np.asarray(v).astype(str) if k == "chr" else v
+                                                                      for k, v in null.items()})
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
 # regionMatrix  (R/regionMatrix.R:124-283)
 
 

@@ -113,6 +113,15 @@ struct dfb_ctx {
     int opt_k2_waves = 16;       // fused kernel: CTAs per resident slot (1 = persistent); see launch_fused
     double opt_null_cap_mb = 0;  // 0 = auto
     int opt_perm_batch = 0;      // 0 = auto
+    // Mask rows of the tensor-core null scan, kept between calls and kept ZERO: the scan writes its non-empty
+    // words only, the null-region stage reads them, and a clean-up kernel zeroes exactly the groups that were
+    // flagged -- instead of a memset of rows * W words (3 GB at the chr1 shape) before every scan.
+    uint32_t* k2_mask = nullptr;
+    size_t k2_mask_cap = 0;        // words
+    unsigned char* k2_gflag = nullptr;
+    size_t k2_gflag_cap = 0;       // bytes
+    bool k2_clean = false;         // both buffers are all zero
+    int opt_mask_cache = 1;
     double null_density = 0;     // exceedance values per (base, permutation) seen by the last null scan (0 = unknown)
     double opt_scratch_gb = 24;  // upper bound for per-call scratch (mask + exceedance values)
     // pinned staging ring for pageable <-> device copies, and the host copy pool that drains it

@@ -685,6 +685,8 @@ void dfb_destroy(dfb_ctx* c) {
     }
     for (auto& b : c->pin_blocks) cudaFreeHost(b.p);
     if (c->lut_dev) cudaFree(c->lut_dev);
+    if (c->k2_mask) cudaFree(c->k2_mask);
+    if (c->k2_gflag) cudaFree(c->k2_gflag);
     if (c->mempool) cudaMemPoolDestroy(c->mempool);  // released once the last outstanding block is freed
     delete c->pool;
     if (c->own_stream) cudaStreamDestroy(c->stream);
@@ -763,6 +765,7 @@ int dfb_set_option(dfb_ctx* c, const char* key, double value) {
     else if (!strcmp(key, "a_stages")) c->opt_a_stages = (int)value;
     else if (!strcmp(key, "a16_fused")) c->opt_a16_fused = value != 0;
     else if (!strcmp(key, "lazy_y")) c->opt_lazy_y = value != 0;
+    else if (!strcmp(key, "mask_cache")) c->opt_mask_cache = value != 0;
     else if (!strcmp(key, "dbg")) c->opt_dbg = (int)value;
     else if (!strcmp(key, "tmem_stages")) c->opt_tmem_stages = (int)value;
     else if (!strcmp(key, "k2_waves")) c->opt_k2_waves = (int)value;

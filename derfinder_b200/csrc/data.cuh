@@ -99,6 +99,11 @@ int ensure_y(dfb_ctx* ctx, const dfb_cov* cov);
 int ensure_lut(dfb_ctx* ctx, double scalefac);
 constexpr int LUT_SMEM = 4096;  // table entries the streaming kernels keep in shared memory
 
+// ---- fstat_tc2.cu
+struct PermBatch;
+// zero the flagged groups of a batch that used the context's kept-zero mask (no-op otherwise)
+int null2_release_mask(dfb_ctx* ctx, PermBatch* batch);
+
 // ---- fstat.cu
 struct ModelBasis {
     int n = 0, p = 0, p0 = 0, pc = 0, chunks = 0, pp = 0;  // pp = padded columns = chunks * pc
@@ -121,6 +126,7 @@ struct PermBatch {
     DevBuf<int64_t> off;   // [rows][tiles] offset of the tile's first exceedance value
     DevBuf<double> vals;   // compacted F values
     DevBuf<unsigned char> gflag;  // optional [rows][ceil(W / 32)]: 1 when the 32-word group holds a non-empty word
+    bool mask_cached = false;     // mask / gflag are the context's kept-zero buffers: null2_release_mask() after use
     int64_t nvals = 0;
     // deferred overflow check (fused path): pinned copy of the value cursor, valid after the next
     // stream synchronisation; the batch is good iff *used_host <= capacity

@@ -726,6 +726,54 @@ __global__ void __launch_bounds__(n2_max_threads(PT - J0), 1) fstat_null2_kernel
     if (warp == mma_warp) tmem_dealloc(tmem_base, 512u);
 }
 
+// Restore the all-zero invariant of the context's mask: zero the 32 words of every flagged group and the flag.
+// A warp reads the flags of 128 groups per step.
+__global__ void __launch_bounds__(256) null2_mask_cleanup_kernel(uint32_t* __restrict__ mask, unsigned char* __restrict__ gflag,
+                                                                 int64_t rows, int64_t W, int64_t Gr) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+        for (int64_t k0 = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * 128; k0 < Gr; k0 += (int64_t)gridDim.x * wpb * 128) {
+            unsigned f = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t k = k0 + 4 * lane + j;
+                if (k < Gr && gflag[row * Gr + k]) {
+                    f |= 1u << j;
+                    gflag[row * Gr + k] = 0;
+                }
+            }
+            unsigned any = __ballot_sync(0xffffffffu, f != 0u);
+            while (any) {
+                const int src = __ffs(any) - 1;
+                any &= any - 1;
+                unsigned fs = __shfl_sync(0xffffffffu, f, src);
+                while (fs) {
+                    const int j = __ffs(fs) - 1;
+                    fs &= fs - 1;
+                    const int64_t w = (k0 + 4 * src + j) * 32 + lane;
+                    if (w < W) mask[row * W + w] = 0u;
+                }
+            }
+        }
+    }
+}
+
+int null2_release_mask(dfb_ctx* ctx, PermBatch* b) {
+    if (!b || !b->mask_cached) return DFB_OK;
+    b->mask_cached = false;
+    if (b->mask.p != ctx->k2_mask || b->rows == 0) return DFB_OK;
+    const int64_t Gr = ceil_div(b->W, 32);
+    const dim3 grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(Gr, 8 * 128), ceil_div((int64_t)ctx->sm_count * 8, b->rows))),
+                    (unsigned)std::min<int64_t>(b->rows, 65535));
+    {
+        KTimer t(ctx, DFB_K_REGIONS);
+        null2_mask_cleanup_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->k2_mask, ctx->k2_gflag, b->rows, b->W, Gr);
+    }
+    DFB_CUDA(cudaGetLastError());
+    ctx->k2_clean = true;
+    return DFB_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 
@@ -974,10 +1022,39 @@ int fstat_perm_batch_null2(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& m
     out->W = ceil_div(cov->N, 32);
     out->tile_bases = 32;
     out->tiles = out->W;
-    DFB_TRY(out->mask.alloc(ctx, (size_t)out->rows * out->W));
-    DFB_TRY(out->off.alloc(ctx, (size_t)out->rows * out->tiles));
     F.Gr = ceil_div(out->W, 32);
-    DFB_TRY(out->gflag.alloc(ctx, (size_t)out->rows * (size_t)F.Gr));
+    const size_t need_w = (size_t)out->rows * out->W, need_g = (size_t)out->rows * (size_t)F.Gr;
+    const bool cached = ctx->opt_mask_cache != 0;
+    if (cached) {
+        // the context's kept-zero buffers (grown when a larger batch comes along)
+        if (ctx->k2_mask_cap < need_w || ctx->k2_gflag_cap < need_g) {
+            DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+            if (ctx->k2_mask) cudaFree(ctx->k2_mask);
+            if (ctx->k2_gflag) cudaFree(ctx->k2_gflag);
+            ctx->k2_mask = nullptr;
+            ctx->k2_gflag = nullptr;
+            ctx->k2_mask_cap = ctx->k2_gflag_cap = 0;
+            ctx->k2_clean = false;
+            if (cudaMalloc((void**)&ctx->k2_mask, need_w * sizeof(uint32_t)) != cudaSuccess ||
+                cudaMalloc((void**)&ctx->k2_gflag, need_g) != cudaSuccess) {
+                cudaGetLastError();
+                if (ctx->k2_mask) cudaFree(ctx->k2_mask);
+                ctx->k2_mask = nullptr;
+                ctx->k2_gflag = nullptr;
+                set_error("device allocation of the null-scan mask (%zu bytes) failed", need_w * sizeof(uint32_t));
+                return DFB_ENOMEM;
+            }
+            ctx->k2_mask_cap = need_w;
+            ctx->k2_gflag_cap = need_g;
+        }
+        out->mask.borrow(ctx->stream, ctx->k2_mask, need_w);
+        out->gflag.borrow(ctx->stream, ctx->k2_gflag, need_g);
+        out->mask_cached = true;
+    } else {
+        DFB_TRY(out->mask.alloc(ctx, need_w));
+        DFB_TRY(out->gflag.alloc(ctx, need_g));
+    }
+    DFB_TRY(out->off.alloc(ctx, (size_t)out->rows * out->tiles));
     F.gflag = out->gflag.p;
     DevBuf<unsigned long long> cursor;
     DFB_TRY(cursor.alloc(ctx, 1));
@@ -1001,8 +1078,16 @@ int fstat_perm_batch_null2(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& m
         DFB_TRY(cursor.zero());
         // the kernel writes the non-empty mask words only (at stringent cutoffs nearly all are empty, and 16
         // warps storing 4-byte zeros to 32 different rows per chunk cost more than the scan itself)
-        DFB_TRY(out->mask.zero());
-        DFB_TRY(out->gflag.zero());
+        if (!cached) {
+            DFB_TRY(out->mask.zero());
+            DFB_TRY(out->gflag.zero());
+        } else {
+            if (!ctx->k2_clean) {  // first use, or a previous user did not hand the buffers back clean
+                DFB_CUDA(cudaMemsetAsync(ctx->k2_mask, 0, ctx->k2_mask_cap * sizeof(uint32_t), ctx->stream));
+                DFB_CUDA(cudaMemsetAsync(ctx->k2_gflag, 0, ctx->k2_gflag_cap, ctx->stream));
+            }
+            ctx->k2_clean = false;  // about to be written; null2_release_mask() restores the invariant
+        }
         F.vals = out->vals.p;
         F.capacity = cap;
         switch (mb.p) {

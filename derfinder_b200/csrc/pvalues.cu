@@ -145,6 +145,7 @@ static int perm_nulls_impl(dfb_ctx* ctx, dfb_cov* cov, const double* mod, int p,
             DFB_TRY(find_regions_rows(ctx, N, pbatch.rows, sides, pbatch.mask.p, seg.p, nullptr, 0, &pbatch, false,
                                       true, &rs));
         }
+        DFB_TRY(null2_release_mask(ctx, &pbatch));  // the mask rows have been consumed: hand the kept-zero buffer back clean
         if (pbatch.used_host) pbatch.nvals = (int64_t)*pbatch.used_host;
         if (density >= 0 && dense > 0) {
             density = std::min(1.0, std::max(1e-4, 1.3 * (double)pbatch.nvals / dense));

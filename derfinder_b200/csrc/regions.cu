@@ -280,6 +280,105 @@ __global__ void __launch_bounds__(256) fill_starts_group_kernel(const uint32_t* 
     }
 }
 
+// Flag-driven variants for the tensor-core null scan, which leaves a byte per group (1 = some word of the group
+// is non-empty).  At stringent cutoffs nearly every group is empty: a warp reads the flags of 128 consecutive
+// groups per step (four per lane), zeroes the counts of the empty ones and visits the live ones one by one --
+// the word-parallel kernels above spent one warp per eight groups just to find out that there was nothing to do.
+constexpr int FLAG_GROUPS_PER_WARP = 128;
+
+__global__ void __launch_bounds__(256) count_starts_flagged_kernel(const uint32_t* __restrict__ mask,
+                                                                   const uint32_t* __restrict__ seg, int64_t rows,
+                                                                   int64_t W, int64_t Gr, uint32_t* __restrict__ counts,
+                                                                   const unsigned char* __restrict__ gflag) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+        for (int64_t k0 = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * FLAG_GROUPS_PER_WARP; k0 < Gr;
+             k0 += (int64_t)gridDim.x * wpb * FLAG_GROUPS_PER_WARP) {
+            unsigned f = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t k = k0 + 4 * lane + j;
+                if (k < Gr) {
+                    if (gflag[row * Gr + k]) f |= 1u << j;
+                    else counts[row * Gr + k] = 0u;
+                }
+            }
+            unsigned any = __ballot_sync(0xffffffffu, f != 0u);
+            while (any) {
+                const int src = __ffs(any) - 1;
+                any &= any - 1;
+                unsigned fs = __shfl_sync(0xffffffffu, f, src);
+                while (fs) {
+                    const int j = __ffs(fs) - 1;
+                    fs &= fs - 1;
+                    const int64_t k = k0 + 4 * src + j;
+                    const int64_t w = k * 32 + lane;
+                    const bool valid = w < W;
+                    const int64_t g = row * W + w;
+                    const uint32_t m = valid ? mask[g] : 0u;
+                    const uint32_t pv = (valid && w > 0) ? mask[g - 1] : 0u;
+                    const uint32_t sg = valid ? seg[w] : 0u;
+                    uint32_t c = __popc(region_starts(m, pv >> 31, sg));
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                    if (lane == 0) counts[row * Gr + k] = c;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) fill_starts_flagged_kernel(const uint32_t* __restrict__ mask,
+                                                                  const uint32_t* __restrict__ seg,
+                                                                  const int64_t* __restrict__ goffsets, int64_t rows,
+                                                                  int64_t W, int64_t Gr, int64_t* __restrict__ start_pos,
+                                                                  const unsigned char* __restrict__ gflag) {
+    const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
+    for (int64_t row = blockIdx.y; row < rows; row += gridDim.y) {
+        for (int64_t k0 = ((int64_t)blockIdx.x * wpb + (threadIdx.x >> 5)) * FLAG_GROUPS_PER_WARP; k0 < Gr;
+             k0 += (int64_t)gridDim.x * wpb * FLAG_GROUPS_PER_WARP) {
+            unsigned f = 0u;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int64_t k = k0 + 4 * lane + j;
+                if (k < Gr && gflag[row * Gr + k]) f |= 1u << j;
+            }
+            unsigned any = __ballot_sync(0xffffffffu, f != 0u);
+            while (any) {
+                const int src = __ffs(any) - 1;
+                any &= any - 1;
+                unsigned fs = __shfl_sync(0xffffffffu, f, src);
+                while (fs) {
+                    const int j = __ffs(fs) - 1;
+                    fs &= fs - 1;
+                    const int64_t k = k0 + 4 * src + j;
+                    const int64_t w = k * 32 + lane;
+                    const bool valid = w < W;
+                    const int64_t g = row * W + w;
+                    const uint32_t m = valid ? mask[g] : 0u;
+                    const uint32_t pv = (valid && w > 0) ? mask[g - 1] : 0u;
+                    const uint32_t sg = valid ? seg[w] : 0u;
+                    uint32_t starts = region_starts(m, pv >> 31, sg);
+                    if (!__any_sync(0xffffffffu, starts != 0u)) continue;
+                    const int c = __popc(starts);
+                    int inc = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                        if (lane >= o) inc += t;
+                    }
+                    int64_t out = goffsets[row * Gr + k] + (int64_t)(inc - c);
+                    while (starts) {
+                        const int b = __ffs(starts) - 1;
+                        starts &= starts - 1;
+                        start_pos[out++] = (g << 5) | (int64_t)b;
+                    }
+                }
+            }
+        }
+    }
+}
+
 // One thread per region: all lanes of a warp walk regions of similar length that are adjacent in
 // memory (the word-parallel predecessor left most lanes idle while one walked).
 // A region that runs past LONG_WORDS mask words is handed to walk_long_regions_kernel (one WARP per
@@ -474,6 +573,10 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
     const int64_t Gr = ceil_div(W, 32), groups = rows * Gr;  // groups of 32 words, row-local
     const unsigned char* gflag = (compact && compact->gflag.p) ? compact->gflag.p : nullptr;
     const dim3 group_grid((unsigned)ceil_div(Gr, 8 * GROUPS_PER_WARP), (unsigned)std::min<int64_t>(rows, 65535));
+    // flag-driven kernels: a block covers 8 * 128 groups of a row per step; enough blocks per row to fill the device
+    const dim3 flag_grid((unsigned)std::max<int64_t>(1, std::min<int64_t>(ceil_div(Gr, 8 * FLAG_GROUPS_PER_WARP),
+                                                                         ceil_div((int64_t)ctx->sm_count * 8, rows))),
+                         (unsigned)std::min<int64_t>(rows, 65535));
     DevBuf<uint32_t> counts;
     DevBuf<int64_t> offsets, total_dev;
     DFB_TRY(counts.alloc(ctx, (size_t)groups));
@@ -481,7 +584,10 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
     DFB_TRY(total_dev.alloc(ctx, 1));
     {
         KTimer t(ctx, DFB_K_REGIONS);
-        count_starts_group_kernel<<<group_grid, 256, 0, ctx->stream>>>(mask, seg, rows, W, Gr, counts.p, gflag);
+        if (gflag)
+            count_starts_flagged_kernel<<<flag_grid, 256, 0, ctx->stream>>>(mask, seg, rows, W, Gr, counts.p, gflag);
+        else
+            count_starts_group_kernel<<<group_grid, 256, 0, ctx->stream>>>(mask, seg, rows, W, Gr, counts.p, gflag);
     }
     DFB_TRY(exclusive_scan_u32(ctx, counts.p, offsets.p, groups, total_dev.p, DFB_K_REGIONS));
     // per-row counts: offsets at the row starts (strided gather) + total, read back through pinned
@@ -539,8 +645,12 @@ int find_regions_rows(dfb_ctx* ctx, int64_t N, int64_t rows, int sides, const ui
     DFB_TRY(long_count.zero());
     {
         KTimer t(ctx, DFB_K_REGIONS);
-        fill_starts_group_kernel<<<group_grid, 256, 0, ctx->stream>>>(mask, seg, offsets.p, rows, W, Gr, start_pos.p,
-                                                                      gflag);
+        if (gflag)
+            fill_starts_flagged_kernel<<<flag_grid, 256, 0, ctx->stream>>>(mask, seg, offsets.p, rows, W, Gr, start_pos.p,
+                                                                           gflag);
+        else
+            fill_starts_group_kernel<<<group_grid, 256, 0, ctx->stream>>>(mask, seg, offsets.p, rows, W, Gr, start_pos.p,
+                                                                          gflag);
     }
     {
         KTimer t(ctx, DFB_K_REGIONS);

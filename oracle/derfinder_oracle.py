@@ -547,6 +547,46 @@ def calculate_pvalues(prep, mod, mod0, fstats, perm_idx, cutoff, maxRegionGap=0,
 
 
 # ---------------------------------------------------------------------------------------------
+# mergeResults: the genome-wide pass over the per-chromosome results  (R/mergeResults.R:199-328)
+
+
+def merge_results(results, nPermute, cutoffFstatUsed=None, significantCut=(0.05, 0.10)):
+    """`results`: ordered dict chr -> output of calculate_pvalues (the per-chromosome regions.Rdata).
+    Returns dict(fullRegions, fullNullSummary) shaped like the objects mergeResults() saves; annotation, timing
+    and q-values (qvalue package) are not restated."""
+    chrs = [c for c in results if results[c]["regions"] is not None]
+    regs = [results[c]["regions"] for c in chrs]
+    keys = [k for k in regs[0] if all(k in r for r in regs)] if regs else []
+    full = {k: np.concatenate([np.asarray(r[k]) for r in regs]) for k in keys}  # unlist(GRangesList(fullRegs)) :199
+    full["seqnames"] = np.concatenate([np.repeat(c, len(r["area"])) for c, r in zip(chrs, regs)]) if regs else np.zeros(0, str)
+    allc = list(results)
+    stat = np.concatenate([np.asarray(results[c]["nullStats"], dtype=np.float64) if results[c]["nullStats"] is not None
+                           else np.zeros(0) for c in allc]) if allc else np.zeros(0)
+    width = np.concatenate([np.asarray(results[c]["nullWidths"], dtype=np.int64) if results[c]["nullWidths"] is not None
+                            else np.zeros(0, np.int64) for c in allc]) if allc else np.zeros(0, np.int64)
+    perm = np.concatenate([np.asarray(results[c]["nullPermutation"], dtype=np.int64)
+                           if results[c]["nullPermutation"] is not None else np.zeros(0, np.int64) for c in allc]) \
+        if allc else np.zeros(0, np.int64)
+    how = [0 if results[c]["nullStats"] is None else len(results[c]["nullStats"]) for c in allc]
+    if len(stat) > 0:  # :224-238
+        area = np.abs(stat) * width  # :231 -- NOT the summed area of calculatePvalues
+        o = np.argsort(-area, kind="stable")  # order(area, decreasing = TRUE)
+        null = dict(stat=stat[o], width=width[o], chr=np.repeat(allc, how)[o], permutation=perm[o], area=area[o])
+    else:
+        null = None
+    if cutoffFstatUsed is not None and null is not None and len(full.get("area", ())) > 0:  # :266-289
+        full["fwer"] = calculate_fwer(cutoffFstatUsed, null["area"], null["permutation"], nPermute, full["area"])
+        full["significantFWER"] = full["fwer"] < significantCut[0]
+    if regs:
+        o = np.argsort(-full["area"], kind="stable")  # :300
+        full = {k: v[o] for k, v in full.items()}
+        if null is not None:  # :302-327
+            full["pvalues"] = calc_pval(full["area"], null["area"])
+            full["significant"] = full["pvalues"] < significantCut[0]
+    return dict(fullRegions=full if regs else None, fullNullSummary=null)
+
+
+# ---------------------------------------------------------------------------------------------
 # regionMatrix  (R/regionMatrix.R:170-283, R/getRegionCoverage.R:132-160)
 
 

@@ -380,3 +380,99 @@ analyzeChr <- function(chr, coverageInfo, models, cutoffPre = 5, cutoffFstat = 1
     if (returnOutput) list(timeinfo = timeinfo, optionsStats = if (writeOutput) optionsStats else NULL,
         coveragePrep = prep, fstats = fstats, regions = regions, annotation = annotation) else invisible(NULL)
 }
+
+## ---- mergeResults (R/mergeResults.R:109-357): the genome-wide pass.  Same signature, same files
+## (fullRegions.Rdata, fullNullSummary.Rdata, fullFstats.Rdata, fullTime.Rdata, optionsMerge.Rdata, fullAnnotatedRegions.Rdata,
+## fullCoveragePrep.Rdata with mergePrep).  The per-chromosome .Rdata files are read as the reference reads them; the
+## two rankings -- .calculateFWER (:380-386) and .calcPval on the pooled nulls (:302-307) -- run in the library.  When the
+## chromosomes were analysed in THIS R session their device handles are still attached to the results
+## (attr "dfb_regions"/"dfb_nulls") and `chrResults` can be passed instead of reading files: the pooling is then ONE
+## library call over every GPU of the communicator (.mergeResultsGPU), the null lists never leave their GPU.
+mergeResults <- function(chrs = c(seq_len(22), "X", "Y"), prefix = ".", significantCut = c(0.05, 0.10), genomicState,
+    minoverlap = 20, mergePrep = FALSE, ...) {
+    stopifnot(length(significantCut) == 2 & all(significantCut >= 0 & significantCut <= 1))              # :112-114
+    verbose <- derfinder:::.advanced_argument("verbose", TRUE, ...)
+    optionsStats <- derfinder:::.advanced_argument("optionsStats", NULL, ...)
+    cutoffFstatUsed <- derfinder:::.advanced_argument("cutoffFstatUsed", optionsStats$cutoffFstatUsed, ...)
+    chrResults <- derfinder:::.advanced_argument("chrResults", NULL, ...)
+    optionsMerge <- list(chrs = chrs, significantCut = significantCut, minoverlap = minoverlap, mergeCall = match.call(),
+        cutoffFstatUsed = cutoffFstatUsed, optionsStats = optionsStats)                                  # :139-147
+    save(optionsMerge, file = file.path(prefix, "optionsMerge.Rdata"))
+    fullCoveragePrep <- fullTime <- fullNullPermutation <- fullNullWidths <- fullNullStats <- fullFstats <- fullAnno <-
+        fullRegs <- structure(vector("list", length(chrs)), names = chrs)
+    for (chr in chrs) {                                                                                  # :161-191
+        e <- new.env()
+        load(file.path(prefix, chr, "fstats.Rdata"), envir = e); fullFstats[[chr]] <- e$fstats
+        if (is.null(chrResults)) load(file.path(prefix, chr, "regions.Rdata"), envir = e) else e$regions <- chrResults[[chr]]
+        fullRegs[[chr]] <- e$regions$regions; fullNullStats[[chr]] <- e$regions$nullStats
+        fullNullWidths[[chr]] <- e$regions$nullWidths; fullNullPermutation[[chr]] <- e$regions$nullPermutation
+        load(file.path(prefix, chr, "annotation.Rdata"), envir = e); fullAnno[[chr]] <- e$annotation
+        load(file.path(prefix, chr, "timeinfo.Rdata"), envir = e); fullTime[[chr]] <- e$timeinfo
+        if (mergePrep) { load(file.path(prefix, chr, "coveragePrep.Rdata"), envir = e); fullCoveragePrep[[chr]] <- e$prep }
+    }
+    fullRegions <- unlist(GenomicRanges::GRangesList(fullRegs[!vapply(fullRegs, is.null, logical(1))]), use.names = FALSE)
+    fullAnnotation <- do.call(rbind, fullAnno)                                                           # :202-214
+    if (!is.null(fullAnnotation)) {
+        colnames(fullAnnotation)[which(colnames(fullAnnotation) == "strand")] <- "annoStrand"
+        rownames(fullAnnotation) <- NULL
+        fullAnnotation$name <- as.character(fullAnnotation$name)
+        fullAnnotation$annotation <- as.character(fullAnnotation$annotation)
+        S4Vectors::values(fullRegions) <- cbind(S4Vectors::values(fullRegions), S4Vectors::DataFrame(fullAnnotation, check.names = FALSE))
+    }
+    nulls <- unlist(IRanges::RleList(fullNullStats), use.names = FALSE)                                  # :218-238
+    widths <- unlist(IRanges::RleList(fullNullWidths), use.names = FALSE)
+    permutations <- unlist(IRanges::RleList(fullNullPermutation), use.names = FALSE)
+    howMany <- unlist(lapply(fullNullStats, length))
+    if (length(nulls) > 0) {
+        fullNullSummary <- S4Vectors::DataFrame(stat = nulls, width = widths, chr = S4Vectors::Rle(names(fullNullStats), howMany),
+            permutation = permutations, check.names = FALSE)
+        fullNullSummary$area <- abs(fullNullSummary$stat) * fullNullSummary$width
+        fullNullSummary <- fullNullSummary[order(fullNullSummary$area, decreasing = TRUE), ]
+    } else fullNullSummary <- S4Vectors::DataFrame(NULL)
+    if (is.null(cutoffFstatUsed) && !is.null(optionsStats)) {                                            # :241-263
+        stopifnot(all(c("cutoffType", "cutoffFstat", "models") %in% names(optionsStats)))
+        cutoffFstatUsed <- switch(optionsStats$cutoffType,
+            empirical = .Call(dfbR_quantile, .engine(), as.numeric(unlist(fullFstats)), as.numeric(optionsStats$cutoffFstat)),
+            theoretical = { m <- optionsStats$models; qf(optionsStats$cutoffFstat, ncol(m$mod) - ncol(m$mod0),
+                                                         nrow(m$mod) - ncol(m$mod), lower.tail = FALSE) },
+            manual = optionsStats$cutoffFstat)
+    }
+    pooled <- NULL
+    if (!is.null(chrResults) && !is.null(cutoffFstatUsed) && nrow(fullNullSummary) > 0) {
+        ## handles alive: one collective library call, p-values and FWER per chromosome in calculatePvalues() order
+        stopifnot("nPermute" %in% names(optionsStats))
+        pooled <- .mergeResultsGPU(chrResults[chrs], optionsStats$nPermute, cutoffFstatUsed, mergeArea = TRUE)
+    }
+    if (!is.null(cutoffFstatUsed)) {                                                                     # :266-289
+        if (nrow(fullNullSummary) > 0) {
+            stopifnot(!is.null(optionsStats)); stopifnot("nPermute" %in% names(optionsStats))
+            fullRegions$fwer <- if (!is.null(pooled)) unlist(pooled$fwer, use.names = FALSE) else
+                .Call(dfbR_calc_fwer, .engine(), as.numeric(cutoffFstatUsed), as.numeric(fullNullSummary$area),
+                      as.integer(fullNullSummary$permutation), as.integer(optionsStats$nPermute), as.numeric(fullRegions$area))
+            fullRegions$significantFWER <- factor(fullRegions$fwer < significantCut[1], levels = c(TRUE, FALSE))
+        } else if (verbose) warning("No null regions were found, so the FWER calculation step will be skipped.")
+    }
+    save(fullNullSummary, file = file.path(prefix, "fullNullSummary.Rdata"))
+    if (!is.null(pooled)) fullRegions$pvalues <- unlist(pooled$pvalues, use.names = FALSE)
+    fullRegions <- fullRegions[order(fullRegions$area, decreasing = TRUE)]                               # :300
+    if (nrow(fullNullSummary) > 0) {                                                                     # :302-327
+        if (is.null(pooled))
+            fullRegions$pvalues <- .Call(dfbR_calc_pval, .engine(), as.numeric(fullRegions$area), as.numeric(fullNullSummary$area))
+        fullRegions$significant <- factor(fullRegions$pvalues < significantCut[1], levels = c(TRUE, FALSE))
+        qvalues <- tryCatch(qvalue::qvalue(fullRegions$pvalues), error = function(e) NULL)
+        if (!is.null(qvalues)) {
+            qvalues <- qvalues$qvalues; sigQval <- factor(qvalues < significantCut[2], levels = c(TRUE, FALSE))
+        } else {
+            qvalues <- rep(NA, length(fullRegions$pvalues)); sigQval <- rep(NA, length(fullRegions$pvalues))
+        }
+        fullRegions$qvalues <- qvalues; fullRegions$significantQval <- sigQval
+    }
+    save(fullRegions, file = file.path(prefix, "fullRegions.Rdata"))
+    fullAnnotatedRegions <- derfinder::annotateRegions(regions = fullRegions, genomicState = genomicState,
+        minoverlap = minoverlap, annotate = TRUE, ...)                                                   # :337-343
+    save(fullAnnotatedRegions, file = file.path(prefix, "fullAnnotatedRegions.Rdata"))
+    save(fullFstats, file = file.path(prefix, "fullFstats.Rdata"))
+    save(fullTime, file = file.path(prefix, "fullTime.Rdata"))
+    if (mergePrep) save(fullCoveragePrep, file = file.path(prefix, "fullCoveragePrep.Rdata"))
+    invisible(prefix)
+}

@@ -496,3 +496,50 @@ def test_lazy_log2_matrix_out_of_table(dfb, eng):
     Fo = O.fstats_projector(O.log2_libm(cov.astype(np.float64) + 32.0), models["mod"], models["mod0"])
     ok = np.isfinite(Fo) & (np.abs(Fo) > 1e-8)
     assert np.allclose(F[ok], Fo[ok], rtol=F_RTOL)
+
+
+# ---------------------------------------------------------------------------------------------
+# mergeResults(): fullRegions / fullNullSummary shaped like the reference's .Rdata objects (R/mergeResults.R:199-328)
+
+
+def test_merge_results_objects(dfb, eng, tmp_path):
+    rng = np.random.default_rng(4711)
+    n, B = 12, 30
+    _, _, _, models = synth(rng, 2000, n)
+    perm = random_perms(rng, B, n)
+    cut = dfb.calcFstatCutoff("theoretical", 0.05, models=models)
+    results, fstats = {}, {}
+    for c, N in (("chr1", 9000), ("chr2", 3000), ("chrX", 5000), ("chrY", 1500)):
+        cov, position, group, _ = synth(rng, N, n)
+        prep = dfb.preprocessCoverage(dict(coverage=cov, position=position), groupInfo=group, engine=eng)
+        F = dfb.calculateStats(prep, models, engine=eng)
+        fstats[c] = np.asarray(F)
+        results[c] = dfb.calculatePvalues(prep, models, F, permIndex=perm, cutoff=1e12 if c == "chr2" else cut, engine=eng)
+    assert results["chr2"]["regions"] is None
+    opts = dict(cutoffType="theoretical", cutoffFstat=0.05, models=models, nPermute=B)
+    got = dfb.mergeResults(results=results, optionsStats=opts, fullFstats=fstats, prefix=str(tmp_path), engine=eng)
+    want = O.merge_results(results, B, cutoffFstatUsed=cut)
+    assert got["optionsMerge"]["cutoffFstatUsed"] == cut and got["optionsMerge"]["chrs"] == list(results)
+    fn, wn = got["fullNullSummary"], want["fullNullSummary"]
+    for k in ("stat", "width", "permutation", "area"):
+        assert np.array_equal(fn[k], wn[k]), k
+    assert list(fn["chr"]) == list(wn["chr"])
+    assert np.all(np.diff(fn["area"]) <= 0)
+    fr, wr = got["fullRegions"], want["fullRegions"]
+    for k in ("start", "end", "area", "value", "indexStart", "indexEnd", "cluster", "fwer", "pvalues"):
+        assert np.array_equal(fr[k], wr[k]), k
+    assert list(fr["seqnames"]) == list(wr["seqnames"])
+    assert np.array_equal(fr["significant"], wr["significant"]) and np.array_equal(fr["significantFWER"], wr["significantFWER"])
+    assert np.all(np.diff(fr["area"]) <= 0) and np.all(np.isnan(fr["qvalues"]))
+    # the pooled p-values differ from the per-chromosome ones (more nulls), the saved objects round-trip
+    saved = np.load(tmp_path / "fullRegions.npz")
+    assert np.array_equal(saved["pvalues"], fr["pvalues"]) and np.array_equal(saved["fwer"], fr["fwer"])
+    assert np.array_equal(np.load(tmp_path / "fullNullSummary.npz")["area"], fn["area"])
+    # empirical cutoff from the concatenated F-statistics (:241-263)
+    got2 = dfb.mergeResults(results=results, optionsStats=dict(opts, cutoffType="empirical", cutoffFstat=0.99),
+                            fullFstats=fstats, engine=eng)
+    q = O.quantile_type7(np.concatenate([fstats[c] for c in results]), 0.99)
+    assert got2["optionsMerge"]["cutoffFstatUsed"] == q
+    # no chromosome has regions
+    none = dfb.mergeResults(results={"chr2": results["chr2"]}, optionsStats=opts, cutoffFstatUsed=cut, engine=eng)
+    assert none["fullRegions"] is None and none["fullNullSummary"] is None
