@@ -416,6 +416,79 @@ __global__ void __launch_bounds__(K1_THREADS) expand_rle_kernel(RleDev R, int64_
     }
 }
 
+// Expansion by scatter + scan: the runs that overlap a (2048-position tile, sample) -- found through the
+// tile_runs_kernel table, so no thread searches -- drop their local index at their first position of the tile in
+// shared memory, an inclusive max-scan over the positions spreads it, and every thread writes its 8 positions
+// as 16-byte stores.  The per-thread binary search of expand_rle_kernel (2 x 19 dependent loads per 8 positions
+// at the chr1 shape) made that kernel latency-bound at 1.3 TB/s.
+template <typename V>
+__global__ void __launch_bounds__(K1_THREADS) expand_rle_tiles_kernel(RleDev R, int64_t tiles, const int64_t* __restrict__ tab,
+                                                                      int64_t ld, V* __restrict__ out) {
+    __shared__ int head_s[K1_TILE];
+    __shared__ V val_s[K1_TILE];
+    __shared__ int wmax_s[K1_THREADS / 32];
+    const int s = blockIdx.y, n = R.n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const V* __restrict__ values = reinterpret_cast<const V*>(R.values);
+    const int64_t* __restrict__ cum = R.cum;
+    const int64_t lo = R.run_off[s], hi = R.run_off[s + 1] - 1, cb = cum[lo];
+    (void)lo;
+    for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const int64_t t0 = tile * K1_TILE, t1 = min(t0 + (int64_t)K1_TILE, R.len);
+        const int64_t ra = tab[tile * n + s];
+        int64_t rb = hi;
+        if (tile + 1 < tiles) {
+            rb = tab[(tile + 1) * n + s];
+            if (cum[rb] - cb >= t1) --rb;  // the run holding t1 starts there: t1 - 1 is in the run before
+        }
+        const int nr = (int)(rb - ra + 1);  // <= 2048: every run holds at least one position of the tile
+        __syncthreads();                    // previous tile consumed
+#pragma unroll
+        for (int q = 0; q < K1_PER; ++q) head_s[q * K1_THREADS + tid] = 0;
+        __syncthreads();
+        for (int j = tid; j < nr; j += K1_THREADS) {
+            const int64_t r = ra + j;
+            const int st = (int)(max(cum[r] - cb, t0) - t0);
+            head_s[st] = j;
+            val_s[j] = values[r];
+        }
+        __syncthreads();
+        // inclusive max-scan of the heads: thread-local over 8 consecutive positions, then across the block
+        int h[K1_PER];
+        int run = 0;
+#pragma unroll
+        for (int q = 0; q < K1_PER; ++q) {
+            run = max(run, head_s[tid * K1_PER + q]);
+            h[q] = run;
+        }
+        int inc = run;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc = max(inc, t);
+        }
+        if (lane == 31) wmax_s[warp] = inc;
+        __syncthreads();
+        int before = __shfl_up_sync(0xffffffffu, inc, 1);
+        if (lane == 0) before = 0;
+        for (int w = 0; w < warp; ++w) before = max(before, wmax_s[w]);
+        const int64_t p0 = t0 + (int64_t)tid * K1_PER;
+        if (p0 < t1) {
+            V vals[K1_PER];
+#pragma unroll
+            for (int q = 0; q < K1_PER; ++q) vals[q] = val_s[max(h[q], before)];
+            V* dst = out + (size_t)s * ld + p0;
+            if (p0 + K1_PER <= t1) {
+                constexpr int NV = (int)(sizeof(V) * K1_PER / 16);
+#pragma unroll
+                for (int q = 0; q < NV; ++q) reinterpret_cast<uint4*>(dst)[q] = reinterpret_cast<const uint4*>(vals)[q];
+            } else {
+                for (int e = 0; p0 + e < t1; ++e) dst[e] = vals[e];
+            }
+        }
+    }
+}
+
 struct RleUpload {
     DevBuf<unsigned char> values;
     DevBuf<uint32_t> lengths;
@@ -1063,9 +1136,18 @@ int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, 
         R.len = N;
         const int64_t tiles = ceil_div(N, K1_TILE);
         const dim3 grid((unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 8), (unsigned)n);
-        KTimer t(ctx, DFB_K_PREP);
-        if (dtype == DFB_I32) expand_rle_kernel<int32_t><<<grid, K1_THREADS, 0, ctx->stream>>>(R, c->ld, c->xi.p);
-        else expand_rle_kernel<double><<<grid, K1_THREADS, 0, ctx->stream>>>(R, c->ld, c->xd.p);
+        DevBuf<int64_t> tab;  // run holding the first position of every (tile, sample)
+        rc = tab.alloc(ctx, (size_t)tiles * n);
+        if (rc < 0) {
+            delete c;
+            return rc;
+        }
+        KTimer t(ctx, DFB_K_PREP, 2);
+        tile_runs_kernel<<<grid_for(tiles * n, 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(R, tiles, tab.p);
+        if (dtype == DFB_I32)
+            expand_rle_tiles_kernel<int32_t><<<grid, K1_THREADS, 0, ctx->stream>>>(R, tiles, tab.p, c->ld, c->xi.p);
+        else
+            expand_rle_tiles_kernel<double><<<grid, K1_THREADS, 0, ctx->stream>>>(R, tiles, tab.p, c->ld, c->xd.p);
     }
     cudaError_t e = cudaGetLastError();
     // the position index is built while the expansion runs (host run loops + two small uploads)
