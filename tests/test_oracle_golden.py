@@ -206,3 +206,36 @@ def test_rle_window_host_marshalling():
     assert np.array_equal(np.repeat(v, l), want)
     v, l = api._rle_window(vals, lens, np.array([1]), np.array([len(dense)]))
     assert np.array_equal(np.repeat(v, l), dense)
+
+
+def test_merge_results_brute_force():
+    """oracle.merge_results (R/mergeResults.R:199-328) against a direct restatement: p = (#{pooled null area >
+    region area} + 1) / (#nulls + 1) with area = abs(stat) * width (:231), FWER from the per-permutation maxima over
+    the whole genome (:380-386, an empty permutation counts as cutoffFstatUsed), both tables in decreasing-area
+    order with stable ties (:236, :300)."""
+    from oracle import derfinder_oracle as O
+    rng = np.random.default_rng(17)
+    B, cut = 6, 1.5
+
+    def fake(R, M):
+        if R == 0:
+            return dict(regions=None, nullStats=None, nullWidths=None, nullPermutation=None)
+        area = np.round(rng.random(R) * 12, 1)  # ties on purpose
+        return dict(regions=dict(area=area, start=np.arange(R) * 10 + 1, value=area / 3.0),
+                    nullStats=np.round(rng.normal(size=M) * 3, 1), nullWidths=rng.integers(1, 4, M),
+                    nullPermutation=rng.integers(1, B, M))  # permutation B never occurs: the empty case
+    res = {"chr1": fake(9, 14), "chr2": fake(0, 0), "chr3": fake(5, 8)}
+    out = O.merge_results(res, B, cutoffFstatUsed=cut)
+    fr, fn = out["fullRegions"], out["fullNullSummary"]
+    z = np.concatenate([np.abs(res[c]["nullStats"]) * res[c]["nullWidths"] for c in ("chr1", "chr3")])
+    zp = np.concatenate([res[c]["nullPermutation"] for c in ("chr1", "chr3")])
+    a_all = np.concatenate([res[c]["regions"]["area"] for c in ("chr1", "chr3")])
+    chr_all = np.array(["chr1"] * 9 + ["chr3"] * 5)
+    o = sorted(range(len(a_all)), key=lambda i: (-a_all[i], i))
+    assert np.array_equal(fr["area"], a_all[o]) and list(fr["seqnames"]) == list(chr_all[o])
+    assert np.array_equal(fr["pvalues"], np.array([((z > a).sum() + 1) / (len(z) + 1) for a in a_all[o]]))
+    mx = np.array([z[zp == b].max() if (zp == b).any() else cut for b in range(1, B + 1)])
+    assert np.array_equal(fr["fwer"], np.array([((mx > a).sum() + 1) / (B + 1) for a in a_all[o]]))
+    oz = sorted(range(len(z)), key=lambda i: (-z[i], i))
+    assert np.array_equal(fn["area"], z[oz]) and np.array_equal(fn["permutation"], zp[oz])
+    assert list(fn["chr"]) == list(np.array(["chr1"] * 14 + ["chr3"] * 8)[oz])
