@@ -109,7 +109,7 @@ struct dfb_ctx {
     int opt_a_stages = 0;        // null2 kernel: A tile ring depth (0 = auto)
     int opt_mma_warps = 0;       // null2 kernel: MMA-issuing warps (0 = auto)
     int opt_lazy_y = 1;          // integer coverage: log2 matrix not materialised by dfb_preprocess (see dfb_cov::y_lazy)
-    int opt_null2 = 1;           // second-generation null scan (fstat_tc2.cu); 0: the first fused kernel
+    int opt_null2 = 1;           // second-generation null scan (fstat_tc2.cu): 1 = when it pays (see null2_wanted), 2 = always, 0 = never
     int opt_k2_waves = 16;       // fused kernel: CTAs per resident slot (1 = persistent); see launch_fused
     double opt_null_cap_mb = 0;  // 0 = auto
     int opt_perm_batch = 0;      // 0 = auto

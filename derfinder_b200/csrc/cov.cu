@@ -1228,7 +1228,8 @@ int dfb_preprocess(dfb_ctx* ctx, dfb_cov* c, double scalefac, const int32_t* gro
     c->scalefac = scalefac;
     c->G = n_groups;
     // integer coverage: the log2 matrix is not written (dfb_cov::y_lazy) unless a value falls outside the table
-    bool lazy = ctx->opt_lazy_y && c->dtype == DFB_I32;
+    // (only when the consumer will be the second-generation null scan: the first-generation kernels read the matrix)
+    bool lazy = ctx->opt_lazy_y && c->dtype == DFB_I32 && null2_wanted(ctx, c->n);
     c->y.release();
     c->y_lazy = false;
     c->has_ym = false;

@@ -760,7 +760,7 @@ int dfb_set_option(dfb_ctx* c, const char* key, double value) {
     DFB_REQUIRE(c && key, "dfb_set_option: NULL argument");
     if (!strcmp(key, "screen")) c->opt_screen = value != 0;
     else if (!strcmp(key, "fused")) c->opt_fused = value != 0;
-    else if (!strcmp(key, "null2")) c->opt_null2 = value != 0;
+    else if (!strcmp(key, "null2")) c->opt_null2 = (int)value;  // 0 off, 1 auto (more than 16 samples), 2 always
     else if (!strcmp(key, "mma_warps")) c->opt_mma_warps = (int)value;
     else if (!strcmp(key, "a_stages")) c->opt_a_stages = (int)value;
     else if (!strcmp(key, "a16_fused")) c->opt_a16_fused = value != 0;

@@ -100,6 +100,11 @@ int ensure_lut(dfb_ctx* ctx, double scalefac);
 constexpr int LUT_SMEM = 4096;  // table entries the streaming kernels keep in shared memory
 
 // ---- fstat_tc2.cu
+// Which tensor-core null scan: the second generation (one fp16 product per chunk, TMA-fed) wins once the
+// contraction is long enough to matter; with up to 16 samples (K = 16: a single MMA per chunk) the scan is bound by
+// the FP64 refinement of frequent candidates and the first fused kernel, which keeps the FP64 tile in shared
+// memory, is faster (C2: 1.37 ms against 2.81 ms, gpurun_out/r2_am_sweep_c2.txt).
+inline bool null2_wanted(const dfb_ctx* ctx, int n) { return ctx->opt_null2 == 2 || (ctx->opt_null2 == 1 && n > 16); }
 struct PermBatch;
 // zero the flagged groups of a batch that used the context's kept-zero mask (no-op otherwise)
 int null2_release_mask(dfb_ctx* ctx, PermBatch* batch);

@@ -611,7 +611,7 @@ int fstat_observed(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, doubl
     {
         dfb_cov* cw = const_cast<dfb_cov*>(cov);
         cw->a16_center = -1;
-        if (ctx->opt_a16_fused && ctx->opt_screen && ctx->opt_null2 && cov->n <= 255 && mb.p >= 2 && mb.p <= 8 &&
+        if (ctx->opt_a16_fused && ctx->opt_screen && null2_wanted(ctx, cov->n) && cov->n <= 255 && mb.p >= 2 && mb.p <= 8 &&
             cov->n - mb.p > 0) {
             const int KA = (int)ceil_div(round_up(cov->n, 16), 64) * 64;
             const int64_t rows_pad = ceil_div(cov->N, 128) * 128;

@@ -233,7 +233,7 @@ static uint32_t umma_idesc_f16(int M, int N) {
 // accumulator stages = epilogue warp groups for `pe` screened columns at the default 32-permutation chunk
 // epilogue warp groups the kernel is compiled for: four for tiny models (the FP64 refinement of frequent
 // candidates dominates there), two otherwise (168 registers per thread: two TMEM register sets without spills)
-__host__ __device__ constexpr int n2_max_groups(int pe) { return pe <= 8 ? 4 : 2; }
+
 // Default chunk width: 32 permutations (a lane per permutation in the bookkeeping; at most 256 accumulator
 // columns for the model sizes the kernel is compiled for).  Measured on the chr1 shape (pe = 5, c3s workload,
 // gpurun_out/r2_*_sweep.txt): 32 permutations x 3 stages x 3 warp groups 2.14 ms; 24 permutations (128 columns)
@@ -244,15 +244,11 @@ __host__ __device__ constexpr int n2_default_ps(int pe) {
     while (ps + n2_pass_perms(pe) <= 32 && ((ps + n2_pass_perms(pe)) * pe + 15) / 16 * 16 <= 256) ps += n2_pass_perms(pe);
     return ps;
 }
-// columns [0, NCOL) of an accumulator row as 32 / 16 / 8-column loads, none of them waited for
-template <int NCOL>
-__device__ __forceinline__ void tmem_ld_row_nw(uint32_t taddr, uint32_t* r) {
-    static_assert(NCOL % 8 == 0, "column count");
-    constexpr int N32 = NCOL / 32, REM = NCOL % 32;
-#pragma unroll
-    for (int i = 0; i < N32; ++i) tmem_ld32_nw(taddr + (uint32_t)(32 * i), r + 32 * i);
-    if (REM >= 16) tmem_ld16_nw(taddr + (uint32_t)(32 * N32), r + 32 * N32);
-    if (REM % 16 >= 8) tmem_ld8_nw(taddr + (uint32_t)(32 * N32 + (REM >= 16 ? 16 : 0)), r + 32 * N32 + (REM >= 16 ? 16 : 0));
+// epilogue warp groups the kernel is compiled for = accumulator stages at the default chunk width (a group owns a
+// stage): 4 for up to four screened columns, 3 for five, 2 beyond -- which leaves 104 / 136 / 184 registers per thread
+__host__ __device__ constexpr int n2_max_groups(int pe) {
+    const int nmma = (n2_default_ps(pe) * pe + 15) / 16 * 16;
+    return 512 / nmma < 4 ? 512 / nmma : 4;
 }
 __host__ __device__ constexpr int n2_max_threads(int pe) { return 128 * n2_max_groups(pe) + 96; }
 
@@ -600,8 +596,11 @@ __global__ void __launch_bounds__(n2_max_threads(PT - J0), 1) fstat_null2_kernel
                             }
                         }
                     };
-                    constexpr int PSD = n2_default_ps(PE);
-                    if (n2_max_groups(PE) > 2 || ps != PSD) {  // 96 registers per thread (or a developer chunk width): pass by pass
+                    // Pass by pass, one register set.  Measured dead ends at the chr1 shape (c3s, gpurun_out/r2_am_sweep_c3s.txt):
+                    // a second register set with the load of pass k + 1 in flight under the evaluation of pass k
+                    // (2.01 -> 2.22 ms), and handing the accumulator back right after the last load instead of after
+                    // the last pass (no change): the epilogue's own latency is not what bounds the stage round trip.
+                    {
                         const int nscan = (P.dbg & 4) ? 0 : nq;
                         for (int q0 = 0; q0 < nscan; q0 += PP) {
                             uint32_t va[NC];
@@ -610,20 +609,10 @@ __global__ void __launch_bounds__(n2_max_threads(PT - J0), 1) fstat_null2_kernel
                             tmem_regs_ready<NC>(va);
                             scan_pass(va, q0);
                         }
-                    } else if (!(P.dbg & 4)) {
-                        // the whole accumulator row of the unit in ONE round trip to TMEM (up to 128 registers; two
-                        // warp groups leave 168 per thread), then the passes back to back
-                        uint32_t va[PSD * PE];
-                        tmem_ld_row_nw<PSD * PE>(taddr, va);
-                        tmem_ld_wait();
-                        tmem_regs_ready<PSD * PE>(va);
-#pragma unroll
-                        for (int pass = 0; pass < PSD / PP; ++pass)
-                            if (pass * PP < nq) scan_pass(va + pass * NC, pass * PP);
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(tmem_empty + 8 * s_mine);  // accumulator free: the next MMAs overlap the refinement
                     }
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(tmem_empty + 8 * s_mine);  // accumulator free: the next MMAs overlap the refinement
                     lap(3);  // epilogue: TMEM loads + candidate scan
                     if (nwork == 0) continue;  // the mask was zeroed before the launch: nothing to write
                     ew_w[lane] = 0u;
@@ -874,7 +863,7 @@ static bool null2_geometry(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBa
 }
 
 bool null2_supported(const dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, double lo, double hi, double adjust_f) {
-    if (!ctx->opt_screen || !ctx->opt_fused || ctx->opt_null2 == 0) return false;
+    if (!ctx->opt_screen || !ctx->opt_fused || !null2_wanted(ctx, cov->n)) return false;
     if (!(hi > 0.0) || !(lo < 0.0)) return false;  // one-sided positive cutoff only
     if (cov->n - mb.p <= 0 || !(adjust_f >= 0.0)) return false;
     const double df1 = (double)(mb.p - mb.p0), df2 = (double)(cov->n - mb.p);

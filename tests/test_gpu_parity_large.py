@@ -460,6 +460,7 @@ def test_lazy_log2_matrix_equals_materialised(dfb, n, extra, N, B, alpha):
         e = dfb.Engine(0)
         try:
             e.set_option("lazy_y", lazy)
+            e.set_option("null2", 2)  # the un-materialised path belongs to the second-generation null scan
             prep = dfb.preprocessCoverage(dict(coverage=cov, position=position), groupInfo=group, engine=e)
             has = C.c_int(0)
             e.lib.dfb_cov_info(prep["coverageProcessed"].h, None, None, None, None, None, None, C.byref(has))
@@ -543,3 +544,25 @@ def test_merge_results_objects(dfb, eng, tmp_path):
     # no chromosome has regions
     none = dfb.mergeResults(results={"chr2": results["chr2"]}, optionsStats=opts, cutoffFstatUsed=cut, engine=eng)
     assert none["fullRegions"] is None and none["fullNullSummary"] is None
+
+
+# ---------------------------------------------------------------------------------------------
+# second-generation null scan forced for small models (by default it is used from 17 samples on)
+
+
+@pytest.mark.parametrize("n,extra,N,B,alpha", [(12, 0, 20000, 70, 0.05), (14, 2, 15000, 40, 0.02), (16, 1, 9000, 33, 0.2)])
+def test_null2_forced_small_models(dfb, n, extra, N, B, alpha):
+    rng = np.random.default_rng(555 + n)
+    cov, position, group, models = synth(rng, N, n, p_extra=extra, seg=[N // 2, N - N // 2])
+    perm = random_perms(rng, B, n)
+    cut = dfb.calcFstatCutoff("theoretical", alpha, models=models)
+    e = dfb.Engine(0)
+    try:
+        e.set_option("null2", 2)
+        res, ores = run_both(dfb, e, cov, position, group, models, perm, cut)
+        assert_pipeline_equal(res, ores)
+        dense, screen, cand, diff = debug_screen(e, dfb.preprocessCoverage(dict(coverage=cov, position=position), engine=e)
+                                                 ["coverageProcessed"], models, perm, cut)
+        assert diff == 0 and dense == screen
+    finally:
+        e.close()
