@@ -122,6 +122,7 @@ struct dfb_ctx {
     size_t k2_gflag_cap = 0;       // bytes
     bool k2_clean = false;         // both buffers are all zero
     int opt_mask_cache = 1;
+    int opt_filter_events = 1;   // filterData mask of integer coverage from run events (0: expansion kernel)
     double null_density = 0;     // exceedance values per (base, permutation) seen by the last null scan (0 = unknown)
     double opt_scratch_gb = 24;  // upper bound for per-call scratch (mask + exceedance values)
     // pinned staging ring for pageable <-> device copies, and the host copy pool that drains it

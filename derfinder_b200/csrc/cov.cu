@@ -320,6 +320,209 @@ __global__ void __launch_bounds__(K1_THREADS) filter_tile_kernel(const FilterPar
     }
 }
 
+// PASS 0 in RUN space, for integer coverage without a library-size divisor ("one" and "mean" filters).
+//
+// The kept mask only needs, per position, the sum over the samples ("mean": sum / n > cutoff) or the number of
+// samples above the cutoff ("one": count > 0).  Both are sums of INTEGERS, so they do not depend on the order of
+// the additions and equal R's left-to-right double sums bit for bit (every partial sum is far below 2^53).  A
+// run [st, en) of value v then is two events -- +v at st, -v at en -- in a per-tile difference array, and one
+// prefix sum over the 2048 positions of the tile gives every position's sum: O(runs) work instead of the
+// O(positions x samples) expansion of filter_tile_kernel (a 2048-position tile of 100 samples holds ~4 500
+// runs but 204 800 position-sample pairs).  Zero runs -- ~90 % of a genome -- contribute nothing and are skipped.
+// Difference array of one tile -> per-position sums.  Block-wide; on return sum of position tid * 8 + q is
+// before + h[q].  (acc_s: K1_TILE + 1 entries, wsum_s: one per warp.)
+template <int FILTER>
+__device__ __forceinline__ void tile_event_sums(const FilterParams& P, int64_t tile, int64_t t0, int64_t t1,
+                                                unsigned long long* acc_s, long long* wsum_s, long long (&h)[K1_PER],
+                                                long long& before) {
+    const int n = P.rle.n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t* __restrict__ values = reinterpret_cast<const int32_t*>(P.rle.values);
+    const int64_t* __restrict__ cum = P.rle.cum;
+    __syncthreads();  // the previous user of acc_s / wsum_s is done
+    for (int i = tid; i <= K1_TILE; i += K1_THREADS) acc_s[i] = 0ull;
+    __syncthreads();
+    for (int s = warp; s < n; s += K1_THREADS / 32) {
+        const int64_t lo = P.rle.run_off[s], hi = P.rle.run_off[s + 1] - 1, cb = cum[lo];
+        const int64_t a = P.tile_run[tile * n + s];
+        int64_t b = hi;  // run holding the tile's last position
+        if (tile + 1 < P.tiles) {
+            b = P.tile_run[(tile + 1) * n + s];
+            if (cum[b] - cb >= t1) --b;  // the run holding t1 starts there: t1 - 1 is in the run before
+        }
+        for (int64_t g = a + lane; g <= b; g += 32) {
+            const int32_t v = values[g];
+            const long long c = FILTER == DFB_FILTER_MEAN ? (long long)v : (((double)v > P.cutoff) ? 1ll : 0ll);
+            if (c != 0) {
+                const int st = (int)(max(cum[g] - cb, t0) - t0);
+                const int en = (int)(min(cum[g + 1] - cb, t1) - t0);
+                atomicAdd(&acc_s[st], (unsigned long long)c);
+                atomicAdd(&acc_s[en], (unsigned long long)(-c));
+            }
+        }
+    }
+    __syncthreads();
+    // inclusive prefix sum over the positions: 8 per thread, then across the block
+    long long run = 0;
+#pragma unroll
+    for (int q = 0; q < K1_PER; ++q) {
+        run += (long long)acc_s[tid * K1_PER + q];
+        h[q] = run;
+    }
+    long long inc = run;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum_s[warp] = inc;
+    __syncthreads();
+    before = inc - run;
+    for (int w = 0; w < warp; ++w) before += wsum_s[w];
+}
+
+template <int FILTER>
+__global__ void __launch_bounds__(K1_THREADS) filter_events_kernel(const FilterParams P) {
+    __shared__ unsigned long long acc_s[K1_TILE + 1];
+    __shared__ long long wsum_s[K1_THREADS / 32];
+    __shared__ int cnt_s[K1_THREADS / 32];
+    const int n = P.rle.n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+        const int64_t t0 = tile * K1_TILE;
+        const int64_t t1 = min(t0 + (int64_t)K1_TILE, P.rle.len);  // exclusive
+        long long h[K1_PER], before;
+        tile_event_sums<FILTER>(P, tile, t0, t1, acc_s, wsum_s, h, before);
+        const int64_t p0 = t0 + (int64_t)tid * K1_PER;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int q = 0; q < K1_PER; ++q) {
+            if (p0 + q < t1) {
+                const long long sum = before + h[q];
+                const bool keep = FILTER == DFB_FILTER_MEAN ? (__ddiv_rn((double)sum, (double)n) > P.cutoff) : (sum > 0);
+                if (keep) bits |= 1u << q;
+            }
+        }
+        // four threads share one 32-bit mask word
+        uint32_t word = bits << ((tid & 3) * 8);
+        word |= __shfl_xor_sync(0xffffffffu, word, 1);
+        word |= __shfl_xor_sync(0xffffffffu, word, 2);
+        const int64_t w = (t0 >> 5) + (tid >> 2);
+        if ((tid & 3) == 0 && w * 32 < t1) P.mask[w] = word;
+        int c = __popc(bits);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+        if (lane == 0) cnt_s[warp] = c;
+        __syncthreads();
+        if (tid == 0) {
+            int t = 0;
+            for (int w2 = 0; w2 < K1_THREADS / 32; ++w2) t += cnt_s[w2];
+            P.tile_count[tile] = (uint32_t)t;
+        }
+    }
+}
+
+// PASS 1 for the same case (integer coverage, no divisor): compaction in RANK space.  Only the kept positions of a
+// tile are ever materialised: rank_s[p] = number of kept positions of the tile before p; a warp takes a sample,
+// every run that holds a kept position drops its index at the rank of its first kept position, a warp-level
+// max-scan spreads the indices over the tile's kept positions, and the values go out as coalesced stores -- no
+// block barrier inside the sample loop, nothing is expanded for positions that are filtered away (the expansion
+// kernel materialises whole 256-position sub-tiles).  meanCoverage comes from the same integer event sums as the
+// mask (exact, so equal to R's left-to-right double sum).
+__global__ void __launch_bounds__(K1_THREADS) filter_compact_events_kernel(const FilterParams P) {
+    __shared__ unsigned long long acc_s[K1_TILE + 1];
+    __shared__ long long wsum_s[K1_THREADS / 32];
+    __shared__ int rank_s[K1_TILE + 1];
+    __shared__ int wcnt_s[K1_THREADS / 32];
+    extern __shared__ int head_all[];  // [warps][K1_TILE + 64]
+    const int n = P.rle.n;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int32_t* __restrict__ values = reinterpret_cast<const int32_t*>(P.rle.values);
+    const int64_t* __restrict__ cum = P.rle.cum;
+    int* head = head_all + (size_t)warp * (K1_TILE + 64);
+    for (int64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
+        const int cnt = (int)P.tile_count[tile];
+        if (cnt == 0) continue;  // block-uniform
+        const int64_t t0 = tile * K1_TILE;
+        const int64_t t1 = min(t0 + (int64_t)K1_TILE, P.rle.len);
+        const int64_t p0 = t0 + (int64_t)tid * K1_PER;
+        const int64_t dst_tile = P.tile_off[tile];
+        uint32_t bits = 0;
+        if (p0 < t1) bits = (P.mask[p0 >> 5] >> (p0 & 31)) & 0xffu;
+        long long h[K1_PER], before = 0;
+        if (P.mean) tile_event_sums<DFB_FILTER_MEAN>(P, tile, t0, t1, acc_s, wsum_s, h, before);
+        else __syncthreads();  // rank_s / wcnt_s of the previous tile have been read
+        // ranks of my 8 positions
+        const int c = __popc(bits);
+        int inc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wcnt_s[warp] = inc;
+        __syncthreads();
+        int r = inc - c;
+        for (int w = 0; w < warp; ++w) r += wcnt_s[w];
+#pragma unroll
+        for (int q = 0; q < K1_PER; ++q) {
+            rank_s[tid * K1_PER + q] = r;
+            if ((bits >> q) & 1u) {
+                if (P.mean) P.mean[dst_tile + r] = __ddiv_rn((double)(before + h[q]), (double)n);
+                ++r;
+            }
+        }
+        if (tid == K1_THREADS - 1) rank_s[K1_TILE] = r;  // == cnt
+        __syncthreads();
+        // odd chunk length: the lanes' contiguous chunks start in different banks
+        const int chunk = ((cnt + 31) / 32) | 1;
+        for (int s = warp; s < n; s += K1_THREADS / 32) {
+            const int64_t lo = P.rle.run_off[s], hi = P.rle.run_off[s + 1] - 1, cb = cum[lo];
+            const int64_t a = P.tile_run[tile * n + s];
+            int64_t b = hi;
+            if (tile + 1 < P.tiles) {
+                b = P.tile_run[(tile + 1) * n + s];
+                if (cum[b] - cb >= t1) --b;
+            }
+            for (int i = lane; i < cnt; i += 32) head[i] = 0;
+            __syncwarp();
+            for (int64_t g = a + lane; g <= b; g += 32) {
+                const int st = (int)(max(cum[g] - cb, t0) - t0);
+                const int en = (int)(min(cum[g + 1] - cb, t1) - t0);
+                const int r0 = rank_s[st], r1 = rank_s[en];
+                if (r1 > r0) head[r0] = (int)(g - a) + 1;  // zero runs too: they end the previous run's value
+            }
+            __syncwarp();
+            // warp max-scan over head[0, cnt): contiguous chunk per lane, lane totals by shuffle, second sweep
+            const int i0 = min(lane * chunk, cnt), i1 = min(i0 + chunk, cnt);
+            int m = 0;
+            for (int i = i0; i < i1; ++i) {
+                m = max(m, head[i]);
+                head[i] = m;
+            }
+            int pm = m;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, pm, o);
+                if (lane >= o) pm = max(pm, t);
+            }
+            int prev = __shfl_up_sync(0xffffffffu, pm, 1);
+            if (lane == 0) prev = 0;
+            if (prev)
+                for (int i = i0; i < i1 && head[i] < prev; ++i) head[i] = prev;  // heads only grow along the tile
+            __syncwarp();
+            if (P.out_is_double) {
+                double* dst = reinterpret_cast<double*>(P.out) + (size_t)s * P.ld + dst_tile;
+                for (int i = lane; i < cnt; i += 32) dst[i] = (double)values[a + head[i] - 1];
+            } else {
+                int32_t* dst = reinterpret_cast<int32_t*>(P.out) + (size_t)s * P.ld + dst_tile;
+                for (int i = lane; i < cnt; i += 32) dst[i] = values[a + head[i] - 1];
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // mask words -> run boundaries: a position starts a run when its bit differs from the previous one
 __global__ void __launch_bounds__(256) mask_run_count_kernel(const uint32_t* __restrict__ mask, int64_t W, int64_t len,
                                                              uint32_t* __restrict__ counts) {
@@ -609,6 +812,20 @@ static int filter_rle_impl(dfb_ctx* ctx, int n, int dtype, const void* const* va
         if (mapped)
             for (int s2 = 0; s2 < n; ++s2) norm = norm || mapped[s2] != 1.0;
         if (dtype == DFB_I32) {
+            if (pass == 0 && !norm && filter != DFB_FILTER_NONE && ctx->opt_filter_events) {
+                // integer sums: the mask comes from run events, no expansion (filter_events_kernel)
+                KTimer t(ctx, DFB_K_PREP);
+                if (filter == DFB_FILTER_MEAN) filter_events_kernel<DFB_FILTER_MEAN><<<grid, K1_THREADS, 0, ctx->stream>>>(P);
+                else filter_events_kernel<DFB_FILTER_ONE><<<grid, K1_THREADS, 0, ctx->stream>>>(P);
+                return DFB_OK;
+            }
+            if (pass == 1 && !norm && filter != DFB_FILTER_NONE && ctx->opt_filter_events) {
+                const size_t hs = (size_t)(K1_THREADS / 32) * (K1_TILE + 64) * sizeof(int);
+                DFB_CUDA(cudaFuncSetAttribute(filter_compact_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
+                KTimer t(ctx, DFB_K_PREP);
+                filter_compact_events_kernel<<<grid, K1_THREADS, hs, ctx->stream>>>(P);
+                return DFB_OK;
+            }
             if (pass == 0) return norm ? go(filter_tile_kernel<int32_t, 0, true>) : go(filter_tile_kernel<int32_t, 0, false>);
             return norm ? go(filter_tile_kernel<int32_t, 1, true>) : go(filter_tile_kernel<int32_t, 1, false>);
         }

@@ -766,6 +766,7 @@ int dfb_set_option(dfb_ctx* c, const char* key, double value) {
     else if (!strcmp(key, "a16_fused")) c->opt_a16_fused = value != 0;
     else if (!strcmp(key, "lazy_y")) c->opt_lazy_y = value != 0;
     else if (!strcmp(key, "mask_cache")) c->opt_mask_cache = value != 0;
+    else if (!strcmp(key, "filter_events")) c->opt_filter_events = value != 0;
     else if (!strcmp(key, "dbg")) c->opt_dbg = (int)value;
     else if (!strcmp(key, "tmem_stages")) c->opt_tmem_stages = (int)value;
     else if (!strcmp(key, "k2_waves")) c->opt_k2_waves = (int)value;

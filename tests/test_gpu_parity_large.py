@@ -566,3 +566,27 @@ def test_null2_forced_small_models(dfb, n, extra, N, B, alpha):
         assert diff == 0 and dense == screen
     finally:
         e.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# filterData: the kept mask from run events (integer coverage, no divisor) == the expansion kernel == the oracle
+
+
+@pytest.mark.parametrize("flt,cutoff,n,length,mean_run", [("mean", 2.5, 9, 300007, 37), ("one", 5, 33, 120011, 11),
+                                                          ("mean", 0, 5, 70001, 3), ("one", -1, 4, 50000, 50),
+                                                          ("mean", 5, 100, 41000, 45)])
+def test_filter_events_equals_expansion(dfb, flt, cutoff, n, length, mean_run):
+    from test_gpu_parity import random_rle_cols
+    rng = np.random.default_rng(8080 + n)
+    cols = random_rle_cols(rng, n, length, mean_run, 0.5)
+    o = O.filter_data(cols, cutoff=cutoff, filter=flt, returnMean=True)
+    for ev in (1, 0):
+        e = dfb.Engine(0)
+        try:
+            e.set_option("filter_events", ev)
+            f = dfb.filterData(cols, cutoff=cutoff, filter=flt, returnMean=True, engine=e)
+            assert np.array_equal(f["position"][0], o.position[0]) and np.array_equal(f["position"][1], o.position[1]), ev
+            assert np.array_equal(f["coverage"].to_numpy(), o.coverage), ev
+            assert np.array_equal(f["meanCoverage"], o.meanCoverage), ev
+        finally:
+            e.close()
