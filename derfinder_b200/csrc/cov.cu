@@ -39,6 +39,7 @@ struct FilterParams {
     void* out;             // [n][ld] int32 or double
     int out_is_double;
     double* mean;          // [N]
+    double* mean_tmp;      // [tiles][K1_TILE] means of a tile's kept positions in tile-local rank order (events path)
     int64_t tiles;
 };
 
@@ -409,37 +410,51 @@ __global__ void __launch_bounds__(K1_THREADS) filter_events_kernel(const FilterP
         word |= __shfl_xor_sync(0xffffffffu, word, 2);
         const int64_t w = (t0 >> 5) + (tid >> 2);
         if ((tid & 3) == 0 && w * 32 < t1) P.mask[w] = word;
-        int c = __popc(bits);
+        const int c = __popc(bits);
+        int inc = c;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-        if (lane == 0) cnt_s[warp] = c;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) cnt_s[warp] = inc;
         __syncthreads();
         if (tid == 0) {
             int t = 0;
             for (int w2 = 0; w2 < K1_THREADS / 32; ++w2) t += cnt_s[w2];
             P.tile_count[tile] = (uint32_t)t;
         }
+        if (FILTER == DFB_FILTER_MEAN && P.mean_tmp) {
+            // the sums are at hand: the means of the kept positions wait in tile-local rank order for the compaction
+            int r = inc - c;
+            for (int w2 = 0; w2 < warp; ++w2) r += cnt_s[w2];
+            double* mt = P.mean_tmp + (size_t)tile * K1_TILE;
+#pragma unroll
+            for (int q = 0; q < K1_PER; ++q)
+                if ((bits >> q) & 1u) mt[r++] = __ddiv_rn((double)(before + h[q]), (double)n);
+        }
     }
 }
 
 // PASS 1 for the same case (integer coverage, no divisor): compaction in RANK space.  Only the kept positions of a
 // tile are ever materialised: rank_s[p] = number of kept positions of the tile before p; a warp takes a sample,
-// every run that holds a kept position drops its index at the rank of its first kept position, a warp-level
-// max-scan spreads the indices over the tile's kept positions, and the values go out as coalesced stores -- no
-// block barrier inside the sample loop, nothing is expanded for positions that are filtered away (the expansion
-// kernel materialises whole 256-position sub-tiles).  meanCoverage comes from the same integer event sums as the
-// mask (exact, so equal to R's left-to-right double sum).
+// every run that holds kept positions is written by the whole warp straight to the ranks of those positions in the
+// output (contiguous, so the stores coalesce) -- no block barrier inside the sample loop, nothing is expanded for
+// positions that are filtered away (the expansion kernel materialises whole 256-position sub-tiles).
+// meanCoverage comes from the same integer event sums as the mask (exact, so equal to R's left-to-right double sum).
 __global__ void __launch_bounds__(K1_THREADS) filter_compact_events_kernel(const FilterParams P) {
     __shared__ unsigned long long acc_s[K1_TILE + 1];
     __shared__ long long wsum_s[K1_THREADS / 32];
     __shared__ int rank_s[K1_TILE + 1];
     __shared__ int wcnt_s[K1_THREADS / 32];
-    extern __shared__ int head_all[];  // [warps][K1_TILE + 64]
+    extern __shared__ int64_t compact_dyn[];  // ra[n], rb[n], cb[n]
     const int n = P.rle.n;
+    int64_t* ra_s = compact_dyn;
+    int64_t* rb_s = compact_dyn + n;
+    int64_t* cb_s = compact_dyn + 2 * (size_t)n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int32_t* __restrict__ values = reinterpret_cast<const int32_t*>(P.rle.values);
     const int64_t* __restrict__ cum = P.rle.cum;
-    int* head = head_all + (size_t)warp * (K1_TILE + 64);
     for (int64_t tile = blockIdx.x; tile < P.tiles; tile += gridDim.x) {
         const int cnt = (int)P.tile_count[tile];
         if (cnt == 0) continue;  // block-uniform
@@ -450,8 +465,24 @@ __global__ void __launch_bounds__(K1_THREADS) filter_compact_events_kernel(const
         uint32_t bits = 0;
         if (p0 < t1) bits = (P.mask[p0 >> 5] >> (p0 & 31)) & 0xffu;
         long long h[K1_PER], before = 0;
-        if (P.mean) tile_event_sums<DFB_FILTER_MEAN>(P, tile, t0, t1, acc_s, wsum_s, h, before);
-        else __syncthreads();  // rank_s / wcnt_s of the previous tile have been read
+        const bool sums_here = P.mean && !P.mean_tmp;  // "one" filter: the mask pass counted samples, not coverage
+        if (sums_here) tile_event_sums<DFB_FILTER_MEAN>(P, tile, t0, t1, acc_s, wsum_s, h, before);
+        else __syncthreads();  // rank_s / wcnt_s / run tables of the previous tile have been read
+        if (P.mean && P.mean_tmp)
+            for (int i = tid; i < cnt; i += K1_THREADS) P.mean[dst_tile + i] = P.mean_tmp[(size_t)tile * K1_TILE + i];
+        // first and last run of every sample in this tile (all samples in parallel: the per-sample loop below
+        // starts from shared memory instead of a chain of dependent global loads)
+        for (int s = tid; s < n; s += K1_THREADS) {
+            const int64_t lo = P.rle.run_off[s], hi = P.rle.run_off[s + 1] - 1, cb = cum[lo];
+            int64_t b = hi;
+            if (tile + 1 < P.tiles) {
+                b = P.tile_run[(tile + 1) * n + s];
+                if (cum[b] - cb >= t1) --b;
+            }
+            ra_s[s] = P.tile_run[tile * n + s];
+            rb_s[s] = b;
+            cb_s[s] = cb;
+        }
         // ranks of my 8 positions
         const int c = __popc(bits);
         int inc = c;
@@ -468,57 +499,42 @@ __global__ void __launch_bounds__(K1_THREADS) filter_compact_events_kernel(const
         for (int q = 0; q < K1_PER; ++q) {
             rank_s[tid * K1_PER + q] = r;
             if ((bits >> q) & 1u) {
-                if (P.mean) P.mean[dst_tile + r] = __ddiv_rn((double)(before + h[q]), (double)n);
+                if (sums_here) P.mean[dst_tile + r] = __ddiv_rn((double)(before + h[q]), (double)n);
                 ++r;
             }
         }
         if (tid == K1_THREADS - 1) rank_s[K1_TILE] = r;  // == cnt
         __syncthreads();
-        // odd chunk length: the lanes' contiguous chunks start in different banks
-        const int chunk = ((cnt + 31) / 32) | 1;
         for (int s = warp; s < n; s += K1_THREADS / 32) {
-            const int64_t lo = P.rle.run_off[s], hi = P.rle.run_off[s + 1] - 1, cb = cum[lo];
-            const int64_t a = P.tile_run[tile * n + s];
-            int64_t b = hi;
-            if (tile + 1 < P.tiles) {
-                b = P.tile_run[(tile + 1) * n + s];
-                if (cum[b] - cb >= t1) --b;
+            const int64_t a = ra_s[s], b = rb_s[s], cb = cb_s[s];
+            double* dstd = reinterpret_cast<double*>(P.out) + (size_t)s * P.ld + dst_tile;
+            int32_t* dsti = reinterpret_cast<int32_t*>(P.out) + (size_t)s * P.ld + dst_tile;
+            for (int64_t g0 = a; g0 <= b; g0 += 32) {
+                const int64_t g = g0 + lane;
+                int r0 = 0, r1 = 0;
+                int32_t v = 0;
+                if (g <= b) {
+                    const int st = (int)(max(cum[g] - cb, t0) - t0);
+                    const int en = (int)(min(cum[g + 1] - cb, t1) - t0);
+                    r0 = rank_s[st];
+                    r1 = rank_s[en];
+                    if (r1 > r0) v = values[g];
+                }
+                // every run with kept positions is written by the whole warp: its ranks are contiguous in the output
+                unsigned live = __ballot_sync(0xffffffffu, r1 > r0);
+                while (live) {
+                    const int j = __ffs(live) - 1;
+                    live &= live - 1;
+                    const int b0 = __shfl_sync(0xffffffffu, r0, j), b1 = __shfl_sync(0xffffffffu, r1, j);
+                    const int32_t bv = __shfl_sync(0xffffffffu, v, j);
+                    if (P.out_is_double) {
+                        const double dv = (double)bv;
+                        for (int i = b0 + lane; i < b1; i += 32) dstd[i] = dv;
+                    } else {
+                        for (int i = b0 + lane; i < b1; i += 32) dsti[i] = bv;
+                    }
+                }
             }
-            for (int i = lane; i < cnt; i += 32) head[i] = 0;
-            __syncwarp();
-            for (int64_t g = a + lane; g <= b; g += 32) {
-                const int st = (int)(max(cum[g] - cb, t0) - t0);
-                const int en = (int)(min(cum[g + 1] - cb, t1) - t0);
-                const int r0 = rank_s[st], r1 = rank_s[en];
-                if (r1 > r0) head[r0] = (int)(g - a) + 1;  // zero runs too: they end the previous run's value
-            }
-            __syncwarp();
-            // warp max-scan over head[0, cnt): contiguous chunk per lane, lane totals by shuffle, second sweep
-            const int i0 = min(lane * chunk, cnt), i1 = min(i0 + chunk, cnt);
-            int m = 0;
-            for (int i = i0; i < i1; ++i) {
-                m = max(m, head[i]);
-                head[i] = m;
-            }
-            int pm = m;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, pm, o);
-                if (lane >= o) pm = max(pm, t);
-            }
-            int prev = __shfl_up_sync(0xffffffffu, pm, 1);
-            if (lane == 0) prev = 0;
-            if (prev)
-                for (int i = i0; i < i1 && head[i] < prev; ++i) head[i] = prev;  // heads only grow along the tile
-            __syncwarp();
-            if (P.out_is_double) {
-                double* dst = reinterpret_cast<double*>(P.out) + (size_t)s * P.ld + dst_tile;
-                for (int i = lane; i < cnt; i += 32) dst[i] = (double)values[a + head[i] - 1];
-            } else {
-                int32_t* dst = reinterpret_cast<int32_t*>(P.out) + (size_t)s * P.ld + dst_tile;
-                for (int i = lane; i < cnt; i += 32) dst[i] = values[a + head[i] - 1];
-            }
-            __syncwarp();
         }
     }
 }
@@ -820,7 +836,7 @@ static int filter_rle_impl(dfb_ctx* ctx, int n, int dtype, const void* const* va
                 return DFB_OK;
             }
             if (pass == 1 && !norm && filter != DFB_FILTER_NONE && ctx->opt_filter_events) {
-                const size_t hs = (size_t)(K1_THREADS / 32) * (K1_TILE + 64) * sizeof(int);
+                const size_t hs = (size_t)3 * n * sizeof(int64_t);
                 DFB_CUDA(cudaFuncSetAttribute(filter_compact_events_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hs));
                 KTimer t(ctx, DFB_K_PREP);
                 filter_compact_events_kernel<<<grid, K1_THREADS, hs, ctx->stream>>>(P);
@@ -832,6 +848,16 @@ static int filter_rle_impl(dfb_ctx* ctx, int n, int dtype, const void* const* va
         if (pass == 0) return norm ? go(filter_tile_kernel<double, 0, true>) : go(filter_tile_kernel<double, 0, false>);
         return norm ? go(filter_tile_kernel<double, 1, true>) : go(filter_tile_kernel<double, 1, false>);
     };
+    DevBuf<double> mean_tmp;
+    {
+        bool norm0 = false;
+        if (mapped)
+            for (int s2 = 0; s2 < n; ++s2) norm0 = norm0 || mapped[s2] != 1.0;
+        if (want_mean && dtype == DFB_I32 && !norm0 && filter == DFB_FILTER_MEAN && ctx->opt_filter_events && tiles > 0) {
+            DFB_TRY(mean_tmp.alloc(ctx, (size_t)tiles * K1_TILE));
+            P.mean_tmp = mean_tmp.p;
+        }
+    }
     if (tiles > 0) DFB_TRY(launch_filter(0));
     DFB_CUDA(cudaGetLastError());
     DFB_TRY(exclusive_scan_u32(ctx, tile_count.p, tile_off.p, tiles, total_dev.p, DFB_K_PREP));
