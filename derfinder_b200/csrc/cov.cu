@@ -57,14 +57,15 @@ __device__ __forceinline__ int64_t find_run(const int64_t* __restrict__ cum, int
 // run of every sample that contains the first position of every tile: tab[tile * n + s].  All
 // tiles x samples searches run in parallel here, so the tile loop of the filter kernel starts from a
 // table look-up instead of 2 x log2(#runs) dependent loads per sample.
-__global__ void __launch_bounds__(256) tile_runs_kernel(RleDev R, int64_t tiles, int64_t* __restrict__ tab) {
+__global__ void __launch_bounds__(256) tile_runs_kernel(RleDev R, int64_t tiles, int64_t* __restrict__ tab,
+                                                        int tile_len = K1_TILE) {
     const int n = R.n;
     const int64_t total = tiles * n;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int64_t tile = i / n;
         const int s = (int)(i - tile * n);
         const int64_t lo = R.run_off[s], hi = R.run_off[s + 1] - 1;
-        tab[i] = find_run(R.cum, R.cum[lo], lo, hi, tile * K1_TILE);
+        tab[i] = find_run(R.cum, R.cum[lo], lo, hi, tile * tile_len);
     }
 }
 
@@ -365,10 +366,16 @@ __device__ __forceinline__ void tile_event_sums(const FilterParams& P, int64_t t
     __syncthreads();
     // inclusive prefix sum over the positions: 8 per thread, then across the block
     long long run = 0;
+    {  // 16-byte loads: element-wise reads at a stride of 64 bytes per thread would be bank conflicts all the way
+        const ulonglong2* av = reinterpret_cast<const ulonglong2*>(acc_s) + tid * (K1_PER / 2);
 #pragma unroll
-    for (int q = 0; q < K1_PER; ++q) {
-        run += (long long)acc_s[tid * K1_PER + q];
-        h[q] = run;
+        for (int q = 0; q < K1_PER; q += 2) {
+            const ulonglong2 v2 = av[q >> 1];
+            run += (long long)v2.x;
+            h[q] = run;
+            run += (long long)v2.y;
+            h[q + 1] = run;
+        }
     }
     long long inc = run;
 #pragma unroll
@@ -384,7 +391,7 @@ __device__ __forceinline__ void tile_event_sums(const FilterParams& P, int64_t t
 
 template <int FILTER>
 __global__ void __launch_bounds__(K1_THREADS) filter_events_kernel(const FilterParams P) {
-    __shared__ unsigned long long acc_s[K1_TILE + 1];
+    __shared__ __align__(16) unsigned long long acc_s[K1_TILE + 2];
     __shared__ long long wsum_s[K1_THREADS / 32];
     __shared__ int cnt_s[K1_THREADS / 32];
     const int n = P.rle.n;
@@ -443,9 +450,9 @@ __global__ void __launch_bounds__(K1_THREADS) filter_events_kernel(const FilterP
 // positions that are filtered away (the expansion kernel materialises whole 256-position sub-tiles).
 // meanCoverage comes from the same integer event sums as the mask (exact, so equal to R's left-to-right double sum).
 __global__ void __launch_bounds__(K1_THREADS) filter_compact_events_kernel(const FilterParams P) {
-    __shared__ unsigned long long acc_s[K1_TILE + 1];
+    __shared__ __align__(16) unsigned long long acc_s[K1_TILE + 2];
     __shared__ long long wsum_s[K1_THREADS / 32];
-    __shared__ int rank_s[K1_TILE + 1];
+    __shared__ __align__(16) int rank_s[K1_TILE + 4];
     __shared__ int wcnt_s[K1_THREADS / 32];
     extern __shared__ int64_t compact_dyn[];  // ra[n], rb[n], cb[n]
     const int n = P.rle.n;
@@ -495,14 +502,17 @@ __global__ void __launch_bounds__(K1_THREADS) filter_compact_events_kernel(const
         __syncthreads();
         int r = inc - c;
         for (int w = 0; w < warp; ++w) r += wcnt_s[w];
+        int rk[K1_PER];
 #pragma unroll
         for (int q = 0; q < K1_PER; ++q) {
-            rank_s[tid * K1_PER + q] = r;
+            rk[q] = r;
             if ((bits >> q) & 1u) {
                 if (sums_here) P.mean[dst_tile + r] = __ddiv_rn((double)(before + h[q]), (double)n);
                 ++r;
             }
         }
+        reinterpret_cast<int4*>(rank_s)[tid * 2] = make_int4(rk[0], rk[1], rk[2], rk[3]);  // 16-byte stores: no bank conflicts
+        reinterpret_cast<int4*>(rank_s)[tid * 2 + 1] = make_int4(rk[4], rk[5], rk[6], rk[7]);
         if (tid == K1_THREADS - 1) rank_s[K1_TILE] = r;  // == cnt
         __syncthreads();
         for (int s = warp; s < n; s += K1_THREADS / 32) {
@@ -640,12 +650,13 @@ __global__ void __launch_bounds__(K1_THREADS) expand_rle_kernel(RleDev R, int64_
 // shared memory, an inclusive max-scan over the positions spreads it, and every thread writes its 8 positions
 // as 16-byte stores.  The per-thread binary search of expand_rle_kernel (2 x 19 dependent loads per 8 positions
 // at the chr1 shape) made that kernel latency-bound at 1.3 TB/s.
-template <typename V>
-__global__ void __launch_bounds__(K1_THREADS) expand_rle_tiles_kernel(RleDev R, int64_t tiles, const int64_t* __restrict__ tab,
-                                                                      int64_t ld, V* __restrict__ out) {
-    __shared__ int head_s[K1_TILE];
-    __shared__ V val_s[K1_TILE];
-    __shared__ int wmax_s[K1_THREADS / 32];
+template <typename V, int THREADS>
+__global__ void __launch_bounds__(THREADS) expand_rle_tiles_kernel(RleDev R, int64_t tiles, const int64_t* __restrict__ tab,
+                                                                   int64_t ld, V* __restrict__ out) {
+    constexpr int TILE = THREADS * K1_PER;
+    __shared__ __align__(16) int head_s[TILE];
+    __shared__ V val_s[TILE];
+    __shared__ int wmax_s[THREADS / 32];
     const int s = blockIdx.y, n = R.n;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const V* __restrict__ values = reinterpret_cast<const V*>(R.values);
@@ -653,19 +664,19 @@ __global__ void __launch_bounds__(K1_THREADS) expand_rle_tiles_kernel(RleDev R, 
     const int64_t lo = R.run_off[s], hi = R.run_off[s + 1] - 1, cb = cum[lo];
     (void)lo;
     for (int64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
-        const int64_t t0 = tile * K1_TILE, t1 = min(t0 + (int64_t)K1_TILE, R.len);
+        const int64_t t0 = tile * TILE, t1 = min(t0 + (int64_t)TILE, R.len);
         const int64_t ra = tab[tile * n + s];
         int64_t rb = hi;
         if (tile + 1 < tiles) {
             rb = tab[(tile + 1) * n + s];
             if (cum[rb] - cb >= t1) --rb;  // the run holding t1 starts there: t1 - 1 is in the run before
         }
-        const int nr = (int)(rb - ra + 1);  // <= 2048: every run holds at least one position of the tile
+        const int nr = (int)(rb - ra + 1);  // <= TILE: every run holds at least one position of the tile
         __syncthreads();                    // previous tile consumed
 #pragma unroll
-        for (int q = 0; q < K1_PER; ++q) head_s[q * K1_THREADS + tid] = 0;
+        for (int q = 0; q < K1_PER; ++q) head_s[q * THREADS + tid] = 0;
         __syncthreads();
-        for (int j = tid; j < nr; j += K1_THREADS) {
+        for (int j = tid; j < nr; j += THREADS) {
             const int64_t r = ra + j;
             const int st = (int)(max(cum[r] - cb, t0) - t0);
             head_s[st] = j;
@@ -674,10 +685,15 @@ __global__ void __launch_bounds__(K1_THREADS) expand_rle_tiles_kernel(RleDev R, 
         __syncthreads();
         // inclusive max-scan of the heads: thread-local over 8 consecutive positions, then across the block
         int h[K1_PER];
+        {  // two 16-byte loads per thread: element-wise reads at stride 8 would be 8-way bank conflicts
+            const int4 ha = reinterpret_cast<const int4*>(head_s)[tid * 2], hb = reinterpret_cast<const int4*>(head_s)[tid * 2 + 1];
+            h[0] = ha.x; h[1] = ha.y; h[2] = ha.z; h[3] = ha.w;
+            h[4] = hb.x; h[5] = hb.y; h[6] = hb.z; h[7] = hb.w;
+        }
         int run = 0;
 #pragma unroll
         for (int q = 0; q < K1_PER; ++q) {
-            run = max(run, head_s[tid * K1_PER + q]);
+            run = max(run, h[q]);
             h[q] = run;
         }
         int inc = run;
@@ -1377,8 +1393,11 @@ int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, 
         R.run_off = up.run_off.p;
         R.n = n;
         R.len = N;
-        const int64_t tiles = ceil_div(N, K1_TILE);
-        const dim3 grid((unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 8), (unsigned)n);
+        // 1024-position tiles on 128 threads: sixteen blocks per SM keep twice the tiles in flight (the kernel is
+        // bound by the latency of a tile's dependent steps, not by bandwidth)
+        constexpr int XT = 128, XTILE = XT * K1_PER;
+        const int64_t tiles = ceil_div(N, XTILE);
+        const dim3 grid((unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 16), (unsigned)n);
         DevBuf<int64_t> tab;  // run holding the first position of every (tile, sample)
         rc = tab.alloc(ctx, (size_t)tiles * n);
         if (rc < 0) {
@@ -1386,11 +1405,11 @@ int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, 
             return rc;
         }
         KTimer t(ctx, DFB_K_PREP, 2);
-        tile_runs_kernel<<<grid_for(tiles * n, 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(R, tiles, tab.p);
+        tile_runs_kernel<<<grid_for(tiles * n, 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(R, tiles, tab.p, XTILE);
         if (dtype == DFB_I32)
-            expand_rle_tiles_kernel<int32_t><<<grid, K1_THREADS, 0, ctx->stream>>>(R, tiles, tab.p, c->ld, c->xi.p);
+            expand_rle_tiles_kernel<int32_t, XT><<<grid, XT, 0, ctx->stream>>>(R, tiles, tab.p, c->ld, c->xi.p);
         else
-            expand_rle_tiles_kernel<double><<<grid, K1_THREADS, 0, ctx->stream>>>(R, tiles, tab.p, c->ld, c->xd.p);
+            expand_rle_tiles_kernel<double, XT><<<grid, XT, 0, ctx->stream>>>(R, tiles, tab.p, c->ld, c->xd.p);
     }
     cudaError_t e = cudaGetLastError();
     // the position index is built while the expansion runs (host run loops + two small uploads)
