@@ -1187,8 +1187,10 @@ static int launch_preprocess(dfb_ctx* ctx, const dfb_cov* c, PrepParams P, bool 
     const size_t smem = ((size_t)P.lut_s + (greg ? 0 : (size_t)P.G * 256)) * sizeof(double) + (size_t)round_up(c->n, 8);
     auto go = [&](auto kern) -> int {
         if (smem > 48 * 1024) DFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;  // one resident wave, grid-stride loop inside (every block loads the table head once)
+        DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(c->N, 256), (int64_t)ctx->sm_count * std::max(occ, 1)));
         KTimer t(ctx, DFB_K_PREP);
-        const int grid = grid_for(c->N, 256, ctx->sm_count, 8);
         kern<<<grid, 256, smem, ctx->stream>>>(P);
         return DFB_OK;
     };

@@ -639,9 +639,13 @@ int fstat_observed(dfb_ctx* ctx, const dfb_cov* cov, const ModelBasis& mb, doubl
     }
     // shared memory: the basis as [chunks][n][pc rounded up to even] + the head of the log2 table
     const size_t smem = ((size_t)mb.chunks * mb.n * ((mb.pc + 1) & ~1) + (srci ? (size_t)LUT_SMEM : 0)) * sizeof(double);
-    const int grid = grid_for(cov->N, 256, ctx->sm_count, 8);
     auto launch = [&](auto kern) -> int {
         if (smem > 48 * 1024) DFB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        // exactly one resident wave (grid-stride loop inside): a grid of 8 blocks per SM with 3 resident ran 2.67 waves,
+        // the last one a third empty, and every block reloads the basis and the table head
+        int occ = 0;
+        DFB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, smem));
+        const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(ceil_div(cov->N, 256), (int64_t)ctx->sm_count * std::max(occ, 1)));
         KTimer t(ctx, DFB_K_FSTAT, 1);
         kern<<<grid, 256, smem, ctx->stream>>>(P);
         return DFB_OK;
