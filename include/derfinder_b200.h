@@ -96,6 +96,14 @@ int dfb_kernel_time(dfb_ctx* ctx, int kernel, double* ms, int64_t* launches);
  *   "null_capacity_mb"  initial capacity of the exceedance value buffer
  *   "perm_batch"        permutations per launch (0 = auto)
  *   "scratch_gb"        upper bound for per-call device scratch (default 24)
+ *   "null2"       0/1/2  second-generation tensor-core null scan: 1 = from 17 samples on (default),
+ *                     2 = always, 0 = never (the first fused kernel)
+ *   "lazy_y"      0/1  integer coverage: dfb_preprocess does not write the log2 matrix; it is
+ *                     produced on demand (default 1; results identical)
+ *   "mask_cache"  0/1  mask rows of the null scan kept zero between calls instead of a memset per
+ *                     call (default 1)
+ *   "filter_events" 0/1  dfb_filter_rle of integer coverage without a divisor in run space
+ *                     (default 1; 0 = tile expansion kernel; results identical)
  * Developer knobs of the fused null kernel (geometry overrides for measurements; results are
  * identical for every valid setting, tests/test_gpu_parity.py::test_fused_kernel_variants_agree):
  *   "chunk_perms" permutations per MMA chunk, "b_stages" B-tile stages (1-4), "tmem_stages"
@@ -154,7 +162,9 @@ int dfb_cov_get_mean(const dfb_cov* cov, double* out);                 /* meanCo
 /* preprocessCoverage() -- R/preprocessCoverage.R:97-260 (the colsubset re-filter is a
  * dfb_filter_rle call made by the glue first).  Computes on the device, in one pass over the
  * filtered coverage: meanCoverage (if absent, :191-193), the G group means (:197-206;
- * group_of_sample[s] in 0..G-1, or NULL/G=0) and Y = log2(x + scalefac) (:209-212). */
+ * group_of_sample[s] in 0..G-1, or NULL/G=0) and Y = log2(x + scalefac) (:209-212).
+ * For integer coverage Y is not stored: the F-stat kernels read the coverage through the same
+ * host-built log2 table; dfb_cov_get_processed_column (coverageProcessed) produces it on demand. */
 int dfb_preprocess(dfb_ctx* ctx, dfb_cov* cov, double scalefac, const int32_t* group_of_sample,
                    int n_groups);
 int dfb_cov_get_processed_column(const dfb_cov* cov, int sample, double* out); /* log2 column */
