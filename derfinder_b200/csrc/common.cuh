@@ -122,6 +122,7 @@ struct dfb_ctx {
     size_t k2_gflag_cap = 0;       // bytes
     bool k2_clean = false;         // both buffers are all zero
     int opt_mask_cache = 1;
+    int opt_wire16 = 1;          // short-run integer Rle columns cross PCIe as 16-bit values / lengths (see upload_rle)
     int opt_filter_events = 1;   // filterData mask of integer coverage from run events (0: expansion kernel)
     double null_density = 0;     // exceedance values per (base, permutation) seen by the last null scan (0 = unknown)
     double opt_scratch_gb = 24;  // upper bound for per-call scratch (mask + exceedance values)
@@ -288,6 +289,8 @@ int bg_download_wait(dfb_ctx* ctx);
 int h2d_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);
 // H2D of `count` host segments packed back to back at dst (through the pinned ring); synchronises.
 int h2d_gather(dfb_ctx* ctx, void* dst, const void* const* srcs, const size_t* bytes, int count, bool sync = true);
+int h2d_gather_narrow16(dfb_ctx* ctx, uint16_t* dst, const int32_t* const* srcs, const int64_t* counts, int count, bool sync,
+                        bool* overflow);
 // D2H of `count` elements of `elem` bytes laid out in B consecutive blocks (block b = elements
 // [pre[b], pre[b+1])) into the reference's duplicated layout: block b is written twice, back to
 // back, at dst element 2*pre[b] (R/calculatePvalues.R:346-354).

@@ -731,8 +731,21 @@ struct RleUpload {
     int64_t total_runs = 0;
 };
 
+// uint16 -> 32-bit columns on the device (the wire format of short-run integer coverage, see upload_rle)
+__global__ void __launch_bounds__(256) widen16_kernel(const uint16_t* __restrict__ v16, const uint16_t* __restrict__ l16,
+                                                      int64_t count, int32_t* __restrict__ v32, uint32_t* __restrict__ l32) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x) {
+        v32[i] = (int32_t)v16[i];
+        l32[i] = (uint32_t)l16[i];
+    }
+}
+
+// try16: integer columns whose values and run lengths all fit 16 bits (filtered coverage: runs of tens of bases,
+// counts in the hundreds) cross PCIe as uint16 -- the narrowing rides on the copy into the pinned ring that the host
+// pool makes anyway -- and are widened again on the device: half the H2D bytes of the end-to-end pass.  A value
+// that does not fit abandons the attempt and the columns travel as they are.
 static int upload_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, const int32_t* const* lengths,
-                      const int64_t* nruns, int64_t len, RleUpload* up) {
+                      const int64_t* nruns, int64_t len, RleUpload* up, bool try16 = false) {
     DFB_REQUIRE(n > 0 && values && lengths && nruns, "Rle input: NULL argument");
     DFB_REQUIRE(dtype == DFB_I32 || dtype == DFB_F64, "Rle input: unknown dtype %d", dtype);
     const size_t es = dtype == DFB_I32 ? 4 : 8;
@@ -746,7 +759,27 @@ static int upload_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values,
     DFB_TRY(up->lengths.alloc(ctx, (size_t)std::max<int64_t>(up->total_runs, 1)));
     DFB_TRY(up->cum.alloc(ctx, (size_t)up->total_runs + 1));
     DFB_TRY(up->run_off.alloc(ctx, (size_t)n + 1));
-    {
+    bool sent = false;
+    if (try16 && dtype == DFB_I32 && ctx->opt_wire16 && up->total_runs >= (1 << 16)) {
+        DevBuf<uint16_t> v16, l16;
+        DFB_TRY(v16.alloc(ctx, (size_t)up->total_runs));
+        DFB_TRY(l16.alloc(ctx, (size_t)up->total_runs));
+        std::vector<const int32_t*> s32((size_t)n);
+        bool over = false;
+        for (int s = 0; s < n; ++s) s32[(size_t)s] = reinterpret_cast<const int32_t*>(values[s]);
+        DFB_TRY(h2d_gather_narrow16(ctx, v16.p, s32.data(), nruns, n, false, &over));
+        if (!over) {
+            for (int s = 0; s < n; ++s) s32[(size_t)s] = lengths[s];
+            DFB_TRY(h2d_gather_narrow16(ctx, l16.p, s32.data(), nruns, n, true, &over));
+        }
+        if (!over) {
+            KTimer t(ctx, DFB_K_PREP);
+            widen16_kernel<<<grid_for(up->total_runs, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(
+                v16.p, l16.p, up->total_runs, reinterpret_cast<int32_t*>(up->values.p), up->lengths.p);
+            sent = true;
+        }
+    }
+    if (!sent) {
         // all columns travel packed through the pinned ring: two streams of DMAs instead of 2n
         // driver-staged pageable copies
         std::vector<const void*> srcs((size_t)n);
@@ -1377,7 +1410,7 @@ int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, 
     *out = nullptr;
     DFB_REQUIRE(pos_len != nullptr, "'coverageInfo$position' is NULL when it shouldn't be.");
     RleUpload up;
-    DFB_TRY(upload_rle(ctx, n, dtype, values, lengths, nruns, N, &up));
+    DFB_TRY(upload_rle(ctx, n, dtype, values, lengths, nruns, N, &up, /*try16=*/true));
     dfb_cov* c = new dfb_cov();
     c->ctx = ctx;
     c->n = n;

@@ -6,6 +6,7 @@
 #include <stdlib.h>
 
 #include <algorithm>
+#include <atomic>
 
 #include "common.cuh"
 
@@ -416,6 +417,91 @@ int h2d_gather(dfb_ctx* ctx, void* dst, const void* const* srcs, const size_t* b
     return DFB_OK;
 }
 
+// int32 -> uint16 with the conversion riding on the copy into pinned memory.  Returns true when a value does
+// not fit (negative or > 65535).
+static bool narrow16_stream(uint16_t* dst, const int32_t* src, size_t n) {
+    uint32_t bad = 0;
+    size_t i = 0;
+    for (; i < n && ((uintptr_t)(dst + i) & 15); ++i) {
+        bad |= (uint32_t)src[i] & 0xffff0000u;
+        dst[i] = (uint16_t)src[i];
+    }
+    __m128i acc = _mm_setzero_si128();
+    const __m128i bias = _mm_set1_epi32(32768), flip = _mm_set1_epi16((short)0x8000), hi = _mm_set1_epi32((int)0xffff0000u);
+    for (; i + 16 <= n; i += 16) {
+        const __m128i a = _mm_loadu_si128((const __m128i*)(src + i));
+        const __m128i b = _mm_loadu_si128((const __m128i*)(src + i + 4));
+        const __m128i c = _mm_loadu_si128((const __m128i*)(src + i + 8));
+        const __m128i d = _mm_loadu_si128((const __m128i*)(src + i + 12));
+        acc = _mm_or_si128(acc, _mm_and_si128(_mm_or_si128(_mm_or_si128(a, b), _mm_or_si128(c, d)), hi));
+        // signed saturating pack of (x - 32768), then flip the sign bit: exact for 0 <= x <= 65535
+        const __m128i p0 = _mm_xor_si128(_mm_packs_epi32(_mm_sub_epi32(a, bias), _mm_sub_epi32(b, bias)), flip);
+        const __m128i p1 = _mm_xor_si128(_mm_packs_epi32(_mm_sub_epi32(c, bias), _mm_sub_epi32(d, bias)), flip);
+        _mm_stream_si128((__m128i*)(dst + i), p0);
+        _mm_stream_si128((__m128i*)(dst + i + 8), p1);
+    }
+    for (; i < n; ++i) {
+        bad |= (uint32_t)src[i] & 0xffff0000u;
+        dst[i] = (uint16_t)src[i];
+    }
+    _mm_sfence();
+    alignas(16) uint32_t lanes[4];
+    _mm_store_si128((__m128i*)lanes, acc);
+    return (bad | lanes[0] | lanes[1] | lanes[2] | lanes[3]) != 0;
+}
+
+// h2d_gather for int32 columns that travel as uint16 (half the PCIe bytes): `counts[i]` elements of srcs[i] are
+// narrowed into the pinned ring by the copy pool and DMAed to dst (uint16, columns back to back).  *overflow is
+// set -- and the transfer abandoned -- as soon as a value does not fit; the caller then falls back to 32 bits.
+int h2d_gather_narrow16(dfb_ctx* ctx, uint16_t* dst, const int32_t* const* srcs, const int64_t* counts, int count, bool sync,
+                        bool* overflow) {
+    *overflow = false;
+    DFB_TRY(ensure_staging(ctx));
+    constexpr size_t GS = SUB_BYTES, NG = NSUB;
+    DFB_TRY(ensure_substage_events(ctx));
+    char* pin = (char*)ctx->pinned;
+    struct Piece { uint16_t* d; const int32_t* s; size_t n; };
+    size_t& chunk = ctx->gather_chunk;
+    size_t fill = 0, dev_off = 0;  // bytes
+    std::vector<Piece> pieces;
+    bool waited = false;
+    std::atomic<int> bad{0};
+    auto flush = [&]() -> int {
+        if (fill == 0) return DFB_OK;
+        ctx->pool->parallel_for((int)pieces.size(), [&](int i) {
+            if (narrow16_stream(pieces[i].d, pieces[i].s, pieces[i].n)) bad.store(1, std::memory_order_relaxed);
+        });
+        DFB_CUDA(cudaMemcpyAsync((char*)dst + dev_off, pin + (chunk % NG) * GS, fill, cudaMemcpyHostToDevice, ctx->stream));
+        DFB_CUDA(cudaEventRecord(ctx->gather_ev[chunk % NG], ctx->stream));
+        dev_off += fill;
+        fill = 0;
+        pieces.clear();
+        ++chunk;
+        waited = false;
+        return DFB_OK;
+    };
+    for (int i = 0; i < count && !bad.load(std::memory_order_relaxed); ++i) {
+        size_t done = 0;  // elements
+        const size_t total = (size_t)counts[i];
+        while (done < total) {
+            if (!waited && chunk >= NG) DFB_CUDA(cudaEventSynchronize(ctx->gather_ev[chunk % NG]));
+            waited = true;
+            const size_t room = (GS - fill) / 2;
+            const size_t take = std::min(room, total - done);
+            uint16_t* base = reinterpret_cast<uint16_t*>(pin + (chunk % NG) * GS + fill);
+            for (size_t o = 0; o < take; o += (64u << 10))
+                pieces.push_back({base + o, srcs[i] + done + o, std::min<size_t>(64u << 10, take - o)});
+            fill += take * 2;
+            done += take;
+            if (fill + 2 > GS) DFB_TRY(flush());
+        }
+    }
+    DFB_TRY(flush());
+    *overflow = bad.load() != 0;
+    if (sync || *overflow) DFB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return DFB_OK;
+}
+
 int h2d_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes) {
     if (bytes < (1u << 20) || is_pinned_host(src)) {
         DFB_TRY(h2d(ctx, dst, src, bytes));
@@ -767,6 +853,7 @@ int dfb_set_option(dfb_ctx* c, const char* key, double value) {
     else if (!strcmp(key, "lazy_y")) c->opt_lazy_y = value != 0;
     else if (!strcmp(key, "mask_cache")) c->opt_mask_cache = value != 0;
     else if (!strcmp(key, "filter_events")) c->opt_filter_events = value != 0;
+    else if (!strcmp(key, "wire16")) c->opt_wire16 = value != 0;
     else if (!strcmp(key, "dbg")) c->opt_dbg = (int)value;
     else if (!strcmp(key, "tmem_stages")) c->opt_tmem_stages = (int)value;
     else if (!strcmp(key, "k2_waves")) c->opt_k2_waves = (int)value;

@@ -590,3 +590,52 @@ def test_filter_events_equals_expansion(dfb, flt, cutoff, n, length, mean_run):
             assert np.array_equal(f["meanCoverage"], o.meanCoverage), ev
         finally:
             e.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# 16-bit wire format of integer Rle columns (dfb_cov_from_rle): fits / value overflow / length overflow
+
+
+@pytest.mark.parametrize("case", ["fits", "value_overflow", "length_overflow", "negative", "off"])
+def test_rle_upload_wire16(dfb, case):
+    from derfinder_b200.api import _upload_filtered
+    rng = np.random.default_rng(2718)
+    n, runs = 5, 40000  # 200 000 runs in total: above the threshold of the 16-bit path
+    cols, dense = [], []
+    for s in range(n):
+        lens = rng.integers(1, 40, size=runs).astype(np.int64)
+        vals = rng.integers(0, 3000, size=runs).astype(np.int32)
+        vals[1:][vals[1:] == vals[:-1]] += 1  # proper Rle: neighbours differ
+        cols.append([vals, lens])
+    N = int(min(l.sum() for _, l in cols))
+    for c in cols:  # trim every column to the common length N
+        v, l = c
+        cs = np.cumsum(l)
+        k = int(np.searchsorted(cs, N))
+        l = l[:k + 1].copy()
+        l[k] -= cs[k] - N
+        c[0], c[1] = v[:k + 1].copy(), l
+    if case == "value_overflow":
+        cols[3][0][1234] = 70000
+    elif case == "negative":
+        cols[2][0][77] = -5
+    elif case == "length_overflow":  # one long run: shorten the column elsewhere to keep the length
+        v, l = cols[1]
+        extra = 70000 - int(l[500])
+        l[500] = 70000
+        cs = np.cumsum(l)
+        k = int(np.searchsorted(cs, N))
+        cols[1][0], l2 = v[:k + 1].copy(), l[:k + 1].copy()
+        l2[k] -= cs[k] - N
+        cols[1][1] = l2
+        assert extra > 0 and l2.sum() == N
+    position = (np.array([True]), np.array([N]))
+    e = dfb.Engine(0)
+    try:
+        if case == "off":
+            e.set_option("wire16", 0)
+        cov = _upload_filtered(e, [(v, l.astype(np.int32)) for v, l in cols], position)
+        for s in range(n):
+            assert np.array_equal(cov.column(s), np.repeat(cols[s][0], cols[s][1])), (case, s)
+    finally:
+        e.close()
