@@ -8,6 +8,7 @@
 #include <math.h>
 
 #include <algorithm>
+#include <memory>
 #include <type_traits>
 
 #include "data.cuh"
@@ -652,8 +653,12 @@ __global__ void __launch_bounds__(K1_THREADS) expand_rle_kernel(RleDev R, int64_
 // at the chr1 shape) made that kernel latency-bound at 1.3 TB/s.
 template <typename V, int THREADS>
 __global__ void __launch_bounds__(THREADS) expand_rle_tiles_kernel(RleDev R, int64_t tiles, const int64_t* __restrict__ tab,
-                                                                   int64_t ld, V* __restrict__ out) {
+                                                                   int64_t ld, V* __restrict__ out,
+                                                                   const int64_t* __restrict__ bad) {
     constexpr int TILE = THREADS * K1_PER;
+    // ragged or corrupt columns (flagged by validate_rle_kernel earlier in the stream) are not expanded: the tile
+    // logic relies on positive run lengths that sum to R.len; the caller reports the error when it synchronises
+    if (bad && (bad[0] >= 0 || bad[1] >= 0)) return;
     __shared__ __align__(16) int head_s[TILE];
     __shared__ V val_s[TILE];
     __shared__ int wmax_s[THREADS / 32];
@@ -744,12 +749,18 @@ __global__ void __launch_bounds__(256) widen16_kernel(const uint16_t* __restrict
 // counts in the hundreds) cross PCIe as uint16 -- the narrowing rides on the copy into the pinned ring that the host
 // pool makes anyway -- and are widened again on the device: half the H2D bytes of the end-to-end pass.  A value
 // that does not fit abandons the attempt and the columns travel as they are.
-static int upload_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, const int32_t* const* lengths,
-                      const int64_t* nruns, int64_t len, RleUpload* up, bool try16 = false) {
+// No host synchronisation in here (unless a 16-bit attempt overflows): the device validation writes the first
+// offending column into bad_dev[0] (non-positive run length) / bad_dev[1] (wrong total length), both preset to -1
+// by the caller, who reads them back when it synchronises anyway.
+static int upload_rle_async(dfb_ctx* ctx, int n, int dtype, const void* const* values, const int32_t* const* lengths,
+                            const int64_t* nruns, int64_t len, RleUpload* up, bool try16, int64_t* bad_dev) {
     DFB_REQUIRE(n > 0 && values && lengths && nruns, "Rle input: NULL argument");
     DFB_REQUIRE(dtype == DFB_I32 || dtype == DFB_F64, "Rle input: unknown dtype %d", dtype);
     const size_t es = dtype == DFB_I32 ? 4 : 8;
-    std::vector<int64_t> off((size_t)n + 1, 0);
+    // run offsets in pinned memory: a pageable source would make the small copy wait for the stream
+    int64_t* off = (int64_t*)arena_alloc(ctx, ((size_t)n + 1) * sizeof(int64_t));
+    DFB_REQUIRE(off != nullptr, "pinned arena allocation failed");
+    off[0] = 0;
     for (int s = 0; s < n; ++s) {
         DFB_REQUIRE(nruns[s] > 0 || len == 0, "Rle column %d is empty", s + 1);
         off[(size_t)s + 1] = off[(size_t)s] + nruns[s];
@@ -770,7 +781,7 @@ static int upload_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values,
         DFB_TRY(h2d_gather_narrow16(ctx, v16.p, s32.data(), nruns, n, false, &over));
         if (!over) {
             for (int s = 0; s < n; ++s) s32[(size_t)s] = lengths[s];
-            DFB_TRY(h2d_gather_narrow16(ctx, l16.p, s32.data(), nruns, n, true, &over));
+            DFB_TRY(h2d_gather_narrow16(ctx, l16.p, s32.data(), nruns, n, false, &over));
         }
         if (!over) {
             KTimer t(ctx, DFB_K_PREP);
@@ -793,26 +804,37 @@ static int upload_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values,
             srcs[(size_t)s] = lengths[s];
             nb[(size_t)s] = (size_t)nruns[s] * sizeof(int32_t);
         }
-        DFB_TRY(h2d_gather(ctx, up->lengths.p, srcs.data(), nb.data(), n));
+        DFB_TRY(h2d_gather(ctx, up->lengths.p, srcs.data(), nb.data(), n, /*sync=*/false));
     }
-    DFB_TRY(h2d(ctx, up->run_off.p, off.data(), off.size() * sizeof(int64_t)));
-    DFB_CUDA(cudaStreamSynchronize(ctx->stream));  // `off` is a local
+    DFB_CUDA(cudaMemcpyAsync(up->run_off.p, off, ((size_t)n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     DFB_TRY(exclusive_scan_u32(ctx, up->lengths.p, up->cum.p, up->total_runs, up->cum.p + up->total_runs, DFB_K_PREP));
     // validation on the device (catches ragged DataFrames like R would, without an O(#runs) host pass):
     // every run length positive, every column sums to `len`
-    DevBuf<int64_t> bad;
-    DFB_TRY(bad.alloc(ctx, 2));
-    DFB_CUDA(cudaMemsetAsync(bad.p, 0xff, 2 * sizeof(int64_t), ctx->stream));  // -1 = nothing wrong
     {
         KTimer t(ctx, DFB_K_PREP);
         validate_rle_kernel<<<grid_for(up->total_runs + n, 256, ctx->sm_count, 8), 256, 0, ctx->stream>>>(
-            reinterpret_cast<const int32_t*>(up->lengths.p), up->cum.p, up->run_off.p, n, up->total_runs, len, bad.p);
+            reinterpret_cast<const int32_t*>(up->lengths.p), up->cum.p, up->run_off.p, n, up->total_runs, len, bad_dev);
     }
-    int64_t hbad[2] = {-1, -1};
-    DFB_TRY(d2h(ctx, hbad, bad.p, sizeof hbad));
-    DFB_REQUIRE(hbad[0] < 0, "Rle column %d has a non-positive run length", (int)hbad[0] + 1);
-    DFB_REQUIRE(hbad[1] < 0, "Rle column %d does not have the expected length %lld", (int)hbad[1] + 1, (long long)len);
+    DFB_CUDA(cudaGetLastError());
     return DFB_OK;
+}
+
+static int check_rle_flags(const int64_t* hbad, int first_column, int64_t len) {
+    DFB_REQUIRE(hbad[0] < 0, "Rle column %d has a non-positive run length", first_column + (int)hbad[0] + 1);
+    DFB_REQUIRE(hbad[1] < 0, "Rle column %d does not have the expected length %lld", first_column + (int)hbad[1] + 1,
+                (long long)len);
+    return DFB_OK;
+}
+
+static int upload_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, const int32_t* const* lengths,
+                      const int64_t* nruns, int64_t len, RleUpload* up, bool try16 = false) {
+    DevBuf<int64_t> bad;
+    DFB_TRY(bad.alloc(ctx, 2));
+    DFB_CUDA(cudaMemsetAsync(bad.p, 0xff, 2 * sizeof(int64_t), ctx->stream));  // -1 = nothing wrong
+    DFB_TRY(upload_rle_async(ctx, n, dtype, values, lengths, nruns, len, up, try16, bad.p));
+    int64_t hbad[2] = {-1, -1};
+    DFB_TRY(d2h(ctx, hbad, bad.p, sizeof hbad));  // synchronises
+    return check_rle_flags(hbad, 0, len);
 }
 
 static int alloc_matrix(dfb_cov* c) {
@@ -1409,8 +1431,6 @@ int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, 
     DFB_REQUIRE(ctx && out, "dfb_cov_from_rle: NULL argument");
     *out = nullptr;
     DFB_REQUIRE(pos_len != nullptr, "'coverageInfo$position' is NULL when it shouldn't be.");
-    RleUpload up;
-    DFB_TRY(upload_rle(ctx, n, dtype, values, lengths, nruns, N, &up, /*try16=*/true));
     dfb_cov* c = new dfb_cov();
     c->ctx = ctx;
     c->n = n;
@@ -1421,50 +1441,74 @@ int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, 
         delete c;
         return rc;
     }
-    if (N > 0) {
-        RleDev R;
-        R.values = up.values.p;
-        R.cum = up.cum.p;
-        R.run_off = up.run_off.p;
-        R.n = n;
-        R.len = N;
-        // 1024-position tiles on 128 threads: sixteen blocks per SM keep twice the tiles in flight (the kernel is
-        // bound by the latency of a tile's dependent steps, not by bandwidth)
-        constexpr int XT = 128, XTILE = XT * K1_PER;
-        const int64_t tiles = ceil_div(N, XTILE);
-        const dim3 grid((unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 16), (unsigned)n);
+    // The samples travel in groups: upload (host pool packs / narrows into the pinned ring, DMA), prefix sums,
+    // validation, run table and expansion of a group are queued without a host synchronisation, so the device
+    // expands group g while the host is still packing group g + 1 (the upload is bound by the host pass).
+    int64_t total_runs = 0;
+    for (int s = 0; s < n; ++s) total_runs += nruns[s];
+    const int G = (N > 0 && n >= 8 && total_runs >= (1 << 20)) ? 4 : 1;
+    struct Group {
+        RleUpload up;
         DevBuf<int64_t> tab;  // run holding the first position of every (tile, sample)
-        rc = tab.alloc(ctx, (size_t)tiles * n);
-        if (rc < 0) {
-            delete c;
-            return rc;
-        }
-        KTimer t(ctx, DFB_K_PREP, 2);
-        tile_runs_kernel<<<grid_for(tiles * n, 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(R, tiles, tab.p, XTILE);
-        if (dtype == DFB_I32)
-            expand_rle_tiles_kernel<int32_t, XT><<<grid, XT, 0, ctx->stream>>>(R, tiles, tab.p, c->ld, c->xi.p);
-        else
-            expand_rle_tiles_kernel<double, XT><<<grid, XT, 0, ctx->stream>>>(R, tiles, tab.p, c->ld, c->xd.p);
-    }
-    cudaError_t e = cudaGetLastError();
-    // the position index is built while the expansion runs (host run loops + two small uploads)
-    if (e == cudaSuccess) {
-        rc = c->pos.build(ctx, pos_len, pos_nruns, pos_first);
-        if (rc >= 0 && c->pos.N != N) {
-            set_error("nrow(coverage) = %lld does not match sum(position) = %lld", (long long)N, (long long)c->pos.N);
-            rc = DFB_EINVAL;
-        }
-        if (rc < 0) {
-            cudaStreamSynchronize(ctx->stream);
-            delete c;
-            return rc;
-        }
-    }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // `up` buffers die with this frame
-    if (e != cudaSuccess) {
-        set_error("Rle expansion: %s", cudaGetErrorString(e));
+        int s0 = 0, ns = 0;
+    };
+    std::vector<std::unique_ptr<Group>> groups;
+    DevBuf<int64_t> bad;
+    auto fail = [&](int code) -> int {
+        cudaStreamSynchronize(ctx->stream);  // queued kernels read the groups' buffers
         delete c;
-        return DFB_ECUDA;
+        return code;
+    };
+    rc = bad.alloc(ctx, (size_t)2 * G);
+    if (rc < 0) return fail(rc);
+    if (cudaMemsetAsync(bad.p, 0xff, (size_t)2 * G * sizeof(int64_t), ctx->stream) != cudaSuccess) return fail(DFB_ECUDA);
+    // 1024-position tiles on 128 threads, 16 blocks per SM
+    constexpr int XT = 128, XTILE = XT * K1_PER;
+    const int64_t tiles = ceil_div(N, XTILE);
+    for (int g = 0; g < G; ++g) {
+        groups.emplace_back(new Group());
+        Group& gr = *groups.back();
+        gr.s0 = (int)((int64_t)n * g / G);
+        gr.ns = (int)((int64_t)n * (g + 1) / G) - gr.s0;
+        rc = upload_rle_async(ctx, gr.ns, dtype, values + gr.s0, lengths + gr.s0, nruns + gr.s0, N, &gr.up, /*try16=*/true,
+                              bad.p + 2 * g);
+        if (rc < 0) return fail(rc);
+        if (N == 0) continue;
+        RleDev R;
+        R.values = gr.up.values.p;
+        R.cum = gr.up.cum.p;
+        R.run_off = gr.up.run_off.p;
+        R.n = gr.ns;
+        R.len = N;
+        rc = gr.tab.alloc(ctx, (size_t)tiles * gr.ns);
+        if (rc < 0) return fail(rc);
+        const dim3 grid((unsigned)std::min<int64_t>(tiles, (int64_t)ctx->sm_count * 16), (unsigned)gr.ns);
+        KTimer t(ctx, DFB_K_PREP, 2);
+        tile_runs_kernel<<<grid_for(tiles * gr.ns, 256, ctx->sm_count, 16), 256, 0, ctx->stream>>>(R, tiles, gr.tab.p, XTILE);
+        if (dtype == DFB_I32)
+            expand_rle_tiles_kernel<int32_t, XT><<<grid, XT, 0, ctx->stream>>>(R, tiles, gr.tab.p, c->ld,
+                                                                               c->xi.p + (size_t)gr.s0 * c->ld, bad.p + 2 * g);
+        else
+            expand_rle_tiles_kernel<double, XT><<<grid, XT, 0, ctx->stream>>>(R, tiles, gr.tab.p, c->ld,
+                                                                              c->xd.p + (size_t)gr.s0 * c->ld, bad.p + 2 * g);
+    }
+    if (cudaGetLastError() != cudaSuccess) {
+        set_error("Rle expansion: launch failed");
+        return fail(DFB_ECUDA);
+    }
+    // the position index is built while the expansion runs (host run loops + two small uploads)
+    rc = c->pos.build(ctx, pos_len, pos_nruns, pos_first);
+    if (rc >= 0 && c->pos.N != N) {
+        set_error("nrow(coverage) = %lld does not match sum(position) = %lld", (long long)N, (long long)c->pos.N);
+        rc = DFB_EINVAL;
+    }
+    if (rc < 0) return fail(rc);
+    std::vector<int64_t> hbad((size_t)2 * G, -1);
+    rc = d2h(ctx, hbad.data(), bad.p, hbad.size() * sizeof(int64_t));  // synchronises: the groups' buffers die with this frame
+    if (rc < 0) return fail(rc);
+    for (int g = 0; g < G; ++g) {
+        rc = check_rle_flags(hbad.data() + 2 * g, groups[(size_t)g]->s0, N);
+        if (rc < 0) return fail(rc);
     }
     *out = c;
     return DFB_OK;
