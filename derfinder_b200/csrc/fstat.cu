@@ -489,7 +489,7 @@ static void fill_common(FstatParams& P, const dfb_cov* cov, const ModelBasis& mb
 // (SRCI: values go through the log2 table, whose head sits in shared memory).  Same arithmetic contract as the
 // tiled kernel.
 template <int PC, bool EMIT, bool SRCI>
-__global__ void __launch_bounds__(256, 3) fstat_observed_kernel(const FstatParams P) {
+__global__ void __launch_bounds__(256, 2) fstat_observed_kernel(const FstatParams P) {
     constexpr int QS = (PC + 1) & ~1;  // row stride of a column chunk in shared memory: 16-byte aligned rows
     extern __shared__ __align__(16) double Qs_obs[];  // [chunks][n][QS], then the table head [LUT_SMEM] (SRCI)
     const int n = P.n;
