@@ -122,6 +122,7 @@ struct dfb_ctx {
     size_t k2_gflag_cap = 0;       // bytes
     bool k2_clean = false;         // both buffers are all zero
     int opt_mask_cache = 1;
+    int opt_poison = 0;          // DFB_POISON=1: fill every fresh device allocation with 0xff (uninitialised-read hunt)
     int opt_wire16 = 1;          // short-run integer Rle columns cross PCIe as 16-bit values / lengths (see upload_rle)
     int opt_filter_events = 1;   // filterData mask of integer coverage from run events (0: expansion kernel)
     double null_density = 0;     // exceedance values per (base, permutation) seen by the last null scan (0 = unknown)
@@ -252,6 +253,9 @@ struct DevBuf {
             cudaGetLastError();
             return DFB_ENOMEM;
         }
+        // developer check (DFB_POISON=1): fresh allocations are filled with 0xff (NaN / -1 / huge) so that a read
+        // of memory nobody wrote shows up in the parity tests instead of hiding behind recycled pool contents
+        if (ctx->opt_poison) cudaMemsetAsync(p, 0xff, count * sizeof(T), s);
         return DFB_OK;
     }
     int zero() {

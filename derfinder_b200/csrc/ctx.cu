@@ -734,6 +734,7 @@ int dfb_create(int device, void* stream, dfb_ctx** out) {
         }
     }
     cudaGetLastError();
+    if (const char* e = getenv("DFB_POISON")) c->opt_poison = atoi(e) != 0;
     *out = c;
     return DFB_OK;
 }
