@@ -628,10 +628,58 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_kernel(const TIn* __re
     }
 }
 
+// Whole scan by ONE block (small inputs: region tables, tile counts of a short chromosome): one launch and no
+// scratch instead of reduce + scan-of-sums + tile scan.
+template <typename TIn>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_one_block_kernel(const TIn* __restrict__ in, int64_t n,
+                                                                      int64_t* __restrict__ out, int64_t* __restrict__ total) {
+    __shared__ int64_t wsum[SCAN_THREADS / 32];
+    __shared__ int64_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < n; base += SCAN_TILE) {
+        int64_t v[SCAN_ITEMS];
+        int64_t tsum = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            const int64_t idx = base + (int64_t)threadIdx.x * SCAN_ITEMS + i;
+            v[i] = idx < n ? (int64_t)in[idx] : 0;
+            tsum += v[i];
+        }
+        int64_t inc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((threadIdx.x & 31) >= o) inc += t;
+        }
+        if ((threadIdx.x & 31) == 31) wsum[threadIdx.x >> 5] = inc;
+        __syncthreads();
+        int64_t wprefix = 0;
+        for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) wprefix += wsum[w];
+        int64_t excl = carry_s + wprefix + inc - tsum;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; ++i) {
+            const int64_t idx = base + (int64_t)threadIdx.x * SCAN_ITEMS + i;
+            if (idx < n) out[idx] = excl;
+            excl += v[i];
+        }
+        __syncthreads();
+        if (threadIdx.x == SCAN_THREADS - 1) carry_s = excl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0 && total) *total = carry_s;
+}
+
 template <typename TIn>
 static int scan_impl(dfb_ctx* ctx, const TIn* in, int64_t* out, int64_t n, int64_t* total_dev, int fam) {
     if (n <= 0) {
         if (total_dev) DFB_CUDA(cudaMemsetAsync(total_dev, 0, sizeof(int64_t), ctx->stream));
+        return DFB_OK;
+    }
+    if (n <= (int64_t)SCAN_TILE * 16 && (const void*)in != (const void*)out) {
+        KTimer t(ctx, fam, 1);
+        scan_one_block_kernel<TIn><<<1, SCAN_THREADS, 0, ctx->stream>>>(in, n, out, total_dev);
+        DFB_CUDA(cudaGetLastError());
         return DFB_OK;
     }
     int64_t tiles = ceil_div(n, SCAN_TILE);
