@@ -293,6 +293,7 @@ int bg_download_wait(dfb_ctx* ctx);
 int h2d_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);
 // H2D of `count` host segments packed back to back at dst (through the pinned ring); synchronises.
 int h2d_gather(dfb_ctx* ctx, void* dst, const void* const* srcs, const size_t* bytes, int count, bool sync = true);
+int copy_threads(dfb_ctx* ctx);
 int h2d_gather_narrow16(dfb_ctx* ctx, uint16_t* dst, const int32_t* const* srcs, const int64_t* counts, int count, bool sync,
                         bool* overflow);
 // D2H of `count` elements of `elem` bytes laid out in B consecutive blocks (block b = elements

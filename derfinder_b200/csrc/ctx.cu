@@ -169,6 +169,12 @@ static int ensure_staging(dfb_ctx* ctx) {
     return DFB_OK;
 }
 
+// threads of the host copy pool (created on first use)
+int copy_threads(dfb_ctx* ctx) {
+    if (ensure_staging(ctx) < 0 || !ctx->pool) return 1;
+    return ctx->pool->size();
+}
+
 constexpr size_t SUB_BYTES = 2u << 20;                       // sub-stage of the ring
 constexpr size_t NSUB = NSTAGE * STAGE_BYTES / SUB_BYTES;      // sub-stages in the ring
 static int ensure_substage_events(dfb_ctx* ctx) {
