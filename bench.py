@@ -360,6 +360,19 @@ class Step:
             starts = np.concatenate(([0], brk))
             vals.append(np.ascontiguousarray(x[starts], dtype=np.int32))
             lens.append(np.diff(np.concatenate((starts, [x.size]))).astype(np.int32))
+        # the step's inputs sit in page-locked host memory (the bench contract): the library DMAs such columns
+        # where they lie; pageable columns (an R session's vectors) go through its pinned staging ring instead
+        # (--e2e-pageable measures that path)
+        if not getattr(self, "pageable", False):
+            keep = []
+            for lst in (vals, lens):
+                for i, a in enumerate(lst):
+                    t = self.torch.empty(a.shape, dtype=self.torch.int32, pin_memory=True)
+                    v = t.numpy()
+                    v[...] = a
+                    keep.append(t)
+                    lst[i] = v
+            self._pinned_keep = keep
         vp = (C.c_void_p * self.n)(*[v.ctypes.data for v in vals])
         lp = (C.c_void_p * self.n)(*[l.ctypes.data for l in lens])
         nr = np.asarray([len(v) for v in vals], dtype=np.int64)
@@ -483,6 +496,9 @@ def main():
     ap.add_argument("--no-e2e", action="store_true", help="developer: skip the end-to-end pass (the line has no e2e key)")
     ap.add_argument("--e2e-input", default="rle", choices=["rle", "dense"],
                     help="host coverage format of the end-to-end pass: Rle columns (the reference's type) or dense")
+    ap.add_argument("--e2e-pageable", action="store_true",
+                    help="end-to-end pass: Rle columns in pageable host memory (the library's pinned staging ring) instead of "
+                         "page-locked memory (direct DMA)")
     ap.add_argument("--e2e-sync-f", action="store_true",
                     help="end-to-end pass: blocking dfb_fstats download instead of dfb_fstats_begin / dfb_fstats_wait")
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (developer knob)")
@@ -559,6 +575,7 @@ def main():
         mine = ["chr"]
     step = chroms[0]
     step.sync_f = args.e2e_sync_f
+    step.pageable = args.e2e_pageable
     pooled = world > 1 or args.force_pool or genome
 
     timed_pass = None  # per-step events around this rank's own chromosome passes (timed region only)

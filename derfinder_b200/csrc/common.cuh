@@ -122,6 +122,7 @@ struct dfb_ctx {
     size_t k2_gflag_cap = 0;       // bytes
     bool k2_clean = false;         // both buffers are all zero
     int opt_mask_cache = 1;
+    int opt_pinned_direct = 1;   // Rle columns in page-locked caller memory are DMAed in place (dfb_cov_from_rle)
     int opt_poison = 0;          // DFB_POISON=1: fill every fresh device allocation with 0xff (uninitialised-read hunt)
     int opt_wire16 = 1;          // short-run integer Rle columns cross PCIe as 16-bit values / lengths (see upload_rle)
     int opt_filter_events = 1;   // filterData mask of integer coverage from run events (0: expansion kernel)
@@ -293,7 +294,9 @@ int bg_download_wait(dfb_ctx* ctx);
 int h2d_big(dfb_ctx* ctx, void* dst, const void* src, size_t bytes);
 // H2D of `count` host segments packed back to back at dst (through the pinned ring); synchronises.
 int h2d_gather(dfb_ctx* ctx, void* dst, const void* const* srcs, const size_t* bytes, int count, bool sync = true);
+int ensure_aux_stream(dfb_ctx* ctx);
 int copy_threads(dfb_ctx* ctx);
+bool host_is_pinned(const void* p);  // page-locked (cudaHostAlloc / cudaHostRegister) host memory
 int h2d_gather_narrow16(dfb_ctx* ctx, uint16_t* dst, const int32_t* const* srcs, const int64_t* counts, int count, bool sync,
                         bool* overflow);
 // D2H of `count` elements of `elem` bytes laid out in B consecutive blocks (block b = elements

@@ -749,11 +749,14 @@ __global__ void __launch_bounds__(256) widen16_kernel(const uint16_t* __restrict
 // counts in the hundreds) cross PCIe as uint16 -- the narrowing rides on the copy into the pinned ring that the host
 // pool makes anyway -- and are widened again on the device: half the H2D bytes of the end-to-end pass.  A value
 // that does not fit abandons the attempt and the columns travel as they are.
-// No host synchronisation in here (unless a 16-bit attempt overflows): the device validation writes the first
-// offending column into bad_dev[0] (non-positive run length) / bad_dev[1] (wrong total length), both preset to -1
-// by the caller, who reads them back when it synchronises anyway.
-static int upload_rle_async(dfb_ctx* ctx, int n, int dtype, const void* const* values, const int32_t* const* lengths,
-                            const int64_t* nruns, int64_t len, RleUpload* up, bool try16, int64_t* bad_dev) {
+// Upload of Rle columns in three steps, none of which synchronises with the host (unless a 16-bit attempt
+// overflows): rle_alloc (device buffers + the run offsets in pinned memory), a transfer -- rle_transfer_staged
+// through the pinned ring, or direct DMAs when the caller's columns are page-locked (dfb_cov_from_rle) -- and
+// rle_finish (prefix sums + validation).  The validation writes the first offending column into bad_dev[0]
+// (non-positive run length) / bad_dev[1] (wrong total length), both preset to -1 by the caller, who reads them back
+// when it synchronises anyway.
+static int rle_alloc(dfb_ctx* ctx, int n, int dtype, const void* const* values, const int32_t* const* lengths,
+                     const int64_t* nruns, int64_t len, RleUpload* up, int64_t** off_out) {
     DFB_REQUIRE(n > 0 && values && lengths && nruns, "Rle input: NULL argument");
     DFB_REQUIRE(dtype == DFB_I32 || dtype == DFB_F64, "Rle input: unknown dtype %d", dtype);
     const size_t es = dtype == DFB_I32 ? 4 : 8;
@@ -770,6 +773,13 @@ static int upload_rle_async(dfb_ctx* ctx, int n, int dtype, const void* const* v
     DFB_TRY(up->lengths.alloc(ctx, (size_t)std::max<int64_t>(up->total_runs, 1)));
     DFB_TRY(up->cum.alloc(ctx, (size_t)up->total_runs + 1));
     DFB_TRY(up->run_off.alloc(ctx, (size_t)n + 1));
+    *off_out = off;
+    return DFB_OK;
+}
+
+static int rle_transfer_staged(dfb_ctx* ctx, int n, int dtype, const void* const* values, const int32_t* const* lengths,
+                               const int64_t* nruns, RleUpload* up, bool try16) {
+    const size_t es = dtype == DFB_I32 ? 4 : 8;
     bool sent = false;
     // (with fewer than six copy threads -- eight ranks sharing a 16-core host -- the pass is bound by the cores, not
     // by memory or PCIe, and the pack instructions cost more than the halved stores save: measured 17.8 against
@@ -809,6 +819,23 @@ static int upload_rle_async(dfb_ctx* ctx, int n, int dtype, const void* const* v
         }
         DFB_TRY(h2d_gather(ctx, up->lengths.p, srcs.data(), nb.data(), n, /*sync=*/false));
     }
+    return DFB_OK;
+}
+
+// direct DMAs from page-locked caller memory on `dma` (no host pass at all)
+static int rle_transfer_pinned(int n, int dtype, const void* const* values, const int32_t* const* lengths,
+                               const int64_t* nruns, const int64_t* off, RleUpload* up, cudaStream_t dma) {
+    const size_t es = dtype == DFB_I32 ? 4 : 8;
+    for (int s = 0; s < n; ++s) {
+        if (nruns[s] == 0) continue;
+        DFB_CUDA(cudaMemcpyAsync(up->values.p + (size_t)off[s] * es, values[s], (size_t)nruns[s] * es, cudaMemcpyHostToDevice, dma));
+        DFB_CUDA(cudaMemcpyAsync(up->lengths.p + (size_t)off[s], lengths[s], (size_t)nruns[s] * sizeof(int32_t),
+                                 cudaMemcpyHostToDevice, dma));
+    }
+    return DFB_OK;
+}
+
+static int rle_finish(dfb_ctx* ctx, int n, int64_t len, const int64_t* off, RleUpload* up, int64_t* bad_dev) {
     DFB_CUDA(cudaMemcpyAsync(up->run_off.p, off, ((size_t)n + 1) * sizeof(int64_t), cudaMemcpyHostToDevice, ctx->stream));
     DFB_TRY(exclusive_scan_u32(ctx, up->lengths.p, up->cum.p, up->total_runs, up->cum.p + up->total_runs, DFB_K_PREP));
     // validation on the device (catches ragged DataFrames like R would, without an O(#runs) host pass):
@@ -820,6 +847,14 @@ static int upload_rle_async(dfb_ctx* ctx, int n, int dtype, const void* const* v
     }
     DFB_CUDA(cudaGetLastError());
     return DFB_OK;
+}
+
+static int upload_rle_async(dfb_ctx* ctx, int n, int dtype, const void* const* values, const int32_t* const* lengths,
+                            const int64_t* nruns, int64_t len, RleUpload* up, bool try16, int64_t* bad_dev) {
+    int64_t* off = nullptr;
+    DFB_TRY(rle_alloc(ctx, n, dtype, values, lengths, nruns, len, up, &off));
+    DFB_TRY(rle_transfer_staged(ctx, n, dtype, values, lengths, nruns, up, try16));
+    return rle_finish(ctx, n, len, off, up, bad_dev);
 }
 
 static int check_rle_flags(const int64_t* hbad, int first_column, int64_t len) {
@@ -1457,8 +1492,15 @@ int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, 
     };
     std::vector<std::unique_ptr<Group>> groups;
     DevBuf<int64_t> bad;
+    std::vector<cudaEvent_t> ev_dma;  // page-locked path: one event per group's DMAs
+    auto drop_events = [&]() {
+        for (auto e : ev_dma) cudaEventDestroy(e);
+        ev_dma.clear();
+    };
     auto fail = [&](int code) -> int {
-        cudaStreamSynchronize(ctx->stream);  // queued kernels read the groups' buffers
+        if (ctx->aux) cudaStreamSynchronize(ctx->aux);  // DMAs of the page-locked path
+        cudaStreamSynchronize(ctx->stream);              // queued kernels read the groups' buffers
+        drop_events();
         delete c;
         return code;
     };
@@ -1468,13 +1510,49 @@ int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, 
     // 1024-position tiles on 128 threads, 16 blocks per SM
     constexpr int XT = 128, XTILE = XT * K1_PER;
     const int64_t tiles = ceil_div(N, XTILE);
+    // Page-locked caller memory (cudaHostAlloc / cudaHostRegister): the columns are DMAed where they lie, on the
+    // auxiliary stream so that group g + 1 travels while group g is expanded -- no host core touches the data, which
+    // matters most when eight ranks share the host.  Pageable memory goes through the pinned ring (above).
+    bool pinned = N > 0 && total_runs >= (1 << 16) && ctx->opt_pinned_direct && ensure_aux_stream(ctx) >= 0;
+    for (int s = 0; s < n && pinned; ++s) pinned = nruns[s] == 0 || (host_is_pinned(values[s]) && host_is_pinned(lengths[s]));
+    std::vector<int64_t*> offs((size_t)G, nullptr);
     for (int g = 0; g < G; ++g) {
         groups.emplace_back(new Group());
         Group& gr = *groups.back();
         gr.s0 = (int)((int64_t)n * g / G);
         gr.ns = (int)((int64_t)n * (g + 1) / G) - gr.s0;
-        rc = upload_rle_async(ctx, gr.ns, dtype, values + gr.s0, lengths + gr.s0, nruns + gr.s0, N, &gr.up, /*try16=*/true,
-                              bad.p + 2 * g);
+        if (pinned) {  // every buffer first: the DMAs on the other stream must not wait behind this stream's kernels
+            rc = rle_alloc(ctx, gr.ns, dtype, values + gr.s0, lengths + gr.s0, nruns + gr.s0, N, &gr.up, &offs[(size_t)g]);
+            if (rc < 0) return fail(rc);
+        }
+    }
+    if (pinned) {
+        bool ok = cudaEventRecord(ctx->ev_main, ctx->stream) == cudaSuccess &&
+                  cudaStreamWaitEvent(ctx->aux, ctx->ev_main, 0) == cudaSuccess;
+        for (int g = 0; g < G && ok; ++g) {
+            Group& gr = *groups[(size_t)g];
+            cudaEvent_t e = nullptr;
+            ok = cudaEventCreateWithFlags(&e, cudaEventDisableTiming) == cudaSuccess;
+            if (!ok) break;
+            ev_dma.push_back(e);
+            ok = rle_transfer_pinned(gr.ns, dtype, values + gr.s0, lengths + gr.s0, nruns + gr.s0, offs[(size_t)g], &gr.up,
+                                     ctx->aux) >= 0 &&
+                 cudaEventRecord(e, ctx->aux) == cudaSuccess;
+        }
+        if (!ok) {
+            set_error("Rle upload from page-locked memory failed: %s", cudaGetErrorString(cudaGetLastError()));
+            return fail(DFB_ECUDA);
+        }
+    }
+    for (int g = 0; g < G; ++g) {
+        Group& gr = *groups[(size_t)g];
+        if (pinned) {
+            rc = cudaStreamWaitEvent(ctx->stream, ev_dma[(size_t)g], 0) == cudaSuccess ? DFB_OK : DFB_ECUDA;
+            if (rc >= 0) rc = rle_finish(ctx, gr.ns, N, offs[(size_t)g], &gr.up, bad.p + 2 * g);
+        } else {
+            rc = upload_rle_async(ctx, gr.ns, dtype, values + gr.s0, lengths + gr.s0, nruns + gr.s0, N, &gr.up, /*try16=*/true,
+                                  bad.p + 2 * g);
+        }
         if (rc < 0) return fail(rc);
         if (N == 0) continue;
         RleDev R;
@@ -1508,6 +1586,7 @@ int dfb_cov_from_rle(dfb_ctx* ctx, int n, int dtype, const void* const* values, 
     if (rc < 0) return fail(rc);
     std::vector<int64_t> hbad((size_t)2 * G, -1);
     rc = d2h(ctx, hbad.data(), bad.p, hbad.size() * sizeof(int64_t));  // synchronises: the groups' buffers die with this frame
+    drop_events();
     if (rc < 0) return fail(rc);
     for (int g = 0; g < G; ++g) {
         rc = check_rle_flags(hbad.data() + 2 * g, groups[(size_t)g]->s0, N);

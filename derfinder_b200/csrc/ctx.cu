@@ -169,6 +169,18 @@ static int ensure_staging(dfb_ctx* ctx) {
     return DFB_OK;
 }
 
+// The auxiliary stream (+ the two events that order it against the main one), created on first use.  Highest
+// priority: when the null scan's CTAs retire, the freed SM slots go to the observed-region chain first.
+int ensure_aux_stream(dfb_ctx* ctx) {
+    if (ctx->aux) return DFB_OK;
+    int prio_lo = 0, prio_hi = 0;
+    DFB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    DFB_CUDA(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prio_hi));
+    DFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
+    DFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
+    return DFB_OK;
+}
+
 // threads of the host copy pool (created on first use)
 int copy_threads(dfb_ctx* ctx) {
     if (ensure_staging(ctx) < 0 || !ctx->pool) return 1;
@@ -184,7 +196,9 @@ static int ensure_substage_events(dfb_ctx* ctx) {
     return DFB_OK;
 }
 
-static bool is_pinned_host(const void* p) {
+bool host_is_pinned(const void* p);
+static bool is_pinned_host(const void* p) { return host_is_pinned(p); }
+bool host_is_pinned(const void* p) {
     cudaPointerAttributes a;
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
         cudaGetLastError();
@@ -909,6 +923,7 @@ int dfb_set_option(dfb_ctx* c, const char* key, double value) {
     else if (!strcmp(key, "mask_cache")) c->opt_mask_cache = value != 0;
     else if (!strcmp(key, "filter_events")) c->opt_filter_events = value != 0;
     else if (!strcmp(key, "wire16")) c->opt_wire16 = value != 0;
+    else if (!strcmp(key, "pinned_direct")) c->opt_pinned_direct = value != 0;
     else if (!strcmp(key, "dbg")) c->opt_dbg = (int)value;
     else if (!strcmp(key, "tmem_stages")) c->opt_tmem_stages = (int)value;
     else if (!strcmp(key, "k2_waves")) c->opt_k2_waves = (int)value;

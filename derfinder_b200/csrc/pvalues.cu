@@ -1267,14 +1267,7 @@ int dfb_calculate_pvalues(dfb_ctx* ctx, dfb_cov* cov, const double* fstats, cons
     // The observed-region chain (threshold, segmentation, clusters: dozens of tiny launches and one host
     // synchronisation) runs on the auxiliary stream WHILE the permutation scan occupies the main one:
     // it is enqueued right after the first null-scan launch.
-    if (!ctx->aux) {
-        // highest priority: when the null scan's CTAs retire, the freed SM slots go to this chain first
-        int prio_lo = 0, prio_hi = 0;
-        DFB_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
-        DFB_CUDA(cudaStreamCreateWithPriority(&ctx->aux, cudaStreamNonBlocking, prio_hi));
-        DFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_main, cudaEventDisableTiming));
-        DFB_CUDA(cudaEventCreateWithFlags(&ctx->ev_aux, cudaEventDisableTiming));
-    }
+    DFB_TRY(ensure_aux_stream(ctx));
     DFB_CUDA(cudaEventRecord(ctx->ev_main, ctx->stream));  // F-statistics are complete past this point
     int rc_obs = DFB_OK;
     bool obs_done = false;

@@ -596,11 +596,11 @@ def test_filter_events_equals_expansion(dfb, flt, cutoff, n, length, mean_run):
 # 16-bit wire format of integer Rle columns (dfb_cov_from_rle): fits / value overflow / length overflow
 
 
-@pytest.mark.parametrize("case", ["fits", "value_overflow", "length_overflow", "negative", "off"])
+@pytest.mark.parametrize("case", ["fits", "value_overflow", "length_overflow", "negative", "off", "pinned", "pinned_ragged"])
 def test_rle_upload_wire16(dfb, case):
     from derfinder_b200.api import _upload_filtered
     rng = np.random.default_rng(2718)
-    n, runs = 5, 40000  # 200 000 runs in total: above the threshold of the 16-bit path
+    n, runs = 8, 135000  # 1.08 M runs in 8 columns: 16-bit wire format and four pipelined sample groups
     cols, dense = [], []
     for s in range(n):
         lens = rng.integers(1, 40, size=runs).astype(np.int64)
@@ -634,7 +634,33 @@ def test_rle_upload_wire16(dfb, case):
     try:
         if case == "off":
             e.set_option("wire16", 0)
-        cov = _upload_filtered(e, [(v, l.astype(np.int32)) for v, l in cols], position)
+        if case.startswith("pinned"):  # page-locked columns are DMAed where they lie (auxiliary stream, per sample group)
+            import ctypes as C2
+            import torch
+            from derfinder_b200 import _lib as L2
+            keep, vals, lens = [], [], []
+            for v, l in cols:
+                for a, dst in ((v.astype(np.int32), vals), (l.astype(np.int32), lens)):
+                    t = torch.empty(a.shape, dtype=torch.int32, pin_memory=True)
+                    t.numpy()[...] = a
+                    keep.append(t)
+                    dst.append(t.numpy())
+            if case == "pinned_ragged":
+                lens[2][10] += 3  # column 3 no longer sums to N: reported, nothing expanded from it
+            vp = (C2.c_void_p * n)(*[v.ctypes.data for v in vals])
+            lp = (C2.c_void_p * n)(*[l.ctypes.data for l in lens])
+            nr = np.asarray([len(v) for v in vals], dtype=np.int64)
+            pl = np.asarray([N], dtype=np.int32)
+            h = C2.c_void_p()
+            rc = e.lib.dfb_cov_from_rle(e.h, n, L2.DFB_I32, vp, lp, L2.ptr(nr, C2.c_int64), N, L2.ptr(pl, C2.c_int32), 1, 1,
+                                        C2.byref(h))
+            if case == "pinned_ragged":
+                assert rc < 0 and b"column 3" in e.lib.dfb_last_error()
+                return
+            assert rc == 0, e.lib.dfb_last_error()
+            cov = dfb.Coverage(e, h)
+        else:
+            cov = _upload_filtered(e, [(v, l.astype(np.int32)) for v, l in cols], position)
         for s in range(n):
             assert np.array_equal(cov.column(s), np.repeat(cols[s][0], cols[s][1])), (case, s)
     finally:
