@@ -285,6 +285,20 @@ regionMatrix <- function(fullCov, cutoff = 5, L, totalMapped = 80e6, targetSize 
     list(coverageMatrix = m)
 }
 
+## the same from RAW BigWig data sections (a reader that hands out the inflated leaf blocks instead of decoded
+## RleLists, e.g. a thin wrapper around the file's R-tree): the decode runs on the device (dfb_cov_from_bigwig).
+## sections: list of raw vectors, secOff: list of byte offsets (+ total), chromId: the files' ids of the chromosome;
+## regs must be sorted and disjoint (GenomicRanges::reduce()d chunks, as railMatrix() passes them)
+.railMatChrRegionBigWig <- function(sections, secOff, chromId, regs, mappedPerXM, L) {
+    st <- GenomicRanges::start(regs); en <- GenomicRanges::end(regs)
+    h <- .Call(dfbR_cov_from_bigwig, .engine(), sections, lapply(secOff, as.numeric), as.integer(chromId), st, en,
+               if (is.null(mappedPerXM)) NULL else as.numeric(mappedPerXM))
+    w <- en - st + 1L; off <- cumsum(c(0L, head(w, -1L)))                 # rows of region k: off[k] + 1 .. off[k] + w[k]
+    m <- .Call(dfbR_view_sums, .engine(), h, off + 1L, off + w, as.numeric(L))
+    colnames(m) <- names(sections)
+    list(coverageMatrix = m)
+}
+
 .calcPval <- function(areas, nullareas) .Call(dfbR_calc_pval, .engine(), as.numeric(areas), as.numeric(nullareas))
 .calculateFWER <- function(cutoffFstatUsed, areaNull, permutation, nPermute, areaReg)
     .Call(dfbR_calc_fwer, .engine(), cutoffFstatUsed, as.numeric(areaNull), as.integer(permutation),
@@ -395,8 +409,10 @@ mergeResults <- function(chrs = c(seq_len(22), "X", "Y"), prefix = ".", signific
     optionsStats <- derfinder:::.advanced_argument("optionsStats", NULL, ...)
     cutoffFstatUsed <- derfinder:::.advanced_argument("cutoffFstatUsed", optionsStats$cutoffFstatUsed, ...)
     chrResults <- derfinder:::.advanced_argument("chrResults", NULL, ...)
+    chrs <- derfinder::extendedMapSeqlevels(chrs, ...)                                                   # :140 (UCSC names)
+    if (!is.null(chrResults) && is.null(names(chrResults))) names(chrResults) <- chrs
     optionsMerge <- list(chrs = chrs, significantCut = significantCut, minoverlap = minoverlap, mergeCall = match.call(),
-        cutoffFstatUsed = cutoffFstatUsed, optionsStats = optionsStats)                                  # :139-147
+        cutoffFstatUsed = cutoffFstatUsed, ...)                                                          # :143-147
     save(optionsMerge, file = file.path(prefix, "optionsMerge.Rdata"))
     fullCoveragePrep <- fullTime <- fullNullPermutation <- fullNullWidths <- fullNullStats <- fullFstats <- fullAnno <-
         fullRegs <- structure(vector("list", length(chrs)), names = chrs)

@@ -346,6 +346,35 @@ SEXP dfbR_view_sums(SEXP ctx, SEXP cov, SEXP start, SEXP end, SEXP L) {
     return out;
 }
 
+/* railMatrix from raw BigWig data sections (R/railMatrix.R:271-289): `sections` = list of raw vectors (per sample: the
+ * inflated data sections of the leaf blocks that overlap the regions, back to back), `sec_off` = list of numeric
+ * vectors (byte offset of every section, plus the total as last entry), `chrom_id` = the id each file gives the
+ * chromosome.  Returns a coverage handle of sum(width(regions)) rows for dfbR_view_sums. */
+SEXP dfbR_cov_from_bigwig(SEXP ctx, SEXP sections, SEXP sec_off, SEXP chrom_id, SEXP start, SEXP end, SEXP mapped_per_xm) {
+    int n = Rf_length(sections);
+    if (Rf_length(sec_off) != n || Rf_length(chrom_id) != n) Rf_error("one entry per sample file is needed");
+    const void** sp = (const void**)R_alloc((size_t)(n > 0 ? n : 1), sizeof(void*));
+    const int64_t** op = (const int64_t**)R_alloc((size_t)(n > 0 ? n : 1), sizeof(void*));
+    int64_t* ns = (int64_t*)R_alloc((size_t)(n > 0 ? n : 1), sizeof(int64_t));
+    uint32_t* ids = (uint32_t*)R_alloc((size_t)(n > 0 ? n : 1), sizeof(uint32_t));
+    for (int s = 0; s < n; ++s) {
+        SEXP o = VECTOR_ELT(sec_off, s);
+        R_xlen_t k = XLENGTH(o);
+        if (k < 1) Rf_error("sec_off[[%d]] needs at least the total byte count", s + 1);
+        int64_t* oo = (int64_t*)R_alloc((size_t)k, sizeof(int64_t));
+        for (R_xlen_t i = 0; i < k; ++i) oo[i] = (int64_t)REAL(o)[i];
+        sp[s] = RAW(VECTOR_ELT(sections, s));
+        op[s] = oo;
+        ns[s] = (int64_t)k - 1;
+        ids[s] = (uint32_t)INTEGER(chrom_id)[s];
+    }
+    dfb_cov* cov = NULL;
+    CHECK(dfb_cov_from_bigwig((dfb_ctx*)unwrap(ctx, "railMatrix"), n, sp, op, ns, ids, (const int32_t*)INTEGER(start),
+                              (const int32_t*)INTEGER(end), XLENGTH(start), Rf_isNull(mapped_per_xm) ? NULL : REAL(mapped_per_xm),
+                              &cov));
+    return wrap(cov, "dfb_cov", cov_finalizer, ctx);
+}
+
 /* ---------------------------------------------------------------- mergeResults -------------- */
 
 /* regions / nulls: lists of external pointers (NULL entries: chromosome without observed regions) */
@@ -422,6 +451,7 @@ static const R_CallMethodDef call_methods[] = {
     {"dfbR_quantile", (DL_FUNC)&dfbR_quantile, 3},
     {"dfbR_region_matrix", (DL_FUNC)&dfbR_region_matrix, 5},
     {"dfbR_view_sums", (DL_FUNC)&dfbR_view_sums, 5},
+    {"dfbR_cov_from_bigwig", (DL_FUNC)&dfbR_cov_from_bigwig, 7},
     {NULL, NULL, 0}};
 
 void R_init_derfinderB200(DllInfo* dll) {

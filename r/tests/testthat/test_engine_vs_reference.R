@@ -98,3 +98,20 @@ test_that("regionMatrix (test_ER_level.R:5-70)", {
     b <- derfinder::regionMatrix(filt, maxRegionGap = 10L, maxClusterGap = 300L, L = 36, runFilter = FALSE, returnBP = FALSE, verbose = FALSE)
     expect_equal(a$chr21$coverageMatrix, b$chr21$coverageMatrix)
 })
+
+test_that("mergeResults (test_Fstats.R:94-145): same files, same fullRegions as the reference on the bundled chr21 results", {
+    for (d in c("merge-ref", "merge-b200")) {
+        dir.create(d, showWarnings = FALSE, recursive = TRUE)
+        file.copy(system.file(file.path("extdata", "chr21"), package = "derfinder", mustWork = TRUE), d, recursive = TRUE)
+    }
+    derfinder::mergeResults(chrs = "21", prefix = "merge-ref", genomicState = derfinder::genomicState$fullGenome, verbose = FALSE)
+    derfinderB200::mergeResults(chrs = "21", prefix = "merge-b200", genomicState = derfinder::genomicState$fullGenome, verbose = FALSE)
+    expect_equal(sort(dir("merge-b200")), sort(dir("merge-ref")))
+    e1 <- new.env(); e2 <- new.env()
+    load(file.path("merge-ref", "fullRegions.Rdata"), envir = e1); load(file.path("merge-b200", "fullRegions.Rdata"), envir = e2)
+    expect_equivalent(ranges(e2$fullRegions), ranges(e1$fullRegions))
+    for (k in c("area", "pvalues", "significant", "qvalues", "significantQval"))
+        expect_equal(mcols(e2$fullRegions)[[k]], mcols(e1$fullRegions)[[k]])
+    load(file.path("merge-ref", "fullNullSummary.Rdata"), envir = e1); load(file.path("merge-b200", "fullNullSummary.Rdata"), envir = e2)
+    expect_equal(as.data.frame(e2$fullNullSummary), as.data.frame(e1$fullNullSummary))
+})
