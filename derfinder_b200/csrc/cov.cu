@@ -607,50 +607,11 @@ __global__ void __launch_bounds__(256) validate_rle_kernel(const int32_t* __rest
     }
 }
 
-// Plain expansion of Rle columns into the dense sample-major matrix (no filter): one block per
-// (2048-position tile, sample); a thread finds the run of its first position by binary search in
-// the sample's prefix sums and walks 8 consecutive positions, written as two 16-byte stores.
-template <typename V>
-__global__ void __launch_bounds__(K1_THREADS) expand_rle_kernel(RleDev R, int64_t ld, V* __restrict__ out) {
-    const int s = blockIdx.y;
-    const V* __restrict__ values = reinterpret_cast<const V*>(R.values);
-    const int64_t* __restrict__ cum = R.cum;
-    const int64_t lo = R.run_off[s], hi = R.run_off[s + 1] - 1, cb = cum[lo];
-    for (int64_t tile = blockIdx.x; tile * K1_TILE < R.len; tile += gridDim.x) {
-        const int64_t p0 = tile * K1_TILE + (int64_t)threadIdx.x * K1_PER;
-        if (p0 >= R.len) continue;
-        int64_t r = find_run(cum, cb, lo, hi, p0);
-        int64_t rend = cum[r + 1] - cb;
-        V v = values[r];
-        V vals[K1_PER];
-#pragma unroll
-        for (int e = 0; e < K1_PER; ++e) {
-            const int64_t p = p0 + e;
-            if (p < R.len) {
-                while (rend <= p) {
-                    ++r;
-                    rend = cum[r + 1] - cb;
-                    v = values[r];
-                }
-            }
-            vals[e] = v;
-        }
-        V* dst = out + (size_t)s * ld + p0;
-        if (p0 + K1_PER <= R.len) {
-            constexpr int NV = (int)(sizeof(V) * K1_PER / 16);
-#pragma unroll
-            for (int q = 0; q < NV; ++q) reinterpret_cast<uint4*>(dst)[q] = reinterpret_cast<const uint4*>(vals)[q];
-        } else {
-            for (int e = 0; p0 + e < R.len; ++e) dst[e] = vals[e];
-        }
-    }
-}
-
 // Expansion by scatter + scan: the runs that overlap a (2048-position tile, sample) -- found through the
 // tile_runs_kernel table, so no thread searches -- drop their local index at their first position of the tile in
 // shared memory, an inclusive max-scan over the positions spreads it, and every thread writes its 8 positions
-// as 16-byte stores.  The per-thread binary search of expand_rle_kernel (2 x 19 dependent loads per 8 positions
-// at the chr1 shape) made that kernel latency-bound at 1.3 TB/s.
+// as 16-byte stores.  (Its predecessor searched the run of every thread's first position: 2 x 19 dependent loads
+// per 8 positions at the chr1 shape, latency-bound at 1.3 TB/s.)
 template <typename V, int THREADS>
 __global__ void __launch_bounds__(THREADS) expand_rle_tiles_kernel(RleDev R, int64_t tiles, const int64_t* __restrict__ tab,
                                                                    int64_t ld, V* __restrict__ out,
