@@ -3,8 +3,11 @@
 //
 // Reference: filterData (R/filterData.R:89-241) and preprocessCoverage (R/preprocessCoverage.R:
 // 97-260).  In R every step materialises Rle objects per sample; here the chromosome is cut into
-// tiles of 2048 positions, a tile whose samples are all constant (one run each -- ~90% of a
-// genome) is decided with one predicate, and only tiles with kept bases are expanded.
+// tiles of 2048 positions.  Integer coverage without a divisor is filtered in RUN space (the kept mask from
+// run events and a prefix sum, the compaction in rank space: filter_events_kernel / filter_compact_events_kernel);
+// doubles and real divisors go through the tile expansion kernel (a tile whose samples are all constant -- ~90% of a
+// genome -- is decided with one predicate, only tiles with kept bases are expanded).  preprocessCoverage of integer
+// coverage does not write the log2 matrix at all (dfb_cov::y_lazy).
 #include <math.h>
 
 #include <algorithm>

@@ -21,9 +21,9 @@
 //     Now a GROUP of permutation chunks stays resident in shared memory while the CTA walks all of its
 //     tiles; the scan makes ceil(chunks / group) passes over the (small) fp16 A matrix instead.
 //   * Three or four accumulator stages in TMEM (160 or 128 columns each) hide the MMA -> epilogue -> MMA
-//     hand-off; 16 epilogue warps (four per TMEM lane quarter) scan the accumulators with packed
-//     fma.rn.f32x2 on permutation pairs (the B rows are ordered so that neighbouring TMEM columns belong
-//     to neighbouring permutations) and take ONE vote per 8 permutations when nothing passes.
+//     hand-off; one group of four epilogue warps (one per TMEM lane quarter) per stage scans its accumulator
+//     with packed fma.rn.f32x2 on permutation pairs (the B rows are ordered so that neighbouring TMEM columns
+//     belong to neighbouring permutations) and takes ONE vote per 8 permutations when nothing passes.
 #include <cuda.h>
 #include <cudaTypedefs.h>
 #include <math.h>
@@ -230,10 +230,6 @@ static uint32_t umma_idesc_f16(int M, int N) {
 // then the producer warp (TMA A tiles, bulk copies of the B group) and mw MMA warps (one lane each; the
 // chunks alternate between them: one thread spends ~600 cycles per chunk on waits, fences, four MMA
 // issues and a commit, which is more than the tensor pipe needs to execute it).
-// accumulator stages = epilogue warp groups for `pe` screened columns at the default 32-permutation chunk
-// epilogue warp groups the kernel is compiled for: four for tiny models (the FP64 refinement of frequent
-// candidates dominates there), two otherwise (168 registers per thread: two TMEM register sets without spills)
-
 // Default chunk width: 32 permutations (a lane per permutation in the bookkeeping; at most 256 accumulator
 // columns for the model sizes the kernel is compiled for).  Measured on the chr1 shape (pe = 5, c3s workload,
 // gpurun_out/r2_*_sweep.txt): 32 permutations x 3 stages x 3 warp groups 2.14 ms; 24 permutations (128 columns)
