@@ -122,6 +122,7 @@ struct dfb_ctx {
     size_t k2_gflag_cap = 0;       // bytes
     bool k2_clean = false;         // both buffers are all zero
     int opt_mask_cache = 1;
+    int opt_cluster_one_block = 1;  // cluster chain of small region tables by one block in one launch
     int opt_pinned_direct = 1;   // Rle columns in page-locked caller memory are DMAed in place (dfb_cov_from_rle)
     int opt_poison = 0;          // DFB_POISON=1: fill every fresh device allocation with 0xff (uninitialised-read hunt)
     int opt_wire16 = 1;          // short-run integer Rle columns cross PCIe as 16-bit values / lengths (see upload_rle)

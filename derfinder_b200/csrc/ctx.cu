@@ -924,6 +924,7 @@ int dfb_set_option(dfb_ctx* c, const char* key, double value) {
     else if (!strcmp(key, "filter_events")) c->opt_filter_events = value != 0;
     else if (!strcmp(key, "wire16")) c->opt_wire16 = value != 0;
     else if (!strcmp(key, "pinned_direct")) c->opt_pinned_direct = value != 0;
+    else if (!strcmp(key, "cluster_one_block")) c->opt_cluster_one_block = value != 0;
     else if (!strcmp(key, "dbg")) c->opt_dbg = (int)value;
     else if (!strcmp(key, "tmem_stages")) c->opt_tmem_stages = (int)value;
     else if (!strcmp(key, "k2_waves")) c->opt_k2_waves = (int)value;

@@ -771,9 +771,103 @@ __global__ void cluster_len_kernel(const int32_t* __restrict__ cf, const int32_t
     else cl[r] = nan("");
 }
 
+// The whole cluster chain of one side -- the six element-wise kernels and five scans below -- by ONE block when the
+// region table is small (it nearly always is: tens of thousands of regions at most): same formulas, same scratch
+// arrays, one launch instead of eleven.  Block-wide exclusive scan of get(r), r < R, into out[]; returns the total.
+template <typename Get>
+__device__ __forceinline__ int64_t block_scan_excl(int64_t R, Get get, int64_t* __restrict__ out) {
+    constexpr int IT = 4;
+    __shared__ int64_t wsum_s[32];
+    __shared__ int64_t carry_s;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    __syncthreads();  // previous users of wsum_s / carry_s and of the arrays get() reads are done
+    if (tid == 0) carry_s = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < R; base += (int64_t)blockDim.x * IT) {
+        int64_t v[IT];
+        int64_t tsum = 0;
+#pragma unroll
+        for (int i = 0; i < IT; ++i) {
+            const int64_t r = base + (int64_t)tid * IT + i;
+            v[i] = r < R ? get(r) : 0;
+            tsum += v[i];
+        }
+        int64_t inc = tsum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int64_t t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        if (lane == 31) wsum_s[warp] = inc;
+        __syncthreads();
+        int64_t wprefix = 0;
+        for (int w = 0; w < warp; ++w) wprefix += wsum_s[w];
+        int64_t excl = carry_s + wprefix + inc - tsum;
+#pragma unroll
+        for (int i = 0; i < IT; ++i) {
+            const int64_t r = base + (int64_t)tid * IT + i;
+            if (r < R) out[r] = excl;
+            excl += v[i];
+        }
+        __syncthreads();
+        if (tid == (int)blockDim.x - 1) carry_s = excl;
+        __syncthreads();
+    }
+    return carry_s;
+}
+
+__global__ void __launch_bounds__(1024) cluster_one_block_kernel(const int32_t* __restrict__ gs, const int32_t* __restrict__ ge,
+                                                                 const int32_t* __restrict__ is, const int32_t* __restrict__ ie,
+                                                                 int64_t R, int32_t max_cluster_gap, int64_t* fexcl, int64_t* G,
+                                                                 int64_t* rc, int64_t* Phi, int64_t* CW, int64_t* gexcl,
+                                                                 int64_t* gfirst, int64_t* glast, int32_t* cf, double* cl) {
+    auto flag = [&](int64_t r) -> int64_t {
+        return (r == 0 || ((int64_t)gs[r] - (int64_t)ge[r - 1] - 1) > (int64_t)max_cluster_gap) ? 1 : 0;
+    };
+    auto gw = [&](int64_t r) -> int64_t { return (int64_t)(ge[r] - gs[r] + 1); };
+    auto iw = [&](int64_t r) -> int64_t { return (int64_t)(ie[r] - is[r] + 1); };
+    block_scan_excl(R, flag, fexcl);
+    const int64_t gtot = block_scan_excl(R, gw, G);  // covered bases
+    for (int64_t r = threadIdx.x; r < R; r += blockDim.x) rc[r] = fexcl[r] + flag(r);  // id of the merged covered range
+    block_scan_excl(R, [&](int64_t r) -> int64_t { return rc[r] * gw(r); }, Phi);
+    block_scan_excl(R, iw, CW);
+    __syncthreads();
+    for (int64_t r = threadIdx.x; r < R; r += blockDim.x) {  // clusterFinal (R/findRegions.R:259-265)
+        const int64_t t0 = CW[r], t1 = CW[r] + iw(r);
+        const int64_t sum = cluster_prefix(G, Phi, rc, R, gtot, t1) - cluster_prefix(G, Phi, rc, R, gtot, t0);
+        cf[r] = (int32_t)trunc((double)sum / (double)iw(r));
+    }
+    const int64_t ngroups =
+        block_scan_excl(R, [&](int64_t r) -> int64_t { return (r == 0 || cf[r] != cf[r - 1]) ? 1 : 0; }, gexcl);
+    for (int64_t r = threadIdx.x; r < R; r += blockDim.x) {  // first / last region of every run of equal clusterFinal
+        const bool first = r == 0 || cf[r] != cf[r - 1];
+        const int64_t grp = gexcl[r] + (first ? 1 : 0) - 1;
+        if (first) gfirst[grp] = r;
+        if (r == R - 1 || cf[r + 1] != cf[r]) glast[grp] = r;
+    }
+    __syncthreads();
+    for (int64_t r = threadIdx.x; r < R; r += blockDim.x) {  // clusterWidth[clusterFinal] (:266-271); NaN encodes NA
+        const int64_t c = cf[r];
+        if (c >= 1 && c <= ngroups) cl[r] = (double)((int64_t)ge[glast[c - 1]] - (int64_t)gs[gfirst[c - 1]] + 1);
+        else cl[r] = nan("");
+    }
+}
+
 static int cluster_side(dfb_ctx* ctx, const int32_t* gs, const int32_t* ge, const int32_t* is, const int32_t* ie,
                         int64_t R, int32_t max_cluster_gap, int32_t* cf, double* cl) {
     if (R == 0) return DFB_OK;
+    if (R <= 32768 && ctx->opt_cluster_one_block) {
+        DevBuf<int64_t> scratch;  // fexcl, G, rc, Phi, CW, gexcl, gfirst, glast
+        DFB_TRY(scratch.alloc(ctx, (size_t)8 * R));
+        int64_t* a = scratch.p;
+        {
+            KTimer t(ctx, DFB_K_REGIONS);
+            cluster_one_block_kernel<<<1, 1024, 0, ctx->stream>>>(gs, ge, is, ie, R, max_cluster_gap, a, a + R, a + 2 * R, a + 3 * R,
+                                                                  a + 4 * R, a + 5 * R, a + 6 * R, a + 7 * R, cf, cl);
+        }
+        DFB_CUDA(cudaGetLastError());
+        return DFB_OK;
+    }
     const unsigned grid = (unsigned)ceil_div(R, 256);
     DevBuf<uint32_t> flag, gw, iw, gflag;
     DevBuf<int64_t> fexcl, G, rc, prod, Phi, CW, gexcl, gfirst, glast, tot;

@@ -665,3 +665,37 @@ def test_rle_upload_wire16(dfb, case):
             assert np.array_equal(cov.column(s), np.repeat(cols[s][0], cols[s][1])), (case, s)
     finally:
         e.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# cluster chain by one block == the multi-kernel chain == the oracle (R/findRegions.R:254-271)
+
+
+@pytest.mark.parametrize("cgap,rgap,two_sided", [(300, 0, False), (50, 0, True), (3000, 5, False), (0, 0, True)])
+def test_cluster_chain_one_block(dfb, cgap, rgap, two_sided):
+    from test_gpu_parity import assert_regions_equal
+    rng = np.random.default_rng(31337 + cgap)
+    N = 120000
+    # kept bases in islands with gaps of many sizes: clusters of one and of dozens of regions
+    lens, vals = [], []
+    tot = 0
+    while tot < N:
+        on = int(rng.integers(20, 900))
+        on = min(on, N - tot)
+        vals += [False, True]
+        lens += [int(rng.choice([1, 7, 40, 250, 301, 2999, 3001, 20000])), on]
+        tot += on
+    position = (np.array(vals), np.array(lens))
+    F = rng.normal(size=N) * 2.0
+    F[rng.random(N) < 0.3] = np.round(F[rng.random(N) < 0.3][0], 1)  # some ties
+    cutoff = (-1.5, 1.5) if two_sided else 1.0
+    want = O.find_regions(position, F, cutoff, maxClusterGap=cgap, maxRegionGap=rgap)
+    for one in (1, 0):
+        e = dfb.Engine(0)
+        try:
+            e.set_option("cluster_one_block", one)
+            got = dfb.findRegions(position=position, fstats=F, chr="chrT", cutoff=cutoff, maxClusterGap=cgap,
+                                  maxRegionGap=rgap, engine=e)
+            assert_regions_equal(got, want)
+        finally:
+            e.close()
