@@ -435,16 +435,39 @@ def findRegions(position=None, fstats=None, chr=None, oneTable=True, maxClusterG
             warnings.warn("Ignoring 'smooth' = TRUE since 'basic' = TRUE")
         else:
             raise NotImplementedError("smooth = TRUE is not supported by the B200 engine (bumphunter smoothers)")
-    if segmentIR is not None:
-        raise NotImplementedError("pass 'position' and 'maxRegionGap'; precomputed segmentIR is an R-side cache")
-    if position is None:
-        raise ValueError("!is.null(position) is not TRUE")
+    if not basic and segmentIR is None and position is None:
+        raise ValueError("!is.null(position) is not TRUE")  # R/findRegions.R:141-144
     engine = engine or default_engine()
-    pl, pf = _position_runs(position)
-    if not np.any(np.asarray(position[0]).astype(bool)):
-        warnings.warn("Found no regions")
-        return None
     x = L.f64(fstats)
+    if segmentIR is None or position is not None:
+        if position is None:
+            raise ValueError("!is.null(position) is not TRUE")
+        if segmentIR is not None:
+            # segmentIR is the cache of .clusterMakerRle(position, maxRegionGap, ranges = TRUE)
+            # (R/calculatePvalues.R:234-237): the engine derives the same segments from `position`
+            st, en = (np.asarray(a, dtype=np.int64) for a in segmentIR)
+            kept = int(np.asarray(position[1])[np.asarray(position[0]).astype(bool)].sum())
+            if int((en - st + 1).sum()) != kept:
+                raise ValueError("sum(width(segmentIR)) == sum(position) is not TRUE")
+        pl, pf = _position_runs(position)
+        if not np.any(np.asarray(position[0]).astype(bool)):
+            warnings.warn("Found no regions")
+            return None
+    else:
+        # basic = TRUE with the segments only (index space, R/findRegions.R:155-170): a position index whose TRUE
+        # runs ARE the segments, one filtered-out base between neighbours
+        if not basic:
+            raise ValueError("!is.null(position) is not TRUE")
+        st, en = (np.asarray(a, dtype=np.int64) for a in segmentIR)
+        w = en - st + 1
+        if len(w) == 0 or int(w.sum()) != len(x) or st[0] != 1 or np.any(st[1:] != en[:-1] + 1):
+            raise ValueError("segmentIR must tile 1..length(fstats)")
+        runs = np.empty(2 * len(w) - 1, dtype=np.int64)
+        runs[0::2] = w
+        runs[1::2] = 1
+        vals = np.arange(len(runs)) % 2 == 0
+        pl, pf = _position_runs((vals, runs))
+        maxRegionGap = 0
     if cutoff is None:  # quantile(fstats, 0.99, na.rm = TRUE) (:118)
         q = C.c_double()
         L.check(engine.lib.dfb_quantile(engine.h, None, L.ptr(x, C.c_double), len(x), 0.99, C.byref(q)))

@@ -699,3 +699,25 @@ def test_cluster_chain_one_block(dfb, cgap, rgap, two_sided):
             assert_regions_equal(got, want)
         finally:
             e.close()
+
+
+def test_find_regions_segment_ir(dfb, eng):
+    """findRegions(position = NULL, segmentIR = ..., basic = TRUE) (R/findRegions.R:155-170) and segmentIR given
+    next to position (the cache calculatePvalues passes, R/calculatePvalues.R:234-244)."""
+    rng = np.random.default_rng(515)
+    N = 30000
+    F = rng.normal(size=N) * 2.0
+    position = (np.array([False, True, False, True, False, True]), np.array([100, 12000, 7, 8000, 400, 10000]))
+    seg = O.cluster_maker_rle(position, maxGap=0, ranges=True)
+    want = O.find_regions(None, F, 1.2, segmentIR=seg, basic=True)
+    got = dfb.findRegions(position=None, fstats=F, cutoff=1.2, segmentIR=seg, basic=True, engine=eng)
+    for k in ("area", "width", "stat"):
+        assert np.array_equal(got[k], want[k]), k
+    full = dfb.findRegions(position=position, fstats=F, chr="chrT", cutoff=1.2, segmentIR=seg, engine=eng)
+    ofull = O.find_regions(position, F, 1.2, segmentIR=seg)
+    from test_gpu_parity import assert_regions_equal
+    assert_regions_equal(full, ofull)
+    with pytest.raises(ValueError):
+        dfb.findRegions(position=None, fstats=F, cutoff=1.2, segmentIR=seg, engine=eng)  # not basic: position needed
+    with pytest.raises(ValueError):
+        dfb.findRegions(position=position, fstats=F, cutoff=1.2, segmentIR=(seg[0][:-1], seg[1][:-1]), engine=eng)
