@@ -239,3 +239,59 @@ def test_merge_results_brute_force():
     oz = sorted(range(len(z)), key=lambda i: (-z[i], i))
     assert np.array_equal(fn["area"], z[oz]) and np.array_equal(fn["permutation"], zp[oz])
     assert list(fn["chr"]) == list(np.array(["chr1"] * 14 + ["chr3"] * 8)[oz])
+
+
+def test_max_region_gap_vs_region_finder(golden):
+    """tests/testthat/test-maxRegionGap.R:14-79: regions of the golden F-statistics turned into a coverage track,
+    filterData(cutoff = 0), then findRegions(..., cutoff = 0, maxRegionGap = 0 / 50) must equal
+    bumphunter::regionFinder(x, pos, cutoff = 0, maxGap = 1 / 50) in start, end, value, area, indexStart, indexEnd.
+    regionFinder is restated here independently of the oracle: clusters of positions whose neighbours are at most
+    maxGap apart, inside them maximal runs of x > cutoff; value = mean, area = |sum|."""
+    from oracle import derfinder_oracle as O
+    prep = O.preprocess_coverage(golden.cov, golden.position, scalefac=32, chunksize=1e3)
+    regs = O.find_regions(prep["position"], golden.fstats, O.quantile_type7(golden.fstats, 0.99))
+    # GenomicRanges::coverage(gr): 1 on every base covered by a region (the regions are disjoint)
+    L = 48129895
+    starts, ends = np.asarray(regs["start"]), np.asarray(regs["end"])
+    o = np.argsort(starts)
+    vals, lens, cur = [], [], 0
+    for s, e in zip(starts[o], ends[o]):
+        if s - 1 > cur:
+            vals.append(0)
+            lens.append(s - 1 - cur)
+        vals.append(1)
+        lens.append(e - s + 1)
+        cur = e
+    vals.append(0)
+    lens.append(L - cur)
+    filt = O.filter_data([(np.asarray(vals, dtype=np.int32), np.asarray(lens, dtype=np.int64))], cutoff=0, returnMean=True)
+    x = np.asarray(filt.meanCoverage, dtype=np.float64)
+    pos = np.flatnonzero(np.repeat(np.asarray(filt.position[0]).astype(bool), filt.position[1])) + 1  # which(position)
+    assert len(pos) == len(x)
+
+    def region_finder(x, pos, cutoff, maxGap):
+        out = []
+        brk = np.flatnonzero(np.diff(pos) > maxGap) + 1  # cluster breaks
+        bounds = np.concatenate(([0], brk, [len(pos)]))
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            above = x[a:b] > cutoff
+            i = a
+            while i < b:
+                if above[i - a]:
+                    j = i
+                    while j + 1 < b and above[j + 1 - a]:
+                        j += 1
+                    seg = x[i:j + 1]
+                    out.append((pos[i], pos[j], seg.mean(), abs(seg.sum()), i + 1, j + 1))
+                    i = j + 1
+                else:
+                    i += 1
+        return sorted(out)
+
+    for gap, bump_gap in ((0, 1), (50, 50)):
+        got = O.find_regions(filt.position, x, 0, maxRegionGap=gap)
+        want = region_finder(x, pos, 0, bump_gap)
+        assert len(want) == len(got["start"]) > 0
+        for k, col in enumerate(("start", "end", "value", "area", "indexStart", "indexEnd")):
+            assert np.array_equal(np.asarray(got[col], dtype=np.float64), np.asarray([w[k] for w in want], dtype=np.float64)), (gap, col)
+        assert set(got["name"]) == {"up"}
